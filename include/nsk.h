@@ -1,0 +1,207 @@
+/*
+ * nsk.h -- C ABI of the B200-native SpMV / matrix-powers / Krylov kernels.
+ *
+ * This is the drop-in boundary for the hot path of aantoine890/navierstokes (tree mpk/): the
+ * entry points below are what a foreign-function binding (ctypes, cgo, JNI, a PETSc
+ * MATOP_MULT callback, or the C++ shims in include/nsk_spmv_compat.hpp) binds instead of the
+ * reference's CPU kernels.  Plain C types only: opaque handles, raw pointers, sizes, int status.
+ *
+ *   reference interface (file:line under /root/reference)        replaced by
+ *   -----------------------------------------------------------  --------------------------------
+ *   struct csrmatrix {n,nnz,ptrow,indcol,coef}  mpk/SpMV.h:18-24  nsk_csr_create / nsk_csr_destroy
+ *   SpMV_CSR, _OPT, _FMA, _AVX2                 mpk/SpMV.h:55-58  nsk_spmv (mode selects arithmetic)
+ *   SpM2V_CSR*, SpM2V (k=2)     mpk/SpM2V.cpp:80,137,195,279      nsk_mpk  (k = 2)
+ *   SpM3V, SpM4V (k=3,4)        mpk/SpMVmulti0.cpp:132,191        nsk_mpk  (k = 3, 4; any k <= NSK_MAX_K)
+ *   Generate{1st,2nd,3rd}layer  mpk/SpM2V.cpp:5, SpMVmulti0:106,157  plan built inside nsk_csr_create
+ *   struct bcsr4x4_matrix, SpMV_BCSR*           mpk/SpMV.h:26-33,61-64  nsk_bcsr4_create / nsk_spmv_bcsr4
+ *   norm2, rel_error                            mpk/utils.cpp:131-143  nsk_norm2 / nsk_rel_error
+ *   orthogonalize (dot + axpy)                  mpk/2SpMV.cpp:3-11     nsk_orthogonalize, nsk_dot, nsk_axpy
+ *   flush_cache                                 mpk/utils.cpp:146-154  nsk_flush_l2
+ *   (no CG in the reference; north star asks for it)             nsk_cg
+ *
+ * Conventions
+ *   - One nsk_ctx per process and per GPU (one process per GPU; ranks are joined by nsk_comm_init).
+ *   - Every function returns NSK_OK (0) or a negative nsk_status; nsk_last_error() gives detail.
+ *     The reference's kernels are `void` and never fail; the C++ shims abort loudly on an error
+ *     because there is NO CPU fallback.
+ *   - `where` says whether vector pointers are host or device memory.  With NSK_HOST the call
+ *     copies inputs to the GPU, runs, copies results back and returns after they have landed (the
+ *     reference's synchronous contract).  With NSK_DEVICE the call only enqueues work on the
+ *     context's stream; use nsk_ctx_sync() or your own stream/event to wait.
+ *   - Matrix arrays passed to *_create are host pointers (like the reference's std::vector data);
+ *     they are copied to HBM once and never referenced afterwards.
+ *   - Outputs are fully overwritten (the reference zeroes then accumulates, mpk/SpMV.cpp:13);
+ *     inputs are never written.
+ */
+#ifndef NSK_H
+#define NSK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NSK_VERSION 100          /* 0.1.0 */
+#define NSK_MAX_K 16             /* largest matrix-powers depth per call */
+#define NSK_UNIQUE_ID_BYTES 128  /* == sizeof(ncclUniqueId) */
+
+typedef enum {
+    NSK_OK = 0,
+    NSK_ERR_INVALID = -1,      /* bad argument (null pointer, negative size, unsorted ptrow ...) */
+    NSK_ERR_CUDA = -2,         /* a CUDA runtime call or kernel failed */
+    NSK_ERR_NO_DEVICE = -3,    /* no usable sm_100 device: there is no CPU fallback */
+    NSK_ERR_ALLOC = -4,        /* host or device allocation failed */
+    NSK_ERR_COMM = -5,         /* NCCL missing or a collective failed */
+    NSK_ERR_UNSUPPORTED = -6,  /* valid request that this build does not implement */
+    NSK_ERR_NOT_CONVERGED = -7 /* nsk_cg hit maxit (x still holds the last iterate) */
+} nsk_status;
+
+/* Arithmetic of one row of y = A x.
+ * NSK_EXACT_FMA    y_i = fma(a_ip, x_p, ...fma(a_i1, x_1, fma(a_i0, x_0, +0.0))) in CSR storage
+ *                  order -- bit-identical to SpMV_CSR_FMA / SpMV_CSR_OPT (mpk/SpMV.cpp:23-56).
+ * NSK_EXACT_MULADD same order, product and sum rounded separately -- bit-identical to the code
+ *                  g++ emits for the inner reduction of SpM2V_CSR_OPT on the development host and
+ *                  to SSE2 evaluation of SpMV_CSR (mpk/SpMV.cpp:6-20).
+ * NSK_FAST         any association (sub-warp partial sums + shuffle tree); within 1e-12 relative
+ *                  (reference metric rel_error, mpk/utils.cpp:138-143) of NSK_EXACT_FMA. */
+typedef enum { NSK_EXACT_FMA = 0, NSK_EXACT_MULADD = 1, NSK_FAST = 2 } nsk_mode;
+
+typedef enum { NSK_HOST = 0, NSK_DEVICE = 1 } nsk_where;
+
+typedef struct nsk_ctx_s *nsk_ctx_t;
+typedef struct nsk_csr_s *nsk_csr_t;
+typedef struct nsk_bcsr4_s *nsk_bcsr4_t;
+
+/* ---- library / context ---------------------------------------------------------------------- */
+int nsk_version(void);
+const char *nsk_strerror(int status);
+/* Text of the last failure on this context (or the last context-less failure when ctx == NULL). */
+const char *nsk_last_error(nsk_ctx_t ctx);
+
+/* Binds the calling process to CUDA device `device` and creates the work stream.
+ * Fails with NSK_ERR_NO_DEVICE when there is no GPU or it is not compute capability 10.x. */
+int nsk_ctx_create(int device, nsk_ctx_t *ctx);
+int nsk_ctx_destroy(nsk_ctx_t ctx);
+/* Use an existing cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); NULL restores ours. */
+int nsk_ctx_set_stream(nsk_ctx_t ctx, void *cuda_stream);
+void *nsk_ctx_get_stream(nsk_ctx_t ctx);
+int nsk_ctx_sync(nsk_ctx_t ctx);
+/* Number of kernels this library has launched on this context since creation. */
+uint64_t nsk_ctx_launch_count(nsk_ctx_t ctx);
+/* Device facts: sm_count, l2_bytes, smem_per_block_optin, total HBM bytes. */
+int nsk_ctx_device_info(nsk_ctx_t ctx, int *sm_count, int64_t *l2_bytes, int *smem_optin,
+                        int64_t *hbm_bytes);
+/* Tuning knobs (name -> integer).  Unknown names give NSK_ERR_INVALID.  See DESIGN.md. */
+int nsk_ctx_set_option(nsk_ctx_t ctx, const char *name, int64_t value);
+
+/* CUDA-event timing on the context's stream (what bench.py brackets its timed regions with). */
+int nsk_event_create(nsk_ctx_t ctx, void **event);
+int nsk_event_destroy(nsk_ctx_t ctx, void *event);
+int nsk_event_record(nsk_ctx_t ctx, void *event);
+/* Waits for `stop`, then returns milliseconds between the two events. */
+int nsk_event_elapsed_ms(nsk_ctx_t ctx, void *start, void *stop, float *ms);
+
+/* ---- memory --------------------------------------------------------------------------------- */
+int nsk_malloc(nsk_ctx_t ctx, size_t bytes, void **dptr);
+int nsk_free(nsk_ctx_t ctx, void *dptr);
+int nsk_host_alloc(nsk_ctx_t ctx, size_t bytes, void **hptr); /* pinned */
+int nsk_host_free(nsk_ctx_t ctx, void *hptr);
+/* kind: 0 = host->device, 1 = device->host, 2 = device->device; asynchronous on the ctx stream. */
+int nsk_memcpy(nsk_ctx_t ctx, void *dst, const void *src, size_t bytes, int kind);
+int nsk_memset0(nsk_ctx_t ctx, void *dptr, size_t bytes);
+/* GPU analogue of flush_cache (mpk/utils.cpp:146-154): overwrites a scratch buffer larger than L2. */
+int nsk_flush_l2(nsk_ctx_t ctx);
+
+/* ---- CSR operator --------------------------------------------------------------------------- */
+/* Uploads a square CSR operator (0-based, int32 indices, fp64 values; columns need not be sorted --
+ * the row-sequential modes accumulate in storage order whatever it is) and builds the launch plan.
+ * n rows, n_cols columns (n_cols >= n; n_cols > n is used for row slabs whose columns include
+ * ghost entries).  nnz must equal ptrow[n] and be < 2^31 (the reference's `int nnz`). */
+int nsk_csr_create(nsk_ctx_t ctx, int n, int n_cols, int64_t nnz, const int *ptrow,
+                   const int *indcol, const double *coef, nsk_csr_t *A);
+int nsk_csr_destroy(nsk_csr_t A);
+int nsk_csr_shape(nsk_csr_t A, int *n, int *n_cols, int64_t *nnz);
+/* Algorithmic bytes of one product / of a depth-k powers call (SURVEY.md 8d definitions). */
+int64_t nsk_csr_spmv_bytes(nsk_csr_t A);
+int64_t nsk_csr_mpk_bytes(nsk_csr_t A, int k);
+
+/* y = A x.   x: n_cols doubles, y: n doubles. */
+int nsk_spmv(nsk_csr_t A, const double *x, double *y, nsk_mode mode, nsk_where where);
+
+/* levels[l] = A^(l+1) x for l = 0 .. k-1 (the reference's y, z, w, v of SpM2V/SpM3V/SpM4V).
+ * Every level is an output of n doubles; x has n doubles (square operator).
+ * In the exact modes each level is bit-identical to k successive nsk_spmv calls. */
+int nsk_mpk(nsk_csr_t A, int k, const double *x, double *const *levels, nsk_mode mode,
+            nsk_where where);
+
+/* ---- 4x4 block CSR (the reference's bcsr4x4_matrix, row-major blocks) ------------------------ */
+int nsk_bcsr4_create(nsk_ctx_t ctx, int nbrows, int64_t nblocks, const int *ptrow,
+                     const int *indcol, const double *coef, nsk_bcsr4_t *B);
+int nsk_bcsr4_destroy(nsk_bcsr4_t B);
+/* y = B x, both 4*nbrows doubles.  Exact modes follow SpMV_BCSR_FMA's (block, j) order. */
+int nsk_spmv_bcsr4(nsk_bcsr4_t B, const double *x, double *y, nsk_mode mode, nsk_where where);
+
+/* ---- vectors (device-side dot / axpy family used by the Krylov solvers) ---------------------- */
+/* result pointers are HOST doubles; the call returns after the value has landed. */
+int nsk_dot(nsk_ctx_t ctx, int64_t n, const double *a, const double *b, double *result,
+            nsk_where where);
+int nsk_norm2(nsk_ctx_t ctx, int64_t n, const double *x, double *result, nsk_where where);
+/* ||ref - test||_2 / ||ref||_2  (mpk/utils.cpp:138-143) */
+int nsk_rel_error(nsk_ctx_t ctx, int64_t n, const double *ref, const double *test, double *result,
+                  nsk_where where);
+/* y += a x */
+int nsk_axpy(nsk_ctx_t ctx, int64_t n, double a, const double *x, double *y, nsk_where where);
+/* beta = <x,y>; y -= alpha*beta*x  (mpk/2SpMV.cpp:3-11); *beta may be NULL */
+int nsk_orthogonalize(nsk_ctx_t ctx, int64_t n, const double *x, double *y, double alpha,
+                      double *beta, nsk_where where);
+/* G[i*m+j] = <V_i, V_j> for m vectors of length n (s-step Gram block); G is m*m HOST doubles. */
+int nsk_gram(nsk_ctx_t ctx, int64_t n, int m, const double *const *V, double *G, nsk_where where);
+
+/* ---- conjugate gradients --------------------------------------------------------------------- */
+/* Solves A x = b (A symmetric positive definite), x0 = 0, stops when ||r||_2/||b||_2 <= tol.
+ * sstep <= 1: classical CG (3 fused kernels per iteration, scalars stay on the device).
+ * sstep  > 1: s-step (communication-avoiding) CG: one matrix-powers call + one Gram reduction per
+ *             s iterations.  iters counts CG iterations (s per outer step).
+ * With a communicator attached (nsk_comm_init) A is this rank's row slab created by
+ * nsk_csr_create_dist and b, x are the owned parts; dots are all-reduced over NCCL. */
+int nsk_cg(nsk_csr_t A, const double *b, double *x, double tol, int maxit, int sstep,
+           int *iters, double *relres, nsk_where where);
+
+/* ---- multi-GPU (one process per GPU, NCCL over NVLink) --------------------------------------- */
+/* Rank 0 calls nsk_comm_unique_id and ships the 128 bytes to the other ranks by any means
+ * (torch.distributed broadcast, MPI, a file); then every rank calls nsk_comm_init. */
+int nsk_comm_unique_id(void *id128);
+int nsk_comm_init(nsk_ctx_t ctx, int nranks, int rank, const void *id128);
+int nsk_comm_destroy(nsk_ctx_t ctx);
+int nsk_comm_allreduce_sum(nsk_ctx_t ctx, double *dbuf, int count); /* in place, device buffer */
+
+/* Distributed operator: this rank owns global rows [row_begin, row_end).
+ * The caller supplies the rows of the depth-(halo_depth-1) closure of the owned block in LOCAL
+ * numbering [owned | ring 1 | ring 2 | ...] as produced by nsk_plan_* (host-only helpers below),
+ * plus, per neighbour rank, which local entries to send and where received entries land.
+ *   n_rows_local : rows stored (owned + ghost rows that must be recomputed redundantly)
+ *   n_cols_local : length of a local vector (owned + all ghosts up to depth halo_depth)
+ *   level_rows[l]: number of leading local rows on which power l+1 is evaluated
+ *                  (level_rows[halo_depth-1] == n_owned), l = 0 .. halo_depth-1
+ * send_idx/recv_idx are local indices, grouped by peer with CSR-style offsets. */
+int nsk_csr_create_dist(nsk_ctx_t ctx, int n_owned, int n_rows_local, int n_cols_local,
+                        int64_t nnz, const int *ptrow, const int *indcol, const double *coef,
+                        int halo_depth, const int *level_rows, int n_peers, const int *peer_rank,
+                        const int *send_off, const int *send_idx, const int *recv_off,
+                        const int *recv_idx, nsk_csr_t *A);
+/* Exchanges ghosts of a local vector (length n_cols_local, device) up to `depth` rings. */
+int nsk_halo_exchange(nsk_csr_t A, double *xlocal, int depth);
+
+/* Host-only planning helper (no GPU needed; used by the Python/C++ host layers and CPU tests).
+ * Given the rows of a set of global row ids (CSR with global columns), returns the sorted unique
+ * column ids that are not in [own_begin, own_end) nor in `known` (sorted).  Two-call protocol:
+ * out == NULL returns the count. */
+int64_t nsk_plan_new_columns(int nrows, const int *ptrow, const int *indcol_global, int own_begin,
+                             int own_end, const int *known_sorted, int64_t n_known, int *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NSK_H */

@@ -1,0 +1,181 @@
+// csr.cu -- CSR operator object and the public SpMV / matrix-powers entry points of nsk.h.
+//
+// nsk_csr_create   <- struct csrmatrix                      (reference mpk/SpMV.h:18-24)
+// nsk_spmv         <- SpMV_CSR / _OPT / _FMA / _AVX2        (reference mpk/SpMV.cpp:6-85)
+// nsk_mpk          <- SpM2V_CSR* / SpM3V / SpM4V            (reference mpk/SpM2V.cpp:80-332,
+//                                                            mpk/SpMVmulti0.cpp:132-221)
+#include <map>
+#include <mutex>
+
+#include "nsk_internal.h"
+
+// host copy of ptrow per operator (needed to (re)build tilings for other tile geometries)
+static std::map<nsk_csr_t, std::vector<int>> g_host_ptrow;
+static std::mutex g_host_ptrow_mu;
+
+std::vector<int> &nsk_csr_host_ptrow(nsk_csr_t A)
+{
+    std::lock_guard<std::mutex> lk(g_host_ptrow_mu);
+    return g_host_ptrow[A];
+}
+
+int nsk_mpk_device(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode);  // mpk.cu
+
+NSK_API int nsk_csr_create(nsk_ctx_t ctx, int n, int n_cols, int64_t nnz, const int *ptrow,
+                           const int *indcol, const double *coef, nsk_csr_t *out)
+{
+    if (!ctx || !out) return NSK_ERR_INVALID;
+    *out = nullptr;
+    NSK_REQUIRE(ctx, n >= 0 && n_cols >= 0 && nnz >= 0, "negative size");
+    NSK_REQUIRE(ctx, nnz < (int64_t)2147483647, "nnz must fit the reference's int (mpk/SpMV.h:20)");
+    NSK_REQUIRE(ctx, ptrow != nullptr, "ptrow is null");
+    NSK_REQUIRE(ctx, nnz == 0 || (indcol && coef), "indcol/coef null");
+    NSK_REQUIRE(ctx, ptrow[0] == 0, "ptrow[0] must be 0");
+    NSK_REQUIRE(ctx, (int64_t)ptrow[n] == nnz, "ptrow[n] must equal nnz");
+    int max_row = 0;
+    for (int i = 0; i < n; i++) {
+        int len = ptrow[i + 1] - ptrow[i];
+        if (len < 0) {
+            nsk_set_error(ctx, "ptrow decreases at row %d", i);
+            return NSK_ERR_INVALID;
+        }
+        if (len > max_row) max_row = len;
+    }
+    for (int64_t e = 0; e < nnz; e++) {
+        if (indcol[e] < 0 || indcol[e] >= n_cols) {
+            nsk_set_error(ctx, "column index %d out of range [0,%d) at entry %lld", indcol[e], n_cols, (long long)e);
+            return NSK_ERR_INVALID;
+        }
+    }
+    NSK_CUDA(ctx, cudaSetDevice(ctx->device));
+    nsk_csr_s *A = new nsk_csr_s();
+    A->ctx = ctx;
+    A->n = n;
+    A->n_cols = n_cols;
+    A->nnz = nnz;
+    A->max_row = max_row;
+    A->mean_row = n ? (double)nnz / (double)n : 0.0;
+    // +64 B: the bulk copies round slices up to 16-byte granules and may read past the end
+    const size_t pad = 64;
+    cudaError_t e1 = cudaMalloc(&A->d_ptrow, sizeof(int) * ((size_t)n + 1) + pad);
+    cudaError_t e2 = cudaMalloc(&A->d_indcol, sizeof(int) * (size_t)nnz + pad);
+    cudaError_t e3 = cudaMalloc(&A->d_coef, sizeof(double) * (size_t)nnz + pad);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
+        nsk_set_error(ctx, "cudaMalloc of the operator (%lld nnz) failed", (long long)nnz);
+        nsk_csr_destroy(A);
+        return NSK_ERR_ALLOC;
+    }
+    NSK_CUDA(ctx, cudaMemset((char *)A->d_ptrow + sizeof(int) * ((size_t)n + 1), 0, pad));
+    NSK_CUDA(ctx, cudaMemset((char *)A->d_indcol + sizeof(int) * (size_t)nnz, 0, pad));
+    NSK_CUDA(ctx, cudaMemset((char *)A->d_coef + sizeof(double) * (size_t)nnz, 0, pad));
+    NSK_CUDA(ctx, cudaMemcpy(A->d_ptrow, ptrow, sizeof(int) * ((size_t)n + 1), cudaMemcpyHostToDevice));
+    if (nnz) {
+        NSK_CUDA(ctx, cudaMemcpy(A->d_indcol, indcol, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice));
+        NSK_CUDA(ctx, cudaMemcpy(A->d_coef, coef, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice));
+    }
+    nsk_csr_host_ptrow(A).assign(ptrow, ptrow + n + 1);
+    int s = nsk_build_tiling(A, ptrow);
+    if (s != NSK_OK) {
+        nsk_csr_destroy(A);
+        return s;
+    }
+    *out = A;
+    return NSK_OK;
+}
+
+void nsk_dist_free(nsk_csr_t A);  // dist.cu
+
+NSK_API int nsk_csr_destroy(nsk_csr_t A)
+{
+    if (!A) return NSK_OK;
+    nsk_ctx_t ctx = A->ctx;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    nsk_dist_free(A);
+    if (A->d_ptrow) cudaFree(A->d_ptrow);
+    if (A->d_indcol) cudaFree(A->d_indcol);
+    if (A->d_coef) cudaFree(A->d_coef);
+    if (A->tiling.d_tiles) cudaFree(A->tiling.d_tiles);
+    if (A->d_flags) cudaFree(A->d_flags);
+    {
+        std::lock_guard<std::mutex> lk(g_host_ptrow_mu);
+        g_host_ptrow.erase(A);
+    }
+    delete A;
+    return NSK_OK;
+}
+
+NSK_API int nsk_csr_shape(nsk_csr_t A, int *n, int *n_cols, int64_t *nnz)
+{
+    if (!A) return NSK_ERR_INVALID;
+    if (n) *n = A->n;
+    if (n_cols) *n_cols = A->n_cols;
+    if (nnz) *nnz = A->nnz;
+    return NSK_OK;
+}
+
+NSK_API int64_t nsk_csr_spmv_bytes(nsk_csr_t A)
+{
+    if (!A) return 0;
+    return 12 * A->nnz + 4 * ((int64_t)A->n + 1) + 16 * (int64_t)A->n;
+}
+
+NSK_API int64_t nsk_csr_mpk_bytes(nsk_csr_t A, int k)
+{
+    if (!A) return 0;
+    return 12 * A->nnz + 4 * ((int64_t)A->n + 1) + 8 * (int64_t)A->n + 8 * (int64_t)A->n * k;
+}
+
+NSK_API int nsk_spmv(nsk_csr_t A, const double *x, double *y, nsk_mode mode, nsk_where where)
+{
+    if (!A) return NSK_ERR_INVALID;
+    nsk_ctx_t ctx = A->ctx;
+    NSK_REQUIRE(ctx, x && y, "x or y is null");
+    NSK_REQUIRE(ctx, mode == NSK_EXACT_FMA || mode == NSK_EXACT_MULADD || mode == NSK_FAST, "bad mode");
+    NSK_CUDA(ctx, cudaSetDevice(ctx->device));
+    nsk_spmv_args a;
+    a.row_begin = 0;
+    a.row_end = A->n;
+    a.mode = mode;
+    if (where == NSK_DEVICE) {
+        a.x = x;
+        a.y = y;
+        return nsk_launch_spmv(A, a);
+    }
+    void *dx, *dy;
+    NSK_TRY(nsk_stage(ctx, 0, sizeof(double) * (size_t)A->n_cols, &dx));
+    NSK_TRY(nsk_stage(ctx, 1, sizeof(double) * (size_t)A->n, &dy));
+    NSK_CUDA(ctx, cudaMemcpyAsync(dx, x, sizeof(double) * (size_t)A->n_cols, cudaMemcpyHostToDevice, ctx->stream));
+    a.x = (const double *)dx;
+    a.y = (double *)dy;
+    NSK_TRY(nsk_launch_spmv(A, a));
+    NSK_CUDA(ctx, cudaMemcpyAsync(y, dy, sizeof(double) * (size_t)A->n, cudaMemcpyDeviceToHost, ctx->stream));
+    NSK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NSK_OK;
+}
+
+NSK_API int nsk_mpk(nsk_csr_t A, int k, const double *x, double *const *levels, nsk_mode mode,
+                    nsk_where where)
+{
+    if (!A) return NSK_ERR_INVALID;
+    nsk_ctx_t ctx = A->ctx;
+    NSK_REQUIRE(ctx, k >= 1 && k <= NSK_MAX_K, "k out of range");
+    NSK_REQUIRE(ctx, x && levels, "x or levels is null");
+    NSK_REQUIRE(ctx, A->dist != nullptr || A->n == A->n_cols, "matrix powers need a square operator");
+    for (int l = 0; l < k; l++) NSK_REQUIRE(ctx, levels[l] != nullptr, "a level pointer is null");
+    NSK_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (where == NSK_DEVICE) return nsk_mpk_device(A, k, x, levels, mode);
+
+    const size_t nb = sizeof(double) * (size_t)A->n;
+    void *dx, *dl;
+    NSK_TRY(nsk_stage(ctx, 0, sizeof(double) * (size_t)A->n_cols, &dx));
+    NSK_TRY(nsk_stage(ctx, 1, nb * (size_t)k, &dl));
+    NSK_CUDA(ctx, cudaMemcpyAsync(dx, x, nb, cudaMemcpyHostToDevice, ctx->stream));
+    double *dlev[NSK_MAX_K];
+    for (int l = 0; l < k; l++) dlev[l] = (double *)dl + (size_t)l * (size_t)A->n;
+    NSK_TRY(nsk_mpk_device(A, k, (const double *)dx, dlev, mode));
+    for (int l = 0; l < k; l++)
+        NSK_CUDA(ctx, cudaMemcpyAsync(levels[l], dlev[l], nb, cudaMemcpyDeviceToHost, ctx->stream));
+    NSK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NSK_OK;
+}

@@ -1,0 +1,47 @@
+// mpk.cu -- matrix-powers driver: levels[l] = A^(l+1) x, l = 0..k-1.
+//
+// Replaces the reference's first-touch fused kernels SpM2V_CSR* (mpk/SpM2V.cpp:80-332), SpM3V and
+// SpM4V (mpk/SpMVmulti0.cpp:132-221) and their schedule builders Generate{1st,2nd,3rd}layer.
+// The reference algorithm is a serial lazy traversal; only its RESULT is shared:
+// every level equals k successive row-sequential products, which is what the exact modes
+// reproduce bit for bit (per-row nonzero order is never changed, only the schedule).
+//
+// Strategy 1 ("levels"): k launches of the streaming SpMV kernel back to back on one stream; the
+//   operator is re-read from HBM k times.
+// Strategy 2 ("wavefront"): see mpk_wavefront.cu -- one persistent launch that sweeps row chunks in
+//   a skewed (chunk + level) order so that a chunk's col/val slice is still L2-resident (126 MB)
+//   when the next level needs it; HBM sees the operator once.
+#include "nsk_internal.h"
+
+int nsk_mpk_wavefront(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode,
+                      const int *level_rows);  // mpk_wavefront.cu
+bool nsk_mpk_wavefront_applicable(nsk_csr_t A, int k);
+int nsk_dist_mpk(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode);  // dist.cu
+
+int nsk_mpk_levels(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode,
+                   const int *level_rows)
+{
+    const double *src = d_x;
+    for (int l = 0; l < k; l++) {
+        nsk_spmv_args a;
+        a.x = src;
+        a.y = d_levels[l];
+        a.row_begin = 0;
+        a.row_end = level_rows ? level_rows[l] : A->n;
+        a.mode = mode;
+        NSK_TRY(nsk_launch_spmv(A, a));
+        src = d_levels[l];
+    }
+    return NSK_OK;
+}
+
+int nsk_mpk_device(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode)
+{
+    nsk_ctx_t ctx = A->ctx;
+    if (A->dist) return nsk_dist_mpk(A, k, d_x, d_levels, mode);
+    int sel = (int)ctx->opt.mpk_kernel;
+    if (sel == 0) sel = 1;
+    if (sel == 2 && k > 1 && nsk_mpk_wavefront_applicable(A, k))
+        return nsk_mpk_wavefront(A, k, d_x, d_levels, mode, nullptr);
+    return nsk_mpk_levels(A, k, d_x, d_levels, mode, nullptr);
+}

@@ -1,0 +1,153 @@
+// nsk_internal.h -- shared declarations of the library's translation units (not installed).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/nsk.h"
+
+#define NSK_API extern "C" __attribute__((visibility("default")))
+
+// ---- error plumbing ------------------------------------------------------------------------
+void nsk_set_error(nsk_ctx_t ctx, const char *fmt, ...);
+
+#define NSK_CUDA(ctx, call)                                                                   \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            nsk_set_error((ctx), "%s:%d %s -> %s", __FILE__, __LINE__, #call,                 \
+                          cudaGetErrorString(e__));                                           \
+            return NSK_ERR_CUDA;                                                              \
+        }                                                                                     \
+    } while (0)
+
+#define NSK_REQUIRE(ctx, cond, msg)                                                           \
+    do {                                                                                      \
+        if (!(cond)) {                                                                        \
+            nsk_set_error((ctx), "%s:%d invalid argument: %s", __FILE__, __LINE__, (msg));    \
+            return NSK_ERR_INVALID;                                                           \
+        }                                                                                     \
+    } while (0)
+
+#define NSK_TRY(call)                                                                         \
+    do {                                                                                      \
+        int s__ = (call);                                                                     \
+        if (s__ != NSK_OK) return s__;                                                        \
+    } while (0)
+
+// ---- context -------------------------------------------------------------------------------
+struct nsk_comm_s;  // comm.cpp
+
+struct nsk_options {
+    int64_t spmv_kernel = 0;      // 0 auto, 1 scalar (thread/row from global), 2 stream (TMA pipeline)
+    int64_t spmv_ctas_per_sm = 0; // 0 = kernel default
+    int64_t mpk_kernel = 0;       // 0 auto, 1 = k separate products, 2 = L2 wavefront
+    int64_t stream_variant = 0;   // 0 auto, else index into the stream kernel table
+};
+
+struct nsk_ctx_s {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaDeviceProp prop{};
+    uint64_t launches = 0;
+    std::string last_error;
+    nsk_options opt;
+    // scratch for reductions: partial sums + ticket + result slots (device) and pinned mirror
+    double *d_partials = nullptr;  // NSK_MAX_PARTIALS * NSK_RED_SLOTS
+    unsigned int *d_ticket = nullptr;
+    double *d_scalars = nullptr;   // NSK_NSCALARS device scalars (dot results, CG state)
+    double *h_scalars = nullptr;   // pinned mirror
+    // L2 scrub buffer
+    void *d_flush = nullptr;
+    size_t flush_bytes = 0;
+    // staging buffers for NSK_HOST calls (grown on demand)
+    void *d_stage[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t stage_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    nsk_comm_s *comm = nullptr;
+};
+
+constexpr int NSK_MAX_PARTIALS = 4096;  // max blocks of a reducing kernel
+constexpr int NSK_RED_SLOTS = 96;       // max simultaneous sums per reducing kernel (Gram 9x9 = 81)
+constexpr int NSK_NSCALARS = 256;
+
+int nsk_stage(nsk_ctx_t ctx, int slot, size_t bytes, void **p);  // grow-only device staging buffer
+
+// ---- CSR operator --------------------------------------------------------------------------
+// One unit of work of the streaming kernels: a run of consecutive rows whose col/val slice fits
+// one shared-memory stage.
+struct nsk_tile {
+    int row0;   // first row
+    int nrows;  // rows in the tile (>= 1)
+    int nz0;    // ptrow[row0]
+    int nz1;    // ptrow[row0 + nrows]
+};
+
+struct nsk_tiling {
+    int tile_nnz = 0;   // capacity of a stage in nonzeros
+    int tile_rows = 0;  // max rows per tile
+    int ntiles = 0;
+    int nlong = 0;      // tiles consisting of one row longer than tile_nnz
+    nsk_tile *d_tiles = nullptr;
+    std::vector<nsk_tile> h_tiles;
+};
+
+struct nsk_dist_s;  // dist.cu
+
+struct nsk_csr_s {
+    nsk_ctx_t ctx = nullptr;
+    int n = 0, n_cols = 0;
+    int64_t nnz = 0;
+    int *d_ptrow = nullptr;    // n+1 (+pad)
+    int *d_indcol = nullptr;   // nnz (+pad)
+    double *d_coef = nullptr;  // nnz (+pad)
+    double mean_row = 0.0;
+    int max_row = 0;
+    nsk_tiling tiling;         // plan of the streaming SpMV kernel
+    // MPK scratch: k level vectors when the caller passes host memory, wavefront flags, ...
+    int *d_flags = nullptr;
+    size_t flags_count = 0;
+    nsk_dist_s *dist = nullptr;
+};
+
+struct nsk_bcsr4_s {
+    nsk_ctx_t ctx = nullptr;
+    int nbrows = 0;
+    int64_t nblocks = 0;
+    int *d_ptrow = nullptr;
+    int *d_indcol = nullptr;
+    double *d_coef = nullptr;
+};
+
+// ---- kernel launchers (spmv_kernels.cu) -----------------------------------------------------
+// Row range [row_begin,row_end) lets MPK levels and distributed slabs evaluate a prefix of rows.
+struct nsk_spmv_args {
+    const double *x = nullptr;
+    double *y = nullptr;
+    int row_begin = 0, row_end = 0;
+    nsk_mode mode = NSK_EXACT_FMA;
+    // optional fused dot: partial sums of w[i]*y[i] over the rows computed (CG: w = x = p)
+    const double *dot_w = nullptr;
+    int dot_slot = -1;  // index into ctx->d_scalars receiving the finished sum
+};
+int nsk_launch_spmv(nsk_csr_t A, const nsk_spmv_args &a);
+int nsk_build_tiling(nsk_csr_t A, const int *h_ptrow);
+void nsk_stream_kernel_config(nsk_ctx_t ctx, double mean_row, int *tile_nnz, int *tile_rows);
+
+// ---- vector kernels (vector_kernels.cu) ------------------------------------------------------
+// All results land in ctx->d_scalars[slot]; nothing synchronises.
+int nsk_launch_dot(nsk_ctx_t ctx, int64_t n, const double *a, const double *b, int slot);
+int nsk_launch_diff_norm2sq(nsk_ctx_t ctx, int64_t n, const double *a, const double *b, int slot);
+int nsk_launch_axpy(nsk_ctx_t ctx, int64_t n, double alpha, const double *x, double *y);
+int nsk_launch_axpy_dev(nsk_ctx_t ctx, int64_t n, const double *d_alpha, double scale,
+                        const double *x, double *y);
+int nsk_launch_gram(nsk_ctx_t ctx, int64_t n, int m, const double *const *d_vptrs, int slot0);
+int nsk_read_scalars(nsk_ctx_t ctx, int slot0, int count, double *out);  // syncs the stream
+
+// ---- comm (comm.cpp) -------------------------------------------------------------------------
+int nsk_comm_allreduce_slots(nsk_ctx_t ctx, int slot0, int count);  // no-op without a communicator
+bool nsk_comm_active(nsk_ctx_t ctx);
+int nsk_comm_sendrecv(nsk_ctx_t ctx, int npeers, const int *peer, const double *const *sendbuf,
+                      const int *sendcount, double *const *recvbuf, const int *recvcount);
