@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native SpMV / matrix-powers path.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[2], the one the north-star target is quoted on): fp64 CSR 7-point Laplacian
+256^3 (n = 16 777 216, nnz = 117 047 296), matrix powers k = 4.  One STEP = one call producing A x, A^2 x,
+A^3 x, A^4 x.  N > 1: weak scaling by default -- every rank owns a 256 x 256 x 256 slab of a 256 x 256 x 256N
+grid (row-partitioned operator, one depth-4 halo exchange per call over NCCL); `--scaling strong` splits the
+256^3 problem instead.
+
+Metric: SpMV-equivalent achieved GB/s = k * B_spmv / t with B_spmv = 12 nnz + 4(n+1) + 16 n, the
+same definition for the GPU arm and the CPU reference arm.  `roofline` is the dominant kernel against the
+measured HBM copy peak (MEASURED_PEAKS.json) using the COMPULSORY bytes of that kernel (fused powers kernel:
+B_mpk = 12 nnz + 4(n+1) + 8n + 8nk per launch; plain SpMV kernel: B_spmv per launch).
+
+The working set (1.74 GB per product) is far larger than the 126 MB L2, so no L2 flush is needed between steps.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+K_POWERS = 4
+GRID = 256
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, torch copy read+write)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU reference arm: the UNMODIFIED reference kernel SpMV_CSR_FMA (oracle/_ref) run data-parallel over
+# row slabs on every host core; falls back to the oracle port when _ref was not built.
+# ---------------------------------------------------------------------------------------------------
+class CpuReference:
+    def __init__(self, A, threads: int):
+        import oracle
+        self.A = A
+        self.threads = max(1, threads)
+        self.kind = "reference" if oracle.ref.available() else "port"
+        n = A.nrows
+        bounds = np.linspace(0, n, self.threads + 1).astype(np.int64)
+        self.slabs = []
+        for t in range(self.threads):
+            r0, r1 = int(bounds[t]), int(bounds[t + 1])
+            p = (A.ptrow[r0:r1 + 1] - A.ptrow[r0]).astype(np.int32)
+            c = A.indcol[A.ptrow[r0]:A.ptrow[r1]]
+            v = A.coef[A.ptrow[r0]:A.ptrow[r1]]
+            if self.kind == "reference":
+                h = oracle.ref.csr(p, c, v)
+                self.slabs.append((r0, r1, h))
+            else:
+                self.slabs.append((r0, r1, (np.ascontiguousarray(p), np.ascontiguousarray(c), np.ascontiguousarray(v))))
+        self.oracle = oracle
+
+    def spmv(self, x, y):
+        def work(s):
+            r0, r1, h = s
+            if self.kind == "reference":
+                h.spmv(x, "fma", out=y[r0:r1])
+            else:
+                p, c, v = h
+                self.oracle.lib.l.oracle_spmv_csr_fma(r1 - r0, p, c, v, x, y[r0:r1])
+        if self.threads == 1:
+            work(self.slabs[0])
+            return
+        ts = [threading.Thread(target=work, args=(s,)) for s in self.slabs]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+
+    def mpk(self, k, x, levels):
+        src = x
+        for l in range(k):
+            self.spmv(src, levels[l])
+            src = levels[l]
+
+
+def cpu_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference_arm(args, A, equiv_bytes):
+    """--impl reference: the reference's CPU kernel on the host cores, same workload, same metric."""
+    T = cpu_threads()
+    ref = CpuReference(A, T)
+    n = A.nrows
+    x = np.sin(0.001 * np.arange(n))
+    levels = [np.zeros(n) for _ in range(K_POWERS)]
+    for _ in range(args.warmup):
+        ref.mpk(K_POWERS, x, levels)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ref.mpk(K_POWERS, x, levels)
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    value = equiv_bytes / dt / 1e9
+    return {
+        "impl": "reference", "metric": "mpk_k4_spmv_equivalent_GBps", "value": value, "unit": "GB/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": T, "kind": ref.kind,
+                         "sample": f"{args.steps} full steps (k=4 x SpMV_CSR_FMA on the whole 256^3 operator), row slabs over "
+                                   f"{T} host threads"},
+        "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+
+
+def workload_config(args, world):
+    return {"workload": f"3D 7-point Laplacian {GRID}^3 per GPU (fp64 CSR, int32 indices), matrix powers k={K_POWERS}"
+                        if args.scaling == "weak" or world == 1 else
+                        f"3D 7-point Laplacian {GRID}^3 split over {world} GPUs, matrix powers k={K_POWERS}",
+            "n_rows_per_gpu": GRID ** 3 if args.scaling == "weak" or world == 1 else GRID ** 3 // world,
+            "k": K_POWERS, "mode": "exact_fma (bit-identical to k x SpMV_CSR_FMA)",
+            "partition": "1 GPU" if world == 1 else f"row slabs along z over {world} GPUs, depth-{K_POWERS} halo per call",
+            "l2": "inputs larger than L2 (1.74 GB per product vs 126 MB), no flush"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--grid", type=int, default=GRID, help="grid edge (default 256; smaller only for debugging)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    globals()["GRID"] = args.grid
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    from navierstokes_b200 import matgen
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        A = matgen.laplace3d_7pt(GRID)
+        print(json.dumps(run_reference_arm(args, A, K_POWERS * A.spmv_bytes())), flush=True)
+        return 0
+
+    import navierstokes_b200 as nsk
+    peak, peak_src = measured_peaks()
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as td
+        torch.cuda.set_device(local_rank)
+        td.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = td
+
+    ctx = nsk.Context(local_rank)
+    n_local = GRID ** 3 if (args.scaling == "weak" or world == 1) else GRID ** 3 // world
+    if world == 1:
+        A = matgen.laplace3d_7pt(GRID)
+        dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
+        spmv_bytes, mpk_bytes = dA.spmv_bytes, dA.mpk_bytes(K_POWERS)
+        x_host = ctx.pinned(A.n)
+        x_host[:] = np.sin(0.001 * np.arange(A.n))
+        lv_host = [ctx.pinned(A.n) for _ in range(K_POWERS)]
+        dx = ctx.to_device(x_host)
+        dlv = [ctx.empty(A.n) for _ in range(K_POWERS)]
+        step_dev = lambda: dA.mpk(K_POWERS, dx, dlv)           # noqa: E731
+        step_e2e = lambda: dA.mpk(K_POWERS, x_host, lv_host)   # noqa: E731
+    else:
+        from navierstokes_b200 import distributed as nd
+        nz_total = GRID * world if args.scaling == "weak" else GRID
+        dop = nd.DistStencil3D(ctx, dist, GRID, GRID, nz_total, halo_depth=K_POWERS)
+        A = dop.local_csr
+        spmv_bytes, mpk_bytes = dop.spmv_bytes_owned, dop.mpk_bytes_owned(K_POWERS)
+        x_host = ctx.pinned(dop.n_owned)
+        x_host[:] = np.sin(0.001 * (dop.row_begin + np.arange(dop.n_owned)))
+        lv_host = [ctx.pinned(dop.n_owned) for _ in range(K_POWERS)]
+        dx = dop.new_vector()
+        dop.set_owned(dx, x_host)
+        dlv = [dop.new_vector() for _ in range(K_POWERS)]
+        step_dev = lambda: dop.mpk(K_POWERS, dx, dlv)                     # noqa: E731
+        step_e2e = lambda: dop.mpk_host(K_POWERS, x_host, lv_host)        # noqa: E731
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            dist.barrier()
+        ctx.sync()
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        import torch
+        t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing (value, roofline) --------------------------------------------------------
+    ctx.set_option("mpk_kernel", 2)  # fused wavefront kernel when applicable, else k launches
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = ctx.launch_count
+    e0, e1 = ctx.event(), ctx.event()
+    e0.record()
+    for _ in range(args.steps):
+        step_dev()
+    e1.record()
+    ms_total = e0.elapsed_ms(e1)
+    barrier()
+    launches = ctx.launch_count - launches0
+    clocks = sampler.stop()
+    ms_step = max_over_ranks(ms_total / args.steps)
+    equiv_total = K_POWERS * spmv_bytes * world
+    value = equiv_total / ms_step / 1e6
+
+    # dominant kernel: launches per step tell which strategy ran
+    per_step = launches / max(args.steps, 1)
+    fused = per_step < K_POWERS
+    if fused:
+        kern_bytes, kern_ms, kern_name = mpk_bytes, ms_total / args.steps, "mpk_wavefront_kernel (1 launch per step)"
+    else:
+        kern_bytes, kern_ms, kern_name = spmv_bytes, ms_total / args.steps / K_POWERS, "spmv_stream_kernel (k launches per step)"
+    achieved = kern_bytes / kern_ms / 1e6
+
+    # secondary: plain SpMV rate of the same operator (one product per launch)
+    y = dlv[0]
+    if world == 1:
+        spmv_once = lambda: dA.spmv(dx, y)   # noqa: E731
+    else:
+        spmv_once = lambda: dop.spmv(dx, y)  # noqa: E731
+    for _ in range(3):
+        spmv_once()
+    s0, s1 = ctx.event(), ctx.event()
+    s0.record()
+    for _ in range(max(args.steps, 10)):
+        spmv_once()
+    s1.record()
+    spmv_ms = max_over_ranks(s0.elapsed_ms(s1) / max(args.steps, 10))
+
+    # ---- end to end through the public host-pointer API (pinned host buffers, copies inside) -------------
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        step_e2e()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / e2e_steps)
+    checksum = float(lv_host[K_POWERS - 1][:1024].sum())  # the D2H result is really read
+
+    out = {
+        "metric": "mpk_k4_spmv_equivalent_GBps", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
+        "clocks": clocks,
+        "e2e": {"value": equiv_total / e2e_ms / 1e6, "unit": "GB/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": 8 * n_local * world, "d2h_bytes_per_step": 8 * n_local * K_POWERS * world,
+                "note": "nsk_mpk with NSK_HOST pointers: pinned x in, k level vectors out, operator resident in HBM",
+                "checksum": checksum},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": kern_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": int(kern_bytes)},
+        "spmv": {"ms": spmv_ms, "achieved_GBps": spmv_bytes * world / spmv_ms / 1e6,
+                 "frac_of_peak": spmv_bytes / spmv_ms / 1e6 / peak, "algorithmic_bytes": int(spmv_bytes)},
+        "mpk_bytes_rate_GBps": mpk_bytes * world / ms_step / 1e6,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        T = cpu_threads()
+        ref = CpuReference(A, T)
+        xs = np.asarray(x_host).copy()
+        lv = [np.zeros(A.nrows) for _ in range(K_POWERS)]
+        ref.mpk(K_POWERS, xs, lv)  # warm
+        reps = 3
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            ref.mpk(K_POWERS, xs, lv)
+        dt = (time.perf_counter() - t0) / reps
+        # the CPU result doubles as a full-size parity check of the GPU path (bit-exact mode)
+        same = all(np.array_equal(lv[l].view(np.int64), np.asarray(lv_host[l]).view(np.int64)) for l in range(K_POWERS))
+        ref1 = CpuReference(A, 1)
+        t1 = time.perf_counter()
+        ref1.spmv(xs, lv[0])
+        dt1 = time.perf_counter() - t1
+        out["cpu_baseline"] = {"value": K_POWERS * spmv_bytes / dt / 1e9, "unit": "GB/s", "cores": T, "kind": ref.kind,
+                               "sample": f"{reps} full steps of the same workload (k=4 x SpMV_CSR_FMA, whole 256^3 operator), "
+                                         f"row slabs over {T} host threads",
+                               "single_thread_spmv_GBps": spmv_bytes / dt1 / 1e9,
+                               "gpu_bitwise_equal_to_cpu_reference": bool(same)}
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -129,6 +129,7 @@ NSK_API int nsk_ctx_set_option(nsk_ctx_t c, const char *name, int64_t v)
     else if (!strcmp(name, "spmv_ctas_per_sm")) c->opt.spmv_ctas_per_sm = v;
     else if (!strcmp(name, "mpk_kernel")) c->opt.mpk_kernel = v;
     else if (!strcmp(name, "stream_variant")) c->opt.stream_variant = v;
+    else if (!strcmp(name, "wave_variant")) c->opt.wave_variant = v;
     else {
         nsk_set_error(c, "unknown option '%s'", name);
         return NSK_ERR_INVALID;

@@ -20,6 +20,8 @@ std::vector<int> &nsk_csr_host_ptrow(nsk_csr_t A)
 }
 
 int nsk_mpk_device(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode);  // mpk.cu
+void nsk_wave_set_block_extents(nsk_csr_t A, const int *ptrow, const int *indcol);                  // mpk_wavefront.cu
+void nsk_wave_free(nsk_csr_t A);
 
 NSK_API int nsk_csr_create(nsk_ctx_t ctx, int n, int n_cols, int64_t nnz, const int *ptrow,
                            const int *indcol, const double *coef, nsk_csr_t *out)
@@ -74,6 +76,7 @@ NSK_API int nsk_csr_create(nsk_ctx_t ctx, int n, int n_cols, int64_t nnz, const 
         NSK_CUDA(ctx, cudaMemcpy(A->d_coef, coef, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice));
     }
     nsk_csr_host_ptrow(A).assign(ptrow, ptrow + n + 1);
+    nsk_wave_set_block_extents(A, ptrow, indcol);
     int s = nsk_build_tiling(A, ptrow);
     if (s != NSK_OK) {
         nsk_csr_destroy(A);
@@ -92,6 +95,7 @@ NSK_API int nsk_csr_destroy(nsk_csr_t A)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     nsk_dist_free(A);
+    nsk_wave_free(A);
     if (A->d_ptrow) cudaFree(A->d_ptrow);
     if (A->d_indcol) cudaFree(A->d_indcol);
     if (A->d_coef) cudaFree(A->d_coef);

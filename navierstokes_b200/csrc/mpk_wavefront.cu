@@ -1,16 +1,422 @@
-// mpk_wavefront.cu -- L2-resident wavefront matrix-powers kernel (placeholder until measured).
+// mpk_wavefront.cu -- fused matrix-powers kernel: levels[l] = A^(l+1) x for l = 0..k-1 in ONE
+// persistent launch that reads the operator from HBM once.
+//
+// Replaces the reference's fused first-touch kernels SpM2V_CSR* (mpk/SpM2V.cpp:80-332), SpM3V and
+// SpM4V (mpk/SpMVmulti0.cpp:132-221).  The reference keeps locality by a serial lazy traversal
+// (compute row j of the lower level the first time some row i needs it); the B200 version keeps it
+// by ORDER: work items are (level, tile) pairs issued along the skewed wavefront
+//
+//        tau = tile + level * D          (D = forward reach of the sparsity pattern, in tiles)
+//
+// so that power l of tile t runs shortly after power l-1 of the tiles it depends on, while their
+// col/val slices (12 B/nnz, the dominant traffic) and the freshly written level vectors are still in
+// the 126 MB L2.  HBM sees 12 nnz + 4(n+1) + 8n read once and 8nk written once (DESIGN.md section
+// 4); the k-1 re-reads are served by L2 (measured 17-34 TB/s vs 7.3 TB/s HBM, profiles/).
+//
+// Mechanics
+//   * same tiles, same shared-memory stage and same TMA bulk-copy ring as the streaming SpMV kernel;
+//   * a CTA's producer lane claims the next work item with one atomicAdd on a global counter
+//     (items are claimed strictly in wavefront order, which is what makes spinning deadlock-free:
+//     the oldest unfinished item is always at the head of some CTA's ring and all its inputs are
+//     older, hence finished) and prefetches its matrix slice immediately -- the slice does not
+//     depend on any flag;
+//   * before reducing rows of (l, t), l >= 1, consumer threads acquire the completion counters of
+//     the level l-1 tile GROUPS covering t's column range (ld.acquire.gpu, bounded spin), then
+//     gather with ordinary coherent loads;
+//   * after the rows are stored: CTA barrier, one thread fences and bumps the group counter.
+//   * per-row arithmetic is the same sequential chain as nsk_spmv, so every level is bit-identical
+//     to k separate products (tests/test_spmv_gpu.py::test_mpk_wavefront_*).
+#include <algorithm>
+
 #include "nsk_internal.h"
+#include "ptx_helpers.cuh"
+#include "stream_common.cuh"
+
+using namespace nskptx;
+
+std::vector<int> &nsk_csr_host_ptrow(nsk_csr_t A);
+
+constexpr int WF_GROUP = 16;  // tiles per completion counter
+
+struct WaveTask {
+    int level, tile, glo, ghi;  // inputs: groups [glo, ghi] of level-1 must be complete
+};
+
+struct WaveParams {
+    const nsk_tile *tiles;
+    const WaveTask *tasks;
+    int ntasks;
+    int ngroups;
+    int *counters;          // [k][ngroups], zeroed before the launch
+    const int *group_size;  // [k][ngroups] tiles that will report per group and level
+    unsigned int *next;     // work-item cursor, zeroed before the launch
+    const int *ptrow;
+    const int *indcol;
+    const double *coef;
+    const double *x;
+    double *levels[NSK_MAX_K];
+    int level_rows[NSK_MAX_K];
+    int k;
+};
+
+template <int T_NNZ, int T_ROWS, int STAGES, int NCW, int MINB, bool MULADD>
+__global__ void __launch_bounds__((NCW + 1) * 32, MINB) mpk_wavefront_kernel(const WaveParams P)
+{
+    using Geo = StageGeom<T_NNZ, T_ROWS>;
+    constexpr int NCT = NCW * 32;
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char *stage_base = smem;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + Geo::BYTES * STAGES);
+    uint64_t *empty = full + STAGES;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NCW);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == NCW) {
+        // ===== producer =====
+        if (lane == 0) {
+            for (int it = 0;; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                const unsigned int q = atomicAdd(P.next, 1u);
+                unsigned char *st = stage_base + (size_t)s * Geo::BYTES;
+                int *hdr = reinterpret_cast<int *>(st + Geo::HDR_OFF);
+                if (q >= (unsigned int)P.ntasks) {
+                    hdr[4] = -1;  // end marker
+                    mbar_arrive(&full[s]);
+                    break;
+                }
+                const WaveTask w = P.tasks[q];
+                const nsk_tile t = P.tiles[w.tile];
+                hdr[0] = t.row0; hdr[1] = t.nrows; hdr[2] = t.nz0; hdr[3] = t.nz1;
+                hdr[4] = w.level; hdr[5] = w.tile; hdr[6] = w.glo; hdr[7] = w.ghi;
+                const int a0 = t.nz0 & ~3, v0 = t.nz0 & ~1, p0 = t.row0 & ~3;
+                const uint32_t cb = (uint32_t)(((t.nz1 - a0) + 3) & ~3) * 4u;
+                const uint32_t vb = (uint32_t)(((t.nz1 - v0) + 1) & ~1) * 8u;
+                const uint32_t pb = (uint32_t)(((t.row0 + t.nrows + 1 - p0) + 3) & ~3) * 4u;
+                mbar_arrive_expect_tx(&full[s], cb + vb + pb);
+                bulk_g2s(st + Geo::PTR_OFF, P.ptrow + p0, pb, &full[s]);
+                if (cb) bulk_g2s(st + Geo::COL_OFF, P.indcol + a0, cb, &full[s]);
+                if (vb) bulk_g2s(st + Geo::VAL_OFF, P.coef + v0, vb, &full[s]);
+            }
+        }
+        return;
+    }
+
+    // ===== consumers =====
+    const int ctid = tid;
+    for (int it = 0;; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        unsigned char *st = stage_base + (size_t)s * Geo::BYTES;
+        const int *hdr = reinterpret_cast<const int *>(st + Geo::HDR_OFF);
+        const int level = hdr[4];
+        if (level < 0) break;
+        const int row0 = hdr[0], nrows = hdr[1], nz0 = hdr[2];
+        const int tile = hdr[5], glo = hdr[6], ghi = hdr[7];
+
+        if (level > 0) {
+            // wait until the level-1 tile groups this tile reads from are complete
+            const int *cnt = P.counters + (size_t)(level - 1) * P.ngroups;
+            const int *need = P.group_size + (size_t)(level - 1) * P.ngroups;
+            for (int g = glo + ctid; g <= ghi; g += NCT) {
+                const int want = need[g];
+                uint32_t spins = 0;
+                while (ld_acquire_gpu(cnt + g) < want) {
+                    __nanosleep(64);
+                    if (++spins > (1u << 24)) __trap();  // protocol bug: fail the launch, never hang
+                }
+            }
+            named_bar_sync(1, NCT);
+        }
+
+        const double *val_s = reinterpret_cast<const double *>(st + Geo::VAL_OFF);
+        const int *col_s = reinterpret_cast<const int *>(st + Geo::COL_OFF);
+        const int *ptr_s = reinterpret_cast<const int *>(st + Geo::PTR_OFF);
+        const int vo = nz0 & ~1, co = nz0 & ~3, po = row0 & ~3;
+        const int row_end = P.level_rows[level];
+        double *dst = P.levels[level];
+        if (level == 0) {
+            const double *src = P.x;  // constant for the whole launch: read-only path
+            for (int r = ctid; r < nrows; r += NCT) {
+                const int row = row0 + r;
+                if (row >= row_end) continue;
+                const int p = ptr_s[row - po], q = ptr_s[row + 1 - po];
+                double acc = 0.0;
+#pragma unroll 4
+                for (int j = p; j < q; j++) acc = row_op<MULADD>(val_s[j - vo], __ldg(src + col_s[j - co]), acc);
+                dst[row] = acc;
+            }
+        } else {
+            // Written earlier in THIS launch by other CTAs: ordinary (coherent, L1-allocating) loads, never
+            // the .nc path.  Visibility: the acquire above compiles to LDG.STRONG.GPU + CCTL.IVALL (this
+            // SM's L1 is invalidated), the named barrier orders every consumer warp after it, and the
+            // producer of the data fenced at GPU scope before bumping the counter.
+            const double *src = P.levels[level - 1];
+            for (int r = ctid; r < nrows; r += NCT) {
+                const int row = row0 + r;
+                if (row >= row_end) continue;
+                const int p = ptr_s[row - po], q = ptr_s[row + 1 - po];
+                double acc = 0.0;
+#pragma unroll 4
+                for (int j = p; j < q; j++) acc = row_op<MULADD>(val_s[j - vo], src[col_s[j - co]], acc);
+                dst[row] = acc;
+            }
+        }
+        if (level < P.k - 1) {
+            named_bar_sync(1, NCT);  // all rows of the tile are stored (CTA scope)
+            if (ctid == 0) {
+                __threadfence();     // ... and made visible at GPU scope before the counter moves
+                atomicAdd(P.counters + (size_t)level * P.ngroups + tile / WF_GROUP, 1);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+    }
+}
+
+// -----------------------------------------------------------------------------------------------
+// host side: plan (cached per operator / k / level_rows) and launch
+// -----------------------------------------------------------------------------------------------
+struct WavePlan {
+    int k = 0;
+    int t_nnz = 0, t_rows = 0;
+    std::vector<int> level_rows;
+    int ntasks = 0, ngroups = 0, D = 0;
+    WaveTask *d_tasks = nullptr;
+    int *d_counters = nullptr;    // k*ngroups ints + 1 cursor (last)
+    int *d_group_size = nullptr;
+};
+
+struct WaveState {
+    std::vector<WavePlan> plans;
+    std::vector<int> blk_min, blk_max;  // per 32-row block: min / max column (filled at create)
+};
+
+#include <map>
+static std::map<nsk_csr_t, WaveState> g_wave;
+
+void nsk_wave_set_block_extents(nsk_csr_t A, const int *ptrow, const int *indcol)
+{
+    WaveState &S = g_wave[A];
+    const int n = A->n;
+    const int nb = (n + 31) / 32;
+    S.blk_min.assign(nb, INT32_MAX);
+    S.blk_max.assign(nb, -1);
+    for (int b = 0; b < nb; b++) {
+        const int r0 = b * 32, r1 = std::min(n, r0 + 32);
+        int mn = INT32_MAX, mx = -1;
+        for (int j = ptrow[r0]; j < ptrow[r1]; j++) {
+            const int c = indcol[j];
+            mn = c < mn ? c : mn;
+            mx = c > mx ? c : mx;
+        }
+        S.blk_min[b] = mn;
+        S.blk_max[b] = mx;
+    }
+}
+
+void nsk_wave_free(nsk_csr_t A)
+{
+    auto it = g_wave.find(A);
+    if (it == g_wave.end()) return;
+    for (WavePlan &p : it->second.plans) {
+        if (p.d_tasks) cudaFree(p.d_tasks);
+        if (p.d_counters) cudaFree(p.d_counters);
+        if (p.d_group_size) cudaFree(p.d_group_size);
+    }
+    g_wave.erase(it);
+}
+
+struct WaveVariant {
+    int t_nnz, t_rows, stages, ncw, minb;
+};
+//                 T_NNZ T_ROWS STAGES NCW MINB
+#define NSK_WAVE_VARIANTS(X) \
+    X(0, 2048, 256, 2, 8, 4)   \
+    X(1, 2048, 256, 3, 8, 3)   \
+    X(2, 4096, 512, 2, 16, 2)  \
+    X(3, 2048, 256, 4, 8, 2)   \
+    X(4, 1024, 128, 3, 4, 5)
+
+static const WaveVariant g_wvariants[] = {
+#define X(id, t, r, s, w, b) {t, r, s, w, b},
+    NSK_WAVE_VARIANTS(X)
+#undef X
+};
+static const int g_nwvariants = sizeof(g_wvariants) / sizeof(g_wvariants[0]);
+
+typedef void (*wave_fn)(const WaveParams);
+static wave_fn wave_lookup(int variant, bool muladd, int *smem)
+{
+    switch (variant) {
+#define X(id, t, r, s, w, b)                                                       \
+    case id:                                                                       \
+        *smem = StageGeom<t, r>::BYTES * s + 2 * s * 8 + 128;                      \
+        return muladd ? mpk_wavefront_kernel<t, r, s, w, b, true> : mpk_wavefront_kernel<t, r, s, w, b, false>;
+        NSK_WAVE_VARIANTS(X)
+#undef X
+    }
+    return nullptr;
+}
+
+int nsk_ensure_tiling_public(nsk_csr_t A, int t_nnz, int t_rows);  // spmv_kernels.cu
+
+static int wave_variant(nsk_ctx_t ctx)
+{
+    int v = (int)ctx->opt.wave_variant;
+    if (v < 0 || v >= g_nwvariants) v = 0;
+    return v;
+}
+
+// Builds (or finds) the plan.  Returns nullptr (and leaves *why) when the wavefront does not apply.
+static WavePlan *get_plan(nsk_csr_t A, int k, const int *level_rows, const WaveVariant &V, const char **why)
+{
+    WaveState &S = g_wave[A];
+    std::vector<int> lr(k);
+    for (int l = 0; l < k; l++) lr[l] = level_rows ? level_rows[l] : A->n;
+    for (WavePlan &p : S.plans)
+        if (p.k == k && p.t_nnz == V.t_nnz && p.t_rows == V.t_rows && p.level_rows == lr) return &p;
+
+    if (S.blk_min.empty()) { *why = "column extents were not recorded"; return nullptr; }
+    if (nsk_ensure_tiling_public(A, V.t_nnz, V.t_rows) != NSK_OK) { *why = "tiling failed"; return nullptr; }
+    const nsk_tiling &T = A->tiling;
+    if (T.nlong) { *why = "operator has rows longer than a stage"; return nullptr; }
+    const int ntiles = T.ntiles;
+    if (ntiles == 0) { *why = "empty operator"; return nullptr; }
+    const int ngroups = (ntiles + WF_GROUP - 1) / WF_GROUP;
+
+    // tile -> group range of its columns
+    std::vector<int> row2tile_start(ntiles);
+    for (int t = 0; t < ntiles; t++) row2tile_start[t] = T.h_tiles[t].row0;
+    auto tile_of_row = [&](int row) {
+        int t = (int)(std::upper_bound(row2tile_start.begin(), row2tile_start.end(), row) - row2tile_start.begin()) - 1;
+        return t < 0 ? 0 : t;
+    };
+    std::vector<int> glo(ntiles), ghi(ntiles);
+    int reach = 0;
+    for (int t = 0; t < ntiles; t++) {
+        const nsk_tile &tl = T.h_tiles[t];
+        int mn = INT32_MAX, mx = -1;
+        for (int b = tl.row0 / 32; b <= (tl.row0 + tl.nrows - 1) / 32; b++) {
+            mn = std::min(mn, S.blk_min[b]);
+            mx = std::max(mx, S.blk_max[b]);
+        }
+        if (mx < 0) { mn = tl.row0; mx = tl.row0; }  // rows without entries depend on nothing
+        if (mx >= A->n) {
+            // columns beyond the stored rows are ghost entries of x: legal only for a distributed slab,
+            // where rows evaluated at level >= 1 never reference them (dist.cu builds the rings so)
+            if (!A->dist) { *why = "columns beyond the row range"; return nullptr; }
+            mx = A->n - 1;
+            if (mn >= A->n) mn = A->n - 1;
+        }
+        glo[t] = tile_of_row(mn) / WF_GROUP;
+        ghi[t] = tile_of_row(mx) / WF_GROUP;
+        const int last_needed = std::min(ntiles - 1, (ghi[t] + 1) * WF_GROUP - 1);
+        reach = std::max(reach, last_needed - t);
+    }
+    const int D = reach + 1;
+    // The window that must stay in L2: (k-1)*D tiles of matrix data plus k level vectors of it.
+    const double tile_bytes = 12.0 * A->mean_row * V.t_rows + 8.0 * V.t_rows * (k + 1);
+    const double window = (double)(k - 1) * D * tile_bytes;
+    if (window > 0.55 * (double)A->ctx->prop.l2CacheSize) { *why = "wavefront window exceeds the L2 budget"; return nullptr; }
+
+    // number of tiles each level evaluates (row-prefix shrink of the distributed operator)
+    std::vector<int> ntl(k);
+    for (int l = 0; l < k; l++) {
+        int cnt = 0;
+        while (cnt < ntiles && T.h_tiles[cnt].row0 < lr[l]) cnt++;
+        ntl[l] = cnt;
+    }
+    std::vector<WaveTask> tasks;
+    tasks.reserve((size_t)k * ntiles);
+    const int tau_end = ntiles + (k - 1) * D;
+    for (int tau = 0; tau < tau_end; tau++)
+        for (int l = k - 1; l >= 0; l--) {
+            const int t = tau - l * D;
+            if (t < 0 || t >= ntl[l]) continue;
+            tasks.push_back(WaveTask{l, t, glo[t], ghi[t]});
+        }
+    std::vector<int> gsize((size_t)k * ngroups, 0);
+    for (int l = 0; l < k; l++)
+        for (int t = 0; t < ntl[l]; t++) gsize[(size_t)l * ngroups + t / WF_GROUP]++;
+    WavePlan p;
+    p.k = k; p.t_nnz = V.t_nnz; p.t_rows = V.t_rows; p.level_rows = lr;
+    p.ntasks = (int)tasks.size(); p.ngroups = ngroups; p.D = D;
+    if (cudaMalloc(&p.d_tasks, sizeof(WaveTask) * tasks.size()) != cudaSuccess ||
+        cudaMalloc(&p.d_counters, sizeof(int) * ((size_t)k * ngroups + 4)) != cudaSuccess ||
+        cudaMalloc(&p.d_group_size, sizeof(int) * (size_t)k * ngroups) != cudaSuccess) {
+        *why = "plan allocation failed";
+        return nullptr;
+    }
+    cudaMemcpy(p.d_tasks, tasks.data(), sizeof(WaveTask) * tasks.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(p.d_group_size, gsize.data(), sizeof(int) * gsize.size(), cudaMemcpyHostToDevice);
+    S.plans.push_back(p);
+    return &S.plans.back();
+}
 
 bool nsk_mpk_wavefront_applicable(nsk_csr_t A, int k)
 {
-    (void)A; (void)k;
-    return false;
+    if (k < 2 || A->mean_row > 12.0 || A->n == 0) return false;
+    const char *why = nullptr;
+    return get_plan(A, k, nullptr, g_wvariants[wave_variant(A->ctx)], &why) != nullptr;
 }
 
 int nsk_mpk_wavefront(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode,
                       const int *level_rows)
 {
-    (void)k; (void)d_x; (void)d_levels; (void)mode; (void)level_rows;
-    nsk_set_error(A->ctx, "wavefront matrix-powers kernel not built");
-    return NSK_ERR_UNSUPPORTED;
+    nsk_ctx_t ctx = A->ctx;
+    const int variant = wave_variant(ctx);
+    const WaveVariant &V = g_wvariants[variant];
+    const char *why = "";
+    WavePlan *plan = get_plan(A, k, level_rows, V, &why);
+    if (!plan) {
+        nsk_set_error(ctx, "wavefront matrix powers not applicable: %s", why);
+        return NSK_ERR_UNSUPPORTED;
+    }
+    NSK_TRY(nsk_ensure_tiling_public(A, V.t_nnz, V.t_rows));
+    int smem = 0;
+    wave_fn fn = wave_lookup(variant, mode == NSK_EXACT_MULADD, &smem);
+    NSK_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int per_sm = 0;
+    NSK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, (V.ncw + 1) * 32, smem));
+    if (ctx->opt.spmv_ctas_per_sm > 0) per_sm = std::min(per_sm, (int)ctx->opt.spmv_ctas_per_sm);
+    NSK_REQUIRE(ctx, per_sm >= 1, "wavefront kernel does not fit on an SM");
+    const int grid = std::min(plan->ntasks, ctx->prop.multiProcessorCount * per_sm);
+
+    const size_t ncnt = (size_t)k * plan->ngroups;
+    NSK_CUDA(ctx, cudaMemsetAsync(plan->d_counters, 0, sizeof(int) * (ncnt + 4), ctx->stream));
+    WaveParams P;
+    P.tiles = A->tiling.d_tiles;
+    P.tasks = plan->d_tasks;
+    P.ntasks = plan->ntasks;
+    P.ngroups = plan->ngroups;
+    P.counters = plan->d_counters;
+    P.group_size = plan->d_group_size;
+    P.next = reinterpret_cast<unsigned int *>(plan->d_counters + ncnt);
+    P.ptrow = A->d_ptrow;
+    P.indcol = A->d_indcol;
+    P.coef = A->d_coef;
+    P.x = d_x;
+    for (int l = 0; l < NSK_MAX_K; l++) {
+        P.levels[l] = l < k ? d_levels[l] : nullptr;
+        P.level_rows[l] = l < k ? plan->level_rows[l] : 0;
+    }
+    P.k = k;
+    fn<<<grid, (V.ncw + 1) * 32, smem, ctx->stream>>>(P);
+    ctx->launches++;
+    NSK_CUDA(ctx, cudaGetLastError());
+    return NSK_OK;
 }

@@ -44,7 +44,8 @@ struct nsk_options {
     int64_t spmv_kernel = 0;      // 0 auto, 1 scalar (thread/row from global), 2 stream (TMA pipeline)
     int64_t spmv_ctas_per_sm = 0; // 0 = kernel default
     int64_t mpk_kernel = 0;       // 0 auto, 1 = k separate products, 2 = L2 wavefront
-    int64_t stream_variant = 0;   // 0 auto, else index into the stream kernel table
+    int64_t stream_variant = 0;   // 0 auto, else 1 + index into the stream kernel table
+    int64_t wave_variant = 0;     // index into the wavefront kernel table
 };
 
 struct nsk_ctx_s {

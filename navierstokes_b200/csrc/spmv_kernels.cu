@@ -28,18 +28,9 @@
 
 #include "nsk_internal.h"
 #include "ptx_helpers.cuh"
+#include "stream_common.cuh"
 
 using namespace nskptx;
-
-// -----------------------------------------------------------------------------------------------
-// arithmetic flavours
-// -----------------------------------------------------------------------------------------------
-template <bool MULADD>
-__device__ __forceinline__ double row_op(double a, double x, double acc)
-{
-    if (MULADD) return __dadd_rn(acc, __dmul_rn(a, x));  // two roundings, never contracted
-    return __fma_rn(a, x, acc);                          // one rounding (vfmadd231sd on the CPU)
-}
 
 // -----------------------------------------------------------------------------------------------
 // simple kernels (global memory only)
@@ -99,20 +90,6 @@ struct StreamParams {
     double *partials;
     unsigned int *ticket;
     double *dot_out;
-};
-
-template <int T_NNZ, int T_ROWS>
-struct StageGeom {
-    static_assert(T_NNZ % 4 == 0 && T_ROWS % 4 == 0, "tile sizes must be multiples of 4");
-    static constexpr int VAL_OFF = 0;
-    static constexpr int VAL_BYTES = (T_NNZ + 2) * 8;
-    static constexpr int COL_OFF = VAL_OFF + VAL_BYTES;
-    static constexpr int COL_BYTES = (T_NNZ + 4) * 4;
-    static constexpr int PTR_OFF = COL_OFF + COL_BYTES;
-    static constexpr int PTR_BYTES = (T_ROWS + 8) * 4;
-    static constexpr int HDR_OFF = PTR_OFF + PTR_BYTES;
-    static constexpr int BYTES = HDR_OFF + 16;
-    static_assert(BYTES % 16 == 0, "stage must keep 16-byte alignment");
 };
 
 template <int T_NNZ, int T_ROWS, int STAGES, int KIND>
@@ -366,8 +343,10 @@ static stream_fn lookup_kernel(int variant, int kind, int g, bool muladd, int *s
 
 static int default_variant(double mean_row)
 {
+    // measured on B200, 256^3 7-point (profiles/r01_sweep_spmv_c3.txt): two shallow stages with 4 CTAs
+    // per SM (32 consumer warps) beat deep rings with one big CTA: 0.249 ms vs 0.322 ms
     (void)mean_row;
-    return 0;
+    return 3;
 }
 
 void nsk_stream_kernel_config(nsk_ctx_t ctx, double mean_row, int *tile_nnz, int *tile_rows)
@@ -430,6 +409,11 @@ static int ensure_tiling(nsk_csr_t A, const std::vector<int> &h_ptrow, int t_nnz
 }
 
 extern std::vector<int> &nsk_csr_host_ptrow(nsk_csr_t A);  // csr.cu
+
+int nsk_ensure_tiling_public(nsk_csr_t A, int t_nnz, int t_rows)
+{
+    return ensure_tiling(A, nsk_csr_host_ptrow(A), t_nnz, t_rows);
+}
 
 int nsk_build_tiling(nsk_csr_t A, const int *h_ptrow)
 {

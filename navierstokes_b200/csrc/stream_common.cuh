@@ -1,0 +1,32 @@
+// stream_common.cuh -- pieces shared by the streaming SpMV kernel and the wavefront matrix-powers kernel.
+#pragma once
+#include "nsk_internal.h"
+#include "ptx_helpers.cuh"
+
+// -----------------------------------------------------------------------------------------------
+// arithmetic flavours
+// -----------------------------------------------------------------------------------------------
+template <bool MULADD>
+__device__ __forceinline__ double row_op(double a, double x, double acc)
+{
+    if (MULADD) return __dadd_rn(acc, __dmul_rn(a, x));  // two roundings, never contracted
+    return __fma_rn(a, x, acc);                          // one rounding (vfmadd231sd on the CPU)
+}
+
+// -----------------------------------------------------------------------------------------------
+// shared-memory stage of one tile: [coef slice | indcol slice | ptrow slice | header]
+// -----------------------------------------------------------------------------------------------
+template <int T_NNZ, int T_ROWS>
+struct StageGeom {
+    static_assert(T_NNZ % 4 == 0 && T_ROWS % 4 == 0, "tile sizes must be multiples of 4");
+    static constexpr int VAL_OFF = 0;
+    static constexpr int VAL_BYTES = (T_NNZ + 2) * 8;
+    static constexpr int COL_OFF = VAL_OFF + VAL_BYTES;
+    static constexpr int COL_BYTES = (T_NNZ + 4) * 4;
+    static constexpr int PTR_OFF = COL_OFF + COL_BYTES;
+    static constexpr int PTR_BYTES = (T_ROWS + 8) * 4;
+    static constexpr int HDR_OFF = PTR_OFF + PTR_BYTES;
+    static constexpr int BYTES = HDR_OFF + 32;  // header: row0, nrows, nz0, nz1, level, tile, dep_lo, dep_hi
+    static_assert(BYTES % 16 == 0, "stage must keep 16-byte alignment");
+};
+

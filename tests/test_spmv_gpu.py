@@ -1,0 +1,255 @@
+"""GPU parity: nsk_spmv / nsk_mpk through the C ABI against the oracle and the golden fixtures."""
+import numpy as np
+import pytest
+
+import navierstokes_b200 as nsk
+from navierstokes_b200 import matgen
+from conftest import CSR_CASES, DEEP_CASES, VECS, assert_bits_equal, golden
+
+pytestmark = pytest.mark.gpu
+
+FAST_TOL = 1e-12  # BASELINE.json north star: fast mode within 1e-12 relative (reference rel_error)
+
+
+def all_kernel_configs(ctx):
+    """(spmv_kernel, stream_variant) pairs: the simple kernels and every streaming geometry."""
+    yield 1, 0
+    for v in range(1, 9):
+        yield 2, v
+
+
+@pytest.fixture()
+def reset_options(ctx):
+    yield
+    ctx.set_option("spmv_kernel", 0)
+    ctx.set_option("stream_variant", 0)
+    ctx.set_option("spmv_ctas_per_sm", 0)
+    ctx.set_option("mpk_kernel", 0)
+
+
+@pytest.mark.parametrize("case", CSR_CASES)
+def test_spmv_exact_fma_golden(ctx, case, reset_options):
+    g = golden(case)
+    A = nsk.CsrMatrix(ctx, g["ptrow"], g["indcol"], g["coef"])
+    for kern, var in all_kernel_configs(ctx):
+        ctx.set_option("spmv_kernel", kern)
+        ctx.set_option("stream_variant", var)
+        for v in VECS:
+            y = A.spmv(g[f"x_{v}"], mode=nsk.EXACT_FMA)
+            assert_bits_equal(y, g[f"spmv_fma_{v}"], f"{case}/{v} kernel={kern} variant={var}")
+
+
+@pytest.mark.parametrize("case", CSR_CASES)
+def test_spmv_exact_muladd_and_fast(ctx, oracle_lib, case, reset_options):
+    g = golden(case)
+    A = nsk.CsrMatrix(ctx, g["ptrow"], g["indcol"], g["coef"])
+    for kern, var in [(1, 0), (2, 1), (2, 2)]:
+        ctx.set_option("spmv_kernel", kern)
+        ctx.set_option("stream_variant", var)
+        for v in VECS:
+            x = g[f"x_{v}"]
+            ym = A.spmv(x, mode=nsk.EXACT_MULADD)
+            assert_bits_equal(ym, oracle_lib.spmv_muladd(g["ptrow"], g["indcol"], g["coef"], x), f"{case}/{v} muladd")
+            yf = A.spmv(x, mode=nsk.FAST)
+            ref = g[f"spmv_fma_{v}"]
+            if np.any(ref):
+                assert oracle_lib.rel_error(ref, yf) <= FAST_TOL
+
+
+def test_reference_named_entry_points(ctx, oracle_lib):
+    """Reads like mpk/2SpMV.cpp:127-293: every variant against variant 0 with rel_error."""
+    g = golden("fem_baij4_m3")
+    A = nsk.csrmatrix(n=len(g["ptrow"]) - 1, nnz=len(g["indcol"]), ptrow=g["ptrow"], indcol=g["indcol"],
+                      coef=g["coef"])
+    x = np.ones(A.n)
+    base = np.zeros(A.n)
+    nsk.SpMV_CSR(base, x, A)
+    for fn in (nsk.SpMV_CSR_OPT, nsk.SpMV_CSR_FMA, nsk.SpMV_CSR_AVX2):
+        y = np.zeros(A.n)
+        fn(y, x, A)
+        assert nsk.rel_error(base, y) <= 1e-12
+    y = np.zeros(A.n)
+    nsk.SpMV_CSR_FMA(y, g["x_uni"], A)
+    assert_bits_equal(y, g["spmv_fma_uni"])
+    z, y2 = np.zeros(A.n), np.zeros(A.n)
+    nsk.SpM2V_CSR_OPT(z, y2, g["x_uni"], A, None)
+    lv = oracle_lib.mpk(g["ptrow"], g["indcol"], g["coef"], 2, g["x_uni"])
+    assert_bits_equal(y2, lv[0])
+    assert_bits_equal(z, lv[1])
+
+
+@pytest.mark.parametrize("n,mean", [(1, 3.0), (7, 2.0), (1000, 0.5), (5000, 5.0), (3000, 40.0), (2000, 130.0)])
+def test_spmv_ragged_edge_cases(ctx, oracle_lib, n, mean, reset_options):
+    """Empty rows, rows longer than a warp, tiny and single-row operators."""
+    A = matgen.random_csr(n, mean, seed=n, empty_rows=True)
+    x = matgen.vec_uniform(n, seed=2)
+    ref = oracle_lib.spmv(A.ptrow, A.indcol, A.coef, x)
+    dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
+    for kern, var in all_kernel_configs(ctx):
+        ctx.set_option("spmv_kernel", kern)
+        ctx.set_option("stream_variant", var)
+        assert_bits_equal(dA.spmv(x, mode=nsk.EXACT_FMA), ref, f"n={n} kernel={kern} variant={var}")
+        yf = dA.spmv(x, mode=nsk.FAST)
+        if np.any(ref):
+            assert oracle_lib.rel_error(ref, yf) <= FAST_TOL
+
+
+def test_spmv_empty_operator(ctx):
+    A = nsk.CsrMatrix(ctx, np.zeros(1, np.int32), np.zeros(0, np.int32), np.zeros(0))
+    assert A.spmv(np.zeros(0)).size == 0
+    B = nsk.CsrMatrix(ctx, np.zeros(6, np.int32), np.zeros(0, np.int32), np.zeros(0))
+    assert np.array_equal(B.spmv(np.ones(5)), np.zeros(5))
+
+
+def test_spmv_row_longer_than_a_stage(ctx, oracle_lib, reset_options):
+    """One dense row of 10000 entries among short ones: exceeds every tile geometry (max 4096)."""
+    n = 12000
+    rng = np.random.default_rng(5)
+    lens = np.full(n, 3)
+    lens[17] = 10000
+    lens[n - 1] = 5000
+    ptrow = np.zeros(n + 1, np.int32)
+    ptrow[1:] = np.cumsum(lens)
+    indcol = np.concatenate([np.sort(rng.choice(n, l, replace=False)) for l in lens]).astype(np.int32)
+    coef = rng.uniform(-1, 1, ptrow[-1])
+    x = rng.uniform(-1, 1, n)
+    ref = oracle_lib.spmv(ptrow, indcol, coef, x)
+    dA = nsk.CsrMatrix(ctx, ptrow, indcol, coef)
+    for var in (1, 2, 5):
+        ctx.set_option("stream_variant", var)
+        assert_bits_equal(dA.spmv(x, mode=nsk.EXACT_FMA), ref, f"variant {var}")
+        assert oracle_lib.rel_error(ref, dA.spmv(x, mode=nsk.FAST)) <= FAST_TOL
+
+
+def test_invalid_arguments_are_errors(ctx):
+    with pytest.raises(nsk.NskError):
+        nsk.CsrMatrix(ctx, np.array([0, 2, 1], np.int32), np.array([0, 1], np.int32), np.ones(2))  # decreasing
+    with pytest.raises(nsk.NskError):
+        nsk.CsrMatrix(ctx, np.array([0, 1], np.int32), np.array([5], np.int32), np.ones(1))  # column out of range
+
+
+@pytest.mark.parametrize("case", CSR_CASES)
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 8])
+def test_mpk_equals_k_products_bitwise(ctx, oracle_lib, case, k):
+    g = golden(case)
+    A = nsk.CsrMatrix(ctx, g["ptrow"], g["indcol"], g["coef"])
+    for v in VECS:
+        lv = A.mpk(k, g[f"x_{v}"], mode=nsk.EXACT_FMA)
+        assert_bits_equal(lv, oracle_lib.mpk(g["ptrow"], g["indcol"], g["coef"], k, g[f"x_{v}"]), f"{case}/{v}/k={k}")
+
+
+@pytest.mark.parametrize("case", DEEP_CASES)
+def test_mpk_against_reference_spmkv_golden(ctx, oracle_lib, case):
+    """SpM2V0 / SpM3V / SpM4V outputs of the reference (x87 / mixed contraction): 1e-12 bound."""
+    g = golden(case)
+    A = nsk.CsrMatrix(ctx, g["ptrow"], g["indcol"], g["coef"])
+    for depth in (2, 3, 4):
+        for v in VECS:
+            lv = A.mpk(depth, g[f"x_{v}"], mode=nsk.EXACT_FMA)
+            ref = g[f"multi0_k{depth}_{v}"]
+            for l in range(depth):
+                assert oracle_lib.rel_error(ref[l], lv[l]) <= 1e-12
+    # multiply-add flavour reproduces the no-fma reference bit for bit on the stencil case
+    if case == "lap3d_7pt_6":
+        lv = A.mpk(4, g["x_uni"], mode=nsk.EXACT_MULADD)
+        assert_bits_equal(lv, g["multi0_k4_uni"])
+
+
+def test_spm2v_opt_golden_mixed_flavour(ctx):
+    """SpM2V_CSR_OPT as the reference compiles here: level 1 multiply-add, level 2 fma."""
+    g = golden("lap3d_7pt_12x10x9")
+    A = nsk.CsrMatrix(ctx, g["ptrow"], g["indcol"], g["coef"])
+    for v in VECS:
+        y = A.spmv(g[f"x_{v}"], mode=nsk.EXACT_MULADD)
+        z = A.spmv(y, mode=nsk.EXACT_FMA)
+        assert_bits_equal(y, g[f"spm2v_opt_y_{v}"])
+        assert_bits_equal(z, g[f"spm2v_opt_z_{v}"])
+
+
+def test_device_resident_path_matches_host_path(ctx):
+    A = matgen.laplace3d_7pt(20)
+    x = matgen.vec_uniform(A.n)
+    dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
+    dx = ctx.to_device(x)
+    lv_d = dA.mpk(4, dx)
+    lv_h = dA.mpk(4, x)
+    for l in range(4):
+        assert_bits_equal(lv_d[l].to_host(), lv_h[l])
+    assert ctx.launch_count > 0
+
+
+@pytest.mark.parametrize("shape", ["2d", "3d"])
+def test_medium_size_properties(ctx, oracle_lib, shape, reset_options):
+    """Larger than any fixture (seconds on the oracle): bit-exact against the oracle, plus linearity
+    A(ax+by) ~= aAx + bAy and the constant-vector identity of the stencil (row sums)."""
+    A = matgen.laplace2d_5pt(700) if shape == "2d" else matgen.laplace3d_7pt(80)
+    x, w = matgen.vec_uniform(A.n, 1), matgen.vec_sin(A.n)
+    dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
+    for var in (1, 2, 3, 4, 5, 6, 7, 8):
+        ctx.set_option("stream_variant", var)
+        y = dA.spmv(x)
+        assert_bits_equal(y, oracle_lib.spmv(A.ptrow, A.indcol, A.coef, x), f"variant {var}")
+    yw = dA.spmv(w)
+    comb = dA.spmv(2.0 * x - 3.0 * w)
+    assert oracle_lib.rel_error(2.0 * y - 3.0 * yw, comb) <= 1e-13
+    ones = dA.spmv(np.ones(A.n))
+    rowsum = np.add.reduceat(A.coef, A.ptrow[:-1])
+    assert np.array_equal(ones, rowsum)
+
+
+# ---- wavefront (single-launch, L2-resident) matrix powers ------------------------------------------
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("gen,args", [("laplace3d_7pt", (40,)), ("laplace2d_5pt", (300,)), ("laplace3d_7pt", (64, 64, 20))])
+def test_mpk_wavefront_bitwise(ctx, oracle_lib, gen, args, variant, reset_options):
+    A = getattr(matgen, gen)(*args)
+    x = matgen.vec_uniform(A.n, seed=9)
+    dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
+    ctx.set_option("mpk_kernel", 2)
+    ctx.set_option("wave_variant", variant)
+    for k in (2, 4, 7):
+        before = ctx.launch_count
+        lv = dA.mpk(k, x, mode=nsk.EXACT_FMA)
+        assert_bits_equal(lv, oracle_lib.mpk(A.ptrow, A.indcol, A.coef, k, x), f"{gen}{args} k={k} variant={variant}")
+    lm = dA.mpk(3, x, mode=nsk.EXACT_MULADD)
+    ctx.set_option("mpk_kernel", 1)
+    assert_bits_equal(lm, dA.mpk(3, x, mode=nsk.EXACT_MULADD))
+
+
+def test_mpk_wavefront_is_one_launch(ctx, reset_options):
+    A = matgen.laplace3d_7pt(48)
+    dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
+    dx = ctx.to_device(matgen.vec_uniform(A.n))
+    lv = [ctx.empty(A.n) for _ in range(4)]
+    ctx.set_option("mpk_kernel", 2)
+    dA.mpk(4, dx, lv)
+    before = ctx.launch_count
+    dA.mpk(4, dx, lv)
+    assert ctx.launch_count - before == 1
+    ctx.set_option("mpk_kernel", 1)
+    before = ctx.launch_count
+    dA.mpk(4, dx, lv)
+    assert ctx.launch_count - before == 4
+
+
+def test_mpk_wavefront_repeated_calls_are_stable(ctx, reset_options):
+    """Counters are reset per call: 20 back-to-back calls give the same bits."""
+    A = matgen.laplace3d_7pt(56)
+    dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
+    dx = ctx.to_device(matgen.vec_uniform(A.n, 4))
+    lv = [ctx.empty(A.n) for _ in range(4)]
+    ctx.set_option("mpk_kernel", 2)
+    dA.mpk(4, dx, lv)
+    first = [l.to_host() for l in lv]
+    for _ in range(20):
+        dA.mpk(4, dx, lv)
+    for l in range(4):
+        assert_bits_equal(lv[l].to_host(), first[l])
+
+
+def test_mpk_wavefront_falls_back_when_not_applicable(ctx, oracle_lib, reset_options):
+    """Unstructured operator whose reach covers the whole matrix: the levels strategy must run."""
+    A = matgen.random_csr(4000, 5.0, seed=1, empty_rows=True)
+    x = matgen.vec_uniform(A.n)
+    dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
+    ctx.set_option("mpk_kernel", 2)
+    assert_bits_equal(dA.mpk(3, x), oracle_lib.mpk(A.ptrow, A.indcol, A.coef, 3, x))
