@@ -177,29 +177,55 @@ int nsk_comm_init(nsk_ctx_t ctx, int nranks, int rank, const void *id128);
 int nsk_comm_destroy(nsk_ctx_t ctx);
 int nsk_comm_allreduce_sum(nsk_ctx_t ctx, double *dbuf, int count); /* in place, device buffer */
 
-/* Distributed operator: this rank owns global rows [row_begin, row_end).
- * The caller supplies the rows of the depth-(halo_depth-1) closure of the owned block in LOCAL
- * numbering [owned | ring 1 | ring 2 | ...] as produced by nsk_plan_* (host-only helpers below),
- * plus, per neighbour rank, which local entries to send and where received entries land.
- *   n_rows_local : rows stored (owned + ghost rows that must be recomputed redundantly)
- *   n_cols_local : length of a local vector (owned + all ghosts up to depth halo_depth)
- *   level_rows[l]: number of leading local rows on which power l+1 is evaluated
- *                  (level_rows[halo_depth-1] == n_owned), l = 0 .. halo_depth-1
- * send_idx/recv_idx are local indices, grouped by peer with CSR-style offsets. */
-int nsk_csr_create_dist(nsk_ctx_t ctx, int n_owned, int n_rows_local, int n_cols_local,
-                        int64_t nnz, const int *ptrow, const int *indcol, const double *coef,
-                        int halo_depth, const int *level_rows, int n_peers, const int *peer_rank,
-                        const int *send_off, const int *send_idx, const int *recv_off,
-                        const int *recv_idx, nsk_csr_t *A);
-/* Exchanges ghosts of a local vector (length n_cols_local, device) up to `depth` rings. */
-int nsk_halo_exchange(nsk_csr_t A, double *xlocal, int depth);
+/* ---- distributed operator: row slabs + depth-k ghost rings ------------------------------------
+ * Rank r owns the contiguous global rows [row_starts[r], row_starts[r+1]).  For a depth-K plan the
+ * rank stores, besides its own rows, the rows of ghost rings 1..K-1 (so that powers can be evaluated
+ * redundantly on the shrinking sets N_{K-1} > ... > N_0 = owned, PA1-style) and addresses x on N_K.
+ * Local numbering: [owned | ring 1 | ring 2 | ... | ring K], each ring ascending in global id, so
+ * that everything one peer sends for one ring lands in ONE contiguous range of the local vector.
+ *
+ * Planning is host-only (no GPU, no communicator) and driven by the host layer, which supplies the
+ * matrix rows of each ring (from a generator, a file, or by fetching them from their owners):
+ *
+ *     nsk_plan_create(...)
+ *     while (nsk_plan_frontier(plan, &cnt, &rows), cnt > 0)  nsk_plan_add_rows(plan, cnt, ptr, cols, vals);
+ *     nsk_plan_finalize(plan)
+ *     for every peer p: nsk_plan_requests(plan, p, ...)  -> ship the id list to p (any transport)
+ *                       nsk_plan_add_send(plan, p, ...)  <- the list p shipped to us
+ *     nsk_csr_create_dist(ctx, plan, &A)
+ */
+typedef struct nsk_plan_s *nsk_plan_t;
 
-/* Host-only planning helper (no GPU needed; used by the Python/C++ host layers and CPU tests).
- * Given the rows of a set of global row ids (CSR with global columns), returns the sorted unique
- * column ids that are not in [own_begin, own_end) nor in `known` (sorted).  Two-call protocol:
- * out == NULL returns the count. */
-int64_t nsk_plan_new_columns(int nrows, const int *ptrow, const int *indcol_global, int own_begin,
-                             int own_end, const int *known_sorted, int64_t n_known, int *out);
+int nsk_plan_create(int nranks, int rank, const int *row_starts /* nranks+1 */, int depth, nsk_plan_t *plan);
+int nsk_plan_destroy(nsk_plan_t plan);
+/* Global ids (ascending) of the rows whose matrix rows must be supplied next; *count == 0 when done.
+ * First call: the owned rows; then ring 1, ..., ring depth-1. */
+int nsk_plan_frontier(nsk_plan_t plan, int *count, const int **global_rows);
+/* Rows of the current frontier, in frontier order: ptr[count+1], global column ids, values. */
+int nsk_plan_add_rows(nsk_plan_t plan, int count, const int *ptr, const int *cols_global, const double *vals);
+int nsk_plan_finalize(nsk_plan_t plan);
+/* level_rows[l], l = 0..depth-1: leading local rows on which power l+1 of a depth-`depth` call is
+ * evaluated (level_rows[depth-1] == n_owned).  ring_start[r], r = 0..depth+1: local index where ring r
+ * begins (ring 0 = owned; ring_start[depth+1] == n_cols_local). */
+int nsk_plan_sizes(nsk_plan_t plan, int *n_owned, int *n_rows_local, int *n_cols_local, int64_t *nnz,
+                   int *level_rows, int *ring_start);
+int nsk_plan_ghosts(nsk_plan_t plan, const int **global_ids); /* n_cols_local - n_owned ids, local order */
+int nsk_plan_local_csr(nsk_plan_t plan, const int **ptrow, const int **indcol_local, const double **coef);
+/* What this rank needs from `peer`: global ids in local (ring-major) order and how many per ring
+ * (ring_counts[r-1] for ring r = 1..depth). */
+int nsk_plan_requests(nsk_plan_t plan, int peer, int *count, const int **global_ids, int *ring_counts);
+/* What `peer` needs from this rank (the list peer obtained from ITS nsk_plan_requests(plan, us)). */
+int nsk_plan_add_send(nsk_plan_t plan, int peer, int count, const int *global_ids, const int *ring_counts);
+
+/* Uploads the local operator of a finalized plan and sets up the exchange buffers.  The returned
+ * operator has n = n_rows_local rows and n_cols = n_cols_local columns; vectors passed with
+ * NSK_DEVICE to nsk_spmv / nsk_mpk / nsk_cg on it are LOCAL vectors of n_cols_local doubles whose
+ * first n_owned entries are the owned part (ghost entries are scratch, filled by the exchange).
+ * With NSK_HOST the pointers are owned parts only (n_owned doubles). */
+int nsk_csr_create_dist(nsk_ctx_t ctx, nsk_plan_t plan, nsk_csr_t *A);
+int nsk_csr_owned_rows(nsk_csr_t A); /* n_owned for a distributed operator, n otherwise */
+/* Refreshes ghost rings 1..depth of a local device vector (pack kernel + grouped ncclSend/ncclRecv). */
+int nsk_halo_exchange(nsk_csr_t A, double *xlocal, int depth);
 
 #ifdef __cplusplus
 }

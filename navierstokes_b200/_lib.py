@@ -63,12 +63,19 @@ SIGNATURES = {
     "nsk_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "nsk_comm_destroy": (C.c_int, [C.c_void_p]),
     "nsk_comm_allreduce_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
-    "nsk_csr_create_dist": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
-                                      C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
-                                      C.c_void_p, C.c_void_p, c_void_pp]),
+    "nsk_plan_create": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, c_void_pp]),
+    "nsk_plan_destroy": (C.c_int, [C.c_void_p]),
+    "nsk_plan_frontier": (C.c_int, [C.c_void_p, c_int_p, c_void_pp]),
+    "nsk_plan_add_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nsk_plan_finalize": (C.c_int, [C.c_void_p]),
+    "nsk_plan_sizes": (C.c_int, [C.c_void_p, c_int_p, c_int_p, c_int_p, c_int64_p, C.c_void_p, C.c_void_p]),
+    "nsk_plan_ghosts": (C.c_int, [C.c_void_p, c_void_pp]),
+    "nsk_plan_local_csr": (C.c_int, [C.c_void_p, c_void_pp, c_void_pp, c_void_pp]),
+    "nsk_plan_requests": (C.c_int, [C.c_void_p, C.c_int, c_int_p, c_void_pp, C.c_void_p]),
+    "nsk_plan_add_send": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "nsk_csr_create_dist": (C.c_int, [C.c_void_p, C.c_void_p, c_void_pp]),
+    "nsk_csr_owned_rows": (C.c_int, [C.c_void_p]),
     "nsk_halo_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
-    "nsk_plan_new_columns": (C.c_int64, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64,
-                                         C.c_void_p]),
 }
 
 _lib = None

@@ -23,7 +23,7 @@ NVCC_FLAGS = [
 
 
 def _sources():
-    return sorted(CSRC.glob("*.cu")) + [CSRC / "comm.cpp"]
+    return sorted(CSRC.glob("*.cu")) + [CSRC / "comm.cpp", CSRC / "dist_plan.cpp"]
 
 
 def _stamp(files, extra=""):
@@ -64,7 +64,7 @@ def build(force: bool = False, verbose: bool = False, jobs: int | None = None) -
         outp, _ = p.communicate()
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src.name}:\n{outp.decode()}")
-    link = [nvcc, "-shared", "-o", str(out), *map(str, objs), "-ldl"]
+    link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(out), *map(str, objs), "-ldl"]
     subprocess.run(link, check=True)
     stamp_file.write_text(stamp)
     build_shim(verbose=verbose)

@@ -156,7 +156,7 @@ static int cg_device(nsk_csr_t A, const double *d_b, double *d_x, double tol, in
                      double *relres)
 {
     nsk_ctx_t ctx = A->ctx;
-    const int n = A->n;  // owned rows
+    const int n = nsk_csr_owned_rows(A);
     const size_t nb = sizeof(double) * (size_t)n;
     void *vr, *vp, *vq;
     NSK_TRY(nsk_stage(ctx, 2, nb, &vr));
@@ -232,7 +232,7 @@ NSK_API int nsk_cg(nsk_csr_t A, const double *b, double *x, double tol, int maxi
     NSK_REQUIRE(ctx, tol > 0.0 && maxit >= 0, "bad tolerance / maxit");
     NSK_REQUIRE(ctx, sstep <= 8, "s-step depth above 8 is not supported");
     NSK_CUDA(ctx, cudaSetDevice(ctx->device));
-    const size_t nb = sizeof(double) * (size_t)A->n;
+    const size_t nb = sizeof(double) * (size_t)nsk_csr_owned_rows(A);
     const double *db = b;
     double *dx = x;
     if (where == NSK_HOST) {

@@ -130,6 +130,8 @@ NSK_API int nsk_ctx_set_option(nsk_ctx_t c, const char *name, int64_t v)
     else if (!strcmp(name, "mpk_kernel")) c->opt.mpk_kernel = v;
     else if (!strcmp(name, "stream_variant")) c->opt.stream_variant = v;
     else if (!strcmp(name, "wave_variant")) c->opt.wave_variant = v;
+    else if (!strcmp(name, "wave_slack_pct")) c->opt.wave_slack_pct = v;
+    else if (!strcmp(name, "wave_l2_pct")) c->opt.wave_l2_pct = v;
     else {
         nsk_set_error(c, "unknown option '%s'", name);
         return NSK_ERR_INVALID;

@@ -130,6 +130,8 @@ NSK_API int64_t nsk_csr_mpk_bytes(nsk_csr_t A, int k)
     return 12 * A->nnz + 4 * ((int64_t)A->n + 1) + 8 * (int64_t)A->n + 8 * (int64_t)A->n * k;
 }
 
+int nsk_halo_exchange_dev(nsk_csr_t A, double *xlocal, int depth);  // dist.cu
+
 NSK_API int nsk_spmv(nsk_csr_t A, const double *x, double *y, nsk_mode mode, nsk_where where)
 {
     if (!A) return NSK_ERR_INVALID;
@@ -137,23 +139,28 @@ NSK_API int nsk_spmv(nsk_csr_t A, const double *x, double *y, nsk_mode mode, nsk
     NSK_REQUIRE(ctx, x && y, "x or y is null");
     NSK_REQUIRE(ctx, mode == NSK_EXACT_FMA || mode == NSK_EXACT_MULADD || mode == NSK_FAST, "bad mode");
     NSK_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int n_out = nsk_csr_owned_rows(A);  // distributed: only the owned rows are produced
     nsk_spmv_args a;
     a.row_begin = 0;
-    a.row_end = A->n;
+    a.row_end = n_out;
     a.mode = mode;
     if (where == NSK_DEVICE) {
+        if (A->dist) NSK_TRY(nsk_halo_exchange_dev(A, const_cast<double *>(x), 1));
         a.x = x;
         a.y = y;
         return nsk_launch_spmv(A, a);
     }
+    // host pointers: x holds the owned part (all of x for a single-GPU operator)
+    const size_t n_in = A->dist ? (size_t)n_out : (size_t)A->n_cols;
     void *dx, *dy;
     NSK_TRY(nsk_stage(ctx, 0, sizeof(double) * (size_t)A->n_cols, &dx));
     NSK_TRY(nsk_stage(ctx, 1, sizeof(double) * (size_t)A->n, &dy));
-    NSK_CUDA(ctx, cudaMemcpyAsync(dx, x, sizeof(double) * (size_t)A->n_cols, cudaMemcpyHostToDevice, ctx->stream));
+    NSK_CUDA(ctx, cudaMemcpyAsync(dx, x, sizeof(double) * n_in, cudaMemcpyHostToDevice, ctx->stream));
+    if (A->dist) NSK_TRY(nsk_halo_exchange_dev(A, (double *)dx, 1));
     a.x = (const double *)dx;
     a.y = (double *)dy;
     NSK_TRY(nsk_launch_spmv(A, a));
-    NSK_CUDA(ctx, cudaMemcpyAsync(y, dy, sizeof(double) * (size_t)A->n, cudaMemcpyDeviceToHost, ctx->stream));
+    NSK_CUDA(ctx, cudaMemcpyAsync(y, dy, sizeof(double) * (size_t)n_out, cudaMemcpyDeviceToHost, ctx->stream));
     NSK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return NSK_OK;
 }
@@ -170,13 +177,16 @@ NSK_API int nsk_mpk(nsk_csr_t A, int k, const double *x, double *const *levels, 
     NSK_CUDA(ctx, cudaSetDevice(ctx->device));
     if (where == NSK_DEVICE) return nsk_mpk_device(A, k, x, levels, mode);
 
-    const size_t nb = sizeof(double) * (size_t)A->n;
+    // host pointers: owned parts in, owned parts out; level scratch is one local vector per level
+    const int n_out = nsk_csr_owned_rows(A);
+    const size_t nb = sizeof(double) * (size_t)n_out;
+    const size_t ld = (size_t)A->n_cols;
     void *dx, *dl;
-    NSK_TRY(nsk_stage(ctx, 0, sizeof(double) * (size_t)A->n_cols, &dx));
-    NSK_TRY(nsk_stage(ctx, 1, nb * (size_t)k, &dl));
+    NSK_TRY(nsk_stage(ctx, 0, sizeof(double) * ld, &dx));
+    NSK_TRY(nsk_stage(ctx, 1, sizeof(double) * ld * (size_t)k, &dl));
     NSK_CUDA(ctx, cudaMemcpyAsync(dx, x, nb, cudaMemcpyHostToDevice, ctx->stream));
     double *dlev[NSK_MAX_K];
-    for (int l = 0; l < k; l++) dlev[l] = (double *)dl + (size_t)l * (size_t)A->n;
+    for (int l = 0; l < k; l++) dlev[l] = (double *)dl + (size_t)l * ld;
     NSK_TRY(nsk_mpk_device(A, k, (const double *)dx, dlev, mode));
     for (int l = 0; l < k; l++)
         NSK_CUDA(ctx, cudaMemcpyAsync(levels[l], dlev[l], nb, cudaMemcpyDeviceToHost, ctx->stream));

@@ -1,44 +1,170 @@
-// dist.cu -- row-slab distributed operator: halo exchange + redundant ghost levels (placeholder).
+// dist.cu -- device side of the row-partitioned operator: halo exchange (pack kernel + grouped
+// NCCL point-to-point over NVLink) and matrix powers with redundant ghost levels.
+//
+// The reference is single-process; this is the multi-GPU layer BASELINE.json's north
+// star asks for: one process per GPU, the depth-k halo exchanged ONCE per matrix-powers call, ghost
+// levels recomputed redundantly on shrinking row prefixes (plan: dist_plan.cpp).
+#include <algorithm>
+
+#include "dist_plan.h"
 #include "nsk_internal.h"
 
-void nsk_dist_free(nsk_csr_t A) { (void)A; }
+int nsk_mpk_levels(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode,
+                   const int *level_rows);  // mpk.cu
+int nsk_mpk_wavefront(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode,
+                      const int *level_rows);  // mpk_wavefront.cu
+bool nsk_mpk_wavefront_applicable(nsk_csr_t A, int k);
+int nsk_comm_rank(nsk_ctx_t ctx);
+int nsk_comm_size(nsk_ctx_t ctx);
 
-int nsk_dist_mpk(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode)
+struct DistPeer {
+    int rank = 0;
+    int *d_send_idx = nullptr;          // local indices to pack, ring-major
+    double *d_sendbuf = nullptr;
+    std::vector<int> send_ring_count;   // depth
+    std::vector<int> recv_ring_count;   // depth
+    std::vector<int> recv_ring_start;   // depth, offset into the local vector
+};
+
+struct nsk_dist_s {
+    int n_owned = 0, depth = 0;
+    std::vector<int> ring_start;  // depth + 2
+    std::vector<DistPeer> peers;
+};
+
+__global__ void __launch_bounds__(256) pack_kernel(const double *__restrict__ x, const int *__restrict__ idx,
+                                                   double *__restrict__ out, int count)
 {
-    (void)k; (void)d_x; (void)d_levels; (void)mode;
-    nsk_set_error(A->ctx, "distributed operator not built");
-    return NSK_ERR_UNSUPPORTED;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = x[idx[i]];
+}
+
+void nsk_dist_free(nsk_csr_t A)
+{
+    if (!A || !A->dist) return;
+    for (DistPeer &p : A->dist->peers) {
+        if (p.d_send_idx) cudaFree(p.d_send_idx);
+        if (p.d_sendbuf) cudaFree(p.d_sendbuf);
+    }
+    delete A->dist;
+    A->dist = nullptr;
+}
+
+NSK_API int nsk_csr_owned_rows(nsk_csr_t A)
+{
+    if (!A) return 0;
+    return A->dist ? A->dist->n_owned : A->n;
+}
+
+NSK_API int nsk_csr_create_dist(nsk_ctx_t ctx, nsk_plan_t plan, nsk_csr_t *out)
+{
+    if (!ctx || !plan || !out) return NSK_ERR_INVALID;
+    NSK_REQUIRE(ctx, plan->finalized, "plan is not finalized");
+    const int n_rows = plan->ring_start[plan->depth];
+    const int n_cols = plan->ring_start[plan->depth + 1];
+    nsk_csr_t A = nullptr;
+    NSK_TRY(nsk_csr_create(ctx, n_rows, n_cols, (int64_t)plan->local_cols.size(), plan->ptr.data(),
+                           plan->local_cols.data(), plan->vals.data(), &A));
+    nsk_dist_s *D = new nsk_dist_s();
+    D->n_owned = plan->own_end - plan->own_begin;
+    D->depth = plan->depth;
+    D->ring_start = plan->ring_start;
+    A->dist = D;
+    // peers = every rank we send to or receive from, ascending
+    std::vector<int> ranks;
+    for (auto &kv : plan->req) ranks.push_back(kv.first);
+    for (auto &kv : plan->sends) ranks.push_back(kv.first);
+    std::sort(ranks.begin(), ranks.end());
+    ranks.erase(std::unique(ranks.begin(), ranks.end()), ranks.end());
+    for (int r : ranks) {
+        DistPeer P;
+        P.rank = r;
+        P.send_ring_count.assign(plan->depth, 0);
+        P.recv_ring_count.assign(plan->depth, 0);
+        P.recv_ring_start.assign(plan->depth, 0);
+        auto rq = plan->req.find(r);
+        if (rq != plan->req.end()) {
+            P.recv_ring_count = rq->second.ring_count;
+            P.recv_ring_start = rq->second.ring_local_start;
+        }
+        auto sd = plan->sends.find(r);
+        if (sd != plan->sends.end() && !sd->second.local_idx.empty()) {
+            P.send_ring_count = sd->second.ring_count;
+            const size_t cnt = sd->second.local_idx.size();
+            if (cudaMalloc(&P.d_send_idx, sizeof(int) * cnt) != cudaSuccess ||
+                cudaMalloc(&P.d_sendbuf, sizeof(double) * cnt) != cudaSuccess) {
+                nsk_set_error(ctx, "halo buffer allocation failed");
+                nsk_csr_destroy(A);
+                return NSK_ERR_ALLOC;
+            }
+            NSK_CUDA(ctx, cudaMemcpy(P.d_send_idx, sd->second.local_idx.data(), sizeof(int) * cnt, cudaMemcpyHostToDevice));
+        }
+        D->peers.push_back(P);
+    }
+    *out = A;
+    return NSK_OK;
 }
 
 int nsk_halo_exchange_dev(nsk_csr_t A, double *xlocal, int depth)
 {
-    (void)xlocal; (void)depth;
-    nsk_set_error(A->ctx, "distributed operator not built");
-    return NSK_ERR_UNSUPPORTED;
-}
-
-NSK_API int nsk_csr_create_dist(nsk_ctx_t ctx, int n_owned, int n_rows_local, int n_cols_local, int64_t nnz,
-                                const int *ptrow, const int *indcol, const double *coef, int halo_depth,
-                                const int *level_rows, int n_peers, const int *peer_rank, const int *send_off,
-                                const int *send_idx, const int *recv_off, const int *recv_idx, nsk_csr_t *A)
-{
-    (void)n_owned; (void)n_rows_local; (void)n_cols_local; (void)nnz; (void)ptrow; (void)indcol; (void)coef;
-    (void)halo_depth; (void)level_rows; (void)n_peers; (void)peer_rank; (void)send_off; (void)send_idx;
-    (void)recv_off; (void)recv_idx; (void)A;
-    nsk_set_error(ctx, "distributed operator not built");
-    return NSK_ERR_UNSUPPORTED;
+    nsk_ctx_t ctx = A->ctx;
+    nsk_dist_s *D = A->dist;
+    if (!D) return NSK_OK;
+    NSK_REQUIRE(ctx, depth >= 1 && depth <= D->depth, "halo depth exceeds the plan's depth");
+    if (D->peers.empty()) return NSK_OK;
+    NSK_REQUIRE(ctx, nsk_comm_active(ctx) || nsk_comm_size(ctx) == 1, "no communicator attached (nsk_comm_init)");
+    // pack: one gather per peer over the first `depth` rings of its list
+    std::vector<const double *> sendbuf;
+    std::vector<int> sendcount, recvcount, peer;
+    std::vector<double *> recvbuf;
+    for (DistPeer &P : D->peers) {
+        int cnt = 0;
+        for (int r = 0; r < depth; r++) cnt += P.send_ring_count[r];
+        if (cnt > 0) {
+            pack_kernel<<<(cnt + 255) / 256, 256, 0, ctx->stream>>>(xlocal, P.d_send_idx, P.d_sendbuf, cnt);
+            ctx->launches++;
+        }
+        // one message per ring and direction: a ring's slice from one peer is contiguous on both sides
+        int off = 0;
+        for (int r = 0; r < depth; r++) {
+            peer.push_back(P.rank);
+            sendbuf.push_back(P.d_sendbuf + off);
+            sendcount.push_back(P.send_ring_count[r]);
+            recvbuf.push_back(xlocal + P.recv_ring_start[r]);
+            recvcount.push_back(P.recv_ring_count[r]);
+            off += P.send_ring_count[r];
+        }
+    }
+    NSK_CUDA(ctx, cudaGetLastError());
+    return nsk_comm_sendrecv(ctx, (int)peer.size(), peer.data(), sendbuf.data(), sendcount.data(), recvbuf.data(),
+                             recvcount.data());
 }
 
 NSK_API int nsk_halo_exchange(nsk_csr_t A, double *xlocal, int depth)
 {
-    if (!A) return NSK_ERR_INVALID;
+    if (!A || !xlocal) return NSK_ERR_INVALID;
+    if (!A->dist) {
+        nsk_set_error(A->ctx, "nsk_halo_exchange: not a distributed operator");
+        return NSK_ERR_INVALID;
+    }
+    NSK_CUDA(A->ctx, cudaSetDevice(A->ctx->device));
     return nsk_halo_exchange_dev(A, xlocal, depth);
 }
 
-NSK_API int64_t nsk_plan_new_columns(int nrows, const int *ptrow, const int *indcol_global, int own_begin,
-                                     int own_end, const int *known_sorted, int64_t n_known, int *out)
+// levels[l] are LOCAL vectors (n_cols_local doubles); level l is valid on its row prefix, the owned part
+// of every level is the distributed result.  d_x is a local vector whose owned part is filled.
+int nsk_dist_mpk(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode)
 {
-    (void)nrows; (void)ptrow; (void)indcol_global; (void)own_begin; (void)own_end; (void)known_sorted;
-    (void)n_known; (void)out;
-    return -1;
+    nsk_ctx_t ctx = A->ctx;
+    nsk_dist_s *D = A->dist;
+    NSK_REQUIRE(ctx, k <= D->depth, "k exceeds the halo depth the operator was planned for");
+    NSK_TRY(nsk_halo_exchange_dev(A, const_cast<double *>(d_x), k));
+    int level_rows[NSK_MAX_K];
+    for (int l = 0; l < k; l++) level_rows[l] = D->ring_start[k - l];
+    int sel = (int)ctx->opt.mpk_kernel;
+    if (sel == 2 && k > 1 && nsk_mpk_wavefront_applicable(A, k)) {
+        int s = nsk_mpk_wavefront(A, k, d_x, d_levels, mode, level_rows);
+        if (s != NSK_ERR_UNSUPPORTED) return s;
+    }
+    return nsk_mpk_levels(A, k, d_x, d_levels, mode, level_rows);
 }

@@ -193,6 +193,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, MINB) mpk_wavefront_kernel(con
 struct WavePlan {
     int k = 0;
     int t_nnz = 0, t_rows = 0;
+    int slack = 0;
     std::vector<int> level_rows;
     int ntasks = 0, ngroups = 0, D = 0;
     WaveTask *d_tasks = nullptr;
@@ -282,13 +283,17 @@ static int wave_variant(nsk_ctx_t ctx)
 }
 
 // Builds (or finds) the plan.  Returns nullptr (and leaves *why) when the wavefront does not apply.
-static WavePlan *get_plan(nsk_csr_t A, int k, const int *level_rows, const WaveVariant &V, const char **why)
+// slack: extra skew (in tiles) between consecutive levels on top of the pattern's reach.  Work items are
+// claimed in wavefront order but complete a few microseconds later (grid x STAGES items are in flight);
+// without slack every level-l item would wait for a level-(l-1) item claimed one step earlier and the
+// whole sweep would serialise on that latency (measured: 16 ms instead of 0.5 ms on 256^3, k = 4).
+static WavePlan *get_plan(nsk_csr_t A, int k, const int *level_rows, const WaveVariant &V, int slack, const char **why)
 {
     WaveState &S = g_wave[A];
     std::vector<int> lr(k);
     for (int l = 0; l < k; l++) lr[l] = level_rows ? level_rows[l] : A->n;
     for (WavePlan &p : S.plans)
-        if (p.k == k && p.t_nnz == V.t_nnz && p.t_rows == V.t_rows && p.level_rows == lr) return &p;
+        if (p.k == k && p.t_nnz == V.t_nnz && p.t_rows == V.t_rows && p.slack == slack && p.level_rows == lr) return &p;
 
     if (S.blk_min.empty()) { *why = "column extents were not recorded"; return nullptr; }
     if (nsk_ensure_tiling_public(A, V.t_nnz, V.t_rows) != NSK_OK) { *why = "tiling failed"; return nullptr; }
@@ -327,11 +332,12 @@ static WavePlan *get_plan(nsk_csr_t A, int k, const int *level_rows, const WaveV
         const int last_needed = std::min(ntiles - 1, (ghi[t] + 1) * WF_GROUP - 1);
         reach = std::max(reach, last_needed - t);
     }
-    const int D = reach + 1;
+    const int D = reach + 1 + slack;
     // The window that must stay in L2: (k-1)*D tiles of matrix data plus k level vectors of it.
     const double tile_bytes = 12.0 * A->mean_row * V.t_rows + 8.0 * V.t_rows * (k + 1);
     const double window = (double)(k - 1) * D * tile_bytes;
-    if (window > 0.55 * (double)A->ctx->prop.l2CacheSize) { *why = "wavefront window exceeds the L2 budget"; return nullptr; }
+    const double budget = (A->ctx->opt.wave_l2_pct > 0 ? (double)A->ctx->opt.wave_l2_pct : 80.0) / 100.0;
+    if (window > budget * (double)A->ctx->prop.l2CacheSize) { *why = "wavefront window exceeds the L2 budget"; return nullptr; }
 
     // number of tiles each level evaluates (row-prefix shrink of the distributed operator)
     std::vector<int> ntl(k);
@@ -353,7 +359,7 @@ static WavePlan *get_plan(nsk_csr_t A, int k, const int *level_rows, const WaveV
     for (int l = 0; l < k; l++)
         for (int t = 0; t < ntl[l]; t++) gsize[(size_t)l * ngroups + t / WF_GROUP]++;
     WavePlan p;
-    p.k = k; p.t_nnz = V.t_nnz; p.t_rows = V.t_rows; p.level_rows = lr;
+    p.k = k; p.t_nnz = V.t_nnz; p.t_rows = V.t_rows; p.level_rows = lr; p.slack = slack;
     p.ntasks = (int)tasks.size(); p.ngroups = ngroups; p.D = D;
     if (cudaMalloc(&p.d_tasks, sizeof(WaveTask) * tasks.size()) != cudaSuccess ||
         cudaMalloc(&p.d_counters, sizeof(int) * ((size_t)k * ngroups + 4)) != cudaSuccess ||
@@ -367,11 +373,34 @@ static WavePlan *get_plan(nsk_csr_t A, int k, const int *level_rows, const WaveV
     return &S.plans.back();
 }
 
+// resident CTAs of the chosen kernel and the slack (tiles) that keeps dependent levels apart
+static int wave_launch_shape(nsk_ctx_t ctx, int variant, bool muladd, int k, wave_fn *fn_out, int *smem_out, int *grid_max,
+                             int *slack)
+{
+    const WaveVariant &V = g_wvariants[variant];
+    int smem = 0;
+    wave_fn fn = wave_lookup(variant, muladd, &smem);
+    NSK_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int per_sm = 0;
+    NSK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, (V.ncw + 1) * 32, smem));
+    if (ctx->opt.spmv_ctas_per_sm > 0) per_sm = std::min(per_sm, (int)ctx->opt.spmv_ctas_per_sm);
+    NSK_REQUIRE(ctx, per_sm >= 1, "wavefront kernel does not fit on an SM");
+    *grid_max = ctx->prop.multiProcessorCount * per_sm;
+    const double pct = ctx->opt.wave_slack_pct >= 0 ? (double)ctx->opt.wave_slack_pct : 150.0;
+    *slack = (int)((pct / 100.0) * (double)(*grid_max) * V.stages / (double)k + 0.999);
+    *fn_out = fn;
+    *smem_out = smem;
+    return NSK_OK;
+}
+
 bool nsk_mpk_wavefront_applicable(nsk_csr_t A, int k)
 {
     if (k < 2 || A->mean_row > 12.0 || A->n == 0) return false;
     const char *why = nullptr;
-    return get_plan(A, k, nullptr, g_wvariants[wave_variant(A->ctx)], &why) != nullptr;
+    wave_fn fn; int smem, grid_max, slack;
+    const int variant = wave_variant(A->ctx);
+    if (wave_launch_shape(A->ctx, variant, false, k, &fn, &smem, &grid_max, &slack) != NSK_OK) return false;
+    return get_plan(A, k, nullptr, g_wvariants[variant], slack, &why) != nullptr;
 }
 
 int nsk_mpk_wavefront(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode,
@@ -381,20 +410,15 @@ int nsk_mpk_wavefront(nsk_csr_t A, int k, const double *d_x, double *const *d_le
     const int variant = wave_variant(ctx);
     const WaveVariant &V = g_wvariants[variant];
     const char *why = "";
-    WavePlan *plan = get_plan(A, k, level_rows, V, &why);
+    wave_fn fn; int smem = 0, grid_max = 0, slack = 0;
+    NSK_TRY(wave_launch_shape(ctx, variant, mode == NSK_EXACT_MULADD, k, &fn, &smem, &grid_max, &slack));
+    WavePlan *plan = get_plan(A, k, level_rows, V, slack, &why);
     if (!plan) {
         nsk_set_error(ctx, "wavefront matrix powers not applicable: %s", why);
         return NSK_ERR_UNSUPPORTED;
     }
     NSK_TRY(nsk_ensure_tiling_public(A, V.t_nnz, V.t_rows));
-    int smem = 0;
-    wave_fn fn = wave_lookup(variant, mode == NSK_EXACT_MULADD, &smem);
-    NSK_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    int per_sm = 0;
-    NSK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, (V.ncw + 1) * 32, smem));
-    if (ctx->opt.spmv_ctas_per_sm > 0) per_sm = std::min(per_sm, (int)ctx->opt.spmv_ctas_per_sm);
-    NSK_REQUIRE(ctx, per_sm >= 1, "wavefront kernel does not fit on an SM");
-    const int grid = std::min(plan->ntasks, ctx->prop.multiProcessorCount * per_sm);
+    const int grid = std::min(plan->ntasks, grid_max);
 
     const size_t ncnt = (size_t)k * plan->ngroups;
     NSK_CUDA(ctx, cudaMemsetAsync(plan->d_counters, 0, sizeof(int) * (ncnt + 4), ctx->stream));

@@ -253,3 +253,40 @@ def test_mpk_wavefront_falls_back_when_not_applicable(ctx, oracle_lib, reset_opt
     dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
     ctx.set_option("mpk_kernel", 2)
     assert_bits_equal(dA.mpk(3, x), oracle_lib.mpk(A.ptrow, A.indcol, A.coef, 3, x))
+
+
+# ---- distributed operator, degenerate world of one rank (the N > 1 path is covered by the gloo tests
+# ---- on CPU and by tools/dist_check.py under torchrun) ----------------------------------------------
+class _OneRank:
+    def get_rank(self):
+        return 0
+
+    def get_world_size(self):
+        return 1
+
+    def all_gather_object(self, out, obj):
+        out[0] = obj
+
+    def broadcast_object_list(self, objs, src=0):
+        return None
+
+
+def test_distributed_operator_world1(ctx, oracle_lib, reset_options):
+    from navierstokes_b200 import distributed as nd
+    nx, ny, nz, K = 20, 18, 16, 4
+    A = matgen.laplace3d_7pt(nx, ny, nz)
+    x = matgen.vec_uniform(A.n, seed=5)
+    op = nd.DistStencil3D(ctx, _OneRank(), nx, ny, nz, halo_depth=K)
+    assert op.n_owned == A.n and op.n_cols_local == A.n
+    dx = op.new_vector()
+    op.set_owned(dx, x)
+    ref = oracle_lib.mpk(A.ptrow, A.indcol, A.coef, K, x)
+    for strat in (1, 2):
+        ctx.set_option("mpk_kernel", strat)
+        lv = [op.new_vector() for _ in range(K)]
+        op.mpk(K, dx, lv)
+        for l in range(K):
+            assert_bits_equal(op.get_owned(lv[l]), ref[l], f"strategy {strat} level {l}")
+    b = oracle_lib.spmv(A.ptrow, A.indcol, A.coef, x)
+    xs, it, rel, ok = op.cg(b, tol=1e-9, maxit=500)
+    assert ok and np.max(np.abs(xs - x)) < 1e-6
