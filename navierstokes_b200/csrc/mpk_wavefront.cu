@@ -20,10 +20,11 @@
 //     the oldest unfinished item is always at the head of some CTA's ring and all its inputs are
 //     older, hence finished) and prefetches its matrix slice immediately -- the slice does not
 //     depend on any flag;
-//   * before reducing rows of (l, t), l >= 1, consumer threads acquire the completion counters of
-//     the level l-1 tile GROUPS covering t's column range (ld.acquire.gpu, bounded spin), then
-//     gather with ordinary coherent loads;
-//   * after the rows are stored: CTA barrier, one thread fences and bumps the group counter.
+//   * a dedicated dependency warp acquires, for each claimed item (l, t), l >= 1, the completion counters
+//     of the level l-1 tile GROUPS covering t's column range (ld.acquire.gpu, bounded spin) and then opens
+//     the item for the consumer warps through an mbarrier -- the wait overlaps the previous item's work;
+//   * consumer warps gather with ordinary coherent loads; when a warp has stored its rows it bumps the
+//     group counter with one red.release.gpu (counters count warps: no CTA-wide barrier in the loop).
 //   * per-row arithmetic is the same sequential chain as nsk_spmv, so every level is bit-identical
 //     to k separate products (tests/test_spmv_gpu.py::test_mpk_wavefront_*).
 #include <algorithm>
@@ -60,14 +61,15 @@ struct WaveParams {
 };
 
 template <int T_NNZ, int T_ROWS, int STAGES, int NCW, int MINB, bool MULADD>
-__global__ void __launch_bounds__((NCW + 1) * 32, MINB) mpk_wavefront_kernel(const WaveParams P)
+__global__ void __launch_bounds__((NCW + 2) * 32, MINB) mpk_wavefront_kernel(const WaveParams P)
 {
     using Geo = StageGeom<T_NNZ, T_ROWS>;
-    constexpr int NCT = NCW * 32;
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *stage_base = smem;
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + Geo::BYTES * STAGES);
-    uint64_t *empty = full + STAGES;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + Geo::BYTES * STAGES);  // TMA bytes of the stage landed
+    uint64_t *empty = full + STAGES;                                            // all consumer warps are done with it
+    uint64_t *claimed = empty + STAGES;                                         // header written (producer -> dependency warp)
+    uint64_t *ready = claimed + STAGES;                                         // inputs of the item are complete
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -77,13 +79,15 @@ __global__ void __launch_bounds__((NCW + 1) * 32, MINB) mpk_wavefront_kernel(con
         for (int s = 0; s < STAGES; s++) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], NCW);
+            mbar_init(&claimed[s], 1);
+            mbar_init(&ready[s], 1);
         }
         fence_mbar_init();
     }
     __syncthreads();
 
     if (warp == NCW) {
-        // ===== producer =====
+        // ===== producer: claims items in wavefront order, prefetches their matrix slices =====
         if (lane == 0) {
             for (int it = 0;; ++it) {
                 const int s = it % STAGES;
@@ -94,6 +98,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, MINB) mpk_wavefront_kernel(con
                 int *hdr = reinterpret_cast<int *>(st + Geo::HDR_OFF);
                 if (q >= (unsigned int)P.ntasks) {
                     hdr[4] = -1;  // end marker
+                    mbar_arrive(&claimed[s]);
                     mbar_arrive(&full[s]);
                     break;
                 }
@@ -101,6 +106,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, MINB) mpk_wavefront_kernel(con
                 const nsk_tile t = P.tiles[w.tile];
                 hdr[0] = t.row0; hdr[1] = t.nrows; hdr[2] = t.nz0; hdr[3] = t.nz1;
                 hdr[4] = w.level; hdr[5] = w.tile; hdr[6] = w.glo; hdr[7] = w.ghi;
+                mbar_arrive(&claimed[s]);
                 const int a0 = t.nz0 & ~3, v0 = t.nz0 & ~1, p0 = t.row0 & ~3;
                 const uint32_t cb = (uint32_t)(((t.nz1 - a0) + 3) & ~3) * 4u;
                 const uint32_t vb = (uint32_t)(((t.nz1 - v0) + 1) & ~1) * 8u;
@@ -114,76 +120,73 @@ __global__ void __launch_bounds__((NCW + 1) * 32, MINB) mpk_wavefront_kernel(con
         return;
     }
 
-    // ===== consumers =====
+    if (warp == NCW + 1) {
+        // ===== dependency warp: waits (off the consumers' critical path) until the level l-1 tile groups an
+        // item reads from are complete, then opens the item for the consumers =====
+        for (int it = 0;; ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            mbar_wait(&claimed[s], ph);
+            const int *hdr = reinterpret_cast<const int *>(stage_base + (size_t)s * Geo::BYTES + Geo::HDR_OFF);
+            const int level = hdr[4];
+            if (level > 0) {
+                const int glo = hdr[6], ghi = hdr[7];
+                const int *cnt = P.counters + (size_t)(level - 1) * P.ngroups;
+                const int *need = P.group_size + (size_t)(level - 1) * P.ngroups;
+                for (int g = glo + lane; g <= ghi; g += 32) {
+                    const int want = need[g];
+                    uint32_t spins = 0;
+                    // ld.acquire.gpu = LDG.STRONG.GPU + CCTL.IVALL: also drops this SM's stale L1 lines
+                    while (ld_acquire_gpu(cnt + g) < want) {
+                        __nanosleep(32);
+                        if (++spins > (1u << 24)) __trap();  // protocol bug: fail the launch, never hang
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ready[s]);  // release.cta: orders the acquires above before the consumers
+            if (level < 0) break;
+        }
+        return;
+    }
+
+    // ===== consumer warps: independent of one another (no CTA-wide barrier in the loop) =====
+    constexpr int NCT = NCW * 32;
     const int ctid = tid;
     for (int it = 0;; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&ready[s], ph);
         mbar_wait(&full[s], ph);
         unsigned char *st = stage_base + (size_t)s * Geo::BYTES;
         const int *hdr = reinterpret_cast<const int *>(st + Geo::HDR_OFF);
         const int level = hdr[4];
         if (level < 0) break;
         const int row0 = hdr[0], nrows = hdr[1], nz0 = hdr[2];
-        const int tile = hdr[5], glo = hdr[6], ghi = hdr[7];
-
-        if (level > 0) {
-            // wait until the level-1 tile groups this tile reads from are complete
-            const int *cnt = P.counters + (size_t)(level - 1) * P.ngroups;
-            const int *need = P.group_size + (size_t)(level - 1) * P.ngroups;
-            for (int g = glo + ctid; g <= ghi; g += NCT) {
-                const int want = need[g];
-                uint32_t spins = 0;
-                while (ld_acquire_gpu(cnt + g) < want) {
-                    __nanosleep(64);
-                    if (++spins > (1u << 24)) __trap();  // protocol bug: fail the launch, never hang
-                }
-            }
-            named_bar_sync(1, NCT);
-        }
-
+        const int tile = hdr[5];
         const double *val_s = reinterpret_cast<const double *>(st + Geo::VAL_OFF);
         const int *col_s = reinterpret_cast<const int *>(st + Geo::COL_OFF);
         const int *ptr_s = reinterpret_cast<const int *>(st + Geo::PTR_OFF);
         const int vo = nz0 & ~1, co = nz0 & ~3, po = row0 & ~3;
         const int row_end = P.level_rows[level];
         double *dst = P.levels[level];
-        if (level == 0) {
-            const double *src = P.x;  // constant for the whole launch: read-only path
-            for (int r = ctid; r < nrows; r += NCT) {
-                const int row = row0 + r;
-                if (row >= row_end) continue;
-                const int p = ptr_s[row - po], q = ptr_s[row + 1 - po];
-                double acc = 0.0;
-#pragma unroll 4
-                for (int j = p; j < q; j++) acc = row_op<MULADD>(val_s[j - vo], __ldg(src + col_s[j - co]), acc);
-                dst[row] = acc;
-            }
-        } else {
-            // Written earlier in THIS launch by other CTAs: ordinary (coherent, L1-allocating) loads, never
-            // the .nc path.  Visibility: the acquire above compiles to LDG.STRONG.GPU + CCTL.IVALL (this
-            // SM's L1 is invalidated), the named barrier orders every consumer warp after it, and the
-            // producer of the data fenced at GPU scope before bumping the counter.
-            const double *src = P.levels[level - 1];
-            for (int r = ctid; r < nrows; r += NCT) {
-                const int row = row0 + r;
-                if (row >= row_end) continue;
-                const int p = ptr_s[row - po], q = ptr_s[row + 1 - po];
-                double acc = 0.0;
-#pragma unroll 4
-                for (int j = p; j < q; j++) acc = row_op<MULADD>(val_s[j - vo], src[col_s[j - co]], acc);
-                dst[row] = acc;
-            }
-        }
-        if (level < P.k - 1) {
-            named_bar_sync(1, NCT);  // all rows of the tile are stored (CTA scope)
-            if (ctid == 0) {
-                __threadfence();     // ... and made visible at GPU scope before the counter moves
-                atomicAdd(P.counters + (size_t)level * P.ngroups + tile / WF_GROUP, 1);
-            }
+        // level 0 reads x (constant for the launch: read-only path); level l >= 1 reads what other CTAs wrote
+        // earlier in THIS launch: ordinary coherent loads, ordered by ready[s] after the dependency warp's
+        // acquires (which also invalidated this SM's L1)
+        const double *src = level == 0 ? P.x : P.levels[level - 1];
+        for (int r = ctid; r < nrows; r += NCT) {
+            const int row = row0 + r;
+            if (row >= row_end) continue;
+            const int p = ptr_s[row - po], q = ptr_s[row + 1 - po];
+            dst[row] = level == 0 ? row_chain<MULADD, true>(val_s, col_s, p, q, vo, co, src)
+                                  : row_chain<MULADD, false>(val_s, col_s, p, q, vo, co, src);
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
+        if (lane == 0) {
+            // one release per warp: the group counter counts warps, so nobody waits for the slowest warp here
+            if (level < P.k - 1) red_release_gpu_add(P.counters + (size_t)level * P.ngroups + tile / WF_GROUP, 1);
+            mbar_arrive(&empty[s]);
+        }
     }
 }
 
@@ -250,7 +253,9 @@ struct WaveVariant {
     X(1, 2048, 256, 3, 8, 3)   \
     X(2, 4096, 512, 2, 16, 2)  \
     X(3, 2048, 256, 4, 8, 2)   \
-    X(4, 1024, 128, 3, 4, 5)
+    X(4, 1024, 128, 3, 4, 5)   \
+    X(5, 2048, 256, 2, 8, 3)   \
+    X(6, 4096, 512, 3, 16, 1)
 
 static const WaveVariant g_wvariants[] = {
 #define X(id, t, r, s, w, b) {t, r, s, w, b},
@@ -265,7 +270,7 @@ static wave_fn wave_lookup(int variant, bool muladd, int *smem)
     switch (variant) {
 #define X(id, t, r, s, w, b)                                                       \
     case id:                                                                       \
-        *smem = StageGeom<t, r>::BYTES * s + 2 * s * 8 + 128;                      \
+        *smem = StageGeom<t, r>::BYTES * s + 4 * s * 8 + 128;                      \
         return muladd ? mpk_wavefront_kernel<t, r, s, w, b, true> : mpk_wavefront_kernel<t, r, s, w, b, false>;
         NSK_WAVE_VARIANTS(X)
 #undef X
@@ -357,7 +362,7 @@ static WavePlan *get_plan(nsk_csr_t A, int k, const int *level_rows, const WaveV
         }
     std::vector<int> gsize((size_t)k * ngroups, 0);
     for (int l = 0; l < k; l++)
-        for (int t = 0; t < ntl[l]; t++) gsize[(size_t)l * ngroups + t / WF_GROUP]++;
+        for (int t = 0; t < ntl[l]; t++) gsize[(size_t)l * ngroups + t / WF_GROUP] += V.ncw;  // one report per consumer warp
     WavePlan p;
     p.k = k; p.t_nnz = V.t_nnz; p.t_rows = V.t_rows; p.level_rows = lr; p.slack = slack;
     p.ntasks = (int)tasks.size(); p.ngroups = ngroups; p.D = D;
@@ -382,11 +387,11 @@ static int wave_launch_shape(nsk_ctx_t ctx, int variant, bool muladd, int k, wav
     wave_fn fn = wave_lookup(variant, muladd, &smem);
     NSK_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int per_sm = 0;
-    NSK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, (V.ncw + 1) * 32, smem));
+    NSK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, (V.ncw + 2) * 32, smem));
     if (ctx->opt.spmv_ctas_per_sm > 0) per_sm = std::min(per_sm, (int)ctx->opt.spmv_ctas_per_sm);
     NSK_REQUIRE(ctx, per_sm >= 1, "wavefront kernel does not fit on an SM");
     *grid_max = ctx->prop.multiProcessorCount * per_sm;
-    const double pct = ctx->opt.wave_slack_pct >= 0 ? (double)ctx->opt.wave_slack_pct : 150.0;
+    const double pct = ctx->opt.wave_slack_pct >= 0 ? (double)ctx->opt.wave_slack_pct : 100.0;
     *slack = (int)((pct / 100.0) * (double)(*grid_max) * V.stages / (double)k + 0.999);
     *fn_out = fn;
     *smem_out = smem;
@@ -439,7 +444,7 @@ int nsk_mpk_wavefront(nsk_csr_t A, int k, const double *d_x, double *const *d_le
         P.level_rows[l] = l < k ? plan->level_rows[l] : 0;
     }
     P.k = k;
-    fn<<<grid, (V.ncw + 1) * 32, smem, ctx->stream>>>(P);
+    fn<<<grid, (V.ncw + 2) * 32, smem, ctx->stream>>>(P);
     ctx->launches++;
     NSK_CUDA(ctx, cudaGetLastError());
     return NSK_OK;

@@ -106,6 +106,11 @@ __device__ __forceinline__ int ld_acquire_gpu(const int *p)
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// Release-ordered increment without a return value (SASS RED): publishes every write that happens-before it.
+__device__ __forceinline__ void red_release_gpu_add(int *p, int v)
+{
+    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 // Coherent (L2) load of data another CTA of the same grid has just published.
 __device__ __forceinline__ double ld_cg_f64(const double *p)
 {

@@ -1,0 +1,136 @@
+// shim_spmv.cpp -- the reference's SpMV.h entry points, implemented on the C ABI (include/nsk.h).
+//
+// Built into libnsk_spmvshim.so.  A reference driver (mpk/2SpMV.cpp ...) linked against this library
+// instead of mpk/SpMV.cpp runs unchanged on the GPU (INTEGRATION.md shows the link line).
+//
+// Ownership follows the reference: the caller owns the matrix (std::vector storage) and
+// the host vectors; kernels are synchronous and allocate nothing the caller can see.  The device copy
+// of an operator is cached, keyed on the identity of the caller's arrays, so the upload happens once
+// per matrix like the reference's one-time COO2CSR.  Errors: the reference's functions are `void` and
+// cannot fail; here a failure (no GPU, out of memory) prints the library's message and aborts -- there
+// is NO CPU fallback.
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "nsk.h"
+#include "nsk_spmv_compat.hpp"
+
+namespace {
+
+std::mutex g_mu;
+nsk_ctx_t g_ctx = nullptr;
+
+[[noreturn]] void die(const char *what, int status)
+{
+    std::fprintf(stderr, "nsk shim: %s failed: %s (%s)\n", what, nsk_strerror(status), nsk_last_error(g_ctx));
+    std::abort();
+}
+
+nsk_ctx_t ctx()
+{
+    if (!g_ctx) {
+        const char *dev = std::getenv("NSK_DEVICE");
+        int s = nsk_ctx_create(dev ? std::atoi(dev) : 0, &g_ctx);
+        if (s != NSK_OK) die("nsk_ctx_create", s);
+    }
+    return g_ctx;
+}
+
+typedef std::tuple<const void *, const void *, const void *, int, long long> Key;
+std::map<Key, nsk_csr_t> g_csr;
+std::map<Key, nsk_bcsr4_t> g_bcsr;
+
+nsk_csr_t device_csr(csrmatrix &A)
+{
+    // the reference leaves A.nnz at the COO count even when duplicates were dropped (mpk/utils.cpp:100):
+    // the true count is ptrow[n]
+    const long long nnz = A.ptrow.empty() ? 0 : (long long)A.ptrow[A.n];
+    Key k(A.ptrow.data(), A.indcol.data(), A.coef.data(), A.n, nnz);
+    auto it = g_csr.find(k);
+    if (it != g_csr.end()) return it->second;
+    nsk_csr_t h = nullptr;
+    int s = nsk_csr_create(ctx(), A.n, A.n, nnz, A.ptrow.data(), A.indcol.data(), A.coef.data(), &h);
+    if (s != NSK_OK) die("nsk_csr_create", s);
+    g_csr[k] = h;
+    return h;
+}
+
+nsk_bcsr4_t device_bcsr(const bcsr4x4_matrix &B)
+{
+    const long long nblk = (long long)B.indcol.size();
+    Key k(B.ptrow.data(), B.indcol.data(), B.coef.data(), B.nrows, nblk);
+    auto it = g_bcsr.find(k);
+    if (it != g_bcsr.end()) return it->second;
+    nsk_bcsr4_t h = nullptr;
+    int s = nsk_bcsr4_create(ctx(), B.nrows, nblk, B.ptrow.data(), B.indcol.data(), B.coef.data(), &h);
+    if (s != NSK_OK) die("nsk_bcsr4_create", s);
+    g_bcsr[k] = h;
+    return h;
+}
+
+void spmv(double *y, const double *x, csrmatrix &A, nsk_mode mode)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    int s = nsk_spmv(device_csr(A), x, y, mode, NSK_HOST);
+    if (s != NSK_OK) die("nsk_spmv", s);
+}
+
+void spmv_b(double *y, const double *x, const bcsr4x4_matrix &B, nsk_mode mode)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    int s = nsk_spmv_bcsr4(device_bcsr(B), x, y, mode, NSK_HOST);
+    if (s != NSK_OK) die("nsk_spmv_bcsr4", s);
+}
+
+void spm2v(double *z, double *y, const double *x, csrmatrix &A, nsk_mode mode)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    double *levels[2] = {y, z};
+    int s = nsk_mpk(device_csr(A), 2, x, levels, mode, NSK_HOST);
+    if (s != NSK_OK) die("nsk_mpk", s);
+}
+
+}  // namespace
+
+void SpMV_CSR(double *y, double *x, csrmatrix &A) { spmv(y, x, A, NSK_EXACT_MULADD); }
+void SpMV_CSR_OPT(double *y, double *x, csrmatrix &A) { spmv(y, x, A, NSK_EXACT_FMA); }
+void SpMV_CSR_FMA(double *y, double *x, csrmatrix &A) { spmv(y, x, A, NSK_EXACT_FMA); }
+void SpMV_CSR_AVX2(double *y, double *x, csrmatrix &A) { spmv(y, x, A, NSK_FAST); }
+
+void SpMV_BCSR(double *y, const double *x, const bcsr4x4_matrix &A) { spmv_b(y, x, A, NSK_EXACT_MULADD); }
+void SpMV_BCSR_OPT(double *y, const double *x, const bcsr4x4_matrix &A) { spmv_b(y, x, A, NSK_EXACT_FMA); }
+void SpMV_BCSR_FMA(double *y, const double *x, const bcsr4x4_matrix &A) { spmv_b(y, x, A, NSK_EXACT_FMA); }
+void SpMV_BCSR_AVX2(double *y, const double *x, const bcsr4x4_matrix &A) { spmv_b(y, x, A, NSK_FAST); }
+
+// Same contract as the reference's schedule builder: entry ia gets the end of row indcol[ia] the first
+// time that column is met in row-major order, its beginning afterwards.  The GPU kernels do not read it.
+void Generate1stlayer(std::vector<int> &ptrowend1, csrmatrix &A)
+{
+    const int n = A.n;
+    const int nnz = A.ptrow.empty() ? 0 : A.ptrow[n];
+    std::vector<char> seen(n > 0 ? n : 1, 0);
+    ptrowend1.assign(A.nnz > nnz ? A.nnz : nnz, 0);
+    for (int ia = 0; ia < nnz; ia++) {
+        const int j = A.indcol[ia];
+        ptrowend1[ia] = seen[j] ? A.ptrow[j] : A.ptrow[j + 1];
+        seen[j] = 1;
+    }
+}
+
+void SpM2V_CSR(double *z, double *y, double *x, csrmatrix &A, std::vector<int> &) { spm2v(z, y, x, A, NSK_EXACT_MULADD); }
+void SpM2V_CSR_OPT(double *z, double *y, double *x, csrmatrix &A, std::vector<int> &) { spm2v(z, y, x, A, NSK_EXACT_FMA); }
+void SpM2V_CSR_AVX2(double *z, double *y, double *x, csrmatrix &A, std::vector<int> &) { spm2v(z, y, x, A, NSK_FAST); }
+
+extern "C" void nsk_shim_reset(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto &kv : g_csr) nsk_csr_destroy(kv.second);
+    for (auto &kv : g_bcsr) nsk_bcsr4_destroy(kv.second);
+    g_csr.clear();
+    g_bcsr.clear();
+    if (g_ctx) nsk_ctx_destroy(g_ctx);
+    g_ctx = nullptr;
+}

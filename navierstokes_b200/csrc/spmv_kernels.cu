@@ -206,9 +206,7 @@ __global__ void __launch_bounds__((NCW + 1) * 32, MINB) spmv_stream_kernel(const
                     const int row = row0 + r;
                     if (row < P.row_begin || row >= P.row_end) continue;
                     const int p = ptr_s[row - po], q = ptr_s[row + 1 - po];
-                    double acc = 0.0;
-#pragma unroll 4
-                    for (int j = p; j < q; j++) acc = row_op<MULADD>(val_s[j - vo], __ldg(P.x + col_s[j - co]), acc);
+                    const double acc = row_chain<MULADD, true>(val_s, col_s, p, q, vo, co, P.x);
                     P.y[row] = acc;
                     if (P.dot_w) dot_acc = __fma_rn(P.dot_w[row], acc, dot_acc);
                 }

@@ -13,6 +13,33 @@ __device__ __forceinline__ double row_op(double a, double x, double acc)
     return __fma_rn(a, x, acc);                          // one rounding (vfmadd231sd on the CPU)
 }
 
+// One row of y = A x out of a shared-memory stage: nonzeros j in [p,q) in storage order.
+// The gathers of up to 8 consecutive nonzeros are issued together (predicated) before the dependent
+// multiply-add chain starts, so a short row (stencils: 5-7 entries) costs ONE memory round trip instead
+// of one per unrolled-loop remainder iteration; the chain itself stays strictly sequential.
+// NC: x is constant for the whole launch (read-only path) vs written earlier in this launch (coherent).
+template <bool MULADD, bool NC>
+__device__ __forceinline__ double row_chain(const double *val_s, const int *col_s, int p, int q, int vo, int co,
+                                            const double *src)
+{
+    double acc = 0.0;
+    for (int j0 = p; j0 < q; j0 += 8) {
+        double xv[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int j = j0 + u;
+            if (j < q) {
+                const int c = col_s[j - co];
+                xv[u] = NC ? __ldg(src + c) : src[c];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+            if (j0 + u < q) acc = row_op<MULADD>(val_s[j0 + u - vo], xv[u], acc);  // coefficient straight from smem
+    }
+    return acc;
+}
+
 // -----------------------------------------------------------------------------------------------
 // shared-memory stage of one tile: [coef slice | indcol slice | ptrow slice | header]
 // -----------------------------------------------------------------------------------------------

@@ -83,7 +83,7 @@ def main():
         ctx.set_option("spmv_ctas_per_sm", 0)
         ctx.set_option("stream_variant", 0)
     # matrix powers
-    for k in (2, 4, 8):
+    for k in (2, 4):
         lv = [ctx.empty(A.n) for _ in range(k)]
         ctx.set_option("mpk_kernel", 1)
         dA.mpk(k, x, lv, 0)
@@ -93,18 +93,23 @@ def main():
         print(f"mpk k={k} levels           : {ms:8.4f} ms  B_mpk rate {Bk/ms/1e6:8.1f} GB/s ({Bk/ms/1e6/peak:5.3f}), "
               f"SpMV-equivalent {k*B/ms/1e6:8.1f} GB/s", flush=True)
         ctx.set_option("mpk_kernel", 2)
-        for wv in range(5):
+        ctx.set_option("wave_l2_pct", 400)  # never refuse in the sweep: we want to see the cliff
+        for wv in (0, 1, 2, 3, 5, 6):
             ctx.set_option("wave_variant", wv)
-            for cps in (0, 2, 3):
-                ctx.set_option("spmv_ctas_per_sm", cps)
+            for slack in (50, 100, 150, 200):
+                ctx.set_option("wave_slack_pct", slack)
                 for l in lv:
                     ctx.lib.nsk_memset0(ctx.h, l.ptr, 8 * A.n)
+                l0 = ctx.launch_count
                 dA.mpk(k, x, lv, 0)
+                fused = (ctx.launch_count - l0) == 1
                 same = all(np.array_equal(lv[i].to_host().view(np.int64), ref[i].view(np.int64)) for i in range(k))
                 ms = timed(ctx, lambda: dA.mpk(k, x, lv, 0), max(4, args.reps // 4))
-                print(f"mpk k={k} wavefront v{wv} cps={cps or 'max'}: {ms:8.4f} ms  B_mpk rate {Bk/ms/1e6:8.1f} GB/s "
-                      f"({Bk/ms/1e6/peak:5.3f}), SpMV-equivalent {k*B/ms/1e6:8.1f} GB/s  {'OK' if same else 'MISMATCH'}",
-                      flush=True)
+                print(f"mpk k={k} wavefront v{wv} slack={slack:3d}% {'fused' if fused else 'LEVELS'}: {ms:8.4f} ms  B_mpk rate "
+                      f"{Bk/ms/1e6:8.1f} GB/s ({Bk/ms/1e6/peak:5.3f}), SpMV-equivalent {k*B/ms/1e6:8.1f} GB/s  "
+                      f"{'OK' if same else 'MISMATCH'}", flush=True)
+        ctx.set_option("wave_slack_pct", -1)
+        ctx.set_option("wave_l2_pct", 0)
         ctx.set_option("spmv_ctas_per_sm", 0)
         ctx.set_option("wave_variant", 0)
 
