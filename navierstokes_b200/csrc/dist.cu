@@ -162,7 +162,8 @@ int nsk_dist_mpk(nsk_csr_t A, int k, const double *d_x, double *const *d_levels,
     int level_rows[NSK_MAX_K];
     for (int l = 0; l < k; l++) level_rows[l] = D->ring_start[k - l];
     int sel = (int)ctx->opt.mpk_kernel;
-    if (sel == 2 && k > 1 && nsk_mpk_wavefront_applicable(A, k)) {
+    if (sel == 0) sel = 2;
+    if (sel == 2 && k > 1 && mode != NSK_FAST && nsk_mpk_wavefront_applicable(A, k)) {
         int s = nsk_mpk_wavefront(A, k, d_x, d_levels, mode, level_rows);
         if (s != NSK_ERR_UNSUPPORTED) return s;
     }

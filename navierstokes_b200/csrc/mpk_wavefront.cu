@@ -23,8 +23,9 @@
 //   * a dedicated dependency warp acquires, for each claimed item (l, t), l >= 1, the completion counters
 //     of the level l-1 tile GROUPS covering t's column range (ld.acquire.gpu, bounded spin) and then opens
 //     the item for the consumer warps through an mbarrier -- the wait overlaps the previous item's work;
-//   * consumer warps gather with ordinary coherent loads; when a warp has stored its rows it bumps the
-//     group counter with one red.release.gpu (counters count warps: no CTA-wide barrier in the loop).
+//   * consumer warps gather with ordinary coherent loads and, when their rows are stored, only arrive on
+//     a CTA-local mbarrier; a publisher thread turns that into one red.release.gpu on the group counter
+//     (the GPU-scope fence costs ~1 us -- measured 23 % of all stall samples when consumers paid it).
 //   * per-row arithmetic is the same sequential chain as nsk_spmv, so every level is bit-identical
 //     to k separate products (tests/test_spmv_gpu.py::test_mpk_wavefront_*).
 #include <algorithm>
@@ -39,7 +40,8 @@ std::vector<int> &nsk_csr_host_ptrow(nsk_csr_t A);
 
 constexpr int WF_GROUP = 16;  // tiles per completion counter
 
-struct WaveTask {
+struct WaveTask {               // 32 bytes: everything a claim needs in one go (two 16-byte loads)
+    int row0, nrows, nz0, nz1;  // the tile (copied from the tiling so a claim costs no second lookup)
     int level, tile, glo, ghi;  // inputs: groups [glo, ghi] of level-1 must be complete
 };
 
@@ -61,7 +63,7 @@ struct WaveParams {
 };
 
 template <int T_NNZ, int T_ROWS, int STAGES, int NCW, int MINB, bool MULADD>
-__global__ void __launch_bounds__((NCW + 2) * 32, MINB) mpk_wavefront_kernel(const WaveParams P)
+__global__ void __launch_bounds__((NCW + 3) * 32, MINB) mpk_wavefront_kernel(const WaveParams P)
 {
     using Geo = StageGeom<T_NNZ, T_ROWS>;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -70,6 +72,7 @@ __global__ void __launch_bounds__((NCW + 2) * 32, MINB) mpk_wavefront_kernel(con
     uint64_t *empty = full + STAGES;                                            // all consumer warps are done with it
     uint64_t *claimed = empty + STAGES;                                         // header written (producer -> dependency warp)
     uint64_t *ready = claimed + STAGES;                                         // inputs of the item are complete
+    uint64_t *done = ready + STAGES;                                            // all consumer warps stored their rows
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -78,43 +81,51 @@ __global__ void __launch_bounds__((NCW + 2) * 32, MINB) mpk_wavefront_kernel(con
     if (tid == 0) {
         for (int s = 0; s < STAGES; s++) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], NCW);
+            mbar_init(&empty[s], 1);      // publisher: stage header read, consumers finished
             mbar_init(&claimed[s], 1);
             mbar_init(&ready[s], 1);
+            mbar_init(&done[s], NCW);
         }
         fence_mbar_init();
     }
     __syncthreads();
 
     if (warp == NCW) {
-        // ===== producer: claims items in wavefront order, prefetches their matrix slices =====
+        // ===== producer: claims items in wavefront order, prefetches their matrix slices.  The claim
+        // (one L2 atomic + one dependent 32-byte load, ~1.5 us under load) is taken ONE ITEM AHEAD, in the
+        // shadow of the wait for a free stage: with the claim inside the stage turn-around the whole
+        // sweep ran at ~0.5 item/us per CTA whatever the geometry (measured, profiles/). =====
         if (lane == 0) {
+            const int4 *tasks4 = reinterpret_cast<const int4 *>(P.tasks);
+            unsigned int q = atomicAdd(P.next, 1u);
+            int4 ta = make_int4(0, 0, 0, 0), tb = make_int4(-1, 0, 0, 0);
+            if (q < (unsigned int)P.ntasks) { ta = tasks4[2 * (size_t)q]; tb = tasks4[2 * (size_t)q + 1]; }
             for (int it = 0;; ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
-                const unsigned int q = atomicAdd(P.next, 1u);
                 unsigned char *st = stage_base + (size_t)s * Geo::BYTES;
                 int *hdr = reinterpret_cast<int *>(st + Geo::HDR_OFF);
-                if (q >= (unsigned int)P.ntasks) {
-                    hdr[4] = -1;  // end marker
-                    mbar_arrive(&claimed[s]);
+                hdr[0] = ta.x; hdr[1] = ta.y; hdr[2] = ta.z; hdr[3] = ta.w;
+                hdr[4] = tb.x; hdr[5] = tb.y; hdr[6] = tb.z; hdr[7] = tb.w;
+                mbar_arrive(&claimed[s]);
+                if (tb.x < 0) {  // end marker
                     mbar_arrive(&full[s]);
                     break;
                 }
-                const WaveTask w = P.tasks[q];
-                const nsk_tile t = P.tiles[w.tile];
-                hdr[0] = t.row0; hdr[1] = t.nrows; hdr[2] = t.nz0; hdr[3] = t.nz1;
-                hdr[4] = w.level; hdr[5] = w.tile; hdr[6] = w.glo; hdr[7] = w.ghi;
-                mbar_arrive(&claimed[s]);
-                const int a0 = t.nz0 & ~3, v0 = t.nz0 & ~1, p0 = t.row0 & ~3;
-                const uint32_t cb = (uint32_t)(((t.nz1 - a0) + 3) & ~3) * 4u;
-                const uint32_t vb = (uint32_t)(((t.nz1 - v0) + 1) & ~1) * 8u;
-                const uint32_t pb = (uint32_t)(((t.row0 + t.nrows + 1 - p0) + 3) & ~3) * 4u;
+                const int row0 = ta.x, nrows = ta.y, nz0 = ta.z, nz1 = ta.w;
+                const int a0 = nz0 & ~3, v0 = nz0 & ~1, p0 = row0 & ~3;
+                const uint32_t cb = (uint32_t)(((nz1 - a0) + 3) & ~3) * 4u;
+                const uint32_t vb = (uint32_t)(((nz1 - v0) + 1) & ~1) * 8u;
+                const uint32_t pb = (uint32_t)(((row0 + nrows + 1 - p0) + 3) & ~3) * 4u;
                 mbar_arrive_expect_tx(&full[s], cb + vb + pb);
                 bulk_g2s(st + Geo::PTR_OFF, P.ptrow + p0, pb, &full[s]);
                 if (cb) bulk_g2s(st + Geo::COL_OFF, P.indcol + a0, cb, &full[s]);
                 if (vb) bulk_g2s(st + Geo::VAL_OFF, P.coef + v0, vb, &full[s]);
+                // next claim, overlapped with the wait above on the next trip
+                q = atomicAdd(P.next, 1u);
+                tb.x = -1;
+                if (q < (unsigned int)P.ntasks) { ta = tasks4[2 * (size_t)q]; tb = tasks4[2 * (size_t)q + 1]; }
             }
         }
         return;
@@ -150,6 +161,27 @@ __global__ void __launch_bounds__((NCW + 2) * 32, MINB) mpk_wavefront_kernel(con
         return;
     }
 
+    if (warp == NCW + 2) {
+        // ===== publisher: makes a finished item visible to the rest of the GPU.  The GPU-scope release
+        // (fence + RED, ~1 us) is paid here, off the consumers' path: consumers only arrive on done[s]
+        // (release.cta); this thread's acquire of done[s] followed by red.release.gpu is cumulative over
+        // their stores. =====
+        if (lane == 0) {
+            for (int it = 0;; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&claimed[s], ph);
+                const int *hdr = reinterpret_cast<const int *>(stage_base + (size_t)s * Geo::BYTES + Geo::HDR_OFF);
+                const int level = hdr[4], tile = hdr[5];
+                if (level < 0) break;
+                mbar_wait(&done[s], ph);
+                mbar_arrive(&empty[s]);  // the producer may refill the stage while we publish
+                if (level < P.k - 1) red_release_gpu_add(P.counters + (size_t)level * P.ngroups + tile / WF_GROUP, 1);
+            }
+        }
+        return;
+    }
+
     // ===== consumer warps: independent of one another (no CTA-wide barrier in the loop) =====
     constexpr int NCT = NCW * 32;
     const int ctid = tid;
@@ -163,7 +195,6 @@ __global__ void __launch_bounds__((NCW + 2) * 32, MINB) mpk_wavefront_kernel(con
         const int level = hdr[4];
         if (level < 0) break;
         const int row0 = hdr[0], nrows = hdr[1], nz0 = hdr[2];
-        const int tile = hdr[5];
         const double *val_s = reinterpret_cast<const double *>(st + Geo::VAL_OFF);
         const int *col_s = reinterpret_cast<const int *>(st + Geo::COL_OFF);
         const int *ptr_s = reinterpret_cast<const int *>(st + Geo::PTR_OFF);
@@ -182,11 +213,7 @@ __global__ void __launch_bounds__((NCW + 2) * 32, MINB) mpk_wavefront_kernel(con
                                   : row_chain<MULADD, false>(val_s, col_s, p, q, vo, co, src);
         }
         __syncwarp();
-        if (lane == 0) {
-            // one release per warp: the group counter counts warps, so nobody waits for the slowest warp here
-            if (level < P.k - 1) red_release_gpu_add(P.counters + (size_t)level * P.ngroups + tile / WF_GROUP, 1);
-            mbar_arrive(&empty[s]);
-        }
+        if (lane == 0) mbar_arrive(&done[s]);  // release.cta; no GPU-scope fence on this path
     }
 }
 
@@ -249,12 +276,12 @@ struct WaveVariant {
 };
 //                 T_NNZ T_ROWS STAGES NCW MINB
 #define NSK_WAVE_VARIANTS(X) \
-    X(0, 2048, 256, 2, 8, 4)   \
-    X(1, 2048, 256, 3, 8, 3)   \
+    X(0, 2048, 256, 2, 8, 3)   \
+    X(1, 2048, 256, 3, 8, 2)   \
     X(2, 4096, 512, 2, 16, 2)  \
-    X(3, 2048, 256, 4, 8, 2)   \
+    X(3, 2048, 256, 2, 8, 4)   \
     X(4, 1024, 128, 3, 4, 5)   \
-    X(5, 2048, 256, 2, 8, 3)   \
+    X(5, 1024, 128, 2, 4, 6)   \
     X(6, 4096, 512, 3, 16, 1)
 
 static const WaveVariant g_wvariants[] = {
@@ -270,7 +297,7 @@ static wave_fn wave_lookup(int variant, bool muladd, int *smem)
     switch (variant) {
 #define X(id, t, r, s, w, b)                                                       \
     case id:                                                                       \
-        *smem = StageGeom<t, r>::BYTES * s + 4 * s * 8 + 128;                      \
+        *smem = StageGeom<t, r>::BYTES * s + 5 * s * 8 + 128;                      \
         return muladd ? mpk_wavefront_kernel<t, r, s, w, b, true> : mpk_wavefront_kernel<t, r, s, w, b, false>;
         NSK_WAVE_VARIANTS(X)
 #undef X
@@ -282,8 +309,9 @@ int nsk_ensure_tiling_public(nsk_csr_t A, int t_nnz, int t_rows);  // spmv_kerne
 
 static int wave_variant(nsk_ctx_t ctx)
 {
-    int v = (int)ctx->opt.wave_variant;
-    if (v < 0 || v >= g_nwvariants) v = 0;
+    // option value 0 = default; n >= 1 selects table entry n - 1
+    int v = (int)ctx->opt.wave_variant - 1;
+    if (v < 0 || v >= g_nwvariants) v = 6;  // measured best on 256^3 (profiles/r01_sweep_mpk_wavefront_claimahead.txt)
     return v;
 }
 
@@ -358,11 +386,14 @@ static WavePlan *get_plan(nsk_csr_t A, int k, const int *level_rows, const WaveV
         for (int l = k - 1; l >= 0; l--) {
             const int t = tau - l * D;
             if (t < 0 || t >= ntl[l]) continue;
-            tasks.push_back(WaveTask{l, t, glo[t], ghi[t]});
+            {
+                const nsk_tile &tl = T.h_tiles[t];
+                tasks.push_back(WaveTask{tl.row0, tl.nrows, tl.nz0, tl.nz1, l, t, glo[t], ghi[t]});
+            }
         }
     std::vector<int> gsize((size_t)k * ngroups, 0);
     for (int l = 0; l < k; l++)
-        for (int t = 0; t < ntl[l]; t++) gsize[(size_t)l * ngroups + t / WF_GROUP] += V.ncw;  // one report per consumer warp
+        for (int t = 0; t < ntl[l]; t++) gsize[(size_t)l * ngroups + t / WF_GROUP]++;
     WavePlan p;
     p.k = k; p.t_nnz = V.t_nnz; p.t_rows = V.t_rows; p.level_rows = lr; p.slack = slack;
     p.ntasks = (int)tasks.size(); p.ngroups = ngroups; p.D = D;
@@ -387,12 +418,12 @@ static int wave_launch_shape(nsk_ctx_t ctx, int variant, bool muladd, int k, wav
     wave_fn fn = wave_lookup(variant, muladd, &smem);
     NSK_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int per_sm = 0;
-    NSK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, (V.ncw + 2) * 32, smem));
+    NSK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, (V.ncw + 3) * 32, smem));
     if (ctx->opt.spmv_ctas_per_sm > 0) per_sm = std::min(per_sm, (int)ctx->opt.spmv_ctas_per_sm);
     NSK_REQUIRE(ctx, per_sm >= 1, "wavefront kernel does not fit on an SM");
     *grid_max = ctx->prop.multiProcessorCount * per_sm;
     const double pct = ctx->opt.wave_slack_pct >= 0 ? (double)ctx->opt.wave_slack_pct : 100.0;
-    *slack = (int)((pct / 100.0) * (double)(*grid_max) * V.stages / (double)k + 0.999);
+    *slack = (int)((pct / 100.0) * (double)(*grid_max) * (V.stages + 1) / (double)k + 0.999);  // +1: the pre-claimed item
     *fn_out = fn;
     *smem_out = smem;
     return NSK_OK;
@@ -444,7 +475,7 @@ int nsk_mpk_wavefront(nsk_csr_t A, int k, const double *d_x, double *const *d_le
         P.level_rows[l] = l < k ? plan->level_rows[l] : 0;
     }
     P.k = k;
-    fn<<<grid, (V.ncw + 2) * 32, smem, ctx->stream>>>(P);
+    fn<<<grid, (V.ncw + 3) * 32, smem, ctx->stream>>>(P);
     ctx->launches++;
     NSK_CUDA(ctx, cudaGetLastError());
     return NSK_OK;

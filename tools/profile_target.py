@@ -17,7 +17,7 @@ ap.add_argument("--grid", type=int, default=256)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--k", type=int, default=4)
 ap.add_argument("--slack", type=int, default=-1)
-ap.add_argument("--wave-variant", type=int, default=0)
+ap.add_argument("--wave-variant", type=int, default=0, help="0 = default, n = table entry n-1")
 args = ap.parse_args()
 A = matgen.laplace3d_7pt(args.grid)
 ctx = nsk.Context(0)

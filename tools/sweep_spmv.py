@@ -94,8 +94,8 @@ def main():
               f"SpMV-equivalent {k*B/ms/1e6:8.1f} GB/s", flush=True)
         ctx.set_option("mpk_kernel", 2)
         ctx.set_option("wave_l2_pct", 400)  # never refuse in the sweep: we want to see the cliff
-        for wv in (0, 1, 2, 3, 5, 6):
-            ctx.set_option("wave_variant", wv)
+        for wv in (0, 1, 2, 3, 4, 5, 6):
+            ctx.set_option("wave_variant", wv + 1)
             for slack in (50, 100, 150, 200):
                 ctx.set_option("wave_slack_pct", slack)
                 for l in lv:
