@@ -77,12 +77,7 @@ NSK_API int nsk_csr_create(nsk_ctx_t ctx, int n, int n_cols, int64_t nnz, const 
     }
     nsk_csr_host_ptrow(A).assign(ptrow, ptrow + n + 1);
     nsk_wave_set_block_extents(A, ptrow, indcol);
-    int s = nsk_build_tiling(A, ptrow);
-    if (s != NSK_OK) {
-        nsk_csr_destroy(A);
-        return s;
-    }
-    *out = A;
+    *out = A;  // tile tables are built on first use (a distributed slab registers its breaks first)
     return NSK_OK;
 }
 
@@ -99,7 +94,7 @@ NSK_API int nsk_csr_destroy(nsk_csr_t A)
     if (A->d_ptrow) cudaFree(A->d_ptrow);
     if (A->d_indcol) cudaFree(A->d_indcol);
     if (A->d_coef) cudaFree(A->d_coef);
-    if (A->tiling.d_tiles) cudaFree(A->tiling.d_tiles);
+    nsk_free_tilings(A);
     if (A->d_flags) cudaFree(A->d_flags);
     {
         std::lock_guard<std::mutex> lk(g_host_ptrow_mu);

@@ -14,6 +14,7 @@ int nsk_mpk_levels(nsk_csr_t A, int k, const double *d_x, double *const *d_level
 int nsk_mpk_wavefront(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode,
                       const int *level_rows);  // mpk_wavefront.cu
 bool nsk_mpk_wavefront_applicable(nsk_csr_t A, int k);
+void nsk_wave_set_block_extents(nsk_csr_t A, const int *ptrow, const int *indcol);
 int nsk_comm_rank(nsk_ctx_t ctx);
 int nsk_comm_size(nsk_ctx_t ctx);
 
@@ -65,6 +66,23 @@ NSK_API int nsk_csr_create_dist(nsk_ctx_t ctx, nsk_plan_t plan, nsk_csr_t *out)
     nsk_csr_t A = nullptr;
     NSK_TRY(nsk_csr_create(ctx, n_rows, n_cols, (int64_t)plan->local_cols.size(), plan->ptr.data(),
                            plan->local_cols.data(), plan->vals.data(), &A));
+    // Tiles must not straddle a jump in global row order, and the fused matrix-powers kernel wants to know
+    // where each stored row sits in that order (ghost rings are stored AFTER the owned rows but belong
+    // below / above them): record both, then redo the column extents in rank space.
+    {
+        const int n_owned = plan->own_end - plan->own_begin;
+        std::vector<int> gid(n_rows);
+        for (int i = 0; i < n_rows; i++) gid[i] = i < n_owned ? plan->own_begin + i : plan->ghost_gids[i - n_owned];
+        std::vector<int> order(n_rows);
+        for (int i = 0; i < n_rows; i++) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](int a, int b) { return gid[a] < gid[b]; });
+        A->row_rank.assign(n_rows, 0);
+        for (int r = 0; r < n_rows; r++) A->row_rank[order[r]] = r;
+        A->breaks.clear();
+        for (int i = 1; i < n_rows; i++)
+            if (gid[i] != gid[i - 1] + 1) A->breaks.push_back(i);
+        nsk_wave_set_block_extents(A, plan->ptr.data(), plan->local_cols.data());
+    }
     nsk_dist_s *D = new nsk_dist_s();
     D->n_owned = plan->own_end - plan->own_begin;
     D->depth = plan->depth;
@@ -163,7 +181,7 @@ int nsk_dist_mpk(nsk_csr_t A, int k, const double *d_x, double *const *d_levels,
     for (int l = 0; l < k; l++) level_rows[l] = D->ring_start[k - l];
     int sel = (int)ctx->opt.mpk_kernel;
     if (sel == 0) sel = 2;
-    if (sel == 2 && k > 1 && mode != NSK_FAST && nsk_mpk_wavefront_applicable(A, k)) {
+    if (sel == 2 && k > 1 && nsk_mpk_wavefront_applicable(A, k)) {
         int s = nsk_mpk_wavefront(A, k, d_x, d_levels, mode, level_rows);
         if (s != NSK_ERR_UNSUPPORTED) return s;
     }

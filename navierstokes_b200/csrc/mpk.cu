@@ -41,7 +41,7 @@ int nsk_mpk_device(nsk_csr_t A, int k, const double *d_x, double *const *d_level
     if (A->dist) return nsk_dist_mpk(A, k, d_x, d_levels, mode);
     int sel = (int)ctx->opt.mpk_kernel;
     if (sel == 0) sel = 2;  // fused wavefront kernel whenever the pattern allows it
-    if (sel == 2 && k > 1 && mode != NSK_FAST && nsk_mpk_wavefront_applicable(A, k)) {
+    if (sel == 2 && k > 1 && nsk_mpk_wavefront_applicable(A, k)) {
         int s = nsk_mpk_wavefront(A, k, d_x, d_levels, mode, nullptr);
         if (s != NSK_ERR_UNSUPPORTED) return s;
     }

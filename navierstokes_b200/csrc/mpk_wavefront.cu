@@ -224,6 +224,7 @@ struct WavePlan {
     int k = 0;
     int t_nnz = 0, t_rows = 0;
     int slack = 0;
+    bool rejected = false;
     std::vector<int> level_rows;
     int ntasks = 0, ngroups = 0, D = 0;
     WaveTask *d_tasks = nullptr;
@@ -233,29 +234,40 @@ struct WavePlan {
 
 struct WaveState {
     std::vector<WavePlan> plans;
-    std::vector<int> blk_min, blk_max;  // per 32-row block: min / max column (filled at create)
+    // column extents per row block (<= 32 rows, never straddling a break), in GLOBAL-ORDER rank space
+    std::vector<int> blk_row0, blk_min, blk_max;
 };
 
 #include <map>
 static std::map<nsk_csr_t, WaveState> g_wave;
 
+// Called at create time (and again by the distributed layer once breaks / row_rank are known).
+// Columns >= A->n are ghost entries of x that only level 0 reads: they create no dependency.
 void nsk_wave_set_block_extents(nsk_csr_t A, const int *ptrow, const int *indcol)
 {
     WaveState &S = g_wave[A];
+    S.plans.clear();
+    S.blk_row0.clear(); S.blk_min.clear(); S.blk_max.clear();
     const int n = A->n;
-    const int nb = (n + 31) / 32;
-    S.blk_min.assign(nb, INT32_MAX);
-    S.blk_max.assign(nb, -1);
-    for (int b = 0; b < nb; b++) {
-        const int r0 = b * 32, r1 = std::min(n, r0 + 32);
+    const bool ranked = !A->row_rank.empty();
+    size_t bi = 0;
+    int r = 0;
+    while (r < n) {
+        while (bi < A->breaks.size() && A->breaks[bi] <= r) bi++;
+        const int seg_end = bi < A->breaks.size() ? std::min(n, A->breaks[bi]) : n;
+        const int r1 = std::min(seg_end, r + 32);
         int mn = INT32_MAX, mx = -1;
-        for (int j = ptrow[r0]; j < ptrow[r1]; j++) {
-            const int c = indcol[j];
+        for (int j = ptrow[r]; j < ptrow[r1]; j++) {
+            int c = indcol[j];
+            if (c >= n) continue;
+            if (ranked) c = A->row_rank[c];
             mn = c < mn ? c : mn;
             mx = c > mx ? c : mx;
         }
-        S.blk_min[b] = mn;
-        S.blk_max[b] = mx;
+        S.blk_row0.push_back(r);
+        S.blk_min.push_back(mn);
+        S.blk_max.push_back(mx);
+        r = r1;
     }
 }
 
@@ -305,7 +317,6 @@ static wave_fn wave_lookup(int variant, bool muladd, int *smem)
     return nullptr;
 }
 
-int nsk_ensure_tiling_public(nsk_csr_t A, int t_nnz, int t_rows);  // spmv_kernels.cu
 
 static int wave_variant(nsk_ctx_t ctx)
 {
@@ -326,74 +337,83 @@ static WavePlan *get_plan(nsk_csr_t A, int k, const int *level_rows, const WaveV
     std::vector<int> lr(k);
     for (int l = 0; l < k; l++) lr[l] = level_rows ? level_rows[l] : A->n;
     for (WavePlan &p : S.plans)
-        if (p.k == k && p.t_nnz == V.t_nnz && p.t_rows == V.t_rows && p.slack == slack && p.level_rows == lr) return &p;
+        if (p.k == k && p.t_nnz == V.t_nnz && p.t_rows == V.t_rows && p.slack == slack && p.level_rows == lr) {
+            if (p.rejected) { *why = "wavefront window exceeds the L2 budget"; return nullptr; }
+            return &p;
+        }
 
-    if (S.blk_min.empty()) { *why = "column extents were not recorded"; return nullptr; }
-    if (nsk_ensure_tiling_public(A, V.t_nnz, V.t_rows) != NSK_OK) { *why = "tiling failed"; return nullptr; }
-    const nsk_tiling &T = A->tiling;
+    if (S.blk_row0.empty()) { *why = "column extents were not recorded"; return nullptr; }
+    const nsk_tiling *Tp = nullptr;
+    if (nsk_get_tiling(A, V.t_nnz, V.t_rows, &Tp) != NSK_OK) { *why = "tiling failed"; return nullptr; }
+    const nsk_tiling &T = *Tp;
     if (T.nlong) { *why = "operator has rows longer than a stage"; return nullptr; }
     const int ntiles = T.ntiles;
     if (ntiles == 0) { *why = "empty operator"; return nullptr; }
     const int ngroups = (ntiles + WF_GROUP - 1) / WF_GROUP;
+    const bool ranked = !A->row_rank.empty();
 
-    // tile -> group range of its columns
-    std::vector<int> row2tile_start(ntiles);
-    for (int t = 0; t < ntiles; t++) row2tile_start[t] = T.h_tiles[t].row0;
-    auto tile_of_row = [&](int row) {
-        int t = (int)(std::upper_bound(row2tile_start.begin(), row2tile_start.end(), row) - row2tile_start.begin()) - 1;
-        return t < 0 ? 0 : t;
+    // POSITION of a tile = its place in global row order (identity for a single-GPU operator; for a
+    // distributed slab the ghost rings, stored after the owned rows, slot in below / above them).
+    // Tiles never straddle a break, so a tile is a contiguous run in rank space too.
+    std::vector<int> tile_at_pos(ntiles), pos_of_tile(ntiles), key(ntiles);
+    for (int t = 0; t < ntiles; t++) {
+        tile_at_pos[t] = t;
+        key[t] = ranked ? A->row_rank[T.h_tiles[t].row0] : T.h_tiles[t].row0;
+    }
+    if (ranked) std::sort(tile_at_pos.begin(), tile_at_pos.end(), [&](int a, int b) { return key[a] < key[b]; });
+    std::vector<int> pos_key(ntiles);
+    for (int p = 0; p < ntiles; p++) {
+        pos_of_tile[tile_at_pos[p]] = p;
+        pos_key[p] = key[tile_at_pos[p]];
+    }
+    auto pos_of_rank = [&](int rank) {
+        int p = (int)(std::upper_bound(pos_key.begin(), pos_key.end(), rank) - pos_key.begin()) - 1;
+        return p < 0 ? 0 : p;
     };
-    std::vector<int> glo(ntiles), ghi(ntiles);
+    std::vector<int> glo(ntiles), ghi(ntiles);  // indexed by tile
     int reach = 0;
     for (int t = 0; t < ntiles; t++) {
         const nsk_tile &tl = T.h_tiles[t];
         int mn = INT32_MAX, mx = -1;
-        for (int b = tl.row0 / 32; b <= (tl.row0 + tl.nrows - 1) / 32; b++) {
+        size_t b = (size_t)(std::upper_bound(S.blk_row0.begin(), S.blk_row0.end(), tl.row0) - S.blk_row0.begin()) - 1;
+        for (; b < S.blk_row0.size() && S.blk_row0[b] < tl.row0 + tl.nrows; b++) {
             mn = std::min(mn, S.blk_min[b]);
             mx = std::max(mx, S.blk_max[b]);
         }
-        if (mx < 0) { mn = tl.row0; mx = tl.row0; }  // rows without entries depend on nothing
-        if (mx >= A->n) {
-            // columns beyond the stored rows are ghost entries of x: legal only for a distributed slab,
-            // where rows evaluated at level >= 1 never reference them (dist.cu builds the rings so)
-            if (!A->dist) { *why = "columns beyond the row range"; return nullptr; }
-            mx = A->n - 1;
-            if (mn >= A->n) mn = A->n - 1;
-        }
-        glo[t] = tile_of_row(mn) / WF_GROUP;
-        ghi[t] = tile_of_row(mx) / WF_GROUP;
+        if (mx < 0) { mn = key[t]; mx = key[t]; }  // rows without (local) entries depend on nothing
+        glo[t] = pos_of_rank(mn) / WF_GROUP;
+        ghi[t] = pos_of_rank(mx) / WF_GROUP;
         const int last_needed = std::min(ntiles - 1, (ghi[t] + 1) * WF_GROUP - 1);
-        reach = std::max(reach, last_needed - t);
+        reach = std::max(reach, last_needed - pos_of_tile[t]);
     }
     const int D = reach + 1 + slack;
     // The window that must stay in L2: (k-1)*D tiles of matrix data plus k level vectors of it.
     const double tile_bytes = 12.0 * A->mean_row * V.t_rows + 8.0 * V.t_rows * (k + 1);
     const double window = (double)(k - 1) * D * tile_bytes;
     const double budget = (A->ctx->opt.wave_l2_pct > 0 ? (double)A->ctx->opt.wave_l2_pct : 80.0) / 100.0;
-    if (window > budget * (double)A->ctx->prop.l2CacheSize) { *why = "wavefront window exceeds the L2 budget"; return nullptr; }
-
-    // number of tiles each level evaluates (row-prefix shrink of the distributed operator)
-    std::vector<int> ntl(k);
-    for (int l = 0; l < k; l++) {
-        int cnt = 0;
-        while (cnt < ntiles && T.h_tiles[cnt].row0 < lr[l]) cnt++;
-        ntl[l] = cnt;
+    if (window > budget * (double)A->ctx->prop.l2CacheSize) {
+        *why = "wavefront window exceeds the L2 budget";
+        WavePlan rej;  // remember the refusal: planning costs O(tiles) host work
+        rej.k = k; rej.t_nnz = V.t_nnz; rej.t_rows = V.t_rows; rej.level_rows = lr; rej.slack = slack; rej.rejected = true;
+        S.plans.push_back(rej);
+        return nullptr;
     }
+
     std::vector<WaveTask> tasks;
     tasks.reserve((size_t)k * ntiles);
+    std::vector<int> gsize((size_t)k * ngroups, 0);
     const int tau_end = ntiles + (k - 1) * D;
     for (int tau = 0; tau < tau_end; tau++)
         for (int l = k - 1; l >= 0; l--) {
-            const int t = tau - l * D;
-            if (t < 0 || t >= ntl[l]) continue;
-            {
-                const nsk_tile &tl = T.h_tiles[t];
-                tasks.push_back(WaveTask{tl.row0, tl.nrows, tl.nz0, tl.nz1, l, t, glo[t], ghi[t]});
-            }
+            const int p = tau - l * D;
+            if (p < 0 || p >= ntiles) continue;
+            const int t = tile_at_pos[p];
+            const nsk_tile &tl = T.h_tiles[t];
+            if (tl.row0 >= lr[l]) continue;  // outside this level's row prefix (distributed shrink)
+            tasks.push_back(WaveTask{tl.row0, tl.nrows, tl.nz0, tl.nz1, l, p, glo[t], ghi[t]});
+            gsize[(size_t)l * ngroups + p / WF_GROUP]++;
         }
-    std::vector<int> gsize((size_t)k * ngroups, 0);
-    for (int l = 0; l < k; l++)
-        for (int t = 0; t < ntl[l]; t++) gsize[(size_t)l * ngroups + t / WF_GROUP]++;
+
     WavePlan p;
     p.k = k; p.t_nnz = V.t_nnz; p.t_rows = V.t_rows; p.level_rows = lr; p.slack = slack;
     p.ntasks = (int)tasks.size(); p.ngroups = ngroups; p.D = D;
@@ -453,13 +473,14 @@ int nsk_mpk_wavefront(nsk_csr_t A, int k, const double *d_x, double *const *d_le
         nsk_set_error(ctx, "wavefront matrix powers not applicable: %s", why);
         return NSK_ERR_UNSUPPORTED;
     }
-    NSK_TRY(nsk_ensure_tiling_public(A, V.t_nnz, V.t_rows));
+    const nsk_tiling *Tp = nullptr;
+    NSK_TRY(nsk_get_tiling(A, V.t_nnz, V.t_rows, &Tp));
     const int grid = std::min(plan->ntasks, grid_max);
 
     const size_t ncnt = (size_t)k * plan->ngroups;
     NSK_CUDA(ctx, cudaMemsetAsync(plan->d_counters, 0, sizeof(int) * (ncnt + 4), ctx->stream));
     WaveParams P;
-    P.tiles = A->tiling.d_tiles;
+    P.tiles = Tp->d_tiles;
     P.tasks = plan->d_tasks;
     P.ntasks = plan->ntasks;
     P.ngroups = plan->ngroups;

@@ -108,7 +108,9 @@ struct nsk_csr_s {
     double *d_coef = nullptr;  // nnz (+pad)
     double mean_row = 0.0;
     int max_row = 0;
-    nsk_tiling tiling;         // plan of the streaming SpMV kernel
+    std::vector<nsk_tiling *> tilings;  // one per tile geometry in use (built on demand, kept)
+    std::vector<int> breaks;            // local rows at which a tile must end (segment starts of a distributed slab)
+    std::vector<int> row_rank;          // distributed: position of each local row in GLOBAL row order (else empty)
     // MPK scratch: k level vectors when the caller passes host memory, wavefront flags, ...
     int *d_flags = nullptr;
     size_t flags_count = 0;
@@ -136,7 +138,8 @@ struct nsk_spmv_args {
     int dot_slot = -1;  // index into ctx->d_scalars receiving the finished sum
 };
 int nsk_launch_spmv(nsk_csr_t A, const nsk_spmv_args &a);
-int nsk_build_tiling(nsk_csr_t A, const int *h_ptrow);
+int nsk_get_tiling(nsk_csr_t A, int t_nnz, int t_rows, const nsk_tiling **out);  // cached per geometry
+void nsk_free_tilings(nsk_csr_t A);
 void nsk_stream_kernel_config(nsk_ctx_t ctx, double mean_row, int *tile_nnz, int *tile_rows);
 
 // ---- vector kernels (vector_kernels.cu) ------------------------------------------------------

@@ -358,23 +358,24 @@ void nsk_stream_kernel_config(nsk_ctx_t ctx, double mean_row, int *tile_nnz, int
 // -----------------------------------------------------------------------------------------------
 // tiling (host)
 // -----------------------------------------------------------------------------------------------
-static void make_tiles(const int *ptrow, int n, int t_nnz, int t_rows, std::vector<nsk_tile> &out, int *nlong)
+static void make_tiles(const int *ptrow, int n, int t_nnz, int t_rows, const std::vector<int> &breaks,
+                       std::vector<nsk_tile> &out, int *nlong)
 {
     out.clear();
     *nlong = 0;
     int r = 0;
+    size_t bi = 0;
     while (r < n) {
-        int r1 = r;
+        while (bi < breaks.size() && breaks[bi] <= r) bi++;
+        const int seg_end = bi < breaks.size() ? std::min(n, breaks[bi]) : n;  // tiles never straddle a break
         const int nz0 = ptrow[r];
-        // greedy: extend while both limits hold
-        int lim = std::min(n, r + t_rows);
-        // binary search for the last row end with nnz <= t_nnz
-        int lo = r, hi = lim;  // invariant: ptrow[lo] - nz0 <= t_nnz
+        const int lim = std::min(seg_end, r + t_rows);
+        int lo = r, hi = lim;  // last row end with nnz <= t_nnz (binary search, ptrow is monotone)
         while (lo < hi) {
             int mid = lo + (hi - lo + 1) / 2;
             if (ptrow[mid] - nz0 <= t_nnz) lo = mid; else hi = mid - 1;
         }
-        r1 = lo;
+        int r1 = lo;
         if (r1 == r) {  // a single row longer than a stage
             r1 = r + 1;
             (*nlong)++;
@@ -384,41 +385,43 @@ static void make_tiles(const int *ptrow, int n, int t_nnz, int t_rows, std::vect
     }
 }
 
-static int ensure_tiling(nsk_csr_t A, const std::vector<int> &h_ptrow, int t_nnz, int t_rows)
+extern std::vector<int> &nsk_csr_host_ptrow(nsk_csr_t A);  // csr.cu
+
+int nsk_get_tiling(nsk_csr_t A, int t_nnz, int t_rows, const nsk_tiling **out)
 {
-    nsk_tiling &T = A->tiling;
-    if (T.d_tiles && T.tile_nnz == t_nnz && T.tile_rows == t_rows) return NSK_OK;
+    for (nsk_tiling *T : A->tilings)
+        if (T->tile_nnz == t_nnz && T->tile_rows == t_rows) {
+            *out = T;
+            return NSK_OK;
+        }
     nsk_ctx_t ctx = A->ctx;
-    if (T.d_tiles) {
-        NSK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        NSK_CUDA(ctx, cudaFree(T.d_tiles));
-        T.d_tiles = nullptr;
+    nsk_tiling *T = new nsk_tiling();
+    make_tiles(nsk_csr_host_ptrow(A).data(), A->n, t_nnz, t_rows, A->breaks, T->h_tiles, &T->nlong);
+    T->tile_nnz = t_nnz;
+    T->tile_rows = t_rows;
+    T->ntiles = (int)T->h_tiles.size();
+    size_t bytes = sizeof(nsk_tile) * (size_t)std::max(T->ntiles, 1);
+    cudaError_t e = cudaMalloc(&T->d_tiles, bytes + 64);
+    if (e == cudaSuccess && T->ntiles)
+        e = cudaMemcpy(T->d_tiles, T->h_tiles.data(), sizeof(nsk_tile) * (size_t)T->ntiles, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        nsk_set_error(ctx, "tile table upload failed: %s", cudaGetErrorString(e));
+        if (T->d_tiles) cudaFree(T->d_tiles);
+        delete T;
+        return NSK_ERR_CUDA;
     }
-    make_tiles(h_ptrow.data(), A->n, t_nnz, t_rows, T.h_tiles, &T.nlong);
-    T.tile_nnz = t_nnz;
-    T.tile_rows = t_rows;
-    T.ntiles = (int)T.h_tiles.size();
-    size_t bytes = sizeof(nsk_tile) * (size_t)std::max(T.ntiles, 1);
-    NSK_CUDA(ctx, cudaMalloc(&T.d_tiles, bytes + 64));
-    if (T.ntiles)
-        NSK_CUDA(ctx, cudaMemcpy(T.d_tiles, T.h_tiles.data(), sizeof(nsk_tile) * (size_t)T.ntiles,
-                                 cudaMemcpyHostToDevice));
+    A->tilings.push_back(T);
+    *out = T;
     return NSK_OK;
 }
 
-extern std::vector<int> &nsk_csr_host_ptrow(nsk_csr_t A);  // csr.cu
-
-int nsk_ensure_tiling_public(nsk_csr_t A, int t_nnz, int t_rows)
+void nsk_free_tilings(nsk_csr_t A)
 {
-    return ensure_tiling(A, nsk_csr_host_ptrow(A), t_nnz, t_rows);
-}
-
-int nsk_build_tiling(nsk_csr_t A, const int *h_ptrow)
-{
-    (void)h_ptrow;
-    int t_nnz, t_rows;
-    nsk_stream_kernel_config(A->ctx, A->mean_row, &t_nnz, &t_rows);
-    return ensure_tiling(A, nsk_csr_host_ptrow(A), t_nnz, t_rows);
+    for (nsk_tiling *T : A->tilings) {
+        if (T->d_tiles) cudaFree(T->d_tiles);
+        delete T;
+    }
+    A->tilings.clear();
 }
 
 // -----------------------------------------------------------------------------------------------
@@ -489,8 +492,9 @@ int nsk_launch_spmv(nsk_csr_t A, const nsk_spmv_args &a)
         fn = lookup_kernel(variant, kind, g, muladd, &smem);
     }
     const StreamVariant &V = g_variants[variant];
-    NSK_TRY(ensure_tiling(A, nsk_csr_host_ptrow(A), V.t_nnz, V.t_rows));
-    const nsk_tiling &T = A->tiling;
+    const nsk_tiling *Tp = nullptr;
+    NSK_TRY(nsk_get_tiling(A, V.t_nnz, V.t_rows, &Tp));
+    const nsk_tiling &T = *Tp;
 
     // tiles covering [rb, re)
     auto cmp = [](const nsk_tile &t, int row) { return t.row0 + t.nrows <= row; };
