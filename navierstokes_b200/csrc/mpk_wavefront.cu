@@ -294,7 +294,12 @@ struct WaveVariant {
     X(3, 2048, 256, 2, 8, 4)   \
     X(4, 1024, 128, 3, 4, 5)   \
     X(5, 1024, 128, 2, 4, 6)   \
-    X(6, 4096, 512, 3, 16, 1)
+    X(6, 4096, 512, 3, 16, 1)  \
+    X(7, 4096, 512, 4, 16, 1)  \
+    X(8, 3584, 512, 5, 16, 1)  \
+    X(9, 2048, 256, 4, 8, 2)   \
+    X(10, 3072, 384, 3, 12, 1) \
+    X(11, 3072, 384, 5, 12, 1)
 
 static const WaveVariant g_wvariants[] = {
 #define X(id, t, r, s, w, b) {t, r, s, w, b},

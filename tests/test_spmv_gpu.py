@@ -198,7 +198,7 @@ def test_medium_size_properties(ctx, oracle_lib, shape, reset_options):
 
 
 # ---- wavefront (single-launch, L2-resident) matrix powers ------------------------------------------
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12])
 @pytest.mark.parametrize("gen,args", [("laplace3d_7pt", (40,)), ("laplace2d_5pt", (300,)), ("laplace3d_7pt", (64, 64, 20))])
 def test_mpk_wavefront_bitwise(ctx, oracle_lib, gen, args, variant, reset_options):
     A = getattr(matgen, gen)(*args)
