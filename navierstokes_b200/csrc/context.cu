@@ -132,6 +132,7 @@ NSK_API int nsk_ctx_set_option(nsk_ctx_t c, const char *name, int64_t v)
     else if (!strcmp(name, "wave_variant")) c->opt.wave_variant = v;
     else if (!strcmp(name, "wave_slack_pct")) c->opt.wave_slack_pct = v;
     else if (!strcmp(name, "wave_l2_pct")) c->opt.wave_l2_pct = v;
+    else if (!strcmp(name, "wave_static")) c->opt.wave_static = v;
     else {
         nsk_set_error(c, "unknown option '%s'", name);
         return NSK_ERR_INVALID;

@@ -40,19 +40,20 @@ std::vector<int> &nsk_csr_host_ptrow(nsk_csr_t A);
 
 constexpr int WF_GROUP = 16;  // tiles per completion counter
 
-struct WaveTask {               // 32 bytes: everything a claim needs in one go (two 16-byte loads)
-    int row0, nrows, nz0, nz1;  // the tile (copied from the tiling so a claim costs no second lookup)
-    int level, tile, glo, ghi;  // inputs: groups [glo, ghi] of level-1 must be complete
+struct WaveTask {               // 32 bytes: everything an item needs in one go (two 16-byte loads)
+    int row0, nrows, nz0, nz1;  // the tile (copied from the tiling so an item costs no second lookup)
+    int level, tile, glo, ghi;  // inputs: groups [0, ghi] of level-1 must be complete; level < 0 = end marker
 };
 
 struct WaveParams {
-    const nsk_tile *tiles;
-    const WaveTask *tasks;
+    const WaveTask *tasks;  // [grid][per_cta]: CTA c runs tasks[c * per_cta + 0 ...] in order (static schedule)
+    int per_cta;
+    const WaveTask *tasks_dyn;  // items in wavefront order (dynamic schedule); ntasks of them
     int ntasks;
+    unsigned int *next;         // dynamic schedule: claim cursor, zeroed before the launch; nullptr = static
     int ngroups;
     int *counters;          // [k][ngroups], zeroed before the launch
     const int *group_size;  // [k][ngroups] tiles that will report per group and level
-    unsigned int *next;     // work-item cursor, zeroed before the launch
     const int *ptrow;
     const int *indcol;
     const double *coef;
@@ -62,7 +63,48 @@ struct WaveParams {
     int k;
 };
 
-template <int T_NNZ, int T_ROWS, int STAGES, int NCW, int MINB, bool MULADD>
+// Rows of one pass of a consumer thread: RPT rows, the gathers of their first 8 nonzeros all in flight
+// before the first dependent multiply-add (the chain of each row stays strictly sequential).
+template <bool MULADD, bool NC, int RPT, int NCT>
+__device__ __forceinline__ void consume_tile(const double *val_s, const int *col_s, const int *ptr_s, int vo, int co,
+                                             int po, int row0, int nrows, int row_end, const double *src, double *dst,
+                                             int ctid)
+{
+    for (int rb = 0; rb < nrows; rb += NCT * RPT) {
+        int p[RPT], q[RPT];
+        double xv[RPT][8];
+#pragma unroll
+        for (int u = 0; u < RPT; u++) {
+            const int r = rb + u * NCT + ctid;
+            const int row = row0 + r;
+            const bool valid = r < nrows && row < row_end;
+            p[u] = valid ? ptr_s[row - po] : 0;
+            q[u] = valid ? ptr_s[row + 1 - po] : -1;  // q < p marks "no row": nothing gathered, nothing stored
+        }
+#pragma unroll
+        for (int u = 0; u < RPT; u++)
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const int j = p[u] + e;
+                xv[u][e] = 0.0;
+                if (j < q[u]) {
+                    const int c = col_s[j - co];
+                    xv[u][e] = NC ? __ldg(src + c) : src[c];
+                }
+            }
+#pragma unroll
+        for (int u = 0; u < RPT; u++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int e = 0; e < 8; e++)
+                if (p[u] + e < q[u]) acc = row_op<MULADD>(val_s[p[u] + e - vo], xv[u][e], acc);
+            if (q[u] > p[u] + 8) acc = row_chain<MULADD, NC>(val_s, col_s, p[u] + 8, q[u], vo, co, src, acc);
+            if (q[u] >= p[u]) dst[row0 + rb + u * NCT + ctid] = acc;
+        }
+    }
+}
+
+template <int T_NNZ, int T_ROWS, int STAGES, int NCW, int MINB, int RPT, bool MULADD>
 __global__ void __launch_bounds__((NCW + 3) * 32, MINB) mpk_wavefront_kernel(const WaveParams P)
 {
     using Geo = StageGeom<T_NNZ, T_ROWS>;
@@ -70,7 +112,7 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) mpk_wavefront_kernel(con
     unsigned char *stage_base = smem;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + Geo::BYTES * STAGES);  // TMA bytes of the stage landed
     uint64_t *empty = full + STAGES;                                            // all consumer warps are done with it
-    uint64_t *claimed = empty + STAGES;                                         // header written (producer -> dependency warp)
+    uint64_t *claimed = empty + STAGES;                                         // header written (producer -> helpers)
     uint64_t *ready = claimed + STAGES;                                         // inputs of the item are complete
     uint64_t *done = ready + STAGES;                                            // all consumer warps stored their rows
 
@@ -91,16 +133,75 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) mpk_wavefront_kernel(con
     __syncthreads();
 
     if (warp == NCW) {
-        // ===== producer: claims items in wavefront order, prefetches their matrix slices.  The claim
-        // (one L2 atomic + one dependent 32-byte load, ~1.5 us under load) is taken ONE ITEM AHEAD, in the
-        // shadow of the wait for a free stage: with the claim inside the stage turn-around the whole
-        // sweep ran at ~0.5 item/us per CTA whatever the geometry (measured, profiles/). =====
-        if (lane == 0) {
-            const int4 *tasks4 = reinterpret_cast<const int4 *>(P.tasks);
-            unsigned int q = atomicAdd(P.next, 1u);
-            int4 ta = make_int4(0, 0, 0, 0), tb = make_int4(-1, 0, 0, 0);
-            if (q < (unsigned int)P.ntasks) { ta = tasks4[2 * (size_t)q]; tb = tasks4[2 * (size_t)q + 1]; }
-            for (int it = 0;; ++it) {
+        // ===== producer.  The schedule is STATIC: this CTA's items sit in wavefront order in its own slice of
+        // P.tasks, so nothing on this path waits for a global atomic (a dynamic claim = atomic + dependent
+        // descriptor load capped every geometry at ~1 item/us per CTA, profiles/r01_sweep_mpk_wavefront_*).
+        // Descriptors are fetched 32 at a time, one per lane, one batch ahead, and handed to lane 0 by shuffle;
+        // an item's matrix slice is prefetched as soon as a stage is free -- it depends on no flag. =====
+        if (P.next != nullptr) {
+            // dynamic schedule: items are claimed in wavefront order with one atomicAdd each, which balances
+            // load across SMs by itself.  A claim is two dependent L2 round trips (cursor, then descriptor):
+            // claims are therefore PIPELINED three items ahead (cursor values q1..q3 and descriptor d0 are in
+            // flight while the current item is issued), so the loop never waits for either.
+            if (lane == 0) {
+                const int4 *tasks4 = reinterpret_cast<const int4 *>(P.tasks_dyn);
+                const unsigned int nt = (unsigned int)P.ntasks;
+                const int4 endA = make_int4(0, 0, 0, 0), endB = make_int4(-1, 0, 0, 0);
+                unsigned int q0 = atomicAdd(P.next, 1u);
+                unsigned int q1 = atomicAdd(P.next, 1u);
+                unsigned int q2 = atomicAdd(P.next, 1u);
+                int4 ta = endA, tb = endB;
+                if (q0 < nt) { ta = tasks4[2 * (size_t)q0]; tb = tasks4[2 * (size_t)q0 + 1]; }
+                for (int it = 0;; ++it) {
+                    const unsigned int q3 = atomicAdd(P.next, 1u);
+                    int4 na = endA, nb = endB;
+                    if (q1 < nt) { na = tasks4[2 * (size_t)q1]; nb = tasks4[2 * (size_t)q1 + 1]; }
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    unsigned char *st = stage_base + (size_t)s * Geo::BYTES;
+                    int *hdr = reinterpret_cast<int *>(st + Geo::HDR_OFF);
+                    hdr[0] = ta.x; hdr[1] = ta.y; hdr[2] = ta.z; hdr[3] = ta.w;
+                    hdr[4] = tb.x; hdr[5] = tb.y; hdr[6] = tb.z; hdr[7] = tb.w;
+                    mbar_arrive(&claimed[s]);
+                    if (tb.x < 0) {  // end marker
+                        mbar_arrive(&full[s]);
+                        break;
+                    }
+                    const int row0 = ta.x, nrows = ta.y, nz0 = ta.z, nz1 = ta.w;
+                    const int a0 = nz0 & ~3, v0 = nz0 & ~1, p0 = row0 & ~3;
+                    const uint32_t cbytes = (uint32_t)(((nz1 - a0) + 3) & ~3) * 4u;
+                    const uint32_t vbytes = (uint32_t)(((nz1 - v0) + 1) & ~1) * 8u;
+                    const uint32_t pbytes = (uint32_t)(((row0 + nrows + 1 - p0) + 3) & ~3) * 4u;
+                    mbar_arrive_expect_tx(&full[s], cbytes + vbytes + pbytes);
+                    bulk_g2s(st + Geo::PTR_OFF, P.ptrow + p0, pbytes, &full[s]);
+                    if (cbytes) bulk_g2s(st + Geo::COL_OFF, P.indcol + a0, cbytes, &full[s]);
+                    if (vbytes) bulk_g2s(st + Geo::VAL_OFF, P.coef + v0, vbytes, &full[s]);
+                    ta = na; tb = nb;
+                    q1 = q2; q2 = q3;
+                }
+            }
+            return;
+        }
+        const int4 *my = reinterpret_cast<const int4 *>(P.tasks) + 2 * (size_t)blockIdx.x * P.per_cta;
+        const int4 endA = make_int4(0, 0, 0, 0), endB = make_int4(-1, 0, 0, 0);
+        int4 ca = endA, cb = endB, na = endA, nb = endB;
+        if (lane < P.per_cta) { ca = my[2 * lane]; cb = my[2 * lane + 1]; }
+        if (32 + lane < P.per_cta) { na = my[2 * (32 + lane)]; nb = my[2 * (32 + lane) + 1]; }
+        for (int it = 0;; ++it) {
+            const int j = it & 31;
+            if (j == 0 && it > 0) {
+                ca = na; cb = nb;
+                na = endA; nb = endB;
+                const int idx = it + 32 + lane;
+                if (idx < P.per_cta) { na = my[2 * idx]; nb = my[2 * idx + 1]; }
+            }
+            int4 ta, tb;
+            ta.x = __shfl_sync(0xffffffffu, ca.x, j); ta.y = __shfl_sync(0xffffffffu, ca.y, j);
+            ta.z = __shfl_sync(0xffffffffu, ca.z, j); ta.w = __shfl_sync(0xffffffffu, ca.w, j);
+            tb.x = __shfl_sync(0xffffffffu, cb.x, j); tb.y = __shfl_sync(0xffffffffu, cb.y, j);
+            tb.z = __shfl_sync(0xffffffffu, cb.z, j); tb.w = __shfl_sync(0xffffffffu, cb.w, j);
+            if (lane == 0) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
@@ -111,29 +212,31 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) mpk_wavefront_kernel(con
                 mbar_arrive(&claimed[s]);
                 if (tb.x < 0) {  // end marker
                     mbar_arrive(&full[s]);
-                    break;
+                } else {
+                    const int row0 = ta.x, nrows = ta.y, nz0 = ta.z, nz1 = ta.w;
+                    const int a0 = nz0 & ~3, v0 = nz0 & ~1, p0 = row0 & ~3;
+                    const uint32_t cbytes = (uint32_t)(((nz1 - a0) + 3) & ~3) * 4u;
+                    const uint32_t vbytes = (uint32_t)(((nz1 - v0) + 1) & ~1) * 8u;
+                    const uint32_t pbytes = (uint32_t)(((row0 + nrows + 1 - p0) + 3) & ~3) * 4u;
+                    mbar_arrive_expect_tx(&full[s], cbytes + vbytes + pbytes);
+                    bulk_g2s(st + Geo::PTR_OFF, P.ptrow + p0, pbytes, &full[s]);
+                    if (cbytes) bulk_g2s(st + Geo::COL_OFF, P.indcol + a0, cbytes, &full[s]);
+                    if (vbytes) bulk_g2s(st + Geo::VAL_OFF, P.coef + v0, vbytes, &full[s]);
                 }
-                const int row0 = ta.x, nrows = ta.y, nz0 = ta.z, nz1 = ta.w;
-                const int a0 = nz0 & ~3, v0 = nz0 & ~1, p0 = row0 & ~3;
-                const uint32_t cb = (uint32_t)(((nz1 - a0) + 3) & ~3) * 4u;
-                const uint32_t vb = (uint32_t)(((nz1 - v0) + 1) & ~1) * 8u;
-                const uint32_t pb = (uint32_t)(((row0 + nrows + 1 - p0) + 3) & ~3) * 4u;
-                mbar_arrive_expect_tx(&full[s], cb + vb + pb);
-                bulk_g2s(st + Geo::PTR_OFF, P.ptrow + p0, pb, &full[s]);
-                if (cb) bulk_g2s(st + Geo::COL_OFF, P.indcol + a0, cb, &full[s]);
-                if (vb) bulk_g2s(st + Geo::VAL_OFF, P.coef + v0, vb, &full[s]);
-                // next claim, overlapped with the wait above on the next trip
-                q = atomicAdd(P.next, 1u);
-                tb.x = -1;
-                if (q < (unsigned int)P.ntasks) { ta = tasks4[2 * (size_t)q]; tb = tasks4[2 * (size_t)q + 1]; }
             }
+            if (tb.x < 0) break;  // warp-uniform
         }
         return;
     }
 
     if (warp == NCW + 1) {
-        // ===== dependency warp: waits (off the consumers' critical path) until the level l-1 tile groups an
-        // item reads from are complete, then opens the item for the consumers =====
+        // ===== dependency warp.  Lane l keeps a WATERMARK for level l: every tile group below it is known to
+        // be complete.  An item whose last input group lies below the watermark opens at once (no memory
+        // traffic); otherwise the warp polls the next 32 group counters in one round trip (ld.acquire.gpu,
+        // bounded spin) and advances the watermark over the complete prefix -- the lower level normally runs
+        // `slack` tiles ahead, so one poll opens several items.  Items of one CTA are in wavefront order and all
+        // inputs of the oldest unfinished item are older, hence finished: spinning cannot deadlock. =====
+        int W = 0;
         for (int it = 0;; ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
@@ -141,17 +244,27 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) mpk_wavefront_kernel(con
             const int *hdr = reinterpret_cast<const int *>(stage_base + (size_t)s * Geo::BYTES + Geo::HDR_OFF);
             const int level = hdr[4];
             if (level > 0) {
-                const int glo = hdr[6], ghi = hdr[7];
-                const int *cnt = P.counters + (size_t)(level - 1) * P.ngroups;
-                const int *need = P.group_size + (size_t)(level - 1) * P.ngroups;
-                for (int g = glo + lane; g <= ghi; g += 32) {
-                    const int want = need[g];
+                const int ghi = hdr[7];
+                int w = __shfl_sync(0xffffffffu, W, level - 1);
+                if (w <= ghi) {
+                    const int *cnt = P.counters + (size_t)(level - 1) * P.ngroups;
+                    const int *need = P.group_size + (size_t)(level - 1) * P.ngroups;
                     uint32_t spins = 0;
-                    // ld.acquire.gpu = LDG.STRONG.GPU + CCTL.IVALL: also drops this SM's stale L1 lines
-                    while (ld_acquire_gpu(cnt + g) < want) {
-                        __nanosleep(32);
-                        if (++spins > (1u << 24)) __trap();  // protocol bug: fail the launch, never hang
+                    while (true) {
+                        const int g = w + lane;
+                        bool ok = true;
+                        // ld.acquire.gpu = LDG.STRONG.GPU + CCTL.IVALL: also drops this SM's stale L1 lines
+                        if (g < P.ngroups) ok = ld_acquire_gpu(cnt + g) >= __ldg(need + g);
+                        const unsigned int bad = __ballot_sync(0xffffffffu, !ok);
+                        const int adv = bad ? __ffs(bad) - 1 : 32;
+                        w = min(w + adv, P.ngroups);
+                        if (w > ghi) break;
+                        if (adv == 0) {
+                            __nanosleep(64);
+                            if (++spins > (1u << 24)) __trap();  // protocol bug: fail the launch, never hang
+                        }
                     }
+                    if (lane == level - 1) W = w;
                 }
             }
             __syncwarp();
@@ -162,21 +275,37 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) mpk_wavefront_kernel(con
     }
 
     if (warp == NCW + 2) {
-        // ===== publisher: makes a finished item visible to the rest of the GPU.  The GPU-scope release
-        // (fence + RED, ~1 us) is paid here, off the consumers' path: consumers only arrive on done[s]
-        // (release.cta); this thread's acquire of done[s] followed by red.release.gpu is cumulative over
-        // their stores. =====
+        // ===== publisher: makes finished items visible to the rest of the GPU.  The GPU-scope fence (~1 us) is
+        // paid here, off the consumers' path, and ONCE for all items found finished at that moment: consumers
+        // only arrive on done[s] (release.cta); this thread's acquire of done[s] followed by fence + RED is
+        // cumulative over their stores. =====
         if (lane == 0) {
-            for (int it = 0;; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(&claimed[s], ph);
-                const int *hdr = reinterpret_cast<const int *>(stage_base + (size_t)s * Geo::BYTES + Geo::HDR_OFF);
-                const int level = hdr[4], tile = hdr[5];
-                if (level < 0) break;
-                mbar_wait(&done[s], ph);
-                mbar_arrive(&empty[s]);  // the producer may refill the stage while we publish
-                if (level < P.k - 1) red_release_gpu_add(P.counters + (size_t)level * P.ngroups + tile / WF_GROUP, 1);
+            for (int it = 0;;) {
+                int slot[STAGES];  // counter index + 1, 0 = nothing to publish (last level)
+                int n = 0;
+                bool end = false;
+#pragma unroll
+                for (int j = 0; j < STAGES; j++) {
+                    if (j > n || end) continue;  // stop at the first item that is not finished yet
+                    const int s = (it + j) % STAGES;
+                    const uint32_t ph = ((it + j) / STAGES) & 1;
+                    if (j == 0) mbar_wait(&claimed[s], ph);
+                    else if (!mbar_try_wait(&claimed[s], ph)) continue;
+                    const int *hdr = reinterpret_cast<const int *>(stage_base + (size_t)s * Geo::BYTES + Geo::HDR_OFF);
+                    const int level = hdr[4], tile = hdr[5];
+                    if (level < 0) { end = true; continue; }
+                    if (j == 0) mbar_wait(&done[s], ph);
+                    else if (!mbar_try_wait(&done[s], ph)) continue;
+                    slot[j] = level < P.k - 1 ? level * P.ngroups + tile / WF_GROUP + 1 : 0;
+                    mbar_arrive(&empty[s]);  // the producer may refill the stage while we publish
+                    n = j + 1;
+                }
+                if (n == 0) break;  // first item was the end marker
+                __threadfence();
+#pragma unroll
+                for (int j = 0; j < STAGES; j++)
+                    if (j < n && slot[j]) red_relaxed_gpu_add(P.counters + (slot[j] - 1), 1);
+                it += n;
             }
         }
         return;
@@ -184,7 +313,6 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) mpk_wavefront_kernel(con
 
     // ===== consumer warps: independent of one another (no CTA-wide barrier in the loop) =====
     constexpr int NCT = NCW * 32;
-    const int ctid = tid;
     for (int it = 0;; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
@@ -199,19 +327,15 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) mpk_wavefront_kernel(con
         const int *col_s = reinterpret_cast<const int *>(st + Geo::COL_OFF);
         const int *ptr_s = reinterpret_cast<const int *>(st + Geo::PTR_OFF);
         const int vo = nz0 & ~1, co = nz0 & ~3, po = row0 & ~3;
-        const int row_end = P.level_rows[level];
-        double *dst = P.levels[level];
         // level 0 reads x (constant for the launch: read-only path); level l >= 1 reads what other CTAs wrote
         // earlier in THIS launch: ordinary coherent loads, ordered by ready[s] after the dependency warp's
         // acquires (which also invalidated this SM's L1)
-        const double *src = level == 0 ? P.x : P.levels[level - 1];
-        for (int r = ctid; r < nrows; r += NCT) {
-            const int row = row0 + r;
-            if (row >= row_end) continue;
-            const int p = ptr_s[row - po], q = ptr_s[row + 1 - po];
-            dst[row] = level == 0 ? row_chain<MULADD, true>(val_s, col_s, p, q, vo, co, src)
-                                  : row_chain<MULADD, false>(val_s, col_s, p, q, vo, co, src);
-        }
+        if (level == 0)
+            consume_tile<MULADD, true, RPT, NCT>(val_s, col_s, ptr_s, vo, co, po, row0, nrows, P.level_rows[0], P.x,
+                                                 P.levels[0], tid);
+        else
+            consume_tile<MULADD, false, RPT, NCT>(val_s, col_s, ptr_s, vo, co, po, row0, nrows, P.level_rows[level],
+                                                  P.levels[level - 1], P.levels[level], tid);
         __syncwarp();
         if (lane == 0) mbar_arrive(&done[s]);  // release.cta; no GPU-scope fence on this path
     }
@@ -224,10 +348,14 @@ struct WavePlan {
     int k = 0;
     int t_nnz = 0, t_rows = 0;
     int slack = 0;
+    int grid_req = 0;  // resident CTAs the plan was asked for (cache key)
+    int grid = 0;      // CTAs it uses: min(grid_req, items)
+    int per_cta = 0;
     bool rejected = false;
     std::vector<int> level_rows;
     int ntasks = 0, ngroups = 0, D = 0;
     WaveTask *d_tasks = nullptr;
+    WaveTask *d_tasks_dyn = nullptr;
     int *d_counters = nullptr;    // k*ngroups ints + 1 cursor (last)
     int *d_group_size = nullptr;
 };
@@ -277,6 +405,7 @@ void nsk_wave_free(nsk_csr_t A)
     if (it == g_wave.end()) return;
     for (WavePlan &p : it->second.plans) {
         if (p.d_tasks) cudaFree(p.d_tasks);
+        if (p.d_tasks_dyn) cudaFree(p.d_tasks_dyn);
         if (p.d_counters) cudaFree(p.d_counters);
         if (p.d_group_size) cudaFree(p.d_group_size);
     }
@@ -284,25 +413,25 @@ void nsk_wave_free(nsk_csr_t A)
 }
 
 struct WaveVariant {
-    int t_nnz, t_rows, stages, ncw, minb;
+    int t_nnz, t_rows, stages, ncw, minb, rpt;
 };
-//                 T_NNZ T_ROWS STAGES NCW MINB
+//                 T_NNZ T_ROWS STAGES NCW MINB RPT(rows per consumer thread and pass)
 #define NSK_WAVE_VARIANTS(X) \
-    X(0, 2048, 256, 2, 8, 3)   \
-    X(1, 2048, 256, 3, 8, 2)   \
-    X(2, 4096, 512, 2, 16, 2)  \
-    X(3, 2048, 256, 2, 8, 4)   \
-    X(4, 1024, 128, 3, 4, 5)   \
-    X(5, 1024, 128, 2, 4, 6)   \
-    X(6, 4096, 512, 3, 16, 1)  \
-    X(7, 4096, 512, 4, 16, 1)  \
-    X(8, 3584, 512, 5, 16, 1)  \
-    X(9, 2048, 256, 4, 8, 2)   \
-    X(10, 3072, 384, 3, 12, 1) \
-    X(11, 3072, 384, 5, 12, 1)
+    X(0, 2048, 256, 3, 8, 2, 1)   \
+    X(1, 2048, 256, 4, 8, 2, 1)   \
+    X(2, 4096, 512, 4, 16, 1, 1)  \
+    X(3, 4096, 512, 4, 8, 1, 2)   \
+    X(4, 3584, 512, 5, 16, 1, 1)  \
+    X(5, 3584, 512, 5, 8, 1, 2)   \
+    X(6, 7168, 1024, 2, 16, 1, 2) \
+    X(7, 1792, 256, 3, 8, 3, 1)   \
+    X(8, 1792, 256, 6, 8, 2, 1)   \
+    X(9, 1792, 256, 10, 8, 1, 1)  \
+    X(10, 1024, 128, 4, 4, 4, 1)  \
+    X(11, 3584, 512, 5, 28, 1, 1)
 
 static const WaveVariant g_wvariants[] = {
-#define X(id, t, r, s, w, b) {t, r, s, w, b},
+#define X(id, t, r, s, w, b, u) {t, r, s, w, b, u},
     NSK_WAVE_VARIANTS(X)
 #undef X
 };
@@ -312,10 +441,10 @@ typedef void (*wave_fn)(const WaveParams);
 static wave_fn wave_lookup(int variant, bool muladd, int *smem)
 {
     switch (variant) {
-#define X(id, t, r, s, w, b)                                                       \
+#define X(id, t, r, s, w, b, u)                                                    \
     case id:                                                                       \
         *smem = StageGeom<t, r>::BYTES * s + 5 * s * 8 + 128;                      \
-        return muladd ? mpk_wavefront_kernel<t, r, s, w, b, true> : mpk_wavefront_kernel<t, r, s, w, b, false>;
+        return muladd ? mpk_wavefront_kernel<t, r, s, w, b, u, true> : mpk_wavefront_kernel<t, r, s, w, b, u, false>;
         NSK_WAVE_VARIANTS(X)
 #undef X
     }
@@ -327,7 +456,7 @@ static int wave_variant(nsk_ctx_t ctx)
 {
     // option value 0 = default; n >= 1 selects table entry n - 1
     int v = (int)ctx->opt.wave_variant - 1;
-    if (v < 0 || v >= g_nwvariants) v = 6;  // measured best on 256^3 (profiles/r01_sweep_mpk_wavefront_claimahead.txt)
+    if (v < 0 || v >= g_nwvariants) v = 2;
     return v;
 }
 
@@ -336,13 +465,14 @@ static int wave_variant(nsk_ctx_t ctx)
 // claimed in wavefront order but complete a few microseconds later (grid x STAGES items are in flight);
 // without slack every level-l item would wait for a level-(l-1) item claimed one step earlier and the
 // whole sweep would serialise on that latency (measured: 16 ms instead of 0.5 ms on 256^3, k = 4).
-static WavePlan *get_plan(nsk_csr_t A, int k, const int *level_rows, const WaveVariant &V, int slack, const char **why)
+static WavePlan *get_plan(nsk_csr_t A, int k, const int *level_rows, const WaveVariant &V, int slack, int grid,
+                          const char **why)
 {
     WaveState &S = g_wave[A];
     std::vector<int> lr(k);
     for (int l = 0; l < k; l++) lr[l] = level_rows ? level_rows[l] : A->n;
     for (WavePlan &p : S.plans)
-        if (p.k == k && p.t_nnz == V.t_nnz && p.t_rows == V.t_rows && p.slack == slack && p.level_rows == lr) {
+        if (p.k == k && p.t_nnz == V.t_nnz && p.t_rows == V.t_rows && p.slack == slack && p.grid_req == grid && p.level_rows == lr) {
             if (p.rejected) { *why = "wavefront window exceeds the L2 budget"; return nullptr; }
             return &p;
         }
@@ -399,7 +529,7 @@ static WavePlan *get_plan(nsk_csr_t A, int k, const int *level_rows, const WaveV
     if (window > budget * (double)A->ctx->prop.l2CacheSize) {
         *why = "wavefront window exceeds the L2 budget";
         WavePlan rej;  // remember the refusal: planning costs O(tiles) host work
-        rej.k = k; rej.t_nnz = V.t_nnz; rej.t_rows = V.t_rows; rej.level_rows = lr; rej.slack = slack; rej.rejected = true;
+        rej.k = k; rej.t_nnz = V.t_nnz; rej.t_rows = V.t_rows; rej.level_rows = lr; rej.slack = slack; rej.grid_req = grid; rej.rejected = true;
         S.plans.push_back(rej);
         return nullptr;
     }
@@ -419,16 +549,33 @@ static WavePlan *get_plan(nsk_csr_t A, int k, const int *level_rows, const WaveV
             gsize[(size_t)l * ngroups + p / WF_GROUP]++;
         }
 
+    // Static schedule: item q of the wavefront order belongs to CTA (q + q / G) mod G, G = min(grid, items) -- round
+    // robin, rotated by one every round so that no CTA is pinned to one level (with G a multiple of k a plain
+    // round robin would leave the HBM-fed level 0 to G/k SMs).  Each CTA's items are stored contiguously, in
+    // order, closed by an end marker.
+    const int ntasks = (int)tasks.size();
+    const int G = std::max(1, std::min(grid, ntasks));
+    const int rounds = (ntasks + G - 1) / G;
+    const int per_cta = rounds + 1;
+    std::vector<WaveTask> sched((size_t)G * per_cta, WaveTask{0, 0, 0, 0, -1, 0, 0, 0});
+    for (int q = 0; q < ntasks; q++) {
+        const int r = q / G;
+        const int c = (q + r) % G;
+        sched[(size_t)c * per_cta + r] = tasks[q];
+    }
+
     WavePlan p;
-    p.k = k; p.t_nnz = V.t_nnz; p.t_rows = V.t_rows; p.level_rows = lr; p.slack = slack;
-    p.ntasks = (int)tasks.size(); p.ngroups = ngroups; p.D = D;
-    if (cudaMalloc(&p.d_tasks, sizeof(WaveTask) * tasks.size()) != cudaSuccess ||
+    p.k = k; p.t_nnz = V.t_nnz; p.t_rows = V.t_rows; p.level_rows = lr; p.slack = slack; p.grid_req = grid; p.grid = G; p.per_cta = per_cta;
+    p.ntasks = ntasks; p.ngroups = ngroups; p.D = D;
+    if (cudaMalloc(&p.d_tasks, sizeof(WaveTask) * sched.size()) != cudaSuccess ||
+        cudaMalloc(&p.d_tasks_dyn, sizeof(WaveTask) * (tasks.size() + 1)) != cudaSuccess ||
         cudaMalloc(&p.d_counters, sizeof(int) * ((size_t)k * ngroups + 4)) != cudaSuccess ||
         cudaMalloc(&p.d_group_size, sizeof(int) * (size_t)k * ngroups) != cudaSuccess) {
         *why = "plan allocation failed";
         return nullptr;
     }
-    cudaMemcpy(p.d_tasks, tasks.data(), sizeof(WaveTask) * tasks.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(p.d_tasks, sched.data(), sizeof(WaveTask) * sched.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(p.d_tasks_dyn, tasks.data(), sizeof(WaveTask) * tasks.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(p.d_group_size, gsize.data(), sizeof(int) * gsize.size(), cudaMemcpyHostToDevice);
     S.plans.push_back(p);
     return &S.plans.back();
@@ -448,7 +595,7 @@ static int wave_launch_shape(nsk_ctx_t ctx, int variant, bool muladd, int k, wav
     NSK_REQUIRE(ctx, per_sm >= 1, "wavefront kernel does not fit on an SM");
     *grid_max = ctx->prop.multiProcessorCount * per_sm;
     const double pct = ctx->opt.wave_slack_pct >= 0 ? (double)ctx->opt.wave_slack_pct : 100.0;
-    *slack = (int)((pct / 100.0) * (double)(*grid_max) * (V.stages + 1) / (double)k + 0.999);  // +1: the pre-claimed item
+    *slack = (int)((pct / 100.0) * (double)(*grid_max) * (V.stages + (ctx->opt.wave_static ? 0 : 3)) / (double)k + 0.999);  // dynamic: + the 3 pre-claimed items
     *fn_out = fn;
     *smem_out = smem;
     return NSK_OK;
@@ -461,7 +608,7 @@ bool nsk_mpk_wavefront_applicable(nsk_csr_t A, int k)
     wave_fn fn; int smem, grid_max, slack;
     const int variant = wave_variant(A->ctx);
     if (wave_launch_shape(A->ctx, variant, false, k, &fn, &smem, &grid_max, &slack) != NSK_OK) return false;
-    return get_plan(A, k, nullptr, g_wvariants[variant], slack, &why) != nullptr;
+    return get_plan(A, k, nullptr, g_wvariants[variant], slack, grid_max, &why) != nullptr;
 }
 
 int nsk_mpk_wavefront(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode,
@@ -473,25 +620,26 @@ int nsk_mpk_wavefront(nsk_csr_t A, int k, const double *d_x, double *const *d_le
     const char *why = "";
     wave_fn fn; int smem = 0, grid_max = 0, slack = 0;
     NSK_TRY(wave_launch_shape(ctx, variant, mode == NSK_EXACT_MULADD, k, &fn, &smem, &grid_max, &slack));
-    WavePlan *plan = get_plan(A, k, level_rows, V, slack, &why);
+    WavePlan *plan = get_plan(A, k, level_rows, V, slack, grid_max, &why);
     if (!plan) {
         nsk_set_error(ctx, "wavefront matrix powers not applicable: %s", why);
         return NSK_ERR_UNSUPPORTED;
     }
     const nsk_tiling *Tp = nullptr;
     NSK_TRY(nsk_get_tiling(A, V.t_nnz, V.t_rows, &Tp));
-    const int grid = std::min(plan->ntasks, grid_max);
+    const int grid = plan->grid;
 
     const size_t ncnt = (size_t)k * plan->ngroups;
     NSK_CUDA(ctx, cudaMemsetAsync(plan->d_counters, 0, sizeof(int) * (ncnt + 4), ctx->stream));
     WaveParams P;
-    P.tiles = Tp->d_tiles;
     P.tasks = plan->d_tasks;
+    P.per_cta = plan->per_cta;
+    P.tasks_dyn = plan->d_tasks_dyn;
     P.ntasks = plan->ntasks;
+    P.next = ctx->opt.wave_static ? nullptr : reinterpret_cast<unsigned int *>(plan->d_counters + ncnt);
     P.ngroups = plan->ngroups;
     P.counters = plan->d_counters;
     P.group_size = plan->d_group_size;
-    P.next = reinterpret_cast<unsigned int *>(plan->d_counters + ncnt);
     P.ptrow = A->d_ptrow;
     P.indcol = A->d_indcol;
     P.coef = A->d_coef;

@@ -47,6 +47,7 @@ struct nsk_options {
     int64_t stream_variant = 0;   // 0 auto, else 1 + index into the stream kernel table
     int64_t wave_variant = 0;     // index into the wavefront kernel table
     int64_t wave_slack_pct = -1;  // extra level skew, % of (resident CTAs x stages / k) tiles; <0 = default 150
+    int64_t wave_static = 0;      // 1 = static round-robin schedule instead of dynamic claims
     int64_t wave_l2_pct = 0;      // share of L2 the wavefront window may occupy, %; 0 = default 80
 };
 

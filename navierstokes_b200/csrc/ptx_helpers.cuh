@@ -111,6 +111,11 @@ __device__ __forceinline__ void red_release_gpu_add(int *p, int v)
 {
     asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// Plain device-scope increment; after a __threadfence() it completes a release pattern.
+__device__ __forceinline__ void red_relaxed_gpu_add(int *p, int v)
+{
+    asm volatile("red.relaxed.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 // Coherent (L2) load of data another CTA of the same grid has just published.
 __device__ __forceinline__ double ld_cg_f64(const double *p)
 {

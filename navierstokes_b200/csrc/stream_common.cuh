@@ -20,9 +20,8 @@ __device__ __forceinline__ double row_op(double a, double x, double acc)
 // NC: x is constant for the whole launch (read-only path) vs written earlier in this launch (coherent).
 template <bool MULADD, bool NC>
 __device__ __forceinline__ double row_chain(const double *val_s, const int *col_s, int p, int q, int vo, int co,
-                                            const double *src)
+                                            const double *src, double acc = 0.0)
 {
-    double acc = 0.0;
     for (int j0 = p; j0 < q; j0 += 8) {
         double xv[8];
 #pragma unroll

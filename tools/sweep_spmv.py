@@ -40,6 +40,10 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--modes", default="0")
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--wave-variants", default="0,1,2,3,4,5,6,7,8,9,10,11")
+    ap.add_argument("--slacks", default="50,100,150")
+    ap.add_argument("--skip-spmv", action="store_true")
+    ap.add_argument("--wave-static", type=int, default=0)
     args = ap.parse_args()
     t0 = time.time()
     if args.cfg == "c3":
@@ -58,7 +62,7 @@ def main():
     yref = ctx.empty(A.n)
     peak = peak_gbs()
     B = dA.spmv_bytes
-    for mode in [int(m) for m in args.modes.split(",")]:
+    for mode in ([] if args.skip_spmv else [int(m) for m in args.modes.split(",")]):
         ctx.set_option("spmv_kernel", 1)
         dA.spmv(x, yref, mode)
         ref = yref.to_host()
@@ -93,10 +97,11 @@ def main():
         print(f"mpk k={k} levels           : {ms:8.4f} ms  B_mpk rate {Bk/ms/1e6:8.1f} GB/s ({Bk/ms/1e6/peak:5.3f}), "
               f"SpMV-equivalent {k*B/ms/1e6:8.1f} GB/s", flush=True)
         ctx.set_option("mpk_kernel", 2)
+        ctx.set_option("wave_static", args.wave_static)
         ctx.set_option("wave_l2_pct", 400)  # never refuse in the sweep: we want to see the cliff
-        for wv in (1, 2, 6, 7, 8, 9, 10, 11):
+        for wv in [int(v) for v in args.wave_variants.split(",")]:
             ctx.set_option("wave_variant", wv + 1)
-            for slack in (75, 100, 125):
+            for slack in [int(v) for v in args.slacks.split(",")]:
                 ctx.set_option("wave_slack_pct", slack)
                 for l in lv:
                     ctx.lib.nsk_memset0(ctx.h, l.ptr, 8 * A.n)
