@@ -261,7 +261,7 @@ def main():
         return float(t.item())
 
     # ---- device-resident timing (value, roofline) --------------------------------------------------------
-    ctx.set_option("mpk_kernel", 2)  # fused wavefront kernel when applicable, else k launches
+    ctx.set_option("mpk_kernel", 0)  # default strategy: fused level pipeline on the packed format when it applies
     for _ in range(max(args.warmup, 3)):
         step_dev()
     sampler = ClockSampler(local_rank)
@@ -284,11 +284,25 @@ def main():
     # dominant kernel: launches per step tell which strategy ran
     per_step = launches / max(args.steps, 1)
     fused = per_step < K_POWERS
+    strategy = ctx.query("last_mpk_strategy")
+    fused_names = {2: "mpk_wavefront_kernel", 3: "mpk_pipeline_kernel", 4: "packed_kernel (level pipeline over the packed format)"}
     if fused:
-        kern_bytes, kern_ms, kern_name = mpk_bytes, ms_total / args.steps, "mpk_wavefront_kernel (1 launch per step)"
+        kern_bytes, kern_ms = mpk_bytes, ms_total / args.steps
+        kern_name = f"{fused_names.get(strategy, 'fused powers kernel')}, 1 launch per step"
     else:
-        kern_bytes, kern_ms, kern_name = spmv_bytes, ms_total / args.steps / K_POWERS, "spmv_stream_kernel (k launches per step)"
+        kern_bytes, kern_ms = spmv_bytes, ms_total / args.steps / K_POWERS
+        kern_name = ("packed_kernel" if ctx.query("last_spmv_kernel") == 3 else "spmv_stream_kernel") + f", {K_POWERS} launches per step"
     achieved = kern_bytes / kern_ms / 1e6
+    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of that kernel, from the committed ncu capture
+    tfile = ROOT / "profiles" / "traffic.json"
+    if tfile.exists() and world == 1:
+        try:
+            t = json.loads(tfile.read_text())
+            key = "fused" if fused else "spmv"
+            if t.get(key, {}).get("strategy") == (strategy if fused else ctx.query("last_spmv_kernel")):
+                traffic = t[key]["dram_bytes_per_launch"]
+        except Exception:
+            traffic = None
 
     # secondary: plain SpMV rate of the same operator (one product per launch)
     y = dlv[0]
@@ -328,7 +342,7 @@ def main():
                 "checksum": checksum},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": kern_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(kern_bytes)},
         "spmv": {"ms": spmv_ms, "achieved_GBps": spmv_bytes * world / spmv_ms / 1e6,
                  "frac_of_peak": spmv_bytes / spmv_ms / 1e6 / peak, "algorithmic_bytes": int(spmv_bytes)},

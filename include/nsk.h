@@ -97,6 +97,10 @@ int nsk_ctx_device_info(nsk_ctx_t ctx, int *sm_count, int64_t *l2_bytes, int *sm
 int nsk_ctx_set_option(nsk_ctx_t ctx, const char *name, int64_t value);
 
 /* CUDA-event timing on the context's stream (what bench.py brackets its timed regions with). */
+/* Introspection for tests / benchmarks: "last_spmv_kernel" (1 scalar, 2 stream over CSR, 3 packed),
+ * "last_mpk_strategy" (1 k launches, 2 wavefront, 3 level pipeline over CSR, 4 level pipeline over the packed
+ * format), "launches". */
+int nsk_ctx_query(nsk_ctx_t ctx, const char *name, int64_t *value);
 int nsk_event_create(nsk_ctx_t ctx, void **event);
 int nsk_event_destroy(nsk_ctx_t ctx, void *event);
 int nsk_event_record(nsk_ctx_t ctx, void *event);
@@ -126,6 +130,10 @@ int nsk_csr_shape(nsk_csr_t A, int *n, int *n_cols, int64_t *nnz);
 /* Algorithmic bytes of one product / of a depth-k powers call (SURVEY.md 8d definitions). */
 int64_t nsk_csr_spmv_bytes(nsk_csr_t A);
 int64_t nsk_csr_mpk_bytes(nsk_csr_t A, int k);
+/* Bytes of the tile-packed copy of the operator (slot-major tiles with 16-bit local column indices, the
+ * form the default kernels stream from HBM), built on first call; 0 when the operator does not pack
+ * (its tiles reference x in too many runs) and the CSR kernels are used instead. */
+int64_t nsk_csr_packed_bytes(nsk_csr_t A);
 
 /* y = A x.   x: n_cols doubles, y: n doubles. */
 int nsk_spmv(nsk_csr_t A, const double *x, double *y, nsk_mode mode, nsk_where where);

@@ -40,12 +40,14 @@ SIGNATURES = {
     "nsk_memcpy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
     "nsk_memset0": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "nsk_flush_l2": (C.c_int, [C.c_void_p]),
+    "nsk_ctx_query": (C.c_int, [C.c_void_p, C.c_char_p, c_int64_p]),
     "nsk_csr_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                  c_void_pp]),
     "nsk_csr_destroy": (C.c_int, [C.c_void_p]),
     "nsk_csr_shape": (C.c_int, [C.c_void_p, c_int_p, c_int_p, c_int64_p]),
     "nsk_csr_spmv_bytes": (C.c_int64, [C.c_void_p]),
     "nsk_csr_mpk_bytes": (C.c_int64, [C.c_void_p, C.c_int]),
+    "nsk_csr_packed_bytes": (C.c_int64, [C.c_void_p]),
     "nsk_spmv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "nsk_mpk": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, c_void_pp, C.c_int, C.c_int]),
     "nsk_bcsr4_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, c_void_pp]),

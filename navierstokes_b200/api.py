@@ -68,6 +68,12 @@ class Context:
     def set_option(self, name: str, value: int):
         self._ck(self.lib.nsk_ctx_set_option(self.h, name.encode(), int(value)))
 
+    def query(self, name: str) -> int:
+        """Introspection: 'last_spmv_kernel', 'last_mpk_strategy', 'launches' (include/nsk.h nsk_ctx_query)."""
+        v = C.c_int64()
+        self._ck(self.lib.nsk_ctx_query(self.h, name.encode(), C.byref(v)))
+        return int(v.value)
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.nsk_ctx_launch_count(self.h))
@@ -277,6 +283,11 @@ class CsrMatrix:
     @property
     def spmv_bytes(self) -> int:
         return int(self.ctx.lib.nsk_csr_spmv_bytes(self.h))
+
+    @property
+    def packed_bytes(self) -> int:
+        """Bytes of the tile-packed copy the default kernels stream (0: operator does not pack, CSR kernels run)."""
+        return int(self.ctx.lib.nsk_csr_packed_bytes(self.h))
 
     def mpk_bytes(self, k: int) -> int:
         return int(self.ctx.lib.nsk_csr_mpk_bytes(self.h, k))

@@ -133,8 +133,27 @@ NSK_API int nsk_ctx_set_option(nsk_ctx_t c, const char *name, int64_t v)
     else if (!strcmp(name, "wave_slack_pct")) c->opt.wave_slack_pct = v;
     else if (!strcmp(name, "wave_l2_pct")) c->opt.wave_l2_pct = v;
     else if (!strcmp(name, "wave_static")) c->opt.wave_static = v;
+    else if (!strcmp(name, "pipe_variant")) c->opt.pipe_variant = v;
+    else if (!strcmp(name, "packed_variant")) c->opt.packed_variant = v;
+    else if (!strcmp(name, "pipe_bp_global")) c->opt.pipe_bp_global = v;
+    else if (!strcmp(name, "pipe_w0_pct")) c->opt.pipe_w0_pct = v;
+    else if (!strcmp(name, "pk_timing")) c->opt.pk_timing = v;
+    else if (!strcmp(name, "pipe_interleave")) c->opt.pipe_interleave = v;
     else {
         nsk_set_error(c, "unknown option '%s'", name);
+        return NSK_ERR_INVALID;
+    }
+    return NSK_OK;
+}
+
+NSK_API int nsk_ctx_query(nsk_ctx_t c, const char *name, int64_t *value)
+{
+    if (!c || !name || !value) return NSK_ERR_INVALID;
+    if (!strcmp(name, "last_spmv_kernel")) *value = c->last_spmv;
+    else if (!strcmp(name, "last_mpk_strategy")) *value = c->last_mpk;
+    else if (!strcmp(name, "launches")) *value = (int64_t)c->launches;
+    else {
+        nsk_set_error(c, "unknown query '%s'", name);
         return NSK_ERR_INVALID;
     }
     return NSK_OK;

@@ -22,6 +22,7 @@ std::vector<int> &nsk_csr_host_ptrow(nsk_csr_t A)
 int nsk_mpk_device(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode);  // mpk.cu
 void nsk_wave_set_block_extents(nsk_csr_t A, const int *ptrow, const int *indcol);                  // mpk_wavefront.cu
 void nsk_wave_free(nsk_csr_t A);
+void nsk_pipe_free(nsk_csr_t A);  // mpk_pipeline.cu
 
 NSK_API int nsk_csr_create(nsk_ctx_t ctx, int n, int n_cols, int64_t nnz, const int *ptrow,
                            const int *indcol, const double *coef, nsk_csr_t *out)
@@ -91,6 +92,8 @@ NSK_API int nsk_csr_destroy(nsk_csr_t A)
     cudaStreamSynchronize(ctx->stream);
     nsk_dist_free(A);
     nsk_wave_free(A);
+    nsk_pipe_free(A);
+    nsk_packed_free(A);
     if (A->d_ptrow) cudaFree(A->d_ptrow);
     if (A->d_indcol) cudaFree(A->d_indcol);
     if (A->d_coef) cudaFree(A->d_coef);
@@ -123,6 +126,13 @@ NSK_API int64_t nsk_csr_mpk_bytes(nsk_csr_t A, int k)
 {
     if (!A) return 0;
     return 12 * A->nnz + 4 * ((int64_t)A->n + 1) + 8 * (int64_t)A->n + 8 * (int64_t)A->n * k;
+}
+
+NSK_API int64_t nsk_csr_packed_bytes(nsk_csr_t A)
+{
+    if (!A) return 0;
+    cudaSetDevice(A->ctx->device);
+    return (int64_t)nsk_packed_bytes(A);
 }
 
 int nsk_halo_exchange_dev(nsk_csr_t A, double *xlocal, int depth);  // dist.cu

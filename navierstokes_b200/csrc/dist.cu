@@ -9,11 +9,8 @@
 #include "dist_plan.h"
 #include "nsk_internal.h"
 
-int nsk_mpk_levels(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode,
-                   const int *level_rows);  // mpk.cu
-int nsk_mpk_wavefront(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode,
-                      const int *level_rows);  // mpk_wavefront.cu
-bool nsk_mpk_wavefront_applicable(nsk_csr_t A, int k);
+int nsk_mpk_local(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode,
+                  const int *level_rows);  // mpk.cu
 void nsk_wave_set_block_extents(nsk_csr_t A, const int *ptrow, const int *indcol);
 int nsk_comm_rank(nsk_ctx_t ctx);
 int nsk_comm_size(nsk_ctx_t ctx);
@@ -179,11 +176,5 @@ int nsk_dist_mpk(nsk_csr_t A, int k, const double *d_x, double *const *d_levels,
     NSK_TRY(nsk_halo_exchange_dev(A, const_cast<double *>(d_x), k));
     int level_rows[NSK_MAX_K];
     for (int l = 0; l < k; l++) level_rows[l] = D->ring_start[k - l];
-    int sel = (int)ctx->opt.mpk_kernel;
-    if (sel == 0) sel = 2;
-    if (sel == 2 && k > 1 && nsk_mpk_wavefront_applicable(A, k)) {
-        int s = nsk_mpk_wavefront(A, k, d_x, d_levels, mode, level_rows);
-        if (s != NSK_ERR_UNSUPPORTED) return s;
-    }
-    return nsk_mpk_levels(A, k, d_x, d_levels, mode, level_rows);
+    return nsk_mpk_local(A, k, d_x, d_levels, mode, level_rows);
 }

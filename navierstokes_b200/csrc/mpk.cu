@@ -8,6 +8,8 @@
 //
 // Strategy 1 ("levels"): k launches of the streaming SpMV kernel back to back on one stream; the
 //   operator is re-read from HBM k times.
+// Strategy 3 ("level pipeline", default): see mpk_pipeline.cu -- one persistent launch, CTAs specialised by
+//   level, chained by completion counters with back-pressure so the window stays in L2.
 // Strategy 2 ("wavefront"): see mpk_wavefront.cu -- one persistent launch that sweeps row chunks in
 //   a skewed (chunk + level) order so that a chunk's col/val slice is still L2-resident (126 MB)
 //   when the next level needs it; HBM sees the operator once.
@@ -16,6 +18,9 @@
 int nsk_mpk_wavefront(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode,
                       const int *level_rows);  // mpk_wavefront.cu
 bool nsk_mpk_wavefront_applicable(nsk_csr_t A, int k);
+int nsk_mpk_pipeline(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode,
+                     const int *level_rows);  // mpk_pipeline.cu
+bool nsk_mpk_pipeline_applicable(nsk_csr_t A, int k);
 int nsk_dist_mpk(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode);  // dist.cu
 
 int nsk_mpk_levels(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode,
@@ -35,15 +40,36 @@ int nsk_mpk_levels(nsk_csr_t A, int k, const double *d_x, double *const *d_level
     return NSK_OK;
 }
 
-int nsk_mpk_device(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode)
+// Picks the strategy: option mpk_kernel = 0 auto (4, then 3, then 1), 1 levels, 2 wavefront, 3 level pipeline on
+// CSR, 4 level pipeline on the packed format (packed.cu).  A fused
+// kernel that does not apply to the pattern (window larger than its L2 budget, long rows) degrades to k
+// launches -- still a GPU path.  level_rows: distributed slabs evaluate level l on a row prefix.
+int nsk_mpk_local(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode,
+                  const int *level_rows)
 {
     nsk_ctx_t ctx = A->ctx;
-    if (A->dist) return nsk_dist_mpk(A, k, d_x, d_levels, mode);
     int sel = (int)ctx->opt.mpk_kernel;
-    if (sel == 0) sel = 2;  // fused wavefront kernel whenever the pattern allows it
-    if (sel == 2 && k > 1 && nsk_mpk_wavefront_applicable(A, k)) {
-        int s = nsk_mpk_wavefront(A, k, d_x, d_levels, mode, nullptr);
-        if (s != NSK_ERR_UNSUPPORTED) return s;
+    const bool automatic = sel == 0;
+    if (automatic) sel = 4;
+    if (sel == 4 && k > 1 && nsk_packed_applicable(A)) {
+        int s = nsk_packed_run(A, k, d_x, d_levels, mode, level_rows, nullptr, -1);
+        if (s != NSK_ERR_UNSUPPORTED) { ctx->last_mpk = 4; return s; }
     }
-    return nsk_mpk_levels(A, k, d_x, d_levels, mode, nullptr);
+    if (automatic) sel = 3;
+    if (sel == 3 && k > 1 && nsk_mpk_pipeline_applicable(A, k)) {
+        int s = nsk_mpk_pipeline(A, k, d_x, d_levels, mode, level_rows);
+        if (s != NSK_ERR_UNSUPPORTED) { ctx->last_mpk = 3; return s; }
+    }
+    if (sel == 2 && k > 1 && nsk_mpk_wavefront_applicable(A, k)) {
+        int s = nsk_mpk_wavefront(A, k, d_x, d_levels, mode, level_rows);
+        if (s != NSK_ERR_UNSUPPORTED) { ctx->last_mpk = 2; return s; }
+    }
+    ctx->last_mpk = 1;
+    return nsk_mpk_levels(A, k, d_x, d_levels, mode, level_rows);
+}
+
+int nsk_mpk_device(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode)
+{
+    if (A->dist) return nsk_dist_mpk(A, k, d_x, d_levels, mode);
+    return nsk_mpk_local(A, k, d_x, d_levels, mode, nullptr);
 }

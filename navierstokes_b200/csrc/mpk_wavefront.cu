@@ -37,8 +37,9 @@
 using namespace nskptx;
 
 std::vector<int> &nsk_csr_host_ptrow(nsk_csr_t A);
+void nsk_pipe_free(nsk_csr_t A);  // mpk_pipeline.cu
 
-constexpr int WF_GROUP = 16;  // tiles per completion counter
+#include "wave_common.h"
 
 struct WaveTask {               // 32 bytes: everything an item needs in one go (two 16-byte loads)
     int row0, nrows, nz0, nz1;  // the tile (copied from the tiling so an item costs no second lookup)
@@ -62,47 +63,6 @@ struct WaveParams {
     int level_rows[NSK_MAX_K];
     int k;
 };
-
-// Rows of one pass of a consumer thread: RPT rows, the gathers of their first 8 nonzeros all in flight
-// before the first dependent multiply-add (the chain of each row stays strictly sequential).
-template <bool MULADD, bool NC, int RPT, int NCT>
-__device__ __forceinline__ void consume_tile(const double *val_s, const int *col_s, const int *ptr_s, int vo, int co,
-                                             int po, int row0, int nrows, int row_end, const double *src, double *dst,
-                                             int ctid)
-{
-    for (int rb = 0; rb < nrows; rb += NCT * RPT) {
-        int p[RPT], q[RPT];
-        double xv[RPT][8];
-#pragma unroll
-        for (int u = 0; u < RPT; u++) {
-            const int r = rb + u * NCT + ctid;
-            const int row = row0 + r;
-            const bool valid = r < nrows && row < row_end;
-            p[u] = valid ? ptr_s[row - po] : 0;
-            q[u] = valid ? ptr_s[row + 1 - po] : -1;  // q < p marks "no row": nothing gathered, nothing stored
-        }
-#pragma unroll
-        for (int u = 0; u < RPT; u++)
-#pragma unroll
-            for (int e = 0; e < 8; e++) {
-                const int j = p[u] + e;
-                xv[u][e] = 0.0;
-                if (j < q[u]) {
-                    const int c = col_s[j - co];
-                    xv[u][e] = NC ? __ldg(src + c) : src[c];
-                }
-            }
-#pragma unroll
-        for (int u = 0; u < RPT; u++) {
-            double acc = 0.0;
-#pragma unroll
-            for (int e = 0; e < 8; e++)
-                if (p[u] + e < q[u]) acc = row_op<MULADD>(val_s[p[u] + e - vo], xv[u][e], acc);
-            if (q[u] > p[u] + 8) acc = row_chain<MULADD, NC>(val_s, col_s, p[u] + 8, q[u], vo, co, src, acc);
-            if (q[u] >= p[u]) dst[row0 + rb + u * NCT + ctid] = acc;
-        }
-    }
-}
 
 template <int T_NNZ, int T_ROWS, int STAGES, int NCW, int MINB, int RPT, bool MULADD>
 __global__ void __launch_bounds__((NCW + 3) * 32, MINB) mpk_wavefront_kernel(const WaveParams P)
@@ -374,6 +334,8 @@ static std::map<nsk_csr_t, WaveState> g_wave;
 void nsk_wave_set_block_extents(nsk_csr_t A, const int *ptrow, const int *indcol)
 {
     WaveState &S = g_wave[A];
+    nsk_pipe_free(A);  // plans of the level-pipeline kernel were built from the old extents
+    nsk_packed_free(A);
     S.plans.clear();
     S.blk_row0.clear(); S.blk_min.clear(); S.blk_max.clear();
     const int n = A->n;
@@ -410,6 +372,62 @@ void nsk_wave_free(nsk_csr_t A)
         if (p.d_group_size) cudaFree(p.d_group_size);
     }
     g_wave.erase(it);
+}
+
+// Dependency geometry of a tiling, shared by the wavefront and the level-pipeline kernels: tile order in
+// global row order (positions), and for every tile the range of position GROUPS its columns fall into.
+bool nsk_wave_deps(nsk_csr_t A, const nsk_tiling &T, WaveDeps &out, const char **why)
+{
+    WaveState &S = g_wave[A];
+    if (S.blk_row0.empty()) { *why = "column extents were not recorded"; return false; }
+    if (T.nlong) { *why = "operator has rows longer than a stage"; return false; }
+    const int ntiles = T.ntiles;
+    if (ntiles == 0) { *why = "empty operator"; return false; }
+    const int ngroups = (ntiles + WF_GROUP - 1) / WF_GROUP;
+    const bool ranked = !A->row_rank.empty();
+
+    // POSITION of a tile = its place in global row order (identity for a single-GPU operator; for a
+    // distributed slab the ghost rings, stored after the owned rows, slot in below / above them).
+    // Tiles never straddle a break, so a tile is a contiguous run in rank space too.
+    std::vector<int> tile_at_pos(ntiles), pos_of_tile(ntiles), key(ntiles);
+    for (int t = 0; t < ntiles; t++) {
+        tile_at_pos[t] = t;
+        key[t] = ranked ? A->row_rank[T.h_tiles[t].row0] : T.h_tiles[t].row0;
+    }
+    if (ranked) std::sort(tile_at_pos.begin(), tile_at_pos.end(), [&](int a, int b) { return key[a] < key[b]; });
+    std::vector<int> pos_key(ntiles);
+    for (int p = 0; p < ntiles; p++) {
+        pos_of_tile[tile_at_pos[p]] = p;
+        pos_key[p] = key[tile_at_pos[p]];
+    }
+    auto pos_of_rank = [&](int rank) {
+        int p = (int)(std::upper_bound(pos_key.begin(), pos_key.end(), rank) - pos_key.begin()) - 1;
+        return p < 0 ? 0 : p;
+    };
+    std::vector<int> glo(ntiles), ghi(ntiles);  // indexed by tile
+    int reach = 0;
+    for (int t = 0; t < ntiles; t++) {
+        const nsk_tile &tl = T.h_tiles[t];
+        int mn = INT32_MAX, mx = -1;
+        size_t b = (size_t)(std::upper_bound(S.blk_row0.begin(), S.blk_row0.end(), tl.row0) - S.blk_row0.begin()) - 1;
+        for (; b < S.blk_row0.size() && S.blk_row0[b] < tl.row0 + tl.nrows; b++) {
+            mn = std::min(mn, S.blk_min[b]);
+            mx = std::max(mx, S.blk_max[b]);
+        }
+        if (mx < 0) { mn = key[t]; mx = key[t]; }  // rows without (local) entries depend on nothing
+        glo[t] = pos_of_rank(mn) / WF_GROUP;
+        ghi[t] = pos_of_rank(mx) / WF_GROUP;
+        const int last_needed = std::min(ntiles - 1, (ghi[t] + 1) * WF_GROUP - 1);
+        reach = std::max(reach, last_needed - pos_of_tile[t]);
+    }
+    out.ntiles = ntiles;
+    out.ngroups = ngroups;
+    out.reach = reach;
+    out.tile_at_pos.swap(tile_at_pos);
+    out.pos_of_tile.swap(pos_of_tile);
+    out.glo.swap(glo);
+    out.ghi.swap(ghi);
+    return true;
 }
 
 struct WaveVariant {
@@ -481,46 +499,10 @@ static WavePlan *get_plan(nsk_csr_t A, int k, const int *level_rows, const WaveV
     const nsk_tiling *Tp = nullptr;
     if (nsk_get_tiling(A, V.t_nnz, V.t_rows, &Tp) != NSK_OK) { *why = "tiling failed"; return nullptr; }
     const nsk_tiling &T = *Tp;
-    if (T.nlong) { *why = "operator has rows longer than a stage"; return nullptr; }
-    const int ntiles = T.ntiles;
-    if (ntiles == 0) { *why = "empty operator"; return nullptr; }
-    const int ngroups = (ntiles + WF_GROUP - 1) / WF_GROUP;
-    const bool ranked = !A->row_rank.empty();
-
-    // POSITION of a tile = its place in global row order (identity for a single-GPU operator; for a
-    // distributed slab the ghost rings, stored after the owned rows, slot in below / above them).
-    // Tiles never straddle a break, so a tile is a contiguous run in rank space too.
-    std::vector<int> tile_at_pos(ntiles), pos_of_tile(ntiles), key(ntiles);
-    for (int t = 0; t < ntiles; t++) {
-        tile_at_pos[t] = t;
-        key[t] = ranked ? A->row_rank[T.h_tiles[t].row0] : T.h_tiles[t].row0;
-    }
-    if (ranked) std::sort(tile_at_pos.begin(), tile_at_pos.end(), [&](int a, int b) { return key[a] < key[b]; });
-    std::vector<int> pos_key(ntiles);
-    for (int p = 0; p < ntiles; p++) {
-        pos_of_tile[tile_at_pos[p]] = p;
-        pos_key[p] = key[tile_at_pos[p]];
-    }
-    auto pos_of_rank = [&](int rank) {
-        int p = (int)(std::upper_bound(pos_key.begin(), pos_key.end(), rank) - pos_key.begin()) - 1;
-        return p < 0 ? 0 : p;
-    };
-    std::vector<int> glo(ntiles), ghi(ntiles);  // indexed by tile
-    int reach = 0;
-    for (int t = 0; t < ntiles; t++) {
-        const nsk_tile &tl = T.h_tiles[t];
-        int mn = INT32_MAX, mx = -1;
-        size_t b = (size_t)(std::upper_bound(S.blk_row0.begin(), S.blk_row0.end(), tl.row0) - S.blk_row0.begin()) - 1;
-        for (; b < S.blk_row0.size() && S.blk_row0[b] < tl.row0 + tl.nrows; b++) {
-            mn = std::min(mn, S.blk_min[b]);
-            mx = std::max(mx, S.blk_max[b]);
-        }
-        if (mx < 0) { mn = key[t]; mx = key[t]; }  // rows without (local) entries depend on nothing
-        glo[t] = pos_of_rank(mn) / WF_GROUP;
-        ghi[t] = pos_of_rank(mx) / WF_GROUP;
-        const int last_needed = std::min(ntiles - 1, (ghi[t] + 1) * WF_GROUP - 1);
-        reach = std::max(reach, last_needed - pos_of_tile[t]);
-    }
+    WaveDeps Dp;
+    if (!nsk_wave_deps(A, T, Dp, why)) return nullptr;
+    const int ntiles = Dp.ntiles, ngroups = Dp.ngroups, reach = Dp.reach;
+    const std::vector<int> &tile_at_pos = Dp.tile_at_pos, &glo = Dp.glo, &ghi = Dp.ghi;
     const int D = reach + 1 + slack;
     // The window that must stay in L2: (k-1)*D tiles of matrix data plus k level vectors of it.
     const double tile_bytes = 12.0 * A->mean_row * V.t_rows + 8.0 * V.t_rows * (k + 1);

@@ -41,9 +41,18 @@ void nsk_set_error(nsk_ctx_t ctx, const char *fmt, ...);
 struct nsk_comm_s;  // comm.cpp
 
 struct nsk_options {
-    int64_t spmv_kernel = 0;      // 0 auto, 1 scalar (thread/row from global), 2 stream (TMA pipeline)
+    int64_t spmv_kernel = 0;      // 0 auto (packed when applicable, else stream), 1 scalar (thread/row from global),
+                                  // 2 stream (CSR slices by TMA, x gathered from global), 3 packed (x runs staged too)
+    int64_t packed_variant = 0;   // 0 default, else 1 + index into the packed kernel table
     int64_t spmv_ctas_per_sm = 0; // 0 = kernel default
-    int64_t mpk_kernel = 0;       // 0 auto, 1 = k separate products, 2 = L2 wavefront
+    int64_t mpk_kernel = 0;       // 0 auto (4, 3, 1 in that order), 1 = k separate products, 2 = L2 wavefront,
+                                  // 3 = level pipeline on CSR, 4 = level pipeline on the packed format
+    int64_t pipe_variant = 0;     // 0 default, else 1 + index into the level-pipeline kernel table
+    int64_t pk_timing = 0;        // 1: packed kernel records its stage cycle and prints per-level averages (debug)
+    int64_t pipe_w0_pct = 0;      // share weight of level 0's team relative to 100 for every other level; 0 = default
+    int64_t pipe_bp_global = -1;  // back-pressure of the packed level pipeline: 0 = level l held by l+1, 1 = level 0 held
+                                  // by k-1 (one window for the whole pipeline), < 0 = default (1)
+    int64_t pipe_interleave = 1;  // 1: level = blockIdx % k (each SM hosts every level), 0: level = blockIdx / team
     int64_t stream_variant = 0;   // 0 auto, else 1 + index into the stream kernel table
     int64_t wave_variant = 0;     // index into the wavefront kernel table
     int64_t wave_slack_pct = -1;  // extra level skew, % of (resident CTAs x stages / k) tiles; <0 = default 150
@@ -57,6 +66,8 @@ struct nsk_ctx_s {
     cudaStream_t stream = nullptr;
     cudaDeviceProp prop{};
     uint64_t launches = 0;
+    int last_spmv = 0;  // kernel family of the last product: 1 scalar, 2 stream (CSR), 3 packed
+    int last_mpk = 0;   // strategy of the last powers call: 1 levels, 2 wavefront, 3 CSR level pipeline, 4 packed level pipeline
     std::string last_error;
     nsk_options opt;
     // scratch for reductions: partial sums + ticket + result slots (device) and pinned mirror
@@ -139,6 +150,12 @@ struct nsk_spmv_args {
     int dot_slot = -1;  // index into ctx->d_scalars receiving the finished sum
 };
 int nsk_launch_spmv(nsk_csr_t A, const nsk_spmv_args &a);
+// packed.cu: k = 1 is the plain product (optionally with the fused dot); NSK_ERR_UNSUPPORTED = use the CSR kernels
+int nsk_packed_run(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode, const int *level_rows,
+                   const double *dot_w, int dot_slot);
+bool nsk_packed_applicable(nsk_csr_t A);
+size_t nsk_packed_bytes(nsk_csr_t A);
+void nsk_packed_free(nsk_csr_t A);
 int nsk_get_tiling(nsk_csr_t A, int t_nnz, int t_rows, const nsk_tiling **out);  // cached per geometry
 void nsk_free_tilings(nsk_csr_t A);
 void nsk_stream_kernel_config(nsk_ctx_t ctx, double mean_row, int *tile_nnz, int *tile_rows);

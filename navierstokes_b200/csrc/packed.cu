@@ -1,0 +1,902 @@
+// packed.cu -- tile-packed operator format + ONE persistent kernel for y = A x and for the fused matrix powers
+// A x, A^2 x, ..., A^k x, in which the consumer warps never touch global memory for their inputs.
+//
+// Replaces SpMV_CSR / _OPT / _FMA / _AVX2 (reference mpk/SpMV.cpp:6-85) and the fused SpM2V_CSR* / SpM3V /
+// SpM4V (mpk/SpM2V.cpp:80-332, mpk/SpMVmulti0.cpp:132-221) for operators whose tiles reference x in a few
+// contiguous runs (stencils on structured grids, banded / block-banded matrices).  Everything else keeps the
+// CSR kernels (spmv_kernels.cu, mpk_pipeline.cu); both are GPU paths.
+//
+// Why.  Every CSR kernel here gathers x[col] with one global load per nonzero.  ncu on the 256^3 7-point
+// operator (profiles/r01_ncu_mpk_wavefront_c_summary.txt) shows those kernels bound by the LATENCY of that
+// gather: ~1 us per round trip, one row per thread in flight, the rows in flight per SM capped by the shared
+// memory their matrix slices occupy -- 67 k rows/us whatever the schedule, i.e. 0.25 ms per product with HBM at
+// 85 % and L2 at 40 %.  The fix is to take the gather off the SM's load path altogether:
+//
+//   * at plan time every tile (<= T_ROWS consecutive rows) gets the list of contiguous column runs (SEGMENTS)
+//     its nonzeros reference -- 3 runs for a 7-point stencil -- and its column indices are rewritten as 16-bit
+//     offsets into the concatenation of those runs;
+//   * the tile is stored as one contiguous BLOB in slot-major (sliced-ELL) order: lens[r], lcol[e][r], val[e][r];
+//     per-row nonzero order is untouched, so the fma chain is bit-identical to the reference's row loop
+//     (10 B/nnz instead of CSR's 12: the operator costs 17 % less HBM traffic as a side effect);
+//   * a stage = blob + x runs, all moved by 1-D bulk async copies (TMA): one for the blob, one per run.  The
+//     copies of the x runs are issued by the dependency warp the moment the tile's inputs are complete, so the
+//     latency of reading another SM's output is hidden by the stage ring, not by resident warps;
+//   * consumer threads (one row each) read lens/lcol/val/x from shared memory only: conflict-free for stencils
+//     (consecutive rows -> consecutive addresses in every array), no long-scoreboard stall at all.
+//
+// Matrix powers use the level pipeline of mpk_pipeline.cu unchanged: CTAs specialised by level, per-group
+// completion counters, back-pressure `lead` that keeps the (k-1)*lead window L2-resident.  k = 1 is the plain
+// product (no counters, no fences).
+#include <algorithm>
+#include <atomic>
+#include <map>
+#include <thread>
+
+#include "nsk_internal.h"
+#include "ptx_helpers.cuh"
+#include "stream_common.cuh"
+#include "wave_common.h"
+
+using namespace nskptx;
+
+std::vector<int> &nsk_csr_host_ptrow(nsk_csr_t A);
+
+constexpr int PK_MAXSEG = 8;
+
+struct PkTile {                   // 96 bytes; words 0..23 are fetched one per lane by the dependency warp
+    long long blob_off;           // w0,1   bytes from the blob base, 16-byte aligned
+    int blob_bytes;               // w2     multiple of 16
+    int nseg;                     // w3
+    int row0, nrows, xlen, pad;   // w4..7  xlen: total doubles of all runs (each run a multiple of 2)
+    int seg_start[PK_MAXSEG];     // w8..15 first column of the run (even)
+    int seg_lenoff[PK_MAXSEG];    // w16..23 length | offset in the stage's x buffer << 16 (doubles)
+};
+static_assert(sizeof(PkTile) == 96, "PkTile is 24 words");
+
+struct PkItem {            // 32 bytes = two 16-byte loads; one per (level, tile)
+    int tile, pos;         // tile index; position in global row order (completion group = pos / WF_GROUP)
+    int ghi, gback;        // forward: groups [0, ghi] of level l-1 complete; back-pressure: [0, gback] of level l+1
+    long long blob_off;
+    int blob_bytes, pad;
+};
+static_assert(sizeof(PkItem) == 32, "PkItem is two int4");
+
+struct PkParams {
+    const PkItem *items[NSK_MAX_K];  // per level, ascending position
+    int count[NSK_MAX_K];
+    const PkTile *tiles;
+    const unsigned char *blobs;
+    int *counters;          // [k][ngroups], zeroed before the launch (unused for k = 1)
+    const int *group_size;  // [k][ngroups]
+    int ngroups;
+    const double *x;
+    double *levels[NSK_MAX_K];
+    int level_rows[NSK_MAX_K];
+    int k;
+    int team[NSK_MAX_K];   // CTAs of each level (level 0 streams from HBM and gets more stages in flight)
+    const int2 *cta_role;  // [grid] {level, index within the level's team}
+    int bp_global;   // 1: only level 0 is held back, by level k-1 (one window for the whole pipeline); 0: level l by l+1
+    // optional stage-cycle instrumentation (tools/pk_timing.py): 8 sums of nanoseconds + item count per CTA
+    unsigned long long *timing;
+    // fused dot <dot_w, levels[0]> (k = 1 only; CG: p.Ap)
+    const double *dot_w;
+    double *partials;
+    unsigned int *ticket;
+    double *dot_out;
+};
+
+// blob header (16 ints at the start of every blob)
+enum { PKH_ROW0 = 0, PKH_NROWS, PKH_WIDTH, PKH_RP, PKH_OFF_LENS, PKH_OFF_LCOL, PKH_OFF_VAL, PKH_WORDS = 16 };
+
+__host__ __device__ constexpr int pk_round_up(int v, int m) { return (v + m - 1) / m * m; }
+static inline int pk_blob_bytes(int nrows, int width)
+{
+    const int rp = pk_round_up(nrows, 32);
+    return PKH_WORDS * 4 + 2 * rp + 2 * width * rp + 8 * width * rp;  // every term is a multiple of 16
+}
+
+__device__ __forceinline__ unsigned long long pk_now()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ int pk_wait_groups(const int *cnt, const int *need, int ngroups, int w, int upto, int lane)
+{
+    uint32_t spins = 0;
+    while (w <= upto) {
+        const int g = w + lane;
+        bool ok = true;
+        if (g < ngroups) ok = ld_acquire_gpu(cnt + g) >= __ldg(need + g);
+        const unsigned int bad = __ballot_sync(0xffffffffu, !ok);
+        const int adv = bad ? __ffs(bad) - 1 : 32;
+        w = min(w + adv, ngroups);
+        if (w > upto || w >= ngroups) break;
+        if (adv == 0) {
+            __nanosleep(32);
+            if (++spins > (1u << 24)) __trap();  // protocol bug: fail the launch, never hang
+        }
+    }
+    return w;
+}
+
+template <int T_ROWS, int BLOB_CAP, int XCAP, int STAGES, int NCW, int MINB, int RPT, bool MULADD>
+__global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkParams P)
+{
+    constexpr int STAGE_BYTES = BLOB_CAP + XCAP * 8;
+    static_assert(BLOB_CAP % 128 == 0 && (XCAP * 8) % 128 == 0, "stage parts keep 128-byte alignment");
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)STAGE_BYTES * STAGES);  // blob + x runs landed
+    uint64_t *done = full + STAGES;                                                      // consumers stored their rows
+    double *red = reinterpret_cast<double *>(done + STAGES);
+    unsigned long long *ts = reinterpret_cast<unsigned long long *>(red + 64);  // [STAGES][4] timestamps (timing only)
+    // per stage: consumer warps that finished it, counted over the whole launch (monotone, so the publisher can
+    // fall behind the stage ring without a phase ever aliasing)
+    unsigned int *fin = reinterpret_cast<unsigned int *>(ts + STAGES * 4);
+    const bool timing = P.timing != nullptr;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(&full[s], 2);  // producer (blob bytes) + dependency warp (x bytes)
+            mbar_init(&done[s], NCW);
+            fin[s] = 0u;
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const int2 role = __ldg(P.cta_role + blockIdx.x);
+    const int level = role.x;
+    const int c = role.y;
+    const int G = P.team[level];
+    const int count = P.count[level];
+    const int n_my = c < count ? (count - c + G - 1) / G : 0;
+    const int4 *my = reinterpret_cast<const int4 *>(P.items[level]);  // item i of this CTA = my[2 * (c + i * G) ...]
+
+    if (warp == NCW) {
+        // ===== producer (one lane).  The blob of a tile depends on no flag: a stage is refilled the moment its
+        // previous item is done. =====
+        if (lane != 0) return;
+        int it_load = 0;
+        int4 db = make_int4(0, 0, 0, 0), nb = db;
+        if (n_my > 0) db = my[2 * (size_t)c + 1];
+        if (n_my > 1) nb = my[2 * (size_t)(c + G) + 1];
+        unsigned long long acc[5] = {0, 0, 0, 0, 0};
+        for (; it_load < n_my; ++it_load) {
+            const int s = it_load % STAGES;
+            if (it_load >= STAGES) {
+                mbar_wait(&done[s], ((it_load / STAGES) - 1) & 1);
+                if (timing) {
+                    const unsigned long long t4 = pk_now();
+                    const volatile unsigned long long *v = ts + s * 4;
+                    acc[0] += v[1] - v[0];  // blob issue -> x issue (stage waits for its inputs / the dependency warp)
+                    acc[1] += v[2] - v[1];  // x issue -> consumers see the stage full (bulk-copy latency)
+                    acc[2] += v[3] - v[2];  // consume (warp 0)
+                    acc[3] += t4 - v[3];    // warp 0 finished -> producer sees every warp done
+                    acc[4] += t4 - v[0];    // whole stage cycle
+                }
+            }
+            const long long off = ((long long)(unsigned int)db.x) | ((long long)db.y << 32);
+            mbar_arrive_expect_tx(&full[s], (uint32_t)db.z);
+            bulk_g2s(smem + (size_t)s * STAGE_BYTES, P.blobs + off, (uint32_t)db.z, &full[s]);
+            if (timing) ts[s * 4 + 0] = pk_now();
+            db = nb;
+            if (it_load + 2 < n_my) nb = my[2 * ((size_t)c + (size_t)(it_load + 2) * G) + 1];
+        }
+        if (timing) {
+            for (int j = 0; j < 5; j++) P.timing[(size_t)blockIdx.x * 16 + j] = acc[j];
+            P.timing[(size_t)blockIdx.x * 16 + 8] = (unsigned long long)(n_my > STAGES ? n_my - STAGES : 0);
+            P.timing[(size_t)blockIdx.x * 16 + 9] = (unsigned long long)level;
+        }
+        return;
+    }
+
+    if (warp == NCW + 2) {
+        // ===== publisher (k > 1): makes finished items visible to the other SMs.  The gpu-scope fence (~0.5 us) is
+        // paid here -- off the consumers' path and off the refill path -- ONCE for all items found finished at
+        // that moment: consumers bump fin[s] with release.cta after their stores; this warp's acquire of fin[s]
+        // followed by fence + RED is cumulative over those stores. =====
+        if (P.k <= 1) return;
+        int *cnt = P.counters + (size_t)level * P.ngroups;
+        int pos_cur = 0;  // lane u: position of item it0 + u
+        unsigned long long tf = 0;
+        for (int it = 0; it < n_my;) {
+            const int j = it & 31;
+            if (j == 0) {
+                pos_cur = 0;
+                if (it + lane < n_my) pos_cur = my[2 * ((size_t)c + (size_t)(it + lane) * G)].y;
+            }
+            int n = 0;
+            uint32_t spins = 0;
+            for (;;) {  // items finish in order per stage; take every consecutive finished one (at most to the batch end)
+                const int i2 = it + n;
+                bool ok = false;
+                if (i2 < n_my && (n == 0 || (i2 & 31) != 0) && n < STAGES) {
+                    const unsigned int need = (unsigned int)NCW * (unsigned int)(i2 / STAGES + 1);
+                    ok = ld_acquire_cta_shared_u32(&fin[i2 % STAGES]) >= need;
+                }
+                ok = __shfl_sync(0xffffffffu, (int)ok, 0) != 0;
+                if (ok) { ++n; continue; }
+                if (n > 0) break;
+                if (++spins > (1u << 26)) __trap();
+            }
+            const unsigned long long t5 = timing ? pk_now() : 0ull;
+            if (lane == 0) __threadfence();
+            __syncwarp();
+            for (int u = 0; u < n; u++) {
+                const int pos = __shfl_sync(0xffffffffu, pos_cur, (it + u) & 31);
+                if (lane == 0) red_relaxed_gpu_add(cnt + pos / WF_GROUP, 1);
+            }
+            if (timing) tf += pk_now() - t5;
+            it += n;
+        }
+        if (timing && lane == 0) P.timing[(size_t)blockIdx.x * 16 + 5] = tf;
+        return;
+    }
+
+    if (warp == NCW + 1) {
+        // ===== dependency warp: once item `it`'s forward inputs (level - 1) are complete and the next level is
+        // not more than `lead` tiles behind, it copies the tile's x runs into the stage -- the consumers only wait
+        // for bytes. =====
+        const bool fwd = level > 0;
+        const bool back = P.bp_global ? (level == 0 && P.k > 1) : (level < P.k - 1);
+        const int lb = P.bp_global ? P.k - 1 : level + 1;  // the level whose progress holds this one back
+        const int *cnt_f = P.counters + (size_t)(fwd ? level - 1 : 0) * P.ngroups;
+        const int *need_f = P.group_size + (size_t)(fwd ? level - 1 : 0) * P.ngroups;
+        const int *cnt_b = P.counters + (size_t)(back ? lb : 0) * P.ngroups;
+        const int *need_b = P.group_size + (size_t)(back ? lb : 0) * P.ngroups;
+        const double *src = level == 0 ? P.x : P.levels[level - 1];
+        const int *tw = reinterpret_cast<const int *>(P.tiles);
+        int wf = 0, wb = 0;
+        unsigned long long w_done = 0, w_dep = 0;
+        int4 cur = make_int4(0, 0, 0, -1), nxt = cur;  // lane u: item it0 + u (cur) and it0 + 32 + u (nxt)
+        if (lane < n_my) cur = my[2 * ((size_t)c + (size_t)lane * G)];
+        if (32 + lane < n_my) nxt = my[2 * ((size_t)c + (size_t)(32 + lane) * G)];
+        int cw = 0, nw = 0;  // lane u < 24: word u of the PkTile of the current / next item
+        if (n_my > 0) {
+            const int t0 = __shfl_sync(0xffffffffu, cur.x, 0);
+            if (lane < 24) cw = __ldg(tw + (size_t)t0 * 24 + lane);
+        }
+        for (int it = 0; it < n_my; ++it) {
+            const int j = it & 31;
+            if (j == 0 && it > 0) {
+                cur = nxt;
+                nxt = make_int4(0, 0, 0, -1);
+                if (it + 32 + lane < n_my) nxt = my[2 * ((size_t)c + (size_t)(it + 32 + lane) * G)];
+            }
+            // prefetch the tile descriptor of item it + 1 (its latency hides behind this item's waits)
+            if (it + 1 < n_my) {
+                const int tn_cur = __shfl_sync(0xffffffffu, cur.x, (j + 1) & 31);
+                const int tn_nxt = __shfl_sync(0xffffffffu, nxt.x, 0);
+                const int tn = j + 1 < 32 ? tn_cur : tn_nxt;
+                if (lane < 24) nw = __ldg(tw + (size_t)tn * 24 + lane);
+            }
+            const int ghi = __shfl_sync(0xffffffffu, cur.z, j);
+            const int gback = __shfl_sync(0xffffffffu, cur.w, j);
+            const int s = it % STAGES;
+            // inputs first: the poll (an L2 round trip whenever the watermark has to move) overlaps the consumers'
+            // work on the item that still occupies this stage
+            const unsigned long long t0 = timing ? pk_now() : 0ull;
+            if (back && gback >= wb) wb = pk_wait_groups(cnt_b, need_b, P.ngroups, wb, gback, lane);
+            if (fwd && ghi >= wf) wf = pk_wait_groups(cnt_f, need_f, P.ngroups, wf, ghi, lane);
+            const unsigned long long t1 = timing ? pk_now() : 0ull;
+            if (it >= STAGES) mbar_wait(&done[s], ((it / STAGES) - 1) & 1);  // the stage's x buffer is free
+            if (timing) { w_dep += t1 - t0; w_done += pk_now() - t1; }
+            if (fwd) fence_proxy_async_global();  // acquired generic-proxy writes -> visible to the bulk copies below
+            const int nseg = __shfl_sync(0xffffffffu, cw, 3);
+            const int xlen = __shfl_sync(0xffffffffu, cw, 6);
+            const int start = __shfl_sync(0xffffffffu, cw, 8 + (lane & 7));
+            const int lenoff = __shfl_sync(0xffffffffu, cw, 16 + (lane & 7));
+            if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)xlen * 8u);
+            __syncwarp();
+            if (lane < nseg) {
+                const int len = lenoff & 0xffff, xoff = (lenoff >> 16) & 0xffff;
+                bulk_g2s(smem + (size_t)s * STAGE_BYTES + BLOB_CAP + (size_t)xoff * 8, src + start, (uint32_t)len * 8u, &full[s]);
+            }
+            if (timing && lane == 0) ts[s * 4 + 1] = pk_now();
+            cw = nw;
+        }
+        if (timing && lane == 0) {
+            P.timing[(size_t)blockIdx.x * 16 + 6] = w_done;  // dependency warp: waiting for its stage to be free
+            P.timing[(size_t)blockIdx.x * 16 + 7] = w_dep;   // ... and for the completion counters
+        }
+        return;
+    }
+
+    // ===== consumer warps: one row per thread and pass, inputs from shared memory only =====
+    constexpr int NCT = NCW * 32;
+    double *dst = P.levels[level];
+    const int row_end = P.level_rows[level];
+    double dot_acc = 0.0;
+    for (int it = 0; it < n_my; ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&full[s], (it / STAGES) & 1);
+        if (timing && tid == 0) ts[s * 4 + 2] = pk_now();
+        const unsigned char *blob = smem + (size_t)s * STAGE_BYTES;
+        const int *hdr = reinterpret_cast<const int *>(blob);
+        const int row0 = hdr[PKH_ROW0], nrows = hdr[PKH_NROWS], width = hdr[PKH_WIDTH], rp = hdr[PKH_RP];
+        const unsigned short *lens = reinterpret_cast<const unsigned short *>(blob + hdr[PKH_OFF_LENS]);
+        const unsigned short *lcol = reinterpret_cast<const unsigned short *>(blob + hdr[PKH_OFF_LCOL]);
+        const double *val = reinterpret_cast<const double *>(blob + hdr[PKH_OFF_VAL]);
+        const double *xb = reinterpret_cast<const double *>(blob + BLOB_CAP);
+        for (int rb = 0; rb < nrows; rb += NCT * RPT) {
+            int len[RPT];
+            double acc[RPT];
+#pragma unroll
+            for (int q = 0; q < RPT; q++) {
+                const int r = rb + q * NCT + tid;
+                len[q] = (r < nrows && row0 + r < row_end) ? (int)lens[r] : -1;  // -1: no row
+                acc[q] = 0.0;
+            }
+            for (int e0 = 0; e0 < width; e0 += 8) {
+                double xv[RPT][8];
+#pragma unroll
+                for (int q = 0; q < RPT; q++) {
+                    const int r = rb + q * NCT + tid;
+#pragma unroll
+                    for (int u = 0; u < 8; u++)
+                        if (e0 + u < len[q]) xv[q][u] = xb[lcol[(e0 + u) * rp + r]];
+                }
+#pragma unroll
+                for (int q = 0; q < RPT; q++) {
+                    const int r = rb + q * NCT + tid;
+#pragma unroll
+                    for (int u = 0; u < 8; u++)
+                        if (e0 + u < len[q]) acc[q] = row_op<MULADD>(val[(e0 + u) * rp + r], xv[q][u], acc[q]);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < RPT; q++) {
+                const int r = rb + q * NCT + tid;
+                if (len[q] >= 0) {
+                    dst[row0 + r] = acc[q];
+                    if (P.dot_w) dot_acc = __fma_rn(P.dot_w[row0 + r], acc[q], dot_acc);
+                }
+            }
+        }
+        __syncwarp();
+        if (timing && tid == 0) ts[s * 4 + 3] = pk_now();
+        if (lane == 0) {
+            mbar_arrive(&done[s]);                                 // release.cta: the stage may be refilled
+            if (P.k > 1) red_release_cta_shared_add(&fin[s], 1u);  // ... and published (the gpu-scope fence is the publisher's)
+        }
+    }
+
+    if (P.dot_w) {
+        // deterministic: lanes -> warp (xor tree), warps in order, CTAs in order (last CTA finishes)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dot_acc += __shfl_xor_sync(0xffffffffu, dot_acc, o);
+        if (lane == 0) red[warp] = dot_acc;
+        named_bar_sync(2, NCT);
+        if (warp == 0) {
+            __shared__ bool is_last;
+            if (lane == 0) {
+                double sum = 0.0;
+                for (int w = 0; w < NCW; w++) sum += red[w];
+                P.partials[blockIdx.x] = sum;
+                __threadfence();
+                const unsigned int ticket = atomicAdd(P.ticket, 1u);
+                is_last = (ticket == gridDim.x - 1);
+            }
+            __syncwarp();
+            if (is_last) {
+                __threadfence();
+                double sum = 0.0;
+                for (int b = lane; b < (int)gridDim.x; b += 32) sum += ld_cg_f64(P.partials + b);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                if (lane == 0) {
+                    *P.dot_out = sum;
+                    *P.ticket = 0u;
+                }
+            }
+        }
+    }
+}
+
+// -----------------------------------------------------------------------------------------------
+// geometry table
+// -----------------------------------------------------------------------------------------------
+struct PkVariant {
+    int t_rows, blob_cap, xcap, stages, ncw, minb, rpt;
+};
+//            id T_ROWS BLOB_CAP XCAP STAGES NCW MINB RPT
+#define NSK_PK_VARIANTS(X)              \
+    X(0, 256, 21504, 1536, 3, 8, 2, 1)  \
+    X(1, 256, 21504, 1536, 2, 8, 3, 1)  \
+    X(2, 512, 42496, 2560, 3, 8, 1, 2)  \
+    X(3, 512, 42496, 2560, 3, 16, 1, 1) \
+    X(4, 256, 21504, 1536, 6, 8, 1, 1)  \
+    X(5, 128, 11264, 1024, 3, 4, 4, 1)  \
+    X(6, 256, 21504, 1536, 2, 4, 3, 2)  \
+    X(7, 256, 21504, 1536, 2, 4, 3, 1)  \
+    X(8, 256, 21504, 1536, 3, 4, 2, 2)  \
+    X(9, 256, 21504, 1536, 6, 4, 1, 2)
+
+static const PkVariant g_pkv[] = {
+#define X(id, r, b, x, s, w, m, u) {r, b, x, s, w, m, u},
+    NSK_PK_VARIANTS(X)
+#undef X
+};
+static const int g_npkv = sizeof(g_pkv) / sizeof(g_pkv[0]);
+
+typedef void (*pk_fn)(const PkParams);
+static pk_fn pk_lookup(int variant, bool muladd, int *smem)
+{
+    switch (variant) {
+#define X(id, r, b, x, s, w, m, u)                                          \
+    case id:                                                                \
+        *smem = (b + x * 8) * s + 2 * s * 8 + 64 * 8 + s * 32 + s * 4 + 128; \
+        return muladd ? packed_kernel<r, b, x, s, w, m, u, true> : packed_kernel<r, b, x, s, w, m, u, false>;
+        NSK_PK_VARIANTS(X)
+#undef X
+    }
+    return nullptr;
+}
+
+static int pk_variant(nsk_ctx_t ctx)
+{
+    // option value 0 = default; n >= 1 selects table entry n - 1.  Default: 256-row tiles, 2 stages, 4 consumer warps
+    // with two rows per thread, 3 CTAs per SM (profiles/r01_sweep_packed_c3.txt)
+    int v = (int)ctx->opt.packed_variant - 1;
+    if (v < 0 || v >= g_npkv) v = 6;
+    return v;
+}
+
+// -----------------------------------------------------------------------------------------------
+// host side: packing (cached per operator and tile geometry), level plans, launches
+// -----------------------------------------------------------------------------------------------
+struct PkLevelPlan {
+    int k = 0, team = 0, lead_pct = 0, bp_global = 0, w0_pct = 0, interleave = 0;
+    bool rejected = false;
+    std::vector<int> teams;     // CTAs per level, sum <= team * k
+    int grid = 0;
+    int2 *d_roles = nullptr;
+    std::vector<int> level_rows;
+    int ngroups = 0, reach = 0, lead = 0;
+    std::vector<int> count;
+    std::vector<size_t> item_off;
+    PkItem *d_items = nullptr;
+    int *d_counters = nullptr;
+    int *d_group_size = nullptr;
+};
+
+struct PackedOp {
+    int t_rows = 0, blob_cap = 0, xcap = 0;
+    bool ok = false;
+    std::string why;
+    int ntiles = 0;
+    size_t blob_bytes = 0;
+    unsigned char *d_blobs = nullptr;
+    PkTile *d_tiles = nullptr;
+    std::vector<PkTile> h_tiles;
+    nsk_tiling csr_view;  // the same tiles as {row0, nrows, nz0, nz1}: input of nsk_wave_deps
+    std::vector<PkLevelPlan> plans;
+};
+
+static std::map<nsk_csr_t, std::vector<PackedOp *>> g_packed;
+
+void nsk_packed_free(nsk_csr_t A)
+{
+    auto it = g_packed.find(A);
+    if (it == g_packed.end()) return;
+    for (PackedOp *op : it->second) {
+        for (PkLevelPlan &p : op->plans) {
+            if (p.d_items) cudaFree(p.d_items);
+            if (p.d_counters) cudaFree(p.d_counters);
+            if (p.d_group_size) cudaFree(p.d_group_size);
+            if (p.d_roles) cudaFree(p.d_roles);
+        }
+        if (op->d_blobs) cudaFree(op->d_blobs);
+        if (op->d_tiles) cudaFree(op->d_tiles);
+        delete op;
+    }
+    g_packed.erase(it);
+}
+
+// Column runs of one tile.  cols: the tile's column indices (any order, duplicates allowed; scratch, sorted in
+// place).  A gap of up to GAP unused columns is bridged (a bulk copy per run costs more than 64 idle bytes).
+static bool pk_segments(std::vector<int> &cols, int n_cols, int xcap, PkTile &t)
+{
+    constexpr int GAP = 8;
+    t.nseg = 0;
+    t.xlen = 0;
+    for (int s = 0; s < PK_MAXSEG; s++) { t.seg_start[s] = 0; t.seg_lenoff[s] = 0; }
+    if (cols.empty()) return true;
+    std::sort(cols.begin(), cols.end());
+    int s0 = cols[0] & ~1, s1 = cols[0] + 1;  // current run [s0, s1)
+    auto flush = [&]() {
+        int e = (s1 + 1) & ~1;
+        if (e > n_cols) e = n_cols;  // n_cols is even (checked by the caller)
+        const int len = e - s0;
+        if (t.nseg >= PK_MAXSEG || t.xlen + len > xcap || len > 0xffff || t.xlen > 0xffff) return false;
+        t.seg_start[t.nseg] = s0;
+        t.seg_lenoff[t.nseg] = len | (t.xlen << 16);
+        t.nseg++;
+        t.xlen += len;
+        return true;
+    };
+    for (size_t i = 1; i < cols.size(); i++) {
+        const int cidx = cols[i];
+        if (cidx < s1) continue;
+        if (cidx <= ((s1 + 1) & ~1) + GAP) { s1 = cidx + 1; continue; }
+        if (!flush()) return false;
+        s0 = cidx & ~1;
+        s1 = cidx + 1;
+    }
+    return flush();
+}
+
+static PackedOp *pk_get(nsk_csr_t A, const PkVariant &V)
+{
+    std::vector<PackedOp *> &ops = g_packed[A];
+    for (PackedOp *op : ops)
+        if (op->t_rows == V.t_rows && op->blob_cap == V.blob_cap && op->xcap == V.xcap) return op;
+    nsk_ctx_t ctx = A->ctx;
+    PackedOp *op = new PackedOp();
+    op->t_rows = V.t_rows; op->blob_cap = V.blob_cap; op->xcap = V.xcap;
+    ops.push_back(op);
+    const int n = A->n;
+    const std::vector<int> &ptrow = nsk_csr_host_ptrow(A);
+    if (n == 0 || A->nnz == 0) { op->why = "empty operator"; return op; }
+    if (A->n_cols & 1) { op->why = "odd number of columns (bulk copies move 16-byte granules)"; return op; }
+    if ((int)ptrow.size() != n + 1) { op->why = "host row pointers missing"; return op; }
+
+    // 1. tiles: up to t_rows consecutive rows, never across a break, blob within the stage
+    std::vector<nsk_tile> tiles;
+    std::vector<int> widths;
+    {
+        size_t bi = 0;
+        int r = 0;
+        while (r < n) {
+            while (bi < A->breaks.size() && A->breaks[bi] <= r) bi++;
+            const int seg_end = bi < A->breaks.size() ? std::min(n, A->breaks[bi]) : n;
+            int rows = std::min(V.t_rows, seg_end - r);
+            int width = 0;
+            for (;;) {
+                width = 0;
+                for (int i = r; i < r + rows; i++) width = std::max(width, ptrow[i + 1] - ptrow[i]);
+                if (pk_blob_bytes(rows, width) <= V.blob_cap) break;
+                if (rows == 1) { op->why = "a row is longer than a stage"; return op; }
+                rows = rows / 2;
+            }
+            tiles.push_back(nsk_tile{r, rows, ptrow[r], ptrow[r + rows]});
+            widths.push_back(width);
+            r += rows;
+        }
+    }
+    const int ntiles = (int)tiles.size();
+    std::vector<size_t> off(ntiles + 1, 0);
+    for (int t = 0; t < ntiles; t++) off[t + 1] = off[t] + (size_t)pk_blob_bytes(tiles[t].nrows, widths[t]);
+    const double csr_equiv = 10.0 * (double)A->nnz + 2.0 * n;
+    if ((double)off[ntiles] > 1.35 * csr_equiv + 65536.0) { op->why = "row lengths too ragged for slot-major tiles"; return op; }
+
+    // 2. the operator's entries (the caller's host arrays are gone: read them back once)
+    std::vector<int> indcol((size_t)A->nnz);
+    std::vector<double> coef((size_t)A->nnz);
+    if (cudaMemcpy(indcol.data(), A->d_indcol, sizeof(int) * (size_t)A->nnz, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(coef.data(), A->d_coef, sizeof(double) * (size_t)A->nnz, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        op->why = "reading the operator back failed";
+        return op;
+    }
+
+    // 3. per tile: column runs, local indices, slot-major blob (parallel over tiles)
+    std::vector<unsigned char> blobs(off[ntiles] + 64, 0);
+    std::vector<PkTile> ptiles(ntiles);
+    std::atomic<int> next(0), failed(0);
+    const int n_cols = A->n_cols;
+    auto work = [&]() {
+        std::vector<int> cols;
+        for (;;) {
+            const int t0 = next.fetch_add(64);
+            if (t0 >= ntiles || failed.load()) return;
+            for (int t = t0; t < std::min(ntiles, t0 + 64); t++) {
+                const nsk_tile &tl = tiles[t];
+                PkTile &pt = ptiles[t];
+                cols.assign(indcol.begin() + tl.nz0, indcol.begin() + tl.nz1);
+                if (!pk_segments(cols, n_cols, V.xcap, pt)) { failed.store(1); return; }
+                const int width = widths[t], rp = pk_round_up(tl.nrows, 32);
+                pt.blob_off = (long long)off[t];
+                pt.blob_bytes = pk_blob_bytes(tl.nrows, width);
+                pt.row0 = tl.row0; pt.nrows = tl.nrows; pt.pad = 0;
+                unsigned char *b = blobs.data() + off[t];
+                int *hdr = reinterpret_cast<int *>(b);
+                const int off_lens = PKH_WORDS * 4, off_lcol = off_lens + 2 * rp, off_val = off_lcol + 2 * width * rp;
+                hdr[PKH_ROW0] = tl.row0; hdr[PKH_NROWS] = tl.nrows; hdr[PKH_WIDTH] = width; hdr[PKH_RP] = rp;
+                hdr[PKH_OFF_LENS] = off_lens; hdr[PKH_OFF_LCOL] = off_lcol; hdr[PKH_OFF_VAL] = off_val;
+                unsigned short *lens = reinterpret_cast<unsigned short *>(b + off_lens);
+                unsigned short *lcol = reinterpret_cast<unsigned short *>(b + off_lcol);
+                double *val = reinterpret_cast<double *>(b + off_val);
+                int sstart[PK_MAXSEG], send[PK_MAXSEG], soff[PK_MAXSEG];
+                for (int s = 0; s < pt.nseg; s++) {
+                    sstart[s] = pt.seg_start[s];
+                    send[s] = sstart[s] + (pt.seg_lenoff[s] & 0xffff);
+                    soff[s] = (pt.seg_lenoff[s] >> 16) & 0xffff;
+                }
+                for (int r = 0; r < tl.nrows; r++) {
+                    const int p = ptrow[tl.row0 + r], q = ptrow[tl.row0 + r + 1];
+                    lens[r] = (unsigned short)(q - p);
+                    int s = 0;
+                    for (int j = p; j < q; j++) {
+                        const int cidx = indcol[j];
+                        if (cidx < sstart[s] || cidx >= send[s]) {  // columns ascend within a row in practice: resume, else rescan
+                            s = 0;
+                            while (s < pt.nseg && !(cidx >= sstart[s] && cidx < send[s])) s++;
+                        }
+                        lcol[(size_t)(j - p) * rp + r] = (unsigned short)(soff[s] + (cidx - sstart[s]));
+                        val[(size_t)(j - p) * rp + r] = coef[j];
+                    }
+                }
+            }
+        }
+    };
+    {
+        const int nth = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        std::vector<std::thread> th;
+        for (int i = 1; i < nth; i++) th.emplace_back(work);
+        work();
+        for (auto &x : th) x.join();
+    }
+    if (failed.load()) { op->why = "a tile references x in too many / too long runs"; return op; }
+
+    // 4. upload
+    if (cudaMalloc(&op->d_blobs, blobs.size()) != cudaSuccess ||
+        cudaMalloc(&op->d_tiles, sizeof(PkTile) * (size_t)ntiles + 128) != cudaSuccess) {
+        op->why = "allocation of the packed operator failed";
+        cudaGetLastError();
+        return op;
+    }
+    cudaMemcpy(op->d_blobs, blobs.data(), blobs.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(op->d_tiles, ptiles.data(), sizeof(PkTile) * (size_t)ntiles, cudaMemcpyHostToDevice);
+    op->ntiles = ntiles;
+    op->blob_bytes = off[ntiles];
+    op->h_tiles.swap(ptiles);
+    op->csr_view.tile_rows = V.t_rows;
+    op->csr_view.ntiles = ntiles;
+    op->csr_view.nlong = 0;
+    op->csr_view.h_tiles.swap(tiles);
+    op->ok = true;
+    (void)ctx;
+    return op;
+}
+
+static int pk_launch_shape(nsk_ctx_t ctx, int variant, bool muladd, int k, pk_fn *fn_out, int *smem_out, int *team)
+{
+    const PkVariant &V = g_pkv[variant];
+    int smem = 0;
+    pk_fn fn = pk_lookup(variant, muladd, &smem);
+    NSK_REQUIRE(ctx, smem <= (int)ctx->prop.sharedMemPerBlockOptin, "packed kernel stage ring exceeds shared memory");
+    NSK_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int per_sm = 0;
+    NSK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, (V.ncw + 3) * 32, smem));
+    if (ctx->opt.spmv_ctas_per_sm > 0) per_sm = std::min(per_sm, (int)ctx->opt.spmv_ctas_per_sm);
+    const int resident = ctx->prop.multiProcessorCount * per_sm;
+    *team = resident;  // all resident CTAs; the plan shares them out over the levels
+    *fn_out = fn;
+    *smem_out = smem;
+    return NSK_OK;
+}
+
+static PkLevelPlan *pk_level_plan(nsk_csr_t A, PackedOp *op, int k, const int *level_rows, int resident, const char **why)
+{
+    nsk_ctx_t ctx = A->ctx;
+    const int team = resident / k;  // even share: the unit of the slack below
+    std::vector<int> lr(k);
+    for (int l = 0; l < k; l++) lr[l] = level_rows ? level_rows[l] : A->n;
+    const int lead_pct = (int)ctx->opt.wave_slack_pct;  // < 0: size the window from the L2 budget
+    const int bp_global = ctx->opt.pipe_bp_global >= 0 ? (ctx->opt.pipe_bp_global ? 1 : 0) : 1;
+    const int w0_pct = k > 1 ? (ctx->opt.pipe_w0_pct > 0 ? (int)ctx->opt.pipe_w0_pct : 100) : 100;
+    const int interleave = ctx->opt.pipe_interleave ? 1 : 0;
+    for (PkLevelPlan &p : op->plans)
+        if (p.k == k && p.team == resident && p.level_rows == lr && p.lead_pct == lead_pct && p.bp_global == bp_global &&
+            p.w0_pct == w0_pct && p.interleave == interleave) {
+            if (p.rejected) { *why = "wavefront window exceeds the L2 budget"; return nullptr; }
+            return &p;
+        }
+    const int ntiles = op->ntiles;
+    PkLevelPlan p;
+    p.k = k; p.team = resident; p.lead_pct = lead_pct; p.level_rows = lr; p.bp_global = bp_global;
+    p.w0_pct = w0_pct; p.interleave = interleave;
+    // teams: `team * k` resident CTAs shared out with weight w0 for level 0 (it streams from HBM: longer fills, so
+    // it needs more stages in flight for the same rate) and 100 for every other level
+    {
+        const double wsum = (double)w0_pct + 100.0 * (k - 1);
+        p.teams.assign(k, 0);
+        int used = 0;
+        for (int l = 1; l < k; l++) {
+            p.teams[l] = std::max(1, (int)(resident * 100.0 / wsum));
+            used += p.teams[l];
+        }
+        p.teams[0] = std::max(1, resident - used);
+    }
+    std::vector<int> pos_tile(ntiles), ghi(ntiles, 0);
+    int ngroups = (ntiles + WF_GROUP - 1) / WF_GROUP;
+    if (k > 1) {
+        WaveDeps D;
+        if (!nsk_wave_deps(A, op->csr_view, D, why)) return nullptr;
+        pos_tile = D.tile_at_pos;
+        ghi = D.ghi;
+        ngroups = D.ngroups;
+        p.reach = D.reach;
+        // lead = how far a level may run ahead of the level that holds it back, per hop: at least the pattern's
+        // reach + one completion group, plus slack that absorbs the publish -> poll -> copy latency (several us,
+        // i.e. hundreds of tiles at full rate).  The window that must stay in L2 is (k-1)*lead tiles of matrix
+        // data plus the level vectors over it; by default the slack is whatever the L2 budget allows -- measured
+        // on 256^3: time falls with the window until it reaches ~100 MB, then HBM re-reads set in.
+        const double tile_bytes = (double)op->blob_bytes / ntiles + 8.0 * op->t_rows * (k + 1);
+        const double budget = (ctx->opt.wave_l2_pct > 0 ? (double)ctx->opt.wave_l2_pct : 80.0) / 100.0 *
+                              (double)ctx->prop.l2CacheSize;
+        const int lead_min = D.reach + 1 + WF_GROUP;
+        if (lead_pct >= 0)
+            p.lead = lead_min + (int)((double)lead_pct / 100.0 * 2.0 * team + 0.999);  // unit: two rounds of an even team
+        else
+            p.lead = std::max(lead_min + 2 * WF_GROUP, (int)(budget / ((double)(k - 1) * tile_bytes)));
+        const double window = (double)(k - 1) * p.lead * tile_bytes;
+        if (window > budget * 1.0001) {
+            *why = "wavefront window exceeds the L2 budget";
+            p.rejected = true;
+            op->plans.push_back(p);
+            return nullptr;
+        }
+    } else {
+        for (int t = 0; t < ntiles; t++) pos_tile[t] = t;
+    }
+    p.ngroups = ngroups;
+    std::vector<PkItem> items;
+    items.reserve((size_t)k * ntiles);
+    std::vector<int> gsize((size_t)k * ngroups, 0);
+    p.count.assign(k, 0);
+    p.item_off.assign(k, 0);
+    for (int l = 0; l < k; l++) {
+        p.item_off[l] = items.size();
+        for (int pos = 0; pos < ntiles; pos++) {
+            const int t = pos_tile[pos];
+            const PkTile &pt = op->h_tiles[t];
+            if (pt.row0 >= lr[l]) continue;  // outside this level's row prefix (distributed shrink)
+            int gback = -1;
+            // adjacent mode: level l trails l+1 by at most `lead`; global mode: level 0 trails k-1 by (k-1)*lead
+            const int hold = bp_global ? (l == 0 ? (k - 1) * p.lead : -1) : (l < k - 1 ? p.lead : -1);
+            if (hold >= 0 && pos - hold >= 0) gback = (pos - hold) / WF_GROUP - 1;
+            items.push_back(PkItem{t, pos, ghi[t], gback, pt.blob_off, pt.blob_bytes, 0});
+            gsize[(size_t)l * ngroups + pos / WF_GROUP]++;
+            p.count[l]++;
+        }
+    }
+    // role table: levels interleaved in proportion to their team sizes (consecutive block indices land on different
+    // SMs, so every SM hosts a mix of levels), or level by level
+    for (int l = 0; l < k; l++) p.teams[l] = std::max(1, std::min(p.teams[l], std::max(1, p.count[l])));
+    std::vector<int2> roles;
+    {
+        int total = 0;
+        for (int l = 0; l < k; l++) total += p.teams[l];
+        std::vector<int> given(k, 0);
+        if (interleave) {
+            for (int b = 0; b < total; b++) {
+                int best = -1;
+                double bestv = 0.0;
+                for (int l = 0; l < k; l++) {  // the level furthest behind its share
+                    if (given[l] >= p.teams[l]) continue;
+                    const double v = (double)(b + 1) * p.teams[l] / total - given[l];
+                    if (best < 0 || v > bestv) { best = l; bestv = v; }
+                }
+                roles.push_back(make_int2(best, given[best]++));
+            }
+        } else {
+            for (int l = 0; l < k; l++)
+                for (int i = 0; i < p.teams[l]; i++) roles.push_back(make_int2(l, i));
+        }
+        p.grid = total;
+    }
+    if (cudaMalloc(&p.d_roles, sizeof(int2) * roles.size()) != cudaSuccess ||
+        cudaMalloc(&p.d_items, sizeof(PkItem) * (items.size() + 1)) != cudaSuccess ||
+        cudaMalloc(&p.d_counters, sizeof(int) * ((size_t)k * ngroups + 4)) != cudaSuccess ||
+        cudaMalloc(&p.d_group_size, sizeof(int) * (size_t)k * ngroups) != cudaSuccess) {
+        *why = "plan allocation failed";
+        cudaGetLastError();
+        return nullptr;
+    }
+    cudaMemcpy(p.d_items, items.data(), sizeof(PkItem) * items.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(p.d_group_size, gsize.data(), sizeof(int) * gsize.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(p.d_roles, roles.data(), sizeof(int2) * roles.size(), cudaMemcpyHostToDevice);
+    op->plans.push_back(p);
+    return &op->plans.back();
+}
+
+static bool pk_aligned(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Returns NSK_ERR_UNSUPPORTED (and sets the context's error text) when the packed path does not apply; the
+// callers then run the CSR kernels.
+int nsk_packed_run(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode, const int *level_rows,
+                   const double *dot_w, int dot_slot)
+{
+    nsk_ctx_t ctx = A->ctx;
+    const int variant = pk_variant(ctx);
+    const PkVariant &V = g_pkv[variant];
+    if (!pk_aligned(d_x)) { nsk_set_error(ctx, "packed path: x is not 16-byte aligned"); return NSK_ERR_UNSUPPORTED; }
+    for (int l = 0; l < k; l++)
+        if (!pk_aligned(d_levels[l])) { nsk_set_error(ctx, "packed path: output is not 16-byte aligned"); return NSK_ERR_UNSUPPORTED; }
+    PackedOp *op = pk_get(A, V);
+    if (!op->ok) { nsk_set_error(ctx, "packed path not applicable: %s", op->why.c_str()); return NSK_ERR_UNSUPPORTED; }
+    pk_fn fn; int smem = 0, team = 0;
+    NSK_TRY(pk_launch_shape(ctx, variant, mode == NSK_EXACT_MULADD, k, &fn, &smem, &team));
+    if (team < k) { nsk_set_error(ctx, "packed path: fewer resident CTAs than levels"); return NSK_ERR_UNSUPPORTED; }
+    const char *why = "";
+    PkLevelPlan *plan = pk_level_plan(A, op, k, level_rows, team, &why);
+    if (!plan) { nsk_set_error(ctx, "packed matrix powers not applicable: %s", why); return NSK_ERR_UNSUPPORTED; }
+    int maxcount = 0;
+    for (int l = 0; l < k; l++) maxcount = std::max(maxcount, plan->count[l]);
+    if (maxcount == 0) return NSK_OK;
+    if (dot_w) NSK_REQUIRE(ctx, k == 1 && plan->grid <= NSK_MAX_PARTIALS, "fused dot: k = 1 and a bounded grid");
+
+    if (k > 1)
+        NSK_CUDA(ctx, cudaMemsetAsync(plan->d_counters, 0, sizeof(int) * ((size_t)k * plan->ngroups + 4), ctx->stream));
+    PkParams P;
+    for (int l = 0; l < NSK_MAX_K; l++) {
+        P.items[l] = l < k ? plan->d_items + plan->item_off[l] : nullptr;
+        P.count[l] = l < k ? plan->count[l] : 0;
+        P.levels[l] = l < k ? d_levels[l] : nullptr;
+        P.level_rows[l] = l < k ? plan->level_rows[l] : 0;
+    }
+    P.tiles = op->d_tiles;
+    P.blobs = op->d_blobs;
+    P.counters = plan->d_counters;
+    P.group_size = plan->d_group_size;
+    P.ngroups = plan->ngroups;
+    P.x = d_x;
+    P.k = k;
+    for (int l = 0; l < NSK_MAX_K; l++) P.team[l] = l < k ? plan->teams[l] : 0;
+    P.cta_role = plan->d_roles;
+    P.bp_global = plan->bp_global;
+    P.timing = nullptr;
+    if (ctx->opt.pk_timing) {
+        void *tb = nullptr;
+        NSK_TRY(nsk_stage(ctx, 7, sizeof(unsigned long long) * 16 * (size_t)plan->grid, &tb));
+        NSK_CUDA(ctx, cudaMemsetAsync(tb, 0, sizeof(unsigned long long) * 16 * (size_t)plan->grid, ctx->stream));
+        P.timing = reinterpret_cast<unsigned long long *>(tb);
+    }
+    P.dot_w = dot_w;
+    P.partials = ctx->d_partials;
+    P.ticket = ctx->d_ticket;
+    P.dot_out = dot_w ? ctx->d_scalars + dot_slot : nullptr;
+    fn<<<plan->grid, (V.ncw + 3) * 32, smem, ctx->stream>>>(P);
+    ctx->launches++;
+    NSK_CUDA(ctx, cudaGetLastError());
+    if (P.timing) {  // debugging aid: per-level averages of the stage cycle on stderr
+        std::vector<unsigned long long> h((size_t)plan->grid * 16);
+        NSK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        NSK_CUDA(ctx, cudaMemcpy(h.data(), P.timing, h.size() * 8, cudaMemcpyDeviceToHost));
+        for (int l = 0; l < k; l++) {
+            double sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            double items = 0;
+            for (int b = 0; b < plan->grid; b++) {
+                if ((int)h[(size_t)b * 16 + 9] != l || h[(size_t)b * 16 + 8] == 0) continue;
+                for (int j = 0; j < 8; j++) sum[j] += (double)(long long)h[(size_t)b * 16 + j];
+                items += (double)h[(size_t)b * 16 + 8];
+            }
+            if (items > 0)
+                fprintf(stderr, "pk_timing k=%d level %d team %d: per item ns: blob->x issue %.0f | x issue->full %.0f | consume %.0f | "
+                        "w0 done->all done seen %.0f | cycle %.0f | fence+red(per item) %.0f | D wait stage %.0f | D wait deps %.0f\n",
+                        k, l, plan->teams[l], sum[0] / items, sum[1] / items, sum[2] / items, sum[3] / items, sum[4] / items,
+                        sum[5] / items, sum[6] / items, sum[7] / items);
+        }
+    }
+    return NSK_OK;
+}
+
+bool nsk_packed_applicable(nsk_csr_t A)
+{
+    if (A->n == 0 || A->nnz == 0) return false;
+    return pk_get(A, g_pkv[pk_variant(A->ctx)])->ok;
+}
+
+// bytes of the packed operator (for traffic accounting in the bench); 0 when not packed
+size_t nsk_packed_bytes(nsk_csr_t A)
+{
+    PackedOp *op = pk_get(A, g_pkv[pk_variant(A->ctx)]);
+    return op->ok ? op->blob_bytes : 0;
+}

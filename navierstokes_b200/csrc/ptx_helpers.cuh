@@ -125,3 +125,26 @@ __device__ __forceinline__ double ld_cg_f64(const double *p)
 }
 
 }  // namespace nskptx
+
+namespace nskptx {
+// Orders this thread's prior generic-proxy view of GLOBAL memory (here: data another CTA published and
+// this thread acquired) before its subsequent async-proxy (bulk copy / TMA) reads of that memory.
+__device__ __forceinline__ void fence_proxy_async_global()
+{
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+}  // namespace nskptx
+
+namespace nskptx {
+// CTA-scope release / acquire on a shared-memory word (monotone counters between warps of one CTA)
+__device__ __forceinline__ void red_release_cta_shared_add(unsigned int *p, unsigned int v)
+{
+    asm volatile("red.release.cta.shared::cta.add.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_cta_shared_u32(const unsigned int *p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+}  // namespace nskptx

@@ -448,7 +448,13 @@ int nsk_launch_spmv(nsk_csr_t A, const nsk_spmv_args &a)
     const bool fast = a.mode == NSK_FAST;
     const bool long_rows = A->mean_row > 12.0;
     int sel = (int)ctx->opt.spmv_kernel;
-    if (sel == 0) sel = 2;
+    if ((sel == 0 || sel == 3) && rb == 0 && nsk_packed_applicable(A)) {
+        double *out = a.y;
+        int s = nsk_packed_run(A, 1, a.x, &out, a.mode, &re, a.dot_w, a.dot_slot);
+        if (s != NSK_ERR_UNSUPPORTED) { ctx->last_spmv = 3; return s; }
+    }
+    if (sel == 0 || sel == 3) sel = 2;
+    ctx->last_spmv = sel;
 
     if (sel == 1) {
         NSK_REQUIRE(ctx, a.dot_w == nullptr, "fused dot needs the streaming kernel");

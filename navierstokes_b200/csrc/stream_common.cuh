@@ -39,6 +39,47 @@ __device__ __forceinline__ double row_chain(const double *val_s, const int *col_
     return acc;
 }
 
+// Rows of one pass of a consumer thread: RPT rows, the gathers of their first 8 nonzeros all in flight
+// before the first dependent multiply-add (the chain of each row stays strictly sequential).
+template <bool MULADD, bool NC, int RPT, int NCT>
+__device__ __forceinline__ void consume_tile(const double *val_s, const int *col_s, const int *ptr_s, int vo, int co,
+                                             int po, int row0, int nrows, int row_end, const double *src, double *dst,
+                                             int ctid)
+{
+    for (int rb = 0; rb < nrows; rb += NCT * RPT) {
+        int p[RPT], q[RPT];
+        double xv[RPT][8];
+#pragma unroll
+        for (int u = 0; u < RPT; u++) {
+            const int r = rb + u * NCT + ctid;
+            const int row = row0 + r;
+            const bool valid = r < nrows && row < row_end;
+            p[u] = valid ? ptr_s[row - po] : 0;
+            q[u] = valid ? ptr_s[row + 1 - po] : -1;  // q < p marks "no row": nothing gathered, nothing stored
+        }
+#pragma unroll
+        for (int u = 0; u < RPT; u++)
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const int j = p[u] + e;
+                xv[u][e] = 0.0;
+                if (j < q[u]) {
+                    const int c = col_s[j - co];
+                    xv[u][e] = NC ? __ldg(src + c) : src[c];
+                }
+            }
+#pragma unroll
+        for (int u = 0; u < RPT; u++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int e = 0; e < 8; e++)
+                if (p[u] + e < q[u]) acc = row_op<MULADD>(val_s[p[u] + e - vo], xv[u][e], acc);
+            if (q[u] > p[u] + 8) acc = row_chain<MULADD, NC>(val_s, col_s, p[u] + 8, q[u], vo, co, src, acc);
+            if (q[u] >= p[u]) dst[row0 + rb + u * NCT + ctid] = acc;
+        }
+    }
+}
+
 // -----------------------------------------------------------------------------------------------
 // shared-memory stage of one tile: [coef slice | indcol slice | ptrow slice | header]
 // -----------------------------------------------------------------------------------------------

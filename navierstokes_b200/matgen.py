@@ -256,6 +256,32 @@ def random_csr(n: int, mean_row: float, seed: int = 0, empty_rows: bool = True, 
     return Csr(n=n, ptrow=ptrow.astype(np.int32), indcol=indcol, coef=coef, ncols=n)
 
 
+def random_banded_csr(n: int, half_bw: int, mean_row: float, seed: int = 0, empty_rows: bool = True,
+                      len_range: tuple[int, int] | None = None) -> Csr:
+    """Ragged random operator whose columns stay within `half_bw` of the diagonal (what RCM produces):
+    Poisson row lengths (some empty) or, with len_range=(lo, hi), uniformly drawn lengths with 2 % empty rows;
+    sorted unique columns.  The fused matrix-powers kernels apply."""
+    rng = np.random.default_rng(seed)
+    if len_range is not None:
+        lens = rng.integers(len_range[0], len_range[1] + 1, size=n)
+        if empty_rows:
+            lens[rng.random(n) < 0.02] = 0
+    else:
+        lens = rng.poisson(mean_row, size=n)
+    lens = np.minimum(lens, half_bw + 1)  # the clipped window at a boundary still holds a row
+    if not empty_rows:
+        lens = np.maximum(lens, 1)
+    ptrow = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lens, out=ptrow[1:])
+    indcol = np.empty(int(ptrow[-1]), dtype=np.int32)
+    for i in range(n):
+        if lens[i]:
+            lo, hi = max(0, i - half_bw), min(n, i + half_bw + 1)
+            indcol[ptrow[i]:ptrow[i + 1]] = np.sort(rng.choice(hi - lo, size=int(lens[i]), replace=False)) + lo
+    coef = rng.uniform(-1.0, 1.0, size=int(ptrow[-1]))
+    return Csr(n=n, ptrow=ptrow.astype(np.int32), indcol=indcol, coef=coef, ncols=n)
+
+
 # ---------------------------------------------------------------------------------------------
 # Input vectors (SURVEY.md section 8d)
 # ---------------------------------------------------------------------------------------------

@@ -16,15 +16,25 @@ def all_kernel_configs(ctx):
     yield 1, 0
     for v in range(1, 9):
         yield 2, v
+    for v in range(1, 11):
+        yield 3, v  # packed format (applies to operators whose tiles read x in a few runs; else the CSR kernels run)
+
+
+def select_kernel(ctx, kern, var):
+    ctx.set_option("spmv_kernel", kern)
+    ctx.set_option("packed_variant" if kern == 3 else "stream_variant", var)
 
 
 @pytest.fixture()
 def reset_options(ctx):
     yield
-    ctx.set_option("spmv_kernel", 0)
-    ctx.set_option("stream_variant", 0)
-    ctx.set_option("spmv_ctas_per_sm", 0)
-    ctx.set_option("mpk_kernel", 0)
+    for name in ("spmv_kernel", "stream_variant", "spmv_ctas_per_sm", "mpk_kernel", "wave_variant", "wave_l2_pct",
+                 "wave_static", "pipe_variant", "packed_variant"):
+        ctx.set_option(name, 0)
+    ctx.set_option("wave_slack_pct", -1)
+    ctx.set_option("pipe_interleave", 1)
+    ctx.set_option("pipe_bp_global", -1)
+    ctx.set_option("pipe_w0_pct", 0)
 
 
 @pytest.mark.parametrize("case", CSR_CASES)
@@ -32,8 +42,7 @@ def test_spmv_exact_fma_golden(ctx, case, reset_options):
     g = golden(case)
     A = nsk.CsrMatrix(ctx, g["ptrow"], g["indcol"], g["coef"])
     for kern, var in all_kernel_configs(ctx):
-        ctx.set_option("spmv_kernel", kern)
-        ctx.set_option("stream_variant", var)
+        select_kernel(ctx, kern, var)
         for v in VECS:
             y = A.spmv(g[f"x_{v}"], mode=nsk.EXACT_FMA)
             assert_bits_equal(y, g[f"spmv_fma_{v}"], f"{case}/{v} kernel={kern} variant={var}")
@@ -44,8 +53,7 @@ def test_spmv_exact_muladd_and_fast(ctx, oracle_lib, case, reset_options):
     g = golden(case)
     A = nsk.CsrMatrix(ctx, g["ptrow"], g["indcol"], g["coef"])
     for kern, var in [(1, 0), (2, 1), (2, 2)]:
-        ctx.set_option("spmv_kernel", kern)
-        ctx.set_option("stream_variant", var)
+        select_kernel(ctx, kern, var)
         for v in VECS:
             x = g[f"x_{v}"]
             ym = A.spmv(x, mode=nsk.EXACT_MULADD)
@@ -86,8 +94,7 @@ def test_spmv_ragged_edge_cases(ctx, oracle_lib, n, mean, reset_options):
     ref = oracle_lib.spmv(A.ptrow, A.indcol, A.coef, x)
     dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
     for kern, var in all_kernel_configs(ctx):
-        ctx.set_option("spmv_kernel", kern)
-        ctx.set_option("stream_variant", var)
+        select_kernel(ctx, kern, var)
         assert_bits_equal(dA.spmv(x, mode=nsk.EXACT_FMA), ref, f"n={n} kernel={kern} variant={var}")
         yf = dA.spmv(x, mode=nsk.FAST)
         if np.any(ref):
@@ -255,6 +262,160 @@ def test_mpk_wavefront_falls_back_when_not_applicable(ctx, oracle_lib, reset_opt
     assert_bits_equal(dA.mpk(3, x), oracle_lib.mpk(A.ptrow, A.indcol, A.coef, 3, x))
 
 
+# ---- level-pipelined (single-launch, CTAs specialised by level) matrix powers -------------------------
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10])
+@pytest.mark.parametrize("gen,args", [("laplace3d_7pt", (40,)), ("laplace2d_5pt", (300,)), ("laplace3d_7pt", (64, 64, 20))])
+def test_mpk_pipeline_bitwise(ctx, oracle_lib, gen, args, variant, reset_options):
+    A = getattr(matgen, gen)(*args)
+    x = matgen.vec_uniform(A.n, seed=9)
+    dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
+    ctx.set_option("mpk_kernel", 3)
+    ctx.set_option("pipe_variant", variant)
+    for k in (2, 4, 7):
+        before = ctx.launch_count
+        lv = dA.mpk(k, x, mode=nsk.EXACT_FMA)
+        assert ctx.launch_count - before == 1, "level pipeline did not apply"
+        assert_bits_equal(lv, oracle_lib.mpk(A.ptrow, A.indcol, A.coef, k, x), f"{gen}{args} k={k} variant={variant}")
+    lm = dA.mpk(3, x, mode=nsk.EXACT_MULADD)
+    ctx.set_option("mpk_kernel", 1)
+    assert_bits_equal(lm, dA.mpk(3, x, mode=nsk.EXACT_MULADD))
+
+
+@pytest.mark.parametrize("interleave", [0, 1])
+@pytest.mark.parametrize("lead_pct", [0, 25, 100, 400])
+def test_mpk_pipeline_lead_and_placement(ctx, oracle_lib, interleave, lead_pct, reset_options):
+    """Back-pressure from tight (lead = reach + 1 group) to loose, both level placements: same bits."""
+    A = matgen.laplace3d_7pt(48, 40, 36)
+    x = matgen.vec_uniform(A.n, seed=3)
+    dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
+    ctx.set_option("mpk_kernel", 3)
+    ctx.set_option("pipe_interleave", interleave)
+    ctx.set_option("wave_slack_pct", lead_pct)
+    ctx.set_option("wave_l2_pct", 1000)  # never refuse: this operator is tiny, the window bound is not the subject
+    for k in (2, 5, 16):
+        before = ctx.launch_count
+        lv = dA.mpk(k, x)
+        assert ctx.launch_count - before == 1
+        assert_bits_equal(lv, oracle_lib.mpk(A.ptrow, A.indcol, A.coef, k, x), f"k={k}")
+
+
+def test_mpk_pipeline_repeated_calls_are_stable(ctx, reset_options):
+    """Counters are reset per call: 20 back-to-back calls give the same bits."""
+    A = matgen.laplace3d_7pt(56)
+    dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
+    dx = ctx.to_device(matgen.vec_uniform(A.n, 4))
+    lv = [ctx.empty(A.n) for _ in range(4)]
+    ctx.set_option("mpk_kernel", 3)
+    dA.mpk(4, dx, lv)
+    first = [l.to_host() for l in lv]
+    for _ in range(20):
+        dA.mpk(4, dx, lv)
+    for l in range(4):
+        assert_bits_equal(lv[l].to_host(), first[l])
+
+
+def test_mpk_pipeline_ragged_and_fallback(ctx, oracle_lib, reset_options):
+    """Banded operator with ragged / empty rows runs fused; an operator whose reach covers the whole matrix
+    degrades to k launches -- same bits either way."""
+    ctx.set_option("mpk_kernel", 3)
+    A = matgen.random_banded_csr(30000, 200, 6.0, seed=2, empty_rows=True)
+    x = matgen.vec_uniform(A.n, seed=8)
+    dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
+    assert_bits_equal(dA.mpk(5, x), oracle_lib.mpk(A.ptrow, A.indcol, A.coef, 5, x))
+    B = matgen.random_csr(4000, 5.0, seed=1, empty_rows=True)
+    xb = matgen.vec_uniform(B.n)
+    dB = nsk.CsrMatrix(ctx, B.ptrow, B.indcol, B.coef)
+    assert_bits_equal(dB.mpk(3, xb), oracle_lib.mpk(B.ptrow, B.indcol, B.coef, 3, xb))
+
+
+# ---- packed format: SpMV and matrix powers with x runs staged in shared memory ------------------------
+PACKED_OPS = [("laplace3d_7pt", (40,)), ("laplace2d_5pt", (300,)), ("laplace3d_7pt", (64, 64, 20)),
+              ("laplace2d_5pt", (1000, 37)), ("laplace3d_7pt", (34, 10, 50))]
+
+
+@pytest.mark.parametrize("variant", list(range(1, 11)))
+@pytest.mark.parametrize("gen,args", PACKED_OPS)
+def test_packed_spmv_and_mpk_bitwise(ctx, oracle_lib, gen, args, variant, reset_options):
+    A = getattr(matgen, gen)(*args)
+    x = matgen.vec_uniform(A.n, seed=11)
+    dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
+    ctx.set_option("packed_variant", variant)
+    ctx.set_option("spmv_kernel", 3)
+    assert dA.packed_bytes > 0, "the packed format must apply to a stencil operator"
+    assert_bits_equal(dA.spmv(x), oracle_lib.spmv(A.ptrow, A.indcol, A.coef, x), f"{gen}{args} spmv")
+    assert_bits_equal(dA.spmv(x, mode=nsk.EXACT_MULADD), oracle_lib.spmv_muladd(A.ptrow, A.indcol, A.coef, x))
+    ctx.set_option("mpk_kernel", 4)
+    for k in (2, 4, 7):
+        before = ctx.launch_count
+        lv = dA.mpk(k, x, mode=nsk.EXACT_FMA)
+        assert ctx.launch_count - before == 1, "packed level pipeline did not apply"
+        assert_bits_equal(lv, oracle_lib.mpk(A.ptrow, A.indcol, A.coef, k, x), f"{gen}{args} k={k} variant={variant}")
+
+
+@pytest.mark.parametrize("interleave,bp,w0", [(1, 1, 0), (0, 1, 0), (1, 0, 0), (0, 0, 250), (1, 1, 40)])
+@pytest.mark.parametrize("lead_pct", [-1, 0, 25, 100, 400])
+def test_packed_mpk_lead_and_placement(ctx, oracle_lib, interleave, bp, w0, lead_pct, reset_options):
+    """Window from tight (lead = reach + one group) to loose, both back-pressure modes, both level placements,
+    uneven teams: same bits."""
+    A = matgen.laplace3d_7pt(48, 40, 36)
+    x = matgen.vec_uniform(A.n, seed=3)
+    dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
+    ctx.set_option("mpk_kernel", 4)
+    ctx.set_option("pipe_interleave", interleave)
+    ctx.set_option("pipe_bp_global", bp)
+    ctx.set_option("pipe_w0_pct", w0)
+    ctx.set_option("wave_slack_pct", lead_pct)
+    ctx.set_option("wave_l2_pct", 1000)  # never refuse: this operator is tiny, the window bound is not the subject
+    for k in (2, 5, 16):
+        before = ctx.launch_count
+        lv = dA.mpk(k, x)
+        assert ctx.launch_count - before == 1
+        assert_bits_equal(lv, oracle_lib.mpk(A.ptrow, A.indcol, A.coef, k, x), f"k={k}")
+
+
+def test_packed_repeated_calls_are_stable(ctx, reset_options):
+    A = matgen.laplace3d_7pt(56)
+    dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
+    dx = ctx.to_device(matgen.vec_uniform(A.n, 4))
+    lv = [ctx.empty(A.n) for _ in range(4)]
+    ctx.set_option("mpk_kernel", 4)
+    dA.mpk(4, dx, lv)
+    first = [l.to_host() for l in lv]
+    for _ in range(20):
+        dA.mpk(4, dx, lv)
+    for l in range(4):
+        assert_bits_equal(lv[l].to_host(), first[l])
+
+
+def test_packed_banded_ragged_and_refusals(ctx, oracle_lib, reset_options):
+    """A banded operator with mildly ragged / empty rows whose tiles need few runs packs; a Poisson-ragged banded
+    operator, a random operator and one with an odd column count do not -- the CSR kernels run instead, same bits."""
+    ctx.set_option("spmv_kernel", 3)
+    ctx.set_option("mpk_kernel", 4)
+    R = matgen.random_banded_csr(20000, 150, 5.0, seed=4, empty_rows=True)
+    xr = matgen.vec_uniform(R.n, seed=8)
+    dR = nsk.CsrMatrix(ctx, R.ptrow, R.indcol, R.coef)
+    assert dR.packed_bytes == 0  # slot-major tiles would pad Poisson row lengths by more than a third
+    assert_bits_equal(dR.mpk(5, xr), oracle_lib.mpk(R.ptrow, R.indcol, R.coef, 5, xr))
+    A = matgen.random_banded_csr(20000, 150, 5.0, seed=4, empty_rows=True, len_range=(4, 6))
+    x = matgen.vec_uniform(A.n, seed=8)
+    dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
+    assert dA.packed_bytes > 0
+    assert_bits_equal(dA.spmv(x), oracle_lib.spmv(A.ptrow, A.indcol, A.coef, x))
+    assert_bits_equal(dA.mpk(5, x), oracle_lib.mpk(A.ptrow, A.indcol, A.coef, 5, x))
+    B = matgen.random_csr(4000, 5.0, seed=1, empty_rows=True)
+    xb = matgen.vec_uniform(B.n)
+    dB = nsk.CsrMatrix(ctx, B.ptrow, B.indcol, B.coef)
+    assert dB.packed_bytes == 0
+    assert_bits_equal(dB.spmv(xb), oracle_lib.spmv(B.ptrow, B.indcol, B.coef, xb))
+    assert_bits_equal(dB.mpk(3, xb), oracle_lib.mpk(B.ptrow, B.indcol, B.coef, 3, xb))
+    C = matgen.laplace3d_7pt(11, 9, 7)  # 693 rows: odd
+    xc = matgen.vec_uniform(C.n)
+    dC = nsk.CsrMatrix(ctx, C.ptrow, C.indcol, C.coef)
+    assert dC.packed_bytes == 0
+    assert_bits_equal(dC.mpk(3, xc), oracle_lib.mpk(C.ptrow, C.indcol, C.coef, 3, xc))
+
+
 # ---- distributed operator, degenerate world of one rank (the N > 1 path is covered by the gloo tests
 # ---- on CPU and by tools/dist_check.py under torchrun) ----------------------------------------------
 class _OneRank:
@@ -281,7 +442,7 @@ def test_distributed_operator_world1(ctx, oracle_lib, reset_options):
     dx = op.new_vector()
     op.set_owned(dx, x)
     ref = oracle_lib.mpk(A.ptrow, A.indcol, A.coef, K, x)
-    for strat in (1, 2):
+    for strat in (1, 2, 3, 4):
         ctx.set_option("mpk_kernel", strat)
         lv = [op.new_vector() for _ in range(K)]
         op.mpk(K, dx, lv)

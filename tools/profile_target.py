@@ -18,6 +18,8 @@ ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--k", type=int, default=4)
 ap.add_argument("--slack", type=int, default=-1)
 ap.add_argument("--wave-variant", type=int, default=0, help="0 = default, n = table entry n-1")
+ap.add_argument("--opt", action="append", default=[], help="name=value context option (repeatable)")
+ap.add_argument("--mpk-kernel", type=int, default=-1)
 args = ap.parse_args()
 A = matgen.laplace3d_7pt(args.grid)
 ctx = nsk.Context(0)
@@ -27,12 +29,18 @@ lv = [ctx.empty(A.n) for _ in range(args.k)]
 ctx.set_option("wave_slack_pct", args.slack)
 ctx.set_option("wave_variant", args.wave_variant)
 ctx.set_option("wave_l2_pct", 400)
+for o in args.opt:
+    name, val = o.split("=")
+    ctx.set_option(name, int(val))
 e0, e1 = ctx.event(), ctx.event()
 for i in range(args.reps + 1):
     if i == 1:
         e0.record()
     if args.what == "spmv":
         dA.spmv(x, lv[0])
+    elif args.what == "mpk":
+        ctx.set_option("mpk_kernel", args.mpk_kernel if args.mpk_kernel >= 0 else 0)
+        dA.mpk(args.k, x, lv)
     elif args.what == "mpk_wave":
         ctx.set_option("mpk_kernel", 2)
         dA.mpk(args.k, x, lv)

@@ -44,6 +44,13 @@ def main():
     ap.add_argument("--slacks", default="50,100,150")
     ap.add_argument("--skip-spmv", action="store_true")
     ap.add_argument("--wave-static", type=int, default=0)
+    ap.add_argument("--pipe-variants", default="0,1,2,3,4,5,6,7,8,9")
+    ap.add_argument("--pipe-leads", default="50,100,200")
+    ap.add_argument("--pipe-interleave", default="1,0")
+    ap.add_argument("--ks", default="4")
+    ap.add_argument("--packed-variants", default="0,1,2,3,4,5,6,7,8,9")
+    ap.add_argument("--bp-global", type=int, default=0)
+    ap.add_argument("--w0", default="100")
     args = ap.parse_args()
     t0 = time.time()
     if args.cfg == "c3":
@@ -87,7 +94,7 @@ def main():
         ctx.set_option("spmv_ctas_per_sm", 0)
         ctx.set_option("stream_variant", 0)
     # matrix powers
-    for k in (4,):
+    for k in [int(v) for v in args.ks.split(',')]:
         lv = [ctx.empty(A.n) for _ in range(k)]
         ctx.set_option("mpk_kernel", 1)
         dA.mpk(k, x, lv, 0)
@@ -99,7 +106,7 @@ def main():
         ctx.set_option("mpk_kernel", 2)
         ctx.set_option("wave_static", args.wave_static)
         ctx.set_option("wave_l2_pct", 400)  # never refuse in the sweep: we want to see the cliff
-        for wv in [int(v) for v in args.wave_variants.split(",")]:
+        for wv in [int(v) for v in args.wave_variants.split(",") if v != ""]:
             ctx.set_option("wave_variant", wv + 1)
             for slack in [int(v) for v in args.slacks.split(",")]:
                 ctx.set_option("wave_slack_pct", slack)
@@ -113,6 +120,55 @@ def main():
                 print(f"mpk k={k} wavefront v{wv} slack={slack:3d}% {'fused' if fused else 'LEVELS'}: {ms:8.4f} ms  B_mpk rate "
                       f"{Bk/ms/1e6:8.1f} GB/s ({Bk/ms/1e6/peak:5.3f}), SpMV-equivalent {k*B/ms/1e6:8.1f} GB/s  "
                       f"{'OK' if same else 'MISMATCH'}", flush=True)
+        ctx.set_option("mpk_kernel", 3)
+        for pv in [int(v) for v in args.pipe_variants.split(",") if v != ""]:
+            ctx.set_option("pipe_variant", pv + 1)
+            for il in [int(v) for v in args.pipe_interleave.split(",")]:
+                ctx.set_option("pipe_interleave", il)
+                for lead in [int(v) for v in args.pipe_leads.split(",")]:
+                    ctx.set_option("wave_slack_pct", lead)
+                    for l in lv:
+                        ctx.lib.nsk_memset0(ctx.h, l.ptr, 8 * A.n)
+                    l0 = ctx.launch_count
+                    dA.mpk(k, x, lv, 0)
+                    fused = (ctx.launch_count - l0) == 1
+                    same = all(np.array_equal(lv[i].to_host().view(np.int64), ref[i].view(np.int64)) for i in range(k))
+                    ms = timed(ctx, lambda: dA.mpk(k, x, lv, 0), max(4, args.reps // 4))
+                    print(f"mpk k={k} pipeline v{pv} il={il} lead={lead:3d}% {'fused' if fused else 'LEVELS'}: {ms:8.4f} ms  B_mpk rate "
+                          f"{Bk/ms/1e6:8.1f} GB/s ({Bk/ms/1e6/peak:5.3f}), SpMV-equivalent {k*B/ms/1e6:8.1f} GB/s  "
+                          f"{'OK' if same else 'MISMATCH'}", flush=True)
+        ctx.set_option("pipe_variant", 0)
+        ctx.set_option("mpk_kernel", 4)
+        ctx.set_option("pipe_bp_global", args.bp_global)
+        for pv in [int(v) for v in args.packed_variants.split(",") if v != ""]:
+            ctx.set_option("packed_variant", pv + 1)
+            t1 = time.time()
+            pb = dA.packed_bytes
+            print(f"# packed v{pv}: {pb/1e6:.1f} MB ({pb/max(1,A.nnz):.2f} B/nnz) packed in {time.time()-t1:.2f}s", flush=True)
+            ctx.set_option("spmv_kernel", 3)
+            dA.spmv(x, y, 0)
+            same = np.array_equal(y.to_host().view(np.int64), ref[0].view(np.int64))
+            ms = timed(ctx, lambda: dA.spmv(x, y, 0), args.reps)
+            print(f"spmv packed v{pv}: {ms:8.4f} ms {B/ms/1e6:8.1f} GB/s {B/ms/1e6/peak:6.3f} of measured peak  {'OK' if same else 'MISMATCH'}", flush=True)
+            ctx.set_option("spmv_kernel", 0)
+            for il, w0 in [(int(v), int(w)) for v in args.pipe_interleave.split(",") for w in args.w0.split(",")]:
+                ctx.set_option("pipe_interleave", il)
+                ctx.set_option("pipe_w0_pct", w0)
+                for lead in [int(v) for v in args.pipe_leads.split(",")]:
+                    ctx.set_option("wave_slack_pct", lead)
+                    for l in lv:
+                        ctx.lib.nsk_memset0(ctx.h, l.ptr, 8 * A.n)
+                    l0 = ctx.launch_count
+                    dA.mpk(k, x, lv, 0)
+                    fused = (ctx.launch_count - l0) == 1
+                    same = all(np.array_equal(lv[i].to_host().view(np.int64), ref[i].view(np.int64)) for i in range(k))
+                    ms = timed(ctx, lambda: dA.mpk(k, x, lv, 0), max(4, args.reps // 4))
+                    print(f"mpk k={k} packed v{pv} il={il} w0={w0} lead={lead:3d}% {'fused' if fused else 'LEVELS'}: {ms:8.4f} ms  B_mpk rate "
+                          f"{Bk/ms/1e6:8.1f} GB/s ({Bk/ms/1e6/peak:5.3f}), SpMV-equivalent {k*B/ms/1e6:8.1f} GB/s  "
+                          f"{'OK' if same else 'MISMATCH'}", flush=True)
+        ctx.set_option("packed_variant", 0)
+        ctx.set_option("pipe_w0_pct", 0)
+        ctx.set_option("pipe_interleave", 1)
         ctx.set_option("wave_slack_pct", -1)
         ctx.set_option("wave_l2_pct", 0)
         ctx.set_option("spmv_ctas_per_sm", 0)
