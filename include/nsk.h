@@ -170,8 +170,9 @@ int nsk_gram(nsk_ctx_t ctx, int64_t n, int m, const double *const *V, double *G,
 /* ---- conjugate gradients --------------------------------------------------------------------- */
 /* Solves A x = b (A symmetric positive definite), x0 = 0, stops when ||r||_2/||b||_2 <= tol.
  * sstep <= 1: classical CG (3 fused kernels per iteration, scalars stay on the device).
- * sstep  > 1: s-step (communication-avoiding) CG: one matrix-powers call + one Gram reduction per
- *             s iterations.  iters counts CG iterations (s per outer step).
+ * sstep  > 1: s-step (communication-avoiding) CG, s = 2..4, monomial basis: two matrix-powers calls
+ *             (depth s on p, s-1 on r), ONE Gram reduction / all-reduce and ONE fused update per s
+ *             iterations.  iters counts CG iterations (the last block is cut at the converged one).
  * With a communicator attached (nsk_comm_init) A is this rank's row slab created by
  * nsk_csr_create_dist and b, x are the owned parts; dots are all-reduced over NCCL. */
 int nsk_cg(nsk_csr_t A, const double *b, double *x, double tol, int maxit, int sstep,

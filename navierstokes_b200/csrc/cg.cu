@@ -230,7 +230,7 @@ NSK_API int nsk_cg(nsk_csr_t A, const double *b, double *x, double tol, int maxi
     nsk_ctx_t ctx = A->ctx;
     NSK_REQUIRE(ctx, b && x, "b or x is null");
     NSK_REQUIRE(ctx, tol > 0.0 && maxit >= 0, "bad tolerance / maxit");
-    NSK_REQUIRE(ctx, sstep <= 8, "s-step depth above 8 is not supported");
+    NSK_REQUIRE(ctx, sstep <= 4, "s-step depth above 4 is not supported (2s+1 <= 9 vectors per Gram pass)");
     NSK_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t nb = sizeof(double) * (size_t)nsk_csr_owned_rows(A);
     const double *db = b;

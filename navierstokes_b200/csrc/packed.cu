@@ -729,7 +729,9 @@ static PkLevelPlan *pk_level_plan(nsk_csr_t A, PackedOp *op, int k, const int *l
         // data plus the level vectors over it; by default the slack is whatever the L2 budget allows -- measured
         // on 256^3: time falls with the window until it reaches ~100 MB, then HBM re-reads set in.
         const double tile_bytes = (double)op->blob_bytes / ntiles + 8.0 * op->t_rows * (k + 1);
-        const double budget = (ctx->opt.wave_l2_pct > 0 ? (double)ctx->opt.wave_l2_pct : 80.0) / 100.0 *
+        // budget: 65 % of L2 by default -- ncu (profiles/r01_ncu_packed_dram_traffic.txt): an 81 MB window costs the
+        // compulsory 1.47 GB of HBM reads, a 101 MB one 4.9 GB (the level vectors and x runs share the cache)
+        const double budget = (ctx->opt.wave_l2_pct > 0 ? (double)ctx->opt.wave_l2_pct : 65.0) / 100.0 *
                               (double)ctx->prop.l2CacheSize;
         const int lead_min = D.reach + 1 + WF_GROUP;
         if (lead_pct >= 0)

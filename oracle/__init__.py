@@ -203,6 +203,61 @@ class _Oracle:
                               C.byref(rel), hist.ctypes.data)
         return x, it, rel.value, hist[:it + 1].copy()
 
+    def scg(self, ptrow, indcol, coef, b, s=4, tol=1e-8, maxit=1000):
+        """s-step (CA-)CG, monomial basis: CPU restatement of navierstokes_b200/csrc/sstep_cg.cu (the reference has
+        no CG, SURVEY.md F2 -- parity unpinned).  Products use the pinned oracle SpMV (SpMV_CSR_FMA,
+        reference mpk/SpMV.cpp:41-56); Gram and updates in numpy.  Returns (x, iterations, relres, converged)."""
+        n = len(ptrow) - 1
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        x = np.zeros(n)
+        r = b.copy()
+        p = b.copy()
+        bb = float(b @ b)
+        if bb == 0.0:
+            return x, 0, 0.0, True
+        m = 2 * s + 1
+        it = 0
+        rr = bb
+        done = False
+        while it < maxit and not done:
+            V = np.empty((m, n))
+            V[0] = p
+            for j in range(s):
+                V[j + 1] = self.spmv(ptrow, indcol, coef, V[j])
+            V[s + 1] = r
+            for j in range(s - 1):
+                V[s + 2 + j] = self.spmv(ptrow, indcol, coef, V[s + 1 + j])
+            G = V @ V.T
+            xc = np.zeros(m); rc = np.zeros(m); pc = np.zeros(m)
+            pc[0] = 1.0
+            rc[s + 1] = 1.0
+            rr = G[s + 1, s + 1]
+            for _ in range(s):
+                if it >= maxit:
+                    break
+                w = np.zeros(m)
+                w[1:s + 1] = pc[0:s]
+                w[s + 2:2 * s + 1] = pc[s + 1:2 * s]
+                denom = pc @ (G @ w)
+                if not (denom > 0.0 and rr > 0.0):
+                    done = True  # breakdown
+                    break
+                alpha = rr / denom
+                xc += alpha * pc
+                rc -= alpha * w
+                rr_new = rc @ (G @ rc)
+                it += 1
+                if rr_new <= tol * tol * bb:
+                    rr = max(rr_new, 0.0)
+                    done = True
+                    break
+                pc = rc + (rr_new / rr) * pc
+                rr = rr_new
+            x = x + xc @ V
+            r = rc @ V
+            p = pc @ V
+        return x, it, float(np.sqrt(max(rr, 0.0) / bb)), bool(rr <= tol * tol * bb)
+
     def true_relres(self, ptrow, indcol, coef, b, x):
         n = len(ptrow) - 1
         return float(self.l.oracle_true_relres(n, _i32(ptrow), _i32(indcol), _f64(coef), _f64(b), _f64(x)))

@@ -451,3 +451,5 @@ def test_distributed_operator_world1(ctx, oracle_lib, reset_options):
     b = oracle_lib.spmv(A.ptrow, A.indcol, A.coef, x)
     xs, it, rel, ok = op.cg(b, tol=1e-9, maxit=500)
     assert ok and np.max(np.abs(xs - x)) < 1e-6
+    xs4, it4, rel4, ok4 = op.cg(b, tol=1e-9, maxit=500, sstep=4)
+    assert ok4 and abs(it4 - it) <= 2 and np.max(np.abs(xs4 - x)) < 1e-6

@@ -103,3 +103,55 @@ def test_cg_zero_rhs(ctx):
     dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
     x, it, rel, ok = dA.cg(np.zeros(A.n))
     assert ok and it == 0 and np.all(x == 0)
+
+
+# ---- s-step (communication-avoiding) CG ------------------------------------------------------------------
+@pytest.mark.parametrize("s", [2, 3, 4])
+@pytest.mark.parametrize("gen,args", [("laplace3d_7pt", (24,)), ("laplace2d_5pt", (96,)), ("laplace3d_7pt", (40, 32, 36))])
+def test_sstep_cg_matches_oracle(ctx, oracle_lib, gen, args, s):
+    """Parity unpinned (no CG in the reference): s-step CG against its numpy restatement (oracle.scg) and against
+    classical CG -- in exact arithmetic all three produce the same iterates, so the iteration counts agree within
+    +-2 and the TRUE residual (CPU oracle SpMV) meets the tolerance."""
+    A = getattr(matgen, gen)(*args)
+    xt = matgen.vec_uniform(A.n, seed=1)
+    b = oracle_lib.spmv(A.ptrow, A.indcol, A.coef, xt)
+    _, it_cg, _, _ = oracle_lib.cg(A.ptrow, A.indcol, A.coef, b, tol=1e-8, maxit=2000)
+    _, it_ref, rel_ref, ok_ref = oracle_lib.scg(A.ptrow, A.indcol, A.coef, b, s=s, tol=1e-8, maxit=2000)
+    assert ok_ref
+    dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
+    x, it, rel, ok = dA.cg(b, tol=1e-8, maxit=2000, sstep=s)
+    assert ok and rel <= 1e-8
+    assert abs(it - it_ref) <= 2 and abs(it - it_cg) <= 2, (it, it_ref, it_cg)
+    assert oracle_lib.true_relres(A.ptrow, A.indcol, A.coef, b, x) <= 5e-8
+    assert np.max(np.abs(x - xt)) <= 1e-5
+
+
+def test_sstep_cg_maxit_and_zero_rhs(ctx, oracle_lib):
+    A = matgen.laplace2d_5pt(64)
+    b = matgen.vec_uniform(A.n, seed=3)
+    dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
+    x, it, rel, ok = dA.cg(b, tol=1e-12, maxit=6, sstep=4)  # 6 = one full block + a block cut after 2 iterations
+    assert not ok and it == 6 and rel > 1e-12
+    _, _, _, hist = oracle_lib.cg(A.ptrow, A.indcol, A.coef, b, tol=1e-12, maxit=6)
+    assert abs(rel - hist[6]) <= 1e-8 * hist[6]
+    x, it, rel, ok = dA.cg(np.zeros(A.n), sstep=4)
+    assert ok and it == 0 and np.all(x == 0)
+
+
+def test_sstep_cg_device_vectors_and_strategies(ctx, oracle_lib):
+    """Device-resident call; the matrix-powers strategy underneath (fused packed pipeline vs k launches) does not
+    change the iterates beyond rounding of the Gram sums."""
+    A = matgen.laplace3d_7pt(48)
+    xt = matgen.vec_uniform(A.n, seed=2)
+    b = oracle_lib.spmv(A.ptrow, A.indcol, A.coef, xt)
+    dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
+    db = ctx.to_device(b)
+    its = []
+    for strat in (0, 1):
+        ctx.set_option("mpk_kernel", strat)
+        dx, it, rel, ok = dA.cg(db, tol=1e-8, maxit=2000, sstep=4)
+        assert ok
+        assert oracle_lib.true_relres(A.ptrow, A.indcol, A.coef, b, dx.to_host()) <= 5e-8
+        its.append(it)
+    ctx.set_option("mpk_kernel", 0)
+    assert abs(its[0] - its[1]) <= 1
