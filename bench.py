@@ -274,8 +274,15 @@ def main():
         step_dev()
     e1.record()
     ms_total = e0.elapsed_ms(e1)
-    barrier()
     launches = ctx.launch_count - launches0
+    # the timed region lasts a few milliseconds, nvidia-smi samples every 200 ms: keep the SAME load running
+    # (untimed) until the sampler has seen it at least twice
+    t_end = time.time() + 1.5
+    while len(sampler.lines) < 3 and time.time() < t_end:
+        for _ in range(20):
+            step_dev()
+        ctx.sync()
+    barrier()
     clocks = sampler.stop()
     ms_step = max_over_ranks(ms_total / args.steps)
     equiv_total = K_POWERS * spmv_bytes * world

@@ -339,6 +339,53 @@ class CsrMatrix:
         return x, it.value, rel.value, s == 0
 
 
+class Bcsr4Matrix:
+    """Device-resident 4x4 block CSR operator (row-major blocks): the reference's bcsr4x4_matrix
+    (mpk/SpMV.h:26-33) as built by generate_BCSR4 (mpk/utils.cpp:45-95)."""
+
+    def __init__(self, ctx: Context, ptrow, indcol, coef):
+        self.ctx = ctx
+        ptrow = np.ascontiguousarray(ptrow, dtype=np.int32)
+        indcol = np.ascontiguousarray(indcol, dtype=np.int32)
+        coef = np.ascontiguousarray(coef, dtype=np.float64)
+        self.nbrows = len(ptrow) - 1
+        self.nblocks = len(indcol)
+        self.n = 4 * self.nbrows
+        assert coef.size == 16 * self.nblocks
+        h = C.c_void_p()
+        ctx._ck(ctx.lib.nsk_bcsr4_create(ctx.h, self.nbrows, self.nblocks, C.c_void_p(_ptr(ptrow)),
+                                         C.c_void_p(_ptr(indcol)), C.c_void_p(_ptr(coef)), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h is not None and self.ctx.h is not None:
+            self.ctx.lib.nsk_bcsr4_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def spmv_bytes(self) -> int:
+        """Algorithmic bytes of one product: 128 B of values + 4 B of index per block, row pointers, x and y once."""
+        return 132 * self.nblocks + 4 * (self.nbrows + 1) + 16 * self.n
+
+    def spmv(self, x, y=None, mode: int = EXACT_FMA):
+        """y = B x.  numpy in -> numpy out (host call); DeviceVector in -> enqueue only."""
+        if isinstance(x, DeviceVector):
+            y = self.ctx.empty(self.n) if y is None else y
+            self.ctx._ck(self.ctx.lib.nsk_spmv_bcsr4(self.h, x.ptr, y.ptr, mode, DEVICE))
+            return y
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        assert x.size == self.n
+        y = np.empty(self.n) if y is None else y
+        self.ctx._ck(self.ctx.lib.nsk_spmv_bcsr4(self.h, C.c_void_p(_ptr(x)), C.c_void_p(_ptr(y)), mode, HOST))
+        return y
+
+
 # =================================================================================================
 # reference-named layer
 # =================================================================================================
@@ -396,6 +443,54 @@ def SpMV_CSR_FMA(y, x, A: csrmatrix):
 def SpMV_CSR_AVX2(y, x, A: csrmatrix):
     """mpk/SpMV.cpp:59-85 -- reassociated; mapped to the fast mode (any row length is fine here)."""
     A.gpu().spmv(x, _out(y, A.n), FAST)
+
+
+@dataclass
+class bcsr4x4_matrix:
+    """Field-for-field the reference's block container (mpk/SpMV.h:26-33); coef is flat, 16 doubles per block,
+    row-major inside a block."""
+    nrows: int = 0
+    nblocks: int = 0
+    ptrow: np.ndarray = field(default_factory=lambda: np.zeros(1, np.int32))
+    indcol: np.ndarray = field(default_factory=lambda: np.zeros(0, np.int32))
+    coef: np.ndarray = field(default_factory=lambda: np.zeros(0, np.float64))
+    _gpu: Bcsr4Matrix | None = field(default=None, repr=False, compare=False)
+    _key: tuple | None = field(default=None, repr=False, compare=False)
+
+    def gpu(self) -> Bcsr4Matrix:
+        key = (self.ptrow.ctypes.data, self.indcol.ctypes.data, self.coef.ctypes.data, self.nrows, len(self.indcol))
+        if self._gpu is None or self._key != key:
+            self._gpu = Bcsr4Matrix(default_context(), self.ptrow, self.indcol, self.coef)
+            self._key = key
+        return self._gpu
+
+
+def SpMV_BCSR(y, x, A: bcsr4x4_matrix):
+    """mpk/SpMV.cpp:90-121 (x87 in the reference) -> separately rounded multiply-add chain in (block, j) order."""
+    A.gpu().spmv(x, _out(y, 4 * A.nrows), EXACT_MULADD)
+
+
+def SpMV_BCSR_OPT(y, x, A: bcsr4x4_matrix):
+    """mpk/SpMV.cpp:124-150 (compiles to fma chains)."""
+    A.gpu().spmv(x, _out(y, 4 * A.nrows), EXACT_FMA)
+
+
+def SpMV_BCSR_FMA(y, x, A: bcsr4x4_matrix):
+    """mpk/SpMV.cpp:153-178 -- the bit-exact flavour."""
+    A.gpu().spmv(x, _out(y, 4 * A.nrows), EXACT_FMA)
+
+
+def SpMV_BCSR_AVX2(y, x, A: bcsr4x4_matrix):
+    """mpk/SpMV.cpp:181-219: lane i of the AVX2 kernel runs the same (block, j) fma chain as row 4*bi+i here."""
+    A.gpu().spmv(x, _out(y, 4 * A.nrows), EXACT_FMA)
+
+
+def SpM2V_BCSR_OPT(z, y, x, A: bcsr4x4_matrix, ptrowend1=None):
+    """mpk/SpM2V.cpp:452 -- y = A x, z = A y on the block operator (two products; the reference's first-touch
+    schedule only changes the order in which rows of y are produced, not their values)."""
+    g = A.gpu()
+    g.spmv(x, _out(y, 4 * A.nrows), EXACT_FMA)
+    g.spmv(y, _out(z, 4 * A.nrows), EXACT_FMA)
 
 
 def Generate1stlayer(ptrowend1, A: csrmatrix):

@@ -257,10 +257,21 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
         int4 cur = make_int4(0, 0, 0, -1), nxt = cur;  // lane u: item it0 + u (cur) and it0 + 32 + u (nxt)
         if (lane < n_my) cur = my[2 * ((size_t)c + (size_t)lane * G)];
         if (32 + lane < n_my) nxt = my[2 * ((size_t)c + (size_t)(32 + lane) * G)];
-        int cw = 0, nw = 0;  // lane u < 24: word u of the PkTile of the current / next item
+        // lane u < 24: word u of the PkTile of item it (cw), it + 1 (nw), it + 2 (fw): fetched TWO items ahead, so
+        // the descriptor's L2 (first sweep: HBM) latency never sits between a stage becoming free and its x copies
+        int cw = 0, nw = 0, fw = 0;
+        auto tile_of = [&](int i, int j0) {  // tile of item i, given that `cur` holds items j0 .. j0 + 31
+            const int a = __shfl_sync(0xffffffffu, cur.x, (i - j0) & 31);
+            const int b = __shfl_sync(0xffffffffu, nxt.x, (i - j0) & 31);
+            return i - j0 < 32 ? a : b;
+        };
         if (n_my > 0) {
-            const int t0 = __shfl_sync(0xffffffffu, cur.x, 0);
+            const int t0 = tile_of(0, 0);
             if (lane < 24) cw = __ldg(tw + (size_t)t0 * 24 + lane);
+        }
+        if (n_my > 1) {
+            const int t1 = tile_of(1, 0);
+            if (lane < 24) nw = __ldg(tw + (size_t)t1 * 24 + lane);
         }
         for (int it = 0; it < n_my; ++it) {
             const int j = it & 31;
@@ -269,12 +280,9 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
                 nxt = make_int4(0, 0, 0, -1);
                 if (it + 32 + lane < n_my) nxt = my[2 * ((size_t)c + (size_t)(it + 32 + lane) * G)];
             }
-            // prefetch the tile descriptor of item it + 1 (its latency hides behind this item's waits)
-            if (it + 1 < n_my) {
-                const int tn_cur = __shfl_sync(0xffffffffu, cur.x, (j + 1) & 31);
-                const int tn_nxt = __shfl_sync(0xffffffffu, nxt.x, 0);
-                const int tn = j + 1 < 32 ? tn_cur : tn_nxt;
-                if (lane < 24) nw = __ldg(tw + (size_t)tn * 24 + lane);
+            if (it + 2 < n_my) {
+                const int tn = tile_of(it + 2, it - j);
+                if (lane < 24) fw = __ldg(tw + (size_t)tn * 24 + lane);
             }
             const int ghi = __shfl_sync(0xffffffffu, cur.z, j);
             const int gback = __shfl_sync(0xffffffffu, cur.w, j);
@@ -300,6 +308,7 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
             }
             if (timing && lane == 0) ts[s * 4 + 1] = pk_now();
             cw = nw;
+            nw = fw;
         }
         if (timing && lane == 0) {
             P.timing[(size_t)blockIdx.x * 16 + 6] = w_done;  // dependency warp: waiting for its stage to be free

@@ -282,6 +282,37 @@ def random_banded_csr(n: int, half_bw: int, mean_row: float, seed: int = 0, empt
     return Csr(n=n, ptrow=ptrow.astype(np.int32), indcol=indcol, coef=coef, ncols=n)
 
 
+@dataclass
+class Bcsr4:
+    """4x4 block CSR with row-major blocks: the layout of the reference's bcsr4x4_matrix (mpk/SpMV.h:26-33)."""
+    nbrows: int
+    ptrow: np.ndarray   # int32 [nbrows + 1]
+    indcol: np.ndarray  # int32 [nblocks], block columns in first-appearance order
+    coef: np.ndarray    # float64 [16 * nblocks]
+
+
+def csr_to_bcsr4(A: Csr) -> Bcsr4:
+    """Blocks a CSR operator (n a multiple of 4) the way generate_BCSR4 does (reference mpk/utils.cpp:45-95): block
+    columns of a block row in order of first appearance in the row-major traversal, explicit zeros inside blocks."""
+    assert A.n % 4 == 0
+    nb = A.n // 4
+    rows = np.repeat(np.arange(A.n, dtype=np.int64), np.diff(A.ptrow))
+    cols = A.indcol.astype(np.int64)
+    key = (rows // 4) * nb + cols // 4
+    uniq, first, inv = np.unique(key, return_index=True, return_inverse=True)
+    order = np.argsort(first, kind="stable")       # block id in storage order -> index into uniq
+    rank = np.empty_like(order)
+    rank[order] = np.arange(len(order))            # uniq index -> block id
+    blk = rank[inv]
+    coef = np.zeros(16 * len(uniq))
+    coef[blk * 16 + (rows % 4) * 4 + cols % 4] = A.coef
+    brow = uniq[order] // nb
+    ptrow = np.zeros(nb + 1, dtype=np.int64)
+    np.add.at(ptrow, brow + 1, 1)
+    ptrow = np.cumsum(ptrow)
+    return Bcsr4(nbrows=nb, ptrow=ptrow.astype(np.int32), indcol=(uniq[order] % nb).astype(np.int32), coef=coef)
+
+
 # ---------------------------------------------------------------------------------------------
 # Input vectors (SURVEY.md section 8d)
 # ---------------------------------------------------------------------------------------------

@@ -453,3 +453,43 @@ def test_distributed_operator_world1(ctx, oracle_lib, reset_options):
     assert ok and np.max(np.abs(xs - x)) < 1e-6
     xs4, it4, rel4, ok4 = op.cg(b, tol=1e-9, maxit=500, sstep=4)
     assert ok4 and abs(it4 - it) <= 2 and np.max(np.abs(xs4 - x)) < 1e-6
+
+
+# ---- 4x4 block CSR (the reference's fastest format for its FEM matrices) -------------
+def test_bcsr4_golden_bitwise(ctx):
+    """SpMV_BCSR_{OPT,FMA,AVX2} on the reference's own generate_BCSR4 output (fixture made by oracle/_ref): bit
+    for bit; the x87 variant within its own reproducibility bound; fused A^2 x = two products."""
+    g = golden("formats")
+    B = nsk.bcsr4x4_matrix(nrows=len(g["bcsr_ptrow"]) - 1, nblocks=len(g["bcsr_indcol"]), ptrow=g["bcsr_ptrow"],
+                           indcol=g["bcsr_indcol"], coef=g["bcsr_coef"])
+    x = g["x"]
+    n = 4 * B.nrows
+    for fn, key in ((nsk.SpMV_BCSR_OPT, "opt"), (nsk.SpMV_BCSR_FMA, "fma"), (nsk.SpMV_BCSR_AVX2, "avx2")):
+        y = np.zeros(n)
+        fn(y, x, B)
+        assert_bits_equal(y, g[f"bcsr_spmv_{key}"], key)
+    y = np.zeros(n)
+    nsk.SpMV_BCSR(y, x, B)
+    assert nsk.rel_error(g["bcsr_spmv_x87"], y) <= 1e-15
+    y, z = np.zeros(n), np.zeros(n)
+    nsk.SpM2V_BCSR_OPT(z, y, x, B)
+    assert nsk.rel_error(g["bcsr_spm2v_opt_y"], y) <= 1e-15 and nsk.rel_error(g["bcsr_spm2v_opt_z"], z) <= 1e-14
+
+
+def test_bcsr4_fem_operator_matches_oracle_and_csr(ctx, oracle_lib):
+    """FEM-like BAIJ-4 operator: blocked on the host like generate_BCSR4, product bit-identical to the oracle's
+    SpMV_BCSR_FMA restatement, and equal to the CSR product up to the explicit zeros' rounding (<= 1e-13)."""
+    A = matgen.fem_baij4(6)
+    Bh = matgen.csr_to_bcsr4(A)
+    rows = np.repeat(np.arange(A.n, dtype=np.int32), np.diff(A.ptrow))
+    bp, bc, bv = oracle_lib.generate_bcsr4(A.n, rows, A.indcol, A.coef)
+    assert np.array_equal(bp, Bh.ptrow) and np.array_equal(bc, Bh.indcol)
+    assert_bits_equal(bv, Bh.coef)
+    x = matgen.vec_uniform(A.n, seed=6)
+    dB = nsk.Bcsr4Matrix(ctx, Bh.ptrow, Bh.indcol, Bh.coef)
+    y = dB.spmv(x)
+    assert_bits_equal(y, oracle_lib.spmv_bcsr4(Bh.ptrow, Bh.indcol, Bh.coef, x))
+    dx = ctx.to_device(x)
+    assert_bits_equal(dB.spmv(dx).to_host(), y)
+    y_csr = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef).spmv(x)
+    assert oracle_lib.rel_error(y_csr, y) <= 1e-13

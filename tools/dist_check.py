@@ -41,11 +41,13 @@ def main():
     y = op.new_vector()
     op.spmv(dx, y)
     bad += not np.array_equal(op.get_owned(y).view(np.int64), ref[0][lo:hi].view(np.int64))
-    for strat in (1, 2):
+    used = {}
+    for strat in (1, 2, 3, 4, 0):
         ctx.set_option("mpk_kernel", strat)
         for k in (1, 2, 3, 4):
             lv = [op.new_vector() for _ in range(k)]
             op.mpk(k, dx, lv)
+            used[(strat, k)] = ctx.query("last_mpk_strategy")
             for l in range(k):
                 ok = np.array_equal(op.get_owned(lv[l]).view(np.int64), ref[l][lo:hi].view(np.int64))
                 bad += not ok
@@ -56,6 +58,9 @@ def main():
     op.mpk_host(K, np.ascontiguousarray(x[lo:hi]), outs)
     for l in range(K):
         bad += not np.array_equal(outs[l].view(np.int64), ref[l][lo:hi].view(np.int64))
+    ctx.set_option("mpk_kernel", 0)
+    if rank == 0:
+        print("strategy actually run per (requested, k):", used, flush=True)
     # CG
     b = lib.spmv(A.ptrow, A.indcol, A.coef, x)
     xs, it, rel, ok = op.cg(np.ascontiguousarray(b[lo:hi]), tol=1e-9, maxit=800)
@@ -63,11 +68,17 @@ def main():
     err = float(np.max(np.abs(xs - x_ref[lo:hi])))
     cg_ok = ok and abs(it - it_ref) <= 2 and err < 1e-6
     bad += not cg_ok
+    xs4, it4, rel4, ok4 = op.cg(np.ascontiguousarray(b[lo:hi]), tol=1e-9, maxit=800, sstep=4)
+    err4 = float(np.max(np.abs(xs4 - x_ref[lo:hi])))
+    scg_ok = ok4 and abs(it4 - it_ref) <= 2 and err4 < 1e-6
+    if not scg_ok:
+        print(f"rank {rank}: s-step CG FAILED it={it4} rel={rel4} err={err4}", flush=True)
+    bad += not scg_ok
     t = torch.tensor([bad], device=f"cuda:{local}")
     dist.all_reduce(t)
     if rank == 0:
         print(f"dist_check world={world}: {'OK' if t.item() == 0 else 'FAILED'}  cg it={it} (oracle {it_ref}) relres={rel:.2e} "
-              f"max|x-x_ref|={err:.2e}", flush=True)
+              f"max|x-x_ref|={err:.2e}; s-step(4) it={it4} relres={rel4:.2e} max|x-x_ref|={err4:.2e}", flush=True)
     dist.destroy_process_group()
     return int(t.item() != 0)
 

@@ -28,7 +28,7 @@ x = ctx.to_device(matgen.vec_uniform(A.n, 1))
 lv = [ctx.empty(A.n) for _ in range(args.k)]
 ctx.set_option("wave_slack_pct", args.slack)
 ctx.set_option("wave_variant", args.wave_variant)
-ctx.set_option("wave_l2_pct", 400)
+pass  # (wave_l2_pct is left at its default; override with --opt wave_l2_pct=N)
 for o in args.opt:
     name, val = o.split("=")
     ctx.set_option(name, int(val))
