@@ -191,6 +191,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--grid", type=int, default=GRID, help="grid edge (default 256; smaller only for debugging)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cg", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     globals()["GRID"] = args.grid
@@ -355,6 +356,24 @@ def main():
                  "frac_of_peak": spmv_bytes / spmv_ms / 1e6 / peak, "algorithmic_bytes": int(spmv_bytes)},
         "mpk_bytes_rate_GBps": mpk_bytes * world / ms_step / 1e6,
     }
+    # ---- Poisson CG iterations per second on the same operator (BASELINE metric, second half) ------------------
+    if world == 1 and not args.no_cg:
+        b = ctx.empty(A.n)
+        dA.spmv(dx, b)
+        xs = ctx.empty(A.n)
+        cg = {}
+        for s_step, name in ((1, "classical"), (4, "sstep4")):
+            nit = 48
+            dA.cg(b, xs, tol=1e-300, maxit=nit, sstep=s_step)  # warm: plans, workspace
+            ctx.sync()
+            t0 = time.perf_counter()
+            _, it, _, _ = dA.cg(b, xs, tol=1e-300, maxit=nit, sstep=s_step)
+            ctx.sync()
+            cg[name + "_iters_per_s"] = it / (time.perf_counter() - t0)
+        cg["note"] = ("48 iterations each on the 256^3 operator, device-resident b and x, host wall clock around the whole "
+                      "nsk_cg call (includes its workspace allocation)")
+        out["cg"] = cg
+        del b, xs
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         T = cpu_threads()
         ref = CpuReference(A, T)

@@ -40,7 +40,7 @@ int nsk_mpk_levels(nsk_csr_t A, int k, const double *d_x, double *const *d_level
     return NSK_OK;
 }
 
-// Picks the strategy: option mpk_kernel = 0 auto (4, then 3, then 1), 1 levels, 2 wavefront, 3 level pipeline on
+// Picks the strategy: option mpk_kernel = 0 auto (4 when the operator packs, else 1), 1 levels, 2 wavefront, 3 level pipeline on
 // CSR, 4 level pipeline on the packed format (packed.cu).  A fused
 // kernel that does not apply to the pattern (window larger than its L2 budget, long rows) degrades to k
 // launches -- still a GPU path.  level_rows: distributed slabs evaluate level l on a row prefix.
@@ -55,7 +55,10 @@ int nsk_mpk_local(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
         int s = nsk_packed_run(A, k, d_x, d_levels, mode, level_rows, nullptr, -1);
         if (s != NSK_ERR_UNSUPPORTED) { ctx->last_mpk = 4; return s; }
     }
-    if (automatic) sel = 3;
+    // the CSR level pipeline (3) and the wavefront kernel (2) stay explicit choices: with global gathers they lose to k
+    // launches of the streaming kernel wherever they were measured (256^3: 0.86 / 0.90 vs 0.98 ms before the packed
+    // format existed; RCM'd tet mesh k=8: 1.03 vs 0.30 ms, profiles/r01_configs.txt)
+    if (automatic) sel = 1;
     if (sel == 3 && k > 1 && nsk_mpk_pipeline_applicable(A, k)) {
         int s = nsk_mpk_pipeline(A, k, d_x, d_levels, mode, level_rows);
         if (s != NSK_ERR_UNSUPPORTED) { ctx->last_mpk = 3; return s; }

@@ -347,7 +347,7 @@ static PipePlan *pipe_plan(nsk_csr_t A, int k, const int *level_rows, const Pipe
     p.k = k; p.t_nnz = V.t_nnz; p.t_rows = V.t_rows; p.team = team; p.lead_pct = lead_pct; p.level_rows = lr;
     p.ngroups = ngroups; p.reach = D.reach; p.lead = lead;
     // The window that must stay in L2: (k-1)*lead tiles of matrix data plus the level vectors over it.
-    const double tile_bytes = 12.0 * A->mean_row * V.t_rows + 8.0 * V.t_rows * (k + 1);
+    const double tile_bytes = (12.0 * (double)A->nnz + 8.0 * (double)A->n * (k + 1)) / (double)ntiles;  // mean tile
     const double window = (double)(k - 1) * lead * tile_bytes;
     const double budget = (ctx->opt.wave_l2_pct > 0 ? (double)ctx->opt.wave_l2_pct : 80.0) / 100.0;
     if (window > budget * (double)ctx->prop.l2CacheSize) {
@@ -389,7 +389,7 @@ static PipePlan *pipe_plan(nsk_csr_t A, int k, const int *level_rows, const Pipe
 
 bool nsk_mpk_pipeline_applicable(nsk_csr_t A, int k)
 {
-    if (k < 2 || A->mean_row > 12.0 || A->n == 0) return false;
+    if (k < 2 || A->mean_row > 64.0 || A->n == 0) return false;
     const char *why = nullptr;
     pipe_fn fn; int smem, team;
     const int variant = pipe_variant(A->ctx);

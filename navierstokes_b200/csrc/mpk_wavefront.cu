@@ -585,7 +585,7 @@ static int wave_launch_shape(nsk_ctx_t ctx, int variant, bool muladd, int k, wav
 
 bool nsk_mpk_wavefront_applicable(nsk_csr_t A, int k)
 {
-    if (k < 2 || A->mean_row > 12.0 || A->n == 0) return false;
+    if (k < 2 || A->mean_row > 64.0 || A->n == 0) return false;
     const char *why = nullptr;
     wave_fn fn; int smem, grid_max, slack;
     const int variant = wave_variant(A->ctx);

@@ -45,7 +45,7 @@ struct nsk_options {
                                   // 2 stream (CSR slices by TMA, x gathered from global), 3 packed (x runs staged too)
     int64_t packed_variant = 0;   // 0 default, else 1 + index into the packed kernel table
     int64_t spmv_ctas_per_sm = 0; // 0 = kernel default
-    int64_t mpk_kernel = 0;       // 0 auto (4, 3, 1 in that order), 1 = k separate products, 2 = L2 wavefront,
+    int64_t mpk_kernel = 0;       // 0 auto (4 if the operator packs, else 1), 1 = k separate products, 2 = L2 wavefront,
                                   // 3 = level pipeline on CSR, 4 = level pipeline on the packed format
     int64_t pipe_variant = 0;     // 0 default, else 1 + index into the level-pipeline kernel table
     int64_t pk_timing = 0;        // 1: packed kernel records its stage cycle and prints per-level averages (debug)
@@ -53,6 +53,7 @@ struct nsk_options {
     int64_t pipe_bp_global = -1;  // back-pressure of the packed level pipeline: 0 = level l held by l+1, 1 = level 0 held
                                   // by k-1 (one window for the whole pipeline), < 0 = default (1)
     int64_t pipe_interleave = 1;  // 1: level = blockIdx % k (each SM hosts every level), 0: level = blockIdx / team
+    int64_t stream_exact_kind = 0; // exact modes of the stream kernel: 0 auto, 1 thread-per-row gathers, 2 gather to smem first
     int64_t stream_variant = 0;   // 0 auto, else 1 + index into the stream kernel table
     int64_t wave_variant = 0;     // index into the wavefront kernel table
     int64_t wave_slack_pct = -1;  // extra level skew, % of (resident CTAs x stages / k) tiles; <0 = default 150

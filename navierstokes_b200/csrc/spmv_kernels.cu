@@ -446,7 +446,10 @@ int nsk_launch_spmv(nsk_csr_t A, const nsk_spmv_args &a)
     }
     const bool muladd = a.mode == NSK_EXACT_MULADD;
     const bool fast = a.mode == NSK_FAST;
-    const bool long_rows = A->mean_row > 12.0;
+    // measured (tools/probe_longrows.py, profiles/r01_probe_longrows.txt): the thread-per-row chain with batched
+    // gathers (KIND 0) beats both the lanes-per-row reduction and the gather-to-shared variant at 15 and at 58
+    // nonzeros per row (tet mesh: 5.5 vs 4.3 / 2.1 TB/s); the others only pay when a tile holds few rows
+    const bool long_rows = A->mean_row > 96.0;
     int sel = (int)ctx->opt.spmv_kernel;
     if ((sel == 0 || sel == 3) && rb == 0 && nsk_packed_applicable(A)) {
         double *out = a.y;
@@ -489,6 +492,8 @@ int nsk_launch_spmv(nsk_csr_t A, const nsk_spmv_args &a)
         if (fast) { kind = 1; g = pick_group(A->mean_row); }
         else kind = 2;
     }
+    if (!fast && ctx->opt.stream_exact_kind == 1) kind = 0;  // experiment switch: thread-per-row chain from global
+    if (!fast && ctx->opt.stream_exact_kind == 2) kind = 2;  // ... or gather-to-shared first
     int smem = 0;
     stream_fn fn = lookup_kernel(variant, kind, g, muladd, &smem);
     NSK_REQUIRE(ctx, fn != nullptr, "no such stream kernel variant");

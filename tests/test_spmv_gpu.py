@@ -328,6 +328,21 @@ def test_mpk_pipeline_ragged_and_fallback(ctx, oracle_lib, reset_options):
     assert_bits_equal(dB.mpk(3, xb), oracle_lib.mpk(B.ptrow, B.indcol, B.coef, 3, xb))
 
 
+@pytest.mark.parametrize("strategy", [2, 3])
+def test_fused_csr_kernels_on_longer_rows(ctx, oracle_lib, strategy, reset_options):
+    """The CSR fused kernels accept operators up to 64 nonzeros per row (tet mesh 15/row, FEM-like 58/row): explicit
+    choices only (auto prefers k launches there), still bit-exact."""
+    ctx.set_option("mpk_kernel", strategy)
+    ctx.set_option("wave_l2_pct", 1000)
+    for A in (matgen.tet_p1_laplacian(9, permute_seed=2, rcm=True), matgen.fem_baij4(5)):
+        x = matgen.vec_uniform(A.n, seed=12)
+        dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
+        for k in (2, 4):
+            lv = dA.mpk(k, x)
+            assert ctx.query("last_mpk_strategy") == strategy
+            assert_bits_equal(lv, oracle_lib.mpk(A.ptrow, A.indcol, A.coef, k, x), f"strategy {strategy} k={k}")
+
+
 # ---- packed format: SpMV and matrix powers with x runs staged in shared memory ------------------------
 PACKED_OPS = [("laplace3d_7pt", (40,)), ("laplace2d_5pt", (300,)), ("laplace3d_7pt", (64, 64, 20)),
               ("laplace2d_5pt", (1000, 37)), ("laplace3d_7pt", (34, 10, 50))]

@@ -59,6 +59,8 @@ def main():
         A = matgen.laplace2d_5pt(4096)
     elif args.cfg == "fem":
         A = matgen.fem_baij4(40)
+    elif "x" in args.cfg:
+        A = matgen.laplace3d_7pt(*[int(v) for v in args.cfg.split("x")])
     else:
         A = matgen.laplace3d_7pt(int(args.cfg))
     print(f"# {args.cfg}: n={A.n} nnz={A.nnz} built in {time.time()-t0:.1f}s", flush=True)
@@ -156,6 +158,7 @@ def main():
                 ctx.set_option("pipe_w0_pct", w0)
                 for lead in [int(v) for v in args.pipe_leads.split(",")]:
                     ctx.set_option("wave_slack_pct", lead)
+                    ctx.set_option("wave_l2_pct", 400 if lead >= 0 else 0)
                     for l in lv:
                         ctx.lib.nsk_memset0(ctx.h, l.ptr, 8 * A.n)
                     l0 = ctx.launch_count
