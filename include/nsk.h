@@ -118,6 +118,23 @@ int nsk_memset0(nsk_ctx_t ctx, void *dptr, size_t bytes);
 /* GPU analogue of flush_cache (mpk/utils.cpp:146-154): overwrites a scratch buffer larger than L2. */
 int nsk_flush_l2(nsk_ctx_t ctx);
 
+/* ---- ingest: the step in front of the hot path (host only, no GPU) ------------------------------ */
+/* COO -> CSR with the semantics of COO2CSR / generate_CSR (reference mpk/utils.cpp:97-127, 5-43): columns
+ * ascending inside a row, a repeated (i,j) is dropped (first wins).  ptrow[nrow+1], indcol/coef sized nnz.
+ * Returns the number of entries kept, or a negative nsk_status. */
+int64_t nsk_coo2csr(int nrow, int64_t nnz, const int *irow, const int *jcol, const double *val, int *ptrow,
+                    int *indcol, double *coef);
+/* COO -> 4x4 block CSR with the semantics of generate_BCSR4 (reference mpk/utils.cpp:45-95): nrow/4 block rows,
+ * block columns in first-appearance order, row-major blocks with explicit zeros, a repeated (i,j) overwrites.
+ * Call with indcol == NULL to get the block count, then with ptrow[nrow/4+1], indcol[nblk], coef[16*nblk]. */
+int64_t nsk_coo2bcsr4(int nrow, int64_t nnz, const int *irow, const int *jcol, const double *val, int *ptrow,
+                      int *indcol, double *coef);
+/* Matrix Market coordinate reader with the quirks of the reference's drivers (mpk/SpM2V.cpp:815-852): banner
+ * line skipped, '%' lines skipped, "rows cols nnz", entries 1-based, values parsed as FLOAT then widened.
+ * Arrays are malloc'ed; release with nsk_mtx_free. */
+int nsk_mtx_read(const char *path, int *nrow, int64_t *nnz, int **irow, int **jcol, double **val);
+void nsk_mtx_free(int *irow, int *jcol, double *val);
+
 /* ---- CSR operator --------------------------------------------------------------------------- */
 /* Uploads a square CSR operator (0-based, int32 indices, fp64 values; columns need not be sorted --
  * the row-sequential modes accumulate in storage order whatever it is) and builds the launch plan.

@@ -41,6 +41,11 @@ SIGNATURES = {
     "nsk_memset0": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "nsk_flush_l2": (C.c_int, [C.c_void_p]),
     "nsk_ctx_query": (C.c_int, [C.c_void_p, C.c_char_p, c_int64_p]),
+    "nsk_coo2csr": (C.c_int64, [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nsk_coo2bcsr4": (C.c_int64, [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nsk_mtx_read": (C.c_int, [C.c_char_p, c_int_p, c_int64_p, C.POINTER(C.POINTER(C.c_int)), C.POINTER(C.POINTER(C.c_int)),
+                               C.POINTER(C.POINTER(C.c_double))]),
+    "nsk_mtx_free": (None, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "nsk_csr_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                  c_void_pp]),
     "nsk_csr_destroy": (C.c_int, [C.c_void_p]),

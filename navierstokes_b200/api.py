@@ -493,6 +493,66 @@ def SpM2V_BCSR_OPT(z, y, x, A: bcsr4x4_matrix, ptrowend1=None):
     g.spmv(y, _out(z, 4 * A.nrows), EXACT_FMA)
 
 
+# ---- ingest (host only): the reference's converters and its Matrix Market reader ------------------------------
+def COO2CSR(A: csrmatrix, nrow: int, irow, jcol, val):
+    """mpk/utils.cpp:97-127 (+ generate_CSR :5-43): fills A from 0-based COO; columns ascending per row, a repeated
+    (i,j) is dropped (first wins); A.nnz keeps the COO count like the reference (utils.cpp:100)."""
+    lib = _lib.load()
+    irow = np.ascontiguousarray(irow, dtype=np.int32)
+    jcol = np.ascontiguousarray(jcol, dtype=np.int32)
+    val = np.ascontiguousarray(val, dtype=np.float64)
+    nnz = len(irow)
+    ptrow = np.zeros(nrow + 1, dtype=np.int32)
+    indcol = np.zeros(max(nnz, 1), dtype=np.int32)
+    coef = np.zeros(max(nnz, 1), dtype=np.float64)
+    kept = lib.nsk_coo2csr(nrow, nnz, C.c_void_p(_ptr(irow)), C.c_void_p(_ptr(jcol)), C.c_void_p(_ptr(val)),
+                           C.c_void_p(_ptr(ptrow)), C.c_void_p(_ptr(indcol)), C.c_void_p(_ptr(coef)))
+    if kept < 0:
+        raise NskError(int(kept), "nsk_coo2csr: bad COO input")
+    A.n, A.nnz = nrow, nnz
+    A.ptrow, A.indcol, A.coef = ptrow, indcol[:kept].copy(), coef[:kept].copy()
+    return A
+
+
+def generate_BCSR4(nrow: int, irow, jcol, val) -> "bcsr4x4_matrix":
+    """mpk/utils.cpp:45-95: 4x4 block CSR from 0-based COO (nrow a multiple of 4): block columns in first-appearance
+    order, row-major blocks, explicit zeros, a repeated (i,j) overwrites.  nblocks is set to 0 like the reference
+    (utils.cpp:78); len(indcol) is the real count."""
+    lib = _lib.load()
+    irow = np.ascontiguousarray(irow, dtype=np.int32)
+    jcol = np.ascontiguousarray(jcol, dtype=np.int32)
+    val = np.ascontiguousarray(val, dtype=np.float64)
+    nnz = len(irow)
+    args = (nrow, nnz, C.c_void_p(_ptr(irow)), C.c_void_p(_ptr(jcol)), C.c_void_p(_ptr(val)))
+    nblk = lib.nsk_coo2bcsr4(*args, None, None, None)
+    if nblk < 0:
+        raise NskError(int(nblk), "nsk_coo2bcsr4: bad COO input")
+    ptrow = np.zeros(nrow // 4 + 1, dtype=np.int32)
+    indcol = np.zeros(max(nblk, 1), dtype=np.int32)
+    coef = np.zeros(16 * max(nblk, 1), dtype=np.float64)
+    lib.nsk_coo2bcsr4(*args, C.c_void_p(_ptr(ptrow)), C.c_void_p(_ptr(indcol)), C.c_void_p(_ptr(coef)))
+    return bcsr4x4_matrix(nrows=nrow // 4, nblocks=0, ptrow=ptrow, indcol=indcol[:nblk].copy(), coef=coef[:16 * nblk].copy())
+
+
+def read_mtx(path: str):
+    """The reader every reference driver inlines (mpk/SpM2V.cpp:815-852): returns (nrow, irow, jcol, val), 0-based,
+    values rounded through float32 exactly like fscanf("%f")."""
+    lib = _lib.load()
+    nrow, nnz = C.c_int(), C.c_int64()
+    pi, pj, pv = C.POINTER(C.c_int)(), C.POINTER(C.c_int)(), C.POINTER(C.c_double)()
+    st = lib.nsk_mtx_read(str(path).encode(), C.byref(nrow), C.byref(nnz), C.byref(pi), C.byref(pj), C.byref(pv))
+    if st != 0:
+        raise NskError(int(st), f"cannot read Matrix Market file {path}")
+    m = nnz.value
+    try:
+        irow = np.ctypeslib.as_array(pi, shape=(max(m, 1),))[:m].copy()
+        jcol = np.ctypeslib.as_array(pj, shape=(max(m, 1),))[:m].copy()
+        val = np.ctypeslib.as_array(pv, shape=(max(m, 1),))[:m].copy()
+    finally:
+        lib.nsk_mtx_free(pi, pj, pv)
+    return nrow.value, irow, jcol, val
+
+
 def Generate1stlayer(ptrowend1, A: csrmatrix):
     """The reference's first-touch schedule (mpk/SpM2V.cpp:5-26) is not needed by the GPU kernels; kept as a
     no-op so drivers written against the reference run unchanged (the plan lives in nsk_csr_create)."""

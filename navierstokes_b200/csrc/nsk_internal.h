@@ -48,6 +48,7 @@ struct nsk_options {
     int64_t mpk_kernel = 0;       // 0 auto (4 if the operator packs, else 1), 1 = k separate products, 2 = L2 wavefront,
                                   // 3 = level pipeline on CSR, 4 = level pipeline on the packed format
     int64_t pipe_variant = 0;     // 0 default, else 1 + index into the level-pipeline kernel table
+    int64_t pk_flags = 1;         // packed kernel switches (see PkParams::flags); default 1: evict-first / streaming hints
     int64_t pk_timing = 0;        // 1: packed kernel records its stage cycle and prints per-level averages (debug)
     int64_t pipe_w0_pct = 0;      // share weight of level 0's team relative to 100 for every other level; 0 = default
     int64_t pipe_bp_global = -1;  // back-pressure of the packed level pipeline: 0 = level l held by l+1, 1 = level 0 held

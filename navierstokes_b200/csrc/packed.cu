@@ -75,6 +75,8 @@ struct PkParams {
     int k;
     int team[NSK_MAX_K];   // CTAs of each level (level 0 streams from HBM and gets more stages in flight)
     const int2 *cta_role;  // [grid] {level, index within the level's team}
+    int flags;       // experiment switches: 1 = evict-first / streaming hints for data nobody re-reads, 2 = poll without
+                     // sleeping, 4 = publish with red.release.gpu instead of fence + relaxed red
     int bp_global;   // 1: only level 0 is held back, by level k-1 (one window for the whole pipeline); 0: level l by l+1
     // optional stage-cycle instrumentation (tools/pk_timing.py): 8 sums of nanoseconds + item count per CTA
     unsigned long long *timing;
@@ -102,7 +104,8 @@ __device__ __forceinline__ unsigned long long pk_now()
     return t;
 }
 
-__device__ __forceinline__ int pk_wait_groups(const int *cnt, const int *need, int ngroups, int w, int upto, int lane)
+__device__ __forceinline__ int pk_wait_groups(const int *cnt, const int *need, int ngroups, int w, int upto, int lane,
+                                              bool nosleep = false)
 {
     uint32_t spins = 0;
     while (w <= upto) {
@@ -114,8 +117,8 @@ __device__ __forceinline__ int pk_wait_groups(const int *cnt, const int *need, i
         w = min(w + adv, ngroups);
         if (w > upto || w >= ngroups) break;
         if (adv == 0) {
-            __nanosleep(32);
-            if (++spins > (1u << 24)) __trap();  // protocol bug: fail the launch, never hang
+            if (!nosleep) __nanosleep(32);
+            if (++spins > (1u << 26)) __trap();  // protocol bug: fail the launch, never hang
         }
     }
     return w;
@@ -167,6 +170,9 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
         if (n_my > 0) db = my[2 * (size_t)c + 1];
         if (n_my > 1) nb = my[2 * (size_t)(c + G) + 1];
         unsigned long long acc[5] = {0, 0, 0, 0, 0};
+        // the last level is the last reader of a blob: tell L2 so (the dead copy otherwise ages out of the window's way)
+        const bool last_reader = (P.flags & 1) && P.k > 1 && level == P.k - 1;
+        const uint64_t pol = policy_evict_first();
         for (; it_load < n_my; ++it_load) {
             const int s = it_load % STAGES;
             if (it_load >= STAGES) {
@@ -183,7 +189,8 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
             }
             const long long off = ((long long)(unsigned int)db.x) | ((long long)db.y << 32);
             mbar_arrive_expect_tx(&full[s], (uint32_t)db.z);
-            bulk_g2s(smem + (size_t)s * STAGE_BYTES, P.blobs + off, (uint32_t)db.z, &full[s]);
+            if (last_reader) bulk_g2s_hint(smem + (size_t)s * STAGE_BYTES, P.blobs + off, (uint32_t)db.z, &full[s], pol);
+            else bulk_g2s(smem + (size_t)s * STAGE_BYTES, P.blobs + off, (uint32_t)db.z, &full[s]);
             if (timing) ts[s * 4 + 0] = pk_now();
             db = nb;
             if (it_load + 2 < n_my) nb = my[2 * ((size_t)c + (size_t)(it_load + 2) * G) + 1];
@@ -226,11 +233,15 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
                 if (++spins > (1u << 26)) __trap();
             }
             const unsigned long long t5 = timing ? pk_now() : 0ull;
-            if (lane == 0) __threadfence();
+            const bool rel = (P.flags & 4) != 0;
+            if (lane == 0 && !rel) __threadfence();
             __syncwarp();
             for (int u = 0; u < n; u++) {
                 const int pos = __shfl_sync(0xffffffffu, pos_cur, (it + u) & 31);
-                if (lane == 0) red_relaxed_gpu_add(cnt + pos / WF_GROUP, 1);
+                if (lane == 0) {
+                    if (rel && u == 0) red_release_gpu_add(cnt + pos / WF_GROUP, 1);
+                    else red_relaxed_gpu_add(cnt + pos / WF_GROUP, 1);
+                }
             }
             if (timing) tf += pk_now() - t5;
             it += n;
@@ -290,8 +301,8 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
             // inputs first: the poll (an L2 round trip whenever the watermark has to move) overlaps the consumers'
             // work on the item that still occupies this stage
             const unsigned long long t0 = timing ? pk_now() : 0ull;
-            if (back && gback >= wb) wb = pk_wait_groups(cnt_b, need_b, P.ngroups, wb, gback, lane);
-            if (fwd && ghi >= wf) wf = pk_wait_groups(cnt_f, need_f, P.ngroups, wf, ghi, lane);
+            if (back && gback >= wb) wb = pk_wait_groups(cnt_b, need_b, P.ngroups, wb, gback, lane, (P.flags & 2) != 0);
+            if (fwd && ghi >= wf) wf = pk_wait_groups(cnt_f, need_f, P.ngroups, wf, ghi, lane, (P.flags & 2) != 0);
             const unsigned long long t1 = timing ? pk_now() : 0ull;
             if (it >= STAGES) mbar_wait(&done[s], ((it / STAGES) - 1) & 1);  // the stage's x buffer is free
             if (timing) { w_dep += t1 - t0; w_done += pk_now() - t1; }
@@ -321,6 +332,7 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
     constexpr int NCT = NCW * 32;
     double *dst = P.levels[level];
     const int row_end = P.level_rows[level];
+    const bool stream_out = (P.flags & 1) && level == P.k - 1;  // nobody in this launch re-reads the last level
     double dot_acc = 0.0;
     for (int it = 0; it < n_my; ++it) {
         const int s = it % STAGES;
@@ -363,7 +375,8 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
             for (int q = 0; q < RPT; q++) {
                 const int r = rb + q * NCT + tid;
                 if (len[q] >= 0) {
-                    dst[row0 + r] = acc[q];
+                    if (stream_out) __stcs(dst + row0 + r, acc[q]);
+                    else dst[row0 + r] = acc[q];
                     if (P.dot_w) dot_acc = __fma_rn(P.dot_w[row0 + r], acc[q], dot_acc);
                 }
             }
@@ -451,9 +464,9 @@ static pk_fn pk_lookup(int variant, bool muladd, int *smem)
 static int pk_variant(nsk_ctx_t ctx)
 {
     // option value 0 = default; n >= 1 selects table entry n - 1.  Default: 256-row tiles, 2 stages, 4 consumer warps
-    // with two rows per thread, 3 CTAs per SM (profiles/r01_sweep_packed_c3.txt)
+    // (one row per thread and pass), 3 CTAs per SM (profiles/r01_sweep_packed_c3.txt)
     int v = (int)ctx->opt.packed_variant - 1;
-    if (v < 0 || v >= g_npkv) v = 6;
+    if (v < 0 || v >= g_npkv) v = 7;
     return v;
 }
 
@@ -738,9 +751,9 @@ static PkLevelPlan *pk_level_plan(nsk_csr_t A, PackedOp *op, int k, const int *l
         // data plus the level vectors over it; by default the slack is whatever the L2 budget allows -- measured
         // on 256^3: time falls with the window until it reaches ~100 MB, then HBM re-reads set in.
         const double tile_bytes = (double)op->blob_bytes / ntiles + 8.0 * op->t_rows * (k + 1);
-        // budget: 65 % of L2 by default -- ncu (profiles/r01_ncu_packed_dram_traffic.txt): an 81 MB window costs the
+        // budget: 70 % of L2 by default -- ncu (profiles/r01_ncu_packed_dram_traffic.txt): an 81 MB window costs the
         // compulsory 1.47 GB of HBM reads, a 101 MB one 4.9 GB (the level vectors and x runs share the cache)
-        const double budget = (ctx->opt.wave_l2_pct > 0 ? (double)ctx->opt.wave_l2_pct : 65.0) / 100.0 *
+        const double budget = (ctx->opt.wave_l2_pct > 0 ? (double)ctx->opt.wave_l2_pct : 70.0) / 100.0 *
                               (double)ctx->prop.l2CacheSize;
         const int lead_min = D.reach + 1 + WF_GROUP;
         if (lead_pct >= 0)
@@ -863,6 +876,7 @@ int nsk_packed_run(nsk_csr_t A, int k, const double *d_x, double *const *d_level
     for (int l = 0; l < NSK_MAX_K; l++) P.team[l] = l < k ? plan->teams[l] : 0;
     P.cta_role = plan->d_roles;
     P.bp_global = plan->bp_global;
+    P.flags = (int)ctx->opt.pk_flags;
     P.timing = nullptr;
     if (ctx->opt.pk_timing) {
         void *tb = nullptr;
