@@ -2,7 +2,7 @@
 //
 // The reference has no CG at all (its only "s-step" code is a monomial-basis builder,
 // src/kernels/spmm_avx2.c:112-168, and a solver stub, src/sstepgmres.c:126-149), so parity is against the
-// restatement in oracle/ (oracle.scg, numpy) -- "parity unpinned" as far as the reference is concerned.
+// restatement kept with the tests (oracle.scg, numpy) -- "parity unpinned" as far as the reference is concerned.
 //
 // Formulation (Carson/Demmel CA-CG, monomial basis).  One OUTER step advances s CG iterations:
 //   1. V = [p, A p, ..., A^s p | r, A r, ..., A^(s-1) r]          two matrix-powers calls (depth s and s-1):
