@@ -508,3 +508,61 @@ def test_bcsr4_fem_operator_matches_oracle_and_csr(ctx, oracle_lib):
     assert_bits_equal(dB.spmv(dx).to_host(), y)
     y_csr = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef).spmv(x)
     assert oracle_lib.rel_error(y_csr, y) <= 1e-13
+
+
+# ---- BASELINE.json full sizes: size-independent properties (the CPU oracle would need minutes here; bench.py
+# ---- additionally compares the 256^3 k=4 run bit for bit with the compiled reference on every round) -------------
+@pytest.mark.parametrize("cfg", ["c2_2d_4096", "c3_3d_256"])
+def test_full_size_properties(ctx, cfg, reset_options):
+    A = matgen.laplace2d_5pt(4096) if cfg == "c2_2d_4096" else matgen.laplace3d_7pt(256)
+    n = A.n
+    dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
+    assert dA.packed_bytes > 0
+    x = matgen.vec_uniform(n, seed=31)
+    w = matgen.vec_sin(n)
+    dx, dw = ctx.to_device(x), ctx.to_device(w)
+    # 1. every kernel family produces the same bits (thread-per-row from global = the simplest possible restatement)
+    outs = {}
+    for kern in (1, 2, 3):
+        ctx.set_option("spmv_kernel", kern)
+        y = ctx.empty(n)
+        dA.spmv(dx, y)
+        assert ctx.query("last_spmv_kernel") == kern
+        outs[kern] = y.to_host()
+    ctx.set_option("spmv_kernel", 0)
+    assert_bits_equal(outs[2], outs[1], "stream vs scalar")
+    assert_bits_equal(outs[3], outs[1], "packed vs scalar")
+    # 2. a sample of rows against the definition, evaluated with the same fma chain on the host
+    rows = np.random.default_rng(5).integers(0, n, 2000)
+    for r in rows:  # numpy has no fma: a few ulp of the row's magnitude instead of bits
+        ref = float(np.dot(A.coef[A.ptrow[r]:A.ptrow[r + 1]], x[A.indcol[A.ptrow[r]:A.ptrow[r + 1]]]))
+        assert abs(outs[1][r] - ref) <= 1e-14 * max(1.0, abs(ref)) * 8
+    # 3. constant vector: interior rows of the Laplacian sum to zero exactly, boundary rows to small integers
+    ones = dA.spmv(ctx.to_device(np.ones(n))).to_host()
+    assert np.array_equal(ones, np.add.reduceat(A.coef, A.ptrow[:-1]))
+    # 4. fused powers == k launches == repeated products, bit for bit, all four levels
+    k = 4
+    fused = [ctx.empty(n) for _ in range(k)]
+    ctx.set_option("mpk_kernel", 0)
+    dA.mpk(k, dx, fused)
+    assert ctx.query("last_mpk_strategy") == 4
+    ctx.set_option("mpk_kernel", 1)
+    ctx.set_option("spmv_kernel", 2)
+    lev = [ctx.empty(n) for _ in range(k)]
+    dA.mpk(k, dx, lev)
+    for l in range(k):
+        assert_bits_equal(fused[l].to_host(), lev[l].to_host(), f"level {l}")
+    ctx.set_option("mpk_kernel", 0)
+    ctx.set_option("spmv_kernel", 0)
+    # 5. linearity of the fused kernel: A^4 (2x - 3w) == 2 A^4 x - 3 A^4 w to rounding
+    comb = ctx.to_device(2.0 * x - 3.0 * w)
+    lc = [ctx.empty(n) for _ in range(k)]
+    lw = [ctx.empty(n) for _ in range(k)]
+    dA.mpk(k, comb, lc)
+    dA.mpk(k, dw, lw)
+    lhs = lc[k - 1].to_host()
+    rhs = 2.0 * fused[k - 1].to_host() - 3.0 * lw[k - 1].to_host()
+    assert nsk.rel_error(rhs, lhs) <= 1e-13
+    # 6. symmetry: <A x, w> == <x, A w>
+    yx, yw = outs[1], dA.spmv(dw).to_host()
+    assert abs(np.dot(yx, w) - np.dot(x, yw)) <= 1e-9 * abs(np.dot(yx, w))
