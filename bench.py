@@ -216,7 +216,8 @@ def main():
         import torch
         import torch.distributed as td
         torch.cuda.set_device(local_rank)
-        td.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        td.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=90))
         dist = td
 
     ctx = nsk.Context(local_rank)
@@ -276,16 +277,15 @@ def main():
     e1.record()
     ms_total = e0.elapsed_ms(e1)
     launches = ctx.launch_count - launches0
-    # the timed region lasts a few milliseconds, nvidia-smi samples every 200 ms: keep the SAME load running
-    # (untimed) until the sampler has seen it at least twice
-    t_end = time.time() + 1.5
-    while len(sampler.lines) < 3 and time.time() < t_end:
-        for _ in range(20):
-            step_dev()
-        ctx.sync()
+    ms_step = max_over_ranks(ms_total / args.steps)
+    # The timed region lasts a few milliseconds, nvidia-smi samples every 200 ms: keep the SAME load running (untimed)
+    # for ~0.7 s so the sampler sees it.  The count is derived from the all-reduced step time, so every rank runs the
+    # same number of extra steps (a distributed step contains a neighbour exchange: unmatched calls would deadlock).
+    extra = int(min(3000, max(20, 700.0 / max(ms_step, 1e-3))))
+    for _ in range(extra):
+        step_dev()
     barrier()
     clocks = sampler.stop()
-    ms_step = max_over_ranks(ms_total / args.steps)
     equiv_total = K_POWERS * spmv_bytes * world
     value = equiv_total / ms_step / 1e6
 
