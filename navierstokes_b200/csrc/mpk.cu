@@ -52,8 +52,36 @@ int nsk_mpk_local(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
     const bool automatic = sel == 0;
     if (automatic) sel = 4;
     if (sel == 4 && k > 1 && nsk_packed_applicable(A)) {
-        int s = nsk_packed_run(A, k, d_x, d_levels, mode, level_rows, nullptr, -1);
-        if (s != NSK_ERR_UNSUPPORTED) { ctx->last_mpk = 4; return s; }
+        // Fuse as many levels per launch as the L2 window allows: a pattern whose reach is large (512^2-row planes)
+        // may fit two levels but not four -- then A^4 x runs as two fused pairs instead of four products.
+        int done = 0;
+        const double *src = d_x;
+        bool any_fused = false;
+        while (done < k) {
+            const int left = k - done;
+            int took = 0;
+            for (int kk = left; kk >= 2 && !took; kk--) {
+                int s = nsk_packed_run(A, kk, src, d_levels + done, mode, level_rows ? level_rows + done : nullptr, nullptr, -1);
+                if (s == NSK_OK) took = kk;
+                else if (s != NSK_ERR_UNSUPPORTED) return s;
+            }
+            if (!took) {  // a single level (or nothing fits): one product
+                nsk_spmv_args a;
+                a.x = src;
+                a.y = d_levels[done];
+                a.row_begin = 0;
+                a.row_end = level_rows ? level_rows[done] : A->n;
+                a.mode = mode;
+                NSK_TRY(nsk_launch_spmv(A, a));
+                took = 1;
+            } else {
+                any_fused = true;
+            }
+            src = d_levels[done + took - 1];
+            done += took;
+        }
+        ctx->last_mpk = any_fused ? 4 : 1;
+        return NSK_OK;
     }
     // the CSR level pipeline (3) and the wavefront kernel (2) stay explicit choices: with global gathers they lose to k
     // launches of the streaming kernel wherever they were measured (256^3: 0.86 / 0.90 vs 0.98 ms before the packed

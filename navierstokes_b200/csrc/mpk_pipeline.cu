@@ -233,7 +233,7 @@ __global__ void __launch_bounds__((NCW + 2) * 32, MINB) mpk_pipeline_kernel(cons
 // host side: plan (cached per operator / k / level_rows / geometry) and launch
 // -----------------------------------------------------------------------------------------------
 struct PipePlan {
-    int k = 0, t_nnz = 0, t_rows = 0, team = 0, lead_pct = 0;
+    int k = 0, t_nnz = 0, t_rows = 0, team = 0, lead_pct = 0, l2_pct = 0;
     bool rejected = false;
     std::vector<int> level_rows;
     int ngroups = 0, reach = 0, lead = 0;
@@ -329,7 +329,7 @@ static PipePlan *pipe_plan(nsk_csr_t A, int k, const int *level_rows, const Pipe
     const int lead_pct = ctx->opt.wave_slack_pct >= 0 ? (int)ctx->opt.wave_slack_pct : 100;
     for (PipePlan &p : plans)
         if (p.k == k && p.t_nnz == V.t_nnz && p.t_rows == V.t_rows && p.team == team && p.level_rows == lr &&
-            p.lead_pct == lead_pct) {
+            p.lead_pct == lead_pct && p.l2_pct == (int)ctx->opt.wave_l2_pct) {
             if (p.rejected) { *why = "wavefront window exceeds the L2 budget"; return nullptr; }
             return &p;
         }
@@ -345,6 +345,7 @@ static PipePlan *pipe_plan(nsk_csr_t A, int k, const int *level_rows, const Pipe
 
     PipePlan p;
     p.k = k; p.t_nnz = V.t_nnz; p.t_rows = V.t_rows; p.team = team; p.lead_pct = lead_pct; p.level_rows = lr;
+    p.l2_pct = (int)ctx->opt.wave_l2_pct;
     p.ngroups = ngroups; p.reach = D.reach; p.lead = lead;
     // The window that must stay in L2: (k-1)*lead tiles of matrix data plus the level vectors over it.
     const double tile_bytes = (12.0 * (double)A->nnz + 8.0 * (double)A->n * (k + 1)) / (double)ntiles;  // mean tile

@@ -309,6 +309,7 @@ struct WavePlan {
     int t_nnz = 0, t_rows = 0;
     int slack = 0;
     int grid_req = 0;  // resident CTAs the plan was asked for (cache key)
+    int l2_pct = 0;    // L2 budget option the plan was built / refused under (cache key)
     int grid = 0;      // CTAs it uses: min(grid_req, items)
     int per_cta = 0;
     bool rejected = false;
@@ -490,7 +491,8 @@ static WavePlan *get_plan(nsk_csr_t A, int k, const int *level_rows, const WaveV
     std::vector<int> lr(k);
     for (int l = 0; l < k; l++) lr[l] = level_rows ? level_rows[l] : A->n;
     for (WavePlan &p : S.plans)
-        if (p.k == k && p.t_nnz == V.t_nnz && p.t_rows == V.t_rows && p.slack == slack && p.grid_req == grid && p.level_rows == lr) {
+        if (p.k == k && p.t_nnz == V.t_nnz && p.t_rows == V.t_rows && p.slack == slack && p.grid_req == grid && p.level_rows == lr &&
+            p.l2_pct == (int)A->ctx->opt.wave_l2_pct) {
             if (p.rejected) { *why = "wavefront window exceeds the L2 budget"; return nullptr; }
             return &p;
         }
@@ -512,6 +514,7 @@ static WavePlan *get_plan(nsk_csr_t A, int k, const int *level_rows, const WaveV
         *why = "wavefront window exceeds the L2 budget";
         WavePlan rej;  // remember the refusal: planning costs O(tiles) host work
         rej.k = k; rej.t_nnz = V.t_nnz; rej.t_rows = V.t_rows; rej.level_rows = lr; rej.slack = slack; rej.grid_req = grid; rej.rejected = true;
+        rej.l2_pct = (int)A->ctx->opt.wave_l2_pct;
         S.plans.push_back(rej);
         return nullptr;
     }
@@ -548,6 +551,7 @@ static WavePlan *get_plan(nsk_csr_t A, int k, const int *level_rows, const WaveV
 
     WavePlan p;
     p.k = k; p.t_nnz = V.t_nnz; p.t_rows = V.t_rows; p.level_rows = lr; p.slack = slack; p.grid_req = grid; p.grid = G; p.per_cta = per_cta;
+    p.l2_pct = (int)A->ctx->opt.wave_l2_pct;
     p.ntasks = ntasks; p.ngroups = ngroups; p.D = D;
     if (cudaMalloc(&p.d_tasks, sizeof(WaveTask) * sched.size()) != cudaSuccess ||
         cudaMalloc(&p.d_tasks_dyn, sizeof(WaveTask) * (tasks.size() + 1)) != cudaSuccess ||

@@ -474,7 +474,7 @@ static int pk_variant(nsk_ctx_t ctx)
 // host side: packing (cached per operator and tile geometry), level plans, launches
 // -----------------------------------------------------------------------------------------------
 struct PkLevelPlan {
-    int k = 0, team = 0, lead_pct = 0, bp_global = 0, w0_pct = 0, interleave = 0;
+    int k = 0, team = 0, lead_pct = 0, bp_global = 0, w0_pct = 0, interleave = 0, l2_pct = 0;
     bool rejected = false;
     std::vector<int> teams;     // CTAs per level, sum <= team * k
     int grid = 0;
@@ -714,16 +714,17 @@ static PkLevelPlan *pk_level_plan(nsk_csr_t A, PackedOp *op, int k, const int *l
     const int bp_global = ctx->opt.pipe_bp_global >= 0 ? (ctx->opt.pipe_bp_global ? 1 : 0) : 1;
     const int w0_pct = k > 1 ? (ctx->opt.pipe_w0_pct > 0 ? (int)ctx->opt.pipe_w0_pct : 100) : 100;
     const int interleave = ctx->opt.pipe_interleave ? 1 : 0;
+    const int l2_pct = (int)ctx->opt.wave_l2_pct;  // part of the key: it sizes the window and decides refusals
     for (PkLevelPlan &p : op->plans)
         if (p.k == k && p.team == resident && p.level_rows == lr && p.lead_pct == lead_pct && p.bp_global == bp_global &&
-            p.w0_pct == w0_pct && p.interleave == interleave) {
+            p.w0_pct == w0_pct && p.interleave == interleave && p.l2_pct == l2_pct) {
             if (p.rejected) { *why = "wavefront window exceeds the L2 budget"; return nullptr; }
             return &p;
         }
     const int ntiles = op->ntiles;
     PkLevelPlan p;
     p.k = k; p.team = resident; p.lead_pct = lead_pct; p.level_rows = lr; p.bp_global = bp_global;
-    p.w0_pct = w0_pct; p.interleave = interleave;
+    p.w0_pct = w0_pct; p.interleave = interleave; p.l2_pct = l2_pct;
     // teams: `team * k` resident CTAs shared out with weight w0 for level 0 (it streams from HBM: longer fills, so
     // it needs more stages in flight for the same rate) and 100 for every other level
     {

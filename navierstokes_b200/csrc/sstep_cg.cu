@@ -134,10 +134,13 @@ int nsk_scg_device(nsk_csr_t A, const double *d_b, double *d_x, double tol, int 
 
     // workspace: p, r (local vectors), s levels of p, s-1 levels of r
     unsigned char *ws = nullptr;
-    if (cudaMalloc(&ws, vec_bytes * (size_t)(2 * s + 1)) != cudaSuccess) {
-        cudaGetLastError();
-        nsk_set_error(ctx, "s-step CG workspace (%d vectors of %zu bytes) does not fit", 2 * s + 1, vec_bytes);
-        return NSK_ERR_ALLOC;
+    {
+        void *vws = nullptr;  // grow-only staging slot of the context: repeated solves do not re-allocate 1.2 GB
+        if (nsk_stage(ctx, 6, vec_bytes * (size_t)(2 * s + 1), &vws) != NSK_OK) {
+            nsk_set_error(ctx, "s-step CG workspace (%d vectors of %zu bytes) does not fit", 2 * s + 1, vec_bytes);
+            return NSK_ERR_ALLOC;
+        }
+        ws = reinterpret_cast<unsigned char *>(vws);
     }
     auto vec = [&](int i) { return reinterpret_cast<double *>(ws + vec_bytes * (size_t)i); };
     double *p = vec(0), *r = vec(1);
@@ -145,7 +148,7 @@ int nsk_scg_device(nsk_csr_t A, const double *d_b, double *d_x, double tol, int 
     for (int l = 0; l < s; l++) lvP[l] = vec(2 + l);
     for (int l = 0; l + 1 < s; l++) lvR[l] = vec(2 + s + l);
     int status = NSK_OK;
-    auto fail = [&](int st) { cudaStreamSynchronize(ctx->stream); cudaFree(ws); return st; };
+    auto fail = [&](int st) { cudaStreamSynchronize(ctx->stream); return st; };
 #define SCG_TRY(call) do { status = (call); if (status != NSK_OK) return fail(status); } while (0)
 #define SCG_CUDA(call) do { if ((call) != cudaSuccess) { nsk_set_error(ctx, "%s failed: %s", #call, cudaGetErrorString(cudaGetLastError())); return fail(NSK_ERR_CUDA); } } while (0)
 
@@ -206,7 +209,6 @@ int nsk_scg_device(nsk_csr_t A, const double *d_b, double *d_x, double tol, int 
     if (iters) *iters = done_iters;
     if (relres) *relres = sqrt((rr < 0.0 ? 0.0 : rr) / bb);
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(ws);
     if (broke && !converged) {
         nsk_set_error(ctx, "s-step CG: basis breakdown (non-positive curvature in the Gram recurrence) after %d iterations",
                       done_iters);

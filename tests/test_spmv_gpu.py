@@ -566,3 +566,23 @@ def test_full_size_properties(ctx, cfg, reset_options):
     # 6. symmetry: <A x, w> == <x, A w>
     yx, yw = outs[1], dA.spmv(dw).to_host()
     assert abs(np.dot(yx, w) - np.dot(x, yw)) <= 1e-9 * abs(np.dot(yx, w))
+
+
+def test_packed_mpk_splits_when_the_window_does_not_fit(ctx, oracle_lib, reset_options):
+    """With an L2 budget too small for k levels the powers call fuses as many levels per launch as fit (here pairs or
+    single products) instead of giving up on fusion altogether; same bits."""
+    A = matgen.laplace3d_7pt(64, 64, 48)
+    x = matgen.vec_uniform(A.n, seed=14)
+    dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
+    ref = oracle_lib.mpk(A.ptrow, A.indcol, A.coef, 5, x)
+    dx = ctx.to_device(x)
+    seen = set()
+    for pct in (1, 2, 3, 5, 100):
+        ctx.set_option("wave_l2_pct", pct)
+        lv = [ctx.empty(A.n) for _ in range(5)]
+        before = ctx.launch_count
+        dA.mpk(5, dx, lv)
+        seen.add(ctx.launch_count - before)
+        for l in range(5):
+            assert_bits_equal(lv[l].to_host(), ref[l], f"budget {pct}% level {l}")
+    assert 1 in seen and len(seen) >= 2, seen  # the generous budget fuses everything; a tight one needs more launches
