@@ -25,7 +25,9 @@ int nsk_scg_device(nsk_csr_t A, const double *d_b, double *d_x, double tol, int 
                    double *relres);  // sstep_cg.cu
 
 // scalar slots used by CG (ctx->d_scalars)
-enum { S_RR0 = 16, S_RR1 = 17, S_PQ = 18, S_BB = 19, S_CONV = 20 /* latched iteration, 0 = running */ };
+enum { S_RR0 = 16, S_RR1 = 17, S_PQ = 18, S_BB = 19, S_CONV = 20 /* latched iteration, 0 = running */,
+       S_RRFIN = 21 /* <r,r> at the latched iteration: with a communicator the frozen iterations that follow in the same
+                       batch still all-reduce the rr slots (a collective cannot be made conditional), which scales them */ };
 
 constexpr int CG_THREADS = 256;
 
@@ -139,7 +141,10 @@ __global__ void __launch_bounds__(CG_THREADS) cg_update_p_kernel(int64_t n, cons
 
 __global__ void cg_latch_kernel(double *scal, int rr_out, double tol2, double iter_no)
 {
-    if (scal[S_CONV] == 0.0 && scal[rr_out] <= tol2 * scal[S_BB]) scal[S_CONV] = iter_no;
+    if (scal[S_CONV] == 0.0 && scal[rr_out] <= tol2 * scal[S_BB]) {
+        scal[S_CONV] = iter_no;
+        scal[S_RRFIN] = scal[rr_out];
+    }
 }
 
 static int cg_grid(nsk_ctx_t ctx, int64_t n)
@@ -169,13 +174,13 @@ static int cg_device(nsk_csr_t A, const double *d_b, double *d_x, double tol, in
     NSK_CUDA(ctx, cudaMemcpyAsync(r, d_b, nb, cudaMemcpyDeviceToDevice, ctx->stream));
     NSK_CUDA(ctx, cudaMemsetAsync(p, 0, sizeof(double) * (size_t)A->n_cols, ctx->stream));
     NSK_CUDA(ctx, cudaMemcpyAsync(p, d_b, nb, cudaMemcpyDeviceToDevice, ctx->stream));
-    NSK_CUDA(ctx, cudaMemsetAsync(scal + S_RR0, 0, sizeof(double) * 5, ctx->stream));
+    NSK_CUDA(ctx, cudaMemsetAsync(scal + S_RR0, 0, sizeof(double) * 6, ctx->stream));
     NSK_TRY(nsk_launch_dot(ctx, n, d_b, d_b, S_BB));
     NSK_TRY(nsk_comm_allreduce_slots(ctx, S_BB, 1));
     NSK_CUDA(ctx, cudaMemcpyAsync(scal + S_RR0, scal + S_BB, sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
 
-    double h[5];
-    NSK_TRY(nsk_read_scalars(ctx, S_RR0, 5, h));
+    double h[6];
+    NSK_TRY(nsk_read_scalars(ctx, S_RR0, 6, h));
     const double bb = h[S_BB - S_RR0];
     if (bb == 0.0) {
         if (iters) *iters = 0;
@@ -212,12 +217,12 @@ static int cg_device(nsk_csr_t A, const double *d_b, double *d_x, double tol, in
             ctx->launches += 2;
         }
         NSK_CUDA(ctx, cudaGetLastError());
-        NSK_TRY(nsk_read_scalars(ctx, S_RR0, 5, h));
+        NSK_TRY(nsk_read_scalars(ctx, S_RR0, 6, h));
         conv_iter = (int)h[S_CONV - S_RR0];
     }
     const int done = conv_iter ? conv_iter : it;
     // rr after `done` iterations sits in slot parity done&1
-    const double rr = h[done & 1];
+    const double rr = conv_iter ? h[S_RRFIN - S_RR0] : h[done & 1];
     if (iters) *iters = done;
     if (relres) *relres = sqrt(rr / bb);
     return conv_iter ? NSK_OK : (sqrt(rr / bb) <= tol ? NSK_OK : NSK_ERR_NOT_CONVERGED);
