@@ -438,7 +438,11 @@ struct PkVariant {
     X(6, 256, 21504, 1536, 2, 4, 3, 2)  \
     X(7, 256, 21504, 1536, 2, 4, 3, 1)  \
     X(8, 256, 21504, 1536, 3, 4, 2, 2)  \
-    X(9, 256, 21504, 1536, 6, 4, 1, 2)
+    X(9, 256, 21504, 1536, 6, 4, 1, 2)  \
+    X(10, 128, 86016, 2048, 2, 4, 1, 1) \
+    X(11, 64, 43008, 1536, 4, 2, 1, 1)  \
+    X(12, 64, 43008, 1536, 2, 2, 2, 1)  \
+    X(13, 128, 86016, 2048, 2, 8, 1, 1)
 
 static const PkVariant g_pkv[] = {
 #define X(id, r, b, x, s, w, m, u) {r, b, x, s, w, m, u},
@@ -461,12 +465,15 @@ static pk_fn pk_lookup(int variant, bool muladd, int *smem)
     return nullptr;
 }
 
-static int pk_variant(nsk_ctx_t ctx)
+static int pk_variant(nsk_csr_t A)
 {
-    // option value 0 = default; n >= 1 selects table entry n - 1.  Default: 256-row tiles, 2 stages, 4 consumer warps
-    // (one row per thread and pass), 3 CTAs per SM (profiles/r01_sweep_packed_c3.txt)
+    // option value 0 = default; n >= 1 selects table entry n - 1.  Default for short rows: 256-row tiles, 2 stages,
+    // 4 consumer warps (one row per thread and pass), 3 CTAs per SM (profiles/r01_sweep_packed_c3.txt).  Rows longer
+    // than ~16 nonzeros (FEM operators, 4 dof per node: 58 per row) would fit only ~32 rows in such a stage; they get
+    // stages of 84 KB (128 rows x 64 slots) so that a tile keeps enough rows per bulk copy and per consumer pass.
+    nsk_ctx_t ctx = A->ctx;
     int v = (int)ctx->opt.packed_variant - 1;
-    if (v < 0 || v >= g_npkv) v = 7;
+    if (v < 0 || v >= g_npkv) v = A->mean_row > 16.0 ? 10 : 7;
     return v;
 }
 
@@ -840,7 +847,7 @@ int nsk_packed_run(nsk_csr_t A, int k, const double *d_x, double *const *d_level
                    const double *dot_w, int dot_slot)
 {
     nsk_ctx_t ctx = A->ctx;
-    const int variant = pk_variant(ctx);
+    const int variant = pk_variant(A);
     const PkVariant &V = g_pkv[variant];
     if (!pk_aligned(d_x)) { nsk_set_error(ctx, "packed path: x is not 16-byte aligned"); return NSK_ERR_UNSUPPORTED; }
     for (int l = 0; l < k; l++)
@@ -917,12 +924,12 @@ int nsk_packed_run(nsk_csr_t A, int k, const double *d_x, double *const *d_level
 bool nsk_packed_applicable(nsk_csr_t A)
 {
     if (A->n == 0 || A->nnz == 0) return false;
-    return pk_get(A, g_pkv[pk_variant(A->ctx)])->ok;
+    return pk_get(A, g_pkv[pk_variant(A)])->ok;
 }
 
 // bytes of the packed operator (for traffic accounting in the bench); 0 when not packed
 size_t nsk_packed_bytes(nsk_csr_t A)
 {
-    PackedOp *op = pk_get(A, g_pkv[pk_variant(A->ctx)]);
+    PackedOp *op = pk_get(A, g_pkv[pk_variant(A)]);
     return op->ok ? op->blob_bytes : 0;
 }

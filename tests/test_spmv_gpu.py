@@ -16,7 +16,7 @@ def all_kernel_configs(ctx):
     yield 1, 0
     for v in range(1, 9):
         yield 2, v
-    for v in range(1, 11):
+    for v in range(1, 15):
         yield 3, v  # packed format (applies to operators whose tiles read x in a few runs; else the CSR kernels run)
 
 
@@ -348,7 +348,7 @@ PACKED_OPS = [("laplace3d_7pt", (40,)), ("laplace2d_5pt", (300,)), ("laplace3d_7
               ("laplace2d_5pt", (1000, 37)), ("laplace3d_7pt", (34, 10, 50))]
 
 
-@pytest.mark.parametrize("variant", list(range(1, 11)))
+@pytest.mark.parametrize("variant", list(range(1, 15)))
 @pytest.mark.parametrize("gen,args", PACKED_OPS)
 def test_packed_spmv_and_mpk_bitwise(ctx, oracle_lib, gen, args, variant, reset_options):
     A = getattr(matgen, gen)(*args)
@@ -386,6 +386,25 @@ def test_packed_mpk_lead_and_placement(ctx, oracle_lib, interleave, bp, w0, lead
         lv = dA.mpk(k, x)
         assert ctx.launch_count - before == 1
         assert_bits_equal(lv, oracle_lib.mpk(A.ptrow, A.indcol, A.coef, k, x), f"k={k}")
+
+
+def test_packed_long_rows_fem_operator(ctx, oracle_lib, reset_options):
+    """FEM-like BAIJ-4 operator (58 nonzeros per row): packs with the long-row stage geometry chosen automatically;
+    SpMV and fused powers bit-exact in both exact flavours."""
+    A = matgen.fem_baij4(7)
+    x = matgen.vec_uniform(A.n, seed=13)
+    dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
+    assert dA.packed_bytes > 0
+    assert_bits_equal(dA.spmv(x), oracle_lib.spmv(A.ptrow, A.indcol, A.coef, x))
+    assert ctx.query("last_spmv_kernel") == 3
+    assert_bits_equal(dA.spmv(x, mode=nsk.EXACT_MULADD), oracle_lib.spmv_muladd(A.ptrow, A.indcol, A.coef, x))
+    for k in (2, 3):
+        assert_bits_equal(dA.mpk(k, x), oracle_lib.mpk(A.ptrow, A.indcol, A.coef, k, x), f"k={k}")
+        assert ctx.query("last_mpk_strategy") == 4
+    for variant in (11, 12, 13, 14, 8):
+        ctx.set_option("packed_variant", variant)
+        assert_bits_equal(dA.spmv(x), oracle_lib.spmv(A.ptrow, A.indcol, A.coef, x), f"variant {variant}")
+        assert_bits_equal(dA.mpk(2, x), oracle_lib.mpk(A.ptrow, A.indcol, A.coef, 2, x), f"variant {variant} k=2")
 
 
 def test_packed_repeated_calls_are_stable(ctx, reset_options):
