@@ -19,6 +19,7 @@ struct DistPeer {
     int rank = 0;
     int *d_send_idx = nullptr;          // local indices to pack, ring-major
     double *d_sendbuf = nullptr;
+    double *d_recvbuf = nullptr;        // one contiguous message per peer lands here, then unpack_kernel scatters it
     std::vector<int> send_ring_count;   // depth
     std::vector<int> recv_ring_count;   // depth
     std::vector<int> recv_ring_start;   // depth, offset into the local vector
@@ -37,12 +38,35 @@ __global__ void __launch_bounds__(256) pack_kernel(const double *__restrict__ x,
     if (i < count) out[i] = x[idx[i]];
 }
 
+// All peers in ONE launch each way (a per-ring message costs ~9 us of NCCL latency, a launch ~3 us: measured 46 us
+// per depth-4 exchange with one neighbour when every ring travelled alone, tools/dist_probe.py).
+constexpr int HALO_MAX_SEG = 64;  // peers x rings
+struct HaloSegs {
+    int nseg;
+    int total;
+    int begin[HALO_MAX_SEG + 1];    // prefix sums of segment lengths
+    const double *src[HALO_MAX_SEG];
+    double *dst[HALO_MAX_SEG];
+    const int *idx[HALO_MAX_SEG];   // pack: gather indices (src = local vector); unpack: nullptr (contiguous copy)
+};
+
+__global__ void __launch_bounds__(256) halo_move_kernel(const HaloSegs S)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= S.total) return;
+    int s = 0;
+    while (s + 1 < S.nseg && i >= S.begin[s + 1]) s++;
+    const int j = i - S.begin[s];
+    S.dst[s][j] = S.idx[s] ? S.src[s][S.idx[s][j]] : S.src[s][j];
+}
+
 void nsk_dist_free(nsk_csr_t A)
 {
     if (!A || !A->dist) return;
     for (DistPeer &p : A->dist->peers) {
         if (p.d_send_idx) cudaFree(p.d_send_idx);
         if (p.d_sendbuf) cudaFree(p.d_sendbuf);
+        if (p.d_recvbuf) cudaFree(p.d_recvbuf);
     }
     delete A->dist;
     A->dist = nullptr;
@@ -114,6 +138,15 @@ NSK_API int nsk_csr_create_dist(nsk_ctx_t ctx, nsk_plan_t plan, nsk_csr_t *out)
             }
             NSK_CUDA(ctx, cudaMemcpy(P.d_send_idx, sd->second.local_idx.data(), sizeof(int) * cnt, cudaMemcpyHostToDevice));
         }
+        {
+            size_t rc = 0;
+            for (int v : P.recv_ring_count) rc += (size_t)v;
+            if (rc > 0 && cudaMalloc(&P.d_recvbuf, sizeof(double) * rc) != cudaSuccess) {
+                nsk_set_error(ctx, "halo buffer allocation failed");
+                nsk_csr_destroy(A);
+                return NSK_ERR_ALLOC;
+            }
+        }
         D->peers.push_back(P);
     }
     *out = A;
@@ -128,31 +161,72 @@ int nsk_halo_exchange_dev(nsk_csr_t A, double *xlocal, int depth)
     NSK_REQUIRE(ctx, depth >= 1 && depth <= D->depth, "halo depth exceeds the plan's depth");
     if (D->peers.empty()) return NSK_OK;
     NSK_REQUIRE(ctx, nsk_comm_active(ctx) || nsk_comm_size(ctx) == 1, "no communicator attached (nsk_comm_init)");
-    // pack: one gather per peer over the first `depth` rings of its list
+    // One message per peer and direction: the first `depth` rings of a peer's send list are contiguous in its send
+    // buffer (ring-major), and land contiguously in d_recvbuf; a ring's slice from one peer is contiguous in the local
+    // vector, so unpacking is `depth` straight copies per peer.  One pack launch and one unpack launch for all peers.
+    HaloSegs pack, unpack;
+    pack.nseg = unpack.nseg = 0;
+    pack.total = unpack.total = 0;
+    pack.begin[0] = unpack.begin[0] = 0;
     std::vector<const double *> sendbuf;
     std::vector<int> sendcount, recvcount, peer;
     std::vector<double *> recvbuf;
+    const bool direct = (int)D->peers.size() * depth > HALO_MAX_SEG;  // too many segments for one descriptor: a message per ring
     for (DistPeer &P : D->peers) {
-        int cnt = 0;
-        for (int r = 0; r < depth; r++) cnt += P.send_ring_count[r];
-        if (cnt > 0) {
-            pack_kernel<<<(cnt + 255) / 256, 256, 0, ctx->stream>>>(xlocal, P.d_send_idx, P.d_sendbuf, cnt);
-            ctx->launches++;
+        int scnt = 0, rcnt = 0;
+        for (int r = 0; r < depth; r++) { scnt += P.send_ring_count[r]; rcnt += P.recv_ring_count[r]; }
+        if (direct) {
+            if (scnt > 0) {
+                pack_kernel<<<(scnt + 255) / 256, 256, 0, ctx->stream>>>(xlocal, P.d_send_idx, P.d_sendbuf, scnt);
+                ctx->launches++;
+            }
+            int off = 0;
+            for (int r = 0; r < depth; r++) {
+                peer.push_back(P.rank);
+                sendbuf.push_back(P.d_sendbuf + off);
+                sendcount.push_back(P.send_ring_count[r]);
+                recvbuf.push_back(xlocal + P.recv_ring_start[r]);
+                recvcount.push_back(P.recv_ring_count[r]);
+                off += P.send_ring_count[r];
+            }
+            continue;
         }
-        // one message per ring and direction: a ring's slice from one peer is contiguous on both sides
+        if (scnt > 0) {
+            pack.src[pack.nseg] = xlocal;
+            pack.idx[pack.nseg] = P.d_send_idx;
+            pack.dst[pack.nseg] = P.d_sendbuf;
+            pack.total += scnt;
+            pack.begin[++pack.nseg] = pack.total;
+        }
         int off = 0;
-        for (int r = 0; r < depth; r++) {
-            peer.push_back(P.rank);
-            sendbuf.push_back(P.d_sendbuf + off);
-            sendcount.push_back(P.send_ring_count[r]);
-            recvbuf.push_back(xlocal + P.recv_ring_start[r]);
-            recvcount.push_back(P.recv_ring_count[r]);
-            off += P.send_ring_count[r];
+        for (int r = 0; r < depth && depth > 1; r++) {  // depth 1: the single ring is received in place, nothing to unpack
+            if (P.recv_ring_count[r] == 0) continue;
+            unpack.src[unpack.nseg] = P.d_recvbuf + off;
+            unpack.idx[unpack.nseg] = nullptr;
+            unpack.dst[unpack.nseg] = xlocal + P.recv_ring_start[r];
+            unpack.total += P.recv_ring_count[r];
+            unpack.begin[++unpack.nseg] = unpack.total;
+            off += P.recv_ring_count[r];
         }
+        peer.push_back(P.rank);
+        sendbuf.push_back(P.d_sendbuf);
+        sendcount.push_back(scnt);
+        recvbuf.push_back(depth > 1 ? P.d_recvbuf : xlocal + P.recv_ring_start[0]);
+        recvcount.push_back(rcnt);
+    }
+    if (!direct && pack.total > 0) {
+        halo_move_kernel<<<(pack.total + 255) / 256, 256, 0, ctx->stream>>>(pack);
+        ctx->launches++;
     }
     NSK_CUDA(ctx, cudaGetLastError());
-    return nsk_comm_sendrecv(ctx, (int)peer.size(), peer.data(), sendbuf.data(), sendcount.data(), recvbuf.data(),
-                             recvcount.data());
+    NSK_TRY(nsk_comm_sendrecv(ctx, (int)peer.size(), peer.data(), sendbuf.data(), sendcount.data(), recvbuf.data(),
+                              recvcount.data()));
+    if (!direct && unpack.total > 0) {
+        halo_move_kernel<<<(unpack.total + 255) / 256, 256, 0, ctx->stream>>>(unpack);
+        ctx->launches++;
+        NSK_CUDA(ctx, cudaGetLastError());
+    }
+    return NSK_OK;
 }
 
 NSK_API int nsk_halo_exchange(nsk_csr_t A, double *xlocal, int depth)

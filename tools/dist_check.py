@@ -66,7 +66,7 @@ def main():
     xs, it, rel, ok = op.cg(np.ascontiguousarray(b[lo:hi]), tol=1e-9, maxit=800)
     x_ref, it_ref, _, _ = lib.cg(A.ptrow, A.indcol, A.coef, b, tol=1e-9, maxit=800)
     err = float(np.max(np.abs(xs - x_ref[lo:hi])))
-    cg_ok = ok and abs(it - it_ref) <= 2 and err < 1e-6
+    cg_ok = ok and abs(it - it_ref) <= 2 and err < 1e-6 and rel <= 1e-9
     bad += not cg_ok
     xs4, it4, rel4, ok4 = op.cg(np.ascontiguousarray(b[lo:hi]), tol=1e-9, maxit=800, sstep=4)
     err4 = float(np.max(np.abs(xs4 - x_ref[lo:hi])))
