@@ -93,7 +93,16 @@ uint64_t nsk_ctx_launch_count(nsk_ctx_t ctx);
 /* Device facts: sm_count, l2_bytes, smem_per_block_optin, total HBM bytes. */
 int nsk_ctx_device_info(nsk_ctx_t ctx, int *sm_count, int64_t *l2_bytes, int *smem_optin,
                         int64_t *hbm_bytes);
-/* Tuning knobs (name -> integer).  Unknown names give NSK_ERR_INVALID.  See DESIGN.md. */
+/* Tuning knobs (name -> integer).  Unknown names give NSK_ERR_INVALID.  Defaults are what bench.py runs.
+ *   spmv_kernel      0 auto (packed when the operator packs, else stream) | 1 scalar | 2 stream (CSR) | 3 packed
+ *   mpk_kernel       0 auto (fused packed level pipeline when it applies, else k launches) | 1 k launches |
+ *                    2 wavefront (CSR) | 3 level pipeline (CSR) | 4 level pipeline (packed)
+ *   packed_variant, stream_variant, pipe_variant, wave_variant   0 default, n = table entry n-1 of that kernel
+ *   wave_l2_pct      share of L2 the fused kernels' window may occupy (0 = default: 70 packed, 80 CSR)
+ *   wave_slack_pct   explicit window slack (< 0 = size it from the L2 budget)
+ *   pipe_bp_global, pipe_interleave, pipe_w0_pct, pk_flags, stream_exact_kind, spmv_ctas_per_sm, wave_static
+ *                    experiment switches documented next to nsk_options in csrc/nsk_internal.h
+ *   pk_timing        1: the packed kernel prints its stage-cycle breakdown to stderr (debugging aid) */
 int nsk_ctx_set_option(nsk_ctx_t ctx, const char *name, int64_t value);
 
 /* CUDA-event timing on the context's stream (what bench.py brackets its timed regions with). */

@@ -23,6 +23,7 @@
 // its inputs complete.  Every spin is bounded and traps instead of hanging.
 #include <algorithm>
 #include <map>
+#include <mutex>
 
 #include "nsk_internal.h"
 #include "ptx_helpers.cuh"
@@ -244,18 +245,24 @@ struct PipePlan {
     int *d_group_size = nullptr;
 };
 
-static std::map<nsk_csr_t, std::vector<PipePlan>> g_pipe;
+static std::map<nsk_csr_t, std::vector<PipePlan>> g_pipe;  // map guarded; an entry belongs to its operator's thread
+static std::mutex g_pipe_mu;
 
 void nsk_pipe_free(nsk_csr_t A)
 {
-    auto it = g_pipe.find(A);
-    if (it == g_pipe.end()) return;
-    for (PipePlan &p : it->second) {
+    std::vector<PipePlan> mine;
+    {
+        std::lock_guard<std::mutex> lk(g_pipe_mu);
+        auto it = g_pipe.find(A);
+        if (it == g_pipe.end()) return;
+        mine.swap(it->second);
+        g_pipe.erase(it);
+    }
+    for (PipePlan &p : mine) {
         if (p.d_items) cudaFree(p.d_items);
         if (p.d_counters) cudaFree(p.d_counters);
         if (p.d_group_size) cudaFree(p.d_group_size);
     }
-    g_pipe.erase(it);
 }
 
 struct PipeVariant {
@@ -323,7 +330,9 @@ static int pipe_launch_shape(nsk_ctx_t ctx, int variant, bool muladd, int k, pip
 static PipePlan *pipe_plan(nsk_csr_t A, int k, const int *level_rows, const PipeVariant &V, int team, const char **why)
 {
     nsk_ctx_t ctx = A->ctx;
+    g_pipe_mu.lock();
     std::vector<PipePlan> &plans = g_pipe[A];
+    g_pipe_mu.unlock();
     std::vector<int> lr(k);
     for (int l = 0; l < k; l++) lr[l] = level_rows ? level_rows[l] : A->n;
     const int lead_pct = ctx->opt.wave_slack_pct >= 0 ? (int)ctx->opt.wave_slack_pct : 100;

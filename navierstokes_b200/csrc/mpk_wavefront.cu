@@ -328,13 +328,20 @@ struct WaveState {
 };
 
 #include <map>
-static std::map<nsk_csr_t, WaveState> g_wave;
+#include <mutex>
+static std::map<nsk_csr_t, WaveState> g_wave;  // map guarded; an entry belongs to its operator's thread
+static std::mutex g_wave_mu;
+static WaveState &wave_state(nsk_csr_t A)
+{
+    std::lock_guard<std::mutex> lk(g_wave_mu);
+    return g_wave[A];
+}
 
 // Called at create time (and again by the distributed layer once breaks / row_rank are known).
 // Columns >= A->n are ghost entries of x that only level 0 reads: they create no dependency.
 void nsk_wave_set_block_extents(nsk_csr_t A, const int *ptrow, const int *indcol)
 {
-    WaveState &S = g_wave[A];
+    WaveState &S = wave_state(A);
     nsk_pipe_free(A);  // plans of the level-pipeline kernel were built from the old extents
     nsk_packed_free(A);
     S.plans.clear();
@@ -364,22 +371,27 @@ void nsk_wave_set_block_extents(nsk_csr_t A, const int *ptrow, const int *indcol
 
 void nsk_wave_free(nsk_csr_t A)
 {
-    auto it = g_wave.find(A);
-    if (it == g_wave.end()) return;
-    for (WavePlan &p : it->second.plans) {
+    std::vector<WavePlan> mine;
+    {
+        std::lock_guard<std::mutex> lk(g_wave_mu);
+        auto it = g_wave.find(A);
+        if (it == g_wave.end()) return;
+        mine.swap(it->second.plans);
+        g_wave.erase(it);
+    }
+    for (WavePlan &p : mine) {
         if (p.d_tasks) cudaFree(p.d_tasks);
         if (p.d_tasks_dyn) cudaFree(p.d_tasks_dyn);
         if (p.d_counters) cudaFree(p.d_counters);
         if (p.d_group_size) cudaFree(p.d_group_size);
     }
-    g_wave.erase(it);
 }
 
 // Dependency geometry of a tiling, shared by the wavefront and the level-pipeline kernels: tile order in
 // global row order (positions), and for every tile the range of position GROUPS its columns fall into.
 bool nsk_wave_deps(nsk_csr_t A, const nsk_tiling &T, WaveDeps &out, const char **why)
 {
-    WaveState &S = g_wave[A];
+    WaveState &S = wave_state(A);
     if (S.blk_row0.empty()) { *why = "column extents were not recorded"; return false; }
     if (T.nlong) { *why = "operator has rows longer than a stage"; return false; }
     const int ntiles = T.ntiles;
@@ -487,7 +499,7 @@ static int wave_variant(nsk_ctx_t ctx)
 static WavePlan *get_plan(nsk_csr_t A, int k, const int *level_rows, const WaveVariant &V, int slack, int grid,
                           const char **why)
 {
-    WaveState &S = g_wave[A];
+    WaveState &S = wave_state(A);
     std::vector<int> lr(k);
     for (int l = 0; l < k; l++) lr[l] = level_rows ? level_rows[l] : A->n;
     for (WavePlan &p : S.plans)

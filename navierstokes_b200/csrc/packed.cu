@@ -30,6 +30,7 @@
 #include <algorithm>
 #include <atomic>
 #include <map>
+#include <mutex>
 #include <thread>
 
 #include "nsk_internal.h"
@@ -508,13 +509,23 @@ struct PackedOp {
     std::vector<PkLevelPlan> plans;
 };
 
+// Per-operator state lives in a process-wide map: the map itself is guarded (operators of different contexts may be
+// created / destroyed from different host threads); an operator's own entry is used by one thread at a time, like
+// the operator (std::map nodes are stable under insertion of other keys).
 static std::map<nsk_csr_t, std::vector<PackedOp *>> g_packed;
+static std::mutex g_packed_mu;
 
 void nsk_packed_free(nsk_csr_t A)
 {
-    auto it = g_packed.find(A);
-    if (it == g_packed.end()) return;
-    for (PackedOp *op : it->second) {
+    std::vector<PackedOp *> mine;
+    {
+        std::lock_guard<std::mutex> lk(g_packed_mu);
+        auto it = g_packed.find(A);
+        if (it == g_packed.end()) return;
+        mine.swap(it->second);
+        g_packed.erase(it);
+    }
+    for (PackedOp *op : mine) {
         for (PkLevelPlan &p : op->plans) {
             if (p.d_items) cudaFree(p.d_items);
             if (p.d_counters) cudaFree(p.d_counters);
@@ -525,7 +536,6 @@ void nsk_packed_free(nsk_csr_t A)
         if (op->d_tiles) cudaFree(op->d_tiles);
         delete op;
     }
-    g_packed.erase(it);
 }
 
 // Column runs of one tile.  cols: the tile's column indices (any order, duplicates allowed; scratch, sorted in
@@ -563,7 +573,9 @@ static bool pk_segments(std::vector<int> &cols, int n_cols, int xcap, PkTile &t)
 
 static PackedOp *pk_get(nsk_csr_t A, const PkVariant &V)
 {
+    g_packed_mu.lock();
     std::vector<PackedOp *> &ops = g_packed[A];
+    g_packed_mu.unlock();
     for (PackedOp *op : ops)
         if (op->t_rows == V.t_rows && op->blob_cap == V.blob_cap && op->xcap == V.xcap) return op;
     nsk_ctx_t ctx = A->ctx;
