@@ -109,6 +109,32 @@ def laplace3d_7pt(nx: int, ny: int | None = None, nz: int | None = None, row0: i
     return _stencil(offsets, valid, 6.0, n, row0, nrows)
 
 
+def random_stencil3d(nx: int, ny: int, nz: int, seed: int = 0, max_points: int = 13, drop: float = 0.05) -> Csr:
+    """Variable-coefficient stencil operator on an nx x ny x nz grid with a RANDOM stencil shape: up to `max_points`
+    offsets (dx, dy, dz) in [-2, 2]^3 drawn from the seed, random fp64 coefficients per entry, neighbours outside the
+    grid truncated, and a fraction `drop` of the remaining entries removed at random (ragged rows, a few empty ones).
+    Structured enough that tiles reference x in a few runs, irregular enough to exercise the packing."""
+    rng = np.random.default_rng(seed)
+    cand = [(dx, dy, dz) for dz in (-2, -1, 0, 1, 2) for dy in (-2, -1, 0, 1, 2) for dx in (-2, -1, 0, 1, 2)]
+    pick = rng.choice(len(cand), size=min(max_points, len(cand)), replace=False)
+    offs = sorted({cand[i] for i in pick} | {(0, 0, 0)}, key=lambda o: (o[2], o[1], o[0]))
+    n = nx * ny * nz
+    r = np.arange(n, dtype=np.int64)
+    ix, iy, iz = r % nx, (r // nx) % ny, r // (nx * ny)
+    m = len(offs)
+    mask = np.empty((n, m), dtype=bool)
+    cols = np.empty((n, m), dtype=np.int64)
+    for j, (dx, dy, dz) in enumerate(offs):
+        ok = (ix + dx >= 0) & (ix + dx < nx) & (iy + dy >= 0) & (iy + dy < ny) & (iz + dz >= 0) & (iz + dz < nz)
+        mask[:, j] = ok & (rng.random(n) >= drop)
+        cols[:, j] = r + dx + dy * nx + dz * nx * ny
+    counts = mask.sum(axis=1, dtype=np.int64)
+    ptrow = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(counts, out=ptrow[1:])
+    vals = rng.uniform(-2.0, 2.0, size=(n, m))
+    return Csr(n=n, ptrow=ptrow.astype(np.int32), indcol=cols[mask].astype(np.int32), coef=vals[mask], ncols=n)
+
+
 # ---------------------------------------------------------------------------------------------
 # Tetrahedral meshes (Kuhn 6-tet split of a structured cube)
 # ---------------------------------------------------------------------------------------------

@@ -605,3 +605,27 @@ def test_packed_mpk_splits_when_the_window_does_not_fit(ctx, oracle_lib, reset_o
         for l in range(5):
             assert_bits_equal(lv[l].to_host(), ref[l], f"budget {pct}% level {l}")
     assert 1 in seen and len(seen) >= 2, seen  # the generous budget fuses everything; a tight one needs more launches
+
+
+@pytest.mark.parametrize("seed", list(range(8)))
+def test_packed_fuzz_random_stencils(ctx, oracle_lib, seed, reset_options):
+    """Random stencil shapes (up to 13 points within +-2 in every direction), random coefficients, truncated and
+    randomly thinned rows, random (even-sized) grids: whatever packs must give the oracle's bits for SpMV and for the
+    fused powers in both exact flavours; whatever does not pack still runs (CSR kernels) with the same bits."""
+    rng = np.random.default_rng(1000 + seed)
+    nx, ny, nz = int(rng.integers(5, 70)), int(rng.integers(3, 40)), int(rng.integers(2, 24))
+    if (nx * ny * nz) % 2:
+        nx += 1
+    A = matgen.random_stencil3d(nx, ny, nz, seed=seed, max_points=int(rng.integers(3, 14)), drop=float(rng.uniform(0, 0.2)))
+    x = matgen.vec_uniform(A.n, seed=seed + 50)
+    dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
+    packed = dA.packed_bytes > 0
+    ref = oracle_lib.mpk(A.ptrow, A.indcol, A.coef, 4, x)
+    assert_bits_equal(dA.spmv(x), ref[0], f"grid {nx}x{ny}x{nz} packed={packed}")
+    assert ctx.query("last_spmv_kernel") == (3 if packed else 2)
+    ctx.set_option("wave_l2_pct", 1000)
+    assert_bits_equal(dA.mpk(4, x), ref, f"grid {nx}x{ny}x{nz} packed={packed} k=4")
+    assert ctx.query("last_mpk_strategy") == (4 if packed else 1)
+    assert_bits_equal(dA.mpk(3, x, mode=nsk.EXACT_MULADD)[2],
+                      oracle_lib.spmv_muladd(A.ptrow, A.indcol, A.coef, oracle_lib.spmv_muladd(
+                          A.ptrow, A.indcol, A.coef, oracle_lib.spmv_muladd(A.ptrow, A.indcol, A.coef, x))))
