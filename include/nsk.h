@@ -144,6 +144,17 @@ int64_t nsk_coo2bcsr4(int nrow, int64_t nnz, const int *irow, const int *jcol, c
 int nsk_mtx_read(const char *path, int *nrow, int64_t *nnz, int **irow, int **jcol, double **val);
 void nsk_mtx_free(int *irow, int *jcol, double *val);
 
+/* ---- the packed format's host half (no GPU): used by the CPU test-suite to check the packer --------------- */
+/* Packs a CSR operator for table entry `variant` of the packed kernel (0-based); nsk_pack_host_why returns "" or
+ * the reason it does not pack; nsk_pack_host_expand rebuilds CSR from the blobs (global columns through the tiles'
+ * x runs) so a test can compare it entry for entry with the input. */
+int nsk_pack_host_create(int n, int n_cols, int64_t nnz, const int *ptrow, const int *indcol, const double *coef,
+                         int variant, void **handle);
+const char *nsk_pack_host_why(void *handle);
+int64_t nsk_pack_host_bytes(void *handle);
+int nsk_pack_host_expand(void *handle, int *ptrow, int *indcol, double *coef, int *max_runs, int *max_xlen);
+void nsk_pack_host_destroy(void *handle);
+
 /* ---- CSR operator --------------------------------------------------------------------------- */
 /* Uploads a square CSR operator (0-based, int32 indices, fp64 values; columns need not be sorted --
  * the row-sequential modes accumulate in storage order whatever it is) and builds the launch plan.

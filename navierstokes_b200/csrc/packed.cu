@@ -571,39 +571,37 @@ static bool pk_segments(std::vector<int> &cols, int n_cols, int xcap, PkTile &t)
     return flush();
 }
 
-static PackedOp *pk_get(nsk_csr_t A, const PkVariant &V)
-{
-    g_packed_mu.lock();
-    std::vector<PackedOp *> &ops = g_packed[A];
-    g_packed_mu.unlock();
-    for (PackedOp *op : ops)
-        if (op->t_rows == V.t_rows && op->blob_cap == V.blob_cap && op->xcap == V.xcap) return op;
-    nsk_ctx_t ctx = A->ctx;
-    PackedOp *op = new PackedOp();
-    op->t_rows = V.t_rows; op->blob_cap = V.blob_cap; op->xcap = V.xcap;
-    ops.push_back(op);
-    const int n = A->n;
-    const std::vector<int> &ptrow = nsk_csr_host_ptrow(A);
-    if (n == 0 || A->nnz == 0) { op->why = "empty operator"; return op; }
-    if (A->n_cols & 1) { op->why = "odd number of columns (bulk copies move 16-byte granules)"; return op; }
-    if ((int)ptrow.size() != n + 1) { op->why = "host row pointers missing"; return op; }
-
-    // 1. tiles: up to t_rows consecutive rows, never across a break, blob within the stage
+// Host-only packer: everything about the packed format that does not need a GPU (also reachable through
+// nsk_pack_host_* for the CPU test-suite).  Returns "" on success, else why the operator does not pack.
+struct PackedHost {
     std::vector<nsk_tile> tiles;
+    std::vector<PkTile> ptiles;
+    std::vector<unsigned char> blobs;  // + 64 bytes of slack
+    size_t blob_bytes = 0;
+};
+
+static std::string pk_pack_host(int n, int n_cols, int64_t nnz, const int *ptrow, const int *indcol, const double *coef,
+                                const std::vector<int> &breaks, int t_rows, int blob_cap, int xcap, PackedHost &out)
+{
+    if (n == 0 || nnz == 0) return "empty operator";
+    if (n_cols & 1) return "odd number of columns (bulk copies move 16-byte granules)";
+    // 1. tiles: up to t_rows consecutive rows, never across a break, blob within the stage
+    std::vector<nsk_tile> &tiles = out.tiles;
     std::vector<int> widths;
+    tiles.clear();
     {
         size_t bi = 0;
         int r = 0;
         while (r < n) {
-            while (bi < A->breaks.size() && A->breaks[bi] <= r) bi++;
-            const int seg_end = bi < A->breaks.size() ? std::min(n, A->breaks[bi]) : n;
-            int rows = std::min(V.t_rows, seg_end - r);
+            while (bi < breaks.size() && breaks[bi] <= r) bi++;
+            const int seg_end = bi < breaks.size() ? std::min(n, breaks[bi]) : n;
+            int rows = std::min(t_rows, seg_end - r);
             int width = 0;
             for (;;) {
                 width = 0;
                 for (int i = r; i < r + rows; i++) width = std::max(width, ptrow[i + 1] - ptrow[i]);
-                if (pk_blob_bytes(rows, width) <= V.blob_cap) break;
-                if (rows == 1) { op->why = "a row is longer than a stage"; return op; }
+                if (pk_blob_bytes(rows, width) <= blob_cap) break;
+                if (rows == 1) return "a row is longer than a stage";
                 rows = rows / 2;
             }
             tiles.push_back(nsk_tile{r, rows, ptrow[r], ptrow[r + rows]});
@@ -614,23 +612,15 @@ static PackedOp *pk_get(nsk_csr_t A, const PkVariant &V)
     const int ntiles = (int)tiles.size();
     std::vector<size_t> off(ntiles + 1, 0);
     for (int t = 0; t < ntiles; t++) off[t + 1] = off[t] + (size_t)pk_blob_bytes(tiles[t].nrows, widths[t]);
-    const double csr_equiv = 10.0 * (double)A->nnz + 2.0 * n;
-    if ((double)off[ntiles] > 1.35 * csr_equiv + 65536.0) { op->why = "row lengths too ragged for slot-major tiles"; return op; }
+    const double csr_equiv = 10.0 * (double)nnz + 2.0 * n;
+    if ((double)off[ntiles] > 1.35 * csr_equiv + 65536.0) return "row lengths too ragged for slot-major tiles";
 
-    // 2. the operator's entries (the caller's host arrays are gone: read them back once)
-    std::vector<int> indcol((size_t)A->nnz);
-    std::vector<double> coef((size_t)A->nnz);
-    if (cudaMemcpy(indcol.data(), A->d_indcol, sizeof(int) * (size_t)A->nnz, cudaMemcpyDeviceToHost) != cudaSuccess ||
-        cudaMemcpy(coef.data(), A->d_coef, sizeof(double) * (size_t)A->nnz, cudaMemcpyDeviceToHost) != cudaSuccess) {
-        op->why = "reading the operator back failed";
-        return op;
-    }
-
-    // 3. per tile: column runs, local indices, slot-major blob (parallel over tiles)
-    std::vector<unsigned char> blobs(off[ntiles] + 64, 0);
-    std::vector<PkTile> ptiles(ntiles);
+    // 2. per tile: column runs, local indices, slot-major blob (parallel over tiles)
+    std::vector<unsigned char> &blobs = out.blobs;
+    blobs.assign(off[ntiles] + 64, 0);
+    std::vector<PkTile> &ptiles = out.ptiles;
+    ptiles.assign(ntiles, PkTile());
     std::atomic<int> next(0), failed(0);
-    const int n_cols = A->n_cols;
     auto work = [&]() {
         std::vector<int> cols;
         for (;;) {
@@ -639,8 +629,8 @@ static PackedOp *pk_get(nsk_csr_t A, const PkVariant &V)
             for (int t = t0; t < std::min(ntiles, t0 + 64); t++) {
                 const nsk_tile &tl = tiles[t];
                 PkTile &pt = ptiles[t];
-                cols.assign(indcol.begin() + tl.nz0, indcol.begin() + tl.nz1);
-                if (!pk_segments(cols, n_cols, V.xcap, pt)) { failed.store(1); return; }
+                cols.assign(indcol + tl.nz0, indcol + tl.nz1);
+                if (!pk_segments(cols, n_cols, xcap, pt)) { failed.store(1); return; }
                 const int width = widths[t], rp = pk_round_up(tl.nrows, 32);
                 pt.blob_off = (long long)off[t];
                 pt.blob_bytes = pk_blob_bytes(tl.nrows, width);
@@ -683,28 +673,129 @@ static PackedOp *pk_get(nsk_csr_t A, const PkVariant &V)
         work();
         for (auto &x : th) x.join();
     }
-    if (failed.load()) { op->why = "a tile references x in too many / too long runs"; return op; }
+    if (failed.load()) return "a tile references x in too many / too long runs";
+    out.blob_bytes = off[ntiles];
+    return "";
+}
 
-    // 4. upload
-    if (cudaMalloc(&op->d_blobs, blobs.size()) != cudaSuccess ||
+static PackedOp *pk_get(nsk_csr_t A, const PkVariant &V)
+{
+    g_packed_mu.lock();
+    std::vector<PackedOp *> &ops = g_packed[A];
+    g_packed_mu.unlock();
+    for (PackedOp *op : ops)
+        if (op->t_rows == V.t_rows && op->blob_cap == V.blob_cap && op->xcap == V.xcap) return op;
+    PackedOp *op = new PackedOp();
+    op->t_rows = V.t_rows; op->blob_cap = V.blob_cap; op->xcap = V.xcap;
+    ops.push_back(op);
+    const int n = A->n;
+    const std::vector<int> &ptrow = nsk_csr_host_ptrow(A);
+    if (n == 0 || A->nnz == 0) { op->why = "empty operator"; return op; }
+    if (A->n_cols & 1) { op->why = "odd number of columns (bulk copies move 16-byte granules)"; return op; }
+    if ((int)ptrow.size() != n + 1) { op->why = "host row pointers missing"; return op; }
+    // cheap refusals first (row lengths only), then the operator's entries: the caller's host arrays are gone, read
+    // them back once
+    std::vector<int> indcol((size_t)A->nnz);
+    std::vector<double> coef((size_t)A->nnz);
+    if (cudaMemcpy(indcol.data(), A->d_indcol, sizeof(int) * (size_t)A->nnz, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(coef.data(), A->d_coef, sizeof(double) * (size_t)A->nnz, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        op->why = "reading the operator back failed";
+        return op;
+    }
+    PackedHost H;
+    op->why = pk_pack_host(n, A->n_cols, A->nnz, ptrow.data(), indcol.data(), coef.data(), A->breaks, V.t_rows, V.blob_cap,
+                           V.xcap, H);
+    if (!op->why.empty()) return op;
+    const int ntiles = (int)H.tiles.size();
+    if (cudaMalloc(&op->d_blobs, H.blobs.size()) != cudaSuccess ||
         cudaMalloc(&op->d_tiles, sizeof(PkTile) * (size_t)ntiles + 128) != cudaSuccess) {
         op->why = "allocation of the packed operator failed";
         cudaGetLastError();
         return op;
     }
-    cudaMemcpy(op->d_blobs, blobs.data(), blobs.size(), cudaMemcpyHostToDevice);
-    cudaMemcpy(op->d_tiles, ptiles.data(), sizeof(PkTile) * (size_t)ntiles, cudaMemcpyHostToDevice);
+    cudaMemcpy(op->d_blobs, H.blobs.data(), H.blobs.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(op->d_tiles, H.ptiles.data(), sizeof(PkTile) * (size_t)ntiles, cudaMemcpyHostToDevice);
     op->ntiles = ntiles;
-    op->blob_bytes = off[ntiles];
-    op->h_tiles.swap(ptiles);
+    op->blob_bytes = H.blob_bytes;
+    op->h_tiles.swap(H.ptiles);
     op->csr_view.tile_rows = V.t_rows;
     op->csr_view.ntiles = ntiles;
     op->csr_view.nlong = 0;
-    op->csr_view.h_tiles.swap(tiles);
+    op->csr_view.h_tiles.swap(H.tiles);
     op->ok = true;
-    (void)ctx;
     return op;
 }
+
+// ---- host-only access to the packer (CPU tests: pack, then expand the blobs back to CSR and compare) --------------
+struct nsk_packed_host_s {
+    PackedHost H;
+    std::string why;
+    int n = 0, n_cols = 0;
+};
+
+NSK_API int nsk_pack_host_create(int n, int n_cols, int64_t nnz, const int *ptrow, const int *indcol, const double *coef,
+                                 int variant, void **out)
+{
+    if (!out || !ptrow || (nnz > 0 && (!indcol || !coef))) return NSK_ERR_INVALID;
+    if (variant < 0 || variant >= g_npkv) return NSK_ERR_INVALID;
+    nsk_packed_host_s *h = new nsk_packed_host_s();
+    h->n = n;
+    h->n_cols = n_cols;
+    const PkVariant &V = g_pkv[variant];
+    h->why = pk_pack_host(n, n_cols, nnz, ptrow, indcol, coef, std::vector<int>(), V.t_rows, V.blob_cap, V.xcap, h->H);
+    *out = h;
+    return NSK_OK;
+}
+
+NSK_API const char *nsk_pack_host_why(void *handle) { return static_cast<nsk_packed_host_s *>(handle)->why.c_str(); }
+
+NSK_API int64_t nsk_pack_host_bytes(void *handle)
+{
+    nsk_packed_host_s *h = static_cast<nsk_packed_host_s *>(handle);
+    return h->why.empty() ? (int64_t)h->H.blob_bytes : 0;
+}
+
+// Expands the packed operator back to CSR (row pointers, GLOBAL column indices through the tiles' runs, values) and
+// reports the largest number of runs / x doubles any tile needs.  Arrays sized n+1 / nnz by the caller.
+NSK_API int nsk_pack_host_expand(void *handle, int *ptrow, int *indcol, double *coef, int *max_runs, int *max_xlen)
+{
+    nsk_packed_host_s *h = static_cast<nsk_packed_host_s *>(handle);
+    if (!h->why.empty()) return NSK_ERR_UNSUPPORTED;
+    int mr = 0, mx = 0;
+    int64_t k = 0;
+    ptrow[0] = 0;
+    for (size_t t = 0; t < h->H.tiles.size(); t++) {
+        const PkTile &pt = h->H.ptiles[t];
+        mr = std::max(mr, pt.nseg);
+        mx = std::max(mx, pt.xlen);
+        const unsigned char *b = h->H.blobs.data() + pt.blob_off;
+        const int *hdr = reinterpret_cast<const int *>(b);
+        const int rp = hdr[PKH_RP];
+        const unsigned short *lens = reinterpret_cast<const unsigned short *>(b + hdr[PKH_OFF_LENS]);
+        const unsigned short *lcol = reinterpret_cast<const unsigned short *>(b + hdr[PKH_OFF_LCOL]);
+        const double *val = reinterpret_cast<const double *>(b + hdr[PKH_OFF_VAL]);
+        for (int r = 0; r < hdr[PKH_NROWS]; r++) {
+            for (int e = 0; e < (int)lens[r]; e++) {
+                const int lc = lcol[(size_t)e * rp + r];
+                int g = -1;
+                for (int s = 0; s < pt.nseg; s++) {
+                    const int len = pt.seg_lenoff[s] & 0xffff, xoff = (pt.seg_lenoff[s] >> 16) & 0xffff;
+                    if (lc >= xoff && lc < xoff + len) { g = pt.seg_start[s] + (lc - xoff); break; }
+                }
+                if (g < 0) return NSK_ERR_INVALID;
+                indcol[k] = g;
+                coef[k] = val[(size_t)e * rp + r];
+                k++;
+            }
+            ptrow[hdr[PKH_ROW0] + r + 1] = (int)k;
+        }
+    }
+    if (max_runs) *max_runs = mr;
+    if (max_xlen) *max_xlen = mx;
+    return NSK_OK;
+}
+
+NSK_API void nsk_pack_host_destroy(void *handle) { delete static_cast<nsk_packed_host_s *>(handle); }
 
 static int pk_launch_shape(nsk_ctx_t ctx, int variant, bool muladd, int k, pk_fn *fn_out, int *smem_out, int *team)
 {

@@ -1,0 +1,109 @@
+"""The packed format's host half (csrc/packed.cu pk_pack_host) without a GPU: pack, expand the blobs back to CSR
+through the tiles' x runs and compare entry for entry with the input; refusals for operators that must not pack."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from navierstokes_b200 import _lib, matgen
+
+from conftest import CSR_CASES, assert_bits_equal, golden
+
+NVARIANTS = 14
+
+
+def pack(A_ptrow, A_indcol, A_coef, n_cols, variant):
+    lib = _lib.load()
+    ptrow = np.ascontiguousarray(A_ptrow, np.int32)
+    indcol = np.ascontiguousarray(A_indcol, np.int32)
+    coef = np.ascontiguousarray(A_coef, np.float64)
+    n = len(ptrow) - 1
+    h = C.c_void_p()
+    st = lib.nsk_pack_host_create(n, n_cols, len(indcol), ptrow.ctypes.data, indcol.ctypes.data, coef.ctypes.data,
+                                  variant, C.byref(h))
+    assert st == 0
+    why = lib.nsk_pack_host_why(h).decode()
+    out = None
+    if not why:
+        p2 = np.zeros(n + 1, np.int32)
+        c2 = np.zeros(max(len(indcol), 1), np.int32)
+        v2 = np.zeros(max(len(indcol), 1), np.float64)
+        mr, mx = C.c_int(), C.c_int()
+        assert lib.nsk_pack_host_expand(h, p2.ctypes.data, c2.ctypes.data, v2.ctypes.data, C.byref(mr), C.byref(mx)) == 0
+        out = (p2, c2[:len(indcol)], v2[:len(indcol)], mr.value, mx.value, int(lib.nsk_pack_host_bytes(h)))
+    lib.nsk_pack_host_destroy(h)
+    return why, out
+
+
+@pytest.mark.parametrize("variant", range(NVARIANTS))
+@pytest.mark.parametrize("gen,args", [("laplace3d_7pt", (24, 18, 10)), ("laplace2d_5pt", (130, 41)), ("laplace3d_7pt", (300, 4, 6)),
+                                      ("fem_baij4", (4,))])
+def test_pack_expand_round_trip(gen, args, variant):
+    A = getattr(matgen, gen)(*args)
+    if A.n % 2:
+        pytest.skip("odd size: refused by design, covered below")
+    why, out = pack(A.ptrow, A.indcol, A.coef, A.n, variant)
+    if why:  # a geometry whose stage is too small for this operator's rows / runs may refuse; it must say why
+        assert "row" in why or "runs" in why
+        return
+    p2, c2, v2, max_runs, max_xlen, nbytes = out
+    assert np.array_equal(p2, A.ptrow) and np.array_equal(c2, A.indcol)
+    assert_bits_equal(v2, A.coef)
+    assert 1 <= max_runs <= 8 and nbytes > 0
+
+
+def test_pack_stencils_use_few_runs_and_ten_bytes_per_nonzero():
+    A = matgen.laplace3d_7pt(64, 64, 16)
+    why, out = pack(A.ptrow, A.indcol, A.coef, A.n, 7)
+    assert not why
+    _, _, _, max_runs, max_xlen, nbytes = out
+    assert max_runs == 3                      # plane below, own lines +-1, plane above
+    assert max_xlen <= 256 + 256 + 2 * 64 + 256 + 16
+    assert nbytes / A.nnz < 10.6              # 8 (value) + 2 (local column) + lens/header/padding
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_pack_random_stencils_round_trip(seed):
+    rng = np.random.default_rng(seed)
+    nx, ny, nz = int(rng.integers(4, 50)), int(rng.integers(3, 30)), int(rng.integers(2, 16))
+    if (nx * ny * nz) % 2:
+        nx += 1
+    A = matgen.random_stencil3d(nx, ny, nz, seed=seed, max_points=int(rng.integers(3, 14)), drop=float(rng.uniform(0, 0.2)))
+    why, out = pack(A.ptrow, A.indcol, A.coef, A.n, 7)
+    if why:
+        return
+    p2, c2, v2, *_ = out
+    assert np.array_equal(p2, A.ptrow) and np.array_equal(c2, A.indcol)
+    assert_bits_equal(v2, A.coef)
+
+
+def test_pack_refusals():
+    odd = matgen.laplace3d_7pt(11, 9, 7)
+    why, _ = pack(odd.ptrow, odd.indcol, odd.coef, odd.n, 7)
+    assert "odd" in why
+    rnd = matgen.random_csr(4000, 5.0, seed=1)
+    why, _ = pack(rnd.ptrow, rnd.indcol, rnd.coef, rnd.n, 7)
+    assert why  # scattered columns: too many runs (or too ragged)
+    ragged = matgen.random_banded_csr(20000, 150, 5.0, seed=4)
+    why, _ = pack(ragged.ptrow, ragged.indcol, ragged.coef, ragged.n, 7)
+    assert "ragged" in why
+    tet = matgen.tet_p1_laplacian(12, permute_seed=2, rcm=True)
+    if tet.n % 2 == 0:
+        why, _ = pack(tet.ptrow, tet.indcol, tet.coef, tet.n, 7)
+        assert why
+
+
+@pytest.mark.parametrize("case", CSR_CASES)
+def test_pack_golden_operators(case):
+    """The fixtures produced by the compiled reference: whatever packs expands back to exactly the fixture."""
+    g = golden(case)
+    n = len(g["ptrow"]) - 1
+    if n % 2:
+        return
+    for variant in (7, 10):
+        why, out = pack(g["ptrow"], g["indcol"], g["coef"], n, variant)
+        if why:
+            continue
+        p2, c2, v2, *_ = out
+        assert np.array_equal(p2, g["ptrow"]) and np.array_equal(c2, g["indcol"])
+        assert_bits_equal(v2, g["coef"])
