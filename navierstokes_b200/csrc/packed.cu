@@ -726,6 +726,123 @@ static PackedOp *pk_get(nsk_csr_t A, const PkVariant &V)
     return op;
 }
 
+// Host-only: the per-level item lists, the group sizes the completion counters are compared with, and the CTA role
+// table.  teams[] comes in as the requested team sizes and goes out clipped to the items a level really has.
+struct PkSchedule {
+    std::vector<PkItem> items;       // all levels back to back
+    std::vector<size_t> item_off;    // per level
+    std::vector<int> count;          // per level
+    std::vector<int> gsize;          // [k][ngroups]
+    std::vector<int2> roles;         // per CTA {level, index in team}
+};
+
+static void pk_build_schedule(const std::vector<PkTile> &tiles, const std::vector<int> &pos_tile, const std::vector<int> &ghi,
+                              const std::vector<int> &lr, int k, int ngroups, int lead, int bp_global, int interleave,
+                              std::vector<int> &teams, PkSchedule &S)
+{
+    const int ntiles = (int)tiles.size();
+    S.items.clear();
+    S.items.reserve((size_t)k * ntiles);
+    S.gsize.assign((size_t)k * ngroups, 0);
+    S.count.assign(k, 0);
+    S.item_off.assign(k, 0);
+    for (int l = 0; l < k; l++) {
+        S.item_off[l] = S.items.size();
+        for (int pos = 0; pos < ntiles; pos++) {
+            const int t = pos_tile[pos];
+            const PkTile &pt = tiles[t];
+            if (pt.row0 >= lr[l]) continue;  // outside this level's row prefix (distributed shrink)
+            int gback = -1;
+            // adjacent mode: level l trails l+1 by at most `lead`; global mode: level 0 trails k-1 by (k-1)*lead
+            const int hold = bp_global ? (l == 0 && k > 1 ? (k - 1) * lead : -1) : (l < k - 1 ? lead : -1);
+            if (hold >= 0 && pos - hold >= 0) gback = (pos - hold) / WF_GROUP - 1;
+            S.items.push_back(PkItem{t, pos, ghi[t], gback, pt.blob_off, pt.blob_bytes, 0});
+            S.gsize[(size_t)l * ngroups + pos / WF_GROUP]++;
+            S.count[l]++;
+        }
+    }
+    // role table: levels interleaved in proportion to their team sizes (consecutive block indices land on different
+    // SMs, so every SM hosts a mix of levels), or level by level
+    for (int l = 0; l < k; l++) teams[l] = std::max(1, std::min(teams[l], std::max(1, S.count[l])));
+    S.roles.clear();
+    int total = 0;
+    for (int l = 0; l < k; l++) total += teams[l];
+    std::vector<int> given(k, 0);
+    if (interleave) {
+        for (int b = 0; b < total; b++) {
+            int best = -1;
+            double bestv = 0.0;
+            for (int l = 0; l < k; l++) {  // the level furthest behind its share
+                if (given[l] >= teams[l]) continue;
+                const double v = (double)(b + 1) * teams[l] / total - given[l];
+                if (best < 0 || v > bestv) { best = l; bestv = v; }
+            }
+            S.roles.push_back(make_int2(best, given[best]++));
+        }
+    } else {
+        for (int l = 0; l < k; l++)
+            for (int i = 0; i < teams[l]; i++) S.roles.push_back(make_int2(l, i));
+    }
+}
+
+// CPU model of the kernel's protocol, for the test-suite: every CTA runs its items strictly in order (the dependency
+// warp is head-of-line blocking), an item may start when all groups <= ghi of level l-1 and all groups <= gback of the
+// level that holds it back have reached their group sizes, and it reports to its own group when it finishes; CTAs are
+// visited in a seeded random order and up to `stages` items per CTA may be open at once (they finish in random order).
+// Returns the number of items that completed; the schedule is sound iff that equals the total.
+static long long pk_simulate(const PkSchedule &S, const std::vector<int> &teams, int k, int ngroups, int bp_global, int stages,
+                             unsigned seed)
+{
+    const int grid = (int)S.roles.size();
+    std::vector<std::vector<int>> cnt(k, std::vector<int>(ngroups, 0));
+    std::vector<int> water(k, 0);  // all groups < water[l] complete at level l
+    auto advance = [&](int l) {
+        while (water[l] < ngroups && cnt[l][water[l]] >= S.gsize[(size_t)l * ngroups + water[l]]) water[l]++;
+    };
+    for (int l = 0; l < k; l++) advance(l);
+    std::vector<int> next(grid, 0);                 // next item index (within the CTA's own sequence) to open
+    std::vector<std::vector<int>> open(grid);       // opened, not yet finished (global item indices)
+    long long done = 0, total = (long long)S.items.size();
+    unsigned rng = seed * 2654435761u + 12345u;
+    auto rnd = [&]() { rng = rng * 1664525u + 1013904223u; return rng >> 8; };
+    std::vector<int> order(grid);
+    for (int b = 0; b < grid; b++) order[b] = b;
+    bool progress = true, force = false;
+    while (done < total && (progress || !force)) {
+        force = !progress;  // a pass in which every coin said "not yet" is not a deadlock: the next pass finishes items
+        progress = false;
+        for (int i = grid - 1; i > 0; i--) std::swap(order[i], order[rnd() % (unsigned)(i + 1)]);
+        for (int oi = 0; oi < grid; oi++) {
+            const int b = order[oi];
+            const int level = S.roles[b].x, c = S.roles[b].y, G = teams[level];
+            // finish one open item (random pick) with probability 1/2, or whenever the ring is full
+            if (!open[b].empty() && (force || (rnd() & 1) || (int)open[b].size() >= stages)) {
+                const int pick = (int)(rnd() % (unsigned)open[b].size());
+                const PkItem &it = S.items[(size_t)open[b][pick]];
+                open[b].erase(open[b].begin() + pick);
+                cnt[level][it.pos / WF_GROUP]++;
+                advance(level);
+                done++;
+                progress = true;
+            }
+            // open the next item if the ring has room and its inputs are complete
+            const long long idx = (long long)c + (long long)next[b] * G;
+            if ((int)open[b].size() < stages && idx < S.count[level]) {
+                const PkItem &it = S.items[S.item_off[level] + (size_t)idx];
+                const int lb = bp_global ? k - 1 : level + 1;
+                const bool fwd_ok = level == 0 || water[level - 1] > it.ghi || water[level - 1] >= ngroups;
+                const bool back_ok = it.gback < 0 || water[lb] > it.gback || water[lb] >= ngroups;
+                if (fwd_ok && back_ok) {
+                    open[b].push_back((int)(S.item_off[level] + (size_t)idx));
+                    next[b]++;
+                    progress = true;
+                }
+            }
+        }
+    }
+    return done;
+}
+
 // ---- host-only access to the packer (CPU tests: pack, then expand the blobs back to CSR and compare) --------------
 struct nsk_packed_host_s {
     PackedHost H;
@@ -793,6 +910,54 @@ NSK_API int nsk_pack_host_expand(void *handle, int *ptrow, int *indcol, double *
     if (max_runs) *max_runs = mr;
     if (max_xlen) *max_xlen = mx;
     return NSK_OK;
+}
+
+// Builds the level schedule for a packed operator exactly like the GPU path (dependencies from the tiles' column
+// extents, natural row order, optional per-level row prefixes) and runs the CPU protocol model.  Returns the number
+// of items that did NOT complete (0 = sound), or a negative status.  *items_out receives the total item count.
+NSK_API long long nsk_pack_host_simulate(void *handle, int k, int lead_slack_tiles, int resident, int w0_pct, int bp_global,
+                                         int interleave, int stages, const int *level_rows, unsigned seed,
+                                         long long *items_out, int *reach_out)
+{
+    nsk_packed_host_s *h = static_cast<nsk_packed_host_s *>(handle);
+    if (!h->why.empty()) return NSK_ERR_UNSUPPORTED;
+    if (k < 1 || k > NSK_MAX_K || resident < k || stages < 1) return NSK_ERR_INVALID;
+    const int ntiles = (int)h->H.tiles.size();
+    const int ngroups = (ntiles + WF_GROUP - 1) / WF_GROUP;
+    // dependencies: the tile range covered by a tile's x runs (columns >= n are ghost entries of x, level 0 only)
+    std::vector<int> pos_tile(ntiles), ghi(ntiles, 0), row0s(ntiles);
+    for (int t = 0; t < ntiles; t++) { pos_tile[t] = t; row0s[t] = h->H.tiles[t].row0; }
+    int reach = 0;
+    for (int t = 0; t < ntiles; t++) {
+        const PkTile &pt = h->H.ptiles[t];
+        int mx = -1;
+        for (int s = 0; s < pt.nseg; s++) {
+            int last = pt.seg_start[s] + (pt.seg_lenoff[s] & 0xffff) - 1;
+            if (last >= h->n) last = h->n - 1;
+            mx = std::max(mx, last);
+        }
+        if (mx < 0) mx = pt.row0;
+        const int tmax = (int)(std::upper_bound(row0s.begin(), row0s.end(), mx) - row0s.begin()) - 1;
+        ghi[t] = std::max(0, tmax) / WF_GROUP;
+        reach = std::max(reach, std::min(ntiles - 1, (ghi[t] + 1) * WF_GROUP - 1) - t);
+    }
+    std::vector<int> lr(k);
+    for (int l = 0; l < k; l++) lr[l] = level_rows ? level_rows[l] : h->n;
+    std::vector<int> teams(k, 0);
+    {
+        const double wsum = (double)w0_pct + 100.0 * (k - 1);
+        int used = 0;
+        for (int l = 1; l < k; l++) { teams[l] = std::max(1, (int)(resident * 100.0 / wsum)); used += teams[l]; }
+        teams[0] = std::max(1, resident - used);
+    }
+    // a negative slack undercuts the safe minimum on purpose: the test-suite checks that the model then reports a deadlock
+    const int lead = std::max(1, reach + 1 + WF_GROUP + lead_slack_tiles);
+    PkSchedule S;
+    pk_build_schedule(h->H.ptiles, pos_tile, ghi, lr, k, ngroups, lead, bp_global, interleave, teams, S);
+    const long long done = pk_simulate(S, teams, k, ngroups, bp_global, stages, seed);
+    if (items_out) *items_out = (long long)S.items.size();
+    if (reach_out) *reach_out = reach;
+    return (long long)S.items.size() - done;
 }
 
 NSK_API void nsk_pack_host_destroy(void *handle) { delete static_cast<nsk_packed_host_s *>(handle); }
@@ -882,51 +1047,14 @@ static PkLevelPlan *pk_level_plan(nsk_csr_t A, PackedOp *op, int k, const int *l
         for (int t = 0; t < ntiles; t++) pos_tile[t] = t;
     }
     p.ngroups = ngroups;
-    std::vector<PkItem> items;
-    items.reserve((size_t)k * ntiles);
-    std::vector<int> gsize((size_t)k * ngroups, 0);
-    p.count.assign(k, 0);
-    p.item_off.assign(k, 0);
-    for (int l = 0; l < k; l++) {
-        p.item_off[l] = items.size();
-        for (int pos = 0; pos < ntiles; pos++) {
-            const int t = pos_tile[pos];
-            const PkTile &pt = op->h_tiles[t];
-            if (pt.row0 >= lr[l]) continue;  // outside this level's row prefix (distributed shrink)
-            int gback = -1;
-            // adjacent mode: level l trails l+1 by at most `lead`; global mode: level 0 trails k-1 by (k-1)*lead
-            const int hold = bp_global ? (l == 0 ? (k - 1) * p.lead : -1) : (l < k - 1 ? p.lead : -1);
-            if (hold >= 0 && pos - hold >= 0) gback = (pos - hold) / WF_GROUP - 1;
-            items.push_back(PkItem{t, pos, ghi[t], gback, pt.blob_off, pt.blob_bytes, 0});
-            gsize[(size_t)l * ngroups + pos / WF_GROUP]++;
-            p.count[l]++;
-        }
-    }
-    // role table: levels interleaved in proportion to their team sizes (consecutive block indices land on different
-    // SMs, so every SM hosts a mix of levels), or level by level
-    for (int l = 0; l < k; l++) p.teams[l] = std::max(1, std::min(p.teams[l], std::max(1, p.count[l])));
-    std::vector<int2> roles;
-    {
-        int total = 0;
-        for (int l = 0; l < k; l++) total += p.teams[l];
-        std::vector<int> given(k, 0);
-        if (interleave) {
-            for (int b = 0; b < total; b++) {
-                int best = -1;
-                double bestv = 0.0;
-                for (int l = 0; l < k; l++) {  // the level furthest behind its share
-                    if (given[l] >= p.teams[l]) continue;
-                    const double v = (double)(b + 1) * p.teams[l] / total - given[l];
-                    if (best < 0 || v > bestv) { best = l; bestv = v; }
-                }
-                roles.push_back(make_int2(best, given[best]++));
-            }
-        } else {
-            for (int l = 0; l < k; l++)
-                for (int i = 0; i < p.teams[l]; i++) roles.push_back(make_int2(l, i));
-        }
-        p.grid = total;
-    }
+    PkSchedule S;
+    pk_build_schedule(op->h_tiles, pos_tile, ghi, lr, k, ngroups, p.lead, bp_global, interleave, p.teams, S);
+    p.count = S.count;
+    p.item_off = S.item_off;
+    p.grid = (int)S.roles.size();
+    std::vector<PkItem> &items = S.items;
+    std::vector<int> &gsize = S.gsize;
+    std::vector<int2> &roles = S.roles;
     if (cudaMalloc(&p.d_roles, sizeof(int2) * roles.size()) != cudaSuccess ||
         cudaMalloc(&p.d_items, sizeof(PkItem) * (items.size() + 1)) != cudaSuccess ||
         cudaMalloc(&p.d_counters, sizeof(int) * ((size_t)k * ngroups + 4)) != cudaSuccess ||
