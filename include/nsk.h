@@ -207,6 +207,11 @@ int nsk_axpy(nsk_ctx_t ctx, int64_t n, double a, const double *x, double *y, nsk
 /* beta = <x,y>; y -= alpha*beta*x  (mpk/2SpMV.cpp:3-11); *beta may be NULL */
 int nsk_orthogonalize(nsk_ctx_t ctx, int64_t n, const double *x, double *y, double alpha,
                       double *beta, nsk_where where);
+/* orthonormalize_against_basis (reference mpk/2SpMV.cpp:13-28): for each of the m basis vectors in order,
+ * y -= <y, b_j> b_j (modified Gram-Schmidt: every projection sees the updated y); *norm receives ||y||_2 afterwards
+ * (the reference computes it and does not scale y; neither does this). */
+int nsk_orthonormalize_against_basis(nsk_ctx_t ctx, int64_t n, int m, const double *const *basis, double *y,
+                                     double *norm, nsk_where where);
 /* G[i*m+j] = <V_i, V_j> for m vectors of length n (s-step Gram block); G is m*m HOST doubles. */
 int nsk_gram(nsk_ctx_t ctx, int64_t n, int m, const double *const *V, double *G, nsk_where where);
 

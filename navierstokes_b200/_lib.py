@@ -70,6 +70,7 @@ SIGNATURES = {
     "nsk_rel_error": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, c_double_p, C.c_int]),
     "nsk_axpy": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_int]),
     "nsk_orthogonalize": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_double, c_double_p, C.c_int]),
+    "nsk_orthonormalize_against_basis": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, c_void_pp, C.c_void_p, c_double_p, C.c_int]),
     "nsk_gram": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, c_void_pp, c_double_p, C.c_int]),
     "nsk_cg": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int, c_int_p, c_double_p,
                          C.c_int]),

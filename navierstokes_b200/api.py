@@ -161,6 +161,20 @@ class Context:
             self._ck(self.lib.nsk_orthogonalize(self.h, n, px, C.c_void_p(_ptr(y)), alpha, C.byref(beta), HOST))
         return beta.value
 
+
+    def orthonormalize_against_basis(self, basis, y):
+        """y (numpy, updated in place, or DeviceVector) swept against the basis vectors in order; returns ||y||_2."""
+        m = len(basis)
+        nrm = C.c_double()
+        if isinstance(y, DeviceVector):
+            ptrs = (C.c_void_p * max(m, 1))(*[b.ptr.value for b in basis])
+            self._ck(self.lib.nsk_orthonormalize_against_basis(self.h, y.n, m, ptrs, y.ptr, C.byref(nrm), DEVICE))
+            return nrm.value
+        assert isinstance(y, np.ndarray) and y.dtype == np.float64 and y.flags.c_contiguous
+        bs = [np.ascontiguousarray(b, dtype=np.float64) for b in basis]
+        ptrs = (C.c_void_p * max(m, 1))(*[_ptr(b) for b in bs])
+        self._ck(self.lib.nsk_orthonormalize_against_basis(self.h, y.size, m, ptrs, C.c_void_p(_ptr(y)), C.byref(nrm), HOST))
+        return nrm.value
     def gram(self, vectors) -> np.ndarray:
         m = len(vectors)
         ptrs = (C.c_void_p * m)()
@@ -604,6 +618,12 @@ def rel_error(ref, test) -> float:
 def orthogonalize(nrow, x, y, alpha: float = 1e-8):
     """mpk/2SpMV.cpp:3-11: y -= alpha * <x,y> * x, in place."""
     return default_context().orthogonalize(x[:nrow], y[:nrow] if y.size != nrow else y, alpha)
+
+
+def orthonormalize_against_basis(nrow, basis, y):
+    """mpk/2SpMV.cpp:13-28: Gram-Schmidt sweep of y (in place) against every vector of `basis` in order; returns the
+    norm the reference computes and drops (y is not scaled, as in the reference)."""
+    return default_context().orthonormalize_against_basis([b[:nrow] for b in basis], y[:nrow] if y.size != nrow else y)
 
 
 def flush_cache():

@@ -6,6 +6,8 @@
 // HBM-bound streaming: 128-bit loads, grid = SM-count multiple, reductions are two-stage and
 // deterministic (fixed grid -> fixed association; the last CTA to finish folds the per-CTA
 // partials in index order), results stay in device scalar slots so solvers never synchronise.
+#include <math.h>
+
 #include "nsk_internal.h"
 #include "ptx_helpers.cuh"
 
@@ -311,6 +313,44 @@ NSK_API int nsk_orthogonalize(nsk_ctx_t ctx, int64_t n, const double *x, double 
         NSK_TRY(nsk_read_scalars(ctx, SLOT_PUBLIC, 1, &b));
         if (beta) *beta = b;
     }
+    return NSK_OK;
+}
+
+// orthonormalize_against_basis (reference mpk/2SpMV.cpp:13-28): modified Gram-Schmidt sweep of y against every basis
+// vector in order -- each projection uses the already updated y -- then ||y||_2, which the reference computes and
+// drops (it never scales y); here it is returned.  Two launches per basis vector, the dot stays on the device.
+NSK_API int nsk_orthonormalize_against_basis(nsk_ctx_t ctx, int64_t n, int m, const double *const *basis, double *y,
+                                             double *norm, nsk_where where)
+{
+    if (!ctx) return NSK_ERR_INVALID;
+    NSK_REQUIRE(ctx, n >= 0 && m >= 0 && (m == 0 || basis) && (n == 0 || y), "bad arguments");
+    const size_t nb = sizeof(double) * (size_t)n;
+    double *dy = y;
+    double *dbuf = nullptr;
+    if (where == NSK_HOST) {
+        void *vy = nullptr, *vb = nullptr;
+        NSK_TRY(nsk_stage(ctx, 1, nb, &vy));
+        NSK_TRY(nsk_stage(ctx, 0, nb, &vb));
+        dy = (double *)vy;
+        dbuf = (double *)vb;
+        NSK_CUDA(ctx, cudaMemcpyAsync(dy, y, nb, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    for (int j = 0; j < m; j++) {
+        const double *dx = basis[j];
+        if (where == NSK_HOST) {
+            NSK_CUDA(ctx, cudaMemcpyAsync(dbuf, basis[j], nb, cudaMemcpyHostToDevice, ctx->stream));
+            dx = dbuf;
+        }
+        NSK_TRY(nsk_launch_dot(ctx, n, dy, dx, SLOT_PUBLIC));
+        NSK_TRY(nsk_comm_allreduce_slots(ctx, SLOT_PUBLIC, 1));
+        NSK_TRY(nsk_launch_axpy_dev(ctx, n, ctx->d_scalars + SLOT_PUBLIC, -1.0, dx, dy));  // y -= <y,x> x
+    }
+    NSK_TRY(nsk_launch_dot(ctx, n, dy, dy, SLOT_PUBLIC));
+    NSK_TRY(nsk_comm_allreduce_slots(ctx, SLOT_PUBLIC, 1));
+    if (where == NSK_HOST) NSK_CUDA(ctx, cudaMemcpyAsync(y, dy, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    double yy = 0.0;
+    NSK_TRY(nsk_read_scalars(ctx, SLOT_PUBLIC, 1, &yy));  // also completes the copy above
+    if (norm) *norm = sqrt(yy);
     return NSK_OK;
 }
 

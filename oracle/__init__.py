@@ -87,6 +87,8 @@ class _Oracle:
             l.oracle_dot.restype = C.c_double
             l.oracle_orthogonalize.argtypes = [C.c_int64, _f64p, _f64p, C.c_double]
             l.oracle_orthogonalize.restype = C.c_double
+            l.oracle_orthonormalize_against_basis.argtypes = [C.c_int64, C.c_int, _f64p, _f64p]
+            l.oracle_orthonormalize_against_basis.restype = C.c_double
             l.oracle_cg.argtypes = [C.c_int, _i32p, _i32p, _f64p, _f64p, _f64p, C.c_double, C.c_int,
                                     C.POINTER(C.c_double), C.c_void_p]
             l.oracle_cg.restype = C.c_int
@@ -193,6 +195,13 @@ class _Oracle:
         beta = self.l.oracle_orthogonalize(len(x), _f64(x), y, alpha)
         return y, float(beta)
 
+    def orthonormalize_against_basis(self, basis, y):
+        """mpk/2SpMV.cpp:13-28: returns (y after the Gram-Schmidt sweep, its norm -- computed and dropped by the reference)."""
+        B = np.ascontiguousarray(np.stack([_f64(b) for b in basis])) if len(basis) else np.zeros((0, len(y)))
+        y = _f64(y).copy()
+        nrm = self.l.oracle_orthonormalize_against_basis(len(y), len(basis), B.reshape(-1) if B.size else np.zeros(1), y)
+        return y, float(nrm)
+
     # -- CG (parity unpinned) --------------------------------------------------------------
     def cg(self, ptrow, indcol, coef, b, tol=1e-8, maxit=1000):
         n = len(ptrow) - 1
@@ -298,6 +307,7 @@ class _Reference:
             s.ref_rel_error.argtypes = [C.c_int, _f64p, _f64p]
             s.ref_rel_error.restype = C.c_double
             s.ref_orthogonalize.argtypes = [C.c_int, _f64p, _f64p, C.c_double]
+            s.ref_orthonormalize_against_basis.argtypes = [C.c_int, C.c_int, _f64p, _f64p]
             self._s = s
         return self._s
 
@@ -399,6 +409,12 @@ class _Reference:
     def orthogonalize(self, x, y, alpha=1e-8):
         y = _f64(y).copy()
         self.s.ref_orthogonalize(len(x), _f64(x), y, alpha)
+        return y
+
+    def orthonormalize_against_basis(self, basis, y):
+        B = np.ascontiguousarray(np.stack([_f64(b) for b in basis]))
+        y = _f64(y).copy()
+        self.s.ref_orthonormalize_against_basis(len(y), len(basis), B.reshape(-1), y)
         return y
 
     def multi0_spmv(self, ptrow, indcol, coef, x):

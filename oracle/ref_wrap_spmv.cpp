@@ -19,6 +19,7 @@ void SpM2V_BCSR(double *z, double *y, double *x, bcsr4x4_matrix &A, std::vector<
 void SpM2V_BCSR_OPT(double *z, double *y, double *x, bcsr4x4_matrix &A, std::vector<int> &ptrowendB);
 void SpM2V_BCSR_AVX2(double *z, double *y, double *x, bcsr4x4_matrix &A, std::vector<int> &ptrowendB);
 void orthogonalize(int nrow, const std::vector<double> &x, std::vector<double> &y, double alpha);
+void orthonormalize_against_basis(int nrow, std::vector<std::vector<double>> &basis, std::vector<double> &y);
 
 namespace {
 csrmatrix make_csr(int n, int nnz, const int *ptrow, const int *indcol, const double *coef)
@@ -166,6 +167,15 @@ void ref_orthogonalize(int n, const double *x, double *y, double alpha)
 {
     std::vector<double> xv(x, x + n), yv(y, y + n);
     orthogonalize(n, xv, yv, alpha);
+    std::copy(yv.begin(), yv.end(), y);
+}
+
+void ref_orthonormalize_against_basis(int n, int m, const double *basis, double *y)
+{
+    std::vector<std::vector<double>> B(m);
+    for (int j = 0; j < m; j++) B[j].assign(basis + (size_t)j * n, basis + (size_t)(j + 1) * n);
+    std::vector<double> yv(y, y + n);
+    orthonormalize_against_basis(n, B, yv);
     std::copy(yv.begin(), yv.end(), y);
 }
 

@@ -3,7 +3,7 @@
 Run in the development container only (needs /root/reference):  python tests/golden/make_golden.py
 The fixtures pin the oracle (tests/test_oracle.py) and the CUDA path (tests/test_*_gpu.py) to outputs
 of the reference's own code: SpMV_CSR{,_OPT,_FMA,_AVX2}, SpM2V_CSR{,_OPT}, SpM2V0/SpM3V/SpM4V with
-their Generate*layer schedules, COO2CSR, generate_BCSR4, SpMV_BCSR*, norm2, rel_error, orthogonalize.
+their Generate*layer schedules, COO2CSR, generate_BCSR4, SpMV_BCSR*, norm2, rel_error, orthogonalize, orthonormalize_against_basis.
 The reference itself ships no vectors or matrices, so these are the golden data.
 """
 import sys
@@ -77,8 +77,24 @@ def formats_case():
     print("formats", len(d["csr_indcol"]), "kept of", nnz, "; bcsr blocks", len(d["bcsr_indcol"]))
 
 
+def orthobasis_case():
+    """orthonormalize_against_basis (mpk/2SpMV.cpp:13-28) on the reference's own fake Krylov basis sin(0.001 j + i)
+    (mpk/2SpMV.cpp:110-116), shortened to 6 vectors of 1003."""
+    ref = oracle.ref
+    n, m = 1003, 6
+    basis = [np.sin(0.001 * j + np.arange(n)) for j in range(m)]
+    y = np.random.default_rng(11).uniform(-1, 1, n)
+    d = {"basis": np.stack(basis), "y": y, "y_out": ref.orthonormalize_against_basis(basis, y)}
+    np.savez_compressed(OUT / "orthobasis.npz", **d)
+    print("orthobasis", n, m)
+
+
 if __name__ == "__main__":
     assert oracle.REFERENCE_SRC.is_dir(), "needs /root/reference (development container)"
+    if "--only-orthobasis" in sys.argv:
+        oracle.build()
+        orthobasis_case()
+        sys.exit(0)
     csr_case("lap3d_7pt_6", matgen.laplace3d_7pt(6), deep=True)
     csr_case("lap3d_7pt_12x10x9", matgen.laplace3d_7pt(12, 10, 9))
     csr_case("lap2d_5pt_33x29", matgen.laplace2d_5pt(33, 29))
@@ -87,3 +103,4 @@ if __name__ == "__main__":
     csr_case("tet_p1_m5_rcm", matgen.tet_p1_laplacian(5, permute_seed=2, rcm=True), deep=True)
     csr_case("ragged_300", matgen.random_csr(300, 6.0, seed=3, empty_rows=True))
     formats_case()
+    orthobasis_case()

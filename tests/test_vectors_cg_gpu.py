@@ -155,3 +155,21 @@ def test_sstep_cg_device_vectors_and_strategies(ctx, oracle_lib):
         its.append(it)
     ctx.set_option("mpk_kernel", 0)
     assert abs(its[0] - its[1]) <= 1
+
+
+def test_orthonormalize_against_basis(ctx, oracle_lib):
+    """Reference helper mpk/2SpMV.cpp:13-28 on the reference's fake Krylov basis: against the fixture made by the
+    compiled reference (reduction order differs: 1e-12 relative, the fast-mode bound), host and device residency."""
+    g = golden("orthobasis")
+    basis = [np.ascontiguousarray(b) for b in g["basis"]]
+    y = g["y"].copy()
+    nrm = nsk.orthonormalize_against_basis(len(y), basis, y)
+    assert oracle_lib.rel_error(g["y_out"], y) <= 1e-12
+    assert abs(nrm - np.linalg.norm(g["y_out"])) <= 1e-12 * nrm
+    dy = ctx.to_device(g["y"])
+    nrm2 = ctx.orthonormalize_against_basis([ctx.to_device(b) for b in basis], dy)
+    assert oracle_lib.rel_error(g["y_out"], dy.to_host()) <= 1e-12 and abs(nrm2 - nrm) <= 1e-12 * nrm
+    # empty basis: y untouched, norm returned
+    z = g["y"].copy()
+    assert abs(nsk.orthonormalize_against_basis(len(z), [], z) - np.linalg.norm(g["y"])) <= 1e-12 * nrm
+    assert np.array_equal(z, g["y"])
