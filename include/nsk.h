@@ -187,6 +187,12 @@ int nsk_spmv(nsk_csr_t A, const double *x, double *y, nsk_mode mode, nsk_where w
 int nsk_mpk(nsk_csr_t A, int k, const double *x, double *const *levels, nsk_mode mode,
             nsk_where where);
 
+/* Matrix powers of several right-hand sides: levels[v*k + l] = A^(l+1) xs[v], v < nvec.  The s-step / block-Krylov
+ * basis builder (the reference's BuildKrylovBasis_AVX2 / MatMatMult_SeqBAIJ_4_AVX2, src/kernels/spmm_avx2.c:7-168):
+ * device-resident vectors are processed two per fused launch, so the operator is streamed once per PAIR and level. */
+int nsk_mpk_multi(nsk_csr_t A, int k, int nvec, const double *const *xs, double *const *levels, nsk_mode mode,
+                  nsk_where where);
+
 /* ---- 4x4 block CSR (the reference's bcsr4x4_matrix, row-major blocks) ------------------------ */
 int nsk_bcsr4_create(nsk_ctx_t ctx, int nbrows, int64_t nblocks, const int *ptrow,
                      const int *indcol, const double *coef, nsk_bcsr4_t *B);

@@ -338,6 +338,24 @@ class CsrMatrix:
         self.ctx._ck(self.ctx.lib.nsk_mpk(self.h, k, C.c_void_p(_ptr(x)), ptrs, mode, HOST))
         return levels
 
+    def mpk_multi(self, k: int, xs, levels=None, mode: int = EXACT_FMA):
+        """levels[v][l] = A^(l+1) xs[v] for several right-hand sides.  DeviceVectors: enqueue only, two vectors per
+        fused launch.  numpy arrays: host call, returns an array [nvec, k, n]."""
+        nvec = len(xs)
+        if isinstance(xs[0], DeviceVector):
+            if levels is None:
+                levels = [[self.ctx.empty(self.n) for _ in range(k)] for _ in range(nvec)]
+            xp = (C.c_void_p * nvec)(*[x.ptr.value for x in xs])
+            lp = (C.c_void_p * (nvec * k))(*[levels[v][l].ptr.value for v in range(nvec) for l in range(k)])
+            self.ctx._ck(self.ctx.lib.nsk_mpk_multi(self.h, k, nvec, xp, lp, mode, DEVICE))
+            return levels
+        xs = [np.ascontiguousarray(x, dtype=np.float64) for x in xs]
+        out = np.empty((nvec, k, self.n))
+        xp = (C.c_void_p * nvec)(*[_ptr(x) for x in xs])
+        lp = (C.c_void_p * (nvec * k))(*[out[v, l].ctypes.data for v in range(nvec) for l in range(k)])
+        self.ctx._ck(self.ctx.lib.nsk_mpk_multi(self.h, k, nvec, xp, lp, mode, HOST))
+        return out
+
     def cg(self, b, x=None, tol: float = 1e-8, maxit: int = 1000, sstep: int = 1):
         """Solves A x = b; returns (x, iterations, relres, converged)."""
         it, rel = C.c_int(), C.c_double()

@@ -20,6 +20,8 @@ std::vector<int> &nsk_csr_host_ptrow(nsk_csr_t A)
 }
 
 int nsk_mpk_device(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode);  // mpk.cu
+int nsk_mpk_device2(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, const double *d_x2,
+                    double *const *d_levels2, nsk_mode mode);  // mpk.cu
 void nsk_wave_set_block_extents(nsk_csr_t A, const int *ptrow, const int *indcol);                  // mpk_wavefront.cu
 void nsk_wave_free(nsk_csr_t A);
 void nsk_pipe_free(nsk_csr_t A);  // mpk_pipeline.cu
@@ -196,5 +198,31 @@ NSK_API int nsk_mpk(nsk_csr_t A, int k, const double *x, double *const *levels, 
     for (int l = 0; l < k; l++)
         NSK_CUDA(ctx, cudaMemcpyAsync(levels[l], dlev[l], nb, cudaMemcpyDeviceToHost, ctx->stream));
     NSK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NSK_OK;
+}
+
+// Several right-hand sides (s-step / block Krylov bases; the reference's counterpart is the dense-block product
+// MatMatMult_SeqBAIJ_4_AVX2(A, X, Y, s_step), src/kernels/spmm_avx2.c:7-109, and its monomial basis builder
+// BuildKrylovBasis_AVX2 :112-168): levels[v * k + l] = A^(l+1) xs[v].  Device-resident vectors are taken two at a
+// time through the two-vector fused kernel (each tile of the operator is streamed once per pair); host vectors go
+// one by one (PCIe dominates there).
+NSK_API int nsk_mpk_multi(nsk_csr_t A, int k, int nvec, const double *const *xs, double *const *levels, nsk_mode mode,
+                          nsk_where where)
+{
+    if (!A) return NSK_ERR_INVALID;
+    nsk_ctx_t ctx = A->ctx;
+    NSK_REQUIRE(ctx, k >= 1 && k <= NSK_MAX_K && nvec >= 1, "k or nvec out of range");
+    NSK_REQUIRE(ctx, xs && levels, "xs or levels is null");
+    NSK_REQUIRE(ctx, A->dist != nullptr || A->n == A->n_cols, "matrix powers need a square operator");
+    for (int v = 0; v < nvec; v++) {
+        NSK_REQUIRE(ctx, xs[v] != nullptr, "an input vector is null");
+        for (int l = 0; l < k; l++) NSK_REQUIRE(ctx, levels[(size_t)v * k + l] != nullptr, "a level pointer is null");
+    }
+    NSK_CUDA(ctx, cudaSetDevice(ctx->device));
+    int v = 0;
+    if (where == NSK_DEVICE)
+        for (; v + 1 < nvec; v += 2)
+            NSK_TRY(nsk_mpk_device2(A, k, xs[v], levels + (size_t)v * k, xs[v + 1], levels + (size_t)(v + 1) * k, mode));
+    for (; v < nvec; v++) NSK_TRY(nsk_mpk(A, k, xs[v], levels + (size_t)v * k, mode, where));
     return NSK_OK;
 }

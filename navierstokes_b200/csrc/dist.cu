@@ -11,6 +11,8 @@
 
 int nsk_mpk_local(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode,
                   const int *level_rows);  // mpk.cu
+int nsk_mpk_local2(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, const double *d_x2,
+                   double *const *d_levels2, nsk_mode mode, const int *level_rows);  // mpk.cu
 void nsk_wave_set_block_extents(nsk_csr_t A, const int *ptrow, const int *indcol);
 int nsk_comm_rank(nsk_ctx_t ctx);
 int nsk_comm_size(nsk_ctx_t ctx);
@@ -251,4 +253,18 @@ int nsk_dist_mpk(nsk_csr_t A, int k, const double *d_x, double *const *d_levels,
     int level_rows[NSK_MAX_K];
     for (int l = 0; l < k; l++) level_rows[l] = D->ring_start[k - l];
     return nsk_mpk_local(A, k, d_x, d_levels, mode, level_rows);
+}
+
+// Two right-hand sides: both halos first (two exchanges back to back on the stream), then one fused sweep for both.
+int nsk_dist_mpk2(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, const double *d_x2,
+                  double *const *d_levels2, nsk_mode mode)
+{
+    nsk_ctx_t ctx = A->ctx;
+    nsk_dist_s *D = A->dist;
+    NSK_REQUIRE(ctx, k <= D->depth, "k exceeds the halo depth the operator was planned for");
+    NSK_TRY(nsk_halo_exchange_dev(A, const_cast<double *>(d_x), k));
+    NSK_TRY(nsk_halo_exchange_dev(A, const_cast<double *>(d_x2), k));
+    int level_rows[NSK_MAX_K];
+    for (int l = 0; l < k; l++) level_rows[l] = D->ring_start[k - l];
+    return nsk_mpk_local2(A, k, d_x, d_levels, d_x2, d_levels2, mode, level_rows);
 }

@@ -99,6 +99,54 @@ int nsk_mpk_local(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
     return nsk_mpk_levels(A, k, d_x, d_levels, mode, level_rows);
 }
 
+// Two right-hand sides at once (s-step methods: powers of p and of r in the same outer step): one fused launch per
+// chunk of levels reads every tile's blob once for both; anything the two-vector kernel does not cover runs the
+// vectors one after the other.
+int nsk_mpk_local2(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, const double *d_x2,
+                   double *const *d_levels2, nsk_mode mode, const int *level_rows)
+{
+    nsk_ctx_t ctx = A->ctx;
+    const int sel = (int)ctx->opt.mpk_kernel;
+    if ((sel == 0 || sel == 4) && nsk_packed_applicable(A)) {
+        int done = 0;
+        const double *src = d_x, *src2 = d_x2;
+        bool ok = true, any = false;
+        while (done < k && ok) {
+            const int left = k - done;
+            int took = 0;
+            for (int kk = left; kk >= 1 && !took; kk--) {
+                int s = nsk_packed_run2(A, kk, src, d_levels + done, src2, d_levels2 + done, mode,
+                                        level_rows ? level_rows + done : nullptr);
+                if (s == NSK_OK) took = kk;
+                else if (s != NSK_ERR_UNSUPPORTED) return s;
+            }
+            if (!took) { ok = false; break; }
+            any = true;
+            src = d_levels[done + took - 1];
+            src2 = d_levels2[done + took - 1];
+            done += took;
+        }
+        if (ok) { ctx->last_mpk = any ? 4 : 1; return NSK_OK; }
+        // partial progress is fine: finish the remaining levels vector by vector
+        if (done > 0) {
+            NSK_TRY(nsk_mpk_local(A, k - done, d_levels[done - 1], d_levels + done, mode, level_rows ? level_rows + done : nullptr));
+            return nsk_mpk_local(A, k - done, d_levels2[done - 1], d_levels2 + done, mode, level_rows ? level_rows + done : nullptr);
+        }
+    }
+    NSK_TRY(nsk_mpk_local(A, k, d_x, d_levels, mode, level_rows));
+    return nsk_mpk_local(A, k, d_x2, d_levels2, mode, level_rows);
+}
+
+int nsk_dist_mpk2(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, const double *d_x2,
+                  double *const *d_levels2, nsk_mode mode);  // dist.cu
+
+int nsk_mpk_device2(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, const double *d_x2,
+                    double *const *d_levels2, nsk_mode mode)
+{
+    if (A->dist) return nsk_dist_mpk2(A, k, d_x, d_levels, d_x2, d_levels2, mode);
+    return nsk_mpk_local2(A, k, d_x, d_levels, d_x2, d_levels2, mode, nullptr);
+}
+
 int nsk_mpk_device(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode)
 {
     if (A->dist) return nsk_dist_mpk(A, k, d_x, d_levels, mode);

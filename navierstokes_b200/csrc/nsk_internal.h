@@ -155,6 +155,8 @@ int nsk_launch_spmv(nsk_csr_t A, const nsk_spmv_args &a);
 // packed.cu: k = 1 is the plain product (optionally with the fused dot); NSK_ERR_UNSUPPORTED = use the CSR kernels
 int nsk_packed_run(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode, const int *level_rows,
                    const double *dot_w, int dot_slot);
+int nsk_packed_run2(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, const double *d_x2,
+                    double *const *d_levels2, nsk_mode mode, const int *level_rows);
 bool nsk_packed_applicable(nsk_csr_t A);
 size_t nsk_packed_bytes(nsk_csr_t A);
 void nsk_packed_free(nsk_csr_t A);

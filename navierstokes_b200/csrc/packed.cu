@@ -72,6 +72,8 @@ struct PkParams {
     int ngroups;
     const double *x;
     double *levels[NSK_MAX_K];
+    const double *x2;            // second right-hand side (NV = 2 kernels): same operator, same schedule, its own
+    double *levels2[NSK_MAX_K];  // powers -- the blob is read once for both
     int level_rows[NSK_MAX_K];
     int k;
     int team[NSK_MAX_K];   // CTAs of each level (level 0 streams from HBM and gets more stages in flight)
@@ -125,10 +127,11 @@ __device__ __forceinline__ int pk_wait_groups(const int *cnt, const int *need, i
     return w;
 }
 
-template <int T_ROWS, int BLOB_CAP, int XCAP, int STAGES, int NCW, int MINB, int RPT, bool MULADD>
+template <int T_ROWS, int BLOB_CAP, int XCAP, int STAGES, int NCW, int MINB, int RPT, int NV, bool MULADD>
 __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkParams P)
 {
-    constexpr int STAGE_BYTES = BLOB_CAP + XCAP * 8;
+    static_assert(NV == 1 || NV == 2, "one or two right-hand sides");
+    constexpr int STAGE_BYTES = BLOB_CAP + NV * XCAP * 8;
     static_assert(BLOB_CAP % 128 == 0 && (XCAP * 8) % 128 == 0, "stage parts keep 128-byte alignment");
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)STAGE_BYTES * STAGES);  // blob + x runs landed
@@ -263,6 +266,7 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
         const int *cnt_b = P.counters + (size_t)(back ? lb : 0) * P.ngroups;
         const int *need_b = P.group_size + (size_t)(back ? lb : 0) * P.ngroups;
         const double *src = level == 0 ? P.x : P.levels[level - 1];
+        const double *src2 = NV == 2 ? (level == 0 ? P.x2 : P.levels2[level - 1]) : nullptr;
         const int *tw = reinterpret_cast<const int *>(P.tiles);
         int wf = 0, wb = 0;
         unsigned long long w_done = 0, w_dep = 0;
@@ -312,11 +316,13 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
             const int xlen = __shfl_sync(0xffffffffu, cw, 6);
             const int start = __shfl_sync(0xffffffffu, cw, 8 + (lane & 7));
             const int lenoff = __shfl_sync(0xffffffffu, cw, 16 + (lane & 7));
-            if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)xlen * 8u);
+            if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)xlen * 8u * NV);
             __syncwarp();
-            if (lane < nseg) {
+            if ((lane & 7) < nseg && (lane >> 3) < NV) {  // lanes 0..7: runs of the first vector, 8..15: of the second
                 const int len = lenoff & 0xffff, xoff = (lenoff >> 16) & 0xffff;
-                bulk_g2s(smem + (size_t)s * STAGE_BYTES + BLOB_CAP + (size_t)xoff * 8, src + start, (uint32_t)len * 8u, &full[s]);
+                const int v = lane >> 3;
+                bulk_g2s(smem + (size_t)s * STAGE_BYTES + BLOB_CAP + ((size_t)v * XCAP + (size_t)xoff) * 8,
+                         (v == 0 ? src : src2) + start, (uint32_t)len * 8u, &full[s]);
             }
             if (timing && lane == 0) ts[s * 4 + 1] = pk_now();
             cw = nw;
@@ -332,6 +338,7 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
     // ===== consumer warps: one row per thread and pass, inputs from shared memory only =====
     constexpr int NCT = NCW * 32;
     double *dst = P.levels[level];
+    double *dst2 = NV == 2 ? P.levels2[level] : nullptr;
     const int row_end = P.level_rows[level];
     const bool stream_out = (P.flags & 1) && level == P.k - 1;  // nobody in this launch re-reads the last level
     double dot_acc = 0.0;
@@ -348,37 +355,50 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
         const double *xb = reinterpret_cast<const double *>(blob + BLOB_CAP);
         for (int rb = 0; rb < nrows; rb += NCT * RPT) {
             int len[RPT];
-            double acc[RPT];
+            double acc[NV][RPT];
 #pragma unroll
             for (int q = 0; q < RPT; q++) {
                 const int r = rb + q * NCT + tid;
                 len[q] = (r < nrows && row0 + r < row_end) ? (int)lens[r] : -1;  // -1: no row
-                acc[q] = 0.0;
+#pragma unroll
+                for (int v = 0; v < NV; v++) acc[v][q] = 0.0;
             }
             for (int e0 = 0; e0 < width; e0 += 8) {
-                double xv[RPT][8];
+                double xv[NV][RPT][8];
 #pragma unroll
                 for (int q = 0; q < RPT; q++) {
                     const int r = rb + q * NCT + tid;
 #pragma unroll
                     for (int u = 0; u < 8; u++)
-                        if (e0 + u < len[q]) xv[q][u] = xb[lcol[(e0 + u) * rp + r]];
+                        if (e0 + u < len[q]) {
+                            const int cidx = lcol[(e0 + u) * rp + r];
+#pragma unroll
+                            for (int v = 0; v < NV; v++) xv[v][q][u] = xb[v * XCAP + cidx];
+                        }
                 }
 #pragma unroll
                 for (int q = 0; q < RPT; q++) {
                     const int r = rb + q * NCT + tid;
 #pragma unroll
                     for (int u = 0; u < 8; u++)
-                        if (e0 + u < len[q]) acc[q] = row_op<MULADD>(val[(e0 + u) * rp + r], xv[q][u], acc[q]);
+                        if (e0 + u < len[q]) {
+                            const double a = val[(e0 + u) * rp + r];
+#pragma unroll
+                            for (int v = 0; v < NV; v++) acc[v][q] = row_op<MULADD>(a, xv[v][q][u], acc[v][q]);
+                        }
                 }
             }
 #pragma unroll
             for (int q = 0; q < RPT; q++) {
                 const int r = rb + q * NCT + tid;
                 if (len[q] >= 0) {
-                    if (stream_out) __stcs(dst + row0 + r, acc[q]);
-                    else dst[row0 + r] = acc[q];
-                    if (P.dot_w) dot_acc = __fma_rn(P.dot_w[row0 + r], acc[q], dot_acc);
+                    if (stream_out) __stcs(dst + row0 + r, acc[0][q]);
+                    else dst[row0 + r] = acc[0][q];
+                    if (NV == 2) {
+                        if (stream_out) __stcs(dst2 + row0 + r, acc[NV - 1][q]);
+                        else dst2[row0 + r] = acc[NV - 1][q];
+                    }
+                    if (NV == 1 && P.dot_w) dot_acc = __fma_rn(P.dot_w[row0 + r], acc[0][q], dot_acc);
                 }
             }
         }
@@ -453,13 +473,21 @@ static const PkVariant g_pkv[] = {
 static const int g_npkv = sizeof(g_pkv) / sizeof(g_pkv[0]);
 
 typedef void (*pk_fn)(const PkParams);
-static pk_fn pk_lookup(int variant, bool muladd, int *smem)
+// Two right-hand sides per launch are built for one geometry: the default short-row one with two stages x two CTAs per
+// SM (a stage carries both vectors' x runs).  Other geometries run the vectors one after the other.
+constexpr int PK_NV2_VARIANT = 7;
+static pk_fn pk_lookup(int variant, bool muladd, int nv, int *smem)
 {
+    if (nv == 2) {
+        if (variant != PK_NV2_VARIANT) return nullptr;
+        *smem = (21504 + 2 * 1536 * 8) * 2 + 2 * 2 * 8 + 64 * 8 + 2 * 32 + 2 * 4 + 128;
+        return muladd ? packed_kernel<256, 21504, 1536, 2, 4, 2, 1, 2, true> : packed_kernel<256, 21504, 1536, 2, 4, 2, 1, 2, false>;
+    }
     switch (variant) {
 #define X(id, r, b, x, s, w, m, u)                                          \
     case id:                                                                \
         *smem = (b + x * 8) * s + 2 * s * 8 + 64 * 8 + s * 32 + s * 4 + 128; \
-        return muladd ? packed_kernel<r, b, x, s, w, m, u, true> : packed_kernel<r, b, x, s, w, m, u, false>;
+        return muladd ? packed_kernel<r, b, x, s, w, m, u, 1, true> : packed_kernel<r, b, x, s, w, m, u, 1, false>;
         NSK_PK_VARIANTS(X)
 #undef X
     }
@@ -482,7 +510,7 @@ static int pk_variant(nsk_csr_t A)
 // host side: packing (cached per operator and tile geometry), level plans, launches
 // -----------------------------------------------------------------------------------------------
 struct PkLevelPlan {
-    int k = 0, team = 0, lead_pct = 0, bp_global = 0, w0_pct = 0, interleave = 0, l2_pct = 0;
+    int k = 0, team = 0, lead_pct = 0, bp_global = 0, w0_pct = 0, interleave = 0, l2_pct = 0, nv = 1;
     bool rejected = false;
     std::vector<int> teams;     // CTAs per level, sum <= team * k
     int grid = 0;
@@ -962,15 +990,19 @@ NSK_API long long nsk_pack_host_simulate(void *handle, int k, int lead_slack_til
 
 NSK_API void nsk_pack_host_destroy(void *handle) { delete static_cast<nsk_packed_host_s *>(handle); }
 
-static int pk_launch_shape(nsk_ctx_t ctx, int variant, bool muladd, int k, pk_fn *fn_out, int *smem_out, int *team)
+static int pk_launch_shape(nsk_ctx_t ctx, int variant, bool muladd, int k, int nv, pk_fn *fn_out, int *smem_out, int *team)
 {
     const PkVariant &V = g_pkv[variant];
     int smem = 0;
-    pk_fn fn = pk_lookup(variant, muladd, &smem);
+    pk_fn fn = pk_lookup(variant, muladd, nv, &smem);
+    if (!fn) {
+        nsk_set_error(ctx, "packed path: no two-vector kernel for this tile geometry");
+        return NSK_ERR_UNSUPPORTED;
+    }
     NSK_REQUIRE(ctx, smem <= (int)ctx->prop.sharedMemPerBlockOptin, "packed kernel stage ring exceeds shared memory");
     NSK_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int per_sm = 0;
-    NSK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, (V.ncw + 3) * 32, smem));
+    NSK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, ((nv == 2 ? 4 : V.ncw) + 3) * 32, smem));
     if (ctx->opt.spmv_ctas_per_sm > 0) per_sm = std::min(per_sm, (int)ctx->opt.spmv_ctas_per_sm);
     const int resident = ctx->prop.multiProcessorCount * per_sm;
     *team = resident;  // all resident CTAs; the plan shares them out over the levels
@@ -979,7 +1011,7 @@ static int pk_launch_shape(nsk_ctx_t ctx, int variant, bool muladd, int k, pk_fn
     return NSK_OK;
 }
 
-static PkLevelPlan *pk_level_plan(nsk_csr_t A, PackedOp *op, int k, const int *level_rows, int resident, const char **why)
+static PkLevelPlan *pk_level_plan(nsk_csr_t A, PackedOp *op, int k, const int *level_rows, int resident, int nv, const char **why)
 {
     nsk_ctx_t ctx = A->ctx;
     const int team = resident / k;  // even share: the unit of the slack below
@@ -992,14 +1024,14 @@ static PkLevelPlan *pk_level_plan(nsk_csr_t A, PackedOp *op, int k, const int *l
     const int l2_pct = (int)ctx->opt.wave_l2_pct;  // part of the key: it sizes the window and decides refusals
     for (PkLevelPlan &p : op->plans)
         if (p.k == k && p.team == resident && p.level_rows == lr && p.lead_pct == lead_pct && p.bp_global == bp_global &&
-            p.w0_pct == w0_pct && p.interleave == interleave && p.l2_pct == l2_pct) {
+            p.w0_pct == w0_pct && p.interleave == interleave && p.l2_pct == l2_pct && p.nv == nv) {
             if (p.rejected) { *why = "wavefront window exceeds the L2 budget"; return nullptr; }
             return &p;
         }
     const int ntiles = op->ntiles;
     PkLevelPlan p;
     p.k = k; p.team = resident; p.lead_pct = lead_pct; p.level_rows = lr; p.bp_global = bp_global;
-    p.w0_pct = w0_pct; p.interleave = interleave; p.l2_pct = l2_pct;
+    p.w0_pct = w0_pct; p.interleave = interleave; p.l2_pct = l2_pct; p.nv = nv;
     // teams: `team * k` resident CTAs shared out with weight w0 for level 0 (it streams from HBM: longer fills, so
     // it needs more stages in flight for the same rate) and 100 for every other level
     {
@@ -1026,7 +1058,7 @@ static PkLevelPlan *pk_level_plan(nsk_csr_t A, PackedOp *op, int k, const int *l
         // i.e. hundreds of tiles at full rate).  The window that must stay in L2 is (k-1)*lead tiles of matrix
         // data plus the level vectors over it; by default the slack is whatever the L2 budget allows -- measured
         // on 256^3: time falls with the window until it reaches ~100 MB, then HBM re-reads set in.
-        const double tile_bytes = (double)op->blob_bytes / ntiles + 8.0 * op->t_rows * (k + 1);
+        const double tile_bytes = (double)op->blob_bytes / ntiles + 8.0 * op->t_rows * (k + 1) * nv;
         // budget: 70 % of L2 by default -- ncu (profiles/r01_ncu_packed_dram_traffic.txt): an 81 MB window costs the
         // compulsory 1.47 GB of HBM reads, a 101 MB one 4.9 GB (the level vectors and x runs share the cache)
         const double budget = (ctx->opt.wave_l2_pct > 0 ? (double)ctx->opt.wave_l2_pct : 70.0) / 100.0 *
@@ -1074,22 +1106,43 @@ static bool pk_aligned(const void *p) { return (reinterpret_cast<uintptr_t>(p) &
 
 // Returns NSK_ERR_UNSUPPORTED (and sets the context's error text) when the packed path does not apply; the
 // callers then run the CSR kernels.
+static int pk_run(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, const double *d_x2, double *const *d_levels2,
+                  nsk_mode mode, const int *level_rows, const double *dot_w, int dot_slot);
+
 int nsk_packed_run(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode, const int *level_rows,
                    const double *dot_w, int dot_slot)
 {
+    return pk_run(A, k, d_x, d_levels, nullptr, nullptr, mode, level_rows, dot_w, dot_slot);
+}
+
+// Two right-hand sides through ONE launch: levels[l] = A^(l+1) x and levels2[l] = A^(l+1) x2; every tile's blob is
+// streamed once for both (s-step Krylov methods need the powers of p and of r in the same outer step).
+int nsk_packed_run2(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, const double *d_x2,
+                    double *const *d_levels2, nsk_mode mode, const int *level_rows)
+{
+    return pk_run(A, k, d_x, d_levels, d_x2, d_levels2, mode, level_rows, nullptr, -1);
+}
+
+static int pk_run(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, const double *d_x2, double *const *d_levels2,
+                  nsk_mode mode, const int *level_rows, const double *dot_w, int dot_slot)
+{
     nsk_ctx_t ctx = A->ctx;
-    const int variant = pk_variant(A);
+    const int nv = d_x2 ? 2 : 1;
+    const int variant = nv == 2 && ctx->opt.packed_variant <= 0 && A->mean_row <= 16.0 ? PK_NV2_VARIANT : pk_variant(A);
     const PkVariant &V = g_pkv[variant];
-    if (!pk_aligned(d_x)) { nsk_set_error(ctx, "packed path: x is not 16-byte aligned"); return NSK_ERR_UNSUPPORTED; }
+    if (!pk_aligned(d_x) || (d_x2 && !pk_aligned(d_x2))) { nsk_set_error(ctx, "packed path: x is not 16-byte aligned"); return NSK_ERR_UNSUPPORTED; }
     for (int l = 0; l < k; l++)
-        if (!pk_aligned(d_levels[l])) { nsk_set_error(ctx, "packed path: output is not 16-byte aligned"); return NSK_ERR_UNSUPPORTED; }
+        if (!pk_aligned(d_levels[l]) || (d_levels2 && !pk_aligned(d_levels2[l]))) {
+            nsk_set_error(ctx, "packed path: output is not 16-byte aligned");
+            return NSK_ERR_UNSUPPORTED;
+        }
     PackedOp *op = pk_get(A, V);
     if (!op->ok) { nsk_set_error(ctx, "packed path not applicable: %s", op->why.c_str()); return NSK_ERR_UNSUPPORTED; }
     pk_fn fn; int smem = 0, team = 0;
-    NSK_TRY(pk_launch_shape(ctx, variant, mode == NSK_EXACT_MULADD, k, &fn, &smem, &team));
+    NSK_TRY(pk_launch_shape(ctx, variant, mode == NSK_EXACT_MULADD, k, nv, &fn, &smem, &team));
     if (team < k) { nsk_set_error(ctx, "packed path: fewer resident CTAs than levels"); return NSK_ERR_UNSUPPORTED; }
     const char *why = "";
-    PkLevelPlan *plan = pk_level_plan(A, op, k, level_rows, team, &why);
+    PkLevelPlan *plan = pk_level_plan(A, op, k, level_rows, team, nv, &why);
     if (!plan) { nsk_set_error(ctx, "packed matrix powers not applicable: %s", why); return NSK_ERR_UNSUPPORTED; }
     int maxcount = 0;
     for (int l = 0; l < k; l++) maxcount = std::max(maxcount, plan->count[l]);
@@ -1103,8 +1156,10 @@ int nsk_packed_run(nsk_csr_t A, int k, const double *d_x, double *const *d_level
         P.items[l] = l < k ? plan->d_items + plan->item_off[l] : nullptr;
         P.count[l] = l < k ? plan->count[l] : 0;
         P.levels[l] = l < k ? d_levels[l] : nullptr;
+        P.levels2[l] = l < k && d_levels2 ? d_levels2[l] : nullptr;
         P.level_rows[l] = l < k ? plan->level_rows[l] : 0;
     }
+    P.x2 = d_x2;
     P.tiles = op->d_tiles;
     P.blobs = op->d_blobs;
     P.counters = plan->d_counters;
@@ -1127,7 +1182,7 @@ int nsk_packed_run(nsk_csr_t A, int k, const double *d_x, double *const *d_level
     P.partials = ctx->d_partials;
     P.ticket = ctx->d_ticket;
     P.dot_out = dot_w ? ctx->d_scalars + dot_slot : nullptr;
-    fn<<<plan->grid, (V.ncw + 3) * 32, smem, ctx->stream>>>(P);
+    fn<<<plan->grid, ((nv == 2 ? 4 : V.ncw) + 3) * 32, smem, ctx->stream>>>(P);
     ctx->launches++;
     NSK_CUDA(ctx, cudaGetLastError());
     if (P.timing) {  // debugging aid: per-level averages of the stage cycle on stderr

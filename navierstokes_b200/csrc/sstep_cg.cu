@@ -5,9 +5,10 @@
 // restatement kept with the tests (oracle.scg, numpy) -- "parity unpinned" as far as the reference is concerned.
 //
 // Formulation (Carson/Demmel CA-CG, monomial basis).  One OUTER step advances s CG iterations:
-//   1. V = [p, A p, ..., A^s p | r, A r, ..., A^(s-1) r]          two matrix-powers calls (depth s and s-1):
-//                                                                 the operator is streamed from HBM once each, and
-//                                                                 a distributed slab exchanges ONE depth-s halo
+//   1. V = [p, A p, ..., A^s p | r, A r, ..., A^(s-1) r]          ONE two-vector matrix-powers call (depth s for both):
+//                                                                 every tile of the operator is streamed once for p
+//                                                                 and r together; a distributed slab exchanges one
+//                                                                 depth-s halo per vector
 //   2. G = V^T V   ((2s+1)^2, symmetric: 45 sums for s = 4)       one pass over the 2s+1 vectors (gram_kernel),
 //                                                                 ONE all-reduce per s iterations
 //   3. s inner iterations on (2s+1)-long coordinate vectors       one thread: alpha_j = r'Gr' / p'G(Bp'),
@@ -21,7 +22,8 @@
 
 #include "nsk_internal.h"
 
-int nsk_mpk_device(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode);  // mpk.cu
+int nsk_mpk_device2(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, const double *d_x2,
+                    double *const *d_levels2, nsk_mode mode);  // mpk.cu
 
 constexpr int SCG_MAXS = 4;               // 2s+1 <= 9 vectors per Gram pass
 constexpr int SCG_MAXM = 2 * SCG_MAXS + 1;
@@ -132,28 +134,29 @@ int nsk_scg_device(nsk_csr_t A, const double *d_b, double *d_x, double tol, int 
     const int m = 2 * s + 1;
     double *scal = ctx->d_scalars;
 
-    // workspace: p, r (local vectors), s levels of p, s-1 levels of r
+    // workspace: p, r (local vectors), s levels of p, s levels of r (the two-vector powers kernel runs both to depth s;
+    // A^s r is not part of the basis and simply not used)
     unsigned char *ws = nullptr;
     {
         void *vws = nullptr;  // grow-only staging slot of the context: repeated solves do not re-allocate 1.2 GB
-        if (nsk_stage(ctx, 6, vec_bytes * (size_t)(2 * s + 1), &vws) != NSK_OK) {
-            nsk_set_error(ctx, "s-step CG workspace (%d vectors of %zu bytes) does not fit", 2 * s + 1, vec_bytes);
+        if (nsk_stage(ctx, 6, vec_bytes * (size_t)(2 * s + 2), &vws) != NSK_OK) {
+            nsk_set_error(ctx, "s-step CG workspace (%d vectors of %zu bytes) does not fit", 2 * s + 2, vec_bytes);
             return NSK_ERR_ALLOC;
         }
         ws = reinterpret_cast<unsigned char *>(vws);
     }
     auto vec = [&](int i) { return reinterpret_cast<double *>(ws + vec_bytes * (size_t)i); };
     double *p = vec(0), *r = vec(1);
-    std::vector<double *> lvP(s), lvR(s > 1 ? s - 1 : 0);
+    std::vector<double *> lvP(s), lvR(s);
     for (int l = 0; l < s; l++) lvP[l] = vec(2 + l);
-    for (int l = 0; l + 1 < s; l++) lvR[l] = vec(2 + s + l);
+    for (int l = 0; l < s; l++) lvR[l] = vec(2 + s + l);
     int status = NSK_OK;
     auto fail = [&](int st) { cudaStreamSynchronize(ctx->stream); return st; };
 #define SCG_TRY(call) do { status = (call); if (status != NSK_OK) return fail(status); } while (0)
 #define SCG_CUDA(call) do { if ((call) != cudaSuccess) { nsk_set_error(ctx, "%s failed: %s", #call, cudaGetErrorString(cudaGetLastError())); return fail(NSK_ERR_CUDA); } } while (0)
 
     const size_t nb = sizeof(double) * (size_t)n;
-    SCG_CUDA(cudaMemsetAsync(ws, 0, vec_bytes * (size_t)(2 * s + 1), ctx->stream));
+    SCG_CUDA(cudaMemsetAsync(ws, 0, vec_bytes * (size_t)(2 * s + 2), ctx->stream));
     SCG_CUDA(cudaMemsetAsync(d_x, 0, nb, ctx->stream));
     SCG_CUDA(cudaMemcpyAsync(r, d_b, nb, cudaMemcpyDeviceToDevice, ctx->stream));
     SCG_CUDA(cudaMemcpyAsync(p, d_b, nb, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -186,8 +189,7 @@ int nsk_scg_device(nsk_csr_t A, const double *d_b, double *d_x, double tol, int 
     bool converged = false, broke = false;
     double rr = bb;
     while (done_iters < maxit && !converged && !broke) {
-        SCG_TRY(nsk_mpk_device(A, s, p, lvP.data(), NSK_EXACT_FMA));
-        if (s > 1) SCG_TRY(nsk_mpk_device(A, s - 1, r, lvR.data(), NSK_EXACT_FMA));
+        SCG_TRY(nsk_mpk_device2(A, s, p, lvP.data(), r, lvR.data(), NSK_EXACT_FMA));
         SCG_TRY(nsk_launch_gram(ctx, n, m, gram_ptrs, SG_G));
         SCG_TRY(nsk_comm_allreduce_slots(ctx, SG_G, m * (m + 1) / 2));
         scg_inner_kernel<<<1, 1, 0, ctx->stream>>>(scal, s, tol2, maxit);

@@ -629,3 +629,41 @@ def test_packed_fuzz_random_stencils(ctx, oracle_lib, seed, reset_options):
     assert_bits_equal(dA.mpk(3, x, mode=nsk.EXACT_MULADD)[2],
                       oracle_lib.spmv_muladd(A.ptrow, A.indcol, A.coef, oracle_lib.spmv_muladd(
                           A.ptrow, A.indcol, A.coef, oracle_lib.spmv_muladd(A.ptrow, A.indcol, A.coef, x))))
+
+
+# ---- several right-hand sides: two vectors per fused launch -------------------------------------------------------
+@pytest.mark.parametrize("gen,args", [("laplace3d_7pt", (40,)), ("laplace2d_5pt", (300,)), ("laplace3d_7pt", (64, 64, 20)),
+                                      ("fem_baij4", (6,)), ("random_csr", (4000, 5.0, 1))])
+def test_mpk_multi_bitwise(ctx, oracle_lib, gen, args, reset_options):
+    """nsk_mpk_multi: powers of 3 right-hand sides (one fused pair + one single) equal the oracle's bits per vector,
+    device-resident and host-pointer calls, for operators that take the two-vector kernel (short-row stencils), the
+    long-row geometry (vector by vector) and the CSR kernels (random pattern)."""
+    A = getattr(matgen, gen)(*args)
+    xs = [matgen.vec_uniform(A.n, seed=20 + v) for v in range(3)]
+    dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
+    for k in (1, 2, 4):
+        ref = [oracle_lib.mpk(A.ptrow, A.indcol, A.coef, k, x) for x in xs]
+        lv = dA.mpk_multi(k, [ctx.to_device(x) for x in xs])
+        for v in range(3):
+            for l in range(k):
+                assert_bits_equal(lv[v][l].to_host(), ref[v][l], f"{gen} k={k} vector {v} level {l}")
+        host = dA.mpk_multi(k, xs)
+        for v in range(3):
+            assert_bits_equal(host[v], ref[v], f"{gen} k={k} host vector {v}")
+
+
+def test_mpk_multi_pair_is_one_launch_and_muladd(ctx, oracle_lib, reset_options):
+    A = matgen.laplace3d_7pt(48)
+    dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
+    xs = [matgen.vec_uniform(A.n, seed=3), matgen.vec_sin(A.n)]
+    dxs = [ctx.to_device(x) for x in xs]
+    lv = dA.mpk_multi(4, dxs)
+    before = ctx.launch_count
+    dA.mpk_multi(4, dxs, lv)
+    assert ctx.launch_count - before == 1  # both vectors, four levels, one launch
+    lm = dA.mpk_multi(3, dxs, mode=nsk.EXACT_MULADD)
+    for v in range(2):
+        y = xs[v]
+        for l in range(3):
+            y = oracle_lib.spmv_muladd(A.ptrow, A.indcol, A.coef, y)
+            assert_bits_equal(lm[v][l].to_host(), y, f"muladd vector {v} level {l}")
