@@ -55,6 +55,22 @@ void SpM2V_CSR(double *z, double *y, double *x, csrmatrix &A, std::vector<int> &
 void SpM2V_CSR_OPT(double *z, double *y, double *x, csrmatrix &A, std::vector<int> &ptrowend1);         // mpk/SpM2V.cpp:137
 void SpM2V_CSR_AVX2(double *z, double *y, double *x, csrmatrix &A, std::vector<int> &ptrowend1);        // mpk/SpM2V.cpp:279
 
+// k = 2, 3, 4 with the signatures of mpk/SpMVmulti0.cpp (:44, :65, :132, :191); the nested first-touch schedules are
+// accepted and ignored.  These are the x87 / no-fma flavours in the reference: multiply-add chain here.
+void SpM2V0(double *z, double *y, double *x, csrmatrix &A, std::vector<int> &ptrowend1);
+void SpM2V(double *z, double *y, double *x, csrmatrix &A, std::vector<int> &ptrowend1);
+void SpM3V(double *w, double *z, double *y, double *x, csrmatrix &A, std::vector<int> &ptrowend1,
+           std::vector<std::vector<int> > &ptrowend2);
+void SpM4V(double *v, double *w, double *z, double *y, double *x, csrmatrix &A, std::vector<int> &ptrowend1,
+           std::vector<std::vector<int> > &ptrowend2, std::vector<std::vector<std::vector<int> > > &ptrowend3);
+
+// Fused A^2 x on the block operator (mpk/SpM2V.cpp:28, :376, :475, :567, :675).
+void Generate1stlayer_BCSR4(std::vector<int> &ptrowendB, const bcsr4x4_matrix &A);
+void SpM2V_BCSR(double *z, double *y, double *x, bcsr4x4_matrix &A, std::vector<int> &ptrowendB);
+void SpM2V_BCSR_OPT(double *z, double *y, double *x, bcsr4x4_matrix &A, std::vector<int> &ptrowendB);
+void SpM2V_BCSR_FMA(double *z, double *y, double *x, bcsr4x4_matrix &A, std::vector<int> &ptrowendB);
+void SpM2V_BCSR_AVX2(double *z, double *y, double *x, bcsr4x4_matrix &A, std::vector<int> &ptrowendB);
+
 // Shim housekeeping (not in the reference): drop every cached device operator / the GPU context.
 extern "C" void nsk_shim_reset(void);
 

@@ -93,6 +93,22 @@ void spm2v(double *z, double *y, const double *x, csrmatrix &A, nsk_mode mode)
     if (s != NSK_OK) die("nsk_mpk", s);
 }
 
+void spmkv(int k, double *const *levels, const double *x, csrmatrix &A, nsk_mode mode)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    int s = nsk_mpk(device_csr(A), k, x, levels, mode, NSK_HOST);
+    if (s != NSK_OK) die("nsk_mpk", s);
+}
+
+void spm2v_b(double *z, double *y, const double *x, const bcsr4x4_matrix &B, nsk_mode mode)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    nsk_bcsr4_t h = device_bcsr(B);
+    int s = nsk_spmv_bcsr4(h, x, y, mode, NSK_HOST);
+    if (s == NSK_OK) s = nsk_spmv_bcsr4(h, y, z, mode, NSK_HOST);
+    if (s != NSK_OK) die("nsk_spmv_bcsr4", s);
+}
+
 }  // namespace
 
 void SpMV_CSR(double *y, double *x, csrmatrix &A) { spmv(y, x, A, NSK_EXACT_MULADD); }
@@ -123,6 +139,40 @@ void Generate1stlayer(std::vector<int> &ptrowend1, csrmatrix &A)
 void SpM2V_CSR(double *z, double *y, double *x, csrmatrix &A, std::vector<int> &) { spm2v(z, y, x, A, NSK_EXACT_MULADD); }
 void SpM2V_CSR_OPT(double *z, double *y, double *x, csrmatrix &A, std::vector<int> &) { spm2v(z, y, x, A, NSK_EXACT_FMA); }
 void SpM2V_CSR_AVX2(double *z, double *y, double *x, csrmatrix &A, std::vector<int> &) { spm2v(z, y, x, A, NSK_FAST); }
+
+// ---- k = 2, 3, 4 with the names and signatures of mpk/SpMVmulti0.cpp (:44, :65, :132, :191).  The nested
+// first-touch schedules are accepted and ignored: the result -- every level of A^k x -- does not depend on them.
+void SpM2V0(double *z, double *y, double *x, csrmatrix &A, std::vector<int> &) { spm2v(z, y, x, A, NSK_EXACT_MULADD); }
+void SpM2V(double *z, double *y, double *x, csrmatrix &A, std::vector<int> &) { spm2v(z, y, x, A, NSK_EXACT_MULADD); }
+void SpM3V(double *w, double *z, double *y, double *x, csrmatrix &A, std::vector<int> &, std::vector<std::vector<int> > &)
+{
+    double *levels[3] = {y, z, w};
+    spmkv(3, levels, x, A, NSK_EXACT_MULADD);
+}
+void SpM4V(double *v, double *w, double *z, double *y, double *x, csrmatrix &A, std::vector<int> &,
+           std::vector<std::vector<int> > &, std::vector<std::vector<std::vector<int> > > &)
+{
+    double *levels[4] = {y, z, w, v};
+    spmkv(4, levels, x, A, NSK_EXACT_MULADD);
+}
+
+// ---- fused A^2 x on the block operator (mpk/SpM2V.cpp:28, :376, :475, :567, :675): two block products; the schedule
+// builder keeps the reference's contract (end of block row bj the first time bj is met, its start afterwards).
+void Generate1stlayer_BCSR4(std::vector<int> &ptrowendB, const bcsr4x4_matrix &A)
+{
+    std::vector<char> seen(A.nrows > 0 ? A.nrows : 1, 0);
+    ptrowendB.assign(A.indcol.size(), 0);
+    for (int bi = 0; bi < A.nrows; bi++)
+        for (int m = A.ptrow[bi]; m < A.ptrow[bi + 1]; m++) {
+            const int bj = A.indcol[m];
+            ptrowendB[m] = seen[bj] ? A.ptrow[bj] : A.ptrow[bj + 1];
+            seen[bj] = 1;
+        }
+}
+void SpM2V_BCSR(double *z, double *y, double *x, bcsr4x4_matrix &A, std::vector<int> &) { spm2v_b(z, y, x, A, NSK_EXACT_MULADD); }
+void SpM2V_BCSR_OPT(double *z, double *y, double *x, bcsr4x4_matrix &A, std::vector<int> &) { spm2v_b(z, y, x, A, NSK_EXACT_FMA); }
+void SpM2V_BCSR_FMA(double *z, double *y, double *x, bcsr4x4_matrix &A, std::vector<int> &) { spm2v_b(z, y, x, A, NSK_EXACT_FMA); }
+void SpM2V_BCSR_AVX2(double *z, double *y, double *x, bcsr4x4_matrix &A, std::vector<int> &) { spm2v_b(z, y, x, A, NSK_EXACT_FMA); }
 
 extern "C" void nsk_shim_reset(void)
 {

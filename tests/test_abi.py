@@ -95,3 +95,40 @@ def test_generators_shapes():
     # full-size row counts of the BASELINE configs (formulas only, nothing allocated)
     assert 5 * 4096**2 - 4 * 4096 == 83_869_696
     assert 7 * 256**3 - 6 * 256**2 == 117_047_296
+
+
+def test_shim_exports_the_reference_mangled_symbols():
+    """Link-time drop-in: every kernel symbol the reference's own objects define for this path --
+    compiled here from /root/reference where available -- is exported by libnsk_spmvshim.so under the same mangled
+    name; on a box without the reference sources the expected list is the one recorded below."""
+    import shutil
+    import subprocess
+    from navierstokes_b200 import _lib
+    shim = _lib.LIB_PATH.parent / "libnsk_spmvshim.so"
+    assert shim.exists(), "build the shim first (python -m navierstokes_b200.build)"
+    if shutil.which("nm") is None:
+        pytest.skip("nm not installed")
+    have = set(subprocess.run(["nm", "-D", "--defined-only", str(shim)], capture_output=True, text=True).stdout.split())
+    expected = [
+        "_Z8SpMV_CSRPdS_R9csrmatrix", "_Z12SpMV_CSR_OPTPdS_R9csrmatrix", "_Z12SpMV_CSR_FMAPdS_R9csrmatrix",
+        "_Z13SpMV_CSR_AVX2PdS_R9csrmatrix",
+        "_Z9SpMV_BCSRPdPKdRK14bcsr4x4_matrix", "_Z13SpMV_BCSR_OPTPdPKdRK14bcsr4x4_matrix",
+        "_Z13SpMV_BCSR_FMAPdPKdRK14bcsr4x4_matrix", "_Z14SpMV_BCSR_AVX2PdPKdRK14bcsr4x4_matrix",
+        "_Z16Generate1stlayerRSt6vectorIiSaIiEER9csrmatrix",
+        "_Z9SpM2V_CSRPdS_S_R9csrmatrixRSt6vectorIiSaIiEE", "_Z13SpM2V_CSR_OPTPdS_S_R9csrmatrixRSt6vectorIiSaIiEE",
+        "_Z14SpM2V_CSR_AVX2PdS_S_R9csrmatrixRSt6vectorIiSaIiEE",
+        "_Z22Generate1stlayer_BCSR4RSt6vectorIiSaIiEERK14bcsr4x4_matrix",
+        "_Z10SpM2V_BCSRPdS_S_R14bcsr4x4_matrixRSt6vectorIiSaIiEE", "_Z14SpM2V_BCSR_OPTPdS_S_R14bcsr4x4_matrixRSt6vectorIiSaIiEE",
+        "_Z14SpM2V_BCSR_FMAPdS_S_R14bcsr4x4_matrixRSt6vectorIiSaIiEE", "_Z15SpM2V_BCSR_AVX2PdS_S_R14bcsr4x4_matrixRSt6vectorIiSaIiEE",
+    ]
+    missing = [s for s in expected if s not in have]
+    assert not missing, missing
+    # cross-check the recorded names against the reference's own objects when they were compiled here
+    ref_dir = ROOT / "oracle" / "_ref"
+    for obj, names in (("SpMV.o", expected[:8]), ("SpM2V.o", expected[8:])):
+        o = ref_dir / obj
+        if not o.exists():
+            continue
+        defined = set(subprocess.run(["nm", "--defined-only", str(o)], capture_output=True, text=True).stdout.split())
+        for s in names:
+            assert s in defined, f"{s} is not a symbol of the reference's {obj}: the recorded list is stale"
