@@ -187,7 +187,7 @@ NSK_API int nsk_mpk(nsk_csr_t A, int k, const double *x, double *const *levels, 
     // host pointers: owned parts in, owned parts out; level scratch is one local vector per level
     const int n_out = nsk_csr_owned_rows(A);
     const size_t nb = sizeof(double) * (size_t)n_out;
-    const size_t ld = (size_t)A->n_cols;
+    const size_t ld = ((size_t)A->n_cols + 1) & ~(size_t)1;  // even: every level starts 16-byte aligned
     void *dx, *dl;
     NSK_TRY(nsk_stage(ctx, 0, sizeof(double) * ld, &dx));
     NSK_TRY(nsk_stage(ctx, 1, sizeof(double) * ld * (size_t)k, &dl));

@@ -57,7 +57,9 @@ struct PkTile {                   // 96 bytes; words 0..23 are fetched one per l
     long long blob_off;           // w0,1   bytes from the blob base, 16-byte aligned
     int blob_bytes;               // w2     multiple of 16
     int nseg;                     // w3
-    int row0, nrows, xlen, pad;   // w4..7  xlen: total doubles of all runs (each run a multiple of 2)
+    int row0, nrows, xlen, tail;  // w4..7  xlen: total doubles of all runs (each run a multiple of 2); tail: 1 + the x
+                                  //        buffer slot of column n_cols-1 when n_cols is odd and the tile needs it
+                                  //        (bulk copies move 16-byte granules: that one element is copied by hand)
     int seg_start[PK_MAXSEG];     // w8..15 first column of the run (even)
     int seg_lenoff[PK_MAXSEG];    // w16..23 length | offset in the stage's x buffer << 16 (doubles)
 };
@@ -79,6 +81,7 @@ struct PkParams {
     int *counters;          // [k][ngroups], zeroed before the launch (unused for k = 1)
     const int *group_size;  // [k][ngroups]
     int ngroups;
+    int n_cols;             // length of x / of the level vectors
     const double *x;
     double *levels[NSK_MAX_K];
     const double *x2;            // second right-hand side (NV = 2 kernels): same operator, same schedule, its own
@@ -325,7 +328,15 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
             const int xlen = __shfl_sync(0xffffffffu, cw, 6);
             const int start = __shfl_sync(0xffffffffu, cw, 8 + (lane & 7));
             const int lenoff = __shfl_sync(0xffffffffu, cw, 16 + (lane & 7));
-            if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)xlen * 8u * NV);
+            const int tail = __shfl_sync(0xffffffffu, cw, 7);
+            if (lane == 0) {
+                if (tail) {  // odd vector length: the last element cannot ride a 16-byte bulk copy
+                    double *xs = reinterpret_cast<double *>(smem + (size_t)s * STAGE_BYTES + BLOB_CAP);
+                    xs[tail - 1] = ld_cg_f64(src + P.n_cols - 1);
+                    if (NV == 2) xs[XCAP + tail - 1] = ld_cg_f64(src2 + P.n_cols - 1);
+                }
+                mbar_arrive_expect_tx(&full[s], (uint32_t)xlen * 8u * NV);  // release: orders the stores above too
+            }
             __syncwarp();
             if ((lane & 7) < nseg && (lane >> 3) < NV) {  // lanes 0..7: runs of the first vector, 8..15: of the second
                 const int len = lenoff & 0xffff, xoff = (lenoff >> 16) & 0xffff;
@@ -582,19 +593,30 @@ static bool pk_segments(std::vector<int> &cols, int n_cols, int xcap, PkTile &t)
     constexpr int GAP = 8;
     t.nseg = 0;
     t.xlen = 0;
+    t.tail = 0;
     for (int s = 0; s < PK_MAXSEG; s++) { t.seg_start[s] = 0; t.seg_lenoff[s] = 0; }
     if (cols.empty()) return true;
     std::sort(cols.begin(), cols.end());
     int s0 = cols[0] & ~1, s1 = cols[0] + 1;  // current run [s0, s1)
     auto flush = [&]() {
         int e = (s1 + 1) & ~1;
-        if (e > n_cols) e = n_cols;  // n_cols is even (checked by the caller)
+        bool tail = false;
+        if (e > n_cols) {  // only possible when n_cols is odd and the run reaches column n_cols - 1
+            e = n_cols - 1;   // even: the run stops one short, the last column gets its own slot after it
+            tail = true;
+        }
         const int len = e - s0;
-        if (t.nseg >= PK_MAXSEG || t.xlen + len > xcap || len > 0xffff || t.xlen > 0xffff) return false;
-        t.seg_start[t.nseg] = s0;
-        t.seg_lenoff[t.nseg] = len | (t.xlen << 16);
-        t.nseg++;
-        t.xlen += len;
+        if (len > 0) {
+            if (t.nseg >= PK_MAXSEG || t.xlen + len > xcap || len > 0xffff || t.xlen > 0xffff) return false;
+            t.seg_start[t.nseg] = s0;
+            t.seg_lenoff[t.nseg] = len | (t.xlen << 16);
+            t.nseg++;
+            t.xlen += len;
+        }
+        if (tail) {
+            if (t.xlen + 2 > xcap) return false;
+            t.tail = t.xlen + 1;  // slot t.xlen, stored + 1 (0 = none); the bulk copies still move t.xlen doubles
+        }
         return true;
     };
     for (size_t i = 1; i < cols.size(); i++) {
@@ -621,7 +643,6 @@ static std::string pk_pack_host(int n, int n_cols, int64_t nnz, const int *ptrow
                                 const std::vector<int> &breaks, int t_rows, int blob_cap, int xcap, PackedHost &out)
 {
     if (n == 0 || nnz == 0) return "empty operator";
-    if (n_cols & 1) return "odd number of columns (bulk copies move 16-byte granules)";
     // 1. tiles: up to t_rows consecutive rows, never across a break, blob within the stage
     std::vector<nsk_tile> &tiles = out.tiles;
     std::vector<int> widths;
@@ -671,7 +692,7 @@ static std::string pk_pack_host(int n, int n_cols, int64_t nnz, const int *ptrow
                 const int width = widths[t], rp = pk_round_up(tl.nrows, 32);
                 pt.blob_off = (long long)off[t];
                 pt.blob_bytes = pk_blob_bytes(tl.nrows, width);
-                pt.row0 = tl.row0; pt.nrows = tl.nrows; pt.pad = 0;
+                pt.row0 = tl.row0; pt.nrows = tl.nrows;
                 unsigned char *b = blobs.data() + off[t];
                 int *hdr = reinterpret_cast<int *>(b);
                 const int off_lens = PKH_WORDS * 4, off_lcol = off_lens + 2 * rp, off_val = off_lcol + 2 * width * rp;
@@ -692,7 +713,12 @@ static std::string pk_pack_host(int n, int n_cols, int64_t nnz, const int *ptrow
                     int s = 0;
                     for (int j = p; j < q; j++) {
                         const int cidx = indcol[j];
-                        if (cidx < sstart[s] || cidx >= send[s]) {  // columns ascend within a row in practice: resume, else rescan
+                        if (pt.tail && cidx == n_cols - 1) {  // the hand-copied last element of an odd-length vector
+                            lcol[(size_t)(j - p) * rp + r] = (unsigned short)(pt.tail - 1);
+                            val[(size_t)(j - p) * rp + r] = coef[j];
+                            continue;
+                        }
+                        if (s >= pt.nseg || cidx < sstart[s] || cidx >= send[s]) {  // columns ascend within a row in practice: resume, else rescan
                             s = 0;
                             while (s < pt.nseg && !(cidx >= sstart[s] && cidx < send[s])) s++;
                         }
@@ -728,7 +754,6 @@ static PackedOp *pk_get(nsk_csr_t A, const PkVariant &V)
     const int n = A->n;
     const std::vector<int> &ptrow = nsk_csr_host_ptrow(A);
     if (n == 0 || A->nnz == 0) { op->why = "empty operator"; return op; }
-    if (A->n_cols & 1) { op->why = "odd number of columns (bulk copies move 16-byte granules)"; return op; }
     if ((int)ptrow.size() != n + 1) { op->why = "host row pointers missing"; return op; }
     // cheap refusals first (row lengths only), then the operator's entries: the caller's host arrays are gone, read
     // them back once
@@ -932,7 +957,8 @@ NSK_API int nsk_pack_host_expand(void *handle, int *ptrow, int *indcol, double *
             for (int e = 0; e < (int)lens[r]; e++) {
                 const int lc = lcol[(size_t)e * rp + r];
                 int g = -1;
-                for (int s = 0; s < pt.nseg; s++) {
+                if (pt.tail && lc == pt.tail - 1) g = h->n_cols - 1;
+                for (int s = 0; s < pt.nseg && g < 0; s++) {
                     const int len = pt.seg_lenoff[s] & 0xffff, xoff = (pt.seg_lenoff[s] >> 16) & 0xffff;
                     if (lc >= xoff && lc < xoff + len) { g = pt.seg_start[s] + (lc - xoff); break; }
                 }
@@ -973,6 +999,7 @@ NSK_API long long nsk_pack_host_simulate(void *handle, int k, int lead_slack_til
             if (last >= h->n) last = h->n - 1;
             mx = std::max(mx, last);
         }
+        if (pt.tail) mx = std::max(mx, std::min(h->n_cols, h->n) - 1);
         if (mx < 0) mx = pt.row0;
         const int tmax = (int)(std::upper_bound(row0s.begin(), row0s.end(), mx) - row0s.begin()) - 1;
         ghi[t] = std::max(0, tmax) / WF_GROUP;
@@ -1174,6 +1201,7 @@ static int pk_run(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
     P.counters = plan->d_counters;
     P.group_size = plan->d_group_size;
     P.ngroups = plan->ngroups;
+    P.n_cols = A->n_cols;
     P.x = d_x;
     P.k = k;
     for (int l = 0; l < NSK_MAX_K; l++) P.team[l] = l < k ? plan->teams[l] : 0;

@@ -345,7 +345,8 @@ def test_fused_csr_kernels_on_longer_rows(ctx, oracle_lib, strategy, reset_optio
 
 # ---- packed format: SpMV and matrix powers with x runs staged in shared memory ------------------------
 PACKED_OPS = [("laplace3d_7pt", (40,)), ("laplace2d_5pt", (300,)), ("laplace3d_7pt", (64, 64, 20)),
-              ("laplace2d_5pt", (1000, 37)), ("laplace3d_7pt", (34, 10, 50))]
+              ("laplace2d_5pt", (1000, 37)), ("laplace3d_7pt", (34, 10, 50)), ("laplace3d_7pt", (33, 7, 5)),
+              ("laplace2d_5pt", (255, 3))]
 
 
 @pytest.mark.parametrize("variant", list(range(1, 15)))
@@ -423,7 +424,7 @@ def test_packed_repeated_calls_are_stable(ctx, reset_options):
 
 def test_packed_banded_ragged_and_refusals(ctx, oracle_lib, reset_options):
     """A banded operator with mildly ragged / empty rows whose tiles need few runs packs; a Poisson-ragged banded
-    operator, a random operator and one with an odd column count do not -- the CSR kernels run instead, same bits."""
+    operator, a random operator and one with a random operator do not -- the CSR kernels run instead, same bits; an odd-sized operator packs too."""
     ctx.set_option("spmv_kernel", 3)
     ctx.set_option("mpk_kernel", 4)
     R = matgen.random_banded_csr(20000, 150, 5.0, seed=4, empty_rows=True)
@@ -443,11 +444,13 @@ def test_packed_banded_ragged_and_refusals(ctx, oracle_lib, reset_options):
     assert dB.packed_bytes == 0
     assert_bits_equal(dB.spmv(xb), oracle_lib.spmv(B.ptrow, B.indcol, B.coef, xb))
     assert_bits_equal(dB.mpk(3, xb), oracle_lib.mpk(B.ptrow, B.indcol, B.coef, 3, xb))
-    C = matgen.laplace3d_7pt(11, 9, 7)  # 693 rows: odd
+    C = matgen.laplace3d_7pt(11, 9, 7)  # 693 rows: odd -- the last element of every vector is copied by hand
     xc = matgen.vec_uniform(C.n)
     dC = nsk.CsrMatrix(ctx, C.ptrow, C.indcol, C.coef)
-    assert dC.packed_bytes == 0
+    assert dC.packed_bytes > 0
+    assert_bits_equal(dC.spmv(xc), oracle_lib.spmv(C.ptrow, C.indcol, C.coef, xc))
     assert_bits_equal(dC.mpk(3, xc), oracle_lib.mpk(C.ptrow, C.indcol, C.coef, 3, xc))
+    assert ctx.query("last_mpk_strategy") == 4
 
 
 # ---- distributed operator, degenerate world of one rank (the N > 1 path is covered by the gloo tests
@@ -614,8 +617,6 @@ def test_packed_fuzz_random_stencils(ctx, oracle_lib, seed, reset_options):
     fused powers in both exact flavours; whatever does not pack still runs (CSR kernels) with the same bits."""
     rng = np.random.default_rng(1000 + seed)
     nx, ny, nz = int(rng.integers(5, 70)), int(rng.integers(3, 40)), int(rng.integers(2, 24))
-    if (nx * ny * nz) % 2:
-        nx += 1
     A = matgen.random_stencil3d(nx, ny, nz, seed=seed, max_points=int(rng.integers(3, 14)), drop=float(rng.uniform(0, 0.2)))
     x = matgen.vec_uniform(A.n, seed=seed + 50)
     dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
