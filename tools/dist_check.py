@@ -29,7 +29,8 @@ def main():
     import oracle
     lib = oracle.lib
     ctx = nsk.Context(local)
-    nx, ny, nz, K = 48, 40, 24 * world, 4
+    odd = "--odd" in sys.argv  # odd plane size: odd local vector lengths on every rank
+    nx, ny, nz, K = (47, 39, 24 * world + 1, 4) if odd else (48, 40, 24 * world, 4)
     A = matgen.laplace3d_7pt(nx, ny, nz)
     x = matgen.vec_uniform(A.n, seed=21)
     ref = lib.mpk(A.ptrow, A.indcol, A.coef, K, x)
