@@ -89,6 +89,9 @@ NSK_API int nsk_ctx_destroy(nsk_ctx_t c)
     cudaFree(c->d_scalars);
     cudaFreeHost(c->h_scalars);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (int i = 0; i < NSK_MAX_K; i++)
+        if (c->copy_event[i]) cudaEventDestroy(c->copy_event[i]);
     delete c;
     return NSK_OK;
 }
@@ -139,6 +142,7 @@ NSK_API int nsk_ctx_set_option(nsk_ctx_t c, const char *name, int64_t v)
     else if (!strcmp(name, "pipe_w0_pct")) c->opt.pipe_w0_pct = v;
     else if (!strcmp(name, "pk_timing")) c->opt.pk_timing = v;
     else if (!strcmp(name, "pk_flags")) c->opt.pk_flags = v;
+    else if (!strcmp(name, "host_overlap")) c->opt.host_overlap = v;
     else if (!strcmp(name, "stream_exact_kind")) c->opt.stream_exact_kind = v;
     else if (!strcmp(name, "pipe_interleave")) c->opt.pipe_interleave = v;
     else {

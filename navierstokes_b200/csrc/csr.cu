@@ -194,6 +194,31 @@ NSK_API int nsk_mpk(nsk_csr_t A, int k, const double *x, double *const *levels, 
     NSK_CUDA(ctx, cudaMemcpyAsync(dx, x, nb, cudaMemcpyHostToDevice, ctx->stream));
     double *dlev[NSK_MAX_K];
     for (int l = 0; l < k; l++) dlev[l] = (double *)dl + (size_t)l * ld;
+    if (A->dist == nullptr && k > 1 && ctx->opt.mpk_kernel == 0 && ctx->opt.host_overlap) {
+        // Host-pointer call on one GPU: PCIe is the bound (k vectors out at ~57 GB/s dwarf the products), so the levels are
+        // produced one product at a time and each is copied out on a second stream while the next ones are computed --
+        // the first copy starts after one product instead of after all k (measured on 256^3, k = 4: 12.5 -> 12.0 ms).
+        if (!ctx->copy_stream) NSK_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        const double *src = (const double *)dx;
+        for (int l = 0; l < k; l++) {
+            if (!ctx->copy_event[l]) NSK_CUDA(ctx, cudaEventCreateWithFlags(&ctx->copy_event[l], cudaEventDisableTiming));
+            nsk_spmv_args a;
+            a.x = src;
+            a.y = dlev[l];
+            a.row_begin = 0;
+            a.row_end = A->n;
+            a.mode = mode;
+            NSK_TRY(nsk_launch_spmv(A, a));
+            NSK_CUDA(ctx, cudaEventRecord(ctx->copy_event[l], ctx->stream));
+            NSK_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_event[l], 0));
+            NSK_CUDA(ctx, cudaMemcpyAsync(levels[l], dlev[l], nb, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            src = dlev[l];
+        }
+        ctx->last_mpk = 1;
+        NSK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        NSK_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+        return NSK_OK;
+    }
     NSK_TRY(nsk_mpk_device(A, k, (const double *)dx, dlev, mode));
     for (int l = 0; l < k; l++)
         NSK_CUDA(ctx, cudaMemcpyAsync(levels[l], dlev[l], nb, cudaMemcpyDeviceToHost, ctx->stream));

@@ -48,6 +48,7 @@ struct nsk_options {
     int64_t mpk_kernel = 0;       // 0 auto (4 if the operator packs, else 1), 1 = k separate products, 2 = L2 wavefront,
                                   // 3 = level pipeline on CSR, 4 = level pipeline on the packed format
     int64_t pipe_variant = 0;     // 0 default, else 1 + index into the level-pipeline kernel table
+    int64_t host_overlap = 1;     // host-pointer powers calls: copy level l out while level l+1.. are computed
     int64_t pk_flags = 1;         // packed kernel switches (see PkParams::flags); default 1: evict-first / streaming hints
     int64_t pk_timing = 0;        // 1: packed kernel records its stage cycle and prints per-level averages (debug)
     int64_t pipe_w0_pct = 0;      // share weight of level 0's team relative to 100 for every other level; 0 = default
@@ -66,6 +67,8 @@ struct nsk_ctx_s {
     int device = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // device->host copies of host-pointer calls, overlapped with later products
+    cudaEvent_t copy_event[NSK_MAX_K] = {};  // (created on first use)
     cudaDeviceProp prop{};
     uint64_t launches = 0;
     int last_spmv = 0;  // kernel family of the last product: 1 scalar, 2 stream (CSR), 3 packed

@@ -399,6 +399,7 @@ def test_packed_long_rows_fem_operator(ctx, oracle_lib, reset_options):
     assert_bits_equal(dA.spmv(x), oracle_lib.spmv(A.ptrow, A.indcol, A.coef, x))
     assert ctx.query("last_spmv_kernel") == 3
     assert_bits_equal(dA.spmv(x, mode=nsk.EXACT_MULADD), oracle_lib.spmv_muladd(A.ptrow, A.indcol, A.coef, x))
+    ctx.set_option("mpk_kernel", 4)
     for k in (2, 3):
         assert_bits_equal(dA.mpk(k, x), oracle_lib.mpk(A.ptrow, A.indcol, A.coef, k, x), f"k={k}")
         assert ctx.query("last_mpk_strategy") == 4
@@ -625,8 +626,10 @@ def test_packed_fuzz_random_stencils(ctx, oracle_lib, seed, reset_options):
     assert_bits_equal(dA.spmv(x), ref[0], f"grid {nx}x{ny}x{nz} packed={packed}")
     assert ctx.query("last_spmv_kernel") == (3 if packed else 2)
     ctx.set_option("wave_l2_pct", 1000)
-    assert_bits_equal(dA.mpk(4, x), ref, f"grid {nx}x{ny}x{nz} packed={packed} k=4")
+    dlv = dA.mpk(4, ctx.to_device(x), [ctx.empty(A.n) for _ in range(4)])  # device-resident: the fused path
     assert ctx.query("last_mpk_strategy") == (4 if packed else 1)
+    assert_bits_equal(np.stack([l.to_host() for l in dlv]), ref, f"grid {nx}x{ny}x{nz} packed={packed} k=4")
+    assert_bits_equal(dA.mpk(4, x), ref, "host-pointer call (levels copied out while the next ones are computed)")
     assert_bits_equal(dA.mpk(3, x, mode=nsk.EXACT_MULADD)[2],
                       oracle_lib.spmv_muladd(A.ptrow, A.indcol, A.coef, oracle_lib.spmv_muladd(
                           A.ptrow, A.indcol, A.coef, oracle_lib.spmv_muladd(A.ptrow, A.indcol, A.coef, x))))
