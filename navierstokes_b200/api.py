@@ -517,12 +517,36 @@ def SpMV_BCSR_AVX2(y, x, A: bcsr4x4_matrix):
     A.gpu().spmv(x, _out(y, 4 * A.nrows), EXACT_FMA)
 
 
-def SpM2V_BCSR_OPT(z, y, x, A: bcsr4x4_matrix, ptrowend1=None):
-    """mpk/SpM2V.cpp:452 -- y = A x, z = A y on the block operator (two products; the reference's first-touch
-    schedule only changes the order in which rows of y are produced, not their values)."""
+def _spm2v_bcsr(z, y, x, A: bcsr4x4_matrix, mode):
     g = A.gpu()
-    g.spmv(x, _out(y, 4 * A.nrows), EXACT_FMA)
-    g.spmv(y, _out(z, 4 * A.nrows), EXACT_FMA)
+    g.spmv(x, _out(y, 4 * A.nrows), mode)
+    g.spmv(y, _out(z, 4 * A.nrows), mode)
+
+
+def SpM2V_BCSR(z, y, x, A: bcsr4x4_matrix, ptrowendB=None):
+    """mpk/SpM2V.cpp:376 (x87 in the reference) -> multiply-add chain."""
+    _spm2v_bcsr(z, y, x, A, EXACT_MULADD)
+
+
+def SpM2V_BCSR_OPT(z, y, x, A: bcsr4x4_matrix, ptrowendB=None):
+    """mpk/SpM2V.cpp:475 -- y = A x, z = A y on the block operator (two products; the reference's first-touch
+    schedule only changes the order in which rows of y are produced, not their values)."""
+    _spm2v_bcsr(z, y, x, A, EXACT_FMA)
+
+
+def SpM2V_BCSR_FMA(z, y, x, A: bcsr4x4_matrix, ptrowendB=None):
+    """mpk/SpM2V.cpp:567."""
+    _spm2v_bcsr(z, y, x, A, EXACT_FMA)
+
+
+def SpM2V_BCSR_AVX2(z, y, x, A: bcsr4x4_matrix, ptrowendB=None):
+    """mpk/SpM2V.cpp:675: lane i of the AVX2 kernel runs row 4*bi+i's (block, j) fma chain."""
+    _spm2v_bcsr(z, y, x, A, EXACT_FMA)
+
+
+def Generate1stlayer_BCSR4(ptrowendB, A: bcsr4x4_matrix):
+    """mpk/SpM2V.cpp:28-46: not needed by the GPU kernels; kept so drivers written against the reference run."""
+    return None
 
 
 # ---- ingest (host only): the reference's converters and its Matrix Market reader ------------------------------
@@ -611,6 +635,16 @@ def SpM2V_CSR_OPT(z, y, x, A: csrmatrix, ptrowend1=None):
 def SpM2V_CSR_AVX2(z, y, x, A: csrmatrix, ptrowend1=None):
     """mpk/SpM2V.cpp:279 -> fast mode."""
     _spmkv([y, z], x, A, FAST)
+
+
+def SpM2V0(z, y, x, A: csrmatrix, ptrowend1=None):
+    """mpk/SpMVmulti0.cpp:44 (no-fma in the reference) -> multiply-add chain."""
+    _spmkv([y, z], x, A, EXACT_MULADD)
+
+
+def SpM2V(z, y, x, A: csrmatrix, ptrowend1=None):
+    """mpk/SpMVmulti0.cpp:65 (unrolled variant of SpM2V0)."""
+    _spmkv([y, z], x, A, EXACT_MULADD)
 
 
 def SpM3V(w, z, y, x, A: csrmatrix, ptrowend1=None, ptrowend2=None):

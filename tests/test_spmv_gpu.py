@@ -509,9 +509,10 @@ def test_bcsr4_golden_bitwise(ctx):
     y = np.zeros(n)
     nsk.SpMV_BCSR(y, x, B)
     assert nsk.rel_error(g["bcsr_spmv_x87"], y) <= 1e-15
-    y, z = np.zeros(n), np.zeros(n)
-    nsk.SpM2V_BCSR_OPT(z, y, x, B)
-    assert nsk.rel_error(g["bcsr_spm2v_opt_y"], y) <= 1e-15 and nsk.rel_error(g["bcsr_spm2v_opt_z"], z) <= 1e-14
+    for fn, key in ((nsk.SpM2V_BCSR_OPT, "opt"), (nsk.SpM2V_BCSR_FMA, "opt"), (nsk.SpM2V_BCSR_AVX2, "avx2"), (nsk.SpM2V_BCSR, "x87")):
+        y, z = np.zeros(n), np.zeros(n)
+        fn(z, y, x, B)
+        assert nsk.rel_error(g[f"bcsr_spm2v_{key}_y"], y) <= 1e-15 and nsk.rel_error(g[f"bcsr_spm2v_{key}_z"], z) <= 1e-14
 
 
 def test_bcsr4_fem_operator_matches_oracle_and_csr(ctx, oracle_lib):
