@@ -4,7 +4,7 @@
 
 #include "nsk_internal.h"
 
-constexpr int WF_GROUP = 16;  // tiles per completion counter
+constexpr int WF_GROUP = 16;  // tiles per completion counter (measured on 256^3, k=4: 4 -> 0.760 ms, 16 -> 0.701, 32 -> 0.702)
 
 struct WaveDeps {
     int ntiles = 0, ngroups = 0;
