@@ -1105,7 +1105,13 @@ static PkLevelPlan *pk_level_plan(nsk_csr_t A, PackedOp *op, int k, const int *l
         else
             p.lead = std::max(lead_min + 2 * WF_GROUP, (int)(budget / ((double)(k - 1) * tile_bytes)));
         const double window = (double)(k - 1) * p.lead * tile_bytes;
-        if (window > budget * 1.0001) {
+        // A window that binds (lead < ntiles) but leaves little slack beyond the pattern's reach makes every level wait
+        // on the loop latency: measured on a 512 x 512 x 64 slab, three levels with 589 tiles of slack per hop cost
+        // 0.25 ms per level -- more than separate products (0.215) -- while two levels with 2460 cost 0.19.  Below
+        // ~180 k rows of slack the planner refuses and the caller fuses fewer levels per launch instead.
+        const int min_slack = 180000 / std::max(1, op->t_rows);
+        const bool thin = lead_pct < 0 && p.lead < ntiles && p.lead - lead_min < min_slack;
+        if (window > budget * 1.0001 || thin) {
             *why = "wavefront window exceeds the L2 budget";
             p.rejected = true;
             op->plans.push_back(p);
