@@ -16,8 +16,13 @@
  *   struct bcsr4x4_matrix, SpMV_BCSR*           mpk/SpMV.h:26-33,61-64  nsk_bcsr4_create / nsk_spmv_bcsr4
  *   norm2, rel_error                            mpk/utils.cpp:131-143  nsk_norm2 / nsk_rel_error
  *   orthogonalize (dot + axpy)                  mpk/2SpMV.cpp:3-11     nsk_orthogonalize, nsk_dot, nsk_axpy
+ *   orthonormalize_against_basis                mpk/2SpMV.cpp:13-28    nsk_orthonormalize_against_basis
  *   flush_cache                                 mpk/utils.cpp:146-154  nsk_flush_l2
- *   (no CG in the reference; north star asks for it)             nsk_cg
+ *   COO2CSR / generate_CSR, generate_BCSR4      mpk/utils.cpp:5-127    nsk_coo2csr, nsk_coo2bcsr4 (host)
+ *   the .mtx reader inlined in every driver     mpk/SpM2V.cpp:815-852  nsk_mtx_read (host)
+ *   BuildKrylovBasis_AVX2 / MatMatMult_SeqBAIJ_4_AVX2 (s-step basis, several right-hand sides)
+ *                                               src/kernels/spmm_avx2.c:7-168  nsk_mpk_multi
+ *   (no CG in the reference; north star asks for it)             nsk_cg (classical and s-step)
  *
  * Conventions
  *   - One nsk_ctx per process and per GPU (one process per GPU; ranks are joined by nsk_comm_init).
