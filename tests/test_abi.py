@@ -132,3 +132,22 @@ def test_shim_exports_the_reference_mangled_symbols():
         defined = set(subprocess.run(["nm", "--defined-only", str(o)], capture_output=True, text=True).stdout.split())
         for s in names:
             assert s in defined, f"{s} is not a symbol of the reference's {obj}: the recorded list is stale"
+
+
+def test_bench_reference_arm_line_has_the_contract_keys():
+    """`bench.py --impl reference` (the CPU arm the driver times beside ours) on a tiny grid: one JSON line with the
+    keys the contract names, same metric / unit / config shape as the native arm."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--grid", "24"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+    d = json.loads(line)
+    assert d["impl"] == "reference" and d["metric"] == "mpk_k4_spmv_equivalent_GBps" and d["unit"] == "GB/s"
+    assert d["higher_is_better"] is True and d["dtype"] == "f64" and d["data"] == "synthetic"
+    assert d["value"] > 0 and d["ms_per_step"] > 0 and d["steps"] == 1
+    assert set(d["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and d["cpu_baseline"]["kind"] in ("reference", "port")
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert "workload" in d["config"] and "model" not in d["config"]
