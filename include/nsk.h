@@ -160,10 +160,13 @@ int64_t nsk_pack_host_bytes(void *handle);
 int nsk_pack_host_expand(void *handle, int *ptrow, int *indcol, double *coef, int *max_runs, int *max_xlen);
 /* CPU model of the fused kernel's protocol on the schedule the GPU path would build (forward dependencies, window
  * back-pressure, per-group completion counters, in-order CTAs with `stages` open items, seeded random interleaving).
- * Returns the number of items that never became runnable (0 = the schedule is sound) or a negative nsk_status. */
+ * The model also checks data readiness: when an item opens, every tile its nonzeros really read must be complete at
+ * the level below.  Returns the number of items that never became runnable (0 = the schedule is sound), a negative
+ * nsk_status, or -1000000 - v when v reads would have seen rows not yet produced. */
 long long nsk_pack_host_simulate(void *handle, int k, int lead_slack_tiles, int resident, int w0_pct, int bp_global,
                                  int interleave, int stages, const int *level_rows, unsigned seed,
-                                 long long *items_out, int *reach_out);
+                                 long long *items_out, int *reach_out, int ghi_bias /* 0; < 0 weakens the forward
+                                 dependencies by that many groups, for negative tests */);
 void nsk_pack_host_destroy(void *handle);
 
 /* ---- CSR operator --------------------------------------------------------------------------- */

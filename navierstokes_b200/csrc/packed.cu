@@ -852,10 +852,18 @@ static void pk_build_schedule(const std::vector<PkTile> &tiles, const std::vecto
 // level that holds it back have reached their group sizes, and it reports to its own group when it finishes; CTAs are
 // visited in a seeded random order and up to `stages` items per CTA may be open at once (they finish in random order).
 // Returns the number of items that completed; the schedule is sound iff that equals the total.
+// reads: per tile, the tiles whose rows its nonzeros really reference (exact, from the local columns); ntile_done marks
+// (level, tile) complete.  *violations counts items opened while a tile they read was not complete at the level below
+// (and inside that level's row prefix): the declared dependencies (prefix of groups <= ghi) must imply data readiness.
 static long long pk_simulate(const PkSchedule &S, const std::vector<int> &teams, int k, int ngroups, int bp_global, int stages,
-                             unsigned seed)
+                             unsigned seed, const std::vector<std::vector<int>> *reads = nullptr,
+                             const std::vector<int> *tile_row0 = nullptr, const std::vector<int> *lr = nullptr,
+                             long long *violations = nullptr)
 {
     const int grid = (int)S.roles.size();
+    const int ntiles_all = reads ? (int)reads->size() : 0;
+    std::vector<std::vector<char>> tile_done(reads ? k : 0, std::vector<char>((size_t)ntiles_all, 0));
+    long long bad = 0;
     std::vector<std::vector<int>> cnt(k, std::vector<int>(ngroups, 0));
     std::vector<int> water(k, 0);  // all groups < water[l] complete at level l
     auto advance = [&](int l) {
@@ -883,6 +891,7 @@ static long long pk_simulate(const PkSchedule &S, const std::vector<int> &teams,
                 const PkItem &it = S.items[(size_t)open[b][pick]];
                 open[b].erase(open[b].begin() + pick);
                 cnt[level][it.pos / WF_GROUP]++;
+                if (reads) tile_done[level][(size_t)it.tile] = 1;
                 advance(level);
                 done++;
                 progress = true;
@@ -895,6 +904,9 @@ static long long pk_simulate(const PkSchedule &S, const std::vector<int> &teams,
                 const bool fwd_ok = level == 0 || water[level - 1] > it.ghi || water[level - 1] >= ngroups;
                 const bool back_ok = it.gback < 0 || water[lb] > it.gback || water[lb] >= ngroups;
                 if (fwd_ok && back_ok) {
+                    if (reads && level > 0)
+                        for (int d : (*reads)[(size_t)it.tile])
+                            if ((*tile_row0)[(size_t)d] < (*lr)[level - 1] && !tile_done[level - 1][(size_t)d]) bad++;
                     open[b].push_back((int)(S.item_off[level] + (size_t)idx));
                     next[b]++;
                     progress = true;
@@ -902,6 +914,7 @@ static long long pk_simulate(const PkSchedule &S, const std::vector<int> &teams,
             }
         }
     }
+    if (violations) *violations = bad;
     return done;
 }
 
@@ -980,7 +993,7 @@ NSK_API int nsk_pack_host_expand(void *handle, int *ptrow, int *indcol, double *
 // of items that did NOT complete (0 = sound), or a negative status.  *items_out receives the total item count.
 NSK_API long long nsk_pack_host_simulate(void *handle, int k, int lead_slack_tiles, int resident, int w0_pct, int bp_global,
                                          int interleave, int stages, const int *level_rows, unsigned seed,
-                                         long long *items_out, int *reach_out)
+                                         long long *items_out, int *reach_out, int ghi_bias)
 {
     nsk_packed_host_s *h = static_cast<nsk_packed_host_s *>(handle);
     if (!h->why.empty()) return NSK_ERR_UNSUPPORTED;
@@ -1004,6 +1017,7 @@ NSK_API long long nsk_pack_host_simulate(void *handle, int k, int lead_slack_til
         const int tmax = (int)(std::upper_bound(row0s.begin(), row0s.end(), mx) - row0s.begin()) - 1;
         ghi[t] = std::max(0, tmax) / WF_GROUP;
         reach = std::max(reach, std::min(ntiles - 1, (ghi[t] + 1) * WF_GROUP - 1) - t);
+        ghi[t] = std::max(0, ghi[t] + ghi_bias);  // tests weaken the dependencies on purpose (ghi_bias < 0) to see the model object
     }
     std::vector<int> lr(k);
     for (int l = 0; l < k; l++) lr[l] = level_rows ? level_rows[l] : h->n;
@@ -1018,9 +1032,37 @@ NSK_API long long nsk_pack_host_simulate(void *handle, int k, int lead_slack_til
     const int lead = std::max(1, reach + 1 + WF_GROUP + lead_slack_tiles);
     PkSchedule S;
     pk_build_schedule(h->H.ptiles, pos_tile, ghi, lr, k, ngroups, lead, bp_global, interleave, teams, S);
-    const long long done = pk_simulate(S, teams, k, ngroups, bp_global, stages, seed);
+    // exact read sets: every local column of every row, mapped back through the runs to a global column, then to a tile
+    std::vector<std::vector<int>> reads((size_t)ntiles);
+    for (int t = 0; t < ntiles; t++) {
+        const PkTile &pt = h->H.ptiles[t];
+        const unsigned char *b = h->H.blobs.data() + pt.blob_off;
+        const int *hdr = reinterpret_cast<const int *>(b);
+        const int rp = hdr[PKH_RP];
+        const unsigned short *lens = reinterpret_cast<const unsigned short *>(b + hdr[PKH_OFF_LENS]);
+        const unsigned short *lcol = reinterpret_cast<const unsigned short *>(b + hdr[PKH_OFF_LCOL]);
+        std::vector<int> &rd = reads[(size_t)t];
+        for (int r = 0; r < hdr[PKH_NROWS]; r++)
+            for (int e = 0; e < (int)lens[r]; e++) {
+                const int lc = lcol[(size_t)e * rp + r];
+                int g = -1;
+                if (pt.tail && lc == pt.tail - 1) g = h->n_cols - 1;
+                for (int sgm = 0; sgm < pt.nseg && g < 0; sgm++) {
+                    const int len = pt.seg_lenoff[sgm] & 0xffff, xoff = (pt.seg_lenoff[sgm] >> 16) & 0xffff;
+                    if (lc >= xoff && lc < xoff + len) g = pt.seg_start[sgm] + (lc - xoff);
+                }
+                if (g < 0 || g >= h->n) continue;  // ghost entry of x: read by level 0 only
+                const int d = (int)(std::upper_bound(row0s.begin(), row0s.end(), g) - row0s.begin()) - 1;
+                if (rd.empty() || rd.back() != d) rd.push_back(d);
+            }
+        std::sort(rd.begin(), rd.end());
+        rd.erase(std::unique(rd.begin(), rd.end()), rd.end());
+    }
+    long long violations = 0;
+    const long long done = pk_simulate(S, teams, k, ngroups, bp_global, stages, seed, &reads, &row0s, &lr, &violations);
     if (items_out) *items_out = (long long)S.items.size();
     if (reach_out) *reach_out = reach;
+    if (violations > 0) return -1000000 - violations;  // a dependency hole: an item would read rows not yet produced
     return (long long)S.items.size() - done;
 }
 

@@ -101,7 +101,8 @@ def test_pack_golden_operators(case):
 
 
 # ---- the fused kernel's protocol, modelled on the CPU ----------------------------------------------------------------
-def simulate(A, variant, k, slack, resident, w0=100, bp_global=1, interleave=1, stages=2, level_rows=None, seed=0):
+def simulate(A, variant, k, slack, resident, w0=100, bp_global=1, interleave=1, stages=2, level_rows=None, seed=0,
+             ghi_bias=0):
     lib = _lib.load()
     ptrow = np.ascontiguousarray(A.ptrow, np.int32)
     indcol = np.ascontiguousarray(A.indcol, np.int32)
@@ -117,7 +118,8 @@ def simulate(A, variant, k, slack, resident, w0=100, bp_global=1, interleave=1, 
         lr = np.ascontiguousarray(level_rows, np.int32)
     items, reach = C.c_longlong(), C.c_int()
     stuck = lib.nsk_pack_host_simulate(h, k, slack, resident, w0, bp_global, interleave, stages,
-                                       lr.ctypes.data if lr is not None else None, seed, C.byref(items), C.byref(reach))
+                                       lr.ctypes.data if lr is not None else None, seed, C.byref(items), C.byref(reach),
+                                       ghi_bias)
     lib.nsk_pack_host_destroy(h)
     return stuck, items.value, reach.value
 
@@ -180,3 +182,17 @@ def test_protocol_model_detects_a_window_smaller_than_the_reach():
     assert stuck > 0
     stuck, _, _ = simulate(A, 7, 3, 0, 30, bp_global=0, seed=0)
     assert stuck == 0
+
+
+def test_protocol_model_detects_missing_forward_dependencies():
+    """Data readiness: with the forward dependencies weakened by a few groups, some item opens before a tile it really
+    reads is complete at the level below -- the model reports the hole (on the real schedule it never does: every
+    other test in this file runs with the check on)."""
+    A = matgen.laplace3d_7pt(64, 24, 20)  # reach 6 tiles: one group back is enough to lose the plane above
+    found = 0
+    for seed in range(8):
+        res, _, _ = simulate(A, 7, 3, 40, 444, seed=seed, ghi_bias=-2)
+        found += res <= -1000000
+    assert found >= 1
+    res, _, _ = simulate(A, 7, 3, 40, 444, seed=0, ghi_bias=0)
+    assert res == 0
