@@ -56,7 +56,12 @@ void SpM2V_CSR_OPT(double *z, double *y, double *x, csrmatrix &A, std::vector<in
 void SpM2V_CSR_AVX2(double *z, double *y, double *x, csrmatrix &A, std::vector<int> &ptrowend1);        // mpk/SpM2V.cpp:279
 
 // k = 2, 3, 4 with the signatures of mpk/SpMVmulti0.cpp (:44, :65, :132, :191); the nested first-touch schedules are
-// accepted and ignored.  These are the x87 / no-fma flavours in the reference: multiply-add chain here.
+// accepted and ignored (Generate2ndlayer / Generate3rdlayer still fill them the reference's way).  These are the
+// x87 / no-fma flavours in the reference: multiply-add chain here.
+void SpMV(double *y, double *x, csrmatrix &A);                                                              // :259
+void Generate2ndlayer(std::vector<std::vector<int> > &ptrowend2, csrmatrix &A, std::vector<int> &ptrowend1);    // :106
+void Generate3rdlayer(std::vector<std::vector<std::vector<int> > > &ptrowend3, csrmatrix &A,                   // :157
+                      std::vector<int> &ptrowend1, std::vector<std::vector<int> > &ptrowend2);
 void SpM2V0(double *z, double *y, double *x, csrmatrix &A, std::vector<int> &ptrowend1);
 void SpM2V(double *z, double *y, double *x, csrmatrix &A, std::vector<int> &ptrowend1);
 void SpM3V(double *w, double *z, double *y, double *x, csrmatrix &A, std::vector<int> &ptrowend1,

@@ -41,6 +41,7 @@ def build(force: bool = False, verbose: bool = False, jobs: int | None = None) -
     stamp = _stamp(deps, " ".join(NVCC_FLAGS))
     stamp_file = LIBDIR / "libnsk.stamp"
     if not force and out.exists() and stamp_file.exists() and stamp_file.read_text() == stamp:
+        build_shim(verbose=verbose, force=False)
         return out
     nvcc = os.environ.get("NVCC", "nvcc")
     objdir = LIBDIR / "obj"
@@ -67,16 +68,19 @@ def build(force: bool = False, verbose: bool = False, jobs: int | None = None) -
     link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(out), *map(str, objs), "-ldl"]
     subprocess.run(link, check=True)
     stamp_file.write_text(stamp)
-    build_shim(verbose=verbose)
+    build_shim(verbose=verbose, force=True)
     return out
 
 
-def build_shim(verbose: bool = False) -> Path | None:
+def build_shim(verbose: bool = False, force: bool = True) -> Path | None:
     """C++ drop-in library exporting the reference's SpMV.h symbols on top of libnsk.so."""
     src = CSRC / "shim_spmv.cpp"
     if not src.exists():
         return None
     out = LIBDIR / "libnsk_spmvshim.so"
+    deps = [src, ROOT / "include" / "nsk_spmv_compat.hpp", ROOT / "include" / "nsk.h"]
+    if not force and out.exists() and all(out.stat().st_mtime >= d.stat().st_mtime for d in deps):
+        return out
     cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", str(ROOT / "include"), str(src), "-o", str(out),
            f"-L{LIBDIR}", "-lnsk", "-Wl,-rpath,$ORIGIN"]
     if verbose:

@@ -136,12 +136,64 @@ void Generate1stlayer(std::vector<int> &ptrowend1, csrmatrix &A)
     }
 }
 
+// ---- deeper schedules of mpk/SpMVmulti0.cpp (:106, :157).  Depth d keeps one seen-set over the whole traversal:
+// walking rows in order and, under each entry, the part of the neighbour row the shallower schedule left open,
+// a column met for the first time at depth d opens its whole row (value = end of that row), any later meeting
+// opens nothing (value = start of that row).  SpM3V / SpM4V below ignore them; they are filled so that a driver
+// which builds or prints them before the product behaves as it did.  Memory is O(nnz * row^(d-1)), as there.
+namespace {
+inline int first_touch_end(std::vector<char> &seen, const csrmatrix &A, int col)
+{
+    const int e = seen[col] ? A.ptrow[col] : A.ptrow[col + 1];
+    seen[col] = 1;
+    return e;
+}
+inline int stored_entries(const csrmatrix &A) { return A.ptrow.empty() ? 0 : A.ptrow[A.n]; }
+}  // namespace
+
+void Generate2ndlayer(std::vector<std::vector<int> > &ptrowend2, csrmatrix &A, std::vector<int> &ptrowend1)
+{
+    std::vector<char> seen(A.n > 0 ? A.n : 1, 0);
+    const int nnz = stored_entries(A);
+    ptrowend2.resize(A.nnz > nnz ? A.nnz : nnz);
+    for (int ia = 0; ia < nnz; ia++) {
+        const int open0 = A.ptrow[A.indcol[ia]];
+        const int nopen = ptrowend1[ia] - open0;
+        std::vector<int> &ends = ptrowend2[ia];
+        ends.resize(nopen > 0 ? nopen : 0);
+        for (int t = 0; t < nopen; t++) ends[t] = first_touch_end(seen, A, A.indcol[open0 + t]);
+    }
+}
+
+void Generate3rdlayer(std::vector<std::vector<std::vector<int> > > &ptrowend3, csrmatrix &A, std::vector<int> &ptrowend1,
+                      std::vector<std::vector<int> > &ptrowend2)
+{
+    std::vector<char> seen(A.n > 0 ? A.n : 1, 0);
+    const int nnz = stored_entries(A);
+    ptrowend3.resize(A.nnz > nnz ? A.nnz : nnz);
+    for (int ia = 0; ia < nnz; ia++) {
+        const int open0 = A.ptrow[A.indcol[ia]];
+        const int nopen = ptrowend1[ia] - open0;
+        std::vector<std::vector<int> > &under = ptrowend3[ia];
+        under.resize(nopen > 0 ? nopen : 0);
+        for (int t = 0; t < nopen; t++) {
+            const int k = A.indcol[open0 + t];
+            const int kopen = ptrowend2[ia][t] - A.ptrow[k];
+            if (kopen <= 0) continue;   // nothing left open under this entry: its list stays as it was
+            std::vector<int> &ends = under[t];
+            ends.resize(kopen);
+            for (int u = 0; u < kopen; u++) ends[u] = first_touch_end(seen, A, A.indcol[A.ptrow[k] + u]);
+        }
+    }
+}
+
 void SpM2V_CSR(double *z, double *y, double *x, csrmatrix &A, std::vector<int> &) { spm2v(z, y, x, A, NSK_EXACT_MULADD); }
 void SpM2V_CSR_OPT(double *z, double *y, double *x, csrmatrix &A, std::vector<int> &) { spm2v(z, y, x, A, NSK_EXACT_FMA); }
 void SpM2V_CSR_AVX2(double *z, double *y, double *x, csrmatrix &A, std::vector<int> &) { spm2v(z, y, x, A, NSK_FAST); }
 
 // ---- k = 2, 3, 4 with the names and signatures of mpk/SpMVmulti0.cpp (:44, :65, :132, :191).  The nested
 // first-touch schedules are accepted and ignored: the result -- every level of A^k x -- does not depend on them.
+void SpMV(double *y, double *x, csrmatrix &A) { spmv(y, x, A, NSK_EXACT_MULADD); }   // the seed file's plain product (:259)
 void SpM2V0(double *z, double *y, double *x, csrmatrix &A, std::vector<int> &) { spm2v(z, y, x, A, NSK_EXACT_MULADD); }
 void SpM2V(double *z, double *y, double *x, csrmatrix &A, std::vector<int> &) { spm2v(z, y, x, A, NSK_EXACT_MULADD); }
 void SpM3V(double *w, double *z, double *y, double *x, csrmatrix &A, std::vector<int> &, std::vector<std::vector<int> > &)

@@ -121,8 +121,21 @@ def test_shim_exports_the_reference_mangled_symbols():
         "_Z10SpM2V_BCSRPdS_S_R14bcsr4x4_matrixRSt6vectorIiSaIiEE", "_Z14SpM2V_BCSR_OPTPdS_S_R14bcsr4x4_matrixRSt6vectorIiSaIiEE",
         "_Z14SpM2V_BCSR_FMAPdS_S_R14bcsr4x4_matrixRSt6vectorIiSaIiEE", "_Z15SpM2V_BCSR_AVX2PdS_S_R14bcsr4x4_matrixRSt6vectorIiSaIiEE",
     ]
-    missing = [s for s in expected if s not in have]
+    # the matrix-powers seed file's names (mpk/SpMVmulti0.cpp :22 :44 :65 :106 :132 :157 :191 :259)
+    multi0 = [
+        "_Z4SpMVPdS_R9csrmatrix", "_Z6SpM2V0PdS_S_R9csrmatrixRSt6vectorIiSaIiEE", "_Z5SpM2VPdS_S_R9csrmatrixRSt6vectorIiSaIiEE",
+        "_Z5SpM3VPdS_S_S_R9csrmatrixRSt6vectorIiSaIiEERS2_IS4_SaIS4_EE",
+        "_Z5SpM4VPdS_S_S_S_R9csrmatrixRSt6vectorIiSaIiEERS2_IS4_SaIS4_EERS2_IS7_SaIS7_EE",
+        "_Z16Generate2ndlayerRSt6vectorIS_IiSaIiEESaIS1_EER9csrmatrixRS1_",
+        "_Z16Generate3rdlayerRSt6vectorIS_IS_IiSaIiEESaIS1_EESaIS3_EER9csrmatrixRS1_RS3_",
+    ]
+    missing = [s for s in expected + multi0 if s not in have]
     assert not missing, missing
+    ref_multi0 = ROOT / "oracle" / "_ref" / "libnsref_multi0.so"
+    if ref_multi0.exists():
+        defined = set(subprocess.run(["nm", "-D", "--defined-only", str(ref_multi0)], capture_output=True, text=True).stdout.split())
+        for s in multi0:
+            assert s in defined, f"{s} is not a symbol of the reference's SpMVmulti0.cpp: the recorded list is stale"
     # cross-check the recorded names against the reference's own objects when they were compiled here
     ref_dir = ROOT / "oracle" / "_ref"
     for obj, names in (("SpMV.o", expected[:8]), ("SpM2V.o", expected[8:])):
@@ -132,6 +145,25 @@ def test_shim_exports_the_reference_mangled_symbols():
         defined = set(subprocess.run(["nm", "--defined-only", str(o)], capture_output=True, text=True).stdout.split())
         for s in names:
             assert s in defined, f"{s} is not a symbol of the reference's {obj}: the recorded list is stale"
+
+
+def test_shim_schedule_builders_match_the_reference(tmp_path):
+    """Generate{1st,2nd,3rd}layer of the shim against the reference's own (compiled here into oracle/_ref), entry for
+    entry on random operators with sorted and unsorted rows.  tests/layers_driver.cpp loads both libraries side by side."""
+    import shutil
+    import subprocess
+    from navierstokes_b200 import _lib
+    shim = _lib.LIB_PATH.parent / "libnsk_spmvshim.so"
+    ref_multi0 = ROOT / "oracle" / "_ref" / "libnsref_multi0.so"
+    if not ref_multi0.exists():
+        pytest.skip("reference not compiled here (oracle/_ref absent)")
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not installed")
+    exe = tmp_path / "layers_driver"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I", str(ROOT / "include"), str(ROOT / "tests" / "layers_driver.cpp"),
+                    "-o", str(exe), "-ldl"], check=True)
+    r = subprocess.run([str(exe), str(shim), str(ref_multi0)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.startswith("OK"), r.stdout + r.stderr
 
 
 def test_bench_reference_arm_line_has_the_contract_keys():
