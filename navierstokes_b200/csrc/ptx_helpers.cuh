@@ -147,4 +147,8 @@ __device__ __forceinline__ unsigned int ld_acquire_cta_shared_u32(const unsigned
     asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
     return v;
 }
+__device__ __forceinline__ void st_release_cta_shared_u32(unsigned int *p, unsigned int v)
+{
+    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
 }  // namespace nskptx
