@@ -219,7 +219,7 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
                 const int idx_next = end ? idx : atomicAdd(claim, 1);
                 uint32_t spins = 0;
                 while ((int)(ld_acquire_cta_shared_u32(npub) + (unsigned int)PK_RING) <= it)
-                    if (++spins > (1u << 28)) __trap();
+                    if (++spins > (1u << 24)) __trap();
                 ring[2 * (it % PK_RING)] = a0;
                 ring[2 * (it % PK_RING) + 1] = a1;
                 st_release_cta_shared_u32(nclaimed, (unsigned int)(it + 1));
@@ -317,7 +317,7 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
                     }
                     if (ok) { ++n; continue; }
                     if (n > 0) break;
-                    if (++spins > (1u << 28)) __trap();
+                    if (++spins > (1u << 24)) __trap();
                 }
                 if (n > 0) {
                     const unsigned long long t5 = timing ? pk_now() : 0ull;
@@ -398,7 +398,7 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
             for (int it = 0;; ++it) {
                 uint32_t spins = 0;
                 while ((int)ld_acquire_cta_shared_u32(nclaimed) <= it)
-                    if (++spins > (1u << 28)) __trap();
+                    if (++spins > (1u << 24)) __trap();
                 const int4 a0 = ring[2 * (it % PK_RING)];
                 const int s = it % STAGES;
                 if (a0.x < 0) {  // end marker: second arrival on the stage's barrier, no bytes

@@ -107,12 +107,88 @@ def timing(ctx, show_cycle):
     ctx.set_option("pk_flags", STATIC)
 
 
+def fast(ctx):
+    """The whole check in well under two minutes: a few small operators, then 256^3 compared bit for bit and timed."""
+    bad = 0
+    ctx.set_option("wave_l2_pct", 1000)
+    for name, A in (("7pt 64x24x20", matgen.laplace3d_7pt(64, 24, 20)), ("7pt 61x17x23 (odd n)", matgen.laplace3d_7pt(61, 17, 23)),
+                    ("7pt 128x64x48", matgen.laplace3d_7pt(128, 64, 48))):
+        dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
+        for nv in (1, 2):
+            xs = [ctx.to_device(matgen.vec_uniform(A.n, 3 + v)) for v in range(nv)]
+            for k in (2, 4):
+                ref, s0 = run(ctx, dA, k, xs, STATIC, nsk.EXACT_FMA)
+                for rep in range(3):
+                    got, s1 = run(ctx, dA, k, xs, DYNAMIC, nsk.EXACT_FMA)
+                    same = all(np.array_equal(a.view(np.uint64), b.view(np.uint64)) for ra, rb in zip(ref, got) for a, b in zip(ra, rb))
+                    bad += (not same) or s0 != s1
+                print(f"{name} nv={nv} k={k}: strategy {s0}/{s1} {'ok' if bad == 0 else 'MISMATCH'}", flush=True)
+        dA.close()
+    ctx.set_option("wave_l2_pct", 0)
+    if bad:
+        return bad
+    A = matgen.laplace3d_7pt(256)
+    dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
+    x = ctx.to_device(matgen.vec_uniform(A.n, 1))
+    x2 = ctx.to_device(matgen.vec_uniform(A.n, 2))
+    print("256^3 ready", flush=True)
+    for k in (4, 2, 3):
+        lv = [ctx.empty(A.n) for _ in range(k)]
+        ctx.set_option("pk_flags", STATIC)
+        dA.mpk(k, x, lv)
+        ref = [v.to_host() for v in lv]
+        ctx.set_option("pk_flags", DYNAMIC)
+        for v in lv:
+            ctx.axpy(1.0, x, v)  # spoil the static result: a launch that wrote nothing must not pass
+        dA.mpk(k, x, lv)
+        same = all(np.array_equal(a.view(np.uint64), v.to_host().view(np.uint64)) for a, v in zip(ref, lv))
+        bad += not same
+        ts = []
+        for flags in (STATIC, DYNAMIC, STATIC, DYNAMIC):
+            ctx.set_option("pk_flags", flags)
+            ts.append(timed(ctx, lambda: dA.mpk(k, x, lv), reps=20))
+        print(f"256^3 k={k}: {'bit-identical' if same else 'MISMATCH'}; static {ts[0]:.4f} / {ts[2]:.4f} ms, dynamic {ts[1]:.4f} / {ts[3]:.4f} ms "
+              f"(strategy {ctx.query('last_mpk_strategy')})", flush=True)
+    k = 4
+    lv2 = [[ctx.empty(A.n) for _ in range(k)] for _ in range(2)]
+    ts = []
+    for flags in (STATIC, DYNAMIC):
+        ctx.set_option("pk_flags", flags)
+        ts.append(timed(ctx, lambda: dA.mpk_multi(k, [x, x2], lv2), reps=10))
+    print(f"256^3 k=4, two vectors: static {ts[0]:.4f} ms, dynamic {ts[1]:.4f} ms", flush=True)
+    lv4 = [ctx.empty(A.n) for _ in range(4)]
+    for l2 in (60, 80):
+        ctx.set_option("wave_l2_pct", l2)
+        ts = []
+        for flags in (STATIC, DYNAMIC):
+            ctx.set_option("pk_flags", flags)
+            ts.append(timed(ctx, lambda: dA.mpk(4, x, lv4), reps=10))
+        print(f"256^3 k=4, L2 budget {l2} %: static {ts[0]:.4f} ms, dynamic {ts[1]:.4f} ms", flush=True)
+    ctx.set_option("wave_l2_pct", 0)
+    lv = [ctx.empty(A.n) for _ in range(4)]
+    for flags in (STATIC, DYNAMIC):
+        ctx.set_option("pk_flags", flags)
+        dA.mpk(4, x, lv)
+        ctx.set_option("pk_timing", 1)
+        print(f"# stage cycle, pk_flags={flags}", file=sys.stderr, flush=True)
+        dA.mpk(4, x, lv)
+        ctx.sync()
+        ctx.set_option("pk_timing", 0)
+    ctx.set_option("pk_flags", STATIC)
+    return bad
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--fast", action="store_true", help="short parity + 256^3 parity and timing, under two minutes")
     ap.add_argument("--timing", action="store_true", help="also time 256^3 (k = 2, 3, 4) and print the stage cycle of both")
     args = ap.parse_args()
     ctx = nsk.Context(0)
+    if args.fast:
+        bad = fast(ctx)
+        print("fast check:", "all bit-identical" if bad == 0 else f"{bad} mismatches", flush=True)
+        return 1 if bad else 0
     bad = parity(ctx, args.quick)
     print("parity:", "all bit-identical" if bad == 0 else f"{bad} mismatches", flush=True)
     if bad == 0 and args.timing:
