@@ -103,6 +103,8 @@ struct PkParams {
     unsigned int *ticket;
     double *dot_out;
     int *claims;     // [k] next unclaimed item of each level (dynamic-claim kernels only), zeroed with the counters
+    const int4 *fat[NSK_MAX_K];  // dynamic-claim kernels: per level, 128 bytes per item = the PkItem followed by its PkTile,
+                                 // so that one load after the claim brings everything every warp needs
 };
 
 // blob header (16 ints at the start of every blob)
@@ -148,6 +150,7 @@ __device__ __forceinline__ int pk_wait_groups(const int *cnt, const int *need, i
 // takes fewer tiles, instead of holding back the prefix watermark everybody downstream waits for.  Items are still
 // taken in ascending order by every CTA, so the dependency rules and the deadlock argument are unchanged.
 constexpr int PK_RING = 16;  // claimed items a CTA remembers (>= STAGES + 2; the publisher may trail the consumers)
+constexpr int PK_FAT = 8;    // int4 per ring entry / per fat item: PkItem (2) + PkTile (6)
 
 template <int T_ROWS, int BLOB_CAP, int XCAP, int STAGES, int NCW, int MINB, int RPT, int NV, bool MULADD, bool DYN = false>
 __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkParams P)
@@ -167,7 +170,7 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
     // DYN only: ring of claimed items (entry = the PkItem, tile < 0 = no more items), how many entries the producer has
     // written, how many the publisher is done with (an entry is reused PK_RING items later)
     int4 *ring = reinterpret_cast<int4 *>(smem + (((size_t)(reinterpret_cast<unsigned char *>(fin + STAGES) - smem) + 15) & ~(size_t)15));
-    unsigned int *nclaimed = reinterpret_cast<unsigned int *>(ring + 2 * PK_RING);
+    unsigned int *nclaimed = reinterpret_cast<unsigned int *>(ring + PK_FAT * PK_RING);
     unsigned int *npub = nclaimed + 1;
     const bool timing = P.timing != nullptr;
 
@@ -203,26 +206,49 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
         if (lane != 0) return;
         if constexpr (DYN) {
             int *claim = P.claims + level;
+            const int4 *fat = P.fat[level];
             const bool last_reader = (P.flags & 1) && level == P.k - 1;
             const uint64_t pol = policy_evict_first();
             unsigned long long acc[5] = {0, 0, 0, 0, 0};
-            int idx = atomicAdd(claim, 1);
+            // How far the claims run ahead of the stage ring (tiles a CTA holds beyond its STAGES open ones):
+            //   1 (default)  the claim for item it+1 is issued before the wait for item it's stage, its descriptor
+            //                loaded after item it's blob copy has been issued;
+            //   2 (flag 16)  ... its descriptor is loaded before that wait too, and item it+2 is claimed: the other
+            //                warps know the next item half a stage cycle earlier, one more tile is in flight;
+            //   0 (flag 32)  nothing is claimed until item it's blob copy has been issued.
+            const int ahead = (P.flags & 16) ? 2 : (P.flags & 32) ? 0 : 1;
+            auto load_desc = [&](int4 *d, int idx) {
+                d[0] = make_int4(-1, 0, 0, -1);  // end marker
+                if (idx < count) {
+#pragma unroll
+                    for (int j = 0; j < PK_FAT; j++) d[j] = fat[(size_t)PK_FAT * idx + j];
+                }
+            };
+            int4 e[PK_FAT], f[PK_FAT];
+            load_desc(e, atomicAdd(claim, 1));
+            int nidx = ahead >= 2 ? atomicAdd(claim, 1) : 0;
             int it = 0;
             for (;; ++it) {
-                const bool end = idx >= count;
-                int4 a0 = make_int4(-1, 0, 0, -1), a1 = make_int4(0, 0, 0, 0);
-                if (!end) {
-                    a0 = my[2 * (size_t)idx];
-                    a1 = my[2 * (size_t)idx + 1];
-                }
-                // the next claim's round trip overlaps this item's wait for its stage (one item held beyond the ring)
-                const int idx_next = end ? idx : atomicAdd(claim, 1);
+                const bool end = e[0].x < 0;
                 uint32_t spins = 0;
                 while ((int)(ld_acquire_cta_shared_u32(npub) + (unsigned int)PK_RING) <= it)
                     if (++spins > (1u << 24)) __trap();
-                ring[2 * (it % PK_RING)] = a0;
-                ring[2 * (it % PK_RING) + 1] = a1;
+                if (end) ring[PK_FAT * (it % PK_RING)] = e[0];
+                else {
+#pragma unroll
+                    for (int j = 0; j < PK_FAT; j++) ring[PK_FAT * (it % PK_RING) + j] = e[j];
+                }
                 st_release_cta_shared_u32(nclaimed, (unsigned int)(it + 1));
+                bool have_f = false;
+                if (!end) {
+                    if (ahead >= 2) {
+                        load_desc(f, nidx);  // item it + 1, claimed one iteration ago
+                        have_f = true;
+                        nidx = atomicAdd(claim, 1);
+                    } else if (ahead == 1) {
+                        nidx = atomicAdd(claim, 1);  // its round trip overlaps the wait below
+                    }
+                }
                 const int s = it % STAGES;
                 if (it >= STAGES) {
                     mbar_wait(&done[s], ((it / STAGES) - 1) & 1);
@@ -240,12 +266,16 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
                     mbar_arrive(&full[s]);  // with the dependency warp's arrival: wakes the consumers, which see the end marker
                     break;
                 }
+                const int4 a1 = e[1];
                 const long long off = ((long long)(unsigned int)a1.x) | ((long long)a1.y << 32);
                 mbar_arrive_expect_tx(&full[s], (uint32_t)a1.z);
                 if (last_reader) bulk_g2s_hint(smem + (size_t)s * STAGE_BYTES, P.blobs + off, (uint32_t)a1.z, &full[s], pol);
                 else bulk_g2s(smem + (size_t)s * STAGE_BYTES, P.blobs + off, (uint32_t)a1.z, &full[s]);
                 if (timing) ts[s * 4 + 0] = pk_now();
-                idx = idx_next;
+                if (ahead == 0) nidx = atomicAdd(claim, 1);
+                if (!have_f) load_desc(f, nidx);
+#pragma unroll
+                for (int j = 0; j < PK_FAT; j++) e[j] = f[j];
             }
             if (timing) {
                 for (int j = 0; j < 5; j++) P.timing[(size_t)blockIdx.x * 16 + j] = acc[j];
@@ -311,7 +341,7 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
                     const int i2 = it + n;
                     bool ok = false;
                     if (n < STAGES && (int)ld_acquire_cta_shared_u32(nclaimed) > i2) {
-                        if (ring[2 * (i2 % PK_RING)].x < 0) { stop = true; break; }
+                        if (ring[PK_FAT * (i2 % PK_RING)].x < 0) { stop = true; break; }
                         const unsigned int need = (unsigned int)NCW * (unsigned int)(i2 / STAGES + 1);
                         ok = ld_acquire_cta_shared_u32(&fin[i2 % STAGES]) >= need;
                     }
@@ -323,7 +353,7 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
                     const unsigned long long t5 = timing ? pk_now() : 0ull;
                     if (!rel) __threadfence();
                     for (int u = 0; u < n; u++) {
-                        const int pos = ring[2 * ((it + u) % PK_RING)].y;
+                        const int pos = ring[PK_FAT * ((it + u) % PK_RING)].y;
                         if (rel && u == 0) red_release_gpu_add(cnt + pos / WF_GROUP, 1);
                         else red_relaxed_gpu_add(cnt + pos / WF_GROUP, 1);
                     }
@@ -393,29 +423,19 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
         int wf = 0, wb = 0;
         unsigned long long w_done = 0, w_dep = 0;
         if constexpr (DYN) {
-            int cw = 0, nw = 0;  // lane u < 24: word u of the PkTile of item it / it + 1
-            bool have_next = false;
             for (int it = 0;; ++it) {
                 uint32_t spins = 0;
                 while ((int)ld_acquire_cta_shared_u32(nclaimed) <= it)
                     if (++spins > (1u << 24)) __trap();
-                const int4 a0 = ring[2 * (it % PK_RING)];
+                const int4 a0 = ring[PK_FAT * (it % PK_RING)];
                 const int s = it % STAGES;
                 if (a0.x < 0) {  // end marker: second arrival on the stage's barrier, no bytes
                     if (it >= STAGES) mbar_wait(&done[s], ((it / STAGES) - 1) & 1);
                     if (lane == 0) mbar_arrive(&full[s]);
                     break;
                 }
-                if (have_next) cw = nw;
-                else if (lane < 24) cw = __ldg(tw + (size_t)a0.x * 24 + lane);
-                have_next = false;
-                if ((int)ld_acquire_cta_shared_u32(nclaimed) > it + 1) {  // next item already claimed: fetch its descriptor now
-                    const int tn = ring[2 * ((it + 1) % PK_RING)].x;
-                    if (tn >= 0) {
-                        if (lane < 24) nw = __ldg(tw + (size_t)tn * 24 + lane);
-                        have_next = true;
-                    }
-                }
+                // lane u < 24: word u of the item's PkTile, straight from the ring entry
+                const int cw = reinterpret_cast<const int *>(ring + PK_FAT * (it % PK_RING) + 2)[lane < 24 ? lane : 0];
                 const int ghi = a0.z, gback = a0.w;
                 const unsigned long long t0 = timing ? pk_now() : 0ull;
                 if (back && gback >= wb) wb = pk_wait_groups(cnt_b, need_b, P.ngroups, wb, gback, lane, (P.flags & 2) != 0);
@@ -536,7 +556,7 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
         const int s = it % STAGES;
         mbar_wait(&full[s], (it / STAGES) & 1);
         if constexpr (DYN) {
-            if (ring[2 * (it % PK_RING)].x < 0) break;  // end marker (written before the producer's arrival on full[s])
+            if (ring[PK_FAT * (it % PK_RING)].x < 0) break;  // end marker (written before the producer's arrival on full[s])
         }
         if (timing && tid == 0) ts[s * 4 + 2] = pk_now();
         const unsigned char *blob = smem + (size_t)s * STAGE_BYTES;
@@ -671,7 +691,7 @@ typedef void (*pk_fn)(const PkParams);
 constexpr int PK_NV2_VARIANT = 7;
 // Dynamic-claim instances (pk_flags bit 8, k > 1) exist for the default short-row geometry, one and two vectors.
 constexpr int PK_DYN_VARIANT = 7;
-constexpr int PK_DYN_SMEM = 16 + PK_RING * 32 + 16;  // alignment + claim ring + its two counters
+constexpr int PK_DYN_SMEM = 16 + PK_RING * PK_FAT * 16 + 16;  // alignment + claim ring + its two counters
 static bool pk_has_dynamic(int variant, int nv) { return nv == 2 ? variant == PK_NV2_VARIANT : variant == PK_DYN_VARIANT; }
 static pk_fn pk_lookup(int variant, bool muladd, int nv, int *smem, bool dyn = false)
 {
@@ -728,6 +748,7 @@ struct PkLevelPlan {
     PkItem *d_items = nullptr;
     int *d_counters = nullptr;
     int *d_group_size = nullptr;
+    int4 *d_fat = nullptr;      // dynamic-claim kernels: item + tile descriptor, 128 bytes each (built on first use)
 };
 
 struct PackedOp {
@@ -765,6 +786,7 @@ void nsk_packed_free(nsk_csr_t A)
             if (p.d_counters) cudaFree(p.d_counters);
             if (p.d_group_size) cudaFree(p.d_group_size);
             if (p.d_roles) cudaFree(p.d_roles);
+            if (p.d_fat) cudaFree(p.d_fat);
         }
         if (op->d_blobs) cudaFree(op->d_blobs);
         if (op->d_tiles) cudaFree(op->d_tiles);
@@ -1283,7 +1305,8 @@ NSK_API long long nsk_pack_host_simulate_dynamic(void *handle, int k, int lead_s
 
 NSK_API void nsk_pack_host_destroy(void *handle) { delete static_cast<nsk_packed_host_s *>(handle); }
 
-static int pk_launch_shape(nsk_ctx_t ctx, int variant, bool muladd, int k, int nv, pk_fn *fn_out, int *smem_out, int *team)
+static int pk_launch_shape(nsk_ctx_t ctx, int variant, bool muladd, int k, int nv, pk_fn *fn_out, int *smem_out, int *team,
+                           bool *dyn_out = nullptr)
 {
     const PkVariant &V = g_pkv[variant];
     int smem = 0;
@@ -1300,6 +1323,7 @@ static int pk_launch_shape(nsk_ctx_t ctx, int variant, bool muladd, int k, int n
     if (ctx->opt.spmv_ctas_per_sm > 0) per_sm = std::min(per_sm, (int)ctx->opt.spmv_ctas_per_sm);
     const int resident = ctx->prop.multiProcessorCount * per_sm;
     *team = resident;  // all resident CTAs; the plan shares them out over the levels
+    if (dyn_out) *dyn_out = dyn;
     *fn_out = fn;
     *smem_out = smem;
     return NSK_OK;
@@ -1439,7 +1463,8 @@ static int pk_run(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
     PackedOp *op = pk_get(A, V);
     if (!op->ok) { nsk_set_error(ctx, "packed path not applicable: %s", op->why.c_str()); return NSK_ERR_UNSUPPORTED; }
     pk_fn fn; int smem = 0, team = 0;
-    NSK_TRY(pk_launch_shape(ctx, variant, mode == NSK_EXACT_MULADD, k, nv, &fn, &smem, &team));
+    bool dyn = false;
+    NSK_TRY(pk_launch_shape(ctx, variant, mode == NSK_EXACT_MULADD, k, nv, &fn, &smem, &team, &dyn));
     if (team < k) { nsk_set_error(ctx, "packed path: fewer resident CTAs than levels"); return NSK_ERR_UNSUPPORTED; }
     const char *why = "";
     PkLevelPlan *plan = pk_level_plan(A, op, k, level_rows, team, nv, &why);
@@ -1448,6 +1473,21 @@ static int pk_run(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
     for (int l = 0; l < k; l++) maxcount = std::max(maxcount, plan->count[l]);
     if (maxcount == 0) return NSK_OK;
     if (dot_w) NSK_REQUIRE(ctx, k == 1 && plan->grid <= NSK_MAX_PARTIALS, "fused dot: k = 1 and a bounded grid");
+    if (dyn && !plan->d_fat) {
+        // one-time: the level items joined with their tile descriptors
+        size_t total = 0;
+        for (int l = 0; l < k; l++) total = std::max(total, plan->item_off[l] + (size_t)plan->count[l]);
+        std::vector<PkItem> items(total);
+        NSK_CUDA(ctx, cudaMemcpy(items.data(), plan->d_items, sizeof(PkItem) * total, cudaMemcpyDeviceToHost));
+        static_assert(sizeof(PkItem) + sizeof(PkTile) == PK_FAT * 16, "fat item = item + tile");
+        std::vector<unsigned char> fat(total * (size_t)PK_FAT * 16);
+        for (size_t i = 0; i < total; i++) {
+            memcpy(fat.data() + i * PK_FAT * 16, &items[i], sizeof(PkItem));
+            memcpy(fat.data() + i * PK_FAT * 16 + sizeof(PkItem), &op->h_tiles[(size_t)items[i].tile], sizeof(PkTile));
+        }
+        NSK_CUDA(ctx, cudaMalloc(&plan->d_fat, fat.size() + 16));
+        NSK_CUDA(ctx, cudaMemcpy(plan->d_fat, fat.data(), fat.size(), cudaMemcpyHostToDevice));
+    }
 
     if (k > 1)
         NSK_CUDA(ctx, cudaMemsetAsync(plan->d_counters, 0, sizeof(int) * ((size_t)k * plan->ngroups + 4 + NSK_MAX_K), ctx->stream));
@@ -1464,6 +1504,7 @@ static int pk_run(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
     P.blobs = op->d_blobs;
     P.counters = plan->d_counters;
     P.claims = plan->d_counters + (size_t)k * plan->ngroups + 4;  // behind the completion counters, zeroed with them
+    for (int l = 0; l < NSK_MAX_K; l++) P.fat[l] = l < k && plan->d_fat ? plan->d_fat + (size_t)PK_FAT * plan->item_off[l] : nullptr;
     P.group_size = plan->d_group_size;
     P.ngroups = plan->ngroups;
     P.n_cols = A->n_cols;
@@ -1494,11 +1535,19 @@ static int pk_run(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
         for (int l = 0; l < k; l++) {
             double sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             double items = 0;
+            double cyc_lo = 1e30, cyc_hi = 0.0, it_lo = 1e30, it_hi = 0.0;  // spread over the team's CTAs
             for (int b = 0; b < plan->grid; b++) {
                 if ((int)h[(size_t)b * 16 + 9] != l || h[(size_t)b * 16 + 8] == 0) continue;
                 for (int j = 0; j < 8; j++) sum[j] += (double)(long long)h[(size_t)b * 16 + j];
-                items += (double)h[(size_t)b * 16 + 8];
+                const double nb = (double)h[(size_t)b * 16 + 8];
+                items += nb;
+                const double cyc = (double)(long long)h[(size_t)b * 16 + 4] / nb;
+                cyc_lo = std::min(cyc_lo, cyc); cyc_hi = std::max(cyc_hi, cyc);
+                it_lo = std::min(it_lo, nb); it_hi = std::max(it_hi, nb);
             }
+            if (items > 0)
+                fprintf(stderr, "pk_timing k=%d level %d: per-CTA mean cycle %.0f .. %.0f ns, items per CTA %.0f .. %.0f\n", k, l,
+                        cyc_lo, cyc_hi, it_lo, it_hi);
             if (items > 0)
                 fprintf(stderr, "pk_timing k=%d level %d team %d: per item ns: blob->x issue %.0f | x issue->full %.0f | consume %.0f | "
                         "w0 done->all done seen %.0f | cycle %.0f | fence+red(per item) %.0f | D wait stage %.0f | D wait deps %.0f\n",

@@ -19,6 +19,8 @@ import navierstokes_b200 as nsk  # noqa: E402
 from navierstokes_b200 import matgen  # noqa: E402
 
 STATIC, DYNAMIC = 1, 1 | 8
+# claim-ahead depth of the dynamic kernels: default 1 item beyond the stage ring, flag 16 -> 2, flag 32 -> 0
+DYN_MODES = (("ahead 1", 1 | 8), ("ahead 2", 1 | 8 | 16), ("ahead 0", 1 | 8 | 32))
 
 
 def run(ctx, dA, k, xs, flags, mode):
@@ -118,10 +120,11 @@ def fast(ctx):
             xs = [ctx.to_device(matgen.vec_uniform(A.n, 3 + v)) for v in range(nv)]
             for k in (2, 4):
                 ref, s0 = run(ctx, dA, k, xs, STATIC, nsk.EXACT_FMA)
-                for rep in range(3):
-                    got, s1 = run(ctx, dA, k, xs, DYNAMIC, nsk.EXACT_FMA)
-                    same = all(np.array_equal(a.view(np.uint64), b.view(np.uint64)) for ra, rb in zip(ref, got) for a, b in zip(ra, rb))
-                    bad += (not same) or s0 != s1
+                for rep in range(2):
+                    for _, flags in DYN_MODES:
+                        got, s1 = run(ctx, dA, k, xs, flags, nsk.EXACT_FMA)
+                        same = all(np.array_equal(a.view(np.uint64), b.view(np.uint64)) for ra, rb in zip(ref, got) for a, b in zip(ra, rb))
+                        bad += (not same) or s0 != s1
                 print(f"{name} nv={nv} k={k}: strategy {s0}/{s1} {'ok' if bad == 0 else 'MISMATCH'}", flush=True)
         dA.close()
     ctx.set_option("wave_l2_pct", 0)
@@ -137,36 +140,38 @@ def fast(ctx):
         ctx.set_option("pk_flags", STATIC)
         dA.mpk(k, x, lv)
         ref = [v.to_host() for v in lv]
-        ctx.set_option("pk_flags", DYNAMIC)
-        for v in lv:
-            ctx.axpy(1.0, x, v)  # spoil the static result: a launch that wrote nothing must not pass
-        dA.mpk(k, x, lv)
-        same = all(np.array_equal(a.view(np.uint64), v.to_host().view(np.uint64)) for a, v in zip(ref, lv))
+        same = True
+        for _, flags in DYN_MODES:
+            ctx.set_option("pk_flags", flags)
+            for v in lv:
+                ctx.axpy(1.0, x, v)  # spoil the previous result: a launch that wrote nothing must not pass
+            dA.mpk(k, x, lv)
+            same = same and all(np.array_equal(a.view(np.uint64), v.to_host().view(np.uint64)) for a, v in zip(ref, lv))
         bad += not same
         ts = []
-        for flags in (STATIC, DYNAMIC, STATIC, DYNAMIC):
+        for flags in (STATIC,) + tuple(f for _, f in DYN_MODES) + (STATIC,):
             ctx.set_option("pk_flags", flags)
             ts.append(timed(ctx, lambda: dA.mpk(k, x, lv), reps=20))
-        print(f"256^3 k={k}: {'bit-identical' if same else 'MISMATCH'}; static {ts[0]:.4f} / {ts[2]:.4f} ms, dynamic {ts[1]:.4f} / {ts[3]:.4f} ms "
-              f"(strategy {ctx.query('last_mpk_strategy')})", flush=True)
+        print(f"256^3 k={k}: {'bit-identical' if same else 'MISMATCH'}; static {ts[0]:.4f} / {ts[4]:.4f} ms, dynamic ahead 1 {ts[1]:.4f}, "
+              f"ahead 2 {ts[2]:.4f}, ahead 0 {ts[3]:.4f} ms (strategy {ctx.query('last_mpk_strategy')})", flush=True)
     k = 4
     lv2 = [[ctx.empty(A.n) for _ in range(k)] for _ in range(2)]
     ts = []
-    for flags in (STATIC, DYNAMIC):
+    for flags in (STATIC,) + tuple(f for _, f in DYN_MODES):
         ctx.set_option("pk_flags", flags)
         ts.append(timed(ctx, lambda: dA.mpk_multi(k, [x, x2], lv2), reps=10))
-    print(f"256^3 k=4, two vectors: static {ts[0]:.4f} ms, dynamic {ts[1]:.4f} ms", flush=True)
+    print(f"256^3 k=4, two vectors: static {ts[0]:.4f} ms, dynamic ahead 1 {ts[1]:.4f}, ahead 2 {ts[2]:.4f}, ahead 0 {ts[3]:.4f} ms", flush=True)
     lv4 = [ctx.empty(A.n) for _ in range(4)]
-    for l2 in (60, 80):
+    for l2 in (60, 80, 90):
         ctx.set_option("wave_l2_pct", l2)
         ts = []
-        for flags in (STATIC, DYNAMIC):
+        for flags in (STATIC,) + tuple(f for _, f in DYN_MODES):
             ctx.set_option("pk_flags", flags)
             ts.append(timed(ctx, lambda: dA.mpk(4, x, lv4), reps=10))
-        print(f"256^3 k=4, L2 budget {l2} %: static {ts[0]:.4f} ms, dynamic {ts[1]:.4f} ms", flush=True)
+        print(f"256^3 k=4, L2 budget {l2} %: static {ts[0]:.4f} ms, dynamic ahead 1 {ts[1]:.4f}, ahead 2 {ts[2]:.4f}, ahead 0 {ts[3]:.4f} ms", flush=True)
     ctx.set_option("wave_l2_pct", 0)
     lv = [ctx.empty(A.n) for _ in range(4)]
-    for flags in (STATIC, DYNAMIC):
+    for flags in (STATIC,) + tuple(f for _, f in DYN_MODES):
         ctx.set_option("pk_flags", flags)
         dA.mpk(4, x, lv)
         ctx.set_option("pk_timing", 1)
