@@ -110,6 +110,8 @@ int nsk_ctx_device_info(nsk_ctx_t ctx, int *sm_count, int64_t *l2_bytes, int *sm
  *   pk_flags         bit 0 (default on) cache hints for data nobody re-reads | bit 1 poll without sleeping | bit 2
  *                    publish with red.release | bit 3 (8) dynamically claimed tiles in the fused packed kernel
  *                    (experimental: validate with tools/check_dynamic.py before use)
+ *   packed_index     1: pack with index compression and run the kernel instances that read it (experimental, default
+ *                    0; built for the default short-row geometry; validate with tools/check_index.py)
  *   pk_timing        1: the packed kernel prints its stage-cycle breakdown to stderr (debugging aid) */
 int nsk_ctx_set_option(nsk_ctx_t ctx, const char *name, int64_t value);
 
@@ -158,6 +160,11 @@ void nsk_mtx_free(int *irow, int *jcol, double *val);
  * x runs) so a test can compare it entry for entry with the input. */
 int nsk_pack_host_create(int n, int n_cols, int64_t nnz, const int *ptrow, const int *indcol, const double *coef,
                          int variant, void **handle);
+/* The same with index compression: tiles whose rows follow one affine column pattern (every interior row of a stencil
+ * or band) store one base per slot plus explicit indices for the exception rows only.  GPU path: option packed_index. */
+int nsk_pack_host_create_indexed(int n, int n_cols, int64_t nnz, const int *ptrow, const int *indcol, const double *coef,
+                                 int variant, void **handle);
+int nsk_pack_host_index_stats(void *handle, int64_t *tiles_indexed, int64_t *exception_rows);
 const char *nsk_pack_host_why(void *handle);
 int64_t nsk_pack_host_bytes(void *handle);
 int nsk_pack_host_expand(void *handle, int *ptrow, int *indcol, double *coef, int *max_runs, int *max_xlen);

@@ -142,6 +142,7 @@ NSK_API int nsk_ctx_set_option(nsk_ctx_t c, const char *name, int64_t v)
     else if (!strcmp(name, "pipe_w0_pct")) c->opt.pipe_w0_pct = v;
     else if (!strcmp(name, "pk_timing")) c->opt.pk_timing = v;
     else if (!strcmp(name, "pk_flags")) c->opt.pk_flags = v;
+    else if (!strcmp(name, "packed_index")) c->opt.packed_index = v;
     else if (!strcmp(name, "host_overlap")) c->opt.host_overlap = v;
     else if (!strcmp(name, "stream_exact_kind")) c->opt.stream_exact_kind = v;
     else if (!strcmp(name, "pipe_interleave")) c->opt.pipe_interleave = v;

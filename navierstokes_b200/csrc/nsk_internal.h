@@ -50,6 +50,7 @@ struct nsk_options {
     int64_t pipe_variant = 0;     // 0 default, else 1 + index into the level-pipeline kernel table
     int64_t host_overlap = 1;     // host-pointer powers calls: copy level l out while level l+1.. are computed
     int64_t pk_flags = 1;         // packed kernel switches (see PkParams::flags); default 1: evict-first / streaming hints
+    int64_t packed_index = 0;     // 1: pack with index compression (blob format 1) and run the CIDX kernel instances (experimental)
     int64_t pk_timing = 0;        // 1: packed kernel records its stage cycle and prints per-level averages (debug)
     int64_t pipe_w0_pct = 0;      // share weight of level 0's team relative to 100 for every other level; 0 = default
     int64_t pipe_bp_global = -1;  // back-pressure of the packed level pipeline: 0 = level l held by l+1, 1 = level 0 held

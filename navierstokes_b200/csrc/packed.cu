@@ -39,6 +39,8 @@
 // CTAs of a team claim their tiles from a counter instead of taking every G-th one -- see the DYN template parameter.
 #include <algorithm>
 #include <atomic>
+#include <cstring>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <thread>
@@ -108,7 +110,14 @@ struct PkParams {
 };
 
 // blob header (16 ints at the start of every blob)
-enum { PKH_ROW0 = 0, PKH_NROWS, PKH_WIDTH, PKH_RP, PKH_OFF_LENS, PKH_OFF_LCOL, PKH_OFF_VAL, PKH_WORDS = 16 };
+enum { PKH_ROW0 = 0, PKH_NROWS, PKH_WIDTH, PKH_RP, PKH_OFF_LENS, PKH_OFF_LCOL, PKH_OFF_VAL, PKH_FORMAT, PKH_OFF_BASE, PKH_NXP,
+       PKH_WORDS = 16 };
+// PKH_FORMAT 0: explicit local columns, lcol u16[width][rp].
+// PKH_FORMAT 1 (index compression, only in operators packed with it and only read by the CIDX kernel instances): slot e of
+// a REGULAR row r references local column base[e] + r -- true of every interior row of a stencil / band -- so only the
+// exception rows keep explicit indices: lens[r] = length | (x << 7) with x = 0 for a regular row, else 1 + the row's
+// index into lcol u16[width][nxp].  Layout: hdr | base s16[round_up(width, 8)] | lens | lcol (exceptions) | val.
+constexpr int PK_LEN_BITS = 7, PK_LEN_MASK = (1 << PK_LEN_BITS) - 1, PK_MAX_EXC = (1 << (16 - PK_LEN_BITS)) - 1;
 
 __host__ __device__ constexpr int pk_round_up(int v, int m) { return (v + m - 1) / m * m; }
 static inline int pk_blob_bytes(int nrows, int width)
@@ -116,6 +125,40 @@ static inline int pk_blob_bytes(int nrows, int width)
     const int rp = pk_round_up(nrows, 32);
     return PKH_WORDS * 4 + 2 * rp + 2 * width * rp + 8 * width * rp;  // every term is a multiple of 16
 }
+
+static inline int pk_blob_bytes_indexed(int nrows, int width, int nexc)
+{
+    const int rp = pk_round_up(nrows, 32);
+    return PKH_WORDS * 4 + 2 * pk_round_up(width, 8) + 2 * rp + 2 * width * pk_round_up(nexc, 8) + 8 * width * rp;
+}
+
+// host-side decoding of either format: length of row r, local column / value of its entry e
+struct PkBlobView {
+    const int *hdr;
+    const unsigned short *lens, *lcol;
+    const short *base;  // signed: a run that starts at the tile's first row gives the "column r - 1" slot base -1
+    const double *val;
+    int rp, nxp, fmt;
+    explicit PkBlobView(const unsigned char *b)
+    {
+        hdr = reinterpret_cast<const int *>(b);
+        rp = hdr[PKH_RP];
+        fmt = hdr[PKH_FORMAT];
+        nxp = hdr[PKH_NXP];
+        lens = reinterpret_cast<const unsigned short *>(b + hdr[PKH_OFF_LENS]);
+        lcol = reinterpret_cast<const unsigned short *>(b + hdr[PKH_OFF_LCOL]);
+        base = reinterpret_cast<const short *>(b + hdr[PKH_OFF_BASE]);
+        val = reinterpret_cast<const double *>(b + hdr[PKH_OFF_VAL]);
+    }
+    int len(int r) const { return fmt ? (int)(lens[r] & PK_LEN_MASK) : (int)lens[r]; }
+    int col(int e, int r) const
+    {
+        if (!fmt) return lcol[(size_t)e * rp + r];
+        const int x = lens[r] >> PK_LEN_BITS;
+        return x ? (int)lcol[(size_t)e * nxp + (x - 1)] : (int)base[e] + r;
+    }
+    double value(int e, int r) const { return val[(size_t)e * rp + r]; }
+};
 
 __device__ __forceinline__ unsigned long long pk_now()
 {
@@ -152,7 +195,10 @@ __device__ __forceinline__ int pk_wait_groups(const int *cnt, const int *need, i
 constexpr int PK_RING = 16;  // claimed items a CTA remembers (>= STAGES + 2; the publisher may trail the consumers)
 constexpr int PK_FAT = 8;    // int4 per ring entry / per fat item: PkItem (2) + PkTile (6)
 
-template <int T_ROWS, int BLOB_CAP, int XCAP, int STAGES, int NCW, int MINB, int RPT, int NV, bool MULADD, bool DYN = false>
+// CIDX = true: the consumers also understand blob format 1 (index compression, see PKH_FORMAT); operators packed with it
+// are only ever given to these instances.
+template <int T_ROWS, int BLOB_CAP, int XCAP, int STAGES, int NCW, int MINB, int RPT, int NV, bool MULADD, bool DYN = false,
+          bool CIDX = false>
 __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkParams P)
 {
     static_assert(NV == 1 || NV == 2, "one or two right-hand sides");
@@ -566,13 +612,30 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
         const unsigned short *lcol = reinterpret_cast<const unsigned short *>(blob + hdr[PKH_OFF_LCOL]);
         const double *val = reinterpret_cast<const double *>(blob + hdr[PKH_OFF_VAL]);
         const double *xb = reinterpret_cast<const double *>(blob + BLOB_CAP);
+        // format 1: slot bases (first eight held in registers for the whole tile), exception-row stride
+        const int fmt = CIDX ? hdr[PKH_FORMAT] : 0;
+        const int nxp = CIDX ? hdr[PKH_NXP] : 0;
+        const short *base = reinterpret_cast<const short *>(blob + (CIDX ? hdr[PKH_OFF_BASE] : 0));
+        int bs[8];
+        if constexpr (CIDX) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) bs[u] = fmt ? (int)base[u] : 0;
+        }
         for (int rb = 0; rb < nrows; rb += NCT * RPT) {
             int len[RPT];
+            int xo[RPT];  // format 1: 0 = regular row, else 1 + index into the exception columns
             double acc[NV][RPT];
 #pragma unroll
             for (int q = 0; q < RPT; q++) {
                 const int r = rb + q * NCT + tid;
                 len[q] = (r < nrows && row0 + r < row_end) ? (int)lens[r] : -1;  // -1: no row
+                xo[q] = 0;
+                if constexpr (CIDX) {
+                    if (fmt && len[q] >= 0) {
+                        xo[q] = len[q] >> PK_LEN_BITS;
+                        len[q] &= PK_LEN_MASK;
+                    }
+                }
 #pragma unroll
                 for (int v = 0; v < NV; v++) acc[v][q] = 0.0;
             }
@@ -584,7 +647,14 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
 #pragma unroll
                     for (int u = 0; u < 8; u++)
                         if (e0 + u < len[q]) {
-                            const int cidx = lcol[(e0 + u) * rp + r];
+                            int cidx;
+                            if constexpr (CIDX) {
+                                if (!fmt) cidx = lcol[(e0 + u) * rp + r];
+                                else if (xo[q]) cidx = lcol[(e0 + u) * nxp + xo[q] - 1];
+                                else cidx = (e0 == 0 ? bs[u] : (int)base[e0 + u]) + r;  // slots >= 8: from the blob
+                            } else {
+                                cidx = lcol[(e0 + u) * rp + r];
+                            }
 #pragma unroll
                             for (int v = 0; v < NV; v++) xv[v][q][u] = xb[v * XCAP + cidx];
                         }
@@ -693,8 +763,19 @@ constexpr int PK_NV2_VARIANT = 7;
 constexpr int PK_DYN_VARIANT = 7;
 constexpr int PK_DYN_SMEM = 16 + PK_RING * PK_FAT * 16 + 16;  // alignment + claim ring + its two counters
 static bool pk_has_dynamic(int variant, int nv) { return nv == 2 ? variant == PK_NV2_VARIANT : variant == PK_DYN_VARIANT; }
-static pk_fn pk_lookup(int variant, bool muladd, int nv, int *smem, bool dyn = false)
+static pk_fn pk_lookup(int variant, bool muladd, int nv, int *smem, bool dyn = false, bool cidx = false)
 {
+    if (cidx) {  // index-compression instances: same geometries as the dynamic ones, static assignment
+        if (dyn || !pk_has_dynamic(variant, nv)) return nullptr;
+        if (nv == 2) {
+            *smem = (21504 + 2 * 1536 * 8) * 2 + 2 * 2 * 8 + 64 * 8 + 2 * 32 + 2 * 4 + 128;
+            return muladd ? packed_kernel<256, 21504, 1536, 2, 4, 2, 1, 2, true, false, true>
+                          : packed_kernel<256, 21504, 1536, 2, 4, 2, 1, 2, false, false, true>;
+        }
+        *smem = (21504 + 1536 * 8) * 2 + 2 * 2 * 8 + 64 * 8 + 2 * 32 + 2 * 4 + 128;
+        return muladd ? packed_kernel<256, 21504, 1536, 2, 4, 3, 1, 1, true, false, true>
+                      : packed_kernel<256, 21504, 1536, 2, 4, 3, 1, 1, false, false, true>;
+    }
     if (dyn && !pk_has_dynamic(variant, nv)) return nullptr;
     if (nv == 2) {
         if (variant != PK_NV2_VARIANT) return nullptr;
@@ -753,6 +834,7 @@ struct PkLevelPlan {
 
 struct PackedOp {
     int t_rows = 0, blob_cap = 0, xcap = 0;
+    bool indexed = false;  // packed with index compression (read by the CIDX kernel instances only)
     bool ok = false;
     std::string why;
     int ntiles = 0;
@@ -848,7 +930,8 @@ struct PackedHost {
 };
 
 static std::string pk_pack_host(int n, int n_cols, int64_t nnz, const int *ptrow, const int *indcol, const double *coef,
-                                const std::vector<int> &breaks, int t_rows, int blob_cap, int xcap, PackedHost &out)
+                                const std::vector<int> &breaks, int t_rows, int blob_cap, int xcap, PackedHost &out,
+                                bool index_compress = false)
 {
     if (n == 0 || nnz == 0) return "empty operator";
     // 1. tiles: up to t_rows consecutive rows, never across a break, blob within the stage
@@ -876,88 +959,165 @@ static std::string pk_pack_host(int n, int n_cols, int64_t nnz, const int *ptrow
         }
     }
     const int ntiles = (int)tiles.size();
-    std::vector<size_t> off(ntiles + 1, 0);
-    for (int t = 0; t < ntiles; t++) off[t + 1] = off[t] + (size_t)pk_blob_bytes(tiles[t].nrows, widths[t]);
-    const double csr_equiv = 10.0 * (double)nnz + 2.0 * n;
-    if ((double)off[ntiles] > 1.35 * csr_equiv + 65536.0) return "row lengths too ragged for slot-major tiles";
+    {
+        size_t explicit_bytes = 0;
+        for (int t = 0; t < ntiles; t++) explicit_bytes += (size_t)pk_blob_bytes(tiles[t].nrows, widths[t]);
+        const double csr_equiv = 10.0 * (double)nnz + 2.0 * n;
+        if ((double)explicit_bytes > 1.35 * csr_equiv + 65536.0) return "row lengths too ragged for slot-major tiles";
+    }
 
-    // 2. per tile: column runs, local indices, slot-major blob (parallel over tiles)
-    std::vector<unsigned char> &blobs = out.blobs;
-    blobs.assign(off[ntiles] + 64, 0);
     std::vector<PkTile> &ptiles = out.ptiles;
     ptiles.assign(ntiles, PkTile());
-    std::atomic<int> next(0), failed(0);
-    auto work = [&]() {
-        std::vector<int> cols;
-        for (;;) {
-            const int t0 = next.fetch_add(64);
-            if (t0 >= ntiles || failed.load()) return;
-            for (int t = t0; t < std::min(ntiles, t0 + 64); t++) {
-                const nsk_tile &tl = tiles[t];
-                PkTile &pt = ptiles[t];
-                cols.assign(indcol + tl.nz0, indcol + tl.nz1);
-                if (!pk_segments(cols, n_cols, xcap, pt)) { failed.store(1); return; }
-                const int width = widths[t], rp = pk_round_up(tl.nrows, 32);
-                pt.blob_off = (long long)off[t];
-                pt.blob_bytes = pk_blob_bytes(tl.nrows, width);
-                pt.row0 = tl.row0; pt.nrows = tl.nrows;
-                unsigned char *b = blobs.data() + off[t];
-                int *hdr = reinterpret_cast<int *>(b);
-                const int off_lens = PKH_WORDS * 4, off_lcol = off_lens + 2 * rp, off_val = off_lcol + 2 * width * rp;
-                hdr[PKH_ROW0] = tl.row0; hdr[PKH_NROWS] = tl.nrows; hdr[PKH_WIDTH] = width; hdr[PKH_RP] = rp;
-                hdr[PKH_OFF_LENS] = off_lens; hdr[PKH_OFF_LCOL] = off_lcol; hdr[PKH_OFF_VAL] = off_val;
-                unsigned short *lens = reinterpret_cast<unsigned short *>(b + off_lens);
-                unsigned short *lcol = reinterpret_cast<unsigned short *>(b + off_lcol);
-                double *val = reinterpret_cast<double *>(b + off_val);
-                int sstart[PK_MAXSEG], send[PK_MAXSEG], soff[PK_MAXSEG];
-                for (int s = 0; s < pt.nseg; s++) {
-                    sstart[s] = pt.seg_start[s];
-                    send[s] = sstart[s] + (pt.seg_lenoff[s] & 0xffff);
-                    soff[s] = (pt.seg_lenoff[s] >> 16) & 0xffff;
-                }
-                for (int r = 0; r < tl.nrows; r++) {
-                    const int p = ptrow[tl.row0 + r], q = ptrow[tl.row0 + r + 1];
-                    lens[r] = (unsigned short)(q - p);
-                    int s = 0;
-                    for (int j = p; j < q; j++) {
-                        const int cidx = indcol[j];
-                        if (pt.tail && cidx == n_cols - 1) {  // the hand-copied last element of an odd-length vector
-                            lcol[(size_t)(j - p) * rp + r] = (unsigned short)(pt.tail - 1);
-                            val[(size_t)(j - p) * rp + r] = coef[j];
-                            continue;
-                        }
-                        if (s >= pt.nseg || cidx < sstart[s] || cidx >= send[s]) {  // columns ascend within a row in practice: resume, else rescan
-                            s = 0;
-                            while (s < pt.nseg && !(cidx >= sstart[s] && cidx < send[s])) s++;
-                        }
-                        lcol[(size_t)(j - p) * rp + r] = (unsigned short)(soff[s] + (cidx - sstart[s]));
-                        val[(size_t)(j - p) * rp + r] = coef[j];
-                    }
-                }
+    std::vector<int> nexc(ntiles, -1);           // >= 0: the tile is stored with index compression, that many exception rows
+    std::vector<std::vector<int>> bases(index_compress ? ntiles : 0);
+    std::atomic<int> failed(0);
+    struct Runs {
+        int nseg, start[PK_MAXSEG], end[PK_MAXSEG], off[PK_MAXSEG];
+        explicit Runs(const PkTile &pt) : nseg(pt.nseg)
+        {
+            for (int sg = 0; sg < nseg; sg++) {
+                start[sg] = pt.seg_start[sg];
+                end[sg] = start[sg] + (pt.seg_lenoff[sg] & 0xffff);
+                off[sg] = (pt.seg_lenoff[sg] >> 16) & 0xffff;
             }
         }
+        // local column of global column cidx; sg = the run the previous column fell into (columns mostly ascend)
+        int local(int cidx, int &sg) const
+        {
+            if (sg >= nseg || cidx < start[sg] || cidx >= end[sg]) {
+                sg = 0;
+                while (sg < nseg && !(cidx >= start[sg] && cidx < end[sg])) sg++;
+            }
+            return off[sg] + (cidx - start[sg]);
+        }
     };
-    {
+    auto local_col = [&](const PkTile &pt, const Runs &R, int cidx, int &sg) {
+        if (pt.tail && cidx == n_cols - 1) return pt.tail - 1;  // the hand-copied last element of an odd-length vector
+        return R.local(cidx, sg);
+    };
+    auto parallel = [&](const std::function<void(int)> &per_tile) {
+        std::atomic<int> next(0);
+        auto work = [&]() {
+            for (;;) {
+                const int t0 = next.fetch_add(64);
+                if (t0 >= ntiles || failed.load()) return;
+                for (int t = t0; t < std::min(ntiles, t0 + 64); t++) per_tile(t);
+            }
+        };
         const int nth = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
         std::vector<std::thread> th;
         for (int i = 1; i < nth; i++) th.emplace_back(work);
         work();
         for (auto &x : th) x.join();
-    }
+    };
+
+    // 2. per tile: column runs; with index compression also the slot bases and the exception rows (decides the size)
+    parallel([&](int t) {
+        const nsk_tile &tl = tiles[t];
+        PkTile &pt = ptiles[t];
+        std::vector<int> cols(indcol + tl.nz0, indcol + tl.nz1);
+        if (!pk_segments(cols, n_cols, xcap, pt)) { failed.store(1); return; }
+        pt.row0 = tl.row0; pt.nrows = tl.nrows;
+        if (!index_compress) return;
+        const int width = widths[t];
+        if (width == 0 || width > PK_LEN_MASK) return;
+        const Runs R(pt);
+        // reference row: the first one of full width; base[e] = its local column in slot e minus its row number
+        int rref = -1;
+        for (int r = 0; r < tl.nrows && rref < 0; r++)
+            if (ptrow[tl.row0 + r + 1] - ptrow[tl.row0 + r] == width) rref = r;
+        std::vector<int> base(width);
+        {
+            int sg = 0;
+            const int p = ptrow[tl.row0 + rref];
+            for (int e = 0; e < width; e++) {
+                base[e] = local_col(pt, R, indcol[p + e], sg) - rref;
+                if (base[e] < -32768 || base[e] > 32767) return;  // not expressible: the tile keeps explicit indices
+            }
+        }
+        int ne = 0;
+        for (int r = 0; r < tl.nrows; r++) {
+            const int p = ptrow[tl.row0 + r], q = ptrow[tl.row0 + r + 1];
+            int sg = 0;
+            bool regular = true;
+            for (int j = p; j < q && regular; j++) regular = local_col(pt, R, indcol[j], sg) == base[j - p] + r;
+            ne += !regular;
+        }
+        if (ne > PK_MAX_EXC || pk_blob_bytes_indexed(tl.nrows, width, ne) >= pk_blob_bytes(tl.nrows, width)) return;
+        nexc[t] = ne;
+        bases[t].swap(base);
+    });
+    if (failed.load()) return "a tile references x in too many / too long runs";
+
+    std::vector<size_t> off(ntiles + 1, 0);
+    for (int t = 0; t < ntiles; t++)
+        off[t + 1] = off[t] + (size_t)(nexc[t] >= 0 ? pk_blob_bytes_indexed(tiles[t].nrows, widths[t], nexc[t])
+                                                    : pk_blob_bytes(tiles[t].nrows, widths[t]));
+
+    // 3. the blobs, slot-major
+    std::vector<unsigned char> &blobs = out.blobs;
+    blobs.assign(off[ntiles] + 64, 0);
+    parallel([&](int t) {
+        const nsk_tile &tl = tiles[t];
+        PkTile &pt = ptiles[t];
+        const int width = widths[t], rp = pk_round_up(tl.nrows, 32);
+        const bool indexed = nexc[t] >= 0;
+        const int nxp = indexed ? pk_round_up(nexc[t], 8) : 0;
+        pt.blob_off = (long long)off[t];
+        pt.blob_bytes = (int)(off[t + 1] - off[t]);
+        unsigned char *b = blobs.data() + off[t];
+        int *hdr = reinterpret_cast<int *>(b);
+        const int off_base = PKH_WORDS * 4;
+        const int off_lens = off_base + (indexed ? 2 * pk_round_up(width, 8) : 0);
+        const int off_lcol = off_lens + 2 * rp;
+        const int off_val = off_lcol + 2 * width * (indexed ? nxp : rp);
+        hdr[PKH_ROW0] = tl.row0; hdr[PKH_NROWS] = tl.nrows; hdr[PKH_WIDTH] = width; hdr[PKH_RP] = rp;
+        hdr[PKH_OFF_LENS] = off_lens; hdr[PKH_OFF_LCOL] = off_lcol; hdr[PKH_OFF_VAL] = off_val;
+        hdr[PKH_FORMAT] = indexed ? 1 : 0; hdr[PKH_OFF_BASE] = indexed ? off_base : 0; hdr[PKH_NXP] = nxp;
+        unsigned short *lens = reinterpret_cast<unsigned short *>(b + off_lens);
+        unsigned short *lcol = reinterpret_cast<unsigned short *>(b + off_lcol);
+        short *bs = reinterpret_cast<short *>(b + off_base);
+        double *val = reinterpret_cast<double *>(b + off_val);
+        const Runs R(pt);
+        if (indexed)
+            for (int e = 0; e < width; e++) bs[e] = (short)bases[t][e];
+        int xord = 0;
+        for (int r = 0; r < tl.nrows; r++) {
+            const int p = ptrow[tl.row0 + r], q = ptrow[tl.row0 + r + 1];
+            int sg = 0;
+            if (!indexed) {
+                lens[r] = (unsigned short)(q - p);
+                for (int j = p; j < q; j++) {
+                    lcol[(size_t)(j - p) * rp + r] = (unsigned short)local_col(pt, R, indcol[j], sg);
+                    val[(size_t)(j - p) * rp + r] = coef[j];
+                }
+                continue;
+            }
+            bool regular = true;
+            for (int j = p; j < q && regular; j++) regular = local_col(pt, R, indcol[j], sg) == bases[t][j - p] + r;
+            const int x = regular ? 0 : ++xord;
+            lens[r] = (unsigned short)((q - p) | (x << PK_LEN_BITS));
+            sg = 0;
+            for (int j = p; j < q; j++) {
+                if (x) lcol[(size_t)(j - p) * nxp + (x - 1)] = (unsigned short)local_col(pt, R, indcol[j], sg);
+                val[(size_t)(j - p) * rp + r] = coef[j];
+            }
+        }
+    });
     if (failed.load()) return "a tile references x in too many / too long runs";
     out.blob_bytes = off[ntiles];
     return "";
 }
 
-static PackedOp *pk_get(nsk_csr_t A, const PkVariant &V)
+static PackedOp *pk_get(nsk_csr_t A, const PkVariant &V, bool indexed = false)
 {
     g_packed_mu.lock();
     std::vector<PackedOp *> &ops = g_packed[A];
     g_packed_mu.unlock();
     for (PackedOp *op : ops)
-        if (op->t_rows == V.t_rows && op->blob_cap == V.blob_cap && op->xcap == V.xcap) return op;
+        if (op->t_rows == V.t_rows && op->blob_cap == V.blob_cap && op->xcap == V.xcap && op->indexed == indexed) return op;
     PackedOp *op = new PackedOp();
-    op->t_rows = V.t_rows; op->blob_cap = V.blob_cap; op->xcap = V.xcap;
+    op->t_rows = V.t_rows; op->blob_cap = V.blob_cap; op->xcap = V.xcap; op->indexed = indexed;
     ops.push_back(op);
     const int n = A->n;
     const std::vector<int> &ptrow = nsk_csr_host_ptrow(A);
@@ -974,7 +1134,7 @@ static PackedOp *pk_get(nsk_csr_t A, const PkVariant &V)
     }
     PackedHost H;
     op->why = pk_pack_host(n, A->n_cols, A->nnz, ptrow.data(), indcol.data(), coef.data(), A->breaks, V.t_rows, V.blob_cap,
-                           V.xcap, H);
+                           V.xcap, H, indexed);
     if (!op->why.empty()) return op;
     const int ntiles = (int)H.tiles.size();
     if (cudaMalloc(&op->d_blobs, H.blobs.size()) != cudaSuccess ||
@@ -1145,8 +1305,8 @@ struct nsk_packed_host_s {
     int n = 0, n_cols = 0;
 };
 
-NSK_API int nsk_pack_host_create(int n, int n_cols, int64_t nnz, const int *ptrow, const int *indcol, const double *coef,
-                                 int variant, void **out)
+static int pk_host_create(int n, int n_cols, int64_t nnz, const int *ptrow, const int *indcol, const double *coef,
+                          int variant, bool index_compress, void **out)
 {
     if (!out || !ptrow || (nnz > 0 && (!indcol || !coef))) return NSK_ERR_INVALID;
     if (variant < 0 || variant >= g_npkv) return NSK_ERR_INVALID;
@@ -1154,8 +1314,39 @@ NSK_API int nsk_pack_host_create(int n, int n_cols, int64_t nnz, const int *ptro
     h->n = n;
     h->n_cols = n_cols;
     const PkVariant &V = g_pkv[variant];
-    h->why = pk_pack_host(n, n_cols, nnz, ptrow, indcol, coef, std::vector<int>(), V.t_rows, V.blob_cap, V.xcap, h->H);
+    h->why = pk_pack_host(n, n_cols, nnz, ptrow, indcol, coef, std::vector<int>(), V.t_rows, V.blob_cap, V.xcap, h->H,
+                          index_compress);
     *out = h;
+    return NSK_OK;
+}
+
+NSK_API int nsk_pack_host_create(int n, int n_cols, int64_t nnz, const int *ptrow, const int *indcol, const double *coef,
+                                 int variant, void **out)
+{
+    return pk_host_create(n, n_cols, nnz, ptrow, indcol, coef, variant, false, out);
+}
+
+// The same with index compression (blob format 1 where a tile allows it; option packed_index on the GPU path).
+NSK_API int nsk_pack_host_create_indexed(int n, int n_cols, int64_t nnz, const int *ptrow, const int *indcol,
+                                         const double *coef, int variant, void **out)
+{
+    return pk_host_create(n, n_cols, nnz, ptrow, indcol, coef, variant, true, out);
+}
+
+// Tiles stored in the compressed-index format / exception rows over all of them (0 / 0 for a plain pack).
+NSK_API int nsk_pack_host_index_stats(void *handle, int64_t *tiles_indexed, int64_t *exception_rows)
+{
+    nsk_packed_host_s *h = static_cast<nsk_packed_host_s *>(handle);
+    if (!h->why.empty()) return NSK_ERR_UNSUPPORTED;
+    int64_t ti = 0, ex = 0;
+    for (const PkTile &pt : h->H.ptiles) {
+        const PkBlobView B(h->H.blobs.data() + pt.blob_off);
+        if (!B.fmt) continue;
+        ti++;
+        for (int r = 0; r < pt.nrows; r++) ex += (B.lens[r] >> PK_LEN_BITS) != 0;
+    }
+    if (tiles_indexed) *tiles_indexed = ti;
+    if (exception_rows) *exception_rows = ex;
     return NSK_OK;
 }
 
@@ -1180,15 +1371,11 @@ NSK_API int nsk_pack_host_expand(void *handle, int *ptrow, int *indcol, double *
         const PkTile &pt = h->H.ptiles[t];
         mr = std::max(mr, pt.nseg);
         mx = std::max(mx, pt.xlen);
-        const unsigned char *b = h->H.blobs.data() + pt.blob_off;
-        const int *hdr = reinterpret_cast<const int *>(b);
-        const int rp = hdr[PKH_RP];
-        const unsigned short *lens = reinterpret_cast<const unsigned short *>(b + hdr[PKH_OFF_LENS]);
-        const unsigned short *lcol = reinterpret_cast<const unsigned short *>(b + hdr[PKH_OFF_LCOL]);
-        const double *val = reinterpret_cast<const double *>(b + hdr[PKH_OFF_VAL]);
+        const PkBlobView B(h->H.blobs.data() + pt.blob_off);
+        const int *hdr = B.hdr;
         for (int r = 0; r < hdr[PKH_NROWS]; r++) {
-            for (int e = 0; e < (int)lens[r]; e++) {
-                const int lc = lcol[(size_t)e * rp + r];
+            for (int e = 0; e < B.len(r); e++) {
+                const int lc = B.col(e, r);
                 int g = -1;
                 if (pt.tail && lc == pt.tail - 1) g = h->n_cols - 1;
                 for (int s = 0; s < pt.nseg && g < 0; s++) {
@@ -1197,7 +1384,7 @@ NSK_API int nsk_pack_host_expand(void *handle, int *ptrow, int *indcol, double *
                 }
                 if (g < 0) return NSK_ERR_INVALID;
                 indcol[k] = g;
-                coef[k] = val[(size_t)e * rp + r];
+                coef[k] = B.value(e, r);
                 k++;
             }
             ptrow[hdr[PKH_ROW0] + r + 1] = (int)k;
@@ -1256,15 +1443,12 @@ static long long pk_host_simulate(void *handle, int k, int lead_slack_tiles, int
     std::vector<std::vector<int>> reads((size_t)ntiles);
     for (int t = 0; t < ntiles; t++) {
         const PkTile &pt = h->H.ptiles[t];
-        const unsigned char *b = h->H.blobs.data() + pt.blob_off;
-        const int *hdr = reinterpret_cast<const int *>(b);
-        const int rp = hdr[PKH_RP];
-        const unsigned short *lens = reinterpret_cast<const unsigned short *>(b + hdr[PKH_OFF_LENS]);
-        const unsigned short *lcol = reinterpret_cast<const unsigned short *>(b + hdr[PKH_OFF_LCOL]);
+        const PkBlobView B(h->H.blobs.data() + pt.blob_off);
+        const int *hdr = B.hdr;
         std::vector<int> &rd = reads[(size_t)t];
         for (int r = 0; r < hdr[PKH_NROWS]; r++)
-            for (int e = 0; e < (int)lens[r]; e++) {
-                const int lc = lcol[(size_t)e * rp + r];
+            for (int e = 0; e < B.len(r); e++) {
+                const int lc = B.col(e, r);
                 int g = -1;
                 if (pt.tail && lc == pt.tail - 1) g = h->n_cols - 1;
                 for (int sgm = 0; sgm < pt.nseg && g < 0; sgm++) {
@@ -1306,12 +1490,12 @@ NSK_API long long nsk_pack_host_simulate_dynamic(void *handle, int k, int lead_s
 NSK_API void nsk_pack_host_destroy(void *handle) { delete static_cast<nsk_packed_host_s *>(handle); }
 
 static int pk_launch_shape(nsk_ctx_t ctx, int variant, bool muladd, int k, int nv, pk_fn *fn_out, int *smem_out, int *team,
-                           bool *dyn_out = nullptr)
+                           bool *dyn_out = nullptr, bool cidx = false)
 {
     const PkVariant &V = g_pkv[variant];
     int smem = 0;
-    const bool dyn = k > 1 && (ctx->opt.pk_flags & 8) && pk_has_dynamic(variant, nv);
-    pk_fn fn = pk_lookup(variant, muladd, nv, &smem, dyn);
+    const bool dyn = !cidx && k > 1 && (ctx->opt.pk_flags & 8) && pk_has_dynamic(variant, nv);
+    pk_fn fn = pk_lookup(variant, muladd, nv, &smem, dyn, cidx);
     if (!fn) {
         nsk_set_error(ctx, "packed path: no two-vector kernel for this tile geometry");
         return NSK_ERR_UNSUPPORTED;
@@ -1460,11 +1644,13 @@ static int pk_run(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
             nsk_set_error(ctx, "packed path: output is not 16-byte aligned");
             return NSK_ERR_UNSUPPORTED;
         }
-    PackedOp *op = pk_get(A, V);
+    // index compression (option packed_index, experimental): its own packed copy of the operator, its own kernel instances
+    const bool indexed = ctx->opt.packed_index && pk_has_dynamic(variant, nv);
+    PackedOp *op = pk_get(A, V, indexed);
     if (!op->ok) { nsk_set_error(ctx, "packed path not applicable: %s", op->why.c_str()); return NSK_ERR_UNSUPPORTED; }
     pk_fn fn; int smem = 0, team = 0;
     bool dyn = false;
-    NSK_TRY(pk_launch_shape(ctx, variant, mode == NSK_EXACT_MULADD, k, nv, &fn, &smem, &team, &dyn));
+    NSK_TRY(pk_launch_shape(ctx, variant, mode == NSK_EXACT_MULADD, k, nv, &fn, &smem, &team, &dyn, indexed));
     if (team < k) { nsk_set_error(ctx, "packed path: fewer resident CTAs than levels"); return NSK_ERR_UNSUPPORTED; }
     const char *why = "";
     PkLevelPlan *plan = pk_level_plan(A, op, k, level_rows, team, nv, &why);
