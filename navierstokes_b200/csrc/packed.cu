@@ -616,24 +616,33 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
         const int fmt = CIDX ? hdr[PKH_FORMAT] : 0;
         const int nxp = CIDX ? hdr[PKH_NXP] : 0;
         const short *base = reinterpret_cast<const short *>(blob + (CIDX ? hdr[PKH_OFF_BASE] : 0));
-        int bs[8];
+        int bs[8];  // bases of the eight slots in flight; tiles of width <= 8 load them once
+        const bool bs_once = width <= 8;
         if constexpr (CIDX) {
 #pragma unroll
             for (int u = 0; u < 8; u++) bs[u] = fmt ? (int)base[u] : 0;
         }
         for (int rb = 0; rb < nrows; rb += NCT * RPT) {
             int len[RPT];
-            int xo[RPT];  // format 1: 0 = regular row, else 1 + index into the exception columns
+            // CIDX: whether the row reads explicit indices (every row of a format-0 tile, exception rows of a format-1
+            // tile) and where: lcol[slot * lstride + lrow[q]]; regular rows compute base + r.  Kept branch-free (one
+            // predicated load + select per entry) so that the loads of a row still issue back to back.
+            bool lexp[RPT];
+            int lrow[RPT];
+            const int lstride = fmt ? nxp : rp;
             double acc[NV][RPT];
 #pragma unroll
             for (int q = 0; q < RPT; q++) {
                 const int r = rb + q * NCT + tid;
                 len[q] = (r < nrows && row0 + r < row_end) ? (int)lens[r] : -1;  // -1: no row
-                xo[q] = 0;
+                lexp[q] = true;
+                lrow[q] = r;
                 if constexpr (CIDX) {
                     if (fmt && len[q] >= 0) {
-                        xo[q] = len[q] >> PK_LEN_BITS;
+                        const int x = len[q] >> PK_LEN_BITS;
                         len[q] &= PK_LEN_MASK;
+                        lexp[q] = x != 0;
+                        lrow[q] = x - 1;
                     }
                 }
 #pragma unroll
@@ -641,23 +650,42 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
             }
             for (int e0 = 0; e0 < width; e0 += 8) {
                 double xv[NV][RPT][8];
+                if constexpr (CIDX) {
+                    if (fmt && !bs_once) {  // wide rows: the bases of this group of slots (the array is padded to a multiple of 8)
+#pragma unroll
+                        for (int u = 0; u < 8; u++) bs[u] = (int)base[e0 + u];
+                    }
+                }
 #pragma unroll
                 for (int q = 0; q < RPT; q++) {
                     const int r = rb + q * NCT + tid;
+                    if constexpr (CIDX) {
+                        // two passes of single-load conditionals (the compiler predicates those; a nested conditional
+                        // became a branch per entry).  Open item: under the 80-register cap of three CTAs per SM ptxas
+                        // still threads each entry's loads through the fma chain one at a time (SASS), so this path is
+                        // slower than the explicit format although it moves 19 % fewer bytes; scheduling fences made
+                        // it spill.  Needs a two-CTA geometry (146 registers) or hand-scheduled loads.
+                        int ci[8];
 #pragma unroll
-                    for (int u = 0; u < 8; u++)
-                        if (e0 + u < len[q]) {
-                            int cidx;
-                            if constexpr (CIDX) {
-                                if (!fmt) cidx = lcol[(e0 + u) * rp + r];
-                                else if (xo[q]) cidx = lcol[(e0 + u) * nxp + xo[q] - 1];
-                                else cidx = (e0 == 0 ? bs[u] : (int)base[e0 + u]) + r;  // slots >= 8: from the blob
-                            } else {
-                                cidx = lcol[(e0 + u) * rp + r];
-                            }
-#pragma unroll
-                            for (int v = 0; v < NV; v++) xv[v][q][u] = xb[v * XCAP + cidx];
+                        for (int u = 0; u < 8; u++) {
+                            ci[u] = bs[u] + r;
+                            if (lexp[q] && e0 + u < len[q]) ci[u] = lcol[(e0 + u) * lstride + lrow[q]];
                         }
+#pragma unroll
+                        for (int u = 0; u < 8; u++)
+                            if (e0 + u < len[q]) {
+#pragma unroll
+                                for (int v = 0; v < NV; v++) xv[v][q][u] = xb[v * XCAP + ci[u]];
+                            }
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 8; u++)
+                            if (e0 + u < len[q]) {
+                                const int cidx = lcol[(e0 + u) * rp + r];
+#pragma unroll
+                                for (int v = 0; v < NV; v++) xv[v][q][u] = xb[v * XCAP + cidx];
+                            }
+                    }
                 }
 #pragma unroll
                 for (int q = 0; q < RPT; q++) {
