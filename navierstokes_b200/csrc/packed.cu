@@ -110,14 +110,16 @@ struct PkParams {
 };
 
 // blob header (16 ints at the start of every blob)
-enum { PKH_ROW0 = 0, PKH_NROWS, PKH_WIDTH, PKH_RP, PKH_OFF_LENS, PKH_OFF_LCOL, PKH_OFF_VAL, PKH_FORMAT, PKH_OFF_BASE, PKH_NXP,
+enum { PKH_ROW0 = 0, PKH_NROWS, PKH_WIDTH, PKH_RP, PKH_OFF_LENS, PKH_OFF_LCOL, PKH_OFF_VAL, PKH_FORMAT, PKH_OFF_BASE,
        PKH_WORDS = 16 };
-// PKH_FORMAT 0: explicit local columns, lcol u16[width][rp].
-// PKH_FORMAT 1 (index compression, only in operators packed with it and only read by the CIDX kernel instances): slot e of
-// a REGULAR row r references local column base[e] + r -- true of every interior row of a stencil / band -- so only the
-// exception rows keep explicit indices: lens[r] = length | (x << 7) with x = 0 for a regular row, else 1 + the row's
-// index into lcol u16[width][nxp].  Layout: hdr | base s16[round_up(width, 8)] | lens | lcol (exceptions) | val.
-constexpr int PK_LEN_BITS = 7, PK_LEN_MASK = (1 << PK_LEN_BITS) - 1, PK_MAX_EXC = (1 << (16 - PK_LEN_BITS)) - 1;
+// PKH_FORMAT 0: explicit local columns, lcol u16[width][rp], lens[r] = row length.
+// PKH_FORMAT 1 (index compression; only in operators packed with it, only read by the CIDX kernel instances): the tile
+// has ONE column pattern -- slot e of row r references local column base[e] + r, true of every interior row of a stencil
+// or band -- and a row may lack some of the slots (line ends, domain faces): lens[r] is then the bit mask of the slots the
+// row has, its entries sit in those slots of val, and no per-entry index is stored at all.  Slots ascend with the row's
+// original entry order, so the fma chain is unchanged.  Tiles with a row that is not a sub-pattern, or wider than 8
+// slots, stay in format 0.  Layout: hdr | base s16[round_up(width, 8)] | masks u16[rp] | val f64[width][rp].
+constexpr int PK_MASK_SLOTS = 8;
 
 __host__ __device__ constexpr int pk_round_up(int v, int m) { return (v + m - 1) / m * m; }
 static inline int pk_blob_bytes(int nrows, int width)
@@ -126,10 +128,10 @@ static inline int pk_blob_bytes(int nrows, int width)
     return PKH_WORDS * 4 + 2 * rp + 2 * width * rp + 8 * width * rp;  // every term is a multiple of 16
 }
 
-static inline int pk_blob_bytes_indexed(int nrows, int width, int nexc)
+static inline int pk_blob_bytes_indexed(int nrows, int width)
 {
     const int rp = pk_round_up(nrows, 32);
-    return PKH_WORDS * 4 + 2 * pk_round_up(width, 8) + 2 * rp + 2 * width * pk_round_up(nexc, 8) + 8 * width * rp;
+    return PKH_WORDS * 4 + 2 * pk_round_up(width, 8) + 2 * rp + 8 * width * rp;
 }
 
 // host-side decoding of either format: length of row r, local column / value of its entry e
@@ -138,26 +140,37 @@ struct PkBlobView {
     const unsigned short *lens, *lcol;
     const short *base;  // signed: a run that starts at the tile's first row gives the "column r - 1" slot base -1
     const double *val;
-    int rp, nxp, fmt;
+    int rp, fmt;
     explicit PkBlobView(const unsigned char *b)
     {
         hdr = reinterpret_cast<const int *>(b);
         rp = hdr[PKH_RP];
         fmt = hdr[PKH_FORMAT];
-        nxp = hdr[PKH_NXP];
         lens = reinterpret_cast<const unsigned short *>(b + hdr[PKH_OFF_LENS]);
         lcol = reinterpret_cast<const unsigned short *>(b + hdr[PKH_OFF_LCOL]);
         base = reinterpret_cast<const short *>(b + hdr[PKH_OFF_BASE]);
         val = reinterpret_cast<const double *>(b + hdr[PKH_OFF_VAL]);
     }
-    int len(int r) const { return fmt ? (int)(lens[r] & PK_LEN_MASK) : (int)lens[r]; }
-    int col(int e, int r) const
+    int slot(int e, int r) const  // slot of the row's e-th entry
     {
-        if (!fmt) return lcol[(size_t)e * rp + r];
-        const int x = lens[r] >> PK_LEN_BITS;
-        return x ? (int)lcol[(size_t)e * nxp + (x - 1)] : (int)base[e] + r;
+        if (!fmt) return e;
+        unsigned m = lens[r];
+        for (int s = 0; s < PK_MASK_SLOTS; s++)
+            if ((m >> s) & 1u) {
+                if (e == 0) return s;
+                e--;
+            }
+        return -1;
     }
-    double value(int e, int r) const { return val[(size_t)e * rp + r]; }
+    int len(int r) const
+    {
+        if (!fmt) return (int)lens[r];
+        int n = 0;
+        for (unsigned m = lens[r]; m; m &= m - 1) n++;
+        return n;
+    }
+    int col(int e, int r) const { return fmt ? (int)base[slot(e, r)] + r : (int)lcol[(size_t)e * rp + r]; }
+    double value(int e, int r) const { return val[(size_t)slot(e, r) * rp + r]; }
 };
 
 __device__ __forceinline__ unsigned long long pk_now()
@@ -612,80 +625,79 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
         const unsigned short *lcol = reinterpret_cast<const unsigned short *>(blob + hdr[PKH_OFF_LCOL]);
         const double *val = reinterpret_cast<const double *>(blob + hdr[PKH_OFF_VAL]);
         const double *xb = reinterpret_cast<const double *>(blob + BLOB_CAP);
-        // format 1: slot bases (first eight held in registers for the whole tile), exception-row stride
-        const int fmt = CIDX ? hdr[PKH_FORMAT] : 0;
-        const int nxp = CIDX ? hdr[PKH_NXP] : 0;
-        const short *base = reinterpret_cast<const short *>(blob + (CIDX ? hdr[PKH_OFF_BASE] : 0));
-        int bs[8];  // bases of the eight slots in flight; tiles of width <= 8 load them once
-        const bool bs_once = width <= 8;
+        bool masked = false;
         if constexpr (CIDX) {
+            if (hdr[PKH_FORMAT]) {
+                // format 1: one pattern per tile (at most eight slots): the entry in slot u of row r multiplies
+                // x[base[u] + r]; no index is loaded, the row's mask says which slots it has.  A loop nest of its own,
+                // so that the slot bases are not live across the explicit-index loop below (register cap: 80 at 3 CTAs/SM).
+                masked = true;
+                const int4 bq = *reinterpret_cast<const int4 *>(blob + hdr[PKH_OFF_BASE]);  // eight signed 16-bit bases
+                int bs[8];
+                bs[0] = (int)(short)(bq.x & 0xffff); bs[1] = bq.x >> 16;
+                bs[2] = (int)(short)(bq.y & 0xffff); bs[3] = bq.y >> 16;
+                bs[4] = (int)(short)(bq.z & 0xffff); bs[5] = bq.z >> 16;
+                bs[6] = (int)(short)(bq.w & 0xffff); bs[7] = bq.w >> 16;
+                for (int rb = 0; rb < nrows; rb += NCT * RPT) {
 #pragma unroll
-            for (int u = 0; u < 8; u++) bs[u] = fmt ? (int)base[u] : 0;
+                    for (int q = 0; q < RPT; q++) {
+                        const int r = rb + q * NCT + tid;
+                        const bool have = r < nrows && row0 + r < row_end;
+                        const int m = have ? (int)lens[r] : 0;
+                        double xv[NV][8], av[8];
+                        const double *vp = val + r;  // slot by slot: one running pointer instead of eight offsets
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            if ((m >> u) & 1) {
+#pragma unroll
+                                for (int v = 0; v < NV; v++) xv[v][u] = xb[v * XCAP + bs[u] + r];
+                                av[u] = *vp;
+                            }
+                            vp += rp;
+                        }
+                        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                        for (int u = 0; u < 8; u++)
+                            if ((m >> u) & 1) {
+                                a0 = row_op<MULADD>(av[u], xv[0][u], a0);
+                                if (NV == 2) a1 = row_op<MULADD>(av[u], xv[NV - 1][u], a1);
+                            }
+                        if (have) {
+                            if (stream_out) __stcs(dst + row0 + r, a0);
+                            else dst[row0 + r] = a0;
+                            if (NV == 2) {
+                                if (stream_out) __stcs(dst2 + row0 + r, a1);
+                                else dst2[row0 + r] = a1;
+                            }
+                            if (NV == 1 && P.dot_w) dot_acc = __fma_rn(P.dot_w[row0 + r], a0, dot_acc);
+                        }
+                    }
+                }
+            }
         }
+        if (!masked)
         for (int rb = 0; rb < nrows; rb += NCT * RPT) {
             int len[RPT];
-            // CIDX: whether the row reads explicit indices (every row of a format-0 tile, exception rows of a format-1
-            // tile) and where: lcol[slot * lstride + lrow[q]]; regular rows compute base + r.  Kept branch-free (one
-            // predicated load + select per entry) so that the loads of a row still issue back to back.
-            bool lexp[RPT];
-            int lrow[RPT];
-            const int lstride = fmt ? nxp : rp;
             double acc[NV][RPT];
 #pragma unroll
             for (int q = 0; q < RPT; q++) {
                 const int r = rb + q * NCT + tid;
                 len[q] = (r < nrows && row0 + r < row_end) ? (int)lens[r] : -1;  // -1: no row
-                lexp[q] = true;
-                lrow[q] = r;
-                if constexpr (CIDX) {
-                    if (fmt && len[q] >= 0) {
-                        const int x = len[q] >> PK_LEN_BITS;
-                        len[q] &= PK_LEN_MASK;
-                        lexp[q] = x != 0;
-                        lrow[q] = x - 1;
-                    }
-                }
 #pragma unroll
                 for (int v = 0; v < NV; v++) acc[v][q] = 0.0;
             }
             for (int e0 = 0; e0 < width; e0 += 8) {
                 double xv[NV][RPT][8];
-                if constexpr (CIDX) {
-                    if (fmt && !bs_once) {  // wide rows: the bases of this group of slots (the array is padded to a multiple of 8)
-#pragma unroll
-                        for (int u = 0; u < 8; u++) bs[u] = (int)base[e0 + u];
-                    }
-                }
 #pragma unroll
                 for (int q = 0; q < RPT; q++) {
                     const int r = rb + q * NCT + tid;
-                    if constexpr (CIDX) {
-                        // two passes of single-load conditionals (the compiler predicates those; a nested conditional
-                        // became a branch per entry).  Open item: under the 80-register cap of three CTAs per SM ptxas
-                        // still threads each entry's loads through the fma chain one at a time (SASS), so this path is
-                        // slower than the explicit format although it moves 19 % fewer bytes; scheduling fences made
-                        // it spill.  Needs a two-CTA geometry (146 registers) or hand-scheduled loads.
-                        int ci[8];
 #pragma unroll
-                        for (int u = 0; u < 8; u++) {
-                            ci[u] = bs[u] + r;
-                            if (lexp[q] && e0 + u < len[q]) ci[u] = lcol[(e0 + u) * lstride + lrow[q]];
+                    for (int u = 0; u < 8; u++)
+                        if (e0 + u < len[q]) {
+                            const int cidx = lcol[(e0 + u) * rp + r];
+#pragma unroll
+                            for (int v = 0; v < NV; v++) xv[v][q][u] = xb[v * XCAP + cidx];
                         }
-#pragma unroll
-                        for (int u = 0; u < 8; u++)
-                            if (e0 + u < len[q]) {
-#pragma unroll
-                                for (int v = 0; v < NV; v++) xv[v][q][u] = xb[v * XCAP + ci[u]];
-                            }
-                    } else {
-#pragma unroll
-                        for (int u = 0; u < 8; u++)
-                            if (e0 + u < len[q]) {
-                                const int cidx = lcol[(e0 + u) * rp + r];
-#pragma unroll
-                                for (int v = 0; v < NV; v++) xv[v][q][u] = xb[v * XCAP + cidx];
-                            }
-                    }
                 }
 #pragma unroll
                 for (int q = 0; q < RPT; q++) {
@@ -996,7 +1008,7 @@ static std::string pk_pack_host(int n, int n_cols, int64_t nnz, const int *ptrow
 
     std::vector<PkTile> &ptiles = out.ptiles;
     ptiles.assign(ntiles, PkTile());
-    std::vector<int> nexc(ntiles, -1);           // >= 0: the tile is stored with index compression, that many exception rows
+    std::vector<char> indexed_tile(ntiles, 0);   // 1: the tile is stored in format 1 (one pattern + per-row slot masks)
     std::vector<std::vector<int>> bases(index_compress ? ntiles : 0);
     std::atomic<int> failed(0);
     struct Runs {
@@ -1048,9 +1060,9 @@ static std::string pk_pack_host(int n, int n_cols, int64_t nnz, const int *ptrow
         pt.row0 = tl.row0; pt.nrows = tl.nrows;
         if (!index_compress) return;
         const int width = widths[t];
-        if (width == 0 || width > PK_LEN_MASK) return;
+        if (width == 0 || width > PK_MASK_SLOTS) return;
         const Runs R(pt);
-        // reference row: the first one of full width; base[e] = its local column in slot e minus its row number
+        // the pattern: the first row of full width; base[e] = its local column in slot e minus its row number
         int rref = -1;
         for (int r = 0; r < tl.nrows && rref < 0; r++)
             if (ptrow[tl.row0 + r + 1] - ptrow[tl.row0 + r] == width) rref = r;
@@ -1063,24 +1075,27 @@ static std::string pk_pack_host(int n, int n_cols, int64_t nnz, const int *ptrow
                 if (base[e] < -32768 || base[e] > 32767) return;  // not expressible: the tile keeps explicit indices
             }
         }
-        int ne = 0;
+        // every row must be a sub-pattern: its entries, in order, match slots of ascending index
         for (int r = 0; r < tl.nrows; r++) {
             const int p = ptrow[tl.row0 + r], q = ptrow[tl.row0 + r + 1];
-            int sg = 0;
-            bool regular = true;
-            for (int j = p; j < q && regular; j++) regular = local_col(pt, R, indcol[j], sg) == base[j - p] + r;
-            ne += !regular;
+            int sg = 0, e = 0;
+            for (int j = p; j < q; j++) {
+                const int lc = local_col(pt, R, indcol[j], sg);
+                while (e < width && base[e] + r != lc) e++;
+                if (e == width) return;
+                e++;
+            }
         }
-        if (ne > PK_MAX_EXC || pk_blob_bytes_indexed(tl.nrows, width, ne) >= pk_blob_bytes(tl.nrows, width)) return;
-        nexc[t] = ne;
+        if (pk_blob_bytes_indexed(tl.nrows, width) >= pk_blob_bytes(tl.nrows, width)) return;
+        indexed_tile[t] = 1;
         bases[t].swap(base);
     });
     if (failed.load()) return "a tile references x in too many / too long runs";
 
     std::vector<size_t> off(ntiles + 1, 0);
     for (int t = 0; t < ntiles; t++)
-        off[t + 1] = off[t] + (size_t)(nexc[t] >= 0 ? pk_blob_bytes_indexed(tiles[t].nrows, widths[t], nexc[t])
-                                                    : pk_blob_bytes(tiles[t].nrows, widths[t]));
+        off[t + 1] = off[t] + (size_t)(indexed_tile[t] ? pk_blob_bytes_indexed(tiles[t].nrows, widths[t])
+                                                       : pk_blob_bytes(tiles[t].nrows, widths[t]));
 
     // 3. the blobs, slot-major
     std::vector<unsigned char> &blobs = out.blobs;
@@ -1089,8 +1104,7 @@ static std::string pk_pack_host(int n, int n_cols, int64_t nnz, const int *ptrow
         const nsk_tile &tl = tiles[t];
         PkTile &pt = ptiles[t];
         const int width = widths[t], rp = pk_round_up(tl.nrows, 32);
-        const bool indexed = nexc[t] >= 0;
-        const int nxp = indexed ? pk_round_up(nexc[t], 8) : 0;
+        const bool indexed = indexed_tile[t] != 0;
         pt.blob_off = (long long)off[t];
         pt.blob_bytes = (int)(off[t + 1] - off[t]);
         unsigned char *b = blobs.data() + off[t];
@@ -1098,10 +1112,10 @@ static std::string pk_pack_host(int n, int n_cols, int64_t nnz, const int *ptrow
         const int off_base = PKH_WORDS * 4;
         const int off_lens = off_base + (indexed ? 2 * pk_round_up(width, 8) : 0);
         const int off_lcol = off_lens + 2 * rp;
-        const int off_val = off_lcol + 2 * width * (indexed ? nxp : rp);
+        const int off_val = off_lcol + (indexed ? 0 : 2 * width * rp);
         hdr[PKH_ROW0] = tl.row0; hdr[PKH_NROWS] = tl.nrows; hdr[PKH_WIDTH] = width; hdr[PKH_RP] = rp;
         hdr[PKH_OFF_LENS] = off_lens; hdr[PKH_OFF_LCOL] = off_lcol; hdr[PKH_OFF_VAL] = off_val;
-        hdr[PKH_FORMAT] = indexed ? 1 : 0; hdr[PKH_OFF_BASE] = indexed ? off_base : 0; hdr[PKH_NXP] = nxp;
+        hdr[PKH_FORMAT] = indexed ? 1 : 0; hdr[PKH_OFF_BASE] = indexed ? off_base : 0;
         unsigned short *lens = reinterpret_cast<unsigned short *>(b + off_lens);
         unsigned short *lcol = reinterpret_cast<unsigned short *>(b + off_lcol);
         short *bs = reinterpret_cast<short *>(b + off_base);
@@ -1109,7 +1123,6 @@ static std::string pk_pack_host(int n, int n_cols, int64_t nnz, const int *ptrow
         const Runs R(pt);
         if (indexed)
             for (int e = 0; e < width; e++) bs[e] = (short)bases[t][e];
-        int xord = 0;
         for (int r = 0; r < tl.nrows; r++) {
             const int p = ptrow[tl.row0 + r], q = ptrow[tl.row0 + r + 1];
             int sg = 0;
@@ -1121,15 +1134,16 @@ static std::string pk_pack_host(int n, int n_cols, int64_t nnz, const int *ptrow
                 }
                 continue;
             }
-            bool regular = true;
-            for (int j = p; j < q && regular; j++) regular = local_col(pt, R, indcol[j], sg) == bases[t][j - p] + r;
-            const int x = regular ? 0 : ++xord;
-            lens[r] = (unsigned short)((q - p) | (x << PK_LEN_BITS));
-            sg = 0;
+            unsigned mask = 0;
+            int e = 0;
             for (int j = p; j < q; j++) {
-                if (x) lcol[(size_t)(j - p) * nxp + (x - 1)] = (unsigned short)local_col(pt, R, indcol[j], sg);
-                val[(size_t)(j - p) * rp + r] = coef[j];
+                const int lc = local_col(pt, R, indcol[j], sg);
+                while (bases[t][e] + r != lc) e++;  // phase 2 proved that a slot matches
+                mask |= 1u << e;
+                val[(size_t)e * rp + r] = coef[j];
+                e++;
             }
+            lens[r] = (unsigned short)mask;
         }
     });
     if (failed.load()) return "a tile references x in too many / too long runs";
@@ -1361,7 +1375,8 @@ NSK_API int nsk_pack_host_create_indexed(int n, int n_cols, int64_t nnz, const i
     return pk_host_create(n, n_cols, nnz, ptrow, indcol, coef, variant, true, out);
 }
 
-// Tiles stored in the compressed-index format / exception rows over all of them (0 / 0 for a plain pack).
+// Tiles stored in the compressed-index format / rows in them that lack some slot of their tile's pattern (0 / 0 for a
+// plain pack).
 NSK_API int nsk_pack_host_index_stats(void *handle, int64_t *tiles_indexed, int64_t *exception_rows)
 {
     nsk_packed_host_s *h = static_cast<nsk_packed_host_s *>(handle);
@@ -1371,7 +1386,7 @@ NSK_API int nsk_pack_host_index_stats(void *handle, int64_t *tiles_indexed, int6
         const PkBlobView B(h->H.blobs.data() + pt.blob_off);
         if (!B.fmt) continue;
         ti++;
-        for (int r = 0; r < pt.nrows; r++) ex += (B.lens[r] >> PK_LEN_BITS) != 0;
+        for (int r = 0; r < pt.nrows; r++) ex += B.len(r) != B.hdr[PKH_WIDTH];  // rows that lack slots of the pattern
     }
     if (tiles_indexed) *tiles_indexed = ti;
     if (exception_rows) *exception_rows = ex;

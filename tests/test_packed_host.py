@@ -76,15 +76,14 @@ def test_pack_indexed_expand_round_trip(gen, args, variant):
 
 
 def test_pack_indexed_stencil_sizes():
-    """7-point operator, 256-row tiles = x-lines: every tile is indexed with its two line-end rows as exceptions
-    (more on the y / z faces, where a whole line lacks a neighbour line and the pattern shifts uniformly -> regular),
-    8.3 bytes per nonzero instead of 10.3; odd vector length and the tail slot go through the same path."""
+    """7-point operator, 256-row tiles = x-lines: every tile has one column pattern; its two line-end rows lack one slot
+    each (mask), lines on the y / z faces lack a whole neighbour line and simply have a narrower pattern.  8.3 bytes
+    per nonzero instead of 10.3; odd vector length and the tail slot go through the same path."""
     A = matgen.laplace3d_7pt(256, 6, 5)
     st = {}
     why, out = pack(A.ptrow, A.indcol, A.coef, A.n, 7, indexed=True, stats=st)
     assert not why
-    # (the very last row only loses trailing slots -- no x+1, y+1, z+1 -- and so stays regular)
-    assert st["tiles_indexed"] == 30 and st["exception_rows"] == 2 * 30 - 1
+    assert st["tiles_indexed"] == 30 and st["exception_rows"] == 2 * 30
     assert out[5] / A.nnz < 8.45
     _, plain = pack(A.ptrow, A.indcol, A.coef, A.n, 7)
     assert plain[5] / A.nnz > 10.2
