@@ -111,7 +111,7 @@ int nsk_ctx_device_info(nsk_ctx_t ctx, int *sm_count, int64_t *l2_bytes, int *sm
  *                    publish with red.release | bit 3 (8) dynamically claimed tiles in the fused packed kernel
  *                    (experimental: validate with tools/check_dynamic.py before use)
  *   packed_index     1: pack with index compression and run the kernel instances that read it (experimental, default
- *                    0; built for the default short-row geometry; validate with tools/check_index.py)
+ *                    0; built for the default short-row geometry; bit-identical but slower so far, tools/check_index.py)
  *   pk_timing        1: the packed kernel prints its stage-cycle breakdown to stderr (debugging aid) */
 int nsk_ctx_set_option(nsk_ctx_t ctx, const char *name, int64_t value);
 
@@ -160,8 +160,9 @@ void nsk_mtx_free(int *irow, int *jcol, double *val);
  * x runs) so a test can compare it entry for entry with the input. */
 int nsk_pack_host_create(int n, int n_cols, int64_t nnz, const int *ptrow, const int *indcol, const double *coef,
                          int variant, void **handle);
-/* The same with index compression: tiles whose rows follow one affine column pattern (every interior row of a stencil
- * or band) store one base per slot plus explicit indices for the exception rows only.  GPU path: option packed_index. */
+/* The same with index compression: a tile whose rows all follow one column pattern (slot u of row r references local
+ * column base[u] + r -- every stencil / band; rows may lack slots) stores the pattern once and a slot mask per row, no
+ * per-entry index.  GPU path: option packed_index (experimental, slower than the explicit format in round 1). */
 int nsk_pack_host_create_indexed(int n, int n_cols, int64_t nnz, const int *ptrow, const int *indcol, const double *coef,
                                  int variant, void **handle);
 int nsk_pack_host_index_stats(void *handle, int64_t *tiles_indexed, int64_t *exception_rows);

@@ -4,8 +4,8 @@ then 256^3 compared and timed.
 
     timeout 300 python tools/check_index.py
 
-The kernel instances that read format 1 were written without a GPU at hand: run this BEFORE turning the option on by
-default.  Exit code 0 = every comparison was bit-identical.
+Exit code 0 = every comparison was bit-identical.  Round-1 result (profiles/r01_check_index*.txt): identical bits,
+but the consumer loop of the format-1 instances is slower than the explicit one -- the option stays off.
 """
 import sys
 from pathlib import Path
