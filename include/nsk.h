@@ -108,8 +108,7 @@ int nsk_ctx_device_info(nsk_ctx_t ctx, int *sm_count, int64_t *l2_bytes, int *sm
  *   pipe_bp_global, pipe_interleave, pipe_w0_pct, pk_flags, stream_exact_kind, spmv_ctas_per_sm, wave_static
  *                    experiment switches documented next to nsk_options in csrc/nsk_internal.h
  *   pk_flags         bit 0 (default on) cache hints for data nobody re-reads | bit 1 poll without sleeping | bit 2
- *                    publish with red.release | bit 3 (8) dynamically claimed tiles in the fused packed kernel
- *                    (experimental: validate with tools/check_dynamic.py before use)
+ *                    publish with red.release
  *   packed_index     1: pack with index compression and run the kernel instances that read it (experimental, default
  *                    0; built for the default short-row geometry; bit-identical but slower so far, tools/check_index.py)
  *   pk_timing        1: the packed kernel prints its stage-cycle breakdown to stderr (debugging aid) */
@@ -178,11 +177,6 @@ long long nsk_pack_host_simulate(void *handle, int k, int lead_slack_tiles, int 
                                  int interleave, int stages, const int *level_rows, unsigned seed,
                                  long long *items_out, int *reach_out, int ghi_bias /* 0; < 0 weakens the forward
                                  dependencies by that many groups, for negative tests */);
-/* The same model for the dynamic-claim instances of the kernel (option pk_flags, bit 8): a CTA takes the next unclaimed
- * tile of its level -- one claim beyond its stage ring -- and opens its claims in order. */
-long long nsk_pack_host_simulate_dynamic(void *handle, int k, int lead_slack_tiles, int resident, int w0_pct, int bp_global,
-                                         int interleave, int stages, const int *level_rows, unsigned seed,
-                                         long long *items_out, int *reach_out, int ghi_bias);
 void nsk_pack_host_destroy(void *handle);
 
 /* ---- CSR operator --------------------------------------------------------------------------- */

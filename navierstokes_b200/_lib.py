@@ -55,8 +55,6 @@ SIGNATURES = {
     "nsk_pack_host_expand": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_int_p, c_int_p]),
     "nsk_pack_host_simulate": (C.c_longlong, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                               C.c_uint, C.POINTER(C.c_longlong), c_int_p, C.c_int]),
-    "nsk_pack_host_simulate_dynamic": (C.c_longlong, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                                      C.c_void_p, C.c_uint, C.POINTER(C.c_longlong), c_int_p, C.c_int]),
     "nsk_pack_host_destroy": (None, [C.c_void_p]),
     "nsk_csr_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                  c_void_pp]),

@@ -35,8 +35,7 @@
 // plain product (no counters, no fences), optionally with the fused dot of CG.  NV = 2 instances carry a second
 // right-hand side through the same stages (nsk_mpk_multi: s-step bases of p and r in one sweep).
 // The host half (tiling, runs, blobs, level schedule) is plain C++ and is tested without a GPU, including a CPU model
-// of this protocol (tests/test_packed_host.py).  Experimental (pk_flags bit 8, off by default): instances in which the
-// CTAs of a team claim their tiles from a counter instead of taking every G-th one -- see the DYN template parameter.
+// of this protocol (tests/test_packed_host.py).
 #include <algorithm>
 #include <atomic>
 #include <cstring>
@@ -94,8 +93,7 @@ struct PkParams {
     int team[NSK_MAX_K];   // CTAs of each level (level 0 streams from HBM and gets more stages in flight)
     const int2 *cta_role;  // [grid] {level, index within the level's team}
     int flags;       // experiment switches: 1 = evict-first / streaming hints for data nobody re-reads, 2 = poll without
-                     // sleeping, 4 = publish with red.release.gpu instead of fence + relaxed red, 8 (host side) = run the
-                     // dynamic-claim instance of the kernel where one is built
+                     // sleeping, 4 = publish with red.release.gpu instead of fence + relaxed red
     int bp_global;   // 1: only level 0 is held back, by level k-1 (one window for the whole pipeline); 0: level l by l+1
     // optional stage-cycle instrumentation (tools/pk_timing.py): 8 sums of nanoseconds + item count per CTA
     unsigned long long *timing;
@@ -104,9 +102,6 @@ struct PkParams {
     double *partials;
     unsigned int *ticket;
     double *dot_out;
-    int *claims;     // [k] next unclaimed item of each level (dynamic-claim kernels only), zeroed with the counters
-    const int4 *fat[NSK_MAX_K];  // dynamic-claim kernels: per level, 128 bytes per item = the PkItem followed by its PkTile,
-                                 // so that one load after the claim brings everything every warp needs
 };
 
 // blob header (16 ints at the start of every blob)
@@ -200,22 +195,12 @@ __device__ __forceinline__ int pk_wait_groups(const int *cnt, const int *need, i
     return w;
 }
 
-// DYN = false: CTA c of a team takes items c, c + G, c + 2G, ... (static).  DYN = true (k > 1 only): the producer lane
-// CLAIMS the next item of its level from a global counter, one item ahead of the stage ring, and hands it to the other
-// warps through a small shared-memory ring -- a CTA that falls behind (slower SM, an unlucky HBM access) then simply
-// takes fewer tiles, instead of holding back the prefix watermark everybody downstream waits for.  Items are still
-// taken in ascending order by every CTA, so the dependency rules and the deadlock argument are unchanged.
-constexpr int PK_RING = 16;  // claimed items a CTA remembers (>= STAGES + 2; the publisher may trail the consumers)
-constexpr int PK_FAT = 8;    // int4 per ring entry / per fat item: PkItem (2) + PkTile (6)
-
 // CIDX = true: the consumers also understand blob format 1 (index compression, see PKH_FORMAT); operators packed with it
 // are only ever given to these instances.
-template <int T_ROWS, int BLOB_CAP, int XCAP, int STAGES, int NCW, int MINB, int RPT, int NV, bool MULADD, bool DYN = false,
-          bool CIDX = false>
+template <int T_ROWS, int BLOB_CAP, int XCAP, int STAGES, int NCW, int MINB, int RPT, int NV, bool MULADD, bool CIDX = false>
 __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkParams P)
 {
     static_assert(NV == 1 || NV == 2, "one or two right-hand sides");
-    static_assert(!DYN || STAGES + 2 <= PK_RING, "claim ring shorter than the stage ring");
     constexpr int STAGE_BYTES = BLOB_CAP + NV * XCAP * 8;
     static_assert(BLOB_CAP % 128 == 0 && (XCAP * 8) % 128 == 0, "stage parts keep 128-byte alignment");
     extern __shared__ __align__(128) unsigned char smem[];
@@ -226,11 +211,6 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
     // per stage: consumer warps that finished it, counted over the whole launch (monotone, so the publisher can
     // fall behind the stage ring without a phase ever aliasing)
     unsigned int *fin = reinterpret_cast<unsigned int *>(ts + STAGES * 4);
-    // DYN only: ring of claimed items (entry = the PkItem, tile < 0 = no more items), how many entries the producer has
-    // written, how many the publisher is done with (an entry is reused PK_RING items later)
-    int4 *ring = reinterpret_cast<int4 *>(smem + (((size_t)(reinterpret_cast<unsigned char *>(fin + STAGES) - smem) + 15) & ~(size_t)15));
-    unsigned int *nclaimed = reinterpret_cast<unsigned int *>(ring + PK_FAT * PK_RING);
-    unsigned int *npub = nclaimed + 1;
     const bool timing = P.timing != nullptr;
 
     const int tid = threadIdx.x;
@@ -242,10 +222,6 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
             mbar_init(&full[s], 2);  // producer (blob bytes) + dependency warp (x bytes)
             mbar_init(&done[s], NCW);
             fin[s] = 0u;
-        }
-        if constexpr (DYN) {
-            *nclaimed = 0u;
-            *npub = 0u;
         }
         fence_mbar_init();
     }
@@ -263,86 +239,6 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
         // ===== producer (one lane).  The blob of a tile depends on no flag: a stage is refilled the moment its
         // previous item is done. =====
         if (lane != 0) return;
-        if constexpr (DYN) {
-            int *claim = P.claims + level;
-            const int4 *fat = P.fat[level];
-            const bool last_reader = (P.flags & 1) && level == P.k - 1;
-            const uint64_t pol = policy_evict_first();
-            unsigned long long acc[5] = {0, 0, 0, 0, 0};
-            // How far the claims run ahead of the stage ring (tiles a CTA holds beyond its STAGES open ones):
-            //   1 (default)  the claim for item it+1 is issued before the wait for item it's stage, its descriptor
-            //                loaded after item it's blob copy has been issued;
-            //   2 (flag 16)  ... its descriptor is loaded before that wait too, and item it+2 is claimed: the other
-            //                warps know the next item half a stage cycle earlier, one more tile is in flight;
-            //   0 (flag 32)  nothing is claimed until item it's blob copy has been issued.
-            const int ahead = (P.flags & 16) ? 2 : (P.flags & 32) ? 0 : 1;
-            auto load_desc = [&](int4 *d, int idx) {
-                d[0] = make_int4(-1, 0, 0, -1);  // end marker
-                if (idx < count) {
-#pragma unroll
-                    for (int j = 0; j < PK_FAT; j++) d[j] = fat[(size_t)PK_FAT * idx + j];
-                }
-            };
-            int4 e[PK_FAT], f[PK_FAT];
-            load_desc(e, atomicAdd(claim, 1));
-            int nidx = ahead >= 2 ? atomicAdd(claim, 1) : 0;
-            int it = 0;
-            for (;; ++it) {
-                const bool end = e[0].x < 0;
-                uint32_t spins = 0;
-                while ((int)(ld_acquire_cta_shared_u32(npub) + (unsigned int)PK_RING) <= it)
-                    if (++spins > (1u << 24)) __trap();
-                if (end) ring[PK_FAT * (it % PK_RING)] = e[0];
-                else {
-#pragma unroll
-                    for (int j = 0; j < PK_FAT; j++) ring[PK_FAT * (it % PK_RING) + j] = e[j];
-                }
-                st_release_cta_shared_u32(nclaimed, (unsigned int)(it + 1));
-                bool have_f = false;
-                if (!end) {
-                    if (ahead >= 2) {
-                        load_desc(f, nidx);  // item it + 1, claimed one iteration ago
-                        have_f = true;
-                        nidx = atomicAdd(claim, 1);
-                    } else if (ahead == 1) {
-                        nidx = atomicAdd(claim, 1);  // its round trip overlaps the wait below
-                    }
-                }
-                const int s = it % STAGES;
-                if (it >= STAGES) {
-                    mbar_wait(&done[s], ((it / STAGES) - 1) & 1);
-                    if (timing) {
-                        const unsigned long long t4 = pk_now();
-                        const volatile unsigned long long *v = ts + s * 4;
-                        acc[0] += v[1] - v[0];
-                        acc[1] += v[2] - v[1];
-                        acc[2] += v[3] - v[2];
-                        acc[3] += t4 - v[3];
-                        acc[4] += t4 - v[0];
-                    }
-                }
-                if (end) {
-                    mbar_arrive(&full[s]);  // with the dependency warp's arrival: wakes the consumers, which see the end marker
-                    break;
-                }
-                const int4 a1 = e[1];
-                const long long off = ((long long)(unsigned int)a1.x) | ((long long)a1.y << 32);
-                mbar_arrive_expect_tx(&full[s], (uint32_t)a1.z);
-                if (last_reader) bulk_g2s_hint(smem + (size_t)s * STAGE_BYTES, P.blobs + off, (uint32_t)a1.z, &full[s], pol);
-                else bulk_g2s(smem + (size_t)s * STAGE_BYTES, P.blobs + off, (uint32_t)a1.z, &full[s]);
-                if (timing) ts[s * 4 + 0] = pk_now();
-                if (ahead == 0) nidx = atomicAdd(claim, 1);
-                if (!have_f) load_desc(f, nidx);
-#pragma unroll
-                for (int j = 0; j < PK_FAT; j++) e[j] = f[j];
-            }
-            if (timing) {
-                for (int j = 0; j < 5; j++) P.timing[(size_t)blockIdx.x * 16 + j] = acc[j];
-                P.timing[(size_t)blockIdx.x * 16 + 8] = (unsigned long long)(it > STAGES ? it - STAGES : 0);
-                P.timing[(size_t)blockIdx.x * 16 + 9] = (unsigned long long)level;
-            }
-            return;
-        }
         int it_load = 0;
         int4 db = make_int4(0, 0, 0, 0), nb = db;
         if (n_my > 0) db = my[2 * (size_t)c + 1];
@@ -388,43 +284,6 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
         // followed by fence + RED is cumulative over those stores. =====
         if (P.k <= 1) return;
         int *cnt = P.counters + (size_t)level * P.ngroups;
-        if constexpr (DYN) {
-            if (lane != 0) return;
-            const bool rel = (P.flags & 4) != 0;
-            unsigned long long tf = 0;
-            for (int it = 0;;) {
-                int n = 0;
-                bool stop = false;
-                uint32_t spins = 0;
-                for (;;) {  // every consecutive finished item, at most one ring of stages at a time
-                    const int i2 = it + n;
-                    bool ok = false;
-                    if (n < STAGES && (int)ld_acquire_cta_shared_u32(nclaimed) > i2) {
-                        if (ring[PK_FAT * (i2 % PK_RING)].x < 0) { stop = true; break; }
-                        const unsigned int need = (unsigned int)NCW * (unsigned int)(i2 / STAGES + 1);
-                        ok = ld_acquire_cta_shared_u32(&fin[i2 % STAGES]) >= need;
-                    }
-                    if (ok) { ++n; continue; }
-                    if (n > 0) break;
-                    if (++spins > (1u << 24)) __trap();
-                }
-                if (n > 0) {
-                    const unsigned long long t5 = timing ? pk_now() : 0ull;
-                    if (!rel) __threadfence();
-                    for (int u = 0; u < n; u++) {
-                        const int pos = ring[PK_FAT * ((it + u) % PK_RING)].y;
-                        if (rel && u == 0) red_release_gpu_add(cnt + pos / WF_GROUP, 1);
-                        else red_relaxed_gpu_add(cnt + pos / WF_GROUP, 1);
-                    }
-                    if (timing) tf += pk_now() - t5;
-                    it += n;
-                    st_release_cta_shared_u32(npub, (unsigned int)it);  // the producer may reuse those ring entries
-                }
-                if (stop) break;
-            }
-            if (timing) P.timing[(size_t)blockIdx.x * 16 + 5] = tf;
-            return;
-        }
         int pos_cur = 0;  // lane u: position of item it0 + u
         unsigned long long tf = 0;
         for (int it = 0; it < n_my;) {
@@ -481,56 +340,6 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
         const int *tw = reinterpret_cast<const int *>(P.tiles);
         int wf = 0, wb = 0;
         unsigned long long w_done = 0, w_dep = 0;
-        if constexpr (DYN) {
-            for (int it = 0;; ++it) {
-                uint32_t spins = 0;
-                while ((int)ld_acquire_cta_shared_u32(nclaimed) <= it)
-                    if (++spins > (1u << 24)) __trap();
-                const int4 a0 = ring[PK_FAT * (it % PK_RING)];
-                const int s = it % STAGES;
-                if (a0.x < 0) {  // end marker: second arrival on the stage's barrier, no bytes
-                    if (it >= STAGES) mbar_wait(&done[s], ((it / STAGES) - 1) & 1);
-                    if (lane == 0) mbar_arrive(&full[s]);
-                    break;
-                }
-                // lane u < 24: word u of the item's PkTile, straight from the ring entry
-                const int cw = reinterpret_cast<const int *>(ring + PK_FAT * (it % PK_RING) + 2)[lane < 24 ? lane : 0];
-                const int ghi = a0.z, gback = a0.w;
-                const unsigned long long t0 = timing ? pk_now() : 0ull;
-                if (back && gback >= wb) wb = pk_wait_groups(cnt_b, need_b, P.ngroups, wb, gback, lane, (P.flags & 2) != 0);
-                if (fwd && ghi >= wf) wf = pk_wait_groups(cnt_f, need_f, P.ngroups, wf, ghi, lane, (P.flags & 2) != 0);
-                const unsigned long long t1 = timing ? pk_now() : 0ull;
-                if (it >= STAGES) mbar_wait(&done[s], ((it / STAGES) - 1) & 1);
-                if (timing) { w_dep += t1 - t0; w_done += pk_now() - t1; }
-                if (fwd) fence_proxy_async_global();
-                const int nseg = __shfl_sync(0xffffffffu, cw, 3);
-                const int xlen = __shfl_sync(0xffffffffu, cw, 6);
-                const int start = __shfl_sync(0xffffffffu, cw, 8 + (lane & 7));
-                const int lenoff = __shfl_sync(0xffffffffu, cw, 16 + (lane & 7));
-                const int tail = __shfl_sync(0xffffffffu, cw, 7);
-                if (lane == 0) {
-                    if (tail) {
-                        double *xs = reinterpret_cast<double *>(smem + (size_t)s * STAGE_BYTES + BLOB_CAP);
-                        xs[tail - 1] = ld_cg_f64(src + P.n_cols - 1);
-                        if (NV == 2) xs[XCAP + tail - 1] = ld_cg_f64(src2 + P.n_cols - 1);
-                    }
-                    mbar_arrive_expect_tx(&full[s], (uint32_t)xlen * 8u * NV);
-                }
-                __syncwarp();
-                if ((lane & 7) < nseg && (lane >> 3) < NV) {
-                    const int len = lenoff & 0xffff, xoff = (lenoff >> 16) & 0xffff;
-                    const int v = lane >> 3;
-                    bulk_g2s(smem + (size_t)s * STAGE_BYTES + BLOB_CAP + ((size_t)v * XCAP + (size_t)xoff) * 8,
-                             (v == 0 ? src : src2) + start, (uint32_t)len * 8u, &full[s]);
-                }
-                if (timing && lane == 0) ts[s * 4 + 1] = pk_now();
-            }
-            if (timing && lane == 0) {
-                P.timing[(size_t)blockIdx.x * 16 + 6] = w_done;
-                P.timing[(size_t)blockIdx.x * 16 + 7] = w_dep;
-            }
-            return;
-        }
         int4 cur = make_int4(0, 0, 0, -1), nxt = cur;  // lane u: item it0 + u (cur) and it0 + 32 + u (nxt)
         if (lane < n_my) cur = my[2 * ((size_t)c + (size_t)lane * G)];
         if (32 + lane < n_my) nxt = my[2 * ((size_t)c + (size_t)(32 + lane) * G)];
@@ -611,12 +420,9 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
     const int row_end = P.level_rows[level];
     const bool stream_out = (P.flags & 1) && level == P.k - 1;  // nobody in this launch re-reads the last level
     double dot_acc = 0.0;
-    for (int it = 0; DYN || it < n_my; ++it) {
+    for (int it = 0; it < n_my; ++it) {
         const int s = it % STAGES;
         mbar_wait(&full[s], (it / STAGES) & 1);
-        if constexpr (DYN) {
-            if (ring[PK_FAT * (it % PK_RING)].x < 0) break;  // end marker (written before the producer's arrival on full[s])
-        }
         if (timing && tid == 0) ts[s * 4 + 2] = pk_now();
         const unsigned char *blob = smem + (size_t)s * STAGE_BYTES;
         const int *hdr = reinterpret_cast<const int *>(blob);
@@ -799,36 +605,26 @@ typedef void (*pk_fn)(const PkParams);
 // Two right-hand sides per launch are built for one geometry: the default short-row one with two stages x two CTAs per
 // SM (a stage carries both vectors' x runs).  Other geometries run the vectors one after the other.
 constexpr int PK_NV2_VARIANT = 7;
-// Dynamic-claim instances (pk_flags bit 8, k > 1) exist for the default short-row geometry, one and two vectors.
-constexpr int PK_DYN_VARIANT = 7;
-constexpr int PK_DYN_SMEM = 16 + PK_RING * PK_FAT * 16 + 16;  // alignment + claim ring + its two counters
-static bool pk_has_dynamic(int variant, int nv) { return nv == 2 ? variant == PK_NV2_VARIANT : variant == PK_DYN_VARIANT; }
-static pk_fn pk_lookup(int variant, bool muladd, int nv, int *smem, bool dyn = false, bool cidx = false)
+// Index-compression instances (option packed_index) exist for the default short-row geometry, one and two vectors.
+constexpr int PK_INDEXED_VARIANT = 7;
+static bool pk_has_indexed(int variant, int nv) { return nv == 2 ? variant == PK_NV2_VARIANT : variant == PK_INDEXED_VARIANT; }
+static pk_fn pk_lookup(int variant, bool muladd, int nv, int *smem, bool cidx = false)
 {
-    if (cidx) {  // index-compression instances: same geometries as the dynamic ones, static assignment
-        if (dyn || !pk_has_dynamic(variant, nv)) return nullptr;
+    if (cidx) {
+        if (!pk_has_indexed(variant, nv)) return nullptr;
         if (nv == 2) {
             *smem = (21504 + 2 * 1536 * 8) * 2 + 2 * 2 * 8 + 64 * 8 + 2 * 32 + 2 * 4 + 128;
-            return muladd ? packed_kernel<256, 21504, 1536, 2, 4, 2, 1, 2, true, false, true>
-                          : packed_kernel<256, 21504, 1536, 2, 4, 2, 1, 2, false, false, true>;
-        }
-        *smem = (21504 + 1536 * 8) * 2 + 2 * 2 * 8 + 64 * 8 + 2 * 32 + 2 * 4 + 128;
-        return muladd ? packed_kernel<256, 21504, 1536, 2, 4, 3, 1, 1, true, false, true>
-                      : packed_kernel<256, 21504, 1536, 2, 4, 3, 1, 1, false, false, true>;
-    }
-    if (dyn && !pk_has_dynamic(variant, nv)) return nullptr;
-    if (nv == 2) {
-        if (variant != PK_NV2_VARIANT) return nullptr;
-        *smem = (21504 + 2 * 1536 * 8) * 2 + 2 * 2 * 8 + 64 * 8 + 2 * 32 + 2 * 4 + 128 + (dyn ? PK_DYN_SMEM : 0);
-        if (dyn)
             return muladd ? packed_kernel<256, 21504, 1536, 2, 4, 2, 1, 2, true, true>
                           : packed_kernel<256, 21504, 1536, 2, 4, 2, 1, 2, false, true>;
-        return muladd ? packed_kernel<256, 21504, 1536, 2, 4, 2, 1, 2, true> : packed_kernel<256, 21504, 1536, 2, 4, 2, 1, 2, false>;
-    }
-    if (dyn) {
-        *smem = (21504 + 1536 * 8) * 2 + 2 * 2 * 8 + 64 * 8 + 2 * 32 + 2 * 4 + 128 + PK_DYN_SMEM;
+        }
+        *smem = (21504 + 1536 * 8) * 2 + 2 * 2 * 8 + 64 * 8 + 2 * 32 + 2 * 4 + 128;
         return muladd ? packed_kernel<256, 21504, 1536, 2, 4, 3, 1, 1, true, true>
                       : packed_kernel<256, 21504, 1536, 2, 4, 3, 1, 1, false, true>;
+    }
+    if (nv == 2) {
+        if (variant != PK_NV2_VARIANT) return nullptr;
+        *smem = (21504 + 2 * 1536 * 8) * 2 + 2 * 2 * 8 + 64 * 8 + 2 * 32 + 2 * 4 + 128;
+        return muladd ? packed_kernel<256, 21504, 1536, 2, 4, 2, 1, 2, true> : packed_kernel<256, 21504, 1536, 2, 4, 2, 1, 2, false>;
     }
     switch (variant) {
 #define X(id, r, b, x, s, w, m, u)                                          \
@@ -869,7 +665,6 @@ struct PkLevelPlan {
     PkItem *d_items = nullptr;
     int *d_counters = nullptr;
     int *d_group_size = nullptr;
-    int4 *d_fat = nullptr;      // dynamic-claim kernels: item + tile descriptor, 128 bytes each (built on first use)
 };
 
 struct PackedOp {
@@ -908,7 +703,6 @@ void nsk_packed_free(nsk_csr_t A)
             if (p.d_counters) cudaFree(p.d_counters);
             if (p.d_group_size) cudaFree(p.d_group_size);
             if (p.d_roles) cudaFree(p.d_roles);
-            if (p.d_fat) cudaFree(p.d_fat);
         }
         if (op->d_blobs) cudaFree(op->d_blobs);
         if (op->d_tiles) cudaFree(op->d_tiles);
@@ -1265,12 +1059,10 @@ static void pk_build_schedule(const std::vector<PkTile> &tiles, const std::vecto
 // reads: per tile, the tiles whose rows its nonzeros really reference (exact, from the local columns); ntile_done marks
 // (level, tile) complete.  *violations counts items opened while a tile they read was not complete at the level below
 // (and inside that level's row prefix): the declared dependencies (prefix of groups <= ghi) must imply data readiness.
-// dynamic: the kernel's DYN mode -- a CTA with room for one more claim (stages open items + one held beyond the ring)
-// takes the next unclaimed item of its level, whatever its inputs' state, and opens its claims strictly in order.
 static long long pk_simulate(const PkSchedule &S, const std::vector<int> &teams, int k, int ngroups, int bp_global, int stages,
                              unsigned seed, const std::vector<std::vector<int>> *reads = nullptr,
                              const std::vector<int> *tile_row0 = nullptr, const std::vector<int> *lr = nullptr,
-                             long long *violations = nullptr, bool dynamic = false)
+                             long long *violations = nullptr)
 {
     const int grid = (int)S.roles.size();
     const int ntiles_all = reads ? (int)reads->size() : 0;
@@ -1284,8 +1076,6 @@ static long long pk_simulate(const PkSchedule &S, const std::vector<int> &teams,
     for (int l = 0; l < k; l++) advance(l);
     std::vector<int> next(grid, 0);                 // next item index (within the CTA's own sequence) to open
     std::vector<std::vector<int>> open(grid);       // opened, not yet finished (global item indices)
-    std::vector<int> claim(k, 0);                   // dynamic: next unclaimed item of each level
-    std::vector<std::vector<int>> held(grid);       // dynamic: claimed, not yet opened (in claim order)
     long long done = 0, total = (long long)S.items.size();
     unsigned rng = seed * 2654435761u + 12345u;
     auto rnd = [&]() { rng = rng * 1664525u + 1013904223u; return rng >> 8; };
@@ -1310,15 +1100,8 @@ static long long pk_simulate(const PkSchedule &S, const std::vector<int> &teams,
                 done++;
                 progress = true;
             }
-            if (dynamic) {
-                if ((int)(open[b].size() + held[b].size()) < stages + 1 && claim[level] < S.count[level] && (force || (rnd() & 1))) {
-                    held[b].push_back(claim[level]++);
-                    progress = true;
-                }
-                if (held[b].empty() || (int)open[b].size() >= stages) continue;
-            }
             // open the next item if the ring has room and its inputs are complete
-            const long long idx = dynamic ? (long long)held[b].front() : (long long)c + (long long)next[b] * G;
+            const long long idx = (long long)c + (long long)next[b] * G;
             if ((int)open[b].size() < stages && idx < S.count[level]) {
                 const PkItem &it = S.items[S.item_off[level] + (size_t)idx];
                 const int lb = bp_global ? k - 1 : level + 1;
@@ -1329,8 +1112,7 @@ static long long pk_simulate(const PkSchedule &S, const std::vector<int> &teams,
                         for (int d : (*reads)[(size_t)it.tile])
                             if ((*tile_row0)[(size_t)d] < (*lr)[level - 1] && !tile_done[level - 1][(size_t)d]) bad++;
                     open[b].push_back((int)(S.item_off[level] + (size_t)idx));
-                    if (dynamic) held[b].erase(held[b].begin());
-                    else next[b]++;
+                    next[b]++;
                     progress = true;
                 }
             }
@@ -1441,9 +1223,9 @@ NSK_API int nsk_pack_host_expand(void *handle, int *ptrow, int *indcol, double *
 // Builds the level schedule for a packed operator exactly like the GPU path (dependencies from the tiles' column
 // extents, natural row order, optional per-level row prefixes) and runs the CPU protocol model.  Returns the number
 // of items that did NOT complete (0 = sound), or a negative status.  *items_out receives the total item count.
-static long long pk_host_simulate(void *handle, int k, int lead_slack_tiles, int resident, int w0_pct, int bp_global,
-                                  int interleave, int stages, const int *level_rows, unsigned seed,
-                                  long long *items_out, int *reach_out, int ghi_bias, bool dynamic)
+NSK_API long long nsk_pack_host_simulate(void *handle, int k, int lead_slack_tiles, int resident, int w0_pct, int bp_global,
+                                         int interleave, int stages, const int *level_rows, unsigned seed,
+                                         long long *items_out, int *reach_out, int ghi_bias)
 {
     nsk_packed_host_s *h = static_cast<nsk_packed_host_s *>(handle);
     if (!h->why.empty()) return NSK_ERR_UNSUPPORTED;
@@ -1506,39 +1288,21 @@ static long long pk_host_simulate(void *handle, int k, int lead_slack_tiles, int
         rd.erase(std::unique(rd.begin(), rd.end()), rd.end());
     }
     long long violations = 0;
-    const long long done = pk_simulate(S, teams, k, ngroups, bp_global, stages, seed, &reads, &row0s, &lr, &violations, dynamic);
+    const long long done = pk_simulate(S, teams, k, ngroups, bp_global, stages, seed, &reads, &row0s, &lr, &violations);
     if (items_out) *items_out = (long long)S.items.size();
     if (reach_out) *reach_out = reach;
     if (violations > 0) return -1000000 - violations;  // a dependency hole: an item would read rows not yet produced
     return (long long)S.items.size() - done;
 }
 
-NSK_API long long nsk_pack_host_simulate(void *handle, int k, int lead_slack_tiles, int resident, int w0_pct, int bp_global,
-                                         int interleave, int stages, const int *level_rows, unsigned seed,
-                                         long long *items_out, int *reach_out, int ghi_bias)
-{
-    return pk_host_simulate(handle, k, lead_slack_tiles, resident, w0_pct, bp_global, interleave, stages, level_rows, seed,
-                            items_out, reach_out, ghi_bias, false);
-}
-
-// The same model with dynamically claimed tiles (the kernel's DYN instances, pk_flags bit 8).
-NSK_API long long nsk_pack_host_simulate_dynamic(void *handle, int k, int lead_slack_tiles, int resident, int w0_pct,
-                                                 int bp_global, int interleave, int stages, const int *level_rows,
-                                                 unsigned seed, long long *items_out, int *reach_out, int ghi_bias)
-{
-    return pk_host_simulate(handle, k, lead_slack_tiles, resident, w0_pct, bp_global, interleave, stages, level_rows, seed,
-                            items_out, reach_out, ghi_bias, true);
-}
-
 NSK_API void nsk_pack_host_destroy(void *handle) { delete static_cast<nsk_packed_host_s *>(handle); }
 
 static int pk_launch_shape(nsk_ctx_t ctx, int variant, bool muladd, int k, int nv, pk_fn *fn_out, int *smem_out, int *team,
-                           bool *dyn_out = nullptr, bool cidx = false)
+                           bool cidx = false)
 {
     const PkVariant &V = g_pkv[variant];
     int smem = 0;
-    const bool dyn = !cidx && k > 1 && (ctx->opt.pk_flags & 8) && pk_has_dynamic(variant, nv);
-    pk_fn fn = pk_lookup(variant, muladd, nv, &smem, dyn, cidx);
+    pk_fn fn = pk_lookup(variant, muladd, nv, &smem, cidx);
     if (!fn) {
         nsk_set_error(ctx, "packed path: no two-vector kernel for this tile geometry");
         return NSK_ERR_UNSUPPORTED;
@@ -1550,7 +1314,6 @@ static int pk_launch_shape(nsk_ctx_t ctx, int variant, bool muladd, int k, int n
     if (ctx->opt.spmv_ctas_per_sm > 0) per_sm = std::min(per_sm, (int)ctx->opt.spmv_ctas_per_sm);
     const int resident = ctx->prop.multiProcessorCount * per_sm;
     *team = resident;  // all resident CTAs; the plan shares them out over the levels
-    if (dyn_out) *dyn_out = dyn;
     *fn_out = fn;
     *smem_out = smem;
     return NSK_OK;
@@ -1640,7 +1403,7 @@ static PkLevelPlan *pk_level_plan(nsk_csr_t A, PackedOp *op, int k, const int *l
     std::vector<int2> &roles = S.roles;
     if (cudaMalloc(&p.d_roles, sizeof(int2) * roles.size()) != cudaSuccess ||
         cudaMalloc(&p.d_items, sizeof(PkItem) * (items.size() + 1)) != cudaSuccess ||
-        cudaMalloc(&p.d_counters, sizeof(int) * ((size_t)k * ngroups + 4 + NSK_MAX_K)) != cudaSuccess ||
+        cudaMalloc(&p.d_counters, sizeof(int) * ((size_t)k * ngroups + 4)) != cudaSuccess ||
         cudaMalloc(&p.d_group_size, sizeof(int) * (size_t)k * ngroups) != cudaSuccess) {
         *why = "plan allocation failed";
         cudaGetLastError();
@@ -1688,12 +1451,11 @@ static int pk_run(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
             return NSK_ERR_UNSUPPORTED;
         }
     // index compression (option packed_index, experimental): its own packed copy of the operator, its own kernel instances
-    const bool indexed = ctx->opt.packed_index && pk_has_dynamic(variant, nv);
+    const bool indexed = ctx->opt.packed_index && pk_has_indexed(variant, nv);
     PackedOp *op = pk_get(A, V, indexed);
     if (!op->ok) { nsk_set_error(ctx, "packed path not applicable: %s", op->why.c_str()); return NSK_ERR_UNSUPPORTED; }
     pk_fn fn; int smem = 0, team = 0;
-    bool dyn = false;
-    NSK_TRY(pk_launch_shape(ctx, variant, mode == NSK_EXACT_MULADD, k, nv, &fn, &smem, &team, &dyn, indexed));
+    NSK_TRY(pk_launch_shape(ctx, variant, mode == NSK_EXACT_MULADD, k, nv, &fn, &smem, &team, indexed));
     if (team < k) { nsk_set_error(ctx, "packed path: fewer resident CTAs than levels"); return NSK_ERR_UNSUPPORTED; }
     const char *why = "";
     PkLevelPlan *plan = pk_level_plan(A, op, k, level_rows, team, nv, &why);
@@ -1702,24 +1464,9 @@ static int pk_run(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
     for (int l = 0; l < k; l++) maxcount = std::max(maxcount, plan->count[l]);
     if (maxcount == 0) return NSK_OK;
     if (dot_w) NSK_REQUIRE(ctx, k == 1 && plan->grid <= NSK_MAX_PARTIALS, "fused dot: k = 1 and a bounded grid");
-    if (dyn && !plan->d_fat) {
-        // one-time: the level items joined with their tile descriptors
-        size_t total = 0;
-        for (int l = 0; l < k; l++) total = std::max(total, plan->item_off[l] + (size_t)plan->count[l]);
-        std::vector<PkItem> items(total);
-        NSK_CUDA(ctx, cudaMemcpy(items.data(), plan->d_items, sizeof(PkItem) * total, cudaMemcpyDeviceToHost));
-        static_assert(sizeof(PkItem) + sizeof(PkTile) == PK_FAT * 16, "fat item = item + tile");
-        std::vector<unsigned char> fat(total * (size_t)PK_FAT * 16);
-        for (size_t i = 0; i < total; i++) {
-            memcpy(fat.data() + i * PK_FAT * 16, &items[i], sizeof(PkItem));
-            memcpy(fat.data() + i * PK_FAT * 16 + sizeof(PkItem), &op->h_tiles[(size_t)items[i].tile], sizeof(PkTile));
-        }
-        NSK_CUDA(ctx, cudaMalloc(&plan->d_fat, fat.size() + 16));
-        NSK_CUDA(ctx, cudaMemcpy(plan->d_fat, fat.data(), fat.size(), cudaMemcpyHostToDevice));
-    }
 
     if (k > 1)
-        NSK_CUDA(ctx, cudaMemsetAsync(plan->d_counters, 0, sizeof(int) * ((size_t)k * plan->ngroups + 4 + NSK_MAX_K), ctx->stream));
+        NSK_CUDA(ctx, cudaMemsetAsync(plan->d_counters, 0, sizeof(int) * ((size_t)k * plan->ngroups + 4), ctx->stream));
     PkParams P;
     for (int l = 0; l < NSK_MAX_K; l++) {
         P.items[l] = l < k ? plan->d_items + plan->item_off[l] : nullptr;
@@ -1732,8 +1479,6 @@ static int pk_run(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
     P.tiles = op->d_tiles;
     P.blobs = op->d_blobs;
     P.counters = plan->d_counters;
-    P.claims = plan->d_counters + (size_t)k * plan->ngroups + 4;  // behind the completion counters, zeroed with them
-    for (int l = 0; l < NSK_MAX_K; l++) P.fat[l] = l < k && plan->d_fat ? plan->d_fat + (size_t)PK_FAT * plan->item_off[l] : nullptr;
     P.group_size = plan->d_group_size;
     P.ngroups = plan->ngroups;
     P.n_cols = A->n_cols;

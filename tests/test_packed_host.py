@@ -157,7 +157,7 @@ def test_pack_golden_operators(case):
 
 # ---- the fused kernel's protocol, modelled on the CPU ----------------------------------------------------------------
 def simulate(A, variant, k, slack, resident, w0=100, bp_global=1, interleave=1, stages=2, level_rows=None, seed=0,
-             ghi_bias=0, dynamic=False):
+             ghi_bias=0):
     lib = _lib.load()
     ptrow = np.ascontiguousarray(A.ptrow, np.int32)
     indcol = np.ascontiguousarray(A.indcol, np.int32)
@@ -172,18 +172,17 @@ def simulate(A, variant, k, slack, resident, w0=100, bp_global=1, interleave=1, 
     if level_rows is not None:
         lr = np.ascontiguousarray(level_rows, np.int32)
     items, reach = C.c_longlong(), C.c_int()
-    model = lib.nsk_pack_host_simulate_dynamic if dynamic else lib.nsk_pack_host_simulate
-    stuck = model(h, k, slack, resident, w0, bp_global, interleave, stages, lr.ctypes.data if lr is not None else None, seed,
-                  C.byref(items), C.byref(reach), ghi_bias)
+    stuck = lib.nsk_pack_host_simulate(h, k, slack, resident, w0, bp_global, interleave, stages,
+                                       lr.ctypes.data if lr is not None else None, seed, C.byref(items), C.byref(reach),
+                                       ghi_bias)
     lib.nsk_pack_host_destroy(h)
     return stuck, items.value, reach.value
 
 
-@pytest.mark.parametrize("dynamic", [False, True])
 @pytest.mark.parametrize("bp_global", [0, 1])
 @pytest.mark.parametrize("k", [1, 2, 4, 7, 16])
 @pytest.mark.parametrize("slack", [0, 5, 300])
-def test_protocol_model_never_deadlocks(k, slack, bp_global, dynamic):
+def test_protocol_model_never_deadlocks(k, slack, bp_global):
     """Forward dependencies + window back-pressure on the schedule the GPU path builds: every item becomes runnable,
     from the tightest window (lead = reach + one completion group) to a loose one, few or many CTAs, even or uneven
     teams, both placements, 1-3 open items per CTA, several random interleavings."""
@@ -195,8 +194,7 @@ def test_protocol_model_never_deadlocks(k, slack, bp_global, dynamic):
             resident = k
         w0 = int(rng.choice([100, 40, 300]))
         stuck, items, reach = simulate(A, 7, k, slack, resident, w0=w0, bp_global=bp_global,
-                                       interleave=int(rng.integers(0, 2)), stages=int(rng.integers(1, 4)), seed=trial,
-                                       dynamic=dynamic)
+                                       interleave=int(rng.integers(0, 2)), stages=int(rng.integers(1, 4)), seed=trial)
         assert stuck == 0, (k, slack, resident, w0, stuck, items)
         assert items == k * 120 and 6 <= reach <= 6 + 16
 
@@ -208,10 +206,9 @@ def test_protocol_model_with_shrinking_row_prefixes():
     k = 4
     lr = [A.n - 1024 * l for l in range(k)]  # one plane less per level
     for seed in range(4):
-        for dynamic in (False, True):
-            stuck, items, _ = simulate(A, 7, k, 3, 37, level_rows=lr, seed=seed, stages=2, dynamic=dynamic)
-            assert stuck == 0
-            assert items == sum(r // 256 for r in lr)
+        stuck, items, _ = simulate(A, 7, k, 3, 37, level_rows=lr, seed=seed, stages=2)
+        assert stuck == 0
+        assert items == sum(r // 256 for r in lr)
 
 
 def test_protocol_model_other_patterns():
@@ -225,8 +222,6 @@ def test_protocol_model_other_patterns():
                 continue
             stuck, items, _ = res
             assert stuck == 0 and items > 0
-            stuck, items2, _ = simulate(A, 10 if A.nnz / A.n > 16 else 7, k, 2, 50, seed=1, dynamic=True)
-            assert stuck == 0 and items2 == items
             ran += 1
     assert ran >= 6
 
@@ -242,11 +237,6 @@ def test_protocol_model_detects_a_window_smaller_than_the_reach():
     assert stuck > 0
     stuck, _, _ = simulate(A, 7, 3, 0, 30, bp_global=0, seed=0)
     assert stuck == 0
-    # dynamically claimed tiles obey the same rule
-    stuck, items, _ = simulate(A, 7, 3, -(6 + 16 + 1) - 10, 30, bp_global=1, seed=0, dynamic=True)
-    assert stuck > 0 and stuck < items
-    stuck, _, _ = simulate(A, 7, 3, 0, 30, bp_global=1, seed=0, dynamic=True)
-    assert stuck == 0
 
 
 def test_protocol_model_detects_missing_forward_dependencies():
@@ -261,6 +251,3 @@ def test_protocol_model_detects_missing_forward_dependencies():
     assert found >= 1
     res, _, _ = simulate(A, 7, 3, 40, 444, seed=0, ghi_bias=0)
     assert res == 0
-    found = sum(simulate(A, 7, 3, 40, 444, seed=seed, ghi_bias=-2, dynamic=True)[0] <= -1000000 for seed in range(8))
-    assert found >= 1
-    assert simulate(A, 7, 3, 40, 444, seed=0, ghi_bias=0, dynamic=True)[0] == 0
