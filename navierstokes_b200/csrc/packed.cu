@@ -439,35 +439,37 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
                 // so that the slot bases are not live across the explicit-index loop below (register cap: 80 at 3 CTAs/SM).
                 masked = true;
                 const int4 bq = *reinterpret_cast<const int4 *>(blob + hdr[PKH_OFF_BASE]);  // eight signed 16-bit bases
-                int bs[8];
-                bs[0] = (int)(short)(bq.x & 0xffff); bs[1] = bq.x >> 16;
-                bs[2] = (int)(short)(bq.y & 0xffff); bs[3] = bq.y >> 16;
-                bs[4] = (int)(short)(bq.z & 0xffff); bs[5] = bq.z >> 16;
-                bs[6] = (int)(short)(bq.w & 0xffff); bs[7] = bq.w >> 16;
+                const int bw[4] = {bq.x, bq.y, bq.z, bq.w};  // kept packed (two per register); unpacked at the point of use
                 for (int rb = 0; rb < nrows; rb += NCT * RPT) {
 #pragma unroll
                     for (int q = 0; q < RPT; q++) {
                         const int r = rb + q * NCT + tid;
                         const bool have = r < nrows && row0 + r < row_end;
                         const int m = have ? (int)lens[r] : 0;
-                        double xv[NV][8], av[8];
-                        const double *vp = val + r;  // slot by slot: one running pointer instead of eight offsets
-#pragma unroll
-                        for (int u = 0; u < 8; u++) {
-                            if ((m >> u) & 1) {
-#pragma unroll
-                                for (int v = 0; v < NV; v++) xv[v][u] = xb[v * XCAP + bs[u] + r];
-                                av[u] = *vp;
-                            }
-                            vp += rp;
-                        }
+                        const double *xr = xb + r;
+                        const double *vr = val + r;
                         double a0 = 0.0, a1 = 0.0;
+                        // two groups of four slots: eight loads in flight per group, then four links of the chain
 #pragma unroll
-                        for (int u = 0; u < 8; u++)
-                            if ((m >> u) & 1) {
-                                a0 = row_op<MULADD>(av[u], xv[0][u], a0);
-                                if (NV == 2) a1 = row_op<MULADD>(av[u], xv[NV - 1][u], a1);
+                        for (int g = 0; g < 2; g++) {
+                            double xv[NV][4], av[4];
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                const int e = 4 * g + u;
+                                const int b = (e & 1) ? (bw[e >> 1] >> 16) : (int)(short)(bw[e >> 1] & 0xffff);
+                                if ((m >> e) & 1) {
+#pragma unroll
+                                    for (int v = 0; v < NV; v++) xv[v][u] = xr[v * XCAP + b];
+                                    av[u] = vr[e * rp];
+                                }
                             }
+#pragma unroll
+                            for (int u = 0; u < 4; u++)
+                                if ((m >> (4 * g + u)) & 1) {
+                                    a0 = row_op<MULADD>(av[u], xv[0][u], a0);
+                                    if (NV == 2) a1 = row_op<MULADD>(av[u], xv[NV - 1][u], a1);
+                                }
+                        }
                         if (have) {
                             if (stream_out) __stcs(dst + row0 + r, a0);
                             else dst[row0 + r] = a0;
