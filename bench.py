@@ -139,6 +139,28 @@ class CpuReference:
             src = levels[l]
 
 
+def slab_parity(matgen, nx, ny, nz_total, row_begin, n_owned, k, gpu_levels, threads):
+    """Multi-GPU parity: this rank's owned rows of all k level vectors against k x SpMV_CSR_FMA on the CPU.
+
+    The CPU multiplies the slab extended by k planes on either side (or up to the domain faces) as a truncated grid of
+    its own: its rows are the global operator's rows except in the outermost plane of an artificial cut, and that error
+    moves inwards one plane per level -- after k levels it has reached exactly the k extension planes, never an owned
+    row.  The input is x[g] = sin(0.001 g) in GLOBAL numbering, so the ghost planes are part of the CPU input."""
+    plane = nx * ny
+    z0, z1 = row_begin // plane, (row_begin + n_owned) // plane
+    e0, e1 = max(0, z0 - k), min(nz_total, z1 + k)
+    Aext = matgen.laplace3d_7pt(nx, ny, e1 - e0)
+    ref = CpuReference(Aext, threads)
+    x = np.sin(0.001 * (e0 * plane + np.arange(Aext.nrows, dtype=np.float64)))
+    lv = [np.zeros(Aext.nrows) for _ in range(k)]
+    ref.mpk(k, x, lv)
+    lo = (z0 - e0) * plane
+    bad = 0
+    for l in range(k):
+        bad += int(np.count_nonzero(lv[l][lo:lo + n_owned].view(np.int64) != np.asarray(gpu_levels[l]).view(np.int64)))
+    return bad, ref.kind
+
+
 def cpu_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -192,6 +214,8 @@ def main():
     ap.add_argument("--grid", type=int, default=GRID, help="grid edge (default 256; smaller only for debugging)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cg", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the per-rank CPU parity check of the multi-GPU run")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling sub-record of a weak multi-GPU run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     globals()["GRID"] = args.grid
@@ -356,6 +380,60 @@ def main():
                  "frac_of_peak": spmv_bytes / spmv_ms / 1e6 / peak, "algorithmic_bytes": int(spmv_bytes)},
         "mpk_bytes_rate_GBps": mpk_bytes * world / ms_step / 1e6,
     }
+    # ---- multi-GPU parity: every rank checks its own slab of all k levels against the CPU reference ---------------
+    if world > 1 and not args.no_parity:
+        import torch
+        bad, kind = slab_parity(matgen, GRID, GRID, nz_total, dop.row_begin, dop.n_owned, K_POWERS, lv_host,
+                                max(1, cpu_threads() // world))
+        t = torch.tensor([1.0 if bad == 0 else 0.0, float(bad)], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        out["parity"] = {"ranks_ok": int(t[0].item()), "ranks": world, "bitwise": bool(int(t[0].item()) == world),
+                         "entries_differing": int(t[1].item()), "against": f"k x SpMV_CSR_FMA ({kind}) on each rank's slab "
+                         f"extended by {K_POWERS} ghost planes, all {K_POWERS} level vectors, owned rows"}
+    # ---- strong scaling beside the weak number: the SAME 256^3 problem split over the ranks ---------------------
+    if world > 1 and args.scaling == "weak" and not args.no_strong:
+        import torch
+        from navierstokes_b200 import distributed as nd
+        sop = nd.DistStencil3D(ctx, dist, GRID, GRID, GRID, halo_depth=K_POWERS)
+        sx_host = np.sin(0.001 * (sop.row_begin + np.arange(sop.n_owned)))
+        sdx = sop.new_vector()
+        sop.set_owned(sdx, sx_host)
+        sdlv = [sop.new_vector() for _ in range(K_POWERS)]
+        for _ in range(5):
+            sop.mpk(K_POWERS, sdx, sdlv)
+        barrier()
+        g0, g1 = ctx.event(), ctx.event()
+        g0.record()
+        for _ in range(args.steps):
+            sop.mpk(K_POWERS, sdx, sdlv)
+        g1.record()
+        s_ms = max_over_ranks(g0.elapsed_ms(g1) / args.steps)
+        # halo exchange alone (depth k), same operator
+        for _ in range(3):
+            sop.halo_exchange(sdx, K_POWERS)
+        barrier()
+        g0.record()
+        for _ in range(args.steps):
+            sop.halo_exchange(sdx, K_POWERS)
+        g1.record()
+        h_ms = max_over_ranks(g0.elapsed_ms(g1) / args.steps)
+        sbad = 0
+        if not args.no_parity:
+            got = [sop.get_owned(v) for v in sdlv]
+            sbad, _ = slab_parity(matgen, GRID, GRID, GRID, sop.row_begin, sop.n_owned, K_POWERS, got,
+                                  max(1, cpu_threads() // world))
+        t = torch.tensor([1.0 if sbad == 0 else 0.0], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        n_tot = GRID ** 3
+        nnz_tot = 7 * n_tot - 6 * GRID * GRID
+        spmv_tot = 12 * nnz_tot + 4 * (n_tot + 1) + 16 * n_tot
+        out["strong"] = {"workload": f"3D 7-point Laplacian {GRID}^3 split over {world} GPUs (z-slabs), k={K_POWERS}",
+                         "ms_per_step": s_ms, "value": K_POWERS * spmv_tot / s_ms / 1e6, "unit": "GB/s",
+                         "halo_exchange_us": h_ms * 1e3,
+                         "efficiency_vs_n1_note": "t(1 GPU) / (N * t(N GPUs)) with t(1 GPU) = this build's N=1 ms_per_step "
+                                                  "(the driver's SCALE record); not computed here",
+                         "parity": {"ranks_ok": int(t[0].item()), "ranks": world, "bitwise": bool(int(t[0].item()) == world)}}
+        sop.close()
     # ---- Poisson CG iterations per second on the same operator (BASELINE metric, second half) ------------------
     if world == 1 and not args.no_cg:
         b = ctx.empty(A.n)

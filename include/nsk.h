@@ -99,9 +99,13 @@ uint64_t nsk_ctx_launch_count(nsk_ctx_t ctx);
 int nsk_ctx_device_info(nsk_ctx_t ctx, int *sm_count, int64_t *l2_bytes, int *smem_optin,
                         int64_t *hbm_bytes);
 /* Tuning knobs (name -> integer).  Unknown names give NSK_ERR_INVALID.  Defaults are what bench.py runs.
- *   spmv_kernel      0 auto (packed when the operator packs, else stream) | 1 scalar | 2 stream (CSR) | 3 packed
+ *   spmv_kernel      0 auto (packed when the operator packs, else stream) | 1 scalar | 2 stream (CSR) | 3 packed |
+ *                    4 sliced-ELL tiles
  *   mpk_kernel       0 auto (fused packed level pipeline when it applies, else k launches) | 1 k launches |
- *                    2 wavefront (CSR) | 3 level pipeline (CSR) | 4 level pipeline (packed)
+ *                    2 wavefront (CSR) | 3 level pipeline (CSR) | 4 level pipeline (packed) | 5 level pipeline
+ *                    (sliced-ELL tiles: any operator whose rows are not too ragged, stencil or unstructured)
+ *   sell_chunk       consecutive tiles a CTA takes per item (0 = default) | sell_geom 0 auto, 1 pattern, 2 explicit |
+ *                    sell_ctas_per_sm | sell_flags (bit 0 eviction hints, bit 1 L2 prefetch of level 0) | sell_pf_dist
  *   packed_variant, stream_variant, pipe_variant, wave_variant   0 default, n = table entry n-1 of that kernel
  *   wave_l2_pct      share of L2 the fused kernels' window may occupy (0 = default: 70 packed, 80 CSR)
  *   wave_slack_pct   explicit window slack (< 0 = size it from the L2 budget)
@@ -178,6 +182,26 @@ long long nsk_pack_host_simulate(void *handle, int k, int lead_slack_tiles, int 
                                  long long *items_out, int *reach_out, int ghi_bias /* 0; < 0 weakens the forward
                                  dependencies by that many groups, for negative tests */);
 void nsk_pack_host_destroy(void *handle);
+
+/* ---- the sliced-ELL format's host half (no GPU; csrc/sell.cu) ------------------------------------------------ */
+/* Cuts a CSR operator into tiles of 256 consecutive rows stored slot-major per 32-row slice.  A tile whose rows all follow
+ * one column pattern (slot e of row r references column r + rel[e]; rows may lack slots) stores the pattern once and a
+ * slot mask per row -- 8 bytes per nonzero, no per-entry index; every other tile keeps explicit 32-bit columns.
+ * nsk_sell_host_why returns "" or the reason the operator is refused (rows too ragged for slot-major slices);
+ * nsk_sell_host_expand rebuilds CSR from the tiles so a test can compare it entry for entry with the input. */
+int nsk_sell_host_create(int n, int n_cols, int64_t nnz, const int *ptrow, const int *indcol, const double *coef,
+                         void **handle);
+const char *nsk_sell_host_why(void *handle);
+int nsk_sell_host_stats(void *handle, int64_t *bytes, int64_t *ntiles, int64_t *pattern_tiles);
+int nsk_sell_host_expand(void *handle, int *ptrow, int *indcol, double *coef);
+/* CPU model of the fused sliced-ELL kernel's protocol on the schedule the GPU path would build: items of `chunk`
+ * consecutive tiles, forward dependencies and window back-pressure through per-group completion counters, in-order
+ * CTAs with up to `ring` open items that finish in any order but are published in order.  Same return convention as
+ * nsk_pack_host_simulate; pmax_bias < 0 weakens the forward dependencies by that many tiles (negative tests). */
+long long nsk_sell_host_simulate(void *handle, int k, int chunk, int lead_slack_tiles, int resident, int w0_pct,
+                                 int interleave, int ring, const int *level_rows, unsigned seed, long long *items_out,
+                                 int *reach_out, int pmax_bias);
+void nsk_sell_host_destroy(void *handle);
 
 /* ---- CSR operator --------------------------------------------------------------------------- */
 /* Uploads a square CSR operator (0-based, int32 indices, fp64 values; columns need not be sorted --

@@ -146,6 +146,11 @@ NSK_API int nsk_ctx_set_option(nsk_ctx_t c, const char *name, int64_t v)
     else if (!strcmp(name, "host_overlap")) c->opt.host_overlap = v;
     else if (!strcmp(name, "stream_exact_kind")) c->opt.stream_exact_kind = v;
     else if (!strcmp(name, "pipe_interleave")) c->opt.pipe_interleave = v;
+    else if (!strcmp(name, "sell_chunk")) c->opt.sell_chunk = v;
+    else if (!strcmp(name, "sell_geom")) c->opt.sell_geom = v;
+    else if (!strcmp(name, "sell_ctas_per_sm")) c->opt.sell_ctas_per_sm = v;
+    else if (!strcmp(name, "sell_flags")) c->opt.sell_flags = v;
+    else if (!strcmp(name, "sell_pf_dist")) c->opt.sell_pf_dist = v;
     else {
         nsk_set_error(c, "unknown option '%s'", name);
         return NSK_ERR_INVALID;

@@ -96,6 +96,7 @@ NSK_API int nsk_csr_destroy(nsk_csr_t A)
     nsk_wave_free(A);
     nsk_pipe_free(A);
     nsk_packed_free(A);
+    nsk_sell_free(A);
     if (A->d_ptrow) cudaFree(A->d_ptrow);
     if (A->d_indcol) cudaFree(A->d_indcol);
     if (A->d_coef) cudaFree(A->d_coef);

@@ -51,7 +51,9 @@ int nsk_mpk_local(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
     int sel = (int)ctx->opt.mpk_kernel;
     const bool automatic = sel == 0;
     if (automatic) sel = 4;
-    if (sel == 4 && k > 1 && nsk_packed_applicable(A)) {
+    const bool sell = sel == 5 && k > 1 && nsk_sell_applicable(A);
+    if (sel == 5 && !sell) sel = 4;
+    if (sell || (sel == 4 && k > 1 && nsk_packed_applicable(A))) {
         // Fuse as many levels per launch as the L2 window allows: a pattern whose reach is large (512^2-row planes)
         // may fit two levels but not four -- then A^4 x runs as two fused pairs instead of four products.
         int done = 0;
@@ -61,7 +63,8 @@ int nsk_mpk_local(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
             const int left = k - done;
             int took = 0;
             for (int kk = left; kk >= 2 && !took; kk--) {
-                int s = nsk_packed_run(A, kk, src, d_levels + done, mode, level_rows ? level_rows + done : nullptr, nullptr, -1);
+                int s = sell ? nsk_sell_run(A, kk, src, d_levels + done, mode, level_rows ? level_rows + done : nullptr, nullptr, -1)
+                             : nsk_packed_run(A, kk, src, d_levels + done, mode, level_rows ? level_rows + done : nullptr, nullptr, -1);
                 if (s == NSK_OK) took = kk;
                 else if (s != NSK_ERR_UNSUPPORTED) return s;
             }
@@ -80,7 +83,7 @@ int nsk_mpk_local(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
             src = d_levels[done + took - 1];
             done += took;
         }
-        ctx->last_mpk = any_fused ? 4 : 1;
+        ctx->last_mpk = any_fused ? (sell ? 5 : 4) : 1;
         return NSK_OK;
     }
     // the CSR level pipeline (3) and the wavefront kernel (2) stay explicit choices: with global gathers they lose to k
@@ -107,7 +110,8 @@ int nsk_mpk_local2(nsk_csr_t A, int k, const double *d_x, double *const *d_level
 {
     nsk_ctx_t ctx = A->ctx;
     const int sel = (int)ctx->opt.mpk_kernel;
-    if ((sel == 0 || sel == 4) && nsk_packed_applicable(A)) {
+    const bool sell = sel == 5 && nsk_sell_applicable(A);
+    if (sell || ((sel == 0 || sel == 4 || sel == 5) && nsk_packed_applicable(A))) {
         int done = 0;
         const double *src = d_x, *src2 = d_x2;
         bool ok = true, any = false;
@@ -115,8 +119,10 @@ int nsk_mpk_local2(nsk_csr_t A, int k, const double *d_x, double *const *d_level
             const int left = k - done;
             int took = 0;
             for (int kk = left; kk >= 1 && !took; kk--) {
-                int s = nsk_packed_run2(A, kk, src, d_levels + done, src2, d_levels2 + done, mode,
-                                        level_rows ? level_rows + done : nullptr);
+                int s = sell ? nsk_sell_run2(A, kk, src, d_levels + done, src2, d_levels2 + done, mode,
+                                             level_rows ? level_rows + done : nullptr)
+                             : nsk_packed_run2(A, kk, src, d_levels + done, src2, d_levels2 + done, mode,
+                                               level_rows ? level_rows + done : nullptr);
                 if (s == NSK_OK) took = kk;
                 else if (s != NSK_ERR_UNSUPPORTED) return s;
             }
@@ -126,7 +132,7 @@ int nsk_mpk_local2(nsk_csr_t A, int k, const double *d_x, double *const *d_level
             src2 = d_levels2[done + took - 1];
             done += took;
         }
-        if (ok) { ctx->last_mpk = any ? 4 : 1; return NSK_OK; }
+        if (ok) { ctx->last_mpk = any ? (sell ? 5 : 4) : 1; return NSK_OK; }
         // partial progress is fine: finish the remaining levels vector by vector
         if (done > 0) {
             NSK_TRY(nsk_mpk_local(A, k - done, d_levels[done - 1], d_levels + done, mode, level_rows ? level_rows + done : nullptr));

@@ -344,6 +344,7 @@ void nsk_wave_set_block_extents(nsk_csr_t A, const int *ptrow, const int *indcol
     WaveState &S = wave_state(A);
     nsk_pipe_free(A);  // plans of the level-pipeline kernel were built from the old extents
     nsk_packed_free(A);
+    nsk_sell_free(A);
     S.plans.clear();
     S.blk_row0.clear(); S.blk_min.clear(); S.blk_max.clear();
     const int n = A->n;

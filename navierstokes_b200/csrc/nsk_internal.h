@@ -62,6 +62,12 @@ struct nsk_options {
     int64_t wave_slack_pct = -1;  // extra level skew, % of (resident CTAs x stages / k) tiles; <0 = default 150
     int64_t wave_static = 0;      // 1 = static round-robin schedule instead of dynamic claims
     int64_t wave_l2_pct = 0;      // share of L2 the wavefront window may occupy, %; 0 = default 80
+    // sliced-ELL kernel (sell.cu)
+    int64_t sell_chunk = 0;       // consecutive tiles a CTA takes per item; 0 = default (2 fused, 4 single product)
+    int64_t sell_geom = 0;        // 0 auto, 1 = pattern geometry (4 entries per round trip, more CTAs per SM), 2 = explicit
+    int64_t sell_ctas_per_sm = 0; // 0 = what the occupancy calculator allows
+    int64_t sell_flags = -1;      // < 0 default (3): bit 0 eviction / streaming hints, bit 1 L2 prefetch of level 0's tiles
+    int64_t sell_pf_dist = 0;     // items ahead the L2 prefetch runs; 0 = default 2
 };
 
 struct nsk_ctx_s {
@@ -162,6 +168,15 @@ int nsk_packed_run(nsk_csr_t A, int k, const double *d_x, double *const *d_level
 int nsk_packed_run2(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, const double *d_x2,
                     double *const *d_levels2, nsk_mode mode, const int *level_rows);
 bool nsk_packed_applicable(nsk_csr_t A);
+// sell.cu: sliced-ELL tiles, any CSR operator; k = 1 is the plain product; NSK_ERR_UNSUPPORTED = use another path
+int nsk_sell_run(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode, const int *level_rows,
+                 const double *dot_w, int dot_slot);
+int nsk_sell_run2(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, const double *d_x2,
+                  double *const *d_levels2, nsk_mode mode, const int *level_rows);
+bool nsk_sell_applicable(nsk_csr_t A);
+size_t nsk_sell_bytes(nsk_csr_t A);
+void nsk_sell_free(nsk_csr_t A);
+int nsk_sell_check_error(nsk_csr_t A);
 size_t nsk_packed_bytes(nsk_csr_t A);
 void nsk_packed_free(nsk_csr_t A);
 int nsk_get_tiling(nsk_csr_t A, int t_nnz, int t_rows, const nsk_tiling **out);  // cached per geometry

@@ -1,0 +1,1420 @@
+// sell.cu -- sliced-ELL tiles + ONE persistent kernel for y = A x and the fused matrix powers A x .. A^k x on ANY CSR
+// operator (stencils and unstructured FEM alike), with the operator's coefficients going HBM/L2 -> registers directly.
+//
+// Replaces SpMV_CSR / _OPT / _FMA / _AVX2 (reference mpk/SpMV.cpp:6-85) and the fused SpM2V_CSR* / SpM3V / SpM4V
+// (mpk/SpM2V.cpp:80-332, mpk/SpMVmulti0.cpp:132-221).  Per-row nonzero order is never changed, so the exact modes are
+// bit-identical to the reference's row loop; only the schedule differs.
+//
+// Why a second fused kernel.  packed.cu stages whole tiles (coefficients, local columns, x runs) in shared memory by
+// bulk copies; ncu + stage-cycle timing (profiles/r01_pk_timing.txt) put its floor at the shared-memory
+// data path: ~34 B per nonzero written and re-read, 74 % busy at 0.64 ms for k = 4 on 256^3.  The coefficients are
+// used exactly once per level, so here they never touch shared memory:
+//
+//   * a TILE is 256 consecutive rows, one row per consumer thread, stored slot-major per 32-row slice (SELL-32,
+//     no row sorting): lane l of warp w reads entry e of its row at val[(slice_off + e) * 32 + l] -- every warp-level
+//     load is one 256-byte line pair, no shared memory, no index arithmetic beyond an add;
+//   * PATTERN tiles (format P): when every row of a tile is a sub-pattern of one column pattern (stencils, bands: slot e
+//     of row r references column r + rel[e]) no per-entry index is stored at all -- 8 bytes per nonzero + 1 mask byte per
+//     row (256^3 7-point: 0.98 GB instead of CSR's 1.47 GB); everything else keeps explicit 32-bit columns (format E);
+//   * x is gathered with ordinary cached loads: after the dependency warp's acquire (which also invalidates this SM's
+//     L1) the level vector below is read through L1, so the +-1 neighbours and the tiles of one chunk share lines;
+//   * matrix powers = the level pipeline of packed.cu (teams of CTAs per level, per-group completion counters, window
+//     back-pressure sized from the L2 budget) with all device-scope latency moved into two helper warps: a DEPENDENCY
+//     warp that polls up to four items ahead, fetches the items' tile descriptors into a shared-memory ring and
+//     prefetches level 0's blobs into L2 (cp.async.bulk.prefetch.L2), and a PUBLISHER warp that fences once for
+//     everything finished at that moment.  The eight consumer warps are decoupled from each other (a warp only waits
+//     for its item's mbarrier) and execute nothing but loads, the fma chain and stores;
+//   * completion counters are monotone over launches (an item is complete when its group's counter reaches
+//     epoch * group size), so no memset precedes a launch; waits are bounded by the global timer and raise an error
+//     flag instead of trapping; k > 1 is launched cooperatively so that co-residency is guaranteed, not assumed.
+//
+// The host half (tiling, pattern detection, blobs, level schedule, CPU model of the protocol) is plain C++ and is
+// tested without a GPU (tests/test_sell_host.py).
+#include <algorithm>
+#include <atomic>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <mutex>
+#include <thread>
+
+#include "nsk_internal.h"
+#include "ptx_helpers.cuh"
+#include "stream_common.cuh"
+#include "wave_common.h"
+
+using namespace nskptx;
+
+std::vector<int> &nsk_csr_host_ptrow(nsk_csr_t A);
+
+constexpr int SL_ROWS = 256;      // rows per tile = consumer threads per CTA
+constexpr int SL_NCW = SL_ROWS / 32;
+constexpr int SL_THREADS = SL_ROWS + 64;  // + dependency warp + publisher warp
+constexpr int SL_PSLOTS = 8;      // pattern format: at most 8 slots per row
+constexpr int SL_MAXCHUNK = 8;    // tiles per item (consecutive tiles taken by one CTA in one go)
+constexpr int SL_RING = 4;        // items the dependency warp may run ahead of the slowest consumer warp
+
+enum { SL_FMT_PATTERN = 0, SL_FMT_EXPLICIT = 1 };
+
+struct SlTile {          // 64 bytes = 16 words, fetched by the dependency warp into shared memory
+    long long off;       // w0,1  byte offset of the blob (128-byte aligned)
+    int row0, nrows;     // w2,3
+    int width;           // w4    slots (longest row of the tile)
+    int fmt;             // w5
+    int rp;              // w6    rows padded to a multiple of 32
+    int bytes;           // w7    blob bytes (multiple of 128)
+    int rel[8];          // w8..15  format P: column of slot e of local row r = row0 + r + rel[e]
+                         //         format E: slots of slice s (its rows' longest), slices stored one after the other
+};
+static_assert(sizeof(SlTile) == 64, "SlTile is 16 words");
+
+struct SlItem {          // 32 bytes; item i of a level = tiles [i * chunk, (i + 1) * chunk) of the level's tile list
+    int group;           // completion group the item reports to
+    int ghi;             // forward: groups [0, ghi] of level l-1 complete (-1: none)
+    int gback;           // back-pressure: groups [0, gback] of the level that holds this one back (-1: none)
+    int pf_bytes;        // blobs of the item's tiles: contiguous bytes starting at pf_off (0: not contiguous)
+    long long pf_off;
+    int pad[2];
+};
+static_assert(sizeof(SlItem) == 32, "SlItem is 8 words");
+
+struct SlParams {
+    const SlItem *items[NSK_MAX_K];   // per level, in position order
+    const SlTile *ltiles[NSK_MAX_K];  // per level: the level's tiles in position order (aliases when all levels agree)
+    int count[NSK_MAX_K];             // items per level
+    int ntl[NSK_MAX_K];               // tiles per level
+    int team[NSK_MAX_K];              // CTAs per level
+    int level_rows[NSK_MAX_K];
+    double *levels[NSK_MAX_K];
+    double *levels2[NSK_MAX_K];
+    const double *x, *x2;
+    const unsigned char *blobs;
+    int *counters;           // [k][ngroups], monotone over launches
+    const int *group_size;   // [k][ngroups]
+    const int2 *cta_role;    // [grid] {level, index within the level's team}
+    int ngroups, n_cols, k, chunk;
+    int epoch;               // an item group is complete when counter >= epoch * group size
+    int bp_level;            // the level whose progress holds level 0 back (k - 1), -1: no back-pressure
+    int flags;               // 1: evict-first / streaming hints for data nobody re-reads; 2: L2 prefetch of level 0's blobs;
+                             // 4: inner levels load tiles with L1 allocation; 8: ... with an evict-last L2 policy
+    int pf_dist;             // items ahead the L2 prefetch runs
+    int *error;              // host-mapped: set to 1 when a bounded wait expired (protocol bug or a lost CTA)
+    // fused dot <dot_w, levels[0]> (k = 1 only; CG: p.Ap)
+    const double *dot_w;
+    double *partials;
+    unsigned int *ticket;
+    double *dot_out;
+};
+
+__host__ __device__ constexpr int sl_round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// blob layouts (all sections 128-byte aligned)
+//   format P:  mask u8[256] | val f64[width][256]      (fixed row stride: slot e of row r at byte 256 + 2048 e + 8 r,
+//                                                       so a thread's loads differ by immediates only)
+//   format E:  len u16[rp] | col i32[tot][32] | val f64[tot][32]      tot = sum of the slices' widths
+static inline int sl_blob_bytes_pattern(int width) { return SL_ROWS + 8 * width * SL_ROWS; }
+static inline int sl_blob_bytes_explicit(int rp, int tot) { return sl_round_up(2 * rp, 128) + sl_round_up(4 * 32 * tot, 128) + 8 * 32 * tot; }
+
+__device__ __forceinline__ unsigned long long sl_now()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// coefficient / column stream (read-only path).  CH selects the cache handling:
+//   SL_CH_NA      no L1 allocation (L1 is for x)
+//   SL_CH_ALLOC   plain read-only load
+//   SL_CH_KEEP    no L1 allocation, evict-last in L2 (window data: the next levels re-read it)
+//   SL_CH_DROP    no L1 allocation, evict-first in L2 (the last level is the last reader of a tile in a launch)
+enum { SL_CH_NA = 0, SL_CH_ALLOC = 1, SL_CH_KEEP = 2, SL_CH_DROP = 3 };
+template <int CH>
+__device__ __forceinline__ uint64_t sl_policy()
+{
+    uint64_t pol = 0;  // (the eviction-priority qualifier without a policy operand exists for 256-bit loads only)
+    if (CH == SL_CH_KEEP) asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    if (CH == SL_CH_DROP) asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+template <int CH>
+__device__ __forceinline__ double sl_ld_coef(const double *p)
+{
+    double v;
+    if (CH == SL_CH_KEEP || CH == SL_CH_DROP)
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(sl_policy<CH>()));
+    else if (CH == SL_CH_ALLOC)
+        asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    else
+        asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+template <int CH>
+__device__ __forceinline__ int sl_ld_col(const int *p)
+{
+    int v;
+    if (CH == SL_CH_KEEP || CH == SL_CH_DROP)
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(sl_policy<CH>()));
+    else if (CH == SL_CH_ALLOC)
+        asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    else
+        asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+// x: ordinary cached load (L1 + L2).  Written as asm so that it can neither become a read-only-path load (the level
+// vectors are written by other CTAs of this launch) nor move above the mbarrier wait that orders it.
+__device__ __forceinline__ double sl_ld_x(const double *p)
+{
+    double v;
+    asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sl_prefetch_l2(const void *p, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+constexpr unsigned long long SL_TIMEOUT_NS = 4000000000ull;  // bounded waits: 4 s, then the error flag
+
+// Advances the watermark w (all groups < w complete) until it passes `upto`; lanes poll 32 groups at a time.
+// Returns the new watermark, or -1 when the wait expired.
+__device__ __forceinline__ int sl_wait_groups(const int *cnt, const int *need, int epoch, int ngroups, int w, int upto, int lane)
+{
+    unsigned long long t0 = 0;
+    while (w <= upto) {
+        const int g = w + lane;
+        bool ok = true;
+        if (g < ngroups) ok = ld_acquire_gpu(cnt + g) >= __ldg(need + g) * epoch;
+        const unsigned int bad = __ballot_sync(0xffffffffu, !ok);
+        const int adv = bad ? __ffs(bad) - 1 : 32;
+        w = min(w + adv, ngroups);
+        if (w > upto || w >= ngroups) break;
+        if (adv == 0) {
+            __nanosleep(40);
+            const unsigned long long t = sl_now();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > SL_TIMEOUT_NS) return -1;
+        }
+    }
+    return w;
+}
+
+// How a consumer treats data nobody re-reads in this launch: SL_MID = an inner level; SL_LAST = the last level (tiles
+// loaded evict-first, results stored streaming); SL_LAST_DOT = the single product with CG's fused dot <w, y>.
+enum { SL_MID = 0, SL_LAST = 1, SL_LAST_DOT = 2, SL_MID_ALLOC = 3, SL_MID_KEEP = 4, SL_LAST_PLAIN = 5 };
+__host__ __device__ constexpr bool sl_is_last(int lm) { return lm == SL_LAST || lm == SL_LAST_DOT; }
+__host__ __device__ constexpr int sl_ch(int lm)
+{
+    return sl_is_last(lm) ? SL_CH_DROP : lm == SL_MID_ALLOC ? SL_CH_ALLOC : lm == SL_MID_KEEP ? SL_CH_KEEP : SL_CH_NA;
+}
+
+template <int NV, int LM>
+__device__ __forceinline__ void sl_store_row(const SlParams &P, double *const *s_dst, int row, double acc0, double acc1,
+                                             double &dot_acc)
+{
+    double *dst = s_dst[0];
+    if (sl_is_last(LM)) __stcs(dst + row, acc0);
+    else dst[row] = acc0;
+    if (NV == 2) {
+        double *dst2 = s_dst[1];
+        if (sl_is_last(LM)) __stcs(dst2 + row, acc1);
+        else dst2[row] = acc1;
+    }
+    if (LM == SL_LAST_DOT) dot_acc = __fma_rn(P.dot_w[row], acc0, dot_acc);
+}
+
+// One tile, format P, W slots: every load of the row is issued before the first link of its chain.  d = the tile's
+// descriptor in shared memory, m = the row's slot mask (staged by the dependency warp).  All loads are unconditional so
+// that every destination register is defined exactly once (a predicated load would keep its old value alive across the
+// whole sequence): a slot the row lacks reads the row's own x entry instead, and is not used.
+template <int NV, bool MULADD, int LM, int W>
+__device__ __forceinline__ void sl_tile_pattern_w(const int *d, unsigned int m, const SlParams &P, const double *const *s_src,
+                                                  double *const *s_dst, int row_end, int r, double &dot_acc)
+{
+    const long long off = ((long long)(unsigned int)d[0]) | ((long long)d[1] << 32);
+    const int row = d[2] + r;
+    const double *val = reinterpret_cast<const double *>(P.blobs + off + SL_ROWS) + r;
+    const int rowc = min(row, P.n_cols - 1);  // padding rows of the last tile stay inside x
+    const double *src = s_src[0];
+    const double *src2 = NV == 2 ? s_src[1] : nullptr;
+    double a[W > 0 ? W : 1], xv[NV][W > 0 ? W : 1];
+#pragma unroll
+    for (int e = 0; e < W; e++) {
+        a[e] = sl_ld_coef<sl_ch(LM)>(val + e * SL_ROWS);
+        const int idx = rowc + (d[8 + e] & -(int)((m >> e) & 1u));
+        xv[0][e] = sl_ld_x(src + idx);
+        if (NV == 2) xv[NV - 1][e] = sl_ld_x(src2 + idx);
+    }
+    double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+    for (int e = 0; e < W; e++)
+        if (m & (1u << e)) {
+            acc0 = row_op<MULADD>(a[e], xv[0][e], acc0);
+            if (NV == 2) acc1 = row_op<MULADD>(a[e], xv[NV - 1][e], acc1);
+        }
+    if (r < d[3] && row < row_end) sl_store_row<NV, LM>(P, s_dst, row, acc0, acc1, dot_acc);
+}
+
+template <int NV, bool MULADD, int LM>
+__device__ __forceinline__ void sl_tile_pattern(const int *d, unsigned int m, const SlParams &P, const double *const *s_src,
+                                                double *const *s_dst, int row_end, int r, double &dot_acc)
+{
+    switch (d[4]) {  // uniform: one instance per width, no per-slot bounds checks
+    case 0: sl_tile_pattern_w<NV, MULADD, LM, 0>(d, m, P, s_src, s_dst, row_end, r, dot_acc); break;
+    case 1: sl_tile_pattern_w<NV, MULADD, LM, 1>(d, m, P, s_src, s_dst, row_end, r, dot_acc); break;
+    case 2: sl_tile_pattern_w<NV, MULADD, LM, 2>(d, m, P, s_src, s_dst, row_end, r, dot_acc); break;
+    case 3: sl_tile_pattern_w<NV, MULADD, LM, 3>(d, m, P, s_src, s_dst, row_end, r, dot_acc); break;
+    case 4: sl_tile_pattern_w<NV, MULADD, LM, 4>(d, m, P, s_src, s_dst, row_end, r, dot_acc); break;
+    case 5: sl_tile_pattern_w<NV, MULADD, LM, 5>(d, m, P, s_src, s_dst, row_end, r, dot_acc); break;
+    case 6: sl_tile_pattern_w<NV, MULADD, LM, 6>(d, m, P, s_src, s_dst, row_end, r, dot_acc); break;
+    case 7: sl_tile_pattern_w<NV, MULADD, LM, 7>(d, m, P, s_src, s_dst, row_end, r, dot_acc); break;
+    default: sl_tile_pattern_w<NV, MULADD, LM, 8>(d, m, P, s_src, s_dst, row_end, r, dot_acc); break;
+    }
+}
+
+// One tile, format E: EB entries of the row in flight per round trip (columns and coefficients, then the gathers).
+template <int NV, bool MULADD, int LM, int EB>
+__device__ __forceinline__ void sl_tile_explicit(const int *d, const SlParams &P, const double *const *s_src, double *const *s_dst,
+                                                 int row_end, int r, double &dot_acc)
+{
+    const double *src = s_src[0];
+    const double *src2 = NV == 2 ? s_src[1] : nullptr;
+    const long long off = ((long long)(unsigned int)d[0]) | ((long long)d[1] << 32);
+    const int row0 = d[2], nrows = d[3], rp = d[6];
+    const unsigned char *blob = P.blobs + off;
+    const int slice = r >> 5, lane = r & 31;
+    int soff = 0, tot = 0;
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+        const int w = d[8 + s];
+        if (s < slice) soff += w;
+        tot += w;
+    }
+    const int mine = d[8 + slice];
+    const int len = (int)__ldg(reinterpret_cast<const unsigned short *>(blob) + r);
+    const int *col = reinterpret_cast<const int *>(blob + sl_round_up(2 * rp, 128)) + (size_t)soff * 32 + lane;
+    const double *val = reinterpret_cast<const double *>(blob + sl_round_up(2 * rp, 128) + sl_round_up(128 * tot, 128)) + (size_t)soff * 32 + lane;
+    const int row = row0 + r;
+    double acc0 = 0.0, acc1 = 0.0;
+    for (int e0 = 0; e0 < mine; e0 += EB) {
+        int cc[EB];
+        double a[EB], xv[NV][EB];
+        // every load unconditional (each destination register defined once): a batch that runs past the slice's last
+        // slot re-reads that slot; padding entries carry a valid column (0); neither is used
+#pragma unroll
+        for (int u = 0; u < EB; u++) {
+            const int e = min(e0 + u, mine - 1);
+            cc[u] = sl_ld_col<sl_ch(LM)>(col + (size_t)e * 32);
+            a[u] = sl_ld_coef<sl_ch(LM)>(val + (size_t)e * 32);
+        }
+#pragma unroll
+        for (int u = 0; u < EB; u++) {
+            xv[0][u] = sl_ld_x(src + cc[u]);
+            if (NV == 2) xv[NV - 1][u] = sl_ld_x(src2 + cc[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < EB; u++)
+            if (e0 + u < len) {
+                acc0 = row_op<MULADD>(a[u], xv[0][u], acc0);
+                if (NV == 2) acc1 = row_op<MULADD>(a[u], xv[NV - 1][u], acc1);
+            }
+    }
+    if (r < nrows && row < row_end) sl_store_row<NV, LM>(P, s_dst, row, acc0, acc1, dot_acc);
+}
+
+// The consumer warps' loop: warp w owns slice w (rows 32 w .. 32 w + 31) of every tile of the CTA's items.
+template <int NV, bool MULADD, int EB, int LM>
+__device__ __forceinline__ double sl_consume(const SlParams &P, int n_my, uint64_t *s_ready, unsigned int *s_fin, const int *s_ntile,
+                                             const int (*s_desc)[SL_MAXCHUNK * 16],
+                                             const unsigned char (*s_mask)[SL_MAXCHUNK][SL_ROWS], const double *const *s_src,
+                                             double *const *s_dst, const int *s_row_end)
+{
+    const int tid = threadIdx.x;
+    double dot_acc = 0.0;
+    for (int it = 0; it < n_my; ++it) {
+        const int s = it % SL_RING;
+        mbar_wait(&s_ready[s], (it / SL_RING) & 1);
+        const int ntile = s_ntile[s];
+        for (int j = 0; j < ntile; j++) {
+            const int *d = s_desc[s] + 16 * j;
+            if ((tid & ~31) >= d[6]) continue;  // the tile has no slice for this warp
+            if (d[5] == SL_FMT_PATTERN)
+                sl_tile_pattern<NV, MULADD, LM>(d, (unsigned int)s_mask[s][j][tid], P, s_src, s_dst, *s_row_end, tid, dot_acc);
+            else
+                sl_tile_explicit<NV, MULADD, LM, EB>(d, P, s_src, s_dst, *s_row_end, tid, dot_acc);
+        }
+        __syncwarp();
+        if ((tid & 31) == 0) red_release_cta_shared_add(&s_fin[s], 1u);  // the slot may be reused and the item published
+    }
+    return dot_acc;
+}
+
+template <int NV, bool MULADD, int EB, int MINB>
+__global__ void __launch_bounds__(SL_THREADS, MINB) sell_kernel(const SlParams P)
+{
+    static_assert(NV == 1 || NV == 2, "one or two right-hand sides");
+    __shared__ __align__(16) int s_desc[SL_RING][SL_MAXCHUNK * 16];  // tile descriptors of the items in flight
+    __shared__ __align__(8) unsigned char s_mask[SL_RING][SL_MAXCHUNK][SL_ROWS];  // format P: the rows' slot masks
+    __shared__ int s_ntile[SL_RING];
+    __shared__ uint64_t s_ready[SL_RING];     // item's inputs complete + descriptors in place (dependency warp arrives)
+    __shared__ unsigned int s_fin[SL_RING];   // consumer warps that finished the slot's item, counted over the whole launch
+    __shared__ double s_red[SL_NCW];
+    // per-CTA constants the consumers need once per tile: kept out of their registers (read back by broadcast LDS)
+    __shared__ const double *s_src[2];
+    __shared__ double *s_dst[2];
+    __shared__ int s_row_end;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < SL_RING; s++) {
+            mbar_init(&s_ready[s], 1);
+            s_fin[s] = 0u;
+        }
+        fence_mbar_init();
+    }
+
+    const int2 role = __ldg(P.cta_role + blockIdx.x);
+    const int level = role.x;
+    const int c = role.y;
+    const int G = P.team[level];
+    const int count = P.count[level];
+    const int n_my = c < count ? (count - c + G - 1) / G : 0;
+    const int M = P.chunk;
+    if (tid == 0) {
+        s_src[0] = level == 0 ? P.x : P.levels[level - 1];
+        s_src[1] = NV == 2 ? (level == 0 ? P.x2 : P.levels2[level - 1]) : nullptr;
+        s_dst[0] = P.levels[level];
+        s_dst[1] = NV == 2 ? P.levels2[level] : nullptr;
+        s_row_end = P.level_rows[level];
+    }
+    __syncthreads();
+
+    if (warp == SL_NCW) {
+        // ===== dependency warp: per item, in order -- (1) fetch the tile descriptors into registers, (2) wait until the
+        // level below has completed the groups the item reads and the level that holds this one back has advanced,
+        // (3) wait for the ring slot (the item four back is finished by every consumer warp), (4) hand over. =====
+        const int ntl = P.ntl[level];
+        const int *itw = reinterpret_cast<const int *>(P.items[level]);
+        const int4 *tl4 = reinterpret_cast<const int4 *>(P.ltiles[level]);
+        const bool fwd = level > 0;
+        const bool back = level == 0 && P.bp_level > 0;
+        const int *cnt_f = P.counters + (size_t)(fwd ? level - 1 : 0) * P.ngroups;
+        const int *need_f = P.group_size + (size_t)(fwd ? level - 1 : 0) * P.ngroups;
+        const int *cnt_b = P.counters + (size_t)(back ? P.bp_level : 0) * P.ngroups;
+        const int *need_b = P.group_size + (size_t)(back ? P.bp_level : 0) * P.ngroups;
+        const bool prefetch = (P.flags & 2) && level == 0 && P.pf_dist > 0;
+        int wf = 0, wb = 0;
+        bool broken = false;
+        for (int it = 0; it < n_my; ++it) {
+            const long long i = (long long)c + (long long)it * G;
+            const int s = it % SL_RING;
+            // lanes 0..7: the item's words; every lane: descriptor quarter-words lane of tile lane/4 (4 int4 per tile)
+            int iw = 0;
+            if (lane < 8) iw = __ldg(itw + i * 8 + lane);
+            const long long t0 = i * M;
+            const int ntile = (int)min((long long)M, (long long)ntl - t0);
+            int4 dq = make_int4(0, 0, 0, 0);
+            if (lane < 4 * ntile) dq = __ldg(tl4 + t0 * 4 + lane);
+            if (prefetch && it + P.pf_dist < n_my) {
+                // level 0 streams its blobs from HBM: pull a later item's bytes into L2 now
+                const long long ip = (long long)c + (long long)(it + P.pf_dist) * G;
+                int pw = 0;
+                if (lane >= 3 && lane < 6) pw = __ldg(itw + ip * 8 + lane);  // pf_bytes, pf_off lo/hi
+                const int pb = __shfl_sync(0xffffffffu, pw, 3);
+                const unsigned int lo = (unsigned int)__shfl_sync(0xffffffffu, pw, 4);
+                const int hi = __shfl_sync(0xffffffffu, pw, 5);
+                if (lane == 0 && pb > 0) sl_prefetch_l2(P.blobs + (((long long)hi << 32) | lo), (uint32_t)pb);
+            }
+            const int ghi = __shfl_sync(0xffffffffu, iw, 1);
+            const int gback = __shfl_sync(0xffffffffu, iw, 2);
+            if (!broken) {
+                if (back && gback >= wb) wb = sl_wait_groups(cnt_b, need_b, P.epoch, P.ngroups, wb, gback, lane);
+                if (fwd && ghi >= wf && wb >= 0) wf = sl_wait_groups(cnt_f, need_f, P.epoch, P.ngroups, wf, ghi, lane);
+                if (wb < 0 || wf < 0) broken = true;
+            }
+            if (it >= SL_RING && !broken) {
+                const unsigned int need = (unsigned int)SL_NCW * (unsigned int)(it / SL_RING);
+                unsigned long long t1 = 0;
+                while (ld_acquire_cta_shared_u32(&s_fin[s]) < need) {
+                    __nanosleep(20);
+                    const unsigned long long t = sl_now();
+                    if (t1 == 0) t1 = t;
+                    else if (t - t1 > SL_TIMEOUT_NS) { broken = true; break; }
+                }
+            }
+            if (broken && lane == 0) *P.error = 1;  // keep going without waiting: the launch ends, the host reports it
+            // slot masks of the item's pattern tiles (256 bytes each: 8 per lane); their addresses come from the descriptors
+            uint2 mk[SL_MAXCHUNK];
+#pragma unroll
+            for (int j = 0; j < SL_MAXCHUNK; j++) {
+                mk[j] = make_uint2(0u, 0u);
+                if (j < ntile) {
+                    const unsigned int lo = (unsigned int)__shfl_sync(0xffffffffu, dq.x, 4 * j);
+                    const int hi = __shfl_sync(0xffffffffu, dq.y, 4 * j);
+                    const int fmt = __shfl_sync(0xffffffffu, dq.y, 4 * j + 1);
+                    if (fmt == SL_FMT_PATTERN)
+                        mk[j] = __ldg(reinterpret_cast<const uint2 *>(P.blobs + (((long long)hi << 32) | lo)) + lane);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < SL_MAXCHUNK; j++)
+                if (j < ntile) reinterpret_cast<uint2 *>(s_mask[s][j])[lane] = mk[j];
+            reinterpret_cast<int4 *>(s_desc[s])[lane] = dq;
+            if (lane == 0) s_ntile[s] = ntile;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_ready[s]);  // release.cta: descriptors + everything acquired above
+        }
+        return;
+    }
+
+    if (warp == SL_NCW + 1) {
+        // ===== publisher (k > 1): one gpu-scope fence for everything found finished at that moment, then one RED per
+        // item.  Consumers bump s_fin[slot] with release.cta after their stores; the acquire here + fence + RED is
+        // cumulative over those stores. =====
+        if (P.k <= 1) return;
+        const int *itw = reinterpret_cast<const int *>(P.items[level]);
+        int *cnt = P.counters + (size_t)level * P.ngroups;
+        int grp = 0;  // lane u: group of item it0 + u
+        for (int it = 0; it < n_my;) {
+            const int j = it & 31;
+            if (j == 0) {
+                grp = 0;
+                if (it + lane < n_my) grp = __ldg(itw + ((long long)c + (long long)(it + lane) * G) * 8);
+            }
+            int n = 0;
+            unsigned long long t0 = 0;
+            bool broken = false;
+            for (;;) {  // every consecutive finished item (at most to the end of this batch of 32)
+                const int i2 = it + n;
+                bool ok = false;
+                if (i2 < n_my && (n == 0 || (i2 & 31) != 0) && n < SL_RING) {
+                    const unsigned int need = (unsigned int)SL_NCW * (unsigned int)(i2 / SL_RING + 1);
+                    ok = ld_acquire_cta_shared_u32(&s_fin[i2 % SL_RING]) >= need;
+                }
+                ok = __shfl_sync(0xffffffffu, (int)ok, 0) != 0;
+                if (ok) { ++n; continue; }
+                if (n > 0) break;
+                __nanosleep(20);
+                const unsigned long long t = sl_now();
+                if (t0 == 0) t0 = t;
+                else if (t - t0 > SL_TIMEOUT_NS) { broken = true; break; }
+            }
+            if (broken) {
+                if (lane == 0) *P.error = 1;
+                return;
+            }
+            if (lane == 0) __threadfence();
+            __syncwarp();
+            for (int u = 0; u < n; u++) {
+                const int g = __shfl_sync(0xffffffffu, grp, (it + u) & 31);
+                if (lane == 0) red_relaxed_gpu_add(cnt + g, 1);
+            }
+            it += n;
+        }
+        return;
+    }
+
+    // ===== consumer warps =====
+    const bool last = (P.flags & 1) && level == P.k - 1;
+    double dot_acc = 0.0;
+    if (NV == 1 && P.dot_w)
+        dot_acc = sl_consume<NV, MULADD, EB, SL_LAST_DOT>(P, n_my, s_ready, s_fin, s_ntile, s_desc, s_mask, s_src, s_dst, &s_row_end);
+    else if (last)
+        sl_consume<NV, MULADD, EB, SL_LAST>(P, n_my, s_ready, s_fin, s_ntile, s_desc, s_mask, s_src, s_dst, &s_row_end);
+    else if (P.flags & 4)
+        sl_consume<NV, MULADD, EB, SL_MID_ALLOC>(P, n_my, s_ready, s_fin, s_ntile, s_desc, s_mask, s_src, s_dst, &s_row_end);
+    else if (P.flags & 8)
+        sl_consume<NV, MULADD, EB, SL_MID_KEEP>(P, n_my, s_ready, s_fin, s_ntile, s_desc, s_mask, s_src, s_dst, &s_row_end);
+    else
+        sl_consume<NV, MULADD, EB, SL_MID>(P, n_my, s_ready, s_fin, s_ntile, s_desc, s_mask, s_src, s_dst, &s_row_end);
+
+    if (P.dot_w) {
+        // deterministic: lanes -> warp (xor tree), warps in order, CTAs in order (last CTA finishes)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dot_acc += __shfl_xor_sync(0xffffffffu, dot_acc, o);
+        if (lane == 0) s_red[warp] = dot_acc;
+        named_bar_sync(2, SL_ROWS);
+        if (warp == 0) {
+            __shared__ bool is_last;
+            if (lane == 0) {
+                double sum = 0.0;
+                for (int w = 0; w < SL_NCW; w++) sum += s_red[w];
+                P.partials[blockIdx.x] = sum;
+                __threadfence();
+                const unsigned int ticket = atomicAdd(P.ticket, 1u);
+                is_last = (ticket == gridDim.x - 1);
+            }
+            __syncwarp();
+            if (is_last) {
+                __threadfence();
+                double sum = 0.0;
+                for (int b = lane; b < (int)gridDim.x; b += 32) sum += ld_cg_f64(P.partials + b);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                if (lane == 0) {
+                    *P.dot_out = sum;
+                    *P.ticket = 0u;
+                }
+            }
+        }
+    }
+}
+
+// -----------------------------------------------------------------------------------------------
+// kernel instances: geometry 0 = pattern operators (explicit tiles 4 entries per round trip; 3 CTAs per SM at 64 registers),
+// 1 = explicit-column operators (8 entries per round trip; 2 CTAs per SM at 96 registers)
+// -----------------------------------------------------------------------------------------------
+typedef void (*sl_fn)(const SlParams);
+static sl_fn sl_lookup(int geom, bool muladd, int nv)
+{
+    if (nv == 2) {
+        if (geom == 0) return muladd ? sell_kernel<2, true, 4, 2> : sell_kernel<2, false, 4, 2>;
+        return muladd ? sell_kernel<2, true, 8, 2> : sell_kernel<2, false, 8, 2>;
+    }
+    if (geom == 0) return muladd ? sell_kernel<1, true, 4, 3> : sell_kernel<1, false, 4, 3>;
+    return muladd ? sell_kernel<1, true, 8, 2> : sell_kernel<1, false, 8, 2>;
+}
+
+// -----------------------------------------------------------------------------------------------
+// host side: tiling + pattern detection + blobs
+// -----------------------------------------------------------------------------------------------
+struct SellHost {
+    std::vector<nsk_tile> tiles;   // {row0, nrows, nz0, nz1}: input of nsk_wave_deps
+    std::vector<SlTile> stiles;
+    std::vector<unsigned char> blobs;
+    size_t blob_bytes = 0;
+    int n_pattern = 0;
+};
+
+static void sl_parallel(int n, const std::function<void(int)> &body)
+{
+    std::atomic<int> next(0);
+    auto work = [&]() {
+        for (;;) {
+            const int t0 = next.fetch_add(64);
+            if (t0 >= n) return;
+            for (int t = t0; t < std::min(n, t0 + 64); t++) body(t);
+        }
+    };
+    const int nth = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::vector<std::thread> th;
+    for (int i = 1; i < nth; i++) th.emplace_back(work);
+    work();
+    for (auto &x : th) x.join();
+}
+
+// Host-only packer.  Returns "" on success, else why the operator is not stored as sliced-ELL tiles.
+static std::string sl_pack_host(int n, int n_cols, int64_t nnz, const int *ptrow, const int *indcol, const double *coef,
+                                const std::vector<int> &breaks, SellHost &out)
+{
+    if (n == 0 || nnz == 0) return "empty operator";
+    (void)n_cols;
+    std::vector<nsk_tile> &tiles = out.tiles;
+    tiles.clear();
+    {
+        size_t bi = 0;
+        int r = 0;
+        while (r < n) {
+            while (bi < breaks.size() && breaks[bi] <= r) bi++;
+            const int seg_end = bi < breaks.size() ? std::min(n, breaks[bi]) : n;
+            const int rows = std::min(SL_ROWS, seg_end - r);
+            tiles.push_back(nsk_tile{r, rows, ptrow[r], ptrow[r + rows]});
+            r += rows;
+        }
+    }
+    const int ntiles = (int)tiles.size();
+    std::vector<SlTile> &st = out.stiles;
+    st.assign(ntiles, SlTile());
+    // 1. per tile: format, geometry, size
+    std::atomic<int> too_long(0);
+    sl_parallel(ntiles, [&](int t) {
+        const nsk_tile &tl = tiles[t];
+        SlTile &d = st[t];
+        d.row0 = tl.row0;
+        d.nrows = tl.nrows;
+        d.rp = sl_round_up(tl.nrows, 32);
+        int width = 0, sw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int r = 0; r < tl.nrows; r++) {
+            const int len = ptrow[tl.row0 + r + 1] - ptrow[tl.row0 + r];
+            width = std::max(width, len);
+            sw[r >> 5] = std::max(sw[r >> 5], len);
+        }
+        if (width > 65535) { too_long.store(1); return; }
+        d.width = width;
+        bool pattern = width > 0 && width <= SL_PSLOTS;
+        int rel[SL_PSLOTS] = {0, 0, 0, 0, 0, 0, 0, 0};
+        int pw = 0;  // slots of the pattern
+        if (pattern) {
+            // rows with ascending columns (the usual case): the pattern is the sorted union of the rows' offsets -- rows
+            // on a domain face lack different neighbours, and no single row need have them all
+            bool ascending = true;
+            for (int r = 0; r < tl.nrows && pattern && ascending; r++) {
+                const int p0 = ptrow[tl.row0 + r], p1 = ptrow[tl.row0 + r + 1];
+                for (int j = p0; j < p1 && pattern; j++) {
+                    if (j > p0 && indcol[j] <= indcol[j - 1]) { ascending = false; break; }
+                    const int o = indcol[j] - (tl.row0 + r);
+                    int e = 0;
+                    while (e < pw && rel[e] < o) e++;
+                    if (e < pw && rel[e] == o) continue;
+                    if (pw == SL_PSLOTS) { pattern = false; break; }
+                    for (int u = pw; u > e; u--) rel[u] = rel[u - 1];
+                    rel[e] = o;
+                    pw++;
+                }
+            }
+            if (pattern && !ascending) {
+                // any other entry order: the first row of full width is the pattern, every row must be a sub-pattern
+                // of it with slots ascending in entry order (the chain's order is the row's storage order)
+                int rref = 0;
+                while (ptrow[tl.row0 + rref + 1] - ptrow[tl.row0 + rref] != width) rref++;
+                const int p = ptrow[tl.row0 + rref];
+                pw = width;
+                for (int e = 0; e < width; e++) rel[e] = indcol[p + e] - (tl.row0 + rref);
+                for (int r = 0; r < tl.nrows && pattern; r++) {
+                    const int p0 = ptrow[tl.row0 + r], p1 = ptrow[tl.row0 + r + 1];
+                    int e = 0;
+                    for (int j = p0; j < p1; j++) {
+                        while (e < pw && rel[e] + tl.row0 + r != indcol[j]) e++;
+                        if (e == pw) { pattern = false; break; }
+                        e++;
+                    }
+                }
+            }
+            if (pattern) d.width = width = pw;
+        }
+        if (width == 0) pattern = true;  // a tile of empty rows: nothing stored but the (zero) masks
+        if (pattern) {
+            d.fmt = SL_FMT_PATTERN;
+            for (int e = 0; e < 8; e++) d.rel[e] = rel[e];
+            d.bytes = sl_blob_bytes_pattern(width);
+        } else {
+            d.fmt = SL_FMT_EXPLICIT;
+            int tot = 0;
+            for (int s = 0; s < 8; s++) { d.rel[s] = sw[s]; tot += sw[s]; }
+            d.bytes = sl_blob_bytes_explicit(d.rp, tot);
+        }
+    });
+    if (too_long.load()) return "a row is longer than 65535 entries";
+    size_t total = 0;
+    int n_pattern = 0;
+    for (int t = 0; t < ntiles; t++) {
+        st[t].off = (long long)total;
+        total += (size_t)st[t].bytes;
+        n_pattern += st[t].fmt == SL_FMT_PATTERN;
+    }
+    // slice padding: refuse operators whose rows are so ragged that the tiles would outweigh CSR by half
+    if ((double)total > 1.5 * (12.0 * (double)nnz + 4.0 * n) + 65536.0) return "row lengths too ragged for sliced-ELL tiles";
+    out.blob_bytes = total;
+    out.n_pattern = n_pattern;
+    out.blobs.assign(total + 128, 0);
+    // 2. the blobs
+    sl_parallel(ntiles, [&](int t) {
+        const nsk_tile &tl = tiles[t];
+        const SlTile &d = st[t];
+        unsigned char *b = out.blobs.data() + d.off;
+        if (d.fmt == SL_FMT_PATTERN) {
+            unsigned char *mask = b;
+            double *val = reinterpret_cast<double *>(b + SL_ROWS);
+            for (int r = 0; r < tl.nrows; r++) {
+                const int p0 = ptrow[tl.row0 + r], p1 = ptrow[tl.row0 + r + 1];
+                unsigned int m = 0;
+                int e = 0;
+                for (int j = p0; j < p1; j++) {
+                    while (d.rel[e] + tl.row0 + r != indcol[j]) e++;  // phase 1 proved that a slot matches
+                    m |= 1u << e;
+                    val[(size_t)e * SL_ROWS + r] = coef[j];
+                    e++;
+                }
+                mask[r] = (unsigned char)m;
+            }
+        } else {
+            int tot = 0, soff[8];
+            for (int s = 0; s < 8; s++) { soff[s] = tot; tot += d.rel[s]; }
+            unsigned short *len = reinterpret_cast<unsigned short *>(b);
+            int *col = reinterpret_cast<int *>(b + sl_round_up(2 * d.rp, 128));
+            double *val = reinterpret_cast<double *>(b + sl_round_up(2 * d.rp, 128) + sl_round_up(128 * tot, 128));
+            for (int r = 0; r < tl.nrows; r++) {
+                const int p0 = ptrow[tl.row0 + r], p1 = ptrow[tl.row0 + r + 1];
+                len[r] = (unsigned short)(p1 - p0);
+                const size_t base = (size_t)soff[r >> 5] * 32 + (size_t)(r & 31);
+                for (int j = p0; j < p1; j++) {
+                    col[base + (size_t)(j - p0) * 32] = indcol[j];
+                    val[base + (size_t)(j - p0) * 32] = coef[j];
+                }
+            }
+        }
+    });
+    return "";
+}
+
+// Expands tile t back to CSR rows (host; tests and the GPU packer's cross-check).
+static void sl_expand_tile(const SlTile &d, const unsigned char *blobs, std::vector<int> &len_out, std::vector<int> &col_out,
+                           std::vector<double> &val_out)
+{
+    const unsigned char *b = blobs + d.off;
+    len_out.assign(d.nrows, 0);
+    col_out.clear();
+    val_out.clear();
+    if (d.fmt == SL_FMT_PATTERN) {
+        const unsigned char *mask = b;
+        const double *val = reinterpret_cast<const double *>(b + SL_ROWS);
+        for (int r = 0; r < d.nrows; r++) {
+            for (int e = 0; e < d.width; e++)
+                if ((mask[r] >> e) & 1) {
+                    col_out.push_back(d.row0 + r + d.rel[e]);
+                    val_out.push_back(val[(size_t)e * SL_ROWS + r]);
+                    len_out[r]++;
+                }
+        }
+    } else {
+        int tot = 0, soff[8];
+        for (int s = 0; s < 8; s++) { soff[s] = tot; tot += d.rel[s]; }
+        const unsigned short *len = reinterpret_cast<const unsigned short *>(b);
+        const int *col = reinterpret_cast<const int *>(b + sl_round_up(2 * d.rp, 128));
+        const double *val = reinterpret_cast<const double *>(b + sl_round_up(2 * d.rp, 128) + sl_round_up(128 * tot, 128));
+        for (int r = 0; r < d.nrows; r++) {
+            const size_t base = (size_t)soff[r >> 5] * 32 + (size_t)(r & 31);
+            len_out[r] = len[r];
+            for (int e = 0; e < (int)len[r]; e++) {
+                col_out.push_back(col[base + (size_t)e * 32]);
+                val_out.push_back(val[base + (size_t)e * 32]);
+            }
+        }
+    }
+}
+
+// -----------------------------------------------------------------------------------------------
+// level schedule (host only): per-level tile lists, items, groups, dependencies, CTA roles
+// -----------------------------------------------------------------------------------------------
+struct SlSchedule {
+    int k = 0, chunk = 1, gi = 1, ngroups = 0;
+    std::vector<std::vector<int>> ltile;   // per level: tile ids in position order (inside the level's row prefix)
+    std::vector<std::vector<SlItem>> items;
+    std::vector<int> gsize;                // [k][ngroups]
+    std::vector<int> teams;
+    std::vector<int2> roles;
+    bool same_lists = true;                // every level has level 0's tile list
+};
+
+// tile_at_pos: tile id at each position of global row order; pmax[t]: last position tile t's columns refer to.
+// lead: how far (positions) level 0 may run ahead of level k-1 per hop.  teams[] in: requested team sizes.
+static void sl_build_schedule(const std::vector<SlTile> &tiles, const std::vector<int> &tile_at_pos, const std::vector<int> &pmax,
+                              const std::vector<int> &lr, int k, int chunk, int lead, int interleave, std::vector<int> teams,
+                              SlSchedule &S)
+{
+    const int ntiles = (int)tiles.size();
+    S.k = k;
+    S.chunk = chunk;
+    S.gi = std::max(1, WF_GROUP / chunk);
+    S.ltile.assign(k, std::vector<int>());
+    S.items.assign(k, std::vector<SlItem>());
+    std::vector<std::vector<int>> lpos(k);  // positions of the level's tiles (ascending)
+    S.same_lists = true;
+    for (int l = 0; l < k; l++) {
+        for (int pos = 0; pos < ntiles; pos++) {
+            const int t = tile_at_pos[pos];
+            if (tiles[t].row0 >= lr[l]) continue;  // outside this level's row prefix (distributed shrink)
+            S.ltile[l].push_back(t);
+            lpos[l].push_back(pos);
+        }
+        if (l > 0 && S.ltile[l] != S.ltile[0]) S.same_lists = false;
+    }
+    int maxitems = 0;
+    for (int l = 0; l < k; l++) maxitems = std::max(maxitems, ((int)S.ltile[l].size() + chunk - 1) / chunk);
+    S.ngroups = std::max(1, (maxitems + S.gi - 1) / S.gi);
+    S.gsize.assign((size_t)k * S.ngroups, 0);
+    const int hold = k > 1 ? (k - 1) * lead : -1;
+    for (int l = 0; l < k; l++) {
+        const int nt = (int)S.ltile[l].size();
+        const int ni = (nt + chunk - 1) / chunk;
+        S.items[l].resize(ni);
+        for (int i = 0; i < ni; i++) {
+            SlItem &it = S.items[l][i];
+            it.group = i / S.gi;
+            it.ghi = -1;
+            it.gback = -1;
+            it.pad[0] = it.pad[1] = 0;
+            const int a = i * chunk, b = std::min(nt, a + chunk);
+            if (l > 0) {
+                int pm = -1;
+                for (int u = a; u < b; u++) pm = std::max(pm, pmax[S.ltile[l][u]]);
+                // tiles of the level below at positions <= pm
+                const int j = (int)(std::upper_bound(lpos[l - 1].begin(), lpos[l - 1].end(), pm) - lpos[l - 1].begin()) - 1;
+                if (j >= 0) it.ghi = (j / chunk) / S.gi;
+            }
+            if (l == 0 && hold >= 0) {
+                const int p = lpos[l][a] - hold;
+                if (p > 0) {
+                    // items of level k-1 that lie entirely below position p
+                    const int j = (int)(std::lower_bound(lpos[k - 1].begin(), lpos[k - 1].end(), p) - lpos[k - 1].begin());
+                    it.gback = (j / chunk) / S.gi - 1;
+                }
+            }
+            // blobs of consecutive tile ids are contiguous
+            bool contiguous = true;
+            for (int u = a + 1; u < b; u++) contiguous = contiguous && S.ltile[l][u] == S.ltile[l][u - 1] + 1;
+            it.pf_off = tiles[S.ltile[l][a]].off;
+            it.pf_bytes = 0;
+            if (contiguous) {
+                const SlTile &lastt = tiles[S.ltile[l][b - 1]];
+                it.pf_bytes = (int)(lastt.off + lastt.bytes - it.pf_off);
+            }
+            S.gsize[(size_t)l * S.ngroups + it.group]++;
+        }
+    }
+    for (int l = 0; l < k; l++) teams[l] = std::max(1, std::min(teams[l], std::max(1, (int)S.items[l].size())));
+    S.teams = teams;
+    S.roles.clear();
+    int total = 0;
+    for (int l = 0; l < k; l++) total += teams[l];
+    std::vector<int> given(k, 0);
+    if (interleave) {
+        for (int b = 0; b < total; b++) {
+            int best = -1;
+            double bestv = 0.0;
+            for (int l = 0; l < k; l++) {  // the level furthest behind its share
+                if (given[l] >= teams[l]) continue;
+                const double v = (double)(b + 1) * teams[l] / total - given[l];
+                if (best < 0 || v > bestv) { best = l; bestv = v; }
+            }
+            S.roles.push_back(make_int2(best, given[best]++));
+        }
+    } else {
+        for (int l = 0; l < k; l++)
+            for (int i = 0; i < teams[l]; i++) S.roles.push_back(make_int2(l, i));
+    }
+}
+
+// CPU model of the kernel's protocol (tests): every CTA opens its items strictly in order (the dependency warp is
+// head-of-line blocking), an item opens when groups <= ghi of the level below and groups <= gback of level k-1 have
+// reached their sizes, up to `ring` items per CTA are open at once and finish in random order, but are PUBLISHED in
+// order.  Returns the number of items published; the schedule is sound iff that equals the total.  reads[t] = tiles
+// whose rows tile t's nonzeros reference; *violations counts items opened while a tile they read was unpublished at
+// the level below (and inside that level's prefix).
+static long long sl_simulate(const SlSchedule &S, int ring, unsigned seed, const std::vector<std::vector<int>> *reads,
+                             const std::vector<SlTile> *tiles, const std::vector<int> *lr, long long *violations)
+{
+    const int k = S.k, grid = (int)S.roles.size();
+    const int ntiles_all = reads ? (int)reads->size() : 0;
+    std::vector<std::vector<char>> tile_done(reads ? k : 0, std::vector<char>((size_t)ntiles_all, 0));
+    std::vector<std::vector<int>> cnt(k, std::vector<int>(S.ngroups, 0));
+    std::vector<int> water(k, 0);
+    auto advance = [&](int l) {
+        while (water[l] < S.ngroups && cnt[l][water[l]] >= S.gsize[(size_t)l * S.ngroups + water[l]]) water[l]++;
+    };
+    for (int l = 0; l < k; l++) advance(l);
+    struct Open { int idx; bool finished; };
+    std::vector<int> next(grid, 0);
+    std::vector<std::vector<Open>> open(grid);  // in opening order
+    long long done = 0, total = 0, bad = 0;
+    for (int l = 0; l < k; l++) total += (long long)S.items[l].size();
+    unsigned rng = seed * 2654435761u + 12345u;
+    auto rnd = [&]() { rng = rng * 1664525u + 1013904223u; return rng >> 8; };
+    std::vector<int> order(grid);
+    for (int b = 0; b < grid; b++) order[b] = b;
+    bool progress = true, force = false;
+    while (done < total && (progress || !force)) {
+        force = !progress;
+        progress = false;
+        for (int i = grid - 1; i > 0; i--) std::swap(order[i], order[rnd() % (unsigned)(i + 1)]);
+        for (int oi = 0; oi < grid; oi++) {
+            const int b = order[oi];
+            const int level = S.roles[b].x, c = S.roles[b].y, G = S.teams[level];
+            // finish one open item (random pick), then publish the finished prefix
+            if (!open[b].empty() && (force || (rnd() & 1) || (int)open[b].size() >= ring)) {
+                std::vector<int> cand;
+                for (int u = 0; u < (int)open[b].size(); u++)
+                    if (!open[b][u].finished) cand.push_back(u);
+                if (!cand.empty()) {
+                    open[b][cand[rnd() % (unsigned)cand.size()]].finished = true;
+                    progress = true;
+                }
+                while (!open[b].empty() && open[b].front().finished) {
+                    const int idx = open[b].front().idx;
+                    const SlItem &it = S.items[level][idx];
+                    open[b].erase(open[b].begin());
+                    cnt[level][it.group]++;
+                    if (reads) {
+                        const int a = idx * S.chunk, e = std::min((int)S.ltile[level].size(), a + S.chunk);
+                        for (int u = a; u < e; u++) tile_done[level][(size_t)S.ltile[level][u]] = 1;
+                    }
+                    advance(level);
+                    done++;
+                    progress = true;
+                }
+            }
+            const long long idx = (long long)c + (long long)next[b] * G;
+            if ((int)open[b].size() < ring && idx < (long long)S.items[level].size()) {
+                const SlItem &it = S.items[level][(size_t)idx];
+                const bool fwd_ok = level == 0 || it.ghi < 0 || water[level - 1] > it.ghi || water[level - 1] >= S.ngroups;
+                const bool back_ok = it.gback < 0 || water[k - 1] > it.gback || water[k - 1] >= S.ngroups;
+                if (fwd_ok && back_ok) {
+                    if (reads && level > 0) {
+                        const int a = (int)idx * S.chunk, e = std::min((int)S.ltile[level].size(), a + S.chunk);
+                        for (int u = a; u < e; u++)
+                            for (int d : (*reads)[(size_t)S.ltile[level][u]])
+                                if ((*tiles)[(size_t)d].row0 < (*lr)[level - 1] && !tile_done[level - 1][(size_t)d]) bad++;
+                    }
+                    open[b].push_back(Open{(int)idx, false});
+                    next[b]++;
+                    progress = true;
+                }
+            }
+        }
+    }
+    if (violations) *violations = bad;
+    return done;
+}
+
+static std::vector<int> sl_team_sizes(int resident, int k, int w0_pct)
+{
+    std::vector<int> teams(k, 0);
+    const double wsum = (double)w0_pct + 100.0 * (k - 1);
+    int used = 0;
+    for (int l = 1; l < k; l++) { teams[l] = std::max(1, (int)(resident * 100.0 / wsum)); used += teams[l]; }
+    teams[0] = std::max(1, resident - used);
+    return teams;
+}
+
+// -----------------------------------------------------------------------------------------------
+// host-only access for the CPU test-suite: pack, expand, simulate
+// -----------------------------------------------------------------------------------------------
+struct nsk_sell_host_s {
+    SellHost H;
+    std::string why;
+    int n = 0, n_cols = 0;
+    std::vector<int> ptrow, indcol;
+};
+
+NSK_API int nsk_sell_host_create(int n, int n_cols, int64_t nnz, const int *ptrow, const int *indcol, const double *coef,
+                                 void **out)
+{
+    if (!out || !ptrow || (nnz > 0 && (!indcol || !coef))) return NSK_ERR_INVALID;
+    nsk_sell_host_s *h = new nsk_sell_host_s();
+    h->n = n;
+    h->n_cols = n_cols;
+    h->ptrow.assign(ptrow, ptrow + n + 1);
+    h->indcol.assign(indcol, indcol + nnz);
+    h->why = sl_pack_host(n, n_cols, nnz, ptrow, indcol, coef, std::vector<int>(), h->H);
+    *out = h;
+    return NSK_OK;
+}
+
+NSK_API const char *nsk_sell_host_why(void *handle) { return static_cast<nsk_sell_host_s *>(handle)->why.c_str(); }
+
+NSK_API int nsk_sell_host_stats(void *handle, int64_t *bytes, int64_t *ntiles, int64_t *pattern_tiles)
+{
+    nsk_sell_host_s *h = static_cast<nsk_sell_host_s *>(handle);
+    if (!h->why.empty()) return NSK_ERR_UNSUPPORTED;
+    if (bytes) *bytes = (int64_t)h->H.blob_bytes;
+    if (ntiles) *ntiles = (int64_t)h->H.stiles.size();
+    if (pattern_tiles) *pattern_tiles = h->H.n_pattern;
+    return NSK_OK;
+}
+
+// Expands the tiles back to CSR (row pointers, global columns, values).  Arrays sized n+1 / nnz by the caller.
+NSK_API int nsk_sell_host_expand(void *handle, int *ptrow, int *indcol, double *coef)
+{
+    nsk_sell_host_s *h = static_cast<nsk_sell_host_s *>(handle);
+    if (!h->why.empty()) return NSK_ERR_UNSUPPORTED;
+    int64_t k = 0;
+    ptrow[0] = 0;
+    std::vector<int> len, col;
+    std::vector<double> val;
+    for (const SlTile &d : h->H.stiles) {
+        sl_expand_tile(d, h->H.blobs.data(), len, col, val);
+        size_t q = 0;
+        for (int r = 0; r < d.nrows; r++) {
+            for (int e = 0; e < len[r]; e++, q++) {
+                indcol[k] = col[q];
+                coef[k] = val[q];
+                k++;
+            }
+            ptrow[d.row0 + r + 1] = (int)k;
+        }
+    }
+    return NSK_OK;
+}
+
+// Builds the level schedule exactly like the GPU path (exact dependencies from the columns, natural row order,
+// optional per-level row prefixes) and runs the CPU protocol model.  Returns the number of items that did NOT get
+// published (0 = sound), -1000000 - v when v items opened before their inputs were published, or a negative status.
+NSK_API long long nsk_sell_host_simulate(void *handle, int k, int chunk, int lead_slack_tiles, int resident, int w0_pct,
+                                         int interleave, int ring, const int *level_rows, unsigned seed, long long *items_out,
+                                         int *reach_out, int pmax_bias)
+{
+    nsk_sell_host_s *h = static_cast<nsk_sell_host_s *>(handle);
+    if (!h->why.empty()) return NSK_ERR_UNSUPPORTED;
+    if (k < 1 || k > NSK_MAX_K || resident < k || ring < 1 || chunk < 1 || chunk > SL_MAXCHUNK) return NSK_ERR_INVALID;
+    const std::vector<SlTile> &tiles = h->H.stiles;
+    const int ntiles = (int)tiles.size();
+    std::vector<int> row0s(ntiles), tile_at_pos(ntiles), pmax(ntiles, 0);
+    for (int t = 0; t < ntiles; t++) { row0s[t] = tiles[t].row0; tile_at_pos[t] = t; }
+    std::vector<std::vector<int>> reads((size_t)ntiles);
+    int reach = 0;
+    for (int t = 0; t < ntiles; t++) {
+        std::vector<int> &rd = reads[(size_t)t];
+        int mx = -1;
+        for (int j = h->ptrow[tiles[t].row0]; j < h->ptrow[tiles[t].row0 + tiles[t].nrows]; j++) {
+            const int g = h->indcol[j];
+            if (g >= h->n) continue;  // ghost entry of x: read by level 0 only
+            const int d = (int)(std::upper_bound(row0s.begin(), row0s.end(), g) - row0s.begin()) - 1;
+            mx = std::max(mx, d);
+            if (rd.empty() || rd.back() != d) rd.push_back(d);
+        }
+        std::sort(rd.begin(), rd.end());
+        rd.erase(std::unique(rd.begin(), rd.end()), rd.end());
+        pmax[t] = mx < 0 ? t : mx;
+        reach = std::max(reach, pmax[t] - t);
+        pmax[t] = std::max(-1, pmax[t] + pmax_bias);  // tests weaken the dependencies on purpose to see the model object
+    }
+    std::vector<int> lr(k);
+    for (int l = 0; l < k; l++) lr[l] = level_rows ? level_rows[l] : h->n;
+    // a negative slack undercuts the safe minimum on purpose: the test-suite checks that the model then reports a deadlock
+    const int lead = std::max(1, reach + 1 + WF_GROUP + chunk + lead_slack_tiles);
+    SlSchedule S;
+    sl_build_schedule(tiles, tile_at_pos, pmax, lr, k, chunk, lead, interleave, sl_team_sizes(resident, k, w0_pct), S);
+    long long violations = 0, total = 0;
+    for (int l = 0; l < k; l++) total += (long long)S.items[l].size();
+    const long long done = sl_simulate(S, ring, seed, &reads, &tiles, &lr, &violations);
+    if (items_out) *items_out = total;
+    if (reach_out) *reach_out = reach;
+    if (violations > 0) return -1000000 - violations;
+    return total - done;
+}
+
+NSK_API void nsk_sell_host_destroy(void *handle) { delete static_cast<nsk_sell_host_s *>(handle); }
+
+// -----------------------------------------------------------------------------------------------
+// device side: the operator's tiles (cached per operator), level plans, launches
+// -----------------------------------------------------------------------------------------------
+struct SlPlan {
+    int k = 0, resident = 0, chunk = 0, w0_pct = 0, interleave = 0, l2_pct = 0, lead_pct = 0, nv = 1;
+    std::vector<int> level_rows;
+    bool rejected = false;
+    int grid = 0, ngroups = 0, reach = 0, lead = 0, epoch = 0;
+    std::vector<int> teams, count, ntl;
+    std::vector<const SlItem *> d_items;    // per level (into d_item_buf)
+    std::vector<const SlTile *> d_ltiles;   // per level (into d_ltile_buf, or the operator's own array)
+    SlItem *d_item_buf = nullptr;
+    SlTile *d_ltile_buf = nullptr;
+    int *d_counters = nullptr, *d_group_size = nullptr;
+    int2 *d_roles = nullptr;
+};
+
+struct SellOp {
+    bool ok = false;
+    std::string why;
+    int ntiles = 0, n_pattern = 0;
+    size_t blob_bytes = 0;
+    unsigned char *d_blobs = nullptr;
+    SlTile *d_tiles = nullptr;
+    std::vector<SlTile> h_tiles;
+    nsk_tiling csr_view;
+    std::vector<SlPlan> plans;
+    int *h_error = nullptr, *d_error = nullptr;  // host-mapped watchdog flag
+};
+
+static std::map<nsk_csr_t, SellOp *> g_sell;
+static std::mutex g_sell_mu;
+
+void nsk_sell_free(nsk_csr_t A)
+{
+    SellOp *op = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_sell_mu);
+        auto it = g_sell.find(A);
+        if (it == g_sell.end()) return;
+        op = it->second;
+        g_sell.erase(it);
+    }
+    for (SlPlan &p : op->plans) {
+        if (p.d_item_buf) cudaFree(p.d_item_buf);
+        if (p.d_ltile_buf) cudaFree(p.d_ltile_buf);
+        if (p.d_counters) cudaFree(p.d_counters);
+        if (p.d_group_size) cudaFree(p.d_group_size);
+        if (p.d_roles) cudaFree(p.d_roles);
+    }
+    if (op->d_blobs) cudaFree(op->d_blobs);
+    if (op->d_tiles) cudaFree(op->d_tiles);
+    if (op->h_error) cudaFreeHost(op->h_error);
+    delete op;
+}
+
+static SellOp *sl_get(nsk_csr_t A)
+{
+    {
+        std::lock_guard<std::mutex> lk(g_sell_mu);
+        auto it = g_sell.find(A);
+        if (it != g_sell.end()) return it->second;
+    }
+    SellOp *op = new SellOp();
+    {
+        std::lock_guard<std::mutex> lk(g_sell_mu);
+        g_sell[A] = op;
+    }
+    const int n = A->n;
+    const std::vector<int> &ptrow = nsk_csr_host_ptrow(A);
+    if (n == 0 || A->nnz == 0) { op->why = "empty operator"; return op; }
+    if ((int)ptrow.size() != n + 1) { op->why = "host row pointers missing"; return op; }
+    // the caller's host arrays are gone: read the entries back once and pack on the host
+    std::vector<int> indcol((size_t)A->nnz);
+    std::vector<double> coef((size_t)A->nnz);
+    if (cudaMemcpy(indcol.data(), A->d_indcol, sizeof(int) * (size_t)A->nnz, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(coef.data(), A->d_coef, sizeof(double) * (size_t)A->nnz, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        op->why = "reading the operator back failed";
+        return op;
+    }
+    SellHost H;
+    op->why = sl_pack_host(n, A->n_cols, A->nnz, ptrow.data(), indcol.data(), coef.data(), A->breaks, H);
+    if (!op->why.empty()) return op;
+    const int ntiles = (int)H.tiles.size();
+    if (cudaMalloc(&op->d_blobs, H.blobs.size()) != cudaSuccess ||
+        cudaMalloc(&op->d_tiles, sizeof(SlTile) * (size_t)ntiles) != cudaSuccess ||
+        cudaHostAlloc(&op->h_error, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer(&op->d_error, op->h_error, 0) != cudaSuccess) {
+        op->why = "allocation of the sliced-ELL operator failed";
+        cudaGetLastError();
+        return op;
+    }
+    *op->h_error = 0;
+    cudaMemcpy(op->d_blobs, H.blobs.data(), H.blobs.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(op->d_tiles, H.stiles.data(), sizeof(SlTile) * (size_t)ntiles, cudaMemcpyHostToDevice);
+    op->ntiles = ntiles;
+    op->n_pattern = H.n_pattern;
+    op->blob_bytes = H.blob_bytes;
+    op->h_tiles.swap(H.stiles);
+    op->csr_view.tile_rows = SL_ROWS;
+    op->csr_view.ntiles = ntiles;
+    op->csr_view.nlong = 0;
+    op->csr_view.h_tiles.swap(H.tiles);
+    op->ok = true;
+    return op;
+}
+
+static int sl_geom(nsk_csr_t A, SellOp *op)
+{
+    const int v = (int)A->ctx->opt.sell_geom;
+    if (v == 1 || v == 2) return v - 1;
+    return 2 * op->n_pattern >= op->ntiles ? 0 : 1;
+}
+
+static SlPlan *sl_plan(nsk_csr_t A, SellOp *op, int k, const int *level_rows, int resident, int nv, const char **why)
+{
+    nsk_ctx_t ctx = A->ctx;
+    std::vector<int> lr(k);
+    for (int l = 0; l < k; l++) lr[l] = level_rows ? level_rows[l] : A->n;
+    int chunk = (int)ctx->opt.sell_chunk;
+    if (chunk <= 0) chunk = k > 1 ? 2 : 4;
+    chunk = std::min(chunk, SL_MAXCHUNK);
+    while (WF_GROUP % chunk) chunk--;  // a chunk never straddles a completion group of level 0
+    const int w0_pct = k > 1 ? (ctx->opt.pipe_w0_pct > 0 ? (int)ctx->opt.pipe_w0_pct : 100) : 100;
+    const int interleave = ctx->opt.pipe_interleave ? 1 : 0;
+    const int l2_pct = (int)ctx->opt.wave_l2_pct;
+    const int lead_pct = (int)ctx->opt.wave_slack_pct;
+    for (SlPlan &p : op->plans)
+        if (p.k == k && p.resident == resident && p.level_rows == lr && p.chunk == chunk && p.w0_pct == w0_pct &&
+            p.interleave == interleave && p.l2_pct == l2_pct && p.lead_pct == lead_pct && p.nv == nv) {
+            if (p.rejected) { *why = "level window exceeds the L2 budget"; return nullptr; }
+            return &p;
+        }
+    const int ntiles = op->ntiles;
+    SlPlan p;
+    p.k = k; p.resident = resident; p.level_rows = lr; p.chunk = chunk; p.w0_pct = w0_pct; p.interleave = interleave;
+    p.l2_pct = l2_pct; p.lead_pct = lead_pct; p.nv = nv;
+    std::vector<int> tile_at_pos(ntiles), pmax(ntiles, 0);
+    for (int t = 0; t < ntiles; t++) tile_at_pos[t] = t;
+    if (k > 1) {
+        WaveDeps D;
+        if (!nsk_wave_deps(A, op->csr_view, D, why)) return nullptr;
+        tile_at_pos = D.tile_at_pos;
+        for (int t = 0; t < ntiles; t++) pmax[t] = std::min(ntiles - 1, (D.ghi[t] + 1) * WF_GROUP - 1);
+        p.reach = D.reach;
+        // lead = how far level 0 may run ahead of level k-1, per hop: the pattern's reach + one completion group + one
+        // chunk at least, plus slack for the publish -> poll latency and the items in flight.  The window that must
+        // stay L2-resident is (k-1) * lead tiles of blobs plus the level vectors over it; by default the slack is
+        // whatever the L2 budget allows.
+        const double tile_bytes = (double)op->blob_bytes / ntiles + 8.0 * SL_ROWS * (k + 1) * nv;
+        const double budget = (l2_pct > 0 ? (double)l2_pct : 70.0) / 100.0 * (double)ctx->prop.l2CacheSize;
+        const int lead_min = D.reach + 1 + WF_GROUP + chunk;
+        if (lead_pct >= 0)
+            p.lead = lead_min + (int)((double)lead_pct / 100.0 * 2.0 * (resident / k) * chunk + 0.999);
+        else
+            p.lead = std::max(lead_min + 2 * WF_GROUP, (int)(budget / ((double)(k - 1) * tile_bytes)));
+        const double window = (double)(k - 1) * p.lead * tile_bytes;
+        // the items a team has in flight (team x chunk tiles) must fit between two levels besides the reach, or every
+        // level waits on the loop latency: below that the caller fuses fewer levels per launch
+        const int min_slack = (resident / k) * chunk;
+        const bool thin = lead_pct < 0 && p.lead < ntiles && p.lead - lead_min < min_slack;
+        if (window > budget * 1.0001 || thin) {
+            *why = "level window exceeds the L2 budget";
+            p.rejected = true;
+            op->plans.push_back(p);
+            return nullptr;
+        }
+    }
+    SlSchedule S;
+    sl_build_schedule(op->h_tiles, tile_at_pos, pmax, lr, k, chunk, p.lead, interleave, sl_team_sizes(resident, k, w0_pct), S);
+    p.teams = S.teams;
+    p.ngroups = S.ngroups;
+    p.grid = (int)S.roles.size();
+    p.count.resize(k);
+    p.ntl.resize(k);
+    size_t nitems = 0, nlt = 0;
+    for (int l = 0; l < k; l++) {
+        p.count[l] = (int)S.items[l].size();
+        p.ntl[l] = (int)S.ltile[l].size();
+        nitems += S.items[l].size();
+        nlt += S.ltile[l].size();
+    }
+    bool identity = S.same_lists && p.ntl[0] == ntiles;
+    for (int t = 0; t < ntiles && identity; t++) identity = S.ltile[0][t] == t;
+    if (cudaMalloc(&p.d_roles, sizeof(int2) * S.roles.size()) != cudaSuccess ||
+        cudaMalloc(&p.d_item_buf, sizeof(SlItem) * (nitems + 1)) != cudaSuccess ||
+        cudaMalloc(&p.d_counters, sizeof(int) * (size_t)k * S.ngroups) != cudaSuccess ||
+        cudaMalloc(&p.d_group_size, sizeof(int) * (size_t)k * S.ngroups) != cudaSuccess ||
+        (!identity && cudaMalloc(&p.d_ltile_buf, sizeof(SlTile) * (nlt + 1)) != cudaSuccess)) {
+        *why = "plan allocation failed";
+        cudaGetLastError();
+        return nullptr;
+    }
+    p.d_items.resize(k);
+    p.d_ltiles.resize(k);
+    size_t io = 0, lo = 0;
+    std::vector<SlTile> lt;
+    for (int l = 0; l < k; l++) {
+        p.d_items[l] = p.d_item_buf + io;
+        if (!S.items[l].empty())
+            cudaMemcpy(p.d_item_buf + io, S.items[l].data(), sizeof(SlItem) * S.items[l].size(), cudaMemcpyHostToDevice);
+        io += S.items[l].size();
+        if (identity) {
+            p.d_ltiles[l] = op->d_tiles;
+        } else {
+            lt.resize(S.ltile[l].size());
+            for (size_t u = 0; u < lt.size(); u++) lt[u] = op->h_tiles[(size_t)S.ltile[l][u]];
+            p.d_ltiles[l] = p.d_ltile_buf + lo;
+            if (!lt.empty()) cudaMemcpy(p.d_ltile_buf + lo, lt.data(), sizeof(SlTile) * lt.size(), cudaMemcpyHostToDevice);
+            lo += lt.size();
+        }
+    }
+    cudaMemset(p.d_counters, 0, sizeof(int) * (size_t)k * S.ngroups);
+    cudaMemcpy(p.d_group_size, S.gsize.data(), sizeof(int) * S.gsize.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(p.d_roles, S.roles.data(), sizeof(int2) * S.roles.size(), cudaMemcpyHostToDevice);
+    op->plans.push_back(p);
+    return &op->plans.back();
+}
+
+static int sl_run(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, const double *d_x2, double *const *d_levels2,
+                  nsk_mode mode, const int *level_rows, const double *dot_w, int dot_slot)
+{
+    nsk_ctx_t ctx = A->ctx;
+    const int nv = d_x2 ? 2 : 1;
+    SellOp *op = sl_get(A);
+    if (!op->ok) { nsk_set_error(ctx, "sliced-ELL path not applicable: %s", op->why.c_str()); return NSK_ERR_UNSUPPORTED; }
+    if (*op->h_error) {
+        nsk_set_error(ctx, "fused matrix-powers kernel: a bounded wait expired in an earlier launch (results invalid)");
+        return NSK_ERR_CUDA;
+    }
+    const int geom = sl_geom(A, op);
+    sl_fn fn = sl_lookup(geom, mode == NSK_EXACT_MULADD, nv);
+    int per_sm = 0;
+    NSK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, SL_THREADS, 0));
+    if (ctx->opt.sell_ctas_per_sm > 0) per_sm = std::min(per_sm, (int)ctx->opt.sell_ctas_per_sm);
+    const int resident = ctx->prop.multiProcessorCount * per_sm;
+    if (resident < k) { nsk_set_error(ctx, "sliced-ELL path: fewer resident CTAs than levels"); return NSK_ERR_UNSUPPORTED; }
+    const char *why = "";
+    SlPlan *plan = sl_plan(A, op, k, level_rows, resident, nv, &why);
+    if (!plan) { nsk_set_error(ctx, "fused matrix powers not applicable: %s", why); return NSK_ERR_UNSUPPORTED; }
+    int maxcount = 0;
+    for (int l = 0; l < k; l++) maxcount = std::max(maxcount, plan->count[l]);
+    if (maxcount == 0) return NSK_OK;
+    if (dot_w) NSK_REQUIRE(ctx, k == 1 && plan->grid <= NSK_MAX_PARTIALS, "fused dot: k = 1 and a bounded grid");
+    if (plan->epoch >= 100000000) {  // counters are monotone over launches: start over long before they overflow
+        NSK_CUDA(ctx, cudaMemsetAsync(plan->d_counters, 0, sizeof(int) * (size_t)k * plan->ngroups, ctx->stream));
+        plan->epoch = 0;
+    }
+    plan->epoch++;
+    SlParams P;
+    memset(&P, 0, sizeof(P));
+    for (int l = 0; l < k; l++) {
+        P.items[l] = plan->d_items[l];
+        P.ltiles[l] = plan->d_ltiles[l];
+        P.count[l] = plan->count[l];
+        P.ntl[l] = plan->ntl[l];
+        P.team[l] = plan->teams[l];
+        P.level_rows[l] = plan->level_rows[l];
+        P.levels[l] = d_levels[l];
+        P.levels2[l] = d_levels2 ? d_levels2[l] : nullptr;
+    }
+    P.x = d_x;
+    P.x2 = d_x2;
+    P.blobs = op->d_blobs;
+    P.counters = plan->d_counters;
+    P.group_size = plan->d_group_size;
+    P.cta_role = plan->d_roles;
+    P.ngroups = plan->ngroups;
+    P.n_cols = A->n_cols;
+    P.k = k;
+    P.chunk = plan->chunk;
+    P.epoch = plan->epoch;
+    P.bp_level = k > 1 ? k - 1 : -1;
+    P.flags = ctx->opt.sell_flags >= 0 ? (int)ctx->opt.sell_flags : 3;
+    P.pf_dist = ctx->opt.sell_pf_dist > 0 ? (int)ctx->opt.sell_pf_dist : 2;
+    P.error = op->d_error;
+    P.dot_w = dot_w;
+    P.partials = ctx->d_partials;
+    P.ticket = ctx->d_ticket;
+    P.dot_out = dot_w ? ctx->d_scalars + dot_slot : nullptr;
+    if (k > 1) {
+        // CTAs of different levels wait on each other: co-residency must be guaranteed, not assumed
+        void *args[] = {&P};
+        cudaError_t e = cudaLaunchCooperativeKernel((const void *)fn, dim3(plan->grid), dim3(SL_THREADS), args, 0, ctx->stream);
+        if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported) {
+            cudaGetLastError();
+            plan->epoch--;
+            nsk_set_error(ctx, "fused matrix powers: the grid cannot be made co-resident on this device now");
+            return NSK_ERR_UNSUPPORTED;
+        }
+        NSK_CUDA(ctx, e);
+    } else {
+        fn<<<plan->grid, SL_THREADS, 0, ctx->stream>>>(P);
+        NSK_CUDA(ctx, cudaGetLastError());
+    }
+    ctx->launches++;
+    return NSK_OK;
+}
+
+int nsk_sell_run(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode, const int *level_rows,
+                 const double *dot_w, int dot_slot)
+{
+    return sl_run(A, k, d_x, d_levels, nullptr, nullptr, mode, level_rows, dot_w, dot_slot);
+}
+
+int nsk_sell_run2(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, const double *d_x2, double *const *d_levels2,
+                  nsk_mode mode, const int *level_rows)
+{
+    return sl_run(A, k, d_x, d_levels, d_x2, d_levels2, mode, level_rows, nullptr, -1);
+}
+
+bool nsk_sell_applicable(nsk_csr_t A)
+{
+    if (A->n == 0 || A->nnz == 0) return false;
+    return sl_get(A)->ok;
+}
+
+// 1 when the watchdog flag of the operator's fused kernel is set (a bounded wait expired); clears it.
+int nsk_sell_check_error(nsk_csr_t A)
+{
+    std::lock_guard<std::mutex> lk(g_sell_mu);
+    auto it = g_sell.find(A);
+    if (it == g_sell.end() || !it->second->h_error) return 0;
+    const int e = *it->second->h_error;
+    *it->second->h_error = 0;
+    return e;
+}
+
+size_t nsk_sell_bytes(nsk_csr_t A)
+{
+    SellOp *op = sl_get(A);
+    return op->ok ? op->blob_bytes + sizeof(SlTile) * (size_t)op->ntiles : 0;
+}
