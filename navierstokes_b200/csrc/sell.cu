@@ -47,11 +47,12 @@ using namespace nskptx;
 
 std::vector<int> &nsk_csr_host_ptrow(nsk_csr_t A);
 
-constexpr int SL_ROWS = 256;      // rows per tile = consumer threads per CTA
-constexpr int SL_NCW = SL_ROWS / 32;
-constexpr int SL_THREADS = SL_ROWS + 64;  // + dependency warp + publisher warp
+constexpr int SL_ROWS = 256;      // rows per tile
+constexpr int SL_CTHREADS = 128;  // consumer threads per CTA (one warpgroup): thread t owns rows t and t + 128 of a tile
+constexpr int SL_NCW = SL_CTHREADS / 32;
+constexpr int SL_THREADS = 256;   // + the helper warpgroup (dependency warp, publisher warp, two idle warps)
 constexpr int SL_PSLOTS = 8;      // pattern format: at most 8 slots per row
-constexpr int SL_MAXCHUNK = 8;    // tiles per item (consecutive tiles taken by one CTA in one go)
+constexpr int SL_MAXCHUNK = 4;    // tiles per item (consecutive tiles taken by one CTA in one go)
 constexpr int SL_RING = 4;        // items the dependency warp may run ahead of the slowest consumer warp
 
 enum { SL_FMT_PATTERN = 0, SL_FMT_EXPLICIT = 1 };
@@ -95,6 +96,7 @@ struct SlParams {
     int ngroups, n_cols, k, chunk;
     int epoch;               // an item group is complete when counter >= epoch * group size
     int bp_level;            // the level whose progress holds level 0 back (k - 1), -1: no back-pressure
+    int muladd;              // 1: NSK_EXACT_MULADD (product and sum rounded separately), 0: fma
     int flags;               // 1: evict-first / streaming hints for data nobody re-reads; 2: L2 prefetch of level 0's blobs;
                              // 4: inner levels load tiles with L1 allocation; 8: ... with an evict-last L2 policy
     int pf_dist;             // items ahead the L2 prefetch runs
@@ -121,42 +123,26 @@ __device__ __forceinline__ unsigned long long sl_now()
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
-// coefficient / column stream (read-only path).  CH selects the cache handling:
-//   SL_CH_NA      no L1 allocation (L1 is for x)
-//   SL_CH_ALLOC   plain read-only load
-//   SL_CH_KEEP    no L1 allocation, evict-last in L2 (window data: the next levels re-read it)
-//   SL_CH_DROP    no L1 allocation, evict-first in L2 (the last level is the last reader of a tile in a launch)
-enum { SL_CH_NA = 0, SL_CH_ALLOC = 1, SL_CH_KEEP = 2, SL_CH_DROP = 3 };
-template <int CH>
-__device__ __forceinline__ uint64_t sl_policy()
+// L2 eviction priority of the coefficient / column stream: normal for tiles the next levels re-read, evict-first when
+// this level is the last reader of a tile in the launch.  (Measured on 256^3, k = 4: loads marked L1::no_allocate are
+// dropped from L2 first as well -- 3.6 GB of HBM reads instead of 1.6 -- so the stream allocates in L1 like any load.)
+__device__ __forceinline__ uint64_t sl_policy(bool evict_first)
 {
-    uint64_t pol = 0;  // (the eviction-priority qualifier without a policy operand exists for 256-bit loads only)
-    if (CH == SL_CH_KEEP) asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    if (CH == SL_CH_DROP) asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    uint64_t pol;
+    if (evict_first) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
-template <int CH>
-__device__ __forceinline__ double sl_ld_coef(const double *p)
+__device__ __forceinline__ double sl_ld_coef(const double *p, uint64_t pol)
 {
     double v;
-    if (CH == SL_CH_KEEP || CH == SL_CH_DROP)
-        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(sl_policy<CH>()));
-    else if (CH == SL_CH_ALLOC)
-        asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
-    else
-        asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
     return v;
 }
-template <int CH>
-__device__ __forceinline__ int sl_ld_col(const int *p)
+__device__ __forceinline__ int sl_ld_col(const int *p, uint64_t pol)
 {
     int v;
-    if (CH == SL_CH_KEEP || CH == SL_CH_DROP)
-        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(sl_policy<CH>()));
-    else if (CH == SL_CH_ALLOC)
-        asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
-    else
-        asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
     return v;
 }
 // x: ordinary cached load (L1 + L2).  Written as asm so that it can neither become a read-only-path load (the level
@@ -171,6 +157,12 @@ __device__ __forceinline__ void sl_prefetch_l2(const void *p, uint32_t bytes)
 {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
+// Register re-allocation between the warpgroups of a CTA (sm_90a+): the helper warpgroup hands its registers to the
+// consumers, which keep the loads of several rows per thread in flight.
+template <int N>
+__device__ __forceinline__ void sl_reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void sl_reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 
 constexpr unsigned long long SL_TIMEOUT_NS = 4000000000ull;  // bounded waits: 4 s, then the error flag
 
@@ -197,343 +189,393 @@ __device__ __forceinline__ int sl_wait_groups(const int *cnt, const int *need, i
     return w;
 }
 
-// How a consumer treats data nobody re-reads in this launch: SL_MID = an inner level; SL_LAST = the last level (tiles
-// loaded evict-first, results stored streaming); SL_LAST_DOT = the single product with CG's fused dot <w, y>.
-enum { SL_MID = 0, SL_LAST = 1, SL_LAST_DOT = 2, SL_MID_ALLOC = 3, SL_MID_KEEP = 4, SL_LAST_PLAIN = 5 };
-__host__ __device__ constexpr bool sl_is_last(int lm) { return lm == SL_LAST || lm == SL_LAST_DOT; }
-__host__ __device__ constexpr int sl_ch(int lm)
-{
-    return sl_is_last(lm) ? SL_CH_DROP : lm == SL_MID_ALLOC ? SL_CH_ALLOC : lm == SL_MID_KEEP ? SL_CH_KEEP : SL_CH_NA;
-}
+// What the consumers of a CTA need once per item, kept in shared memory (read back by broadcast LDS).
+struct SlCta {
+    const double *src[2];
+    double *dst[2];
+    int row_end, last, muladd, pad;
+};
 
-template <int NV, int LM>
-__device__ __forceinline__ void sl_store_row(const SlParams &P, double *const *s_dst, int row, double acc0, double acc1,
-                                             double &dot_acc)
+template <int NV>
+__device__ __forceinline__ void sl_store_row(const SlParams &P, const SlCta &C, int row, double acc0, double acc1, double &dot_acc)
 {
-    double *dst = s_dst[0];
-    if (sl_is_last(LM)) __stcs(dst + row, acc0);
+    double *dst = C.dst[0];
+    if (C.last) __stcs(dst + row, acc0);  // nobody in this launch re-reads the last level
     else dst[row] = acc0;
     if (NV == 2) {
-        double *dst2 = s_dst[1];
-        if (sl_is_last(LM)) __stcs(dst2 + row, acc1);
+        double *dst2 = C.dst[1];
+        if (C.last) __stcs(dst2 + row, acc1);
         else dst2[row] = acc1;
     }
-    if (LM == SL_LAST_DOT) dot_acc = __fma_rn(P.dot_w[row], acc0, dot_acc);
+    if (NV == 1 && P.dot_w) dot_acc = __fma_rn(P.dot_w[row], acc0, dot_acc);
 }
 
-// One tile, format P, W slots: every load of the row is issued before the first link of its chain.  d = the tile's
-// descriptor in shared memory, m = the row's slot mask (staged by the dependency warp).  All loads are unconditional so
-// that every destination register is defined exactly once (a predicated load would keep its old value alive across the
-// whole sequence): a slot the row lacks reads the row's own x entry instead, and is not used.
-template <int NV, bool MULADD, int LM, int W>
-__device__ __forceinline__ void sl_tile_pattern_w(const int *d, unsigned int m, const SlParams &P, const double *const *s_src,
-                                                  double *const *s_dst, int row_end, int r, double &dot_acc)
+// T pattern tiles of W slots at once: thread t owns rows t and t + 128 of every tile, i.e. 2 T rows, and issues ALL their
+// loads (W coefficients + W x entries each) before the first link of any chain -- one memory round trip per item, with
+// 2 T W (NV + 1) loads in flight per thread.  d = the item's tile descriptors in shared memory (the tiles share one
+// pattern), msk = the rows' slot masks (staged by the dependency warp).  Every load is unconditional so that every
+// destination register is defined exactly once: a slot the row lacks reads the row's own x entry and is not used.
+template <int NV, int W, int T>
+__device__ __forceinline__ void sl_rows_pattern(const int *d, const unsigned char (*msk)[SL_ROWS], const SlParams &P, const SlCta &C,
+                                                int t, uint64_t pol, double &dot_acc)
 {
-    const long long off = ((long long)(unsigned int)d[0]) | ((long long)d[1] << 32);
-    const int row = d[2] + r;
-    const double *val = reinterpret_cast<const double *>(P.blobs + off + SL_ROWS) + r;
-    const int rowc = min(row, P.n_cols - 1);  // padding rows of the last tile stay inside x
-    const double *src = s_src[0];
-    const double *src2 = NV == 2 ? s_src[1] : nullptr;
-    double a[W > 0 ? W : 1], xv[NV][W > 0 ? W : 1];
+    constexpr int WW = W > 0 ? W : 1;
+    const int4 r0 = *reinterpret_cast<const int4 *>(d + 8), r1 = *reinterpret_cast<const int4 *>(d + 12);
+    const int rel[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+    const double *src = C.src[0];
+    const double *src2 = NV == 2 ? C.src[1] : nullptr;
+    const int cmax = P.n_cols - 1;
+    double a[T][2][WW], xv[NV][T][2][WW];
+    unsigned int m[T][2];
+    int row[T][2];
+    bool live[T][2];
 #pragma unroll
-    for (int e = 0; e < W; e++) {
-        a[e] = sl_ld_coef<sl_ch(LM)>(val + e * SL_ROWS);
-        const int idx = rowc + (d[8 + e] & -(int)((m >> e) & 1u));
-        xv[0][e] = sl_ld_x(src + idx);
-        if (NV == 2) xv[NV - 1][e] = sl_ld_x(src2 + idx);
-    }
-    double acc0 = 0.0, acc1 = 0.0;
+    for (int j = 0; j < T; j++) {
+        const int4 q = *reinterpret_cast<const int4 *>(d + 16 * j);  // off lo, off hi, row0, nrows
+        const long long off = ((long long)(unsigned int)q.x) | ((long long)q.y << 32);
 #pragma unroll
-    for (int e = 0; e < W; e++)
-        if (m & (1u << e)) {
-            acc0 = row_op<MULADD>(a[e], xv[0][e], acc0);
-            if (NV == 2) acc1 = row_op<MULADD>(a[e], xv[NV - 1][e], acc1);
+        for (int h = 0; h < 2; h++) {
+            const int r = t + SL_CTHREADS * h;
+            m[j][h] = msk[j][r];
+            row[j][h] = q.z + r;
+            live[j][h] = r < q.w && row[j][h] < C.row_end;
+            const double *val = reinterpret_cast<const double *>(P.blobs + off + SL_ROWS) + r;
+            const int rowc = min(row[j][h], cmax);  // padding rows of a short tile stay inside x
+#pragma unroll
+            for (int e = 0; e < W; e++) {
+                a[j][h][e] = sl_ld_coef(val + e * SL_ROWS, pol);
+                const int idx = rowc + (rel[e] & -(int)((m[j][h] >> e) & 1u));
+                xv[0][j][h][e] = sl_ld_x(src + idx);
+                if (NV == 2) xv[NV - 1][j][h][e] = sl_ld_x(src2 + idx);
+            }
         }
-    if (r < d[3] && row < row_end) sl_store_row<NV, LM>(P, s_dst, row, acc0, acc1, dot_acc);
+    }
+    double acc0[T][2], acc1[T][2];
+    if (C.muladd) {
+#pragma unroll
+        for (int j = 0; j < T; j++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                acc0[j][h] = 0.0;
+                acc1[j][h] = 0.0;
+#pragma unroll
+                for (int e = 0; e < W; e++)
+                    if (m[j][h] & (1u << e)) {
+                        acc0[j][h] = row_op<true>(a[j][h][e], xv[0][j][h][e], acc0[j][h]);
+                        if (NV == 2) acc1[j][h] = row_op<true>(a[j][h][e], xv[NV - 1][j][h][e], acc1[j][h]);
+                    }
+            }
+    } else {
+#pragma unroll
+        for (int j = 0; j < T; j++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                acc0[j][h] = 0.0;
+                acc1[j][h] = 0.0;
+#pragma unroll
+                for (int e = 0; e < W; e++)
+                    if (m[j][h] & (1u << e)) {
+                        acc0[j][h] = row_op<false>(a[j][h][e], xv[0][j][h][e], acc0[j][h]);
+                        if (NV == 2) acc1[j][h] = row_op<false>(a[j][h][e], xv[NV - 1][j][h][e], acc1[j][h]);
+                    }
+            }
+    }
+#pragma unroll
+    for (int j = 0; j < T; j++)
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+            if (live[j][h]) sl_store_row<NV>(P, C, row[j][h], acc0[j][h], acc1[j][h], dot_acc);
 }
 
-template <int NV, bool MULADD, int LM>
-__device__ __forceinline__ void sl_tile_pattern(const int *d, unsigned int m, const SlParams &P, const double *const *s_src,
-                                                double *const *s_dst, int row_end, int r, double &dot_acc)
+template <int NV, int T>
+__device__ __forceinline__ void sl_rows_pattern_any(int width, const int *d, const unsigned char (*msk)[SL_ROWS], const SlParams &P,
+                                                    const SlCta &C, int t, uint64_t pol, double &dot_acc)
 {
-    switch (d[4]) {  // uniform: one instance per width, no per-slot bounds checks
-    case 0: sl_tile_pattern_w<NV, MULADD, LM, 0>(d, m, P, s_src, s_dst, row_end, r, dot_acc); break;
-    case 1: sl_tile_pattern_w<NV, MULADD, LM, 1>(d, m, P, s_src, s_dst, row_end, r, dot_acc); break;
-    case 2: sl_tile_pattern_w<NV, MULADD, LM, 2>(d, m, P, s_src, s_dst, row_end, r, dot_acc); break;
-    case 3: sl_tile_pattern_w<NV, MULADD, LM, 3>(d, m, P, s_src, s_dst, row_end, r, dot_acc); break;
-    case 4: sl_tile_pattern_w<NV, MULADD, LM, 4>(d, m, P, s_src, s_dst, row_end, r, dot_acc); break;
-    case 5: sl_tile_pattern_w<NV, MULADD, LM, 5>(d, m, P, s_src, s_dst, row_end, r, dot_acc); break;
-    case 6: sl_tile_pattern_w<NV, MULADD, LM, 6>(d, m, P, s_src, s_dst, row_end, r, dot_acc); break;
-    case 7: sl_tile_pattern_w<NV, MULADD, LM, 7>(d, m, P, s_src, s_dst, row_end, r, dot_acc); break;
-    default: sl_tile_pattern_w<NV, MULADD, LM, 8>(d, m, P, s_src, s_dst, row_end, r, dot_acc); break;
+    switch (width) {  // uniform: one straight-line instance per width
+    case 0: sl_rows_pattern<NV, 0, T>(d, msk, P, C, t, pol, dot_acc); break;
+    case 1: sl_rows_pattern<NV, 1, T>(d, msk, P, C, t, pol, dot_acc); break;
+    case 2: sl_rows_pattern<NV, 2, T>(d, msk, P, C, t, pol, dot_acc); break;
+    case 3: sl_rows_pattern<NV, 3, T>(d, msk, P, C, t, pol, dot_acc); break;
+    case 4: sl_rows_pattern<NV, 4, T>(d, msk, P, C, t, pol, dot_acc); break;
+    case 5: sl_rows_pattern<NV, 5, T>(d, msk, P, C, t, pol, dot_acc); break;
+    case 6: sl_rows_pattern<NV, 6, T>(d, msk, P, C, t, pol, dot_acc); break;
+    case 7: sl_rows_pattern<NV, 7, T>(d, msk, P, C, t, pol, dot_acc); break;
+    default:  // 8 slots: the widest pattern keeps one tile less in flight (registers)
+        if (T >= 2 && (NV == 2 || T >= 3)) {
+            sl_rows_pattern<NV, 8, (T > 1 ? T - 1 : 1)>(d, msk, P, C, t, pol, dot_acc);
+            sl_rows_pattern<NV, 8, 1>(d + 16 * (T - 1), msk + (T - 1), P, C, t, pol, dot_acc);
+        } else {
+            sl_rows_pattern<NV, 8, T>(d, msk, P, C, t, pol, dot_acc);
+        }
+        break;
     }
 }
 
-// One tile, format E: EB entries of the row in flight per round trip (columns and coefficients, then the gathers).
-template <int NV, bool MULADD, int LM, int EB>
-__device__ __forceinline__ void sl_tile_explicit(const int *d, const SlParams &P, const double *const *s_src, double *const *s_dst,
-                                                 int row_end, int r, double &dot_acc)
+// One tile, format E (explicit 32-bit columns, per-slice widths): thread t owns rows t and t + 128; EB entries of both
+// rows per round trip (columns and coefficients, then the gathers).
+template <int NV, int EB>
+__device__ __forceinline__ void sl_tile_explicit(const int *d, const SlParams &P, const SlCta &C, int t, uint64_t pol, double &dot_acc)
 {
-    const double *src = s_src[0];
-    const double *src2 = NV == 2 ? s_src[1] : nullptr;
+    const double *src = C.src[0];
+    const double *src2 = NV == 2 ? C.src[1] : nullptr;
     const long long off = ((long long)(unsigned int)d[0]) | ((long long)d[1] << 32);
     const int row0 = d[2], nrows = d[3], rp = d[6];
     const unsigned char *blob = P.blobs + off;
-    const int slice = r >> 5, lane = r & 31;
-    int soff = 0, tot = 0;
+    const int lane = t & 31, w = t >> 5;  // rows t and t + 128 lie in slices w and w + 4
+    int soff[2] = {0, 0}, tot = 0;
 #pragma unroll
     for (int s = 0; s < 8; s++) {
-        const int w = d[8 + s];
-        if (s < slice) soff += w;
-        tot += w;
+        const int ws = d[8 + s];
+        if (s < w) soff[0] += ws;
+        if (s < w + 4) soff[1] += ws;
+        tot += ws;
     }
-    const int mine = d[8 + slice];
-    const int len = (int)__ldg(reinterpret_cast<const unsigned short *>(blob) + r);
-    const int *col = reinterpret_cast<const int *>(blob + sl_round_up(2 * rp, 128)) + (size_t)soff * 32 + lane;
-    const double *val = reinterpret_cast<const double *>(blob + sl_round_up(2 * rp, 128) + sl_round_up(128 * tot, 128)) + (size_t)soff * 32 + lane;
-    const int row = row0 + r;
-    double acc0 = 0.0, acc1 = 0.0;
-    for (int e0 = 0; e0 < mine; e0 += EB) {
-        int cc[EB];
-        double a[EB], xv[NV][EB];
-        // every load unconditional (each destination register defined once): a batch that runs past the slice's last
-        // slot re-reads that slot; padding entries carry a valid column (0); neither is used
+    const unsigned char *colbase = blob + sl_round_up(2 * rp, 128);
+    const unsigned char *valbase = colbase + sl_round_up(128 * tot, 128);
 #pragma unroll
-        for (int u = 0; u < EB; u++) {
-            const int e = min(e0 + u, mine - 1);
-            cc[u] = sl_ld_col<sl_ch(LM)>(col + (size_t)e * 32);
-            a[u] = sl_ld_coef<sl_ch(LM)>(val + (size_t)e * 32);
-        }
+    for (int h = 0; h < 2; h++) {
+        const int r = t + SL_CTHREADS * h;
+        if ((r & ~31) >= rp) continue;  // the tile has no slice for this warp's second row
+        const int mine = d[8 + w + 4 * h];
+        const int len = (int)__ldg(reinterpret_cast<const unsigned short *>(blob) + r);
+        const int *col = reinterpret_cast<const int *>(colbase) + (size_t)soff[h] * 32 + lane;
+        const double *val = reinterpret_cast<const double *>(valbase) + (size_t)soff[h] * 32 + lane;
+        double acc0 = 0.0, acc1 = 0.0;
+        for (int e0 = 0; e0 < mine; e0 += EB) {
+            int cc[EB];
+            double a[EB], xv[NV][EB];
+            // every load unconditional (each destination register defined once): a batch that runs past the slice's
+            // last slot re-reads that slot; padding entries carry a valid column (0); neither is used
 #pragma unroll
-        for (int u = 0; u < EB; u++) {
-            xv[0][u] = sl_ld_x(src + cc[u]);
-            if (NV == 2) xv[NV - 1][u] = sl_ld_x(src2 + cc[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < EB; u++)
-            if (e0 + u < len) {
-                acc0 = row_op<MULADD>(a[u], xv[0][u], acc0);
-                if (NV == 2) acc1 = row_op<MULADD>(a[u], xv[NV - 1][u], acc1);
+            for (int u = 0; u < EB; u++) {
+                const int e = min(e0 + u, mine - 1);
+                cc[u] = sl_ld_col(col + (size_t)e * 32, pol);
+                a[u] = sl_ld_coef(val + (size_t)e * 32, pol);
             }
-    }
-    if (r < nrows && row < row_end) sl_store_row<NV, LM>(P, s_dst, row, acc0, acc1, dot_acc);
-}
-
-// The consumer warps' loop: warp w owns slice w (rows 32 w .. 32 w + 31) of every tile of the CTA's items.
-template <int NV, bool MULADD, int EB, int LM>
-__device__ __forceinline__ double sl_consume(const SlParams &P, int n_my, uint64_t *s_ready, unsigned int *s_fin, const int *s_ntile,
-                                             const int (*s_desc)[SL_MAXCHUNK * 16],
-                                             const unsigned char (*s_mask)[SL_MAXCHUNK][SL_ROWS], const double *const *s_src,
-                                             double *const *s_dst, const int *s_row_end)
-{
-    const int tid = threadIdx.x;
-    double dot_acc = 0.0;
-    for (int it = 0; it < n_my; ++it) {
-        const int s = it % SL_RING;
-        mbar_wait(&s_ready[s], (it / SL_RING) & 1);
-        const int ntile = s_ntile[s];
-        for (int j = 0; j < ntile; j++) {
-            const int *d = s_desc[s] + 16 * j;
-            if ((tid & ~31) >= d[6]) continue;  // the tile has no slice for this warp
-            if (d[5] == SL_FMT_PATTERN)
-                sl_tile_pattern<NV, MULADD, LM>(d, (unsigned int)s_mask[s][j][tid], P, s_src, s_dst, *s_row_end, tid, dot_acc);
-            else
-                sl_tile_explicit<NV, MULADD, LM, EB>(d, P, s_src, s_dst, *s_row_end, tid, dot_acc);
+#pragma unroll
+            for (int u = 0; u < EB; u++) {
+                xv[0][u] = sl_ld_x(src + cc[u]);
+                if (NV == 2) xv[NV - 1][u] = sl_ld_x(src2 + cc[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < EB; u++)
+                if (e0 + u < len) {
+                    if (C.muladd) {
+                        acc0 = row_op<true>(a[u], xv[0][u], acc0);
+                        if (NV == 2) acc1 = row_op<true>(a[u], xv[NV - 1][u], acc1);
+                    } else {
+                        acc0 = row_op<false>(a[u], xv[0][u], acc0);
+                        if (NV == 2) acc1 = row_op<false>(a[u], xv[NV - 1][u], acc1);
+                    }
+                }
         }
-        __syncwarp();
-        if ((tid & 31) == 0) red_release_cta_shared_add(&s_fin[s], 1u);  // the slot may be reused and the item published
+        const int row = row0 + r;
+        if (r < nrows && row < C.row_end) sl_store_row<NV>(P, C, row, acc0, acc1, dot_acc);
     }
-    return dot_acc;
 }
 
-template <int NV, bool MULADD, int EB, int MINB>
-__global__ void __launch_bounds__(SL_THREADS, MINB) sell_kernel(const SlParams P)
+// CTA = two warpgroups.  Warps 0..3: consumers (rows t and t + 128 of every tile; most of the CTA's registers).
+// Warp 4: dependency warp.  Warp 5: publisher.  Warps 6, 7 only give their registers away.
+template <int NV, int T>
+__global__ void __launch_bounds__(SL_THREADS, 2) sell_kernel(const SlParams P)
 {
     static_assert(NV == 1 || NV == 2, "one or two right-hand sides");
-    __shared__ __align__(16) int s_desc[SL_RING][SL_MAXCHUNK * 16];  // tile descriptors of the items in flight
+    static_assert(T >= 1 && T <= SL_MAXCHUNK, "tiles per item");
+    __shared__ __align__(16) int s_desc[SL_RING][SL_MAXCHUNK * 16];               // tile descriptors of the items in flight
     __shared__ __align__(8) unsigned char s_mask[SL_RING][SL_MAXCHUNK][SL_ROWS];  // format P: the rows' slot masks
-    __shared__ int s_ntile[SL_RING];
+    __shared__ int s_hdr[SL_RING][2];         // tiles in the item; their common width when they share one pattern, else -1
     __shared__ uint64_t s_ready[SL_RING];     // item's inputs complete + descriptors in place (dependency warp arrives)
     __shared__ unsigned int s_fin[SL_RING];   // consumer warps that finished the slot's item, counted over the whole launch
     __shared__ double s_red[SL_NCW];
-    // per-CTA constants the consumers need once per tile: kept out of their registers (read back by broadcast LDS)
-    __shared__ const double *s_src[2];
-    __shared__ double *s_dst[2];
-    __shared__ int s_row_end;
+    __shared__ SlCta s_cta;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
-    if (tid == 0) {
-        for (int s = 0; s < SL_RING; s++) {
-            mbar_init(&s_ready[s], 1);
-            s_fin[s] = 0u;
-        }
-        fence_mbar_init();
-    }
-
     const int2 role = __ldg(P.cta_role + blockIdx.x);
     const int level = role.x;
     const int c = role.y;
     const int G = P.team[level];
     const int count = P.count[level];
     const int n_my = c < count ? (count - c + G - 1) / G : 0;
-    const int M = P.chunk;
     if (tid == 0) {
-        s_src[0] = level == 0 ? P.x : P.levels[level - 1];
-        s_src[1] = NV == 2 ? (level == 0 ? P.x2 : P.levels2[level - 1]) : nullptr;
-        s_dst[0] = P.levels[level];
-        s_dst[1] = NV == 2 ? P.levels2[level] : nullptr;
-        s_row_end = P.level_rows[level];
+        for (int s = 0; s < SL_RING; s++) {
+            mbar_init(&s_ready[s], 1);
+            s_fin[s] = 0u;
+        }
+        fence_mbar_init();
+        s_cta.src[0] = level == 0 ? P.x : P.levels[level - 1];
+        s_cta.src[1] = NV == 2 ? (level == 0 ? P.x2 : P.levels2[level - 1]) : nullptr;
+        s_cta.dst[0] = P.levels[level];
+        s_cta.dst[1] = NV == 2 ? P.levels2[level] : nullptr;
+        s_cta.row_end = P.level_rows[level];
+        s_cta.last = ((P.flags & 1) && level == P.k - 1) ? 1 : 0;
+        s_cta.muladd = P.muladd;
     }
     __syncthreads();
 
-    if (warp == SL_NCW) {
-        // ===== dependency warp: per item, in order -- (1) fetch the tile descriptors into registers, (2) wait until the
-        // level below has completed the groups the item reads and the level that holds this one back has advanced,
-        // (3) wait for the ring slot (the item four back is finished by every consumer warp), (4) hand over. =====
-        const int ntl = P.ntl[level];
-        const int *itw = reinterpret_cast<const int *>(P.items[level]);
-        const int4 *tl4 = reinterpret_cast<const int4 *>(P.ltiles[level]);
-        const bool fwd = level > 0;
-        const bool back = level == 0 && P.bp_level > 0;
-        const int *cnt_f = P.counters + (size_t)(fwd ? level - 1 : 0) * P.ngroups;
-        const int *need_f = P.group_size + (size_t)(fwd ? level - 1 : 0) * P.ngroups;
-        const int *cnt_b = P.counters + (size_t)(back ? P.bp_level : 0) * P.ngroups;
-        const int *need_b = P.group_size + (size_t)(back ? P.bp_level : 0) * P.ngroups;
-        const bool prefetch = (P.flags & 2) && level == 0 && P.pf_dist > 0;
-        int wf = 0, wb = 0;
-        bool broken = false;
-        for (int it = 0; it < n_my; ++it) {
-            const long long i = (long long)c + (long long)it * G;
-            const int s = it % SL_RING;
-            // lanes 0..7: the item's words; every lane: descriptor quarter-words lane of tile lane/4 (4 int4 per tile)
-            int iw = 0;
-            if (lane < 8) iw = __ldg(itw + i * 8 + lane);
-            const long long t0 = i * M;
-            const int ntile = (int)min((long long)M, (long long)ntl - t0);
-            int4 dq = make_int4(0, 0, 0, 0);
-            if (lane < 4 * ntile) dq = __ldg(tl4 + t0 * 4 + lane);
-            if (prefetch && it + P.pf_dist < n_my) {
-                // level 0 streams its blobs from HBM: pull a later item's bytes into L2 now
-                const long long ip = (long long)c + (long long)(it + P.pf_dist) * G;
-                int pw = 0;
-                if (lane >= 3 && lane < 6) pw = __ldg(itw + ip * 8 + lane);  // pf_bytes, pf_off lo/hi
-                const int pb = __shfl_sync(0xffffffffu, pw, 3);
-                const unsigned int lo = (unsigned int)__shfl_sync(0xffffffffu, pw, 4);
-                const int hi = __shfl_sync(0xffffffffu, pw, 5);
-                if (lane == 0 && pb > 0) sl_prefetch_l2(P.blobs + (((long long)hi << 32) | lo), (uint32_t)pb);
-            }
-            const int ghi = __shfl_sync(0xffffffffu, iw, 1);
-            const int gback = __shfl_sync(0xffffffffu, iw, 2);
-            if (!broken) {
-                if (back && gback >= wb) wb = sl_wait_groups(cnt_b, need_b, P.epoch, P.ngroups, wb, gback, lane);
-                if (fwd && ghi >= wf && wb >= 0) wf = sl_wait_groups(cnt_f, need_f, P.epoch, P.ngroups, wf, ghi, lane);
-                if (wb < 0 || wf < 0) broken = true;
-            }
-            if (it >= SL_RING && !broken) {
-                const unsigned int need = (unsigned int)SL_NCW * (unsigned int)(it / SL_RING);
-                unsigned long long t1 = 0;
-                while (ld_acquire_cta_shared_u32(&s_fin[s]) < need) {
-                    __nanosleep(20);
-                    const unsigned long long t = sl_now();
-                    if (t1 == 0) t1 = t;
-                    else if (t - t1 > SL_TIMEOUT_NS) { broken = true; break; }
+    if (warp >= SL_NCW) {
+        sl_reg_dec<24>();
+        if (warp == SL_NCW) {
+            // ===== dependency warp: per item, in order -- (1) fetch the tile descriptors into registers, (2) wait until
+            // the level below has completed the groups the item reads and the level that holds this one back has
+            // advanced, (3) wait for the ring slot (the item four back is finished by every consumer warp), (4) stage
+            // descriptors + slot masks and hand over. =====
+            const int M = P.chunk;
+            const int ntl = P.ntl[level];
+            const int *itw = reinterpret_cast<const int *>(P.items[level]);
+            const int4 *tl4 = reinterpret_cast<const int4 *>(P.ltiles[level]);
+            const bool fwd = level > 0;
+            const bool back = level == 0 && P.bp_level > 0;
+            const int *cnt_f = P.counters + (size_t)(fwd ? level - 1 : 0) * P.ngroups;
+            const int *need_f = P.group_size + (size_t)(fwd ? level - 1 : 0) * P.ngroups;
+            const int *cnt_b = P.counters + (size_t)(back ? P.bp_level : 0) * P.ngroups;
+            const int *need_b = P.group_size + (size_t)(back ? P.bp_level : 0) * P.ngroups;
+            const bool prefetch = (P.flags & 2) && level == 0 && P.pf_dist > 0;
+            int wf = 0, wb = 0;
+            bool broken = false;
+            for (int it = 0; it < n_my; ++it) {
+                const long long i = (long long)c + (long long)it * G;
+                const int s = it % SL_RING;
+                // lanes 0..7: the item's words; lane l: descriptor quarter l % 4 of tile l / 4 (4 int4 per tile)
+                int iw = 0;
+                if (lane < 8) iw = __ldg(itw + i * 8 + lane);
+                const long long t0 = i * M;
+                const int ntile = (int)min((long long)M, (long long)ntl - t0);
+                int4 dq = make_int4(0, 0, 0, 0);
+                if (lane < 4 * ntile) dq = __ldg(tl4 + t0 * 4 + lane);
+                if (prefetch && it + P.pf_dist < n_my) {
+                    // level 0 streams its tiles from HBM: pull a later item's bytes into L2 now
+                    const long long ip = (long long)c + (long long)(it + P.pf_dist) * G;
+                    int pw = 0;
+                    if (lane >= 3 && lane < 6) pw = __ldg(itw + ip * 8 + lane);  // pf_bytes, pf_off lo / hi
+                    const int pb = __shfl_sync(0xffffffffu, pw, 3);
+                    const unsigned int lo = (unsigned int)__shfl_sync(0xffffffffu, pw, 4);
+                    const int hi = __shfl_sync(0xffffffffu, pw, 5);
+                    if (lane == 0 && pb > 0) sl_prefetch_l2(P.blobs + (((long long)hi << 32) | lo), (uint32_t)pb);
                 }
-            }
-            if (broken && lane == 0) *P.error = 1;  // keep going without waiting: the launch ends, the host reports it
-            // slot masks of the item's pattern tiles (256 bytes each: 8 per lane); their addresses come from the descriptors
-            uint2 mk[SL_MAXCHUNK];
-#pragma unroll
-            for (int j = 0; j < SL_MAXCHUNK; j++) {
-                mk[j] = make_uint2(0u, 0u);
-                if (j < ntile) {
+                // do the item's tiles share one pattern (format P, same width, same offsets)?
+                bool same = true;
+                {
+                    const int q = lane & 3;
+                    const int rx = __shfl_sync(0xffffffffu, dq.x, q), ry = __shfl_sync(0xffffffffu, dq.y, q);
+                    const int rz = __shfl_sync(0xffffffffu, dq.z, q), rw = __shfl_sync(0xffffffffu, dq.w, q);
+                    if (lane < 4 * ntile) {
+                        if (q == 1) same = dq.x == rx && dq.y == ry && dq.y == SL_FMT_PATTERN;
+                        if (q >= 2) same = dq.x == rx && dq.y == ry && dq.z == rz && dq.w == rw;
+                    }
+                    same = __all_sync(0xffffffffu, same);
+                }
+                const int width0 = __shfl_sync(0xffffffffu, dq.x, 1);
+                const int ghi = __shfl_sync(0xffffffffu, iw, 1);
+                const int gback = __shfl_sync(0xffffffffu, iw, 2);
+                if (!broken) {
+                    if (back && gback >= wb) wb = sl_wait_groups(cnt_b, need_b, P.epoch, P.ngroups, wb, gback, lane);
+                    if (fwd && ghi >= wf && wb >= 0) wf = sl_wait_groups(cnt_f, need_f, P.epoch, P.ngroups, wf, ghi, lane);
+                    if (wb < 0 || wf < 0) broken = true;
+                }
+                if (it >= SL_RING && !broken) {
+                    const unsigned int need = (unsigned int)SL_NCW * (unsigned int)(it / SL_RING);
+                    unsigned long long t1 = 0;
+                    while (ld_acquire_cta_shared_u32(&s_fin[s]) < need) {
+                        __nanosleep(20);
+                        const unsigned long long t = sl_now();
+                        if (t1 == 0) t1 = t;
+                        else if (t - t1 > SL_TIMEOUT_NS) { broken = true; break; }
+                    }
+                }
+                if (broken && lane == 0) *P.error = 1;  // keep going without waiting: the launch ends, the host reports it
+                // slot masks of the item's pattern tiles (256 bytes each: 8 per lane); their addresses come from the descriptors
+                for (int j = 0; j < ntile; j++) {
                     const unsigned int lo = (unsigned int)__shfl_sync(0xffffffffu, dq.x, 4 * j);
                     const int hi = __shfl_sync(0xffffffffu, dq.y, 4 * j);
                     const int fmt = __shfl_sync(0xffffffffu, dq.y, 4 * j + 1);
-                    if (fmt == SL_FMT_PATTERN)
-                        mk[j] = __ldg(reinterpret_cast<const uint2 *>(P.blobs + (((long long)hi << 32) | lo)) + lane);
+                    uint2 mk = make_uint2(0u, 0u);
+                    if (fmt == SL_FMT_PATTERN) mk = __ldg(reinterpret_cast<const uint2 *>(P.blobs + (((long long)hi << 32) | lo)) + lane);
+                    reinterpret_cast<uint2 *>(s_mask[s][j])[lane] = mk;
                 }
+                if (lane < 4 * SL_MAXCHUNK) reinterpret_cast<int4 *>(s_desc[s])[lane] = dq;
+                if (lane == 0) {
+                    s_hdr[s][0] = ntile;
+                    s_hdr[s][1] = same ? width0 : -1;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_ready[s]);  // release.cta: descriptors + everything acquired above
             }
-#pragma unroll
-            for (int j = 0; j < SL_MAXCHUNK; j++)
-                if (j < ntile) reinterpret_cast<uint2 *>(s_mask[s][j])[lane] = mk[j];
-            reinterpret_cast<int4 *>(s_desc[s])[lane] = dq;
-            if (lane == 0) s_ntile[s] = ntile;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_ready[s]);  // release.cta: descriptors + everything acquired above
+        } else if (warp == SL_NCW + 1 && P.k > 1) {
+            // ===== publisher: one gpu-scope fence for everything found finished at that moment, then one RED per item.
+            // Consumers bump s_fin[slot] with release.cta after their stores; the acquire here + fence + RED is
+            // cumulative over those stores. =====
+            const int *itw = reinterpret_cast<const int *>(P.items[level]);
+            int *cnt = P.counters + (size_t)level * P.ngroups;
+            int grp = 0;  // lane u: group of item it0 + u
+            for (int it = 0; it < n_my;) {
+                const int j = it & 31;
+                if (j == 0) {
+                    grp = 0;
+                    if (it + lane < n_my) grp = __ldg(itw + ((long long)c + (long long)(it + lane) * G) * 8);
+                }
+                int n = 0;
+                unsigned long long t0 = 0;
+                bool broken = false;
+                for (;;) {  // every consecutive finished item (at most to the end of this batch of 32)
+                    const int i2 = it + n;
+                    bool ok = false;
+                    if (i2 < n_my && (n == 0 || (i2 & 31) != 0) && n < SL_RING) {
+                        const unsigned int need = (unsigned int)SL_NCW * (unsigned int)(i2 / SL_RING + 1);
+                        ok = ld_acquire_cta_shared_u32(&s_fin[i2 % SL_RING]) >= need;
+                    }
+                    ok = __shfl_sync(0xffffffffu, (int)ok, 0) != 0;
+                    if (ok) { ++n; continue; }
+                    if (n > 0) break;
+                    __nanosleep(20);
+                    const unsigned long long t = sl_now();
+                    if (t0 == 0) t0 = t;
+                    else if (t - t0 > SL_TIMEOUT_NS) { broken = true; break; }
+                }
+                if (broken) {
+                    if (lane == 0) *P.error = 1;
+                    break;
+                }
+                if (lane == 0) __threadfence();
+                __syncwarp();
+                for (int u = 0; u < n; u++) {
+                    const int g = __shfl_sync(0xffffffffu, grp, (it + u) & 31);
+                    if (lane == 0) red_relaxed_gpu_add(cnt + g, 1);
+                }
+                it += n;
+            }
         }
         return;
     }
 
-    if (warp == SL_NCW + 1) {
-        // ===== publisher (k > 1): one gpu-scope fence for everything found finished at that moment, then one RED per
-        // item.  Consumers bump s_fin[slot] with release.cta after their stores; the acquire here + fence + RED is
-        // cumulative over those stores. =====
-        if (P.k <= 1) return;
-        const int *itw = reinterpret_cast<const int *>(P.items[level]);
-        int *cnt = P.counters + (size_t)level * P.ngroups;
-        int grp = 0;  // lane u: group of item it0 + u
-        for (int it = 0; it < n_my;) {
-            const int j = it & 31;
-            if (j == 0) {
-                grp = 0;
-                if (it + lane < n_my) grp = __ldg(itw + ((long long)c + (long long)(it + lane) * G) * 8);
-            }
-            int n = 0;
-            unsigned long long t0 = 0;
-            bool broken = false;
-            for (;;) {  // every consecutive finished item (at most to the end of this batch of 32)
-                const int i2 = it + n;
-                bool ok = false;
-                if (i2 < n_my && (n == 0 || (i2 & 31) != 0) && n < SL_RING) {
-                    const unsigned int need = (unsigned int)SL_NCW * (unsigned int)(i2 / SL_RING + 1);
-                    ok = ld_acquire_cta_shared_u32(&s_fin[i2 % SL_RING]) >= need;
-                }
-                ok = __shfl_sync(0xffffffffu, (int)ok, 0) != 0;
-                if (ok) { ++n; continue; }
-                if (n > 0) break;
-                __nanosleep(20);
-                const unsigned long long t = sl_now();
-                if (t0 == 0) t0 = t;
-                else if (t - t0 > SL_TIMEOUT_NS) { broken = true; break; }
-            }
-            if (broken) {
-                if (lane == 0) *P.error = 1;
-                return;
-            }
-            if (lane == 0) __threadfence();
-            __syncwarp();
-            for (int u = 0; u < n; u++) {
-                const int g = __shfl_sync(0xffffffffu, grp, (it + u) & 31);
-                if (lane == 0) red_relaxed_gpu_add(cnt + g, 1);
-            }
-            it += n;
-        }
-        return;
-    }
-
-    // ===== consumer warps =====
-    const bool last = (P.flags & 1) && level == P.k - 1;
+    // ===== consumer warpgroup =====
+    sl_reg_inc<232>();
+    const uint64_t pol = sl_policy(s_cta.last != 0);
     double dot_acc = 0.0;
-    if (NV == 1 && P.dot_w)
-        dot_acc = sl_consume<NV, MULADD, EB, SL_LAST_DOT>(P, n_my, s_ready, s_fin, s_ntile, s_desc, s_mask, s_src, s_dst, &s_row_end);
-    else if (last)
-        sl_consume<NV, MULADD, EB, SL_LAST>(P, n_my, s_ready, s_fin, s_ntile, s_desc, s_mask, s_src, s_dst, &s_row_end);
-    else if (P.flags & 4)
-        sl_consume<NV, MULADD, EB, SL_MID_ALLOC>(P, n_my, s_ready, s_fin, s_ntile, s_desc, s_mask, s_src, s_dst, &s_row_end);
-    else if (P.flags & 8)
-        sl_consume<NV, MULADD, EB, SL_MID_KEEP>(P, n_my, s_ready, s_fin, s_ntile, s_desc, s_mask, s_src, s_dst, &s_row_end);
-    else
-        sl_consume<NV, MULADD, EB, SL_MID>(P, n_my, s_ready, s_fin, s_ntile, s_desc, s_mask, s_src, s_dst, &s_row_end);
+    for (int it = 0; it < n_my; ++it) {
+        const int s = it % SL_RING;
+        mbar_wait(&s_ready[s], (it / SL_RING) & 1);
+        const int ntile = s_hdr[s][0], width = s_hdr[s][1];
+        if (ntile == T && width >= 0) {
+            sl_rows_pattern_any<NV, T>(width, s_desc[s], s_mask[s], P, s_cta, tid, pol, dot_acc);
+        } else {
+            for (int j = 0; j < ntile; j++) {  // a short last item, mixed formats or explicit tiles: tile by tile
+                const int *d = s_desc[s] + 16 * j;
+                if (d[5] == SL_FMT_PATTERN) sl_rows_pattern_any<NV, 1>(d[4], d, s_mask[s] + j, P, s_cta, tid, pol, dot_acc);
+                else sl_tile_explicit<NV, NV == 2 ? 8 : 16>(d, P, s_cta, tid, pol, dot_acc);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) red_release_cta_shared_add(&s_fin[s], 1u);  // the slot may be reused and the item published
+    }
 
     if (P.dot_w) {
         // deterministic: lanes -> warp (xor tree), warps in order, CTAs in order (last CTA finishes)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) dot_acc += __shfl_xor_sync(0xffffffffu, dot_acc, o);
         if (lane == 0) s_red[warp] = dot_acc;
-        named_bar_sync(2, SL_ROWS);
+        named_bar_sync(2, SL_CTHREADS);
         if (warp == 0) {
             __shared__ bool is_last;
             if (lane == 0) {
@@ -561,19 +603,15 @@ __global__ void __launch_bounds__(SL_THREADS, MINB) sell_kernel(const SlParams P
 }
 
 // -----------------------------------------------------------------------------------------------
-// kernel instances: geometry 0 = pattern operators (explicit tiles 4 entries per round trip; 3 CTAs per SM at 64 registers),
-// 1 = explicit-column operators (8 entries per round trip; 2 CTAs per SM at 96 registers)
+// kernel instances: NV right-hand sides x T tiles per item (2 T rows per consumer thread in flight)
 // -----------------------------------------------------------------------------------------------
 typedef void (*sl_fn)(const SlParams);
-static sl_fn sl_lookup(int geom, bool muladd, int nv)
+static sl_fn sl_lookup(int nv, int chunk)
 {
-    if (nv == 2) {
-        if (geom == 0) return muladd ? sell_kernel<2, true, 4, 2> : sell_kernel<2, false, 4, 2>;
-        return muladd ? sell_kernel<2, true, 8, 2> : sell_kernel<2, false, 8, 2>;
-    }
-    if (geom == 0) return muladd ? sell_kernel<1, true, 4, 3> : sell_kernel<1, false, 4, 3>;
-    return muladd ? sell_kernel<1, true, 8, 2> : sell_kernel<1, false, 8, 2>;
+    if (nv == 2) return chunk >= 2 ? sell_kernel<2, 2> : sell_kernel<2, 1>;
+    return chunk >= 3 ? sell_kernel<1, 3> : chunk == 2 ? sell_kernel<1, 2> : sell_kernel<1, 1>;
 }
+static int sl_max_chunk(int nv) { return nv == 2 ? 2 : 3; }
 
 // -----------------------------------------------------------------------------------------------
 // host side: tiling + pattern detection + blobs
@@ -1192,22 +1230,16 @@ static SellOp *sl_get(nsk_csr_t A)
     return op;
 }
 
-static int sl_geom(nsk_csr_t A, SellOp *op)
-{
-    const int v = (int)A->ctx->opt.sell_geom;
-    if (v == 1 || v == 2) return v - 1;
-    return 2 * op->n_pattern >= op->ntiles ? 0 : 1;
-}
-
 static SlPlan *sl_plan(nsk_csr_t A, SellOp *op, int k, const int *level_rows, int resident, int nv, const char **why)
 {
     nsk_ctx_t ctx = A->ctx;
     std::vector<int> lr(k);
     for (int l = 0; l < k; l++) lr[l] = level_rows ? level_rows[l] : A->n;
+    // tiles per item = tiles a consumer thread keeps in flight at once (2 rows of each): 3 for one right-hand side, 2 for
+    // two; operators with explicit-column tiles go tile by tile anyway
     int chunk = (int)ctx->opt.sell_chunk;
-    if (chunk <= 0) chunk = k > 1 ? 2 : 4;
-    chunk = std::min(chunk, SL_MAXCHUNK);
-    while (WF_GROUP % chunk) chunk--;  // a chunk never straddles a completion group of level 0
+    if (chunk <= 0) chunk = sl_max_chunk(nv);
+    chunk = std::max(1, std::min(chunk, sl_max_chunk(nv)));
     const int w0_pct = k > 1 ? (ctx->opt.pipe_w0_pct > 0 ? (int)ctx->opt.pipe_w0_pct : 100) : 100;
     const int interleave = ctx->opt.pipe_interleave ? 1 : 0;
     const int l2_pct = (int)ctx->opt.wave_l2_pct;
@@ -1315,8 +1347,10 @@ static int sl_run(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
         nsk_set_error(ctx, "fused matrix-powers kernel: a bounded wait expired in an earlier launch (results invalid)");
         return NSK_ERR_CUDA;
     }
-    const int geom = sl_geom(A, op);
-    sl_fn fn = sl_lookup(geom, mode == NSK_EXACT_MULADD, nv);
+    int chunk_req = (int)ctx->opt.sell_chunk;
+    if (chunk_req <= 0) chunk_req = sl_max_chunk(nv);
+    chunk_req = std::max(1, std::min(chunk_req, sl_max_chunk(nv)));
+    sl_fn fn = sl_lookup(nv, chunk_req);
     int per_sm = 0;
     NSK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, SL_THREADS, 0));
     if (ctx->opt.sell_ctas_per_sm > 0) per_sm = std::min(per_sm, (int)ctx->opt.sell_ctas_per_sm);
@@ -1358,6 +1392,7 @@ static int sl_run(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
     P.chunk = plan->chunk;
     P.epoch = plan->epoch;
     P.bp_level = k > 1 ? k - 1 : -1;
+    P.muladd = mode == NSK_EXACT_MULADD ? 1 : 0;
     P.flags = ctx->opt.sell_flags >= 0 ? (int)ctx->opt.sell_flags : 3;
     P.pf_dist = ctx->opt.sell_pf_dist > 0 ? (int)ctx->opt.sell_pf_dist : 2;
     P.error = op->d_error;

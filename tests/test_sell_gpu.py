@@ -1,6 +1,6 @@
 """GPU parity of the sliced-ELL path (csrc/sell.cu): nsk_spmv / nsk_mpk / nsk_mpk_multi through the C ABI against the
 oracle and the golden fixtures -- bit-exact in both exact modes, stencil (pattern tiles) and unstructured (explicit
-columns) operators, every chunk size, both kernel geometries."""
+columns) operators, every number of tiles per item."""
 import numpy as np
 import pytest
 
@@ -10,7 +10,7 @@ from conftest import CSR_CASES, VECS, assert_bits_equal, golden
 
 pytestmark = pytest.mark.gpu
 
-SELL_OPTS = ("spmv_kernel", "mpk_kernel", "sell_chunk", "sell_geom", "sell_ctas_per_sm", "sell_pf_dist", "wave_l2_pct",
+SELL_OPTS = ("spmv_kernel", "mpk_kernel", "sell_chunk", "sell_ctas_per_sm", "sell_pf_dist", "wave_l2_pct",
              "pipe_w0_pct")
 
 
@@ -31,17 +31,15 @@ def test_sell_spmv_golden(sell, oracle_lib, case):
     ctx = sell
     g = golden(case)
     A = nsk.CsrMatrix(ctx, g["ptrow"], g["indcol"], g["coef"])
-    for geom in (1, 2):
-        ctx.set_option("sell_geom", geom)
-        for chunk in (1, 3, 8):
-            ctx.set_option("sell_chunk", chunk)
-            for v in VECS:
-                x = g[f"x_{v}"]
-                y = A.spmv(x, mode=nsk.EXACT_FMA)
-                assert ctx.query("last_spmv_kernel") == 4, "the sliced-ELL kernel did not run"
-                assert_bits_equal(y, g[f"spmv_fma_{v}"], f"{case}/{v} geom={geom} chunk={chunk}")
-                assert_bits_equal(A.spmv(x, mode=nsk.EXACT_MULADD),
-                                  oracle_lib.spmv_muladd(g["ptrow"], g["indcol"], g["coef"], x), f"{case}/{v} muladd")
+    for chunk in (1, 2, 3):
+        ctx.set_option("sell_chunk", chunk)
+        for v in VECS:
+            x = g[f"x_{v}"]
+            y = A.spmv(x, mode=nsk.EXACT_FMA)
+            assert ctx.query("last_spmv_kernel") == 4, "the sliced-ELL kernel did not run"
+            assert_bits_equal(y, g[f"spmv_fma_{v}"], f"{case}/{v} chunk={chunk}")
+            assert_bits_equal(A.spmv(x, mode=nsk.EXACT_MULADD),
+                              oracle_lib.spmv_muladd(g["ptrow"], g["indcol"], g["coef"], x), f"{case}/{v} muladd")
 
 
 @pytest.mark.parametrize("case", CSR_CASES)
@@ -54,7 +52,7 @@ def test_sell_mpk_golden_equals_k_products_bitwise(sell, oracle_lib, case, k):
     x = g["x_uni"]
     ref = oracle_lib.mpk(g["ptrow"], g["indcol"], g["coef"], k, x)
     dx = ctx.to_device(x)
-    for chunk in (1, 2, 4):
+    for chunk in (1, 2, 3):
         ctx.set_option("sell_chunk", chunk)
         lv = [ctx.zeros(A.n) for _ in range(k)]
         before = ctx.launch_count
@@ -68,9 +66,9 @@ SELL_OPS = [("laplace3d_7pt", (40,)), ("laplace2d_5pt", (300,)), ("laplace3d_7pt
             ("tet_p1_laplacian", (24, 2, True)), ("fem_baij4", (7,)), ("random_banded_csr", (30000, 700, 9.0, 3))]
 
 
-@pytest.mark.parametrize("geom", [1, 2])
+@pytest.mark.parametrize("chunk", [0, 2])
 @pytest.mark.parametrize("gen,args", SELL_OPS)
-def test_sell_spmv_and_mpk_bitwise(sell, oracle_lib, gen, args, geom):
+def test_sell_spmv_and_mpk_bitwise(sell, oracle_lib, gen, args, chunk):
     """Stencils (pattern tiles, no per-entry index), an RCM-ordered tetrahedral P1 Laplacian, a 4-dof-per-node FEM operator
     (58 per row) and a ragged banded matrix (explicit tiles with per-slice widths): product and fused powers, both
     exact flavours, several repetitions (the completion counters are monotone over launches)."""
@@ -78,7 +76,7 @@ def test_sell_spmv_and_mpk_bitwise(sell, oracle_lib, gen, args, geom):
     A = getattr(matgen, gen)(*args)
     x = matgen.vec_uniform(A.n, seed=11)
     dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
-    ctx.set_option("sell_geom", geom)
+    ctx.set_option("sell_chunk", chunk)
     ctx.set_option("wave_l2_pct", 1000)
     assert_bits_equal(dA.spmv(x), oracle_lib.spmv(A.ptrow, A.indcol, A.coef, x), f"{gen}{args} spmv")
     applies = ctx.query("last_spmv_kernel") == 4
@@ -94,7 +92,7 @@ def test_sell_spmv_and_mpk_bitwise(sell, oracle_lib, gen, args, geom):
             dA.mpk(k, dx, lv)
             if applies:
                 assert ctx.launch_count - before == 1 and ctx.query("last_mpk_strategy") == 5
-            assert_bits_equal(np.stack([l.to_host() for l in lv]), ref, f"{gen}{args} k={k} geom={geom} rep={rep}")
+            assert_bits_equal(np.stack([l.to_host() for l in lv]), ref, f"{gen}{args} k={k} chunk={chunk} rep={rep}")
     y = x
     lm = dA.mpk(3, x, mode=nsk.EXACT_MULADD)
     for l in range(3):
@@ -118,7 +116,7 @@ def test_sell_mpk_window_and_placement(sell, oracle_lib, interleave, w0, cps, le
     dx = ctx.to_device(x)
     for k in (2, 5):
         ref = oracle_lib.mpk(A.ptrow, A.indcol, A.coef, k, x)
-        for chunk in (1, 2, 8):
+        for chunk in (1, 2, 3):
             ctx.set_option("sell_chunk", chunk)
             lv = dA.mpk(k, dx)
             assert ctx.query("last_mpk_strategy") == 5
@@ -132,7 +130,7 @@ def test_sell_flags_prefetch_and_hints(sell, oracle_lib):
     dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
     ref = oracle_lib.mpk(A.ptrow, A.indcol, A.coef, 4, x)
     dx = ctx.to_device(x)
-    for flags in (0, 1, 2, 3, 7, 11):
+    for flags in (0, 1, 2, 3):
         for pf in (1, 4):
             ctx.set_option("sell_flags", flags)
             ctx.set_option("sell_pf_dist", pf)
