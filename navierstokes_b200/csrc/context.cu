@@ -151,6 +151,8 @@ NSK_API int nsk_ctx_set_option(nsk_ctx_t c, const char *name, int64_t v)
     else if (!strcmp(name, "sell_ctas_per_sm")) c->opt.sell_ctas_per_sm = v;
     else if (!strcmp(name, "sell_flags")) c->opt.sell_flags = v;
     else if (!strcmp(name, "sell_pf_dist")) c->opt.sell_pf_dist = v;
+    else if (!strcmp(name, "sell_stream")) c->opt.sell_stream = v;
+    else if (!strcmp(name, "sell_rows")) c->opt.sell_rows = v;
     else {
         nsk_set_error(c, "unknown option '%s'", name);
         return NSK_ERR_INVALID;

@@ -68,6 +68,9 @@ struct nsk_options {
     int64_t sell_ctas_per_sm = 0; // 0 = what the occupancy calculator allows
     int64_t sell_flags = -1;      // < 0 default (3): bit 0 eviction / streaming hints, bit 1 L2 prefetch of level 0's tiles
     int64_t sell_pf_dist = 0;     // items ahead the L2 prefetch runs; 0 = default 2
+    int64_t sell_rows = 0;        // streaming kernel: rows of a tile per consumer thread (0 = default 1, 2)
+    int64_t sell_stream = 0;      // all-pattern operators: tiles in flight per consumer thread (0 = default 3, < 0 = the
+                                  // item-at-a-time kernel)
 };
 
 struct nsk_ctx_s {

@@ -374,11 +374,161 @@ __device__ __forceinline__ void sl_tile_explicit(const int *d, const SlParams &P
     }
 }
 
+// ---- streaming consumers (operators made of pattern tiles of one width W) ---------------------------------------
+// A consumer thread keeps D tiles in flight (rows t and t + 128 of each) in D statically named register sets and
+// software-pipelines the tile stream of its CTA: [issue the loads of tile n + D - 1] [chain + store tile n] ... so the
+// load pipe is fed continuously instead of in bursts, and a load has D - 1 tiles' worth of work to complete.  The sets
+// rotate in a fixed order (fill order = compute order).  A tile whose item is not ready yet is NOT waited for while
+// other sets hold tiles (a bubble passes through instead): finishing an item never depends on a later item's inputs,
+// which is what the level schedule's deadlock-freedom argument (and its CPU model) assumes.
+template <int NV, int W, int R>
+struct SlSet {
+    double a[R][W], xv[NV][R][W];
+    unsigned int m[R];
+    int row[R];
+    int state;  // bit 0: holds a tile; bit 1: last tile of its item; bits 2, 3: row h is stored; bits 8..: ring slot
+};
+
+struct SlCursor {
+    int it, j, ntile;  // next tile: j-th of item it; ntile < 0: the item has not been opened yet
+};
+
+// Fills `S` with the next tile of the stream; returns false when the stream has ended or (may_block == false) its item
+// is not ready.
+template <int NV, int W, int R>
+__device__ __forceinline__ bool sl_stream_issue(SlSet<NV, W, R> &S, SlCursor &cur, int n_my, bool may_block, const SlParams &P,
+                                                const SlCta &C, uint64_t *s_ready, const int (*s_hdr)[2],
+                                                const int (*s_desc)[SL_MAXCHUNK * 16],
+                                                const unsigned char (*s_mask)[SL_MAXCHUNK][SL_ROWS], int t, uint64_t pol)
+{
+    S.state = 0;
+    if (cur.it >= n_my) return false;
+    const int slot = cur.it % SL_RING;
+    if (cur.ntile < 0) {
+        const uint32_t parity = (uint32_t)(cur.it / SL_RING) & 1u;
+        if (!mbar_try_wait(&s_ready[slot], parity)) {
+            if (!may_block) return false;
+            mbar_wait(&s_ready[slot], parity);
+        }
+        cur.ntile = s_hdr[slot][0];
+    }
+    const int *d = s_desc[slot] + 16 * cur.j;
+    const int4 q = *reinterpret_cast<const int4 *>(d);  // off lo, off hi, row0, nrows
+    const int4 r0 = *reinterpret_cast<const int4 *>(d + 8), r1 = *reinterpret_cast<const int4 *>(d + 12);
+    const int rel[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+    const long long off = ((long long)(unsigned int)q.x) | ((long long)q.y << 32);
+    const double *src = C.src[0];
+    const double *src2 = NV == 2 ? C.src[1] : nullptr;
+    const int cmax = P.n_cols - 1;
+    int state = 1 | (slot << 8);
+#pragma unroll
+    for (int h = 0; h < R; h++) {
+        const int r = t + (SL_ROWS / R) * h;
+        S.m[h] = s_mask[slot][cur.j][r];
+        S.row[h] = q.z + r;
+        if (r < q.w && S.row[h] < C.row_end) state |= 4 << h;
+        const double *val = reinterpret_cast<const double *>(P.blobs + off + SL_ROWS) + r;
+        const int rowc = min(S.row[h], cmax);  // padding rows of a short tile stay inside x
+#pragma unroll
+        for (int e = 0; e < W; e++) {
+            S.a[h][e] = sl_ld_coef(val + e * SL_ROWS, pol);
+            const int idx = rowc + (rel[e] & -(int)((S.m[h] >> e) & 1u));  // a slot the row lacks reads its own x entry
+            S.xv[0][h][e] = sl_ld_x(src + idx);
+            if (NV == 2) S.xv[NV - 1][h][e] = sl_ld_x(src2 + idx);
+        }
+    }
+    if (++cur.j == cur.ntile) {
+        state |= 2;
+        cur.j = 0;
+        cur.ntile = -1;
+        cur.it++;
+    }
+    S.state = state;
+    return true;
+}
+
+template <int NV, int W, int R>
+__device__ __forceinline__ void sl_stream_compute(const SlSet<NV, W, R> &S, const SlParams &P, const SlCta &C, unsigned int *s_fin,
+                                                  double &dot_acc)
+{
+    double acc0[R], acc1[R];
+#pragma unroll
+    for (int h = 0; h < R; h++) {
+        acc0[h] = 0.0;
+        acc1[h] = 0.0;
+        if (C.muladd) {
+#pragma unroll
+            for (int e = 0; e < W; e++)
+                if (S.m[h] & (1u << e)) {
+                    acc0[h] = row_op<true>(S.a[h][e], S.xv[0][h][e], acc0[h]);
+                    if (NV == 2) acc1[h] = row_op<true>(S.a[h][e], S.xv[NV - 1][h][e], acc1[h]);
+                }
+        } else {
+#pragma unroll
+            for (int e = 0; e < W; e++)
+                if (S.m[h] & (1u << e)) {
+                    acc0[h] = row_op<false>(S.a[h][e], S.xv[0][h][e], acc0[h]);
+                    if (NV == 2) acc1[h] = row_op<false>(S.a[h][e], S.xv[NV - 1][h][e], acc1[h]);
+                }
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < R; h++)
+        if (S.state & (4 << h)) sl_store_row<NV>(P, C, S.row[h], acc0[h], acc1[h], dot_acc);
+    if (S.state & 2) {  // last tile of its item: the slot may be reused and the item published
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) red_release_cta_shared_add(&s_fin[S.state >> 8], 1u);
+    }
+}
+
+template <int NV, int W, int D, int R>
+__device__ __forceinline__ double sl_consume_stream(const SlParams &P, const SlCta &C, int n_my, uint64_t *s_ready, unsigned int *s_fin,
+                                                    const int (*s_hdr)[2], const int (*s_desc)[SL_MAXCHUNK * 16],
+                                                    const unsigned char (*s_mask)[SL_MAXCHUNK][SL_ROWS], uint64_t pol)
+{
+    const int t = threadIdx.x;
+    SlSet<NV, W, R> S[D];
+    SlCursor cur{0, 0, -1};
+    double dot_acc = 0.0;
+    int pending = 0;
+#pragma unroll
+    for (int d = 0; d < D - 1; d++)
+        pending += sl_stream_issue<NV, W, R>(S[d], cur, n_my, pending == 0, P, C, s_ready, s_hdr, s_desc, s_mask, t, pol) ? 1 : 0;
+    while (cur.it < n_my || pending > 0) {
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            // the set computed in the previous step is free: fill it (or let a bubble through), then compute the oldest
+            pending += sl_stream_issue<NV, W, R>(S[(d + D - 1) % D], cur, n_my, pending == 0, P, C, s_ready, s_hdr, s_desc, s_mask, t,
+                                              pol) ? 1 : 0;
+            if (S[d].state & 1) {
+                sl_stream_compute<NV, W, R>(S[d], P, C, s_fin, dot_acc);
+                S[d].state = 0;
+                pending--;
+            }
+        }
+    }
+    return dot_acc;
+}
+
 // CTA = two warpgroups.  Warps 0..3: consumers (rows t and t + 128 of every tile; most of the CTA's registers).
 // Warp 4: dependency warp.  Warp 5: publisher.  Warps 6, 7 only give their registers away.
-template <int NV, int T>
-__global__ void __launch_bounds__(SL_THREADS, 2) sell_kernel(const SlParams P)
+// PW = 0: any operator, an item at a time (T tiles of one pattern at once, everything else tile by tile).
+// PW > 0: operators made of pattern tiles of width PW only -- streaming consumers with T tiles in flight per thread.
+// R = rows of a tile per consumer thread (streaming kernel): 2 -> one consumer warpgroup with 232 registers per thread,
+// 1 -> two consumer warpgroups (256 threads, 104 registers): twice the warps, half the loads in flight per warp.
+template <int R>
+struct SlShape {
+    static constexpr int CT = SL_ROWS / R;       // consumer threads
+    static constexpr int NCW = CT / 32;          // consumer warps
+    static constexpr int NT = CT + 128;          // + the helper warpgroup
+    static constexpr int REGS = R == 2 ? 232 : 104;  // consumers after the helper warpgroup has dropped to 24
+    static constexpr int LAUNCH_REGS = R == 2 ? 128 : 80;  // what the launch bounds must give for the pool to add up
+};
+
+template <int NV, int T, int PW, int R>
+__global__ void __launch_bounds__(SlShape<R>::NT, 2) sell_kernel(const SlParams P)
 {
+    constexpr int NCW = SlShape<R>::NCW;
     static_assert(NV == 1 || NV == 2, "one or two right-hand sides");
     static_assert(T >= 1 && T <= SL_MAXCHUNK, "tiles per item");
     __shared__ __align__(16) int s_desc[SL_RING][SL_MAXCHUNK * 16];               // tile descriptors of the items in flight
@@ -386,7 +536,7 @@ __global__ void __launch_bounds__(SL_THREADS, 2) sell_kernel(const SlParams P)
     __shared__ int s_hdr[SL_RING][2];         // tiles in the item; their common width when they share one pattern, else -1
     __shared__ uint64_t s_ready[SL_RING];     // item's inputs complete + descriptors in place (dependency warp arrives)
     __shared__ unsigned int s_fin[SL_RING];   // consumer warps that finished the slot's item, counted over the whole launch
-    __shared__ double s_red[SL_NCW];
+    __shared__ double s_red[NCW];
     __shared__ SlCta s_cta;
 
     const int tid = threadIdx.x;
@@ -414,9 +564,9 @@ __global__ void __launch_bounds__(SL_THREADS, 2) sell_kernel(const SlParams P)
     }
     __syncthreads();
 
-    if (warp >= SL_NCW) {
+    if (warp >= NCW) {
         sl_reg_dec<24>();
-        if (warp == SL_NCW) {
+        if (warp == NCW) {
             // ===== dependency warp: per item, in order -- (1) fetch the tile descriptors into registers, (2) wait until
             // the level below has completed the groups the item reads and the level that holds this one back has
             // advanced, (3) wait for the ring slot (the item four back is finished by every consumer warp), (4) stage
@@ -475,7 +625,7 @@ __global__ void __launch_bounds__(SL_THREADS, 2) sell_kernel(const SlParams P)
                     if (wb < 0 || wf < 0) broken = true;
                 }
                 if (it >= SL_RING && !broken) {
-                    const unsigned int need = (unsigned int)SL_NCW * (unsigned int)(it / SL_RING);
+                    const unsigned int need = (unsigned int)NCW * (unsigned int)(it / SL_RING);
                     unsigned long long t1 = 0;
                     while (ld_acquire_cta_shared_u32(&s_fin[s]) < need) {
                         __nanosleep(20);
@@ -502,7 +652,7 @@ __global__ void __launch_bounds__(SL_THREADS, 2) sell_kernel(const SlParams P)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&s_ready[s]);  // release.cta: descriptors + everything acquired above
             }
-        } else if (warp == SL_NCW + 1 && P.k > 1) {
+        } else if (warp == NCW + 1 && P.k > 1) {
             // ===== publisher: one gpu-scope fence for everything found finished at that moment, then one RED per item.
             // Consumers bump s_fin[slot] with release.cta after their stores; the acquire here + fence + RED is
             // cumulative over those stores. =====
@@ -522,7 +672,7 @@ __global__ void __launch_bounds__(SL_THREADS, 2) sell_kernel(const SlParams P)
                     const int i2 = it + n;
                     bool ok = false;
                     if (i2 < n_my && (n == 0 || (i2 & 31) != 0) && n < SL_RING) {
-                        const unsigned int need = (unsigned int)SL_NCW * (unsigned int)(i2 / SL_RING + 1);
+                        const unsigned int need = (unsigned int)NCW * (unsigned int)(i2 / SL_RING + 1);
                         ok = ld_acquire_cta_shared_u32(&s_fin[i2 % SL_RING]) >= need;
                     }
                     ok = __shfl_sync(0xffffffffu, (int)ok, 0) != 0;
@@ -550,10 +700,11 @@ __global__ void __launch_bounds__(SL_THREADS, 2) sell_kernel(const SlParams P)
     }
 
     // ===== consumer warpgroup =====
-    sl_reg_inc<232>();
+    sl_reg_inc<SlShape<R>::REGS>();
     const uint64_t pol = sl_policy(s_cta.last != 0);
     double dot_acc = 0.0;
-    for (int it = 0; it < n_my; ++it) {
+    if (PW > 0) dot_acc = sl_consume_stream<NV, PW, T, R>(P, s_cta, n_my, s_ready, s_fin, s_hdr, s_desc, s_mask, pol);
+    for (int it = 0; PW == 0 && it < n_my; ++it) {
         const int s = it % SL_RING;
         mbar_wait(&s_ready[s], (it / SL_RING) & 1);
         const int ntile = s_hdr[s][0], width = s_hdr[s][1];
@@ -575,12 +726,12 @@ __global__ void __launch_bounds__(SL_THREADS, 2) sell_kernel(const SlParams P)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) dot_acc += __shfl_xor_sync(0xffffffffu, dot_acc, o);
         if (lane == 0) s_red[warp] = dot_acc;
-        named_bar_sync(2, SL_CTHREADS);
+        named_bar_sync(2, SlShape<R>::CT);
         if (warp == 0) {
             __shared__ bool is_last;
             if (lane == 0) {
                 double sum = 0.0;
-                for (int w = 0; w < SL_NCW; w++) sum += s_red[w];
+                for (int w = 0; w < NCW; w++) sum += s_red[w];
                 P.partials[blockIdx.x] = sum;
                 __threadfence();
                 const unsigned int ticket = atomicAdd(P.ticket, 1u);
@@ -606,12 +757,56 @@ __global__ void __launch_bounds__(SL_THREADS, 2) sell_kernel(const SlParams P)
 // kernel instances: NV right-hand sides x T tiles per item (2 T rows per consumer thread in flight)
 // -----------------------------------------------------------------------------------------------
 typedef void (*sl_fn)(const SlParams);
-static sl_fn sl_lookup(int nv, int chunk)
+struct SlLaunch {
+    sl_fn fn = nullptr;
+    int threads = 0, launch_regs = 0;
+};
+// generic kernel: chunk = tiles per item = tiles of one pattern a consumer thread takes at once
+static SlLaunch sl_lookup(int nv, int chunk)
 {
-    if (nv == 2) return chunk >= 2 ? sell_kernel<2, 2> : sell_kernel<2, 1>;
-    return chunk >= 3 ? sell_kernel<1, 3> : chunk == 2 ? sell_kernel<1, 2> : sell_kernel<1, 1>;
+    SlLaunch L;
+    L.threads = SlShape<2>::NT;
+    L.launch_regs = SlShape<2>::LAUNCH_REGS;
+    if (nv == 2) L.fn = chunk >= 2 ? sell_kernel<2, 2, 0, 2> : sell_kernel<2, 1, 0, 2>;
+    else L.fn = chunk >= 3 ? sell_kernel<1, 3, 0, 2> : chunk == 2 ? sell_kernel<1, 2, 0, 2> : sell_kernel<1, 1, 0, 2>;
+    return L;
 }
 static int sl_max_chunk(int nv) { return nv == 2 ? 2 : 3; }
+// streaming kernel (all tiles pattern tiles of width w): depth tiles in flight per thread, rows of a tile per thread
+template <int NV, int D, int R>
+static sl_fn sl_lookup_stream_w(int w)
+{
+    switch (w) {
+    case 1: return sell_kernel<NV, D, 1, R>;
+    case 2: return sell_kernel<NV, D, 2, R>;
+    case 3: return sell_kernel<NV, D, 3, R>;
+    case 4: return sell_kernel<NV, D, 4, R>;
+    case 5: return sell_kernel<NV, D, 5, R>;
+    case 6: return sell_kernel<NV, D, 6, R>;
+    case 7: return sell_kernel<NV, D, 7, R>;
+    case 8: return sell_kernel<NV, D, 8, R>;
+    }
+    return nullptr;
+}
+static SlLaunch sl_lookup_stream(int nv, int w, int depth, int rows)
+{
+    SlLaunch L;
+    if (rows == 1) {  // 104 registers: two tiles in flight (one for two right-hand sides of a wide pattern)
+        L.threads = SlShape<1>::NT;
+        L.launch_regs = SlShape<1>::LAUNCH_REGS;
+        if (nv == 2) L.fn = w <= 5 ? sl_lookup_stream_w<2, 2, 1>(w) : sl_lookup_stream_w<2, 1, 1>(w);
+        else L.fn = depth >= 2 ? sl_lookup_stream_w<1, 2, 1>(w) : sl_lookup_stream_w<1, 1, 1>(w);
+        return L;
+    }
+    L.threads = SlShape<2>::NT;
+    L.launch_regs = SlShape<2>::LAUNCH_REGS;
+    if (nv == 2) L.fn = sl_lookup_stream_w<2, 2, 2>(w);
+    else {
+        if (w == 8) depth = std::min(depth, 2);  // 8 slots x 2 rows x 3 tiles would not fit the consumers' registers
+        L.fn = depth >= 3 ? sl_lookup_stream_w<1, 3, 2>(w) : sl_lookup_stream_w<1, 2, 2>(w);
+    }
+    return L;
+}
 
 // -----------------------------------------------------------------------------------------------
 // host side: tiling + pattern detection + blobs
@@ -622,6 +817,7 @@ struct SellHost {
     std::vector<unsigned char> blobs;
     size_t blob_bytes = 0;
     int n_pattern = 0;
+    int uniform_width = 0;  // > 0: every tile is a pattern tile stored with this many slots
 };
 
 static void sl_parallel(int n, const std::function<void(int)> &body)
@@ -734,11 +930,24 @@ static std::string sl_pack_host(int n, int n_cols, int64_t nnz, const int *ptrow
     });
     if (too_long.load()) return "a row is longer than 65535 entries";
     size_t total = 0;
-    int n_pattern = 0;
+    int n_pattern = 0, wmax = 0;
+    for (int t = 0; t < ntiles; t++) {
+        n_pattern += st[t].fmt == SL_FMT_PATTERN;
+        if (st[t].fmt == SL_FMT_PATTERN) wmax = std::max(wmax, st[t].width);
+    }
+    // An operator made of pattern tiles only gets ONE width: narrower tiles (lines on a domain face lack a neighbour
+    // line) are padded with slots no row has, so the streaming kernel runs one straight-line instance over all of them.
+    out.uniform_width = 0;
+    if (n_pattern == ntiles && wmax >= 1) {
+        out.uniform_width = wmax;
+        for (int t = 0; t < ntiles; t++) {
+            st[t].width = wmax;  // rel[] beyond the tile's own slots is already zero
+            st[t].bytes = sl_blob_bytes_pattern(wmax);
+        }
+    }
     for (int t = 0; t < ntiles; t++) {
         st[t].off = (long long)total;
         total += (size_t)st[t].bytes;
-        n_pattern += st[t].fmt == SL_FMT_PATTERN;
     }
     // slice padding: refuse operators whose rows are so ragged that the tiles would outweigh CSR by half
     if ((double)total > 1.5 * (12.0 * (double)nnz + 4.0 * n) + 65536.0) return "row lengths too ragged for sliced-ELL tiles";
@@ -1143,7 +1352,7 @@ struct SlPlan {
 struct SellOp {
     bool ok = false;
     std::string why;
-    int ntiles = 0, n_pattern = 0;
+    int ntiles = 0, n_pattern = 0, uniform_width = 0;
     size_t blob_bytes = 0;
     unsigned char *d_blobs = nullptr;
     SlTile *d_tiles = nullptr;
@@ -1220,6 +1429,7 @@ static SellOp *sl_get(nsk_csr_t A)
     cudaMemcpy(op->d_tiles, H.stiles.data(), sizeof(SlTile) * (size_t)ntiles, cudaMemcpyHostToDevice);
     op->ntiles = ntiles;
     op->n_pattern = H.n_pattern;
+    op->uniform_width = H.uniform_width;
     op->blob_bytes = H.blob_bytes;
     op->h_tiles.swap(H.stiles);
     op->csr_view.tile_rows = SL_ROWS;
@@ -1230,16 +1440,22 @@ static SellOp *sl_get(nsk_csr_t A)
     return op;
 }
 
-static SlPlan *sl_plan(nsk_csr_t A, SellOp *op, int k, const int *level_rows, int resident, int nv, const char **why)
+// tiles per item.  Generic kernel: the tiles a consumer thread takes at once (3 for one right-hand side, 2 for two).
+// Streaming kernel: only the granularity of dependencies and publication.
+static int sl_plan_chunk(nsk_ctx_t ctx, int nv, bool stream)
+{
+    int chunk = (int)ctx->opt.sell_chunk;
+    const int cap = stream ? SL_MAXCHUNK : sl_max_chunk(nv);
+    if (chunk <= 0) chunk = stream ? 2 : cap;
+    return std::max(1, std::min(chunk, cap));
+}
+
+static SlPlan *sl_plan(nsk_csr_t A, SellOp *op, int k, const int *level_rows, int resident, int nv, bool stream, const char **why)
 {
     nsk_ctx_t ctx = A->ctx;
     std::vector<int> lr(k);
     for (int l = 0; l < k; l++) lr[l] = level_rows ? level_rows[l] : A->n;
-    // tiles per item = tiles a consumer thread keeps in flight at once (2 rows of each): 3 for one right-hand side, 2 for
-    // two; operators with explicit-column tiles go tile by tile anyway
-    int chunk = (int)ctx->opt.sell_chunk;
-    if (chunk <= 0) chunk = sl_max_chunk(nv);
-    chunk = std::max(1, std::min(chunk, sl_max_chunk(nv)));
+    const int chunk = sl_plan_chunk(ctx, nv, stream);
     const int w0_pct = k > 1 ? (ctx->opt.pipe_w0_pct > 0 ? (int)ctx->opt.pipe_w0_pct : 100) : 100;
     const int interleave = ctx->opt.pipe_interleave ? 1 : 0;
     const int l2_pct = (int)ctx->opt.wave_l2_pct;
@@ -1347,17 +1563,30 @@ static int sl_run(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
         nsk_set_error(ctx, "fused matrix-powers kernel: a bounded wait expired in an earlier launch (results invalid)");
         return NSK_ERR_CUDA;
     }
-    int chunk_req = (int)ctx->opt.sell_chunk;
-    if (chunk_req <= 0) chunk_req = sl_max_chunk(nv);
-    chunk_req = std::max(1, std::min(chunk_req, sl_max_chunk(nv)));
-    sl_fn fn = sl_lookup(nv, chunk_req);
+    // all-pattern operators: streaming consumers (option sell_stream: 0 = default depth 3, n = depth n, < 0 = off);
+    // everything else: an item at a time
+    const int depth = ctx->opt.sell_stream == 0 ? 3 : (int)ctx->opt.sell_stream;
+    const bool stream = op->uniform_width > 0 && depth >= 2;
+    const int rows = ctx->opt.sell_rows == 2 ? 2 : 1;
+    const SlLaunch L = stream ? sl_lookup_stream(nv, op->uniform_width, depth, rows) : sl_lookup(nv, sl_plan_chunk(ctx, nv, false));
+    sl_fn fn = L.fn;
+    {
+        // the register hand-over between the warpgroups only adds up when the kernel got the register count its launch
+        // bounds imply (ptxas pins it to that when setmaxnreg is used): refuse to launch otherwise rather than hang
+        cudaFuncAttributes fa;
+        NSK_CUDA(ctx, cudaFuncGetAttributes(&fa, fn));
+        if (fa.numRegs != L.launch_regs) {
+            nsk_set_error(ctx, "sliced-ELL kernel was built with %d registers per thread, expected %d", fa.numRegs, L.launch_regs);
+            return NSK_ERR_UNSUPPORTED;
+        }
+    }
     int per_sm = 0;
-    NSK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, SL_THREADS, 0));
+    NSK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, L.threads, 0));
     if (ctx->opt.sell_ctas_per_sm > 0) per_sm = std::min(per_sm, (int)ctx->opt.sell_ctas_per_sm);
     const int resident = ctx->prop.multiProcessorCount * per_sm;
     if (resident < k) { nsk_set_error(ctx, "sliced-ELL path: fewer resident CTAs than levels"); return NSK_ERR_UNSUPPORTED; }
     const char *why = "";
-    SlPlan *plan = sl_plan(A, op, k, level_rows, resident, nv, &why);
+    SlPlan *plan = sl_plan(A, op, k, level_rows, resident, nv, stream, &why);
     if (!plan) { nsk_set_error(ctx, "fused matrix powers not applicable: %s", why); return NSK_ERR_UNSUPPORTED; }
     int maxcount = 0;
     for (int l = 0; l < k; l++) maxcount = std::max(maxcount, plan->count[l]);
@@ -1403,7 +1632,7 @@ static int sl_run(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
     if (k > 1) {
         // CTAs of different levels wait on each other: co-residency must be guaranteed, not assumed
         void *args[] = {&P};
-        cudaError_t e = cudaLaunchCooperativeKernel((const void *)fn, dim3(plan->grid), dim3(SL_THREADS), args, 0, ctx->stream);
+        cudaError_t e = cudaLaunchCooperativeKernel((const void *)fn, dim3(plan->grid), dim3(L.threads), args, 0, ctx->stream);
         if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported) {
             cudaGetLastError();
             plan->epoch--;
@@ -1412,7 +1641,7 @@ static int sl_run(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
         }
         NSK_CUDA(ctx, e);
     } else {
-        fn<<<plan->grid, SL_THREADS, 0, ctx->stream>>>(P);
+        fn<<<plan->grid, L.threads, 0, ctx->stream>>>(P);
         NSK_CUDA(ctx, cudaGetLastError());
     }
     ctx->launches++;
