@@ -287,7 +287,7 @@ def main():
         return float(t.item())
 
     # ---- device-resident timing (value, roofline) --------------------------------------------------------
-    ctx.set_option("mpk_kernel", 0)  # default strategy: fused level pipeline on the packed format when it applies
+    ctx.set_option("mpk_kernel", 0)  # default strategy: fused level pipeline (sliced-ELL pattern tiles for a stencil)
     for _ in range(max(args.warmup, 3)):
         step_dev()
     sampler = ClockSampler(local_rank)
@@ -317,13 +317,15 @@ def main():
     per_step = launches / max(args.steps, 1)
     fused = per_step < K_POWERS
     strategy = ctx.query("last_mpk_strategy")
-    fused_names = {2: "mpk_wavefront_kernel", 3: "mpk_pipeline_kernel", 4: "packed_kernel (level pipeline over the packed format)"}
+    fused_names = {4: "packed_kernel (level pipeline over the packed format)",
+                   5: "sell_tma_kernel (level pipeline over sliced-ELL pattern tiles, coefficients staged by bulk copies)"}
     if fused:
         kern_bytes, kern_ms = mpk_bytes, ms_total / args.steps
         kern_name = f"{fused_names.get(strategy, 'fused powers kernel')}, 1 launch per step"
     else:
         kern_bytes, kern_ms = spmv_bytes, ms_total / args.steps / K_POWERS
-        kern_name = ("packed_kernel" if ctx.query("last_spmv_kernel") == 3 else "spmv_stream_kernel") + f", {K_POWERS} launches per step"
+        kern_name = ({3: "packed_kernel", 4: "sell_tma_kernel"}.get(ctx.query("last_spmv_kernel"), "spmv_stream_kernel")
+                     + f", {K_POWERS} launches per step")
     achieved = kern_bytes / kern_ms / 1e6
     traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of that kernel, from the committed ncu capture
     tfile = ROOT / "profiles" / "traffic.json"

@@ -99,29 +99,28 @@ uint64_t nsk_ctx_launch_count(nsk_ctx_t ctx);
 int nsk_ctx_device_info(nsk_ctx_t ctx, int *sm_count, int64_t *l2_bytes, int *smem_optin,
                         int64_t *hbm_bytes);
 /* Tuning knobs (name -> integer).  Unknown names give NSK_ERR_INVALID.  Defaults are what bench.py runs.
- *   spmv_kernel      0 auto (packed when the operator packs, else stream) | 1 scalar | 2 stream (CSR) | 3 packed |
- *                    4 sliced-ELL tiles
- *   mpk_kernel       0 auto (fused packed level pipeline when it applies, else k launches) | 1 k launches |
- *                    2 wavefront (CSR) | 3 level pipeline (CSR) | 4 level pipeline (packed) | 5 level pipeline
- *                    (sliced-ELL tiles: any operator whose rows are not too ragged, stencil or unstructured)
- *   sell_chunk       consecutive tiles a CTA takes per item (0 = default) | sell_geom 0 auto, 1 pattern, 2 explicit |
- *                    sell_ctas_per_sm | sell_flags (bit 0 eviction hints, bit 1 L2 prefetch of level 0) | sell_pf_dist
- *   packed_variant, stream_variant, pipe_variant, wave_variant   0 default, n = table entry n-1 of that kernel
- *   wave_l2_pct      share of L2 the fused kernels' window may occupy (0 = default: 70 packed, 80 CSR)
+ *   spmv_kernel      0 auto (sliced-ELL tiles for operators made of pattern tiles, packed when the operator packs, else
+ *                    stream) | 1 scalar | 2 stream (CSR) | 3 packed | 4 sliced-ELL tiles
+ *   mpk_kernel       0 auto (fused level pipeline: sliced-ELL tiles for operators made of pattern tiles, the packed
+ *                    format for other operators that pack, else k launches) | 1 k launches | 4 level pipeline
+ *                    (packed) | 5 level pipeline (sliced-ELL tiles: any operator whose rows are not too ragged)
+ *   sell_tma         all-pattern operators: coefficient stages per CTA of the staged kernel (0 = default 3: four CTAs per
+ *                    SM; 4: three CTAs; < 0 = the register kernels) | sell_chunk tiles per item (0 = default) |
+ *                    sell_stream, sell_rows (register kernels) | sell_ctas_per_sm | sell_flags | sell_pf_dist
+ *   packed_variant, stream_variant   0 default, n = table entry n-1 of that kernel
+ *   wave_l2_pct      share of L2 the fused kernels' window may occupy (0 = default: 88 sliced-ELL, 70 packed)
  *   wave_slack_pct   explicit window slack (< 0 = size it from the L2 budget)
- *   pipe_bp_global, pipe_interleave, pipe_w0_pct, pk_flags, stream_exact_kind, spmv_ctas_per_sm, wave_static
+ *   pipe_bp_global, pipe_interleave, pipe_w0_pct, pk_flags, stream_exact_kind, spmv_ctas_per_sm
  *                    experiment switches documented next to nsk_options in csrc/nsk_internal.h
  *   pk_flags         bit 0 (default on) cache hints for data nobody re-reads | bit 1 poll without sleeping | bit 2
  *                    publish with red.release
- *   packed_index     1: pack with index compression and run the kernel instances that read it (experimental, default
- *                    0; built for the default short-row geometry; bit-identical but slower so far, tools/check_index.py)
  *   pk_timing        1: the packed kernel prints its stage-cycle breakdown to stderr (debugging aid) */
 int nsk_ctx_set_option(nsk_ctx_t ctx, const char *name, int64_t value);
 
 /* CUDA-event timing on the context's stream (what bench.py brackets its timed regions with). */
-/* Introspection for tests / benchmarks: "last_spmv_kernel" (1 scalar, 2 stream over CSR, 3 packed),
- * "last_mpk_strategy" (1 k launches, 2 wavefront, 3 level pipeline over CSR, 4 level pipeline over the packed
- * format), "launches". */
+/* Introspection for tests / benchmarks: "last_spmv_kernel" (1 scalar, 2 stream over CSR, 3 packed, 4 sliced-ELL tiles),
+ * "last_mpk_strategy" (1 k launches, 4 level pipeline over the packed format, 5 level pipeline over sliced-ELL tiles),
+ * "launches". */
 int nsk_ctx_query(nsk_ctx_t ctx, const char *name, int64_t *value);
 int nsk_event_create(nsk_ctx_t ctx, void **event);
 int nsk_event_destroy(nsk_ctx_t ctx, void *event);
@@ -163,12 +162,6 @@ void nsk_mtx_free(int *irow, int *jcol, double *val);
  * x runs) so a test can compare it entry for entry with the input. */
 int nsk_pack_host_create(int n, int n_cols, int64_t nnz, const int *ptrow, const int *indcol, const double *coef,
                          int variant, void **handle);
-/* The same with index compression: a tile whose rows all follow one column pattern (slot u of row r references local
- * column base[u] + r -- every stencil / band; rows may lack slots) stores the pattern once and a slot mask per row, no
- * per-entry index.  GPU path: option packed_index (experimental, slower than the explicit format in round 1). */
-int nsk_pack_host_create_indexed(int n, int n_cols, int64_t nnz, const int *ptrow, const int *indcol, const double *coef,
-                                 int variant, void **handle);
-int nsk_pack_host_index_stats(void *handle, int64_t *tiles_indexed, int64_t *exception_rows);
 const char *nsk_pack_host_why(void *handle);
 int64_t nsk_pack_host_bytes(void *handle);
 int nsk_pack_host_expand(void *handle, int *ptrow, int *indcol, double *coef, int *max_runs, int *max_xlen);

@@ -47,9 +47,6 @@ SIGNATURES = {
                                C.POINTER(C.POINTER(C.c_double))]),
     "nsk_mtx_free": (None, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "nsk_pack_host_create": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, c_void_pp]),
-    "nsk_pack_host_create_indexed": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
-                                               c_void_pp]),
-    "nsk_pack_host_index_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "nsk_pack_host_why": (C.c_char_p, [C.c_void_p]),
     "nsk_pack_host_bytes": (C.c_int64, [C.c_void_p]),
     "nsk_pack_host_expand": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_int_p, c_int_p]),

@@ -132,17 +132,13 @@ NSK_API int nsk_ctx_set_option(nsk_ctx_t c, const char *name, int64_t v)
     else if (!strcmp(name, "spmv_ctas_per_sm")) c->opt.spmv_ctas_per_sm = v;
     else if (!strcmp(name, "mpk_kernel")) c->opt.mpk_kernel = v;
     else if (!strcmp(name, "stream_variant")) c->opt.stream_variant = v;
-    else if (!strcmp(name, "wave_variant")) c->opt.wave_variant = v;
     else if (!strcmp(name, "wave_slack_pct")) c->opt.wave_slack_pct = v;
     else if (!strcmp(name, "wave_l2_pct")) c->opt.wave_l2_pct = v;
-    else if (!strcmp(name, "wave_static")) c->opt.wave_static = v;
-    else if (!strcmp(name, "pipe_variant")) c->opt.pipe_variant = v;
     else if (!strcmp(name, "packed_variant")) c->opt.packed_variant = v;
     else if (!strcmp(name, "pipe_bp_global")) c->opt.pipe_bp_global = v;
     else if (!strcmp(name, "pipe_w0_pct")) c->opt.pipe_w0_pct = v;
     else if (!strcmp(name, "pk_timing")) c->opt.pk_timing = v;
     else if (!strcmp(name, "pk_flags")) c->opt.pk_flags = v;
-    else if (!strcmp(name, "packed_index")) c->opt.packed_index = v;
     else if (!strcmp(name, "host_overlap")) c->opt.host_overlap = v;
     else if (!strcmp(name, "stream_exact_kind")) c->opt.stream_exact_kind = v;
     else if (!strcmp(name, "pipe_interleave")) c->opt.pipe_interleave = v;
@@ -153,6 +149,7 @@ NSK_API int nsk_ctx_set_option(nsk_ctx_t c, const char *name, int64_t v)
     else if (!strcmp(name, "sell_pf_dist")) c->opt.sell_pf_dist = v;
     else if (!strcmp(name, "sell_stream")) c->opt.sell_stream = v;
     else if (!strcmp(name, "sell_rows")) c->opt.sell_rows = v;
+    else if (!strcmp(name, "sell_tma")) c->opt.sell_tma = v;
     else {
         nsk_set_error(c, "unknown option '%s'", name);
         return NSK_ERR_INVALID;

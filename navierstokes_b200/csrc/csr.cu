@@ -22,9 +22,8 @@ std::vector<int> &nsk_csr_host_ptrow(nsk_csr_t A)
 int nsk_mpk_device(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode);  // mpk.cu
 int nsk_mpk_device2(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, const double *d_x2,
                     double *const *d_levels2, nsk_mode mode);  // mpk.cu
-void nsk_wave_set_block_extents(nsk_csr_t A, const int *ptrow, const int *indcol);                  // mpk_wavefront.cu
+void nsk_wave_set_block_extents(nsk_csr_t A, const int *ptrow, const int *indcol);  // wave_deps.cu
 void nsk_wave_free(nsk_csr_t A);
-void nsk_pipe_free(nsk_csr_t A);  // mpk_pipeline.cu
 
 NSK_API int nsk_csr_create(nsk_ctx_t ctx, int n, int n_cols, int64_t nnz, const int *ptrow,
                            const int *indcol, const double *coef, nsk_csr_t *out)
@@ -94,7 +93,6 @@ NSK_API int nsk_csr_destroy(nsk_csr_t A)
     cudaStreamSynchronize(ctx->stream);
     nsk_dist_free(A);
     nsk_wave_free(A);
-    nsk_pipe_free(A);
     nsk_packed_free(A);
     nsk_sell_free(A);
     if (A->d_ptrow) cudaFree(A->d_ptrow);

@@ -6,21 +6,17 @@
 // every level equals k successive row-sequential products, which is what the exact modes
 // reproduce bit for bit (per-row nonzero order is never changed, only the schedule).
 //
-// Strategy 1 ("levels"): k launches of the streaming SpMV kernel back to back on one stream; the
-//   operator is re-read from HBM k times.
-// Strategy 3 ("level pipeline", default): see mpk_pipeline.cu -- one persistent launch, CTAs specialised by
-//   level, chained by completion counters with back-pressure so the window stays in L2.
-// Strategy 2 ("wavefront"): see mpk_wavefront.cu -- one persistent launch that sweeps row chunks in
-//   a skewed (chunk + level) order so that a chunk's col/val slice is still L2-resident (126 MB)
-//   when the next level needs it; HBM sees the operator once.
+// Strategy 1 ("levels"): k launches of the product kernel back to back on one stream; the operator is re-read from
+//   HBM k times.
+// Strategy 5 (default for operators made of pattern tiles -- stencils, regular bands): sell.cu, one persistent launch,
+//   CTAs specialised by level and chained by completion counters with window back-pressure so that the k - 1
+//   re-reads of every tile come from L2; coefficients staged by bulk copies, no per-entry column index.
+// Strategy 4 (default for other operators that pack -- block-banded FEM rows): packed.cu, the same level pipeline
+//   with whole tiles (coefficients, local columns, x runs) staged in shared memory.
+// (Strategies 2 and 3 of round 1 -- the skewed wavefront and the level pipeline over plain CSR with global gathers --
+// lost to k launches wherever they were measured and are gone.)
 #include "nsk_internal.h"
 
-int nsk_mpk_wavefront(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode,
-                      const int *level_rows);  // mpk_wavefront.cu
-bool nsk_mpk_wavefront_applicable(nsk_csr_t A, int k);
-int nsk_mpk_pipeline(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode,
-                     const int *level_rows);  // mpk_pipeline.cu
-bool nsk_mpk_pipeline_applicable(nsk_csr_t A, int k);
 int nsk_dist_mpk(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode);  // dist.cu
 
 int nsk_mpk_levels(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode,
@@ -40,8 +36,8 @@ int nsk_mpk_levels(nsk_csr_t A, int k, const double *d_x, double *const *d_level
     return NSK_OK;
 }
 
-// Picks the strategy: option mpk_kernel = 0 auto (4 when the operator packs, else 1), 1 levels, 2 wavefront, 3 level pipeline on
-// CSR, 4 level pipeline on the packed format (packed.cu).  A fused
+// Picks the strategy: option mpk_kernel = 0 auto, 1 levels, 4 level pipeline on the packed format (packed.cu), 5 level
+// pipeline on sliced-ELL tiles (sell.cu).  A fused
 // kernel that does not apply to the pattern (window larger than its L2 budget, long rows) degrades to k
 // launches -- still a GPU path.  level_rows: distributed slabs evaluate level l on a row prefix.
 int nsk_mpk_local(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode,
@@ -50,7 +46,9 @@ int nsk_mpk_local(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
     nsk_ctx_t ctx = A->ctx;
     int sel = (int)ctx->opt.mpk_kernel;
     const bool automatic = sel == 0;
-    if (automatic) sel = 4;
+    // default: the sliced-ELL level pipeline for operators made of pattern tiles (stencils, regular bands: staged
+    // coefficients, no per-entry index), else the packed one when the operator packs, else k products
+    if (automatic) sel = (k > 1 && nsk_sell_uniform(A)) ? 5 : 4;
     const bool sell = sel == 5 && k > 1 && nsk_sell_applicable(A);
     if (sel == 5 && !sell) sel = 4;
     if (sell || (sel == 4 && k > 1 && nsk_packed_applicable(A))) {
@@ -86,18 +84,6 @@ int nsk_mpk_local(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
         ctx->last_mpk = any_fused ? (sell ? 5 : 4) : 1;
         return NSK_OK;
     }
-    // the CSR level pipeline (3) and the wavefront kernel (2) stay explicit choices: with global gathers they lose to k
-    // launches of the streaming kernel wherever they were measured (256^3: 0.86 / 0.90 vs 0.98 ms before the packed
-    // format existed; RCM'd tet mesh k=8: 1.03 vs 0.30 ms, profiles/r01_configs.txt)
-    if (automatic) sel = 1;
-    if (sel == 3 && k > 1 && nsk_mpk_pipeline_applicable(A, k)) {
-        int s = nsk_mpk_pipeline(A, k, d_x, d_levels, mode, level_rows);
-        if (s != NSK_ERR_UNSUPPORTED) { ctx->last_mpk = 3; return s; }
-    }
-    if (sel == 2 && k > 1 && nsk_mpk_wavefront_applicable(A, k)) {
-        int s = nsk_mpk_wavefront(A, k, d_x, d_levels, mode, level_rows);
-        if (s != NSK_ERR_UNSUPPORTED) { ctx->last_mpk = 2; return s; }
-    }
     ctx->last_mpk = 1;
     return nsk_mpk_levels(A, k, d_x, d_levels, mode, level_rows);
 }
@@ -109,7 +95,8 @@ int nsk_mpk_local2(nsk_csr_t A, int k, const double *d_x, double *const *d_level
                    double *const *d_levels2, nsk_mode mode, const int *level_rows)
 {
     nsk_ctx_t ctx = A->ctx;
-    const int sel = (int)ctx->opt.mpk_kernel;
+    int sel = (int)ctx->opt.mpk_kernel;
+    if (sel == 0 && nsk_sell_uniform(A)) sel = 5;
     const bool sell = sel == 5 && nsk_sell_applicable(A);
     if (sell || ((sel == 0 || sel == 4 || sel == 5) && nsk_packed_applicable(A))) {
         int done = 0;

@@ -42,15 +42,14 @@ struct nsk_comm_s;  // comm.cpp
 
 struct nsk_options {
     int64_t spmv_kernel = 0;      // 0 auto (packed when applicable, else stream), 1 scalar (thread/row from global),
-                                  // 2 stream (CSR slices by TMA, x gathered from global), 3 packed (x runs staged too)
+                                  // 2 stream (CSR slices by TMA, x gathered from global), 3 packed (x runs staged too),
+                                  // 4 sliced-ELL tiles (sell.cu)
     int64_t packed_variant = 0;   // 0 default, else 1 + index into the packed kernel table
     int64_t spmv_ctas_per_sm = 0; // 0 = kernel default
-    int64_t mpk_kernel = 0;       // 0 auto (4 if the operator packs, else 1), 1 = k separate products, 2 = L2 wavefront,
-                                  // 3 = level pipeline on CSR, 4 = level pipeline on the packed format
-    int64_t pipe_variant = 0;     // 0 default, else 1 + index into the level-pipeline kernel table
+    int64_t mpk_kernel = 0;       // 0 auto (5 for operators made of pattern tiles, else 4 if the operator packs, else 1),
+                                  // 1 = k separate products, 4 = level pipeline on the packed format, 5 = on sliced-ELL tiles
     int64_t host_overlap = 1;     // host-pointer powers calls: copy level l out while level l+1.. are computed
     int64_t pk_flags = 1;         // packed kernel switches (see PkParams::flags); default 1: evict-first / streaming hints
-    int64_t packed_index = 0;     // 1: pack with index compression (blob format 1) and run the CIDX kernel instances (experimental)
     int64_t pk_timing = 0;        // 1: packed kernel records its stage cycle and prints per-level averages (debug)
     int64_t pipe_w0_pct = 0;      // share weight of level 0's team relative to 100 for every other level; 0 = default
     int64_t pipe_bp_global = -1;  // back-pressure of the packed level pipeline: 0 = level l held by l+1, 1 = level 0 held
@@ -58,9 +57,7 @@ struct nsk_options {
     int64_t pipe_interleave = 1;  // 1: level = blockIdx % k (each SM hosts every level), 0: level = blockIdx / team
     int64_t stream_exact_kind = 0; // exact modes of the stream kernel: 0 auto, 1 thread-per-row gathers, 2 gather to smem first
     int64_t stream_variant = 0;   // 0 auto, else 1 + index into the stream kernel table
-    int64_t wave_variant = 0;     // index into the wavefront kernel table
     int64_t wave_slack_pct = -1;  // extra level skew, % of (resident CTAs x stages / k) tiles; <0 = default 150
-    int64_t wave_static = 0;      // 1 = static round-robin schedule instead of dynamic claims
     int64_t wave_l2_pct = 0;      // share of L2 the wavefront window may occupy, %; 0 = default 80
     // sliced-ELL kernel (sell.cu)
     int64_t sell_chunk = 0;       // consecutive tiles a CTA takes per item; 0 = default (2 fused, 4 single product)
@@ -69,6 +66,8 @@ struct nsk_options {
     int64_t sell_flags = -1;      // < 0 default (3): bit 0 eviction / streaming hints, bit 1 L2 prefetch of level 0's tiles
     int64_t sell_pf_dist = 0;     // items ahead the L2 prefetch runs; 0 = default 2
     int64_t sell_rows = 0;        // streaming kernel: rows of a tile per consumer thread (0 = default 1, 2)
+    int64_t sell_tma = 0;         // all-pattern operators: coefficient stages per CTA of the staged kernel (0 = default 4,
+                                  // < 0 = use the register kernels)
     int64_t sell_stream = 0;      // all-pattern operators: tiles in flight per consumer thread (0 = default 3, < 0 = the
                                   // item-at-a-time kernel)
 };
@@ -81,8 +80,8 @@ struct nsk_ctx_s {
     cudaEvent_t copy_event[NSK_MAX_K] = {};  // (created on first use)
     cudaDeviceProp prop{};
     uint64_t launches = 0;
-    int last_spmv = 0;  // kernel family of the last product: 1 scalar, 2 stream (CSR), 3 packed
-    int last_mpk = 0;   // strategy of the last powers call: 1 levels, 2 wavefront, 3 CSR level pipeline, 4 packed level pipeline
+    int last_spmv = 0;  // kernel family of the last product: 1 scalar, 2 stream (CSR), 3 packed, 4 sliced-ELL tiles
+    int last_mpk = 0;   // strategy of the last powers call: 1 levels, 4 packed level pipeline, 5 sliced-ELL level pipeline
     std::string last_error;
     nsk_options opt;
     // scratch for reductions: partial sums + ticket + result slots (device) and pinned mirror
@@ -177,6 +176,7 @@ int nsk_sell_run(nsk_csr_t A, int k, const double *d_x, double *const *d_levels,
 int nsk_sell_run2(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, const double *d_x2,
                   double *const *d_levels2, nsk_mode mode, const int *level_rows);
 bool nsk_sell_applicable(nsk_csr_t A);
+bool nsk_sell_uniform(nsk_csr_t A);  // all tiles pattern tiles of one width (stencils, regular bands)
 size_t nsk_sell_bytes(nsk_csr_t A);
 void nsk_sell_free(nsk_csr_t A);
 int nsk_sell_check_error(nsk_csr_t A);

@@ -107,14 +107,8 @@ struct PkParams {
 // blob header (16 ints at the start of every blob)
 enum { PKH_ROW0 = 0, PKH_NROWS, PKH_WIDTH, PKH_RP, PKH_OFF_LENS, PKH_OFF_LCOL, PKH_OFF_VAL, PKH_FORMAT, PKH_OFF_BASE,
        PKH_WORDS = 16 };
-// PKH_FORMAT 0: explicit local columns, lcol u16[width][rp], lens[r] = row length.
-// PKH_FORMAT 1 (index compression; only in operators packed with it, only read by the CIDX kernel instances): the tile
-// has ONE column pattern -- slot e of row r references local column base[e] + r, true of every interior row of a stencil
-// or band -- and a row may lack some of the slots (line ends, domain faces): lens[r] is then the bit mask of the slots the
-// row has, its entries sit in those slots of val, and no per-entry index is stored at all.  Slots ascend with the row's
-// original entry order, so the fma chain is unchanged.  Tiles with a row that is not a sub-pattern, or wider than 8
-// slots, stay in format 0.  Layout: hdr | base s16[round_up(width, 8)] | masks u16[rp] | val f64[width][rp].
-constexpr int PK_MASK_SLOTS = 8;
+// PKH_FORMAT is always 0 (explicit local columns, lcol u16[width][rp], lens[r] = row length); the pattern-compressed
+// format of round 1 moved to sell.cu, where no per-entry index is stored at all.
 
 __host__ __device__ constexpr int pk_round_up(int v, int m) { return (v + m - 1) / m * m; }
 static inline int pk_blob_bytes(int nrows, int width)
@@ -123,49 +117,23 @@ static inline int pk_blob_bytes(int nrows, int width)
     return PKH_WORDS * 4 + 2 * rp + 2 * width * rp + 8 * width * rp;  // every term is a multiple of 16
 }
 
-static inline int pk_blob_bytes_indexed(int nrows, int width)
-{
-    const int rp = pk_round_up(nrows, 32);
-    return PKH_WORDS * 4 + 2 * pk_round_up(width, 8) + 2 * rp + 8 * width * rp;
-}
-
-// host-side decoding of either format: length of row r, local column / value of its entry e
+// host-side decoding of a blob: length of row r, local column / value of its entry e
 struct PkBlobView {
     const int *hdr;
     const unsigned short *lens, *lcol;
-    const short *base;  // signed: a run that starts at the tile's first row gives the "column r - 1" slot base -1
     const double *val;
-    int rp, fmt;
+    int rp;
     explicit PkBlobView(const unsigned char *b)
     {
         hdr = reinterpret_cast<const int *>(b);
         rp = hdr[PKH_RP];
-        fmt = hdr[PKH_FORMAT];
         lens = reinterpret_cast<const unsigned short *>(b + hdr[PKH_OFF_LENS]);
         lcol = reinterpret_cast<const unsigned short *>(b + hdr[PKH_OFF_LCOL]);
-        base = reinterpret_cast<const short *>(b + hdr[PKH_OFF_BASE]);
         val = reinterpret_cast<const double *>(b + hdr[PKH_OFF_VAL]);
     }
-    int slot(int e, int r) const  // slot of the row's e-th entry
-    {
-        if (!fmt) return e;
-        unsigned m = lens[r];
-        for (int s = 0; s < PK_MASK_SLOTS; s++)
-            if ((m >> s) & 1u) {
-                if (e == 0) return s;
-                e--;
-            }
-        return -1;
-    }
-    int len(int r) const
-    {
-        if (!fmt) return (int)lens[r];
-        int n = 0;
-        for (unsigned m = lens[r]; m; m &= m - 1) n++;
-        return n;
-    }
-    int col(int e, int r) const { return fmt ? (int)base[slot(e, r)] + r : (int)lcol[(size_t)e * rp + r]; }
-    double value(int e, int r) const { return val[(size_t)slot(e, r) * rp + r]; }
+    int len(int r) const { return (int)lens[r]; }
+    int col(int e, int r) const { return (int)lcol[(size_t)e * rp + r]; }
+    double value(int e, int r) const { return val[(size_t)e * rp + r]; }
 };
 
 __device__ __forceinline__ unsigned long long pk_now()
@@ -195,9 +163,7 @@ __device__ __forceinline__ int pk_wait_groups(const int *cnt, const int *need, i
     return w;
 }
 
-// CIDX = true: the consumers also understand blob format 1 (index compression, see PKH_FORMAT); operators packed with it
-// are only ever given to these instances.
-template <int T_ROWS, int BLOB_CAP, int XCAP, int STAGES, int NCW, int MINB, int RPT, int NV, bool MULADD, bool CIDX = false>
+template <int T_ROWS, int BLOB_CAP, int XCAP, int STAGES, int NCW, int MINB, int RPT, int NV, bool MULADD>
 __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkParams P)
 {
     static_assert(NV == 1 || NV == 2, "one or two right-hand sides");
@@ -431,59 +397,6 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
         const unsigned short *lcol = reinterpret_cast<const unsigned short *>(blob + hdr[PKH_OFF_LCOL]);
         const double *val = reinterpret_cast<const double *>(blob + hdr[PKH_OFF_VAL]);
         const double *xb = reinterpret_cast<const double *>(blob + BLOB_CAP);
-        bool masked = false;
-        if constexpr (CIDX) {
-            if (hdr[PKH_FORMAT]) {
-                // format 1: one pattern per tile (at most eight slots): the entry in slot u of row r multiplies
-                // x[base[u] + r]; no index is loaded, the row's mask says which slots it has.  A loop nest of its own,
-                // so that the slot bases are not live across the explicit-index loop below (register cap: 80 at 3 CTAs/SM).
-                masked = true;
-                const int4 bq = *reinterpret_cast<const int4 *>(blob + hdr[PKH_OFF_BASE]);  // eight signed 16-bit bases
-                const int bw[4] = {bq.x, bq.y, bq.z, bq.w};  // kept packed (two per register); unpacked at the point of use
-                for (int rb = 0; rb < nrows; rb += NCT * RPT) {
-#pragma unroll
-                    for (int q = 0; q < RPT; q++) {
-                        const int r = rb + q * NCT + tid;
-                        const bool have = r < nrows && row0 + r < row_end;
-                        const int m = have ? (int)lens[r] : 0;
-                        const double *xr = xb + r;
-                        const double *vr = val + r;
-                        double a0 = 0.0, a1 = 0.0;
-                        // two groups of four slots: eight loads in flight per group, then four links of the chain
-#pragma unroll
-                        for (int g = 0; g < 2; g++) {
-                            double xv[NV][4], av[4];
-#pragma unroll
-                            for (int u = 0; u < 4; u++) {
-                                const int e = 4 * g + u;
-                                const int b = (e & 1) ? (bw[e >> 1] >> 16) : (int)(short)(bw[e >> 1] & 0xffff);
-                                if ((m >> e) & 1) {
-#pragma unroll
-                                    for (int v = 0; v < NV; v++) xv[v][u] = xr[v * XCAP + b];
-                                    av[u] = vr[e * rp];
-                                }
-                            }
-#pragma unroll
-                            for (int u = 0; u < 4; u++)
-                                if ((m >> (4 * g + u)) & 1) {
-                                    a0 = row_op<MULADD>(av[u], xv[0][u], a0);
-                                    if (NV == 2) a1 = row_op<MULADD>(av[u], xv[NV - 1][u], a1);
-                                }
-                        }
-                        if (have) {
-                            if (stream_out) __stcs(dst + row0 + r, a0);
-                            else dst[row0 + r] = a0;
-                            if (NV == 2) {
-                                if (stream_out) __stcs(dst2 + row0 + r, a1);
-                                else dst2[row0 + r] = a1;
-                            }
-                            if (NV == 1 && P.dot_w) dot_acc = __fma_rn(P.dot_w[row0 + r], a0, dot_acc);
-                        }
-                    }
-                }
-            }
-        }
-        if (!masked)
         for (int rb = 0; rb < nrows; rb += NCT * RPT) {
             int len[RPT];
             double acc[NV][RPT];
@@ -607,22 +520,8 @@ typedef void (*pk_fn)(const PkParams);
 // Two right-hand sides per launch are built for one geometry: the default short-row one with two stages x two CTAs per
 // SM (a stage carries both vectors' x runs).  Other geometries run the vectors one after the other.
 constexpr int PK_NV2_VARIANT = 7;
-// Index-compression instances (option packed_index) exist for the default short-row geometry, one and two vectors.
-constexpr int PK_INDEXED_VARIANT = 7;
-static bool pk_has_indexed(int variant, int nv) { return nv == 2 ? variant == PK_NV2_VARIANT : variant == PK_INDEXED_VARIANT; }
-static pk_fn pk_lookup(int variant, bool muladd, int nv, int *smem, bool cidx = false)
+static pk_fn pk_lookup(int variant, bool muladd, int nv, int *smem)
 {
-    if (cidx) {
-        if (!pk_has_indexed(variant, nv)) return nullptr;
-        if (nv == 2) {
-            *smem = (21504 + 2 * 1536 * 8) * 2 + 2 * 2 * 8 + 64 * 8 + 2 * 32 + 2 * 4 + 128;
-            return muladd ? packed_kernel<256, 21504, 1536, 2, 4, 2, 1, 2, true, true>
-                          : packed_kernel<256, 21504, 1536, 2, 4, 2, 1, 2, false, true>;
-        }
-        *smem = (21504 + 1536 * 8) * 2 + 2 * 2 * 8 + 64 * 8 + 2 * 32 + 2 * 4 + 128;
-        return muladd ? packed_kernel<256, 21504, 1536, 2, 4, 3, 1, 1, true, true>
-                      : packed_kernel<256, 21504, 1536, 2, 4, 3, 1, 1, false, true>;
-    }
     if (nv == 2) {
         if (variant != PK_NV2_VARIANT) return nullptr;
         *smem = (21504 + 2 * 1536 * 8) * 2 + 2 * 2 * 8 + 64 * 8 + 2 * 32 + 2 * 4 + 128;
@@ -671,7 +570,6 @@ struct PkLevelPlan {
 
 struct PackedOp {
     int t_rows = 0, blob_cap = 0, xcap = 0;
-    bool indexed = false;  // packed with index compression (read by the CIDX kernel instances only)
     bool ok = false;
     std::string why;
     int ntiles = 0;
@@ -766,8 +664,7 @@ struct PackedHost {
 };
 
 static std::string pk_pack_host(int n, int n_cols, int64_t nnz, const int *ptrow, const int *indcol, const double *coef,
-                                const std::vector<int> &breaks, int t_rows, int blob_cap, int xcap, PackedHost &out,
-                                bool index_compress = false)
+                                const std::vector<int> &breaks, int t_rows, int blob_cap, int xcap, PackedHost &out)
 {
     if (n == 0 || nnz == 0) return "empty operator";
     // 1. tiles: up to t_rows consecutive rows, never across a break, blob within the stage
@@ -804,8 +701,6 @@ static std::string pk_pack_host(int n, int n_cols, int64_t nnz, const int *ptrow
 
     std::vector<PkTile> &ptiles = out.ptiles;
     ptiles.assign(ntiles, PkTile());
-    std::vector<char> indexed_tile(ntiles, 0);   // 1: the tile is stored in format 1 (one pattern + per-row slot masks)
-    std::vector<std::vector<int>> bases(index_compress ? ntiles : 0);
     std::atomic<int> failed(0);
     struct Runs {
         int nseg, start[PK_MAXSEG], end[PK_MAXSEG], off[PK_MAXSEG];
@@ -847,51 +742,19 @@ static std::string pk_pack_host(int n, int n_cols, int64_t nnz, const int *ptrow
         for (auto &x : th) x.join();
     };
 
-    // 2. per tile: column runs; with index compression also the slot bases and the exception rows (decides the size)
+    // 2. per tile: column runs
     parallel([&](int t) {
         const nsk_tile &tl = tiles[t];
         PkTile &pt = ptiles[t];
         std::vector<int> cols(indcol + tl.nz0, indcol + tl.nz1);
         if (!pk_segments(cols, n_cols, xcap, pt)) { failed.store(1); return; }
         pt.row0 = tl.row0; pt.nrows = tl.nrows;
-        if (!index_compress) return;
-        const int width = widths[t];
-        if (width == 0 || width > PK_MASK_SLOTS) return;
-        const Runs R(pt);
-        // the pattern: the first row of full width; base[e] = its local column in slot e minus its row number
-        int rref = -1;
-        for (int r = 0; r < tl.nrows && rref < 0; r++)
-            if (ptrow[tl.row0 + r + 1] - ptrow[tl.row0 + r] == width) rref = r;
-        std::vector<int> base(width);
-        {
-            int sg = 0;
-            const int p = ptrow[tl.row0 + rref];
-            for (int e = 0; e < width; e++) {
-                base[e] = local_col(pt, R, indcol[p + e], sg) - rref;
-                if (base[e] < -32768 || base[e] > 32767) return;  // not expressible: the tile keeps explicit indices
-            }
-        }
-        // every row must be a sub-pattern: its entries, in order, match slots of ascending index
-        for (int r = 0; r < tl.nrows; r++) {
-            const int p = ptrow[tl.row0 + r], q = ptrow[tl.row0 + r + 1];
-            int sg = 0, e = 0;
-            for (int j = p; j < q; j++) {
-                const int lc = local_col(pt, R, indcol[j], sg);
-                while (e < width && base[e] + r != lc) e++;
-                if (e == width) return;
-                e++;
-            }
-        }
-        if (pk_blob_bytes_indexed(tl.nrows, width) >= pk_blob_bytes(tl.nrows, width)) return;
-        indexed_tile[t] = 1;
-        bases[t].swap(base);
     });
     if (failed.load()) return "a tile references x in too many / too long runs";
 
     std::vector<size_t> off(ntiles + 1, 0);
     for (int t = 0; t < ntiles; t++)
-        off[t + 1] = off[t] + (size_t)(indexed_tile[t] ? pk_blob_bytes_indexed(tiles[t].nrows, widths[t])
-                                                       : pk_blob_bytes(tiles[t].nrows, widths[t]));
+        off[t + 1] = off[t] + (size_t)pk_blob_bytes(tiles[t].nrows, widths[t]);
 
     // 3. the blobs, slot-major
     std::vector<unsigned char> &blobs = out.blobs;
@@ -900,46 +763,29 @@ static std::string pk_pack_host(int n, int n_cols, int64_t nnz, const int *ptrow
         const nsk_tile &tl = tiles[t];
         PkTile &pt = ptiles[t];
         const int width = widths[t], rp = pk_round_up(tl.nrows, 32);
-        const bool indexed = indexed_tile[t] != 0;
         pt.blob_off = (long long)off[t];
         pt.blob_bytes = (int)(off[t + 1] - off[t]);
         unsigned char *b = blobs.data() + off[t];
         int *hdr = reinterpret_cast<int *>(b);
         const int off_base = PKH_WORDS * 4;
-        const int off_lens = off_base + (indexed ? 2 * pk_round_up(width, 8) : 0);
+        const int off_lens = off_base;
         const int off_lcol = off_lens + 2 * rp;
-        const int off_val = off_lcol + (indexed ? 0 : 2 * width * rp);
+        const int off_val = off_lcol + 2 * width * rp;
         hdr[PKH_ROW0] = tl.row0; hdr[PKH_NROWS] = tl.nrows; hdr[PKH_WIDTH] = width; hdr[PKH_RP] = rp;
         hdr[PKH_OFF_LENS] = off_lens; hdr[PKH_OFF_LCOL] = off_lcol; hdr[PKH_OFF_VAL] = off_val;
-        hdr[PKH_FORMAT] = indexed ? 1 : 0; hdr[PKH_OFF_BASE] = indexed ? off_base : 0;
+        hdr[PKH_FORMAT] = 0; hdr[PKH_OFF_BASE] = 0;
         unsigned short *lens = reinterpret_cast<unsigned short *>(b + off_lens);
         unsigned short *lcol = reinterpret_cast<unsigned short *>(b + off_lcol);
-        short *bs = reinterpret_cast<short *>(b + off_base);
         double *val = reinterpret_cast<double *>(b + off_val);
         const Runs R(pt);
-        if (indexed)
-            for (int e = 0; e < width; e++) bs[e] = (short)bases[t][e];
         for (int r = 0; r < tl.nrows; r++) {
             const int p = ptrow[tl.row0 + r], q = ptrow[tl.row0 + r + 1];
             int sg = 0;
-            if (!indexed) {
-                lens[r] = (unsigned short)(q - p);
-                for (int j = p; j < q; j++) {
-                    lcol[(size_t)(j - p) * rp + r] = (unsigned short)local_col(pt, R, indcol[j], sg);
-                    val[(size_t)(j - p) * rp + r] = coef[j];
-                }
-                continue;
-            }
-            unsigned mask = 0;
-            int e = 0;
+            lens[r] = (unsigned short)(q - p);
             for (int j = p; j < q; j++) {
-                const int lc = local_col(pt, R, indcol[j], sg);
-                while (bases[t][e] + r != lc) e++;  // phase 2 proved that a slot matches
-                mask |= 1u << e;
-                val[(size_t)e * rp + r] = coef[j];
-                e++;
+                lcol[(size_t)(j - p) * rp + r] = (unsigned short)local_col(pt, R, indcol[j], sg);
+                val[(size_t)(j - p) * rp + r] = coef[j];
             }
-            lens[r] = (unsigned short)mask;
         }
     });
     if (failed.load()) return "a tile references x in too many / too long runs";
@@ -947,15 +793,15 @@ static std::string pk_pack_host(int n, int n_cols, int64_t nnz, const int *ptrow
     return "";
 }
 
-static PackedOp *pk_get(nsk_csr_t A, const PkVariant &V, bool indexed = false)
+static PackedOp *pk_get(nsk_csr_t A, const PkVariant &V)
 {
     g_packed_mu.lock();
     std::vector<PackedOp *> &ops = g_packed[A];
     g_packed_mu.unlock();
     for (PackedOp *op : ops)
-        if (op->t_rows == V.t_rows && op->blob_cap == V.blob_cap && op->xcap == V.xcap && op->indexed == indexed) return op;
+        if (op->t_rows == V.t_rows && op->blob_cap == V.blob_cap && op->xcap == V.xcap) return op;
     PackedOp *op = new PackedOp();
-    op->t_rows = V.t_rows; op->blob_cap = V.blob_cap; op->xcap = V.xcap; op->indexed = indexed;
+    op->t_rows = V.t_rows; op->blob_cap = V.blob_cap; op->xcap = V.xcap;
     ops.push_back(op);
     const int n = A->n;
     const std::vector<int> &ptrow = nsk_csr_host_ptrow(A);
@@ -972,7 +818,7 @@ static PackedOp *pk_get(nsk_csr_t A, const PkVariant &V, bool indexed = false)
     }
     PackedHost H;
     op->why = pk_pack_host(n, A->n_cols, A->nnz, ptrow.data(), indcol.data(), coef.data(), A->breaks, V.t_rows, V.blob_cap,
-                           V.xcap, H, indexed);
+                           V.xcap, H);
     if (!op->why.empty()) return op;
     const int ntiles = (int)H.tiles.size();
     if (cudaMalloc(&op->d_blobs, H.blobs.size()) != cudaSuccess ||
@@ -1132,7 +978,7 @@ struct nsk_packed_host_s {
 };
 
 static int pk_host_create(int n, int n_cols, int64_t nnz, const int *ptrow, const int *indcol, const double *coef,
-                          int variant, bool index_compress, void **out)
+                          int variant, void **out)
 {
     if (!out || !ptrow || (nnz > 0 && (!indcol || !coef))) return NSK_ERR_INVALID;
     if (variant < 0 || variant >= g_npkv) return NSK_ERR_INVALID;
@@ -1140,8 +986,7 @@ static int pk_host_create(int n, int n_cols, int64_t nnz, const int *ptrow, cons
     h->n = n;
     h->n_cols = n_cols;
     const PkVariant &V = g_pkv[variant];
-    h->why = pk_pack_host(n, n_cols, nnz, ptrow, indcol, coef, std::vector<int>(), V.t_rows, V.blob_cap, V.xcap, h->H,
-                          index_compress);
+    h->why = pk_pack_host(n, n_cols, nnz, ptrow, indcol, coef, std::vector<int>(), V.t_rows, V.blob_cap, V.xcap, h->H);
     *out = h;
     return NSK_OK;
 }
@@ -1149,32 +994,7 @@ static int pk_host_create(int n, int n_cols, int64_t nnz, const int *ptrow, cons
 NSK_API int nsk_pack_host_create(int n, int n_cols, int64_t nnz, const int *ptrow, const int *indcol, const double *coef,
                                  int variant, void **out)
 {
-    return pk_host_create(n, n_cols, nnz, ptrow, indcol, coef, variant, false, out);
-}
-
-// The same with index compression (blob format 1 where a tile allows it; option packed_index on the GPU path).
-NSK_API int nsk_pack_host_create_indexed(int n, int n_cols, int64_t nnz, const int *ptrow, const int *indcol,
-                                         const double *coef, int variant, void **out)
-{
-    return pk_host_create(n, n_cols, nnz, ptrow, indcol, coef, variant, true, out);
-}
-
-// Tiles stored in the compressed-index format / rows in them that lack some slot of their tile's pattern (0 / 0 for a
-// plain pack).
-NSK_API int nsk_pack_host_index_stats(void *handle, int64_t *tiles_indexed, int64_t *exception_rows)
-{
-    nsk_packed_host_s *h = static_cast<nsk_packed_host_s *>(handle);
-    if (!h->why.empty()) return NSK_ERR_UNSUPPORTED;
-    int64_t ti = 0, ex = 0;
-    for (const PkTile &pt : h->H.ptiles) {
-        const PkBlobView B(h->H.blobs.data() + pt.blob_off);
-        if (!B.fmt) continue;
-        ti++;
-        for (int r = 0; r < pt.nrows; r++) ex += B.len(r) != B.hdr[PKH_WIDTH];  // rows that lack slots of the pattern
-    }
-    if (tiles_indexed) *tiles_indexed = ti;
-    if (exception_rows) *exception_rows = ex;
-    return NSK_OK;
+    return pk_host_create(n, n_cols, nnz, ptrow, indcol, coef, variant, out);
 }
 
 NSK_API const char *nsk_pack_host_why(void *handle) { return static_cast<nsk_packed_host_s *>(handle)->why.c_str(); }
@@ -1299,12 +1119,11 @@ NSK_API long long nsk_pack_host_simulate(void *handle, int k, int lead_slack_til
 
 NSK_API void nsk_pack_host_destroy(void *handle) { delete static_cast<nsk_packed_host_s *>(handle); }
 
-static int pk_launch_shape(nsk_ctx_t ctx, int variant, bool muladd, int k, int nv, pk_fn *fn_out, int *smem_out, int *team,
-                           bool cidx = false)
+static int pk_launch_shape(nsk_ctx_t ctx, int variant, bool muladd, int k, int nv, pk_fn *fn_out, int *smem_out, int *team)
 {
     const PkVariant &V = g_pkv[variant];
     int smem = 0;
-    pk_fn fn = pk_lookup(variant, muladd, nv, &smem, cidx);
+    pk_fn fn = pk_lookup(variant, muladd, nv, &smem);
     if (!fn) {
         nsk_set_error(ctx, "packed path: no two-vector kernel for this tile geometry");
         return NSK_ERR_UNSUPPORTED;
@@ -1452,12 +1271,10 @@ static int pk_run(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
             nsk_set_error(ctx, "packed path: output is not 16-byte aligned");
             return NSK_ERR_UNSUPPORTED;
         }
-    // index compression (option packed_index, experimental): its own packed copy of the operator, its own kernel instances
-    const bool indexed = ctx->opt.packed_index && pk_has_indexed(variant, nv);
-    PackedOp *op = pk_get(A, V, indexed);
+    PackedOp *op = pk_get(A, V);
     if (!op->ok) { nsk_set_error(ctx, "packed path not applicable: %s", op->why.c_str()); return NSK_ERR_UNSUPPORTED; }
     pk_fn fn; int smem = 0, team = 0;
-    NSK_TRY(pk_launch_shape(ctx, variant, mode == NSK_EXACT_MULADD, k, nv, &fn, &smem, &team, indexed));
+    NSK_TRY(pk_launch_shape(ctx, variant, mode == NSK_EXACT_MULADD, k, nv, &fn, &smem, &team));
     if (team < k) { nsk_set_error(ctx, "packed path: fewer resident CTAs than levels"); return NSK_ERR_UNSUPPORTED; }
     const char *why = "";
     PkLevelPlan *plan = pk_level_plan(A, op, k, level_rows, team, nv, &why);

@@ -808,6 +808,324 @@ static SlLaunch sl_lookup_stream(int nv, int w, int depth, int rows)
     return L;
 }
 
+// ---- staged-coefficient kernel (operators made of pattern tiles of one width W) ------------------------------------
+// The coefficients of a tile are ONE contiguous block (mask + W x 256 doubles): a producer lane streams them into a
+// shared-memory ring with 1-D bulk copies (TMA, SASS UBLKCP) as soon as a stage is free -- they depend on no other CTA,
+// so their HBM / L2 latency is hidden by the ring, not by registers.  Consumer threads (one row each, many warps) only
+// hold the row's x entries in flight: W ordinary cached loads issued the moment the item's inputs are complete, then the
+// chain with coefficients read from the stage.  Per row and level the shared-memory / L1 data path carries the
+// coefficients twice (bulk write + read) and x once -- against coefficients, local columns AND x twice in packed.cu.
+constexpr int SLT_NCW = SL_ROWS / 32;            // consumer warps: thread t owns row t of every tile
+constexpr int SLT_THREADS = SL_ROWS + 64;        // + dependency warp + service warp (producer and publisher)
+
+template <int NV, int W, int NS, int MINB>
+__global__ void __launch_bounds__(SLT_THREADS, MINB) sell_tma_kernel(const SlParams P)
+{
+    static_assert(W >= 1 && W <= SL_PSLOTS, "pattern width");
+    constexpr int STAGE = SL_ROWS + 8 * W * SL_ROWS;  // == sl_blob_bytes_pattern(W), a multiple of 128
+    extern __shared__ __align__(128) unsigned char stages[];  // NS stages
+    __shared__ uint64_t s_full[NS];           // the stage's tile has landed (bulk copy complete_tx)
+    __shared__ unsigned int s_free[NS];       // consumer warps that finished the stage's tile, counted over the launch
+    __shared__ __align__(16) int s_desc[SL_RING][SL_MAXCHUNK * 16];
+    __shared__ int s_hdr[SL_RING][2];
+    __shared__ uint64_t s_ready[SL_RING];     // item's inputs complete + descriptors in place
+    __shared__ unsigned int s_fin[SL_RING];   // consumer warps that finished the slot's item, counted over the launch
+    __shared__ double s_red[SLT_NCW];
+    __shared__ SlCta s_cta;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+    const int lane = tid & 31;
+    const int2 role = __ldg(P.cta_role + blockIdx.x);
+    const int level = role.x;
+    const int c = role.y;
+    const int G = P.team[level];
+    const int count = P.count[level];
+    const int n_my = c < count ? (count - c + G - 1) / G : 0;
+    const int M = P.chunk;
+    const int ntl = P.ntl[level];
+    if (tid == 0) {
+        for (int s = 0; s < SL_RING; s++) {
+            mbar_init(&s_ready[s], 1);
+            s_fin[s] = 0u;
+        }
+        for (int s = 0; s < NS; s++) {
+            mbar_init(&s_full[s], 1);
+            s_free[s] = 0u;
+        }
+        fence_mbar_init();
+        s_cta.src[0] = level == 0 ? P.x : P.levels[level - 1];
+        s_cta.src[1] = NV == 2 ? (level == 0 ? P.x2 : P.levels2[level - 1]) : nullptr;
+        s_cta.dst[0] = P.levels[level];
+        s_cta.dst[1] = NV == 2 ? P.levels2[level] : nullptr;
+        s_cta.row_end = P.level_rows[level];
+        s_cta.last = ((P.flags & 1) && level == P.k - 1) ? 1 : 0;
+        s_cta.muladd = P.muladd;
+    }
+    __syncthreads();
+
+    if (warp == SLT_NCW + 1) {
+        // ===== service warp, two duties polled in turn (neither ever blocks the other):
+        //  producer  -- tile n of the CTA's stream (items in order, tiles in order) goes to stage n % NS as soon as every
+        //               consumer warp has finished the tile NS back;
+        //  publisher -- (k > 1) one gpu-scope fence for everything found finished at that moment, then one RED per item.
+        //               Consumers bump s_fin[slot] with release.cta after their stores; the acquire here + fence + RED is
+        //               cumulative over those stores. =====
+        const long long *tl8 = reinterpret_cast<const long long *>(P.ltiles[level]);  // word pair 0 of a tile = blob offset
+        const int *itw = reinterpret_cast<const int *>(P.items[level]);
+        int *cnt = P.counters + (size_t)level * P.ngroups;
+        const bool last_reader = (P.flags & 1) && level == P.k - 1;
+        const uint64_t pol = policy_evict_first();
+        int total = 0;  // tiles of the stream: only the level's very last item is short
+        if (n_my > 0) {
+            const long long t_last = ((long long)c + (long long)(n_my - 1) * G) * M;
+            total = (n_my - 1) * M + (int)min((long long)M, (long long)ntl - t_last);
+        }
+        const int n_pub = P.k > 1 ? n_my : 0;
+        long long off_l = 0;  // lane u: blob offset of tile (n & ~31) + u
+        int grp = 0;          // lane u: group of item (ip & ~31) + u
+        int n = 0, ip = 0, off_base = -1, grp_base = -1;
+        unsigned long long t_idle = 0;
+        while (n < total || ip < n_pub) {
+            bool progress = false;
+            if (n < total) {
+                const int st = n % NS;
+                const bool ok = n < NS || ld_acquire_cta_shared_u32(&s_free[st]) >= (unsigned int)SLT_NCW * (unsigned int)(n / NS);
+                if (ok) {
+                    if ((n & ~31) != off_base) {
+                        off_base = n & ~31;
+                        const int nn = off_base + lane;
+                        off_l = 0;
+                        if (nn < total) {
+                            const long long it = nn / M, j = nn - it * M;
+                            off_l = __ldg(tl8 + (((long long)c + it * G) * M + j) * 8);
+                        }
+                    }
+                    const long long off = __shfl_sync(0xffffffffu, off_l, n & 31);
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(&s_full[st], (uint32_t)STAGE);
+                        if (last_reader) bulk_g2s_hint(stages + (size_t)st * STAGE, P.blobs + off, (uint32_t)STAGE, &s_full[st], pol);
+                        else bulk_g2s(stages + (size_t)st * STAGE, P.blobs + off, (uint32_t)STAGE, &s_full[st]);
+                    }
+                    ++n;
+                    progress = true;
+                }
+            }
+            if (ip < n_pub) {
+                int nf = 0;  // consecutive finished items (at most to the end of this batch of 32)
+                while (ip + nf < n_pub && nf < SL_RING && (nf == 0 || ((ip + nf) & 31) != 0) &&
+                       ld_acquire_cta_shared_u32(&s_fin[(ip + nf) % SL_RING]) >= (unsigned int)SLT_NCW * (unsigned int)((ip + nf) / SL_RING + 1))
+                    ++nf;
+                if (nf > 0) {
+                    if ((ip & ~31) != grp_base) {
+                        grp_base = ip & ~31;
+                        grp = 0;
+                        if (grp_base + lane < n_pub) grp = __ldg(itw + ((long long)c + (long long)(grp_base + lane) * G) * 8);
+                    }
+                    if (lane == 0) __threadfence();
+                    __syncwarp();
+                    for (int u = 0; u < nf; u++) {
+                        const int g = __shfl_sync(0xffffffffu, grp, (ip + u) & 31);
+                        if (lane == 0) red_relaxed_gpu_add(cnt + g, 1);
+                    }
+                    ip += nf;
+                    progress = true;
+                }
+            }
+            if (progress) {
+                t_idle = 0;
+            } else {
+                __nanosleep(100);
+                const unsigned long long t = sl_now();
+                if (t_idle == 0) t_idle = t;
+                else if (t - t_idle > SL_TIMEOUT_NS) {
+                    if (lane == 0) *P.error = 1;
+                    return;
+                }
+            }
+        }
+        return;
+    }
+
+    if (warp == SLT_NCW) {
+        // ===== dependency warp: per item, in order -- descriptors, forward dependencies and back-pressure, ring slot =====
+        const int *itw = reinterpret_cast<const int *>(P.items[level]);
+        const int4 *tl4 = reinterpret_cast<const int4 *>(P.ltiles[level]);
+        const bool fwd = level > 0;
+        const bool back = level == 0 && P.bp_level > 0;
+        const int *cnt_f = P.counters + (size_t)(fwd ? level - 1 : 0) * P.ngroups;
+        const int *need_f = P.group_size + (size_t)(fwd ? level - 1 : 0) * P.ngroups;
+        const int *cnt_b = P.counters + (size_t)(back ? P.bp_level : 0) * P.ngroups;
+        const int *need_b = P.group_size + (size_t)(back ? P.bp_level : 0) * P.ngroups;
+        int wf = 0, wb = 0;
+        bool broken = false;
+        // software pipeline over the items: the words and descriptors of item it + 1 are fetched while item it waits
+        int iw_n = 0;
+        int4 dq_n = make_int4(0, 0, 0, 0);
+        auto fetch = [&](int it, int &iw, int4 &dq) {
+            const long long i = (long long)c + (long long)it * G;
+            iw = 0;
+            if (lane < 8) iw = __ldg(itw + i * 8 + lane);
+            const long long t0 = i * M;
+            const int ntile = (int)min((long long)M, (long long)ntl - t0);
+            dq = make_int4(0, 0, 0, 0);
+            if (lane < 4 * ntile) dq = __ldg(tl4 + t0 * 4 + lane);
+        };
+        if (n_my > 0) fetch(0, iw_n, dq_n);
+        for (int it = 0; it < n_my; ++it) {
+            const int iw = iw_n;
+            const int4 dq = dq_n;
+            if (it + 1 < n_my) fetch(it + 1, iw_n, dq_n);
+            const long long t0 = ((long long)c + (long long)it * G) * M;
+            const int ntile = (int)min((long long)M, (long long)ntl - t0);
+            const int s = it % SL_RING;
+            const int ghi = __shfl_sync(0xffffffffu, iw, 1);
+            const int gback = __shfl_sync(0xffffffffu, iw, 2);
+            if (!broken) {
+                if (back && gback >= wb) wb = sl_wait_groups(cnt_b, need_b, P.epoch, P.ngroups, wb, gback, lane);
+                if (fwd && ghi >= wf && wb >= 0) wf = sl_wait_groups(cnt_f, need_f, P.epoch, P.ngroups, wf, ghi, lane);
+                if (wb < 0 || wf < 0) broken = true;
+            }
+            if (it >= SL_RING && !broken) {
+                const unsigned int need = (unsigned int)SLT_NCW * (unsigned int)(it / SL_RING);
+                unsigned long long t1 = 0;
+                while (ld_acquire_cta_shared_u32(&s_fin[s]) < need) {
+                    __nanosleep(100);
+                    const unsigned long long t = sl_now();
+                    if (t1 == 0) t1 = t;
+                    else if (t - t1 > SL_TIMEOUT_NS) { broken = true; break; }
+                }
+            }
+            if (broken && lane == 0) *P.error = 1;
+            if (lane < 4 * SL_MAXCHUNK) reinterpret_cast<int4 *>(s_desc[s])[lane] = dq;
+            if (lane == 0) s_hdr[s][0] = ntile;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_ready[s]);  // release.cta: descriptors + everything acquired above
+        }
+        return;
+    }
+
+    // ===== consumer warps: thread t owns row t of every tile; only the row's x entries are loads in flight =====
+    const int t = tid;
+    const int cmax = P.n_cols - 1;
+    const double *val = reinterpret_cast<const double *>(stages + SL_ROWS) + t;
+    double dot_acc = 0.0;
+    int st = 0;
+    uint32_t ph = 0;  // stage of the next tile, parity of its completion
+    for (int it = 0; it < n_my; ++it) {
+        const int slot = it % SL_RING;
+        mbar_wait(&s_ready[slot], (it / SL_RING) & 1);
+        const int ntile = s_hdr[slot][0];
+        for (int j = 0; j < ntile; ++j) {
+            const int *d = s_desc[slot] + 16 * j;
+            const int2 q = *reinterpret_cast<const int2 *>(d + 2);  // row0, nrows
+            const int4 r0 = *reinterpret_cast<const int4 *>(d + 8), r1 = *reinterpret_cast<const int4 *>(d + 12);
+            const int rel[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+            const int row = q.x + t;
+            const int rowc = min(row, cmax);
+            mbar_wait(&s_full[st], ph);
+            const unsigned int m = stages[(size_t)st * STAGE + t];
+            const double *src = s_cta.src[0];
+            const double *src2 = NV == 2 ? s_cta.src[1] : nullptr;
+            double xv[NV][W];
+#pragma unroll
+            for (int e = 0; e < W; e++) {
+                const int idx = rowc + ((m & (1u << e)) ? rel[e] : 0);  // a slot the row lacks reads its own x entry
+                xv[0][e] = sl_ld_x(src + idx);
+                if (NV == 2) xv[NV - 1][e] = sl_ld_x(src2 + idx);
+            }
+            const double *vs = val + (size_t)st * (STAGE / 8);
+            double acc0 = 0.0, acc1 = 0.0;
+            if (s_cta.muladd) {
+#pragma unroll
+                for (int e = 0; e < W; e++)
+                    if (m & (1u << e)) {
+                        const double a = vs[e * SL_ROWS];
+                        acc0 = row_op<true>(a, xv[0][e], acc0);
+                        if (NV == 2) acc1 = row_op<true>(a, xv[NV - 1][e], acc1);
+                    }
+            } else {
+#pragma unroll
+                for (int e = 0; e < W; e++)
+                    if (m & (1u << e)) {
+                        const double a = vs[e * SL_ROWS];
+                        acc0 = row_op<false>(a, xv[0][e], acc0);
+                        if (NV == 2) acc1 = row_op<false>(a, xv[NV - 1][e], acc1);
+                    }
+            }
+            if (t < q.y && row < s_cta.row_end) sl_store_row<NV>(P, s_cta, row, acc0, acc1, dot_acc);
+            __syncwarp();
+            if (lane == 0) red_release_cta_shared_add(&s_free[st], 1u);  // the stage may be refilled
+            if (++st == NS) {
+                st = 0;
+                ph ^= 1u;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) red_release_cta_shared_add(&s_fin[slot], 1u);  // the slot may be reused and the item published
+    }
+
+    if (P.dot_w) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dot_acc += __shfl_xor_sync(0xffffffffu, dot_acc, o);
+        if (lane == 0) s_red[warp] = dot_acc;
+        named_bar_sync(2, SL_ROWS);
+        if (warp == 0) {
+            __shared__ bool is_last;
+            if (lane == 0) {
+                double sum = 0.0;
+                for (int w = 0; w < SLT_NCW; w++) sum += s_red[w];
+                P.partials[blockIdx.x] = sum;
+                __threadfence();
+                const unsigned int ticket = atomicAdd(P.ticket, 1u);
+                is_last = (ticket == gridDim.x - 1);
+            }
+            __syncwarp();
+            if (is_last) {
+                __threadfence();
+                double sum = 0.0;
+                for (int b = lane; b < (int)gridDim.x; b += 32) sum += ld_cg_f64(P.partials + b);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                if (lane == 0) {
+                    *P.dot_out = sum;
+                    *P.ticket = 0u;
+                }
+            }
+        }
+    }
+}
+
+template <int NV, int NS, int MINB>
+static sl_fn sl_lookup_tma_w(int w, int *stage_bytes)
+{
+    *stage_bytes = SL_ROWS + 8 * w * SL_ROWS;
+    switch (w) {
+    case 1: return sell_tma_kernel<NV, 1, NS, MINB>;
+    case 2: return sell_tma_kernel<NV, 2, NS, MINB>;
+    case 3: return sell_tma_kernel<NV, 3, NS, MINB>;
+    case 4: return sell_tma_kernel<NV, 4, NS, MINB>;
+    case 5: return sell_tma_kernel<NV, 5, NS, MINB>;
+    case 6: return sell_tma_kernel<NV, 6, NS, MINB>;
+    case 7: return sell_tma_kernel<NV, 7, NS, MINB>;
+    case 8: return sell_tma_kernel<NV, 8, NS, MINB>;
+    }
+    return nullptr;
+}
+// stages per CTA: 3 (four CTAs of 48 registers per SM) or 4 (three CTAs of 64 registers); two right-hand sides: 3 CTAs
+static SlLaunch sl_lookup_tma(int nv, int w, int ns, int *smem)
+{
+    SlLaunch L;
+    L.threads = SLT_THREADS;
+    L.launch_regs = 0;  // no register hand-over in this kernel
+    int sb = 0;
+    if (nv == 2) { L.fn = sl_lookup_tma_w<2, 3, 3>(w, &sb); ns = 3; }
+    else if (ns >= 4) { L.fn = sl_lookup_tma_w<1, 4, 3>(w, &sb); ns = 4; }
+    else { L.fn = sl_lookup_tma_w<1, 3, 4>(w, &sb); ns = 3; }
+    *smem = sb * ns;
+    return L;
+}
+
 // -----------------------------------------------------------------------------------------------
 // host side: tiling + pattern detection + blobs
 // -----------------------------------------------------------------------------------------------
@@ -1446,7 +1764,7 @@ static int sl_plan_chunk(nsk_ctx_t ctx, int nv, bool stream)
 {
     int chunk = (int)ctx->opt.sell_chunk;
     const int cap = stream ? SL_MAXCHUNK : sl_max_chunk(nv);
-    if (chunk <= 0) chunk = stream ? 2 : cap;
+    if (chunk <= 0) chunk = stream ? 4 : cap;
     return std::max(1, std::min(chunk, cap));
 }
 
@@ -1483,7 +1801,8 @@ static SlPlan *sl_plan(nsk_csr_t A, SellOp *op, int k, const int *level_rows, in
         // stay L2-resident is (k-1) * lead tiles of blobs plus the level vectors over it; by default the slack is
         // whatever the L2 budget allows.
         const double tile_bytes = (double)op->blob_bytes / ntiles + 8.0 * SL_ROWS * (k + 1) * nv;
-        const double budget = (l2_pct > 0 ? (double)l2_pct : 70.0) / 100.0 * (double)ctx->prop.l2CacheSize;
+        // budget: 88 % of L2 by default (256^3, k = 4: 0.583 ms at 80 %, 0.553 at 90 %, 0.560 at 100 %, 0.581 at 110 %)
+        const double budget = (l2_pct > 0 ? (double)l2_pct : 88.0) / 100.0 * (double)ctx->prop.l2CacheSize;
         const int lead_min = D.reach + 1 + WF_GROUP + chunk;
         if (lead_pct >= 0)
             p.lead = lead_min + (int)((double)lead_pct / 100.0 * 2.0 * (resident / k) * chunk + 0.999);
@@ -1568,9 +1887,16 @@ static int sl_run(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
     const int depth = ctx->opt.sell_stream == 0 ? 3 : (int)ctx->opt.sell_stream;
     const bool stream = op->uniform_width > 0 && depth >= 2;
     const int rows = ctx->opt.sell_rows == 2 ? 2 : 1;
-    const SlLaunch L = stream ? sl_lookup_stream(nv, op->uniform_width, depth, rows) : sl_lookup(nv, sl_plan_chunk(ctx, nv, false));
+    // all-pattern operators, default: coefficients staged by bulk copies (option sell_tma: 0 = default 4 stages, n = n
+    // stages, < 0 = off -> the register kernels above)
+    const bool tma = op->uniform_width > 0 && ctx->opt.sell_tma >= 0;
+    int smem = 0;
+    const SlLaunch L = tma ? sl_lookup_tma(nv, op->uniform_width, ctx->opt.sell_tma == 0 ? 3 : (int)ctx->opt.sell_tma, &smem)
+                           : stream ? sl_lookup_stream(nv, op->uniform_width, depth, rows)
+                                    : sl_lookup(nv, sl_plan_chunk(ctx, nv, false));
     sl_fn fn = L.fn;
-    {
+    if (tma) NSK_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (!tma) {
         // the register hand-over between the warpgroups only adds up when the kernel got the register count its launch
         // bounds imply (ptxas pins it to that when setmaxnreg is used): refuse to launch otherwise rather than hang
         cudaFuncAttributes fa;
@@ -1581,12 +1907,12 @@ static int sl_run(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
         }
     }
     int per_sm = 0;
-    NSK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, L.threads, 0));
+    NSK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, L.threads, smem));
     if (ctx->opt.sell_ctas_per_sm > 0) per_sm = std::min(per_sm, (int)ctx->opt.sell_ctas_per_sm);
     const int resident = ctx->prop.multiProcessorCount * per_sm;
     if (resident < k) { nsk_set_error(ctx, "sliced-ELL path: fewer resident CTAs than levels"); return NSK_ERR_UNSUPPORTED; }
     const char *why = "";
-    SlPlan *plan = sl_plan(A, op, k, level_rows, resident, nv, stream, &why);
+    SlPlan *plan = sl_plan(A, op, k, level_rows, resident, nv, stream || tma, &why);
     if (!plan) { nsk_set_error(ctx, "fused matrix powers not applicable: %s", why); return NSK_ERR_UNSUPPORTED; }
     int maxcount = 0;
     for (int l = 0; l < k; l++) maxcount = std::max(maxcount, plan->count[l]);
@@ -1632,7 +1958,7 @@ static int sl_run(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
     if (k > 1) {
         // CTAs of different levels wait on each other: co-residency must be guaranteed, not assumed
         void *args[] = {&P};
-        cudaError_t e = cudaLaunchCooperativeKernel((const void *)fn, dim3(plan->grid), dim3(L.threads), args, 0, ctx->stream);
+        cudaError_t e = cudaLaunchCooperativeKernel((const void *)fn, dim3(plan->grid), dim3(L.threads), args, (size_t)smem, ctx->stream);
         if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported) {
             cudaGetLastError();
             plan->epoch--;
@@ -1641,7 +1967,7 @@ static int sl_run(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
         }
         NSK_CUDA(ctx, e);
     } else {
-        fn<<<plan->grid, L.threads, 0, ctx->stream>>>(P);
+        fn<<<plan->grid, L.threads, smem, ctx->stream>>>(P);
         NSK_CUDA(ctx, cudaGetLastError());
     }
     ctx->launches++;
@@ -1664,6 +1990,14 @@ bool nsk_sell_applicable(nsk_csr_t A)
 {
     if (A->n == 0 || A->nnz == 0) return false;
     return sl_get(A)->ok;
+}
+
+// Every tile is a pattern tile of one width: the staged-coefficient kernel applies (stencils, regular bands).
+bool nsk_sell_uniform(nsk_csr_t A)
+{
+    if (A->n == 0 || A->nnz == 0) return false;
+    SellOp *op = sl_get(A);
+    return op->ok && op->uniform_width > 0;
 }
 
 // 1 when the watchdog flag of the operator's fused kernel is set (a bounded wait expired); clears it.

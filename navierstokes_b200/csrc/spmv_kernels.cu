@@ -451,6 +451,8 @@ int nsk_launch_spmv(nsk_csr_t A, const nsk_spmv_args &a)
     // nonzeros per row (tet mesh: 5.5 vs 4.3 / 2.1 TB/s); the others only pay when a tile holds few rows
     const bool long_rows = A->mean_row > 96.0;
     int sel = (int)ctx->opt.spmv_kernel;
+    // default for operators made of pattern tiles (stencils, regular bands): the staged-coefficient sliced-ELL kernel
+    if (sel == 0 && rb == 0 && nsk_sell_uniform(A)) sel = 4;
     if (sel == 4 && rb == 0 && nsk_sell_applicable(A)) {  // sliced-ELL tiles (sell.cu)
         double *out = a.y;
         int s = nsk_sell_run(A, 1, a.x, &out, a.mode, &re, a.dot_w, a.dot_slot);

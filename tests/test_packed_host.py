@@ -12,15 +12,14 @@ from conftest import CSR_CASES, assert_bits_equal, golden
 NVARIANTS = 14
 
 
-def pack(A_ptrow, A_indcol, A_coef, n_cols, variant, indexed=False, stats=None):
+def pack(A_ptrow, A_indcol, A_coef, n_cols, variant):
     lib = _lib.load()
     ptrow = np.ascontiguousarray(A_ptrow, np.int32)
     indcol = np.ascontiguousarray(A_indcol, np.int32)
     coef = np.ascontiguousarray(A_coef, np.float64)
     n = len(ptrow) - 1
     h = C.c_void_p()
-    create = lib.nsk_pack_host_create_indexed if indexed else lib.nsk_pack_host_create
-    st = create(n, n_cols, len(indcol), ptrow.ctypes.data, indcol.ctypes.data, coef.ctypes.data, variant, C.byref(h))
+    st = lib.nsk_pack_host_create(n, n_cols, len(indcol), ptrow.ctypes.data, indcol.ctypes.data, coef.ctypes.data, variant, C.byref(h))
     assert st == 0
     why = lib.nsk_pack_host_why(h).decode()
     out = None
@@ -31,10 +30,6 @@ def pack(A_ptrow, A_indcol, A_coef, n_cols, variant, indexed=False, stats=None):
         mr, mx = C.c_int(), C.c_int()
         assert lib.nsk_pack_host_expand(h, p2.ctypes.data, c2.ctypes.data, v2.ctypes.data, C.byref(mr), C.byref(mx)) == 0
         out = (p2, c2[:len(indcol)], v2[:len(indcol)], mr.value, mx.value, int(lib.nsk_pack_host_bytes(h)))
-        if stats is not None:
-            ti, ex = C.c_int64(), C.c_int64()
-            assert lib.nsk_pack_host_index_stats(h, C.byref(ti), C.byref(ex)) == 0
-            stats["tiles_indexed"], stats["exception_rows"] = ti.value, ex.value
     lib.nsk_pack_host_destroy(h)
     return why, out
 
@@ -53,57 +48,6 @@ def test_pack_expand_round_trip(gen, args, variant):
     assert np.array_equal(p2, A.ptrow) and np.array_equal(c2, A.indcol)
     assert_bits_equal(v2, A.coef)
     assert 1 <= max_runs <= 8 and nbytes > 0
-
-
-@pytest.mark.parametrize("variant", [5, 7, 10, 11])
-@pytest.mark.parametrize("gen,args", [("laplace3d_7pt", (24, 18, 10)), ("laplace2d_5pt", (130, 41)), ("laplace3d_7pt", (300, 4, 6)),
-                                      ("fem_baij4", (4,)), ("laplace3d_7pt", (11, 9, 7)), ("laplace2d_5pt", (33, 29)),
-                                      ("laplace3d_7pt", (257, 3, 1)), ("laplace3d_7pt", (256, 6, 5)), ("laplace2d_5pt", (1024, 7))])
-def test_pack_indexed_expand_round_trip(gen, args, variant):
-    """Index compression (blob format 1): the expansion is still exactly the input, never larger than the plain pack."""
-    A = getattr(matgen, gen)(*args)
-    why0, out0 = pack(A.ptrow, A.indcol, A.coef, A.n, variant)
-    st = {}
-    why, out = pack(A.ptrow, A.indcol, A.coef, A.n, variant, indexed=True, stats=st)
-    assert bool(why) == bool(why0)
-    if why:
-        return
-    p2, c2, v2, max_runs, max_xlen, nbytes = out
-    assert np.array_equal(p2, A.ptrow) and np.array_equal(c2, A.indcol)
-    assert_bits_equal(v2, A.coef)
-    assert nbytes <= out0[5] and (max_runs, max_xlen) == out0[3:5]
-    assert st["tiles_indexed"] >= 0
-
-
-def test_pack_indexed_stencil_sizes():
-    """7-point operator, 256-row tiles = x-lines: every tile has one column pattern; its two line-end rows lack one slot
-    each (mask), lines on the y / z faces lack a whole neighbour line and simply have a narrower pattern.  8.3 bytes
-    per nonzero instead of 10.3; odd vector length and the tail slot go through the same path."""
-    A = matgen.laplace3d_7pt(256, 6, 5)
-    st = {}
-    why, out = pack(A.ptrow, A.indcol, A.coef, A.n, 7, indexed=True, stats=st)
-    assert not why
-    assert st["tiles_indexed"] == 30 and st["exception_rows"] == 2 * 30
-    assert out[5] / A.nnz < 8.45
-    _, plain = pack(A.ptrow, A.indcol, A.coef, A.n, 7)
-    assert plain[5] / A.nnz > 10.2
-    B = matgen.laplace3d_7pt(61, 17, 23)  # odd n: the tail slot
-    st = {}
-    why, out = pack(B.ptrow, B.indcol, B.coef, B.n, 7, indexed=True, stats=st)
-    assert not why and np.array_equal(out[1], B.indcol)
-
-
-@pytest.mark.parametrize("seed", range(6))
-def test_pack_indexed_random_stencils_round_trip(seed):
-    rng = np.random.default_rng(seed)
-    nx, ny, nz = int(rng.integers(4, 50)), int(rng.integers(3, 30)), int(rng.integers(2, 16))
-    A = matgen.random_stencil3d(nx, ny, nz, seed=seed, max_points=int(rng.integers(3, 14)), drop=float(rng.uniform(0, 0.2)))
-    why, out = pack(A.ptrow, A.indcol, A.coef, A.n, 7, indexed=True)
-    if why:
-        return
-    p2, c2, v2, *_ = out
-    assert np.array_equal(p2, A.ptrow) and np.array_equal(c2, A.indcol)
-    assert_bits_equal(v2, A.coef)
 
 
 def test_pack_stencils_use_few_runs_and_ten_bytes_per_nonzero():

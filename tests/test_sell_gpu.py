@@ -10,7 +10,7 @@ from conftest import CSR_CASES, VECS, assert_bits_equal, golden
 
 pytestmark = pytest.mark.gpu
 
-SELL_OPTS = ("spmv_kernel", "mpk_kernel", "sell_chunk", "sell_ctas_per_sm", "sell_stream", "sell_rows", "sell_pf_dist", "wave_l2_pct",
+SELL_OPTS = ("spmv_kernel", "mpk_kernel", "sell_chunk", "sell_ctas_per_sm", "sell_stream", "sell_rows", "sell_tma", "sell_pf_dist", "wave_l2_pct",
              "pipe_w0_pct")
 
 
@@ -31,15 +31,17 @@ def test_sell_spmv_golden(sell, oracle_lib, case):
     ctx = sell
     g = golden(case)
     A = nsk.CsrMatrix(ctx, g["ptrow"], g["indcol"], g["coef"])
-    for chunk, stream, rows in ((1, 0, 1), (2, -1, 0), (3, -1, 0), (4, 2, 2), (3, 3, 2), (2, 1, 1)):
+    for chunk, stream, rows, tma in ((1, 0, 1, 0), (4, 0, 0, 3), (3, 0, 0, 6), (2, -1, 0, -1), (3, -1, 0, -1), (4, 2, 2, -1),
+                                     (3, 3, 2, -1), (2, 2, 1, -1)):
         ctx.set_option("sell_chunk", chunk)
+        ctx.set_option("sell_tma", tma)        # all-pattern operators: staged-coefficient kernel (n stages), -1: register kernels
         ctx.set_option("sell_rows", rows)      # streaming kernel: rows of a tile per consumer thread
         ctx.set_option("sell_stream", stream)  # 0 / n: streaming consumers on all-pattern operators; -1: an item at a time
         for v in VECS:
             x = g[f"x_{v}"]
             y = A.spmv(x, mode=nsk.EXACT_FMA)
             assert ctx.query("last_spmv_kernel") == 4, "the sliced-ELL kernel did not run"
-            assert_bits_equal(y, g[f"spmv_fma_{v}"], f"{case}/{v} chunk={chunk} stream={stream}")
+            assert_bits_equal(y, g[f"spmv_fma_{v}"], f"{case}/{v} chunk={chunk} stream={stream} tma={tma}")
             assert_bits_equal(A.spmv(x, mode=nsk.EXACT_MULADD),
                               oracle_lib.spmv_muladd(g["ptrow"], g["indcol"], g["coef"], x), f"{case}/{v} muladd")
 
@@ -54,9 +56,10 @@ def test_sell_mpk_golden_equals_k_products_bitwise(sell, oracle_lib, case, k):
     x = g["x_uni"]
     ref = oracle_lib.mpk(g["ptrow"], g["indcol"], g["coef"], k, x)
     dx = ctx.to_device(x)
-    for chunk, stream in ((1, 0), (2, 0), (3, -1), (4, 2)):
+    for chunk, stream, tma in ((1, 0, 0), (4, 0, 3), (2, 0, -1), (3, -1, -1), (4, 2, -1)):
         ctx.set_option("sell_chunk", chunk)
         ctx.set_option("sell_stream", stream)
+        ctx.set_option("sell_tma", tma)
         lv = [ctx.zeros(A.n) for _ in range(k)]
         before = ctx.launch_count
         A.mpk(k, dx, lv)
@@ -69,9 +72,10 @@ SELL_OPS = [("laplace3d_7pt", (40,)), ("laplace2d_5pt", (300,)), ("laplace3d_7pt
             ("tet_p1_laplacian", (24, 2, True)), ("fem_baij4", (7,)), ("random_banded_csr", (30000, 700, 9.0, 3))]
 
 
-@pytest.mark.parametrize("chunk,stream,rows", [(0, 0, 0), (2, -1, 0), (4, 2, 2), (3, 3, 2), (1, 1, 1)])
+@pytest.mark.parametrize("chunk,stream,rows,tma", [(0, 0, 0, 0), (1, 0, 0, 3), (4, 0, 0, 6), (2, -1, 0, -1), (4, 2, 2, -1),
+                                                   (3, 3, 2, -1), (1, 2, 1, -1)])
 @pytest.mark.parametrize("gen,args", SELL_OPS)
-def test_sell_spmv_and_mpk_bitwise(sell, oracle_lib, gen, args, chunk, stream, rows):
+def test_sell_spmv_and_mpk_bitwise(sell, oracle_lib, gen, args, chunk, stream, rows, tma):
     """Stencils (pattern tiles, no per-entry index), an RCM-ordered tetrahedral P1 Laplacian, a 4-dof-per-node FEM operator
     (58 per row) and a ragged banded matrix (explicit tiles with per-slice widths): product and fused powers, both
     exact flavours, several repetitions (the completion counters are monotone over launches)."""
@@ -82,6 +86,7 @@ def test_sell_spmv_and_mpk_bitwise(sell, oracle_lib, gen, args, chunk, stream, r
     ctx.set_option("sell_chunk", chunk)
     ctx.set_option("sell_stream", stream)
     ctx.set_option("sell_rows", rows)
+    ctx.set_option("sell_tma", tma)
     ctx.set_option("wave_l2_pct", 1000)
     assert_bits_equal(dA.spmv(x), oracle_lib.spmv(A.ptrow, A.indcol, A.coef, x), f"{gen}{args} spmv")
     applies = ctx.query("last_spmv_kernel") == 4
@@ -121,9 +126,10 @@ def test_sell_mpk_window_and_placement(sell, oracle_lib, interleave, w0, cps, le
     dx = ctx.to_device(x)
     for k in (2, 5):
         ref = oracle_lib.mpk(A.ptrow, A.indcol, A.coef, k, x)
-        for chunk, stream in ((1, 0), (2, -1), (4, 3)):
+        for chunk, stream, tma in ((1, 0, 0), (3, 0, 6), (2, -1, -1), (4, 3, -1)):
             ctx.set_option("sell_chunk", chunk)
             ctx.set_option("sell_stream", stream)
+            ctx.set_option("sell_tma", tma)
             lv = dA.mpk(k, dx)
             assert ctx.query("last_mpk_strategy") == 5
             assert_bits_equal(np.stack([l.to_host() for l in lv]), ref, f"k={k} chunk={chunk}")

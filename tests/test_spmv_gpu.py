@@ -14,6 +14,7 @@ FAST_TOL = 1e-12  # BASELINE.json north star: fast mode within 1e-12 relative (r
 def all_kernel_configs(ctx):
     """(spmv_kernel, stream_variant) pairs: the simple kernels and every streaming geometry."""
     yield 1, 0
+    yield 4, 0  # sliced-ELL tiles (refused for very ragged rows; then the CSR kernels run)
     for v in range(1, 9):
         yield 2, v
     for v in range(1, 15):
@@ -28,8 +29,7 @@ def select_kernel(ctx, kern, var):
 @pytest.fixture()
 def reset_options(ctx):
     yield
-    for name in ("spmv_kernel", "stream_variant", "spmv_ctas_per_sm", "mpk_kernel", "wave_variant", "wave_l2_pct",
-                 "wave_static", "pipe_variant", "packed_variant"):
+    for name in ("spmv_kernel", "stream_variant", "spmv_ctas_per_sm", "mpk_kernel", "wave_l2_pct", "packed_variant"):
         ctx.set_option(name, 0)
     ctx.set_option("wave_slack_pct", -1)
     ctx.set_option("pipe_interleave", 1)
@@ -205,144 +205,7 @@ def test_medium_size_properties(ctx, oracle_lib, shape, reset_options):
 
 
 # ---- wavefront (single-launch, L2-resident) matrix powers ------------------------------------------
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12])
-@pytest.mark.parametrize("gen,args", [("laplace3d_7pt", (40,)), ("laplace2d_5pt", (300,)), ("laplace3d_7pt", (64, 64, 20))])
-def test_mpk_wavefront_bitwise(ctx, oracle_lib, gen, args, variant, reset_options):
-    A = getattr(matgen, gen)(*args)
-    x = matgen.vec_uniform(A.n, seed=9)
-    dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
-    ctx.set_option("mpk_kernel", 2)
-    ctx.set_option("wave_variant", variant)
-    for k in (2, 4, 7):
-        before = ctx.launch_count
-        lv = dA.mpk(k, x, mode=nsk.EXACT_FMA)
-        assert_bits_equal(lv, oracle_lib.mpk(A.ptrow, A.indcol, A.coef, k, x), f"{gen}{args} k={k} variant={variant}")
-    lm = dA.mpk(3, x, mode=nsk.EXACT_MULADD)
-    ctx.set_option("mpk_kernel", 1)
-    assert_bits_equal(lm, dA.mpk(3, x, mode=nsk.EXACT_MULADD))
-
-
-def test_mpk_wavefront_is_one_launch(ctx, reset_options):
-    A = matgen.laplace3d_7pt(48)
-    dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
-    dx = ctx.to_device(matgen.vec_uniform(A.n))
-    lv = [ctx.empty(A.n) for _ in range(4)]
-    ctx.set_option("mpk_kernel", 2)
-    dA.mpk(4, dx, lv)
-    before = ctx.launch_count
-    dA.mpk(4, dx, lv)
-    assert ctx.launch_count - before == 1
-    ctx.set_option("mpk_kernel", 1)
-    before = ctx.launch_count
-    dA.mpk(4, dx, lv)
-    assert ctx.launch_count - before == 4
-
-
-def test_mpk_wavefront_repeated_calls_are_stable(ctx, reset_options):
-    """Counters are reset per call: 20 back-to-back calls give the same bits."""
-    A = matgen.laplace3d_7pt(56)
-    dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
-    dx = ctx.to_device(matgen.vec_uniform(A.n, 4))
-    lv = [ctx.empty(A.n) for _ in range(4)]
-    ctx.set_option("mpk_kernel", 2)
-    dA.mpk(4, dx, lv)
-    first = [l.to_host() for l in lv]
-    for _ in range(20):
-        dA.mpk(4, dx, lv)
-    for l in range(4):
-        assert_bits_equal(lv[l].to_host(), first[l])
-
-
-def test_mpk_wavefront_falls_back_when_not_applicable(ctx, oracle_lib, reset_options):
-    """Unstructured operator whose reach covers the whole matrix: the levels strategy must run."""
-    A = matgen.random_csr(4000, 5.0, seed=1, empty_rows=True)
-    x = matgen.vec_uniform(A.n)
-    dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
-    ctx.set_option("mpk_kernel", 2)
-    assert_bits_equal(dA.mpk(3, x), oracle_lib.mpk(A.ptrow, A.indcol, A.coef, 3, x))
-
-
 # ---- level-pipelined (single-launch, CTAs specialised by level) matrix powers -------------------------
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10])
-@pytest.mark.parametrize("gen,args", [("laplace3d_7pt", (40,)), ("laplace2d_5pt", (300,)), ("laplace3d_7pt", (64, 64, 20))])
-def test_mpk_pipeline_bitwise(ctx, oracle_lib, gen, args, variant, reset_options):
-    A = getattr(matgen, gen)(*args)
-    x = matgen.vec_uniform(A.n, seed=9)
-    dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
-    ctx.set_option("mpk_kernel", 3)
-    ctx.set_option("pipe_variant", variant)
-    for k in (2, 4, 7):
-        before = ctx.launch_count
-        lv = dA.mpk(k, x, mode=nsk.EXACT_FMA)
-        assert ctx.launch_count - before == 1, "level pipeline did not apply"
-        assert_bits_equal(lv, oracle_lib.mpk(A.ptrow, A.indcol, A.coef, k, x), f"{gen}{args} k={k} variant={variant}")
-    lm = dA.mpk(3, x, mode=nsk.EXACT_MULADD)
-    ctx.set_option("mpk_kernel", 1)
-    assert_bits_equal(lm, dA.mpk(3, x, mode=nsk.EXACT_MULADD))
-
-
-@pytest.mark.parametrize("interleave", [0, 1])
-@pytest.mark.parametrize("lead_pct", [0, 25, 100, 400])
-def test_mpk_pipeline_lead_and_placement(ctx, oracle_lib, interleave, lead_pct, reset_options):
-    """Back-pressure from tight (lead = reach + 1 group) to loose, both level placements: same bits."""
-    A = matgen.laplace3d_7pt(48, 40, 36)
-    x = matgen.vec_uniform(A.n, seed=3)
-    dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
-    ctx.set_option("mpk_kernel", 3)
-    ctx.set_option("pipe_interleave", interleave)
-    ctx.set_option("wave_slack_pct", lead_pct)
-    ctx.set_option("wave_l2_pct", 1000)  # never refuse: this operator is tiny, the window bound is not the subject
-    for k in (2, 5, 16):
-        before = ctx.launch_count
-        lv = dA.mpk(k, x)
-        assert ctx.launch_count - before == 1
-        assert_bits_equal(lv, oracle_lib.mpk(A.ptrow, A.indcol, A.coef, k, x), f"k={k}")
-
-
-def test_mpk_pipeline_repeated_calls_are_stable(ctx, reset_options):
-    """Counters are reset per call: 20 back-to-back calls give the same bits."""
-    A = matgen.laplace3d_7pt(56)
-    dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
-    dx = ctx.to_device(matgen.vec_uniform(A.n, 4))
-    lv = [ctx.empty(A.n) for _ in range(4)]
-    ctx.set_option("mpk_kernel", 3)
-    dA.mpk(4, dx, lv)
-    first = [l.to_host() for l in lv]
-    for _ in range(20):
-        dA.mpk(4, dx, lv)
-    for l in range(4):
-        assert_bits_equal(lv[l].to_host(), first[l])
-
-
-def test_mpk_pipeline_ragged_and_fallback(ctx, oracle_lib, reset_options):
-    """Banded operator with ragged / empty rows runs fused; an operator whose reach covers the whole matrix
-    degrades to k launches -- same bits either way."""
-    ctx.set_option("mpk_kernel", 3)
-    A = matgen.random_banded_csr(30000, 200, 6.0, seed=2, empty_rows=True)
-    x = matgen.vec_uniform(A.n, seed=8)
-    dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
-    assert_bits_equal(dA.mpk(5, x), oracle_lib.mpk(A.ptrow, A.indcol, A.coef, 5, x))
-    B = matgen.random_csr(4000, 5.0, seed=1, empty_rows=True)
-    xb = matgen.vec_uniform(B.n)
-    dB = nsk.CsrMatrix(ctx, B.ptrow, B.indcol, B.coef)
-    assert_bits_equal(dB.mpk(3, xb), oracle_lib.mpk(B.ptrow, B.indcol, B.coef, 3, xb))
-
-
-@pytest.mark.parametrize("strategy", [2, 3])
-def test_fused_csr_kernels_on_longer_rows(ctx, oracle_lib, strategy, reset_options):
-    """The CSR fused kernels accept operators up to 64 nonzeros per row (tet mesh 15/row, FEM-like 58/row): explicit
-    choices only (auto prefers k launches there), still bit-exact."""
-    ctx.set_option("mpk_kernel", strategy)
-    ctx.set_option("wave_l2_pct", 1000)
-    for A in (matgen.tet_p1_laplacian(9, permute_seed=2, rcm=True), matgen.fem_baij4(5)):
-        x = matgen.vec_uniform(A.n, seed=12)
-        dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
-        for k in (2, 4):
-            lv = dA.mpk(k, x)
-            assert ctx.query("last_mpk_strategy") == strategy
-            assert_bits_equal(lv, oracle_lib.mpk(A.ptrow, A.indcol, A.coef, k, x), f"strategy {strategy} k={k}")
-
-
 # ---- packed format: SpMV and matrix powers with x runs staged in shared memory ------------------------
 PACKED_OPS = [("laplace3d_7pt", (40,)), ("laplace2d_5pt", (300,)), ("laplace3d_7pt", (64, 64, 20)),
               ("laplace2d_5pt", (1000, 37)), ("laplace3d_7pt", (34, 10, 50)), ("laplace3d_7pt", (33, 7, 5)),
@@ -397,7 +260,7 @@ def test_packed_long_rows_fem_operator(ctx, oracle_lib, reset_options):
     dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
     assert dA.packed_bytes > 0
     assert_bits_equal(dA.spmv(x), oracle_lib.spmv(A.ptrow, A.indcol, A.coef, x))
-    assert ctx.query("last_spmv_kernel") == 3
+    assert ctx.query("last_spmv_kernel") == 3  # explicit-column tiles: the packed long-row geometry is the default
     assert_bits_equal(dA.spmv(x, mode=nsk.EXACT_MULADD), oracle_lib.spmv_muladd(A.ptrow, A.indcol, A.coef, x))
     ctx.set_option("mpk_kernel", 4)
     for k in (2, 3):
@@ -537,7 +400,7 @@ def test_bcsr4_fem_operator_matches_oracle_and_csr(ctx, oracle_lib):
 # ---- BASELINE.json full sizes: size-independent properties (the CPU oracle would need minutes here; bench.py
 # ---- additionally compares the 256^3 k=4 run bit for bit with the compiled reference on every round) -------------
 @pytest.mark.parametrize("cfg", ["c2_2d_4096", "c3_3d_256"])
-def test_full_size_properties(ctx, cfg, reset_options):
+def test_full_size_properties(ctx, oracle_lib, cfg, reset_options):
     A = matgen.laplace2d_5pt(4096) if cfg == "c2_2d_4096" else matgen.laplace3d_7pt(256)
     n = A.n
     dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
@@ -547,7 +410,7 @@ def test_full_size_properties(ctx, cfg, reset_options):
     dx, dw = ctx.to_device(x), ctx.to_device(w)
     # 1. every kernel family produces the same bits (thread-per-row from global = the simplest possible restatement)
     outs = {}
-    for kern in (1, 2, 3):
+    for kern in (1, 2, 3, 4):
         ctx.set_option("spmv_kernel", kern)
         y = ctx.empty(n)
         dA.spmv(dx, y)
@@ -556,6 +419,14 @@ def test_full_size_properties(ctx, cfg, reset_options):
     ctx.set_option("spmv_kernel", 0)
     assert_bits_equal(outs[2], outs[1], "stream vs scalar")
     assert_bits_equal(outs[3], outs[1], "packed vs scalar")
+    assert_bits_equal(outs[4], outs[1], "sliced-ELL vs scalar")
+    # 1b. against the ORACLE at full size: 16 random slabs of 65536 rows, bit for bit (SpMV_CSR_FMA, mpk/SpMV.cpp:41-56)
+    rng = np.random.default_rng(77)
+    for r0 in rng.integers(0, n - 65536, 16):
+        r0 = int(r0)
+        p0, p1 = int(A.ptrow[r0]), int(A.ptrow[r0 + 65536])
+        ref = oracle_lib.spmv((A.ptrow[r0:r0 + 65537] - p0).astype(np.int32), A.indcol[p0:p1], A.coef[p0:p1], x)
+        assert_bits_equal(outs[1][r0:r0 + 65536], ref, f"{cfg} rows {r0}..{r0 + 65536} vs oracle")
     # 2. a sample of rows against the definition, evaluated with the same fma chain on the host
     rows = np.random.default_rng(5).integers(0, n, 2000)
     for r in rows:  # numpy has no fma: a few ulp of the row's magnitude instead of bits
@@ -569,7 +440,14 @@ def test_full_size_properties(ctx, cfg, reset_options):
     fused = [ctx.empty(n) for _ in range(k)]
     ctx.set_option("mpk_kernel", 0)
     dA.mpk(k, dx, fused)
+    assert ctx.query("last_mpk_strategy") == 5  # stencil: the sliced-ELL level pipeline is the default
+    ctx.set_option("mpk_kernel", 4)
+    packed4 = [ctx.empty(n) for _ in range(k)]
+    dA.mpk(k, dx, packed4)
     assert ctx.query("last_mpk_strategy") == 4
+    for l in range(k):
+        assert_bits_equal(packed4[l].to_host(), fused[l].to_host(), f"packed vs sliced-ELL level {l}")
+    del packed4
     ctx.set_option("mpk_kernel", 1)
     ctx.set_option("spmv_kernel", 2)
     lev = [ctx.empty(n) for _ in range(k)]
@@ -590,6 +468,46 @@ def test_full_size_properties(ctx, cfg, reset_options):
     # 6. symmetry: <A x, w> == <x, A w>
     yx, yw = outs[1], dA.spmv(dw).to_host()
     assert abs(np.dot(yx, w) - np.dot(x, yw)) <= 1e-9 * abs(np.dot(yx, w))
+
+
+@pytest.mark.parametrize("cfg", ["c1_fem_530k", "c4_tet_531k"])
+def test_c1_c4_half_million_rows_vs_oracle(ctx, oracle_lib, cfg, reset_options):
+    """BASELINE configs 1 and 4 at half a million rows against the oracle, bit for bit: the FEM-like 4-dof-per-node
+    operator (58 per row) and the RCM-ordered tetrahedral P1 Laplacian (15 per row, unstructured): product in every
+    kernel family, fused powers (k = 4 / k = 8) in the default strategy and as k products."""
+    if cfg == "c1_fem_530k":
+        A, k = matgen.fem_baij4(50), 4
+    else:
+        A, k = matgen.tet_p1_laplacian(80, permute_seed=2, rcm=True), 8
+    assert A.n > 500000
+    x = matgen.vec_uniform(A.n, seed=41)
+    ref = oracle_lib.mpk(A.ptrow, A.indcol, A.coef, k, x)
+    dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
+    dx = ctx.to_device(x)
+    for kern in (1, 2, 3, 4, 0):
+        ctx.set_option("spmv_kernel", kern)
+        assert_bits_equal(dA.spmv(dx).to_host(), ref[0], f"{cfg} spmv kernel {kern}")
+    ctx.set_option("spmv_kernel", 0)
+    for strategy in (0, 1, 4, 5):
+        ctx.set_option("mpk_kernel", strategy)
+        lv = dA.mpk(k, dx)
+        assert_bits_equal(np.stack([l.to_host() for l in lv]), ref, f"{cfg} k={k} strategy {strategy}")
+
+
+def test_flush_l2_keeps_results(ctx, oracle_lib):
+    """nsk_flush_l2 (the reference's flush_cache, mpk/utils.cpp:146-154): scrubs the cache, touches no operand."""
+    A = matgen.laplace3d_7pt(64)
+    x = matgen.vec_uniform(A.n, seed=5)
+    dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
+    dx = ctx.to_device(x)
+    y0 = dA.spmv(dx).to_host()
+    before = ctx.launch_count
+    ctx.flush_l2()
+    ctx.sync()
+    assert ctx.launch_count >= before
+    nsk.flush_cache()  # the reference-named entry point
+    assert_bits_equal(dA.spmv(dx).to_host(), y0)
+    assert_bits_equal(y0, oracle_lib.spmv(A.ptrow, A.indcol, A.coef, x))
 
 
 def test_packed_mpk_splits_when_the_window_does_not_fit(ctx, oracle_lib, reset_options):
@@ -624,6 +542,8 @@ def test_packed_fuzz_random_stencils(ctx, oracle_lib, seed, reset_options):
     dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
     packed = dA.packed_bytes > 0
     ref = oracle_lib.mpk(A.ptrow, A.indcol, A.coef, 4, x)
+    ctx.set_option("spmv_kernel", 3)
+    ctx.set_option("mpk_kernel", 4)
     assert_bits_equal(dA.spmv(x), ref[0], f"grid {nx}x{ny}x{nz} packed={packed}")
     assert ctx.query("last_spmv_kernel") == (3 if packed else 2)
     ctx.set_option("wave_l2_pct", 1000)

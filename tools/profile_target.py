@@ -27,7 +27,6 @@ dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
 x = ctx.to_device(matgen.vec_uniform(A.n, 1))
 lv = [ctx.empty(A.n) for _ in range(args.k)]
 ctx.set_option("wave_slack_pct", args.slack)
-ctx.set_option("wave_variant", args.wave_variant)
 pass  # (wave_l2_pct is left at its default; override with --opt wave_l2_pct=N)
 for o in args.opt:
     name, val = o.split("=")
@@ -40,9 +39,6 @@ for i in range(args.reps + 1):
         dA.spmv(x, lv[0])
     elif args.what == "mpk":
         ctx.set_option("mpk_kernel", args.mpk_kernel if args.mpk_kernel >= 0 else 0)
-        dA.mpk(args.k, x, lv)
-    elif args.what == "mpk_wave":
-        ctx.set_option("mpk_kernel", 2)
         dA.mpk(args.k, x, lv)
     else:
         ctx.set_option("mpk_kernel", 1)
