@@ -33,13 +33,6 @@ struct nsk_dist_s {
     std::vector<DistPeer> peers;
 };
 
-__global__ void __launch_bounds__(256) pack_kernel(const double *__restrict__ x, const int *__restrict__ idx,
-                                                   double *__restrict__ out, int count)
-{
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) out[i] = x[idx[i]];
-}
-
 // All peers in ONE launch each way (a per-ring message costs ~9 us of NCCL latency, a launch ~3 us: measured 46 us
 // per depth-4 exchange with one neighbour when every ring travelled alone, tools/dist_probe.py).
 constexpr int HALO_MAX_SEG = 64;  // peers x rings
@@ -162,52 +155,25 @@ int nsk_halo_exchange_dev(nsk_csr_t A, double *xlocal, int depth)
     if (!D) return NSK_OK;
     NSK_REQUIRE(ctx, depth >= 1 && depth <= D->depth, "halo depth exceeds the plan's depth");
     if (D->peers.empty()) return NSK_OK;
-    NSK_REQUIRE(ctx, nsk_comm_active(ctx) || nsk_comm_size(ctx) == 1, "no communicator attached (nsk_comm_init)");
-    // One message per peer and direction: the first `depth` rings of a peer's send list are contiguous in its send
-    // buffer (ring-major), and land contiguously in d_recvbuf; a ring's slice from one peer is contiguous in the local
-    // vector, so unpacking is `depth` straight copies per peer.  One pack launch and one unpack launch for all peers.
-    HaloSegs pack, unpack;
-    pack.nseg = unpack.nseg = 0;
-    pack.total = unpack.total = 0;
-    pack.begin[0] = unpack.begin[0] = 0;
+    NSK_REQUIRE(ctx, nsk_comm_active(ctx), "the operator has peers but no communicator is attached (nsk_comm_init)");
+    // One message per peer and direction, ALWAYS (the protocol must not depend on anything only this rank knows, such
+    // as its own number of peers: both ends of a message have to agree on its size): the first `depth` rings of a
+    // peer's send list are contiguous in its send buffer (ring-major), and land contiguously in d_recvbuf; a ring's
+    // slice from one peer is contiguous in the local vector, so unpacking is `depth` straight copies per peer.  Pack
+    // and unpack run as one launch per HALO_MAX_SEG segments (one launch each up to 64 peers x rings).
+    struct Seg { const double *src; double *dst; const int *idx; int count; };
+    std::vector<Seg> pack, unpack;
     std::vector<const double *> sendbuf;
     std::vector<int> sendcount, recvcount, peer;
     std::vector<double *> recvbuf;
-    const bool direct = (int)D->peers.size() * depth > HALO_MAX_SEG;  // too many segments for one descriptor: a message per ring
     for (DistPeer &P : D->peers) {
         int scnt = 0, rcnt = 0;
         for (int r = 0; r < depth; r++) { scnt += P.send_ring_count[r]; rcnt += P.recv_ring_count[r]; }
-        if (direct) {
-            if (scnt > 0) {
-                pack_kernel<<<(scnt + 255) / 256, 256, 0, ctx->stream>>>(xlocal, P.d_send_idx, P.d_sendbuf, scnt);
-                ctx->launches++;
-            }
-            int off = 0;
-            for (int r = 0; r < depth; r++) {
-                peer.push_back(P.rank);
-                sendbuf.push_back(P.d_sendbuf + off);
-                sendcount.push_back(P.send_ring_count[r]);
-                recvbuf.push_back(xlocal + P.recv_ring_start[r]);
-                recvcount.push_back(P.recv_ring_count[r]);
-                off += P.send_ring_count[r];
-            }
-            continue;
-        }
-        if (scnt > 0) {
-            pack.src[pack.nseg] = xlocal;
-            pack.idx[pack.nseg] = P.d_send_idx;
-            pack.dst[pack.nseg] = P.d_sendbuf;
-            pack.total += scnt;
-            pack.begin[++pack.nseg] = pack.total;
-        }
+        if (scnt > 0) pack.push_back(Seg{xlocal, P.d_sendbuf, P.d_send_idx, scnt});
         int off = 0;
         for (int r = 0; r < depth && depth > 1; r++) {  // depth 1: the single ring is received in place, nothing to unpack
             if (P.recv_ring_count[r] == 0) continue;
-            unpack.src[unpack.nseg] = P.d_recvbuf + off;
-            unpack.idx[unpack.nseg] = nullptr;
-            unpack.dst[unpack.nseg] = xlocal + P.recv_ring_start[r];
-            unpack.total += P.recv_ring_count[r];
-            unpack.begin[++unpack.nseg] = unpack.total;
+            unpack.push_back(Seg{P.d_recvbuf + off, xlocal + P.recv_ring_start[r], nullptr, P.recv_ring_count[r]});
             off += P.recv_ring_count[r];
         }
         peer.push_back(P.rank);
@@ -216,18 +182,31 @@ int nsk_halo_exchange_dev(nsk_csr_t A, double *xlocal, int depth)
         recvbuf.push_back(depth > 1 ? P.d_recvbuf : xlocal + P.recv_ring_start[0]);
         recvcount.push_back(rcnt);
     }
-    if (!direct && pack.total > 0) {
-        halo_move_kernel<<<(pack.total + 255) / 256, 256, 0, ctx->stream>>>(pack);
-        ctx->launches++;
-    }
+    auto move = [&](const std::vector<Seg> &segs) {
+        for (size_t s0 = 0; s0 < segs.size(); s0 += HALO_MAX_SEG) {
+            HaloSegs H;
+            H.nseg = 0;
+            H.total = 0;
+            H.begin[0] = 0;
+            for (size_t i = s0; i < std::min(segs.size(), s0 + (size_t)HALO_MAX_SEG); i++) {
+                H.src[H.nseg] = segs[i].src;
+                H.dst[H.nseg] = segs[i].dst;
+                H.idx[H.nseg] = segs[i].idx;
+                H.total += segs[i].count;
+                H.begin[++H.nseg] = H.total;
+            }
+            if (H.total > 0) {
+                halo_move_kernel<<<(H.total + 255) / 256, 256, 0, ctx->stream>>>(H);
+                ctx->launches++;
+            }
+        }
+    };
+    move(pack);
     NSK_CUDA(ctx, cudaGetLastError());
     NSK_TRY(nsk_comm_sendrecv(ctx, (int)peer.size(), peer.data(), sendbuf.data(), sendcount.data(), recvbuf.data(),
                               recvcount.data()));
-    if (!direct && unpack.total > 0) {
-        halo_move_kernel<<<(unpack.total + 255) / 256, 256, 0, ctx->stream>>>(unpack);
-        ctx->launches++;
-        NSK_CUDA(ctx, cudaGetLastError());
-    }
+    move(unpack);
+    NSK_CUDA(ctx, cudaGetLastError());
     return NSK_OK;
 }
 

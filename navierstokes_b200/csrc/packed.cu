@@ -270,6 +270,7 @@ __global__ void __launch_bounds__((NCW + 3) * 32, MINB) packed_kernel(const PkPa
                 ok = __shfl_sync(0xffffffffu, (int)ok, 0) != 0;
                 if (ok) { ++n; continue; }
                 if (n > 0) break;
+                __nanosleep(32);
                 if (++spins > (1u << 26)) __trap();
             }
             const unsigned long long t5 = timing ? pk_now() : 0ull;
@@ -1318,9 +1319,23 @@ static int pk_run(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
     P.partials = ctx->d_partials;
     P.ticket = ctx->d_ticket;
     P.dot_out = dot_w ? ctx->d_scalars + dot_slot : nullptr;
-    fn<<<plan->grid, ((nv == 2 ? 4 : V.ncw) + 3) * 32, smem, ctx->stream>>>(P);
+    if (k > 1) {
+        // CTAs of different levels wait on each other: co-residency must be guaranteed, not assumed from the occupancy
+        // calculator (another kernel on the device, MPS or a user stream could hold SMs)
+        void *args[] = {&P};
+        cudaError_t e = cudaLaunchCooperativeKernel((const void *)fn, dim3(plan->grid), dim3(((nv == 2 ? 4 : V.ncw) + 3) * 32),
+                                                    args, (size_t)smem, ctx->stream);
+        if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported) {
+            cudaGetLastError();
+            nsk_set_error(ctx, "packed matrix powers: the grid cannot be made co-resident on this device now");
+            return NSK_ERR_UNSUPPORTED;
+        }
+        NSK_CUDA(ctx, e);
+    } else {
+        fn<<<plan->grid, ((nv == 2 ? 4 : V.ncw) + 3) * 32, smem, ctx->stream>>>(P);
+        NSK_CUDA(ctx, cudaGetLastError());
+    }
     ctx->launches++;
-    NSK_CUDA(ctx, cudaGetLastError());
     if (P.timing) {  // debugging aid: per-level averages of the stage cycle on stderr
         std::vector<unsigned long long> h((size_t)plan->grid * 16);
         NSK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -11,6 +11,7 @@
 // is NO CPU fallback.
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -40,8 +41,61 @@ nsk_ctx_t ctx()
 }
 
 typedef std::tuple<const void *, const void *, const void *, int, long long> Key;
-std::map<Key, nsk_csr_t> g_csr;
-std::map<Key, nsk_bcsr4_t> g_bcsr;
+// The reference's kernels read the caller's live arrays on every call; the shim keeps a device copy keyed on the
+// arrays' addresses and sizes.  A caller may update coef in place (new Jacobian values, same pattern) or free a matrix
+// and get the same addresses back, so every call re-validates the entry with a fingerprint of the host arrays and
+// re-uploads the operator when it changed.  NSK_SHIM_VALIDATE = "sample" (default: 4096 windows of 64 bytes spread over
+// each array, plus both ends -- catches any wholesale update), "full" (every byte) or "off".
+template <class H>
+struct Entry {
+    H handle = nullptr;
+    unsigned long long print = 0;
+};
+std::map<Key, Entry<nsk_csr_t>> g_csr;
+std::map<Key, Entry<nsk_bcsr4_t>> g_bcsr;
+
+int validate_mode()
+{
+    static int mode = -1;
+    if (mode < 0) {
+        const char *e = std::getenv("NSK_SHIM_VALIDATE");
+        mode = !e ? 1 : !std::strcmp(e, "off") ? 0 : !std::strcmp(e, "full") ? 2 : 1;
+    }
+    return mode;
+}
+
+unsigned long long mix(unsigned long long h, const void *p, size_t bytes)
+{
+    const unsigned char *b = static_cast<const unsigned char *>(p);
+    size_t i = 0;
+    for (; i + 8 <= bytes; i += 8) {
+        unsigned long long w;
+        std::memcpy(&w, b + i, 8);
+        h = (h ^ w) * 0x9E3779B97F4A7C15ull;
+        h ^= h >> 29;
+    }
+    for (; i < bytes; i++) h = (h ^ b[i]) * 0x100000001B3ull;
+    return h;
+}
+
+unsigned long long fingerprint_array(unsigned long long h, const void *p, size_t bytes)
+{
+    const int mode = validate_mode();
+    if (mode == 0 || bytes == 0) return h;
+    if (mode == 2 || bytes <= 4096 * 64 * 2) return mix(h, p, bytes);
+    const unsigned char *b = static_cast<const unsigned char *>(p);
+    const size_t windows = 4096, step = (bytes - 64) / (windows - 1);
+    for (size_t w = 0; w < windows; w++) h = mix(h, b + w * step, 64);
+    return mix(h, b + bytes - 64, 64);
+}
+
+unsigned long long fingerprint(const void *ptrow, size_t pb, const void *indcol, size_t ib, const void *coef, size_t cb)
+{
+    unsigned long long h = 0xcbf29ce484222325ull;
+    h = fingerprint_array(h, ptrow, pb);
+    h = fingerprint_array(h, indcol, ib);
+    return fingerprint_array(h, coef, cb);
+}
 
 nsk_csr_t device_csr(csrmatrix &A)
 {
@@ -49,12 +103,18 @@ nsk_csr_t device_csr(csrmatrix &A)
     // the true count is ptrow[n]
     const long long nnz = A.ptrow.empty() ? 0 : (long long)A.ptrow[A.n];
     Key k(A.ptrow.data(), A.indcol.data(), A.coef.data(), A.n, nnz);
+    const unsigned long long fp = fingerprint(A.ptrow.data(), sizeof(int) * ((size_t)A.n + 1), A.indcol.data(),
+                                              sizeof(int) * (size_t)nnz, A.coef.data(), sizeof(double) * (size_t)nnz);
     auto it = g_csr.find(k);
-    if (it != g_csr.end()) return it->second;
+    if (it != g_csr.end()) {
+        if (it->second.print == fp) return it->second.handle;
+        nsk_csr_destroy(it->second.handle);  // same addresses, different contents: the device copy is stale
+        g_csr.erase(it);
+    }
     nsk_csr_t h = nullptr;
     int s = nsk_csr_create(ctx(), A.n, A.n, nnz, A.ptrow.data(), A.indcol.data(), A.coef.data(), &h);
     if (s != NSK_OK) die("nsk_csr_create", s);
-    g_csr[k] = h;
+    g_csr[k] = Entry<nsk_csr_t>{h, fp};
     return h;
 }
 
@@ -62,12 +122,18 @@ nsk_bcsr4_t device_bcsr(const bcsr4x4_matrix &B)
 {
     const long long nblk = (long long)B.indcol.size();
     Key k(B.ptrow.data(), B.indcol.data(), B.coef.data(), B.nrows, nblk);
+    const unsigned long long fp = fingerprint(B.ptrow.data(), sizeof(int) * ((size_t)B.nrows + 1), B.indcol.data(),
+                                              sizeof(int) * (size_t)nblk, B.coef.data(), sizeof(double) * B.coef.size());
     auto it = g_bcsr.find(k);
-    if (it != g_bcsr.end()) return it->second;
+    if (it != g_bcsr.end()) {
+        if (it->second.print == fp) return it->second.handle;
+        nsk_bcsr4_destroy(it->second.handle);
+        g_bcsr.erase(it);
+    }
     nsk_bcsr4_t h = nullptr;
     int s = nsk_bcsr4_create(ctx(), B.nrows, nblk, B.ptrow.data(), B.indcol.data(), B.coef.data(), &h);
     if (s != NSK_OK) die("nsk_bcsr4_create", s);
-    g_bcsr[k] = h;
+    g_bcsr[k] = Entry<nsk_bcsr4_t>{h, fp};
     return h;
 }
 
@@ -229,8 +295,8 @@ void SpM2V_BCSR_AVX2(double *z, double *y, double *x, bcsr4x4_matrix &A, std::ve
 extern "C" void nsk_shim_reset(void)
 {
     std::lock_guard<std::mutex> lk(g_mu);
-    for (auto &kv : g_csr) nsk_csr_destroy(kv.second);
-    for (auto &kv : g_bcsr) nsk_bcsr4_destroy(kv.second);
+    for (auto &kv : g_csr) nsk_csr_destroy(kv.second.handle);
+    for (auto &kv : g_bcsr) nsk_bcsr4_destroy(kv.second.handle);
     g_csr.clear();
     g_bcsr.clear();
     if (g_ctx) nsk_ctx_destroy(g_ctx);

@@ -100,6 +100,19 @@ int main()
     SpM2V_BCSR_AVX2(z.data(), y.data(), x.data(), B, peB);
     bad += !same(y, r1) + !same(z, r2);
 
+    // the caller updates the coefficients IN PLACE (same addresses, same pattern: a new Jacobian every Newton step) and
+    // calls again without telling anyone -- the reference reads the live arrays, so must the shim
+    for (size_t j = 0; j < A.coef.size(); j++) A.coef[j] = A.coef[j] * 1.25 + 0.5;
+    host_spmv(A, x, r1, true); host_spmv(A, r1, r2, true);
+    SpMV_CSR_FMA(y.data(), x.data(), A);
+    bad += !same(y, r1);
+    SpM2V_CSR_OPT(z.data(), y.data(), x.data(), A, pe1);
+    bad += !same(y, r1) + !same(z, r2);
+    for (size_t j = 0; j < B.coef.size(); j++) B.coef[j] = -B.coef[j];
+    host_bcsr(x, r1);
+    SpMV_BCSR_FMA(y.data(), x.data(), B);
+    bad += !same(y, r1);
+
     nsk_shim_reset();
     std::printf("shim_driver: %s (%d mismatching outputs)\n", bad ? "FAILED" : "OK", bad);
     return bad ? 1 : 0;
