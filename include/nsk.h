@@ -156,6 +156,17 @@ int64_t nsk_coo2bcsr4(int nrow, int64_t nnz, const int *irow, const int *jcol, c
 int nsk_mtx_read(const char *path, int *nrow, int64_t *nnz, int **irow, int **jcol, double **val);
 void nsk_mtx_free(int *irow, int *jcol, double *val);
 
+/* ---- ordering (host; the reference has none; north star: "RCM-ordered blocks") ----------------- */
+/* Reverse Cuthill-McKee on the pattern of A + A^T: perm[new] = old.  Level-set BFS from a pseudo-peripheral node of
+ * every connected component, neighbours by ascending degree, the order reversed. */
+int nsk_rcm(int n, const int *ptrow, const int *indcol, int *perm);
+/* B = P A P^T (row new = row perm[new] of A, columns renumbered and sorted ascending, values with their entries).
+ * Output arrays sized n+1 / nnz by the caller; coef / coef_out may be NULL (pattern only). */
+int nsk_csr_permute(int n, const int *ptrow, const int *indcol, const double *coef, const int *perm, int *ptrow_out,
+                    int *indcol_out, double *coef_out);
+/* max |i - j| over the entries of A. */
+int64_t nsk_csr_bandwidth(int n, const int *ptrow, const int *indcol);
+
 /* ---- the packed format's host half (no GPU): used by the CPU test-suite to check the packer --------------- */
 /* Packs a CSR operator for table entry `variant` of the packed kernel (0-based); nsk_pack_host_why returns "" or
  * the reason it does not pack; nsk_pack_host_expand rebuilds CSR from the blobs (global columns through the tiles'

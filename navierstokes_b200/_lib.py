@@ -46,6 +46,9 @@ SIGNATURES = {
     "nsk_mtx_read": (C.c_int, [C.c_char_p, c_int_p, c_int64_p, C.POINTER(C.POINTER(C.c_int)), C.POINTER(C.POINTER(C.c_int)),
                                C.POINTER(C.POINTER(C.c_double))]),
     "nsk_mtx_free": (None, [C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double)]),
+    "nsk_rcm": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nsk_csr_permute": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nsk_csr_bandwidth": (C.c_int64, [C.c_int, C.c_void_p, C.c_void_p]),
     "nsk_pack_host_create": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, c_void_pp]),
     "nsk_pack_host_why": (C.c_char_p, [C.c_void_p]),
     "nsk_pack_host_bytes": (C.c_int64, [C.c_void_p]),

@@ -23,7 +23,7 @@ NVCC_FLAGS = [
 
 
 def _sources():
-    return sorted(CSRC.glob("*.cu")) + [CSRC / "comm.cpp", CSRC / "dist_plan.cpp", CSRC / "ingest.cpp"]
+    return sorted(CSRC.glob("*.cu")) + [CSRC / "comm.cpp", CSRC / "dist_plan.cpp", CSRC / "ingest.cpp", CSRC / "reorder.cpp"]
 
 
 def _stamp(files, extra=""):

@@ -208,12 +208,38 @@ def tet_p1_laplacian(m: int, permute_seed: int | None = None, rcm: bool = False,
     if permute_seed is not None:
         perm = np.random.default_rng(permute_seed).permutation(n)
         A = A[perm][:, perm].tocsr()
-    if rcm:
-        from scipy.sparse.csgraph import reverse_cuthill_mckee
-        p = reverse_cuthill_mckee(A, symmetric_mode=True)
-        A = A[p][:, p].tocsr()
     A.sort_indices()
-    return _from_scipy(A)
+    out = _from_scipy(A)
+    if rcm:
+        out = rcm_reorder(out)
+    return out
+
+
+def rcm_reorder(A: Csr) -> Csr:
+    """Reverse Cuthill-McKee through the library's own host code (nsk_rcm + nsk_csr_permute, csrc/reorder.cpp)."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    n = A.nrows
+    ptrow = np.ascontiguousarray(A.ptrow, np.int32)
+    indcol = np.ascontiguousarray(A.indcol, np.int32)
+    coef = np.ascontiguousarray(A.coef, np.float64)
+    perm = np.empty(n, np.int32)
+    _lib.check(lib.nsk_rcm(n, ptrow.ctypes.data, indcol.ctypes.data, perm.ctypes.data))
+    p2 = np.empty(n + 1, np.int32)
+    c2 = np.empty(len(indcol), np.int32)
+    v2 = np.empty(len(indcol), np.float64)
+    _lib.check(lib.nsk_csr_permute(n, ptrow.ctypes.data, indcol.ctypes.data, coef.ctypes.data, perm.ctypes.data,
+                                   p2.ctypes.data, c2.ctypes.data, v2.ctypes.data))
+    return Csr(n=n, ptrow=p2, indcol=c2, coef=v2, ncols=n)
+
+
+def bandwidth(A: Csr) -> int:
+    from . import _lib
+    lib = _lib.load()
+    ptrow = np.ascontiguousarray(A.ptrow, np.int32)
+    indcol = np.ascontiguousarray(A.indcol, np.int32)
+    return int(lib.nsk_csr_bandwidth(A.nrows, ptrow.ctypes.data, indcol.ctypes.data))
 
 
 def fem_baij4(m: int, jitter: float = 0.2, float_round: bool = True) -> Csr:
