@@ -48,7 +48,15 @@ int nsk_mpk_local(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
     const bool automatic = sel == 0;
     // default: the sliced-ELL level pipeline for operators made of pattern tiles (stencils, regular bands: staged
     // coefficients, no per-entry index), else the packed one when the operator packs, else k products
-    if (automatic) sel = (k > 1 && nsk_sell_uniform(A)) ? 5 : 4;
+    if (automatic) {
+        sel = 4;
+        if (k > 1 && nsk_sell_uniform(A)) sel = 5;
+        // Unstructured operators (explicit columns, x gathered entry by entry) stay with k products: measured on the
+        // RCM-ordered tetrahedral P1 Laplacian (8.1 M rows, 15 per row), the product already runs at the HBM copy rate
+        // (0.237 ms, 6.8 TB/s) and both it and the fused sliced-ELL pipeline (mpk_kernel = 5: 2.43 ms for k = 8 against
+        // 1.90 ms for 8 products) sit on the same bound -- the L1 wavefronts of the uncoalesced x gathers, ~12 per
+        // warp-load -- which re-reading the operator from L2 instead of HBM does not move (profiles/r02_configs.txt).
+    }
     const bool sell = sel == 5 && k > 1 && nsk_sell_applicable(A);
     if (sel == 5 && !sell) sel = 4;
     if (sell || (sel == 4 && k > 1 && nsk_packed_applicable(A))) {

@@ -176,7 +176,8 @@ int nsk_sell_run(nsk_csr_t A, int k, const double *d_x, double *const *d_levels,
 int nsk_sell_run2(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, const double *d_x2,
                   double *const *d_levels2, nsk_mode mode, const int *level_rows);
 bool nsk_sell_applicable(nsk_csr_t A);
-bool nsk_sell_uniform(nsk_csr_t A);  // all tiles pattern tiles of one width (stencils, regular bands)
+bool nsk_sell_uniform(nsk_csr_t A);
+bool nsk_sell_explicit_staged(nsk_csr_t A);  // explicit columns, lengths + columns of every tile fit a stage  // all tiles pattern tiles of one width (stencils, regular bands)
 size_t nsk_sell_bytes(nsk_csr_t A);
 void nsk_sell_free(nsk_csr_t A);
 int nsk_sell_check_error(nsk_csr_t A);

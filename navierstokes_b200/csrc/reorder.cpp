@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <numeric>
+#include <thread>
 #include <vector>
 
 #include "../../include/nsk.h"
@@ -18,6 +19,20 @@
 #define NSK_API extern "C" __attribute__((visibility("default")))
 
 namespace {
+
+// rows [0, n) split over the host threads
+template <class F>
+void parallel_rows(int n, F body)
+{
+    const int nth = (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    if (n < 100000 || nth == 1) { body(0, n); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nth; t++) {
+        const int a = (int)((int64_t)n * t / nth), b = (int)((int64_t)n * (t + 1) / nth);
+        th.emplace_back(body, a, b);
+    }
+    for (auto &x : th) x.join();
+}
 
 // adjacency of A + A^T without the diagonal, neighbours sorted and unique
 void symmetric_pattern(int n, const int *ptrow, const int *indcol, std::vector<int64_t> &ptr, std::vector<int> &adj)
@@ -41,19 +56,20 @@ void symmetric_pattern(int n, const int *ptrow, const int *indcol, std::vector<i
             raw[(size_t)fill[i]++] = c;
             raw[(size_t)fill[c]++] = i;
         }
-    adj.clear();
-    adj.reserve(raw.size());
     std::vector<int64_t> nptr((size_t)n + 1, 0);
-    for (int i = 0; i < n; i++) {
-        std::sort(raw.begin() + ptr[i], raw.begin() + ptr[(size_t)i + 1]);
-        int last = -1;
-        for (int64_t p = ptr[i]; p < ptr[(size_t)i + 1]; p++)
-            if (raw[(size_t)p] != last) {
-                adj.push_back(raw[(size_t)p]);
-                last = raw[(size_t)p];
-            }
-        nptr[(size_t)i + 1] = (int64_t)adj.size();
-    }
+    parallel_rows(n, [&](int a, int b) {  // sort every row's list, unique in place, remember the count
+        for (int i = a; i < b; i++) {
+            int *first = raw.data() + ptr[i], *last = raw.data() + ptr[(size_t)i + 1];
+            std::sort(first, last);
+            nptr[(size_t)i + 1] = std::unique(first, last) - first;
+        }
+    });
+    for (int i = 0; i < n; i++) nptr[(size_t)i + 1] += nptr[i];
+    adj.resize((size_t)nptr[n]);
+    parallel_rows(n, [&](int a, int b) {
+        for (int i = a; i < b; i++)
+            std::copy(raw.data() + ptr[i], raw.data() + ptr[i] + (nptr[(size_t)i + 1] - nptr[i]), adj.data() + nptr[i]);
+    });
     ptr.swap(nptr);
 }
 
@@ -154,25 +170,26 @@ NSK_API int nsk_csr_permute(int n, const int *ptrow, const int *indcol, const do
     }
     ptrow_out[0] = 0;
     for (int i = 0; i < n; i++) ptrow_out[i + 1] = ptrow_out[i] + (ptrow[perm[i] + 1] - ptrow[perm[i]]);
-    std::vector<std::pair<int, double>> row;
-    for (int i = 0; i < n; i++) {
-        const int o = perm[i];
-        row.clear();
-        for (int j = ptrow[o]; j < ptrow[o + 1]; j++) {
-            const int c = indcol[j];
-            if (c < 0 || c >= n) return NSK_ERR_INVALID;
-            row.emplace_back(inv[c], coef ? coef[j] : 0.0);
+    for (int i = 0; i < n; i++)
+        for (int j = ptrow[i]; j < ptrow[i + 1]; j++)
+            if (indcol[j] < 0 || indcol[j] >= n) return NSK_ERR_INVALID;
+    parallel_rows(n, [&](int a, int b) {
+        std::vector<std::pair<int, double>> row;
+        for (int i = a; i < b; i++) {
+            const int o = perm[i];
+            row.clear();
+            for (int j = ptrow[o]; j < ptrow[o + 1]; j++) row.emplace_back(inv[indcol[j]], coef ? coef[j] : 0.0);
+            std::stable_sort(row.begin(), row.end(), [](const std::pair<int, double> &x, const std::pair<int, double> &y) {
+                return x.first < y.first;
+            });
+            int q = ptrow_out[i];
+            for (const auto &e : row) {
+                indcol_out[q] = e.first;
+                if (coef_out) coef_out[q] = e.second;
+                q++;
+            }
         }
-        std::stable_sort(row.begin(), row.end(), [](const std::pair<int, double> &a, const std::pair<int, double> &b) {
-            return a.first < b.first;
-        });
-        int q = ptrow_out[i];
-        for (const auto &e : row) {
-            indcol_out[q] = e.first;
-            if (coef_out) coef_out[q] = e.second;
-            q++;
-        }
-    }
+    });
     return NSK_OK;
 }
 

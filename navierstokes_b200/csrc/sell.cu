@@ -31,6 +31,7 @@
 // The host half (tiling, pattern detection, blobs, level schedule, CPU model of the protocol) is plain C++ and is
 // tested without a GPU (tests/test_sell_host.py).
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <cstring>
 #include <functional>
@@ -815,14 +816,17 @@ static SlLaunch sl_lookup_stream(int nv, int w, int depth, int rows)
 // hold the row's x entries in flight: W ordinary cached loads issued the moment the item's inputs are complete, then the
 // chain with coefficients read from the stage.  Per row and level the shared-memory / L1 data path carries the
 // coefficients twice (bulk write + read) and x once -- against coefficients, local columns AND x twice in packed.cu.
+constexpr int SL_EXPLICIT_STAGE = 24576;         // stage of the explicit-column instances: lengths + columns of a tile
 constexpr int SLT_NCW = SL_ROWS / 32;            // consumer warps: thread t owns row t of every tile
 constexpr int SLT_THREADS = SL_ROWS + 64;        // + dependency warp + service warp (producer and publisher)
 
 template <int NV, int W, int NS, int MINB>
 __global__ void __launch_bounds__(SLT_THREADS, MINB) sell_tma_kernel(const SlParams P)
 {
-    static_assert(W >= 1 && W <= SL_PSLOTS, "pattern width");
-    constexpr int STAGE = SL_ROWS + 8 * W * SL_ROWS;  // == sl_blob_bytes_pattern(W), a multiple of 128
+    static_assert(W >= 0 && W <= SL_PSLOTS, "pattern width (0: tiles with explicit columns)");
+    // pattern tiles: a stage holds the whole blob (mask + W x 256 coefficients); explicit tiles: the lengths + columns
+    // prefix of the blob (the coefficients are loaded by the consumers together with the x gathers)
+    constexpr int STAGE = W > 0 ? SL_ROWS + 8 * W * SL_ROWS : SL_EXPLICIT_STAGE;
     extern __shared__ __align__(128) unsigned char stages[];  // NS stages
     __shared__ uint64_t s_full[NS];           // the stage's tile has landed (bulk copy complete_tx)
     __shared__ unsigned int s_free[NS];       // consumer warps that finished the stage's tile, counted over the launch
@@ -871,7 +875,7 @@ __global__ void __launch_bounds__(SLT_THREADS, MINB) sell_tma_kernel(const SlPar
         //  publisher -- (k > 1) one gpu-scope fence for everything found finished at that moment, then one RED per item.
         //               Consumers bump s_fin[slot] with release.cta after their stores; the acquire here + fence + RED is
         //               cumulative over those stores. =====
-        const long long *tl8 = reinterpret_cast<const long long *>(P.ltiles[level]);  // word pair 0 of a tile = blob offset
+        const int4 *tl4p = reinterpret_cast<const int4 *>(P.ltiles[level]);  // quarter 0: blob offset; quarter 1: width, fmt, rp, bytes
         const int *itw = reinterpret_cast<const int *>(P.items[level]);
         int *cnt = P.counters + (size_t)level * P.ngroups;
         const bool last_reader = (P.flags & 1) && level == P.k - 1;
@@ -883,6 +887,7 @@ __global__ void __launch_bounds__(SLT_THREADS, MINB) sell_tma_kernel(const SlPar
         }
         const int n_pub = P.k > 1 ? n_my : 0;
         long long off_l = 0;  // lane u: blob offset of tile (n & ~31) + u
+        int pre_l = STAGE, blob_l = 0;  // ... explicit tiles: bytes of its lengths + columns prefix, of the whole blob
         int grp = 0;          // lane u: group of item (ip & ~31) + u
         int n = 0, ip = 0, off_base = -1, grp_base = -1;
         unsigned long long t_idle = 0;
@@ -898,14 +903,26 @@ __global__ void __launch_bounds__(SLT_THREADS, MINB) sell_tma_kernel(const SlPar
                         off_l = 0;
                         if (nn < total) {
                             const long long it = nn / M, j = nn - it * M;
-                            off_l = __ldg(tl8 + (((long long)c + it * G) * M + j) * 8);
+                            const int4 *q = tl4p + (((long long)c + it * G) * M + j) * 4;
+                            const int4 q0 = __ldg(q);
+                            off_l = ((long long)(unsigned int)q0.x) | ((long long)q0.y << 32);
+                            if (W == 0) {
+                                const int4 q1 = __ldg(q + 1);
+                                pre_l = sl_round_up(2 * q1.z, 128) + 128 * q1.x;
+                                blob_l = q1.w;
+                            }
                         }
                     }
                     const long long off = __shfl_sync(0xffffffffu, off_l, n & 31);
+                    const int pre = W == 0 ? __shfl_sync(0xffffffffu, pre_l, n & 31) : STAGE;
+                    const int blob_bytes = W == 0 ? __shfl_sync(0xffffffffu, blob_l, n & 31) : STAGE;
                     if (lane == 0) {
-                        mbar_arrive_expect_tx(&s_full[st], (uint32_t)STAGE);
-                        if (last_reader) bulk_g2s_hint(stages + (size_t)st * STAGE, P.blobs + off, (uint32_t)STAGE, &s_full[st], pol);
-                        else bulk_g2s(stages + (size_t)st * STAGE, P.blobs + off, (uint32_t)STAGE, &s_full[st]);
+                        mbar_arrive_expect_tx(&s_full[st], (uint32_t)pre);
+                        if (last_reader) bulk_g2s_hint(stages + (size_t)st * STAGE, P.blobs + off, (uint32_t)pre, &s_full[st], pol);
+                        else bulk_g2s(stages + (size_t)st * STAGE, P.blobs + off, (uint32_t)pre, &s_full[st]);
+                        // explicit tiles: the coefficients are read by the consumers; level 0 streams them from HBM, so
+                        // pull them into L2 now (NS tiles ahead of their use)
+                        if (W == 0 && level == 0 && blob_bytes > pre) sl_prefetch_l2(P.blobs + off + pre, (uint32_t)(blob_bytes - pre));
                     }
                     ++n;
                     progress = true;
@@ -1022,36 +1039,79 @@ __global__ void __launch_bounds__(SLT_THREADS, MINB) sell_tma_kernel(const SlPar
             const int4 r0 = *reinterpret_cast<const int4 *>(d + 8), r1 = *reinterpret_cast<const int4 *>(d + 12);
             const int rel[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
             const int row = q.x + t;
-            const int rowc = min(row, cmax);
-            mbar_wait(&s_full[st], ph);
-            const unsigned int m = stages[(size_t)st * STAGE + t];
             const double *src = s_cta.src[0];
             const double *src2 = NV == 2 ? s_cta.src[1] : nullptr;
-            double xv[NV][W];
-#pragma unroll
-            for (int e = 0; e < W; e++) {
-                const int idx = rowc + ((m & (1u << e)) ? rel[e] : 0);  // a slot the row lacks reads its own x entry
-                xv[0][e] = sl_ld_x(src + idx);
-                if (NV == 2) xv[NV - 1][e] = sl_ld_x(src2 + idx);
-            }
-            const double *vs = val + (size_t)st * (STAGE / 8);
             double acc0 = 0.0, acc1 = 0.0;
-            if (s_cta.muladd) {
+            if constexpr (W > 0) {
+                const int rowc = min(row, cmax);
+                mbar_wait(&s_full[st], ph);
+                const unsigned int m = stages[(size_t)st * STAGE + t];
+                double xv[NV][W];
 #pragma unroll
-                for (int e = 0; e < W; e++)
-                    if (m & (1u << e)) {
-                        const double a = vs[e * SL_ROWS];
-                        acc0 = row_op<true>(a, xv[0][e], acc0);
-                        if (NV == 2) acc1 = row_op<true>(a, xv[NV - 1][e], acc1);
-                    }
+                for (int e = 0; e < W; e++) {
+                    const int idx = rowc + ((m & (1u << e)) ? rel[e] : 0);  // a slot the row lacks reads its own x entry
+                    xv[0][e] = sl_ld_x(src + idx);
+                    if (NV == 2) xv[NV - 1][e] = sl_ld_x(src2 + idx);
+                }
+                const double *vs = val + (size_t)st * (STAGE / 8);
+                if (s_cta.muladd) {
+#pragma unroll
+                    for (int e = 0; e < W; e++)
+                        if (m & (1u << e)) {
+                            const double a = vs[e * SL_ROWS];
+                            acc0 = row_op<true>(a, xv[0][e], acc0);
+                            if (NV == 2) acc1 = row_op<true>(a, xv[NV - 1][e], acc1);
+                        }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < W; e++)
+                        if (m & (1u << e)) {
+                            const double a = vs[e * SL_ROWS];
+                            acc0 = row_op<false>(a, xv[0][e], acc0);
+                            if (NV == 2) acc1 = row_op<false>(a, xv[NV - 1][e], acc1);
+                        }
+                }
             } else {
+                // explicit columns: rel[s] = slots of slice s (this warp's rows: slice `warp`), the slices stored one
+                // after the other; lengths and columns from the stage, coefficients and x from global in batches of 8
+                const int rp = d[6], tot = d[4];
+                int soff = 0;
 #pragma unroll
-                for (int e = 0; e < W; e++)
-                    if (m & (1u << e)) {
-                        const double a = vs[e * SL_ROWS];
-                        acc0 = row_op<false>(a, xv[0][e], acc0);
-                        if (NV == 2) acc1 = row_op<false>(a, xv[NV - 1][e], acc1);
+                for (int sl = 0; sl < 8; sl++)
+                    if (sl < warp) soff += rel[sl];
+                const int mine = warp * 32 < rp ? d[8 + warp] : 0;
+                const long long off = ((long long)(unsigned int)d[0]) | ((long long)d[1] << 32);
+                const int pre = sl_round_up(2 * rp, 128) + 128 * tot;
+                const double *vg = reinterpret_cast<const double *>(P.blobs + off + pre) + (size_t)soff * 32 + lane;
+                const uint64_t pol = sl_policy(s_cta.last != 0);
+                mbar_wait(&s_full[st], ph);
+                const unsigned char *stg = stages + (size_t)st * STAGE;
+                const int len = warp * 32 < rp ? (int)reinterpret_cast<const unsigned short *>(stg)[t] : 0;
+                const int *cs = reinterpret_cast<const int *>(stg + sl_round_up(2 * rp, 128)) + (size_t)soff * 32 + lane;
+                for (int e0 = 0; e0 < mine; e0 += 8) {
+                    double a[8], xv[NV][8];
+                    // every load unconditional (each destination register defined once): a batch that runs past the
+                    // slice's last slot re-reads that slot; padding entries carry a valid column (0); neither is used
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int e = min(e0 + u, mine - 1);
+                        const int cc = cs[e * 32];
+                        a[u] = sl_ld_coef(vg + (size_t)e * 32, pol);
+                        xv[0][u] = sl_ld_x(src + cc);
+                        if (NV == 2) xv[NV - 1][u] = sl_ld_x(src2 + cc);
                     }
+#pragma unroll
+                    for (int u = 0; u < 8; u++)
+                        if (e0 + u < len) {
+                            if (s_cta.muladd) {
+                                acc0 = row_op<true>(a[u], xv[0][u], acc0);
+                                if (NV == 2) acc1 = row_op<true>(a[u], xv[NV - 1][u], acc1);
+                            } else {
+                                acc0 = row_op<false>(a[u], xv[0][u], acc0);
+                                if (NV == 2) acc1 = row_op<false>(a[u], xv[NV - 1][u], acc1);
+                            }
+                        }
+                }
             }
             if (t < q.y && row < s_cta.row_end) sl_store_row<NV>(P, s_cta, row, acc0, acc1, dot_acc);
             __syncwarp();
@@ -1112,12 +1172,18 @@ static sl_fn sl_lookup_tma_w(int w, int *stage_bytes)
     }
     return nullptr;
 }
-// stages per CTA: 3 (four CTAs of 48 registers per SM) or 4 (three CTAs of 64 registers); two right-hand sides: 3 CTAs
+// stages per CTA: 3 (four CTAs of 48 registers per SM) or 4 (three CTAs of 64 registers); two right-hand sides: 3 CTAs;
+// w = 0: explicit-column tiles (3 stages of 24 KB, three CTAs per SM)
 static SlLaunch sl_lookup_tma(int nv, int w, int ns, int *smem)
 {
     SlLaunch L;
     L.threads = SLT_THREADS;
     L.launch_regs = 0;  // no register hand-over in this kernel
+    if (w == 0) {
+        L.fn = nv == 2 ? sell_tma_kernel<2, 0, 3, 2> : sell_tma_kernel<1, 0, 3, 3>;
+        *smem = SL_EXPLICIT_STAGE * 3;
+        return L;
+    }
     int sb = 0;
     if (nv == 2) { L.fn = sl_lookup_tma_w<2, 3, 3>(w, &sb); ns = 3; }
     else if (ns >= 4) { L.fn = sl_lookup_tma_w<1, 4, 3>(w, &sb); ns = 4; }
@@ -1136,6 +1202,7 @@ struct SellHost {
     size_t blob_bytes = 0;
     int n_pattern = 0;
     int uniform_width = 0;  // > 0: every tile is a pattern tile stored with this many slots
+    int explicit_prefix = 0;  // > 0: every tile has explicit columns; largest lengths + columns prefix of a blob (bytes)
 };
 
 static void sl_parallel(int n, const std::function<void(int)> &body)
@@ -1179,6 +1246,7 @@ static std::string sl_pack_host(int n, int n_cols, int64_t nnz, const int *ptrow
     st.assign(ntiles, SlTile());
     // 1. per tile: format, geometry, size
     std::atomic<int> too_long(0);
+    std::vector<std::array<int, 8>> sw_all((size_t)ntiles);  // the slices' widths (explicit layout)
     sl_parallel(ntiles, [&](int t) {
         const nsk_tile &tl = tiles[t];
         SlTile &d = st[t];
@@ -1243,8 +1311,10 @@ static std::string sl_pack_host(int n, int n_cols, int64_t nnz, const int *ptrow
             d.fmt = SL_FMT_EXPLICIT;
             int tot = 0;
             for (int s = 0; s < 8; s++) { d.rel[s] = sw[s]; tot += sw[s]; }
+            d.width = tot;  // explicit tiles: slots summed over the slices (sizes the column block)
             d.bytes = sl_blob_bytes_explicit(d.rp, tot);
         }
+        sw_all[t] = {sw[0], sw[1], sw[2], sw[3], sw[4], sw[5], sw[6], sw[7]};
     });
     if (too_long.load()) return "a row is longer than 65535 entries";
     size_t total = 0;
@@ -1256,11 +1326,25 @@ static std::string sl_pack_host(int n, int n_cols, int64_t nnz, const int *ptrow
     // An operator made of pattern tiles only gets ONE width: narrower tiles (lines on a domain face lack a neighbour
     // line) are padded with slots no row has, so the streaming kernel runs one straight-line instance over all of them.
     out.uniform_width = 0;
+    out.explicit_prefix = 0;
     if (n_pattern == ntiles && wmax >= 1) {
         out.uniform_width = wmax;
         for (int t = 0; t < ntiles; t++) {
             st[t].width = wmax;  // rel[] beyond the tile's own slots is already zero
             st[t].bytes = sl_blob_bytes_pattern(wmax);
+        }
+    } else {
+        // Anything else is stored with explicit columns THROUGHOUT (a pattern tile here and there would only make the
+        // kernels branch): the staged kernel copies a tile's lengths + columns (a contiguous prefix of its blob).
+        n_pattern = 0;
+        for (int t = 0; t < ntiles; t++) {
+            SlTile &d = st[t];
+            int tot = 0;
+            for (int s = 0; s < 8; s++) { d.rel[s] = sw_all[t][s]; tot += d.rel[s]; }
+            d.fmt = SL_FMT_EXPLICIT;
+            d.width = tot;
+            d.bytes = sl_blob_bytes_explicit(d.rp, tot);
+            out.explicit_prefix = std::max(out.explicit_prefix, sl_round_up(2 * d.rp, 128) + 128 * tot);
         }
     }
     for (int t = 0; t < ntiles; t++) {
@@ -1670,7 +1754,7 @@ struct SlPlan {
 struct SellOp {
     bool ok = false;
     std::string why;
-    int ntiles = 0, n_pattern = 0, uniform_width = 0;
+    int ntiles = 0, n_pattern = 0, uniform_width = 0, explicit_prefix = 0;
     size_t blob_bytes = 0;
     unsigned char *d_blobs = nullptr;
     SlTile *d_tiles = nullptr;
@@ -1748,6 +1832,7 @@ static SellOp *sl_get(nsk_csr_t A)
     op->ntiles = ntiles;
     op->n_pattern = H.n_pattern;
     op->uniform_width = H.uniform_width;
+    op->explicit_prefix = H.explicit_prefix;
     op->blob_bytes = H.blob_bytes;
     op->h_tiles.swap(H.stiles);
     op->csr_view.tile_rows = SL_ROWS;
@@ -1889,7 +1974,9 @@ static int sl_run(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
     const int rows = ctx->opt.sell_rows == 2 ? 2 : 1;
     // all-pattern operators, default: coefficients staged by bulk copies (option sell_tma: 0 = default 4 stages, n = n
     // stages, < 0 = off -> the register kernels above)
-    const bool tma = op->uniform_width > 0 && ctx->opt.sell_tma >= 0;
+    // operators with explicit columns whose lengths + columns fit a stage: the same kernel, columns staged
+    const bool tma_e = op->uniform_width == 0 && op->explicit_prefix > 0 && op->explicit_prefix <= SL_EXPLICIT_STAGE;
+    const bool tma = (op->uniform_width > 0 || tma_e) && ctx->opt.sell_tma >= 0;
     int smem = 0;
     const SlLaunch L = tma ? sl_lookup_tma(nv, op->uniform_width, ctx->opt.sell_tma == 0 ? 3 : (int)ctx->opt.sell_tma, &smem)
                            : stream ? sl_lookup_stream(nv, op->uniform_width, depth, rows)
@@ -1990,6 +2077,15 @@ bool nsk_sell_applicable(nsk_csr_t A)
 {
     if (A->n == 0 || A->nnz == 0) return false;
     return sl_get(A)->ok;
+}
+
+// Explicit-column operator whose tiles' lengths + columns fit a stage of the staged kernel (unstructured FEM operators with
+// up to ~23 entries per row on average).
+bool nsk_sell_explicit_staged(nsk_csr_t A)
+{
+    if (A->n == 0 || A->nnz == 0) return false;
+    SellOp *op = sl_get(A);
+    return op->ok && op->uniform_width == 0 && op->explicit_prefix > 0 && op->explicit_prefix <= SL_EXPLICIT_STAGE;
 }
 
 // Every tile is a pattern tile of one width: the staged-coefficient kernel applies (stencils, regular bands).
