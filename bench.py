@@ -266,7 +266,7 @@ def main():
         x_host = ctx.pinned(dop.n_owned)
         x_host[:] = np.sin(0.001 * (dop.row_begin + np.arange(dop.n_owned)))
         lv_host = [ctx.pinned(dop.n_owned) for _ in range(K_POWERS)]
-        dx = dop.new_vector()
+        dx = dop.new_vector(shared=True)  # registered: its halo is pushed over NVLink peer memory (no NCCL on the path)
         dop.set_owned(dx, x_host)
         dlv = [dop.new_vector() for _ in range(K_POWERS)]
         step_dev = lambda: dop.mpk(K_POWERS, dx, dlv)                     # noqa: E731
@@ -398,7 +398,7 @@ def main():
         from navierstokes_b200 import distributed as nd
         sop = nd.DistStencil3D(ctx, dist, GRID, GRID, GRID, halo_depth=K_POWERS)
         sx_host = np.sin(0.001 * (sop.row_begin + np.arange(sop.n_owned)))
-        sdx = sop.new_vector()
+        sdx = sop.new_vector(shared=True)
         sop.set_owned(sdx, sx_host)
         sdlv = [sop.new_vector() for _ in range(K_POWERS)]
         for _ in range(5):
@@ -419,6 +419,16 @@ def main():
             sop.halo_exchange(sdx, K_POWERS)
         g1.record()
         h_ms = max_over_ranks(g0.elapsed_ms(g1) / args.steps)
+        ctx.set_option("halo_push", 0)  # the same exchange through pack + ncclSend/ncclRecv + unpack, for comparison
+        for _ in range(3):
+            sop.halo_exchange(sdx, K_POWERS)
+        barrier()
+        g0.record()
+        for _ in range(args.steps):
+            sop.halo_exchange(sdx, K_POWERS)
+        g1.record()
+        hn_ms = max_over_ranks(g0.elapsed_ms(g1) / args.steps)
+        ctx.set_option("halo_push", 1)
         sbad = 0
         if not args.no_parity:
             got = [sop.get_owned(v) for v in sdlv]
@@ -431,7 +441,7 @@ def main():
         spmv_tot = 12 * nnz_tot + 4 * (n_tot + 1) + 16 * n_tot
         out["strong"] = {"workload": f"3D 7-point Laplacian {GRID}^3 split over {world} GPUs (z-slabs), k={K_POWERS}",
                          "ms_per_step": s_ms, "value": K_POWERS * spmv_tot / s_ms / 1e6, "unit": "GB/s",
-                         "halo_exchange_us": h_ms * 1e3,
+                         "halo_exchange_us": h_ms * 1e3, "halo_exchange_nccl_us": hn_ms * 1e3,
                          "efficiency_vs_n1_note": "t(1 GPU) / (N * t(N GPUs)) with t(1 GPU) = this build's N=1 ms_per_step "
                                                   "(the driver's SCALE record); not computed here",
                          "parity": {"ranks_ok": int(t[0].item()), "ranks": world, "bitwise": bool(int(t[0].item()) == world)}}

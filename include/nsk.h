@@ -336,6 +336,27 @@ int nsk_csr_owned_rows(nsk_csr_t A); /* n_owned for a distributed operator, n ot
 /* Refreshes ghost rings 1..depth of a local device vector (pack kernel + grouped ncclSend/ncclRecv). */
 int nsk_halo_exchange(nsk_csr_t A, double *xlocal, int depth);
 
+/* ---- halo push over NVLink peer memory (optional; one node, one process per GPU) ---------------------------------
+ * A vector registered with nsk_dist_vector_register is mapped into the neighbours' address spaces (CUDA IPC); for such
+ * a vector the depth-k halo of nsk_mpk / nsk_spmv is ONE kernel that stores the entries the neighbours need straight
+ * into their ghost slots and raises an arrival flag there, plus a one-warp wait for the neighbours' flags -- no send /
+ * receive buffers, no unpack, no NCCL call on the path.  Setup, once per operator (every rank, same order):
+ *   nsk_dist_push_flags(A, &f);  nsk_ipc_export(ctx, f, h)          -> send h and, per neighbour p, nsk_dist_recv_layout(A, p, ..)
+ *   for every neighbour p: nsk_ipc_import(ctx, h_p, &fp);  nsk_dist_push_peer(A, p, my index in p's peer list,
+ *                                                                              p's recv layout for me, fp)
+ * then per vector: allocate with nsk_malloc, export, import the neighbours' handles, nsk_dist_vector_register.
+ * Unregistered vectors (and the option halo_push = 0) keep the NCCL exchange. */
+#define NSK_IPC_HANDLE_BYTES 80 /* CUDA IPC handle of the enclosing allocation + the pointer's offset in it */
+int nsk_ipc_export(nsk_ctx_t ctx, void *devptr, unsigned char *handle /* NSK_IPC_HANDLE_BYTES */);
+int nsk_ipc_import(nsk_ctx_t ctx, const unsigned char *handle, void **peerptr); /* stays mapped until nsk_ctx_destroy */
+int nsk_dist_push_flags(nsk_csr_t A, void **flags);
+int nsk_dist_recv_layout(nsk_csr_t A, int peer_rank, int *ring_start, int *ring_count);
+int nsk_dist_peer_count(nsk_csr_t A);
+int nsk_dist_peer_rank(nsk_csr_t A, int index);
+int nsk_dist_push_peer(nsk_csr_t A, int peer_rank, int index_at_peer, const int *peer_ring_start, const int *peer_ring_count,
+                       void *peer_flags);
+int nsk_dist_vector_register(nsk_csr_t A, double *local, double *const *peer_ptrs);
+
 #ifdef __cplusplus
 }
 #endif

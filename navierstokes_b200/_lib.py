@@ -102,6 +102,14 @@ SIGNATURES = {
     "nsk_csr_create_dist": (C.c_int, [C.c_void_p, C.c_void_p, c_void_pp]),
     "nsk_csr_owned_rows": (C.c_int, [C.c_void_p]),
     "nsk_halo_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "nsk_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nsk_ipc_import": (C.c_int, [C.c_void_p, C.c_void_p, c_void_pp]),
+    "nsk_dist_push_flags": (C.c_int, [C.c_void_p, c_void_pp]),
+    "nsk_dist_recv_layout": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "nsk_dist_peer_count": (C.c_int, [C.c_void_p]),
+    "nsk_dist_peer_rank": (C.c_int, [C.c_void_p, C.c_int]),
+    "nsk_dist_push_peer": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nsk_dist_vector_register": (C.c_int, [C.c_void_p, C.c_void_p, c_void_pp]),
 }
 
 _lib = None

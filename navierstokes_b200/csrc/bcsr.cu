@@ -13,7 +13,18 @@
 #include "nsk_internal.h"
 #include "stream_common.cuh"
 
-template <bool MULADD>
+// The value stream is read exactly once: no L1 allocation, so L1 keeps the x sectors the four threads of a block row share.
+__device__ __forceinline__ double2 ld_stream(const double2 *p)
+{
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
+// Loads of BATCH consecutive blocks (block column, two 16-byte halves of the thread's block row, the 32-byte x sector)
+// are all issued before the first dependent fma, so one thread keeps 4 x BATCH 16-byte loads in flight instead of 4: the
+// chain itself stays strictly in (block, j) order.
+template <bool MULADD, int BATCH>
 __global__ void __launch_bounds__(256) spmv_bcsr4_kernel(int nbrows, const int *__restrict__ ptrow,
                                                          const int *__restrict__ indcol,
                                                          const double *__restrict__ coef,
@@ -24,12 +35,37 @@ __global__ void __launch_bounds__(256) spmv_bcsr4_kernel(int nbrows, const int *
     if (bi >= nbrows) return;
     const int p = ptrow[bi], q = ptrow[bi + 1];
     double acc = 0.0;
-#pragma unroll 2
-    for (int ia = p; ia < q; ia++) {
+    int ia = p;
+    for (; ia + BATCH <= q; ia += BATCH) {
+        int bj[BATCH];
+        double2 a01[BATCH], a23[BATCH], x01[BATCH], x23[BATCH];
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) bj[u] = __ldg(indcol + ia + u);
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) {
+            const double2 *blk = reinterpret_cast<const double2 *>(coef + 16 * (size_t)(ia + u) + 4 * i);
+            a01[u] = ld_stream(blk);
+            a23[u] = ld_stream(blk + 1);
+        }
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) {
+            const double2 *xv = reinterpret_cast<const double2 *>(x + 4 * (size_t)bj[u]);
+            x01[u] = __ldg(xv);
+            x23[u] = __ldg(xv + 1);
+        }
+#pragma unroll
+        for (int u = 0; u < BATCH; u++) {
+            acc = row_op<MULADD>(a01[u].x, x01[u].x, acc);
+            acc = row_op<MULADD>(a01[u].y, x01[u].y, acc);
+            acc = row_op<MULADD>(a23[u].x, x23[u].x, acc);
+            acc = row_op<MULADD>(a23[u].y, x23[u].y, acc);
+        }
+    }
+    for (; ia < q; ia++) {
         const int bj = __ldg(indcol + ia);
         const double2 *blk = reinterpret_cast<const double2 *>(coef + 16 * (size_t)ia + 4 * i);
         const double2 *xv = reinterpret_cast<const double2 *>(x + 4 * (size_t)bj);
-        const double2 a01 = __ldg(blk), a23 = __ldg(blk + 1);
+        const double2 a01 = ld_stream(blk), a23 = ld_stream(blk + 1);
         const double2 x01 = __ldg(xv), x23 = __ldg(xv + 1);
         acc = row_op<MULADD>(a01.x, x01.x, acc);
         acc = row_op<MULADD>(a01.y, x01.y, acc);
@@ -104,10 +140,14 @@ NSK_API int nsk_spmv_bcsr4(nsk_bcsr4_t B, const double *x, double *y, nsk_mode m
     const int rows = 4 * B->nbrows;
     if (rows > 0) {
         const int blocks = (rows + 255) / 256;
-        if (mode == NSK_EXACT_MULADD)
-            spmv_bcsr4_kernel<true><<<blocks, 256, 0, ctx->stream>>>(B->nbrows, B->d_ptrow, B->d_indcol, B->d_coef, dx, dy);
-        else
-            spmv_bcsr4_kernel<false><<<blocks, 256, 0, ctx->stream>>>(B->nbrows, B->d_ptrow, B->d_indcol, B->d_coef, dx, dy);
+        const int batch = ctx->opt.bcsr_batch > 0 ? (int)ctx->opt.bcsr_batch : 4;
+#define NSK_BCSR_LAUNCH(MA, BT) \
+    spmv_bcsr4_kernel<MA, BT><<<blocks, 256, 0, ctx->stream>>>(B->nbrows, B->d_ptrow, B->d_indcol, B->d_coef, dx, dy)
+        const bool ma = mode == NSK_EXACT_MULADD;
+        if (batch >= 4) { if (ma) NSK_BCSR_LAUNCH(true, 4); else NSK_BCSR_LAUNCH(false, 4); }
+        else if (batch >= 2) { if (ma) NSK_BCSR_LAUNCH(true, 2); else NSK_BCSR_LAUNCH(false, 2); }
+        else { if (ma) NSK_BCSR_LAUNCH(true, 1); else NSK_BCSR_LAUNCH(false, 1); }
+#undef NSK_BCSR_LAUNCH
         ctx->launches++;
         NSK_CUDA(ctx, cudaGetLastError());
     }

@@ -155,7 +155,8 @@ static int cg_grid(nsk_ctx_t ctx, int64_t n)
     return (int)(want < cap ? want : cap);
 }
 
-int nsk_halo_exchange_dev(nsk_csr_t A, double *xlocal, int depth);  // dist.cu
+int nsk_halo_exchange_dev(nsk_csr_t A, double *xlocal, int depth, bool allow_push);
+int nsk_halo_release_dev(nsk_csr_t A, const double *xlocal, int depth);  // dist.cu
 
 static int cg_device(nsk_csr_t A, const double *d_b, double *d_x, double tol, int maxit, int *iters,
                      double *relres)
@@ -196,7 +197,7 @@ static int cg_device(nsk_csr_t A, const double *d_b, double *d_x, double tol, in
         int batch = maxit - it < check_every ? maxit - it : check_every;
         for (int b = 0; b < batch; b++, it++) {
             const int rr_in = S_RR0 + (it & 1), rr_out = S_RR0 + ((it + 1) & 1);
-            if (A->dist) NSK_TRY(nsk_halo_exchange_dev(A, p, 1));
+            if (A->dist) NSK_TRY(nsk_halo_exchange_dev(A, p, 1, false));
             nsk_spmv_args a;
             a.x = p;
             a.y = q;

@@ -82,6 +82,7 @@ NSK_API int nsk_ctx_destroy(nsk_ctx_t c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     nsk_comm_destroy(c);
+    nsk_ipc_close_all(c);
     for (int i = 0; i < 8; i++) if (c->d_stage[i]) cudaFree(c->d_stage[i]);
     if (c->d_flush) cudaFree(c->d_flush);
     cudaFree(c->d_partials);
@@ -142,6 +143,8 @@ NSK_API int nsk_ctx_set_option(nsk_ctx_t c, const char *name, int64_t v)
     else if (!strcmp(name, "host_overlap")) c->opt.host_overlap = v;
     else if (!strcmp(name, "stream_exact_kind")) c->opt.stream_exact_kind = v;
     else if (!strcmp(name, "pipe_interleave")) c->opt.pipe_interleave = v;
+    else if (!strcmp(name, "halo_push")) c->opt.halo_push = v;
+    else if (!strcmp(name, "bcsr_batch")) c->opt.bcsr_batch = v;
     else if (!strcmp(name, "sell_chunk")) c->opt.sell_chunk = v;
     else if (!strcmp(name, "sell_geom")) c->opt.sell_geom = v;
     else if (!strcmp(name, "sell_ctas_per_sm")) c->opt.sell_ctas_per_sm = v;
@@ -163,6 +166,14 @@ NSK_API int nsk_ctx_query(nsk_ctx_t c, const char *name, int64_t *value)
     if (!strcmp(name, "last_spmv_kernel")) *value = c->last_spmv;
     else if (!strcmp(name, "last_mpk_strategy")) *value = c->last_mpk;
     else if (!strcmp(name, "launches")) *value = (int64_t)c->launches;
+    else if (!strcmp(name, "sell_uniform_width")) *value = c->last_sell[0];
+    else if (!strcmp(name, "sell_reach")) *value = c->last_sell[1];
+    else if (!strcmp(name, "sell_lead")) *value = c->last_sell[2];
+    else if (!strcmp(name, "sell_grid")) *value = c->last_sell[3];
+    else if (!strcmp(name, "sell_identity_tiles")) *value = c->last_sell[4];
+    else if (!strcmp(name, "sell_ntiles")) *value = c->last_sell[5];
+    else if (!strcmp(name, "sell_staged")) *value = c->last_sell[6];
+    else if (!strcmp(name, "sell_ngroups")) *value = c->last_sell[7];
     else {
         nsk_set_error(c, "unknown query '%s'", name);
         return NSK_ERR_INVALID;

@@ -136,7 +136,8 @@ NSK_API int64_t nsk_csr_packed_bytes(nsk_csr_t A)
     return (int64_t)nsk_packed_bytes(A);
 }
 
-int nsk_halo_exchange_dev(nsk_csr_t A, double *xlocal, int depth);  // dist.cu
+int nsk_halo_exchange_dev(nsk_csr_t A, double *xlocal, int depth, bool allow_push);
+int nsk_halo_release_dev(nsk_csr_t A, const double *xlocal, int depth);  // dist.cu
 
 NSK_API int nsk_spmv(nsk_csr_t A, const double *x, double *y, nsk_mode mode, nsk_where where)
 {
@@ -151,10 +152,11 @@ NSK_API int nsk_spmv(nsk_csr_t A, const double *x, double *y, nsk_mode mode, nsk
     a.row_end = n_out;
     a.mode = mode;
     if (where == NSK_DEVICE) {
-        if (A->dist) NSK_TRY(nsk_halo_exchange_dev(A, const_cast<double *>(x), 1));
+        if (A->dist) NSK_TRY(nsk_halo_exchange_dev(A, const_cast<double *>(x), 1, true));
         a.x = x;
         a.y = y;
-        return nsk_launch_spmv(A, a);
+        NSK_TRY(nsk_launch_spmv(A, a));
+        return A->dist ? nsk_halo_release_dev(A, x, 1) : NSK_OK;
     }
     // host pointers: x holds the owned part (all of x for a single-GPU operator)
     const size_t n_in = A->dist ? (size_t)n_out : (size_t)A->n_cols;
@@ -162,7 +164,7 @@ NSK_API int nsk_spmv(nsk_csr_t A, const double *x, double *y, nsk_mode mode, nsk
     NSK_TRY(nsk_stage(ctx, 0, sizeof(double) * (size_t)A->n_cols, &dx));
     NSK_TRY(nsk_stage(ctx, 1, sizeof(double) * (size_t)A->n, &dy));
     NSK_CUDA(ctx, cudaMemcpyAsync(dx, x, sizeof(double) * n_in, cudaMemcpyHostToDevice, ctx->stream));
-    if (A->dist) NSK_TRY(nsk_halo_exchange_dev(A, (double *)dx, 1));
+    if (A->dist) NSK_TRY(nsk_halo_exchange_dev(A, (double *)dx, 1, false));
     a.x = (const double *)dx;
     a.y = (double *)dy;
     NSK_TRY(nsk_launch_spmv(A, a));

@@ -59,6 +59,9 @@ struct nsk_options {
     int64_t stream_variant = 0;   // 0 auto, else 1 + index into the stream kernel table
     int64_t wave_slack_pct = -1;  // extra level skew, % of (resident CTAs x stages / k) tiles; <0 = default 150
     int64_t wave_l2_pct = 0;      // share of L2 the wavefront window may occupy, %; 0 = default 80
+    int64_t halo_push = 1;        // distributed operators: registered vectors exchange their halo by pushing over NVLink
+                                  // peer memory (0: always NCCL)
+    int64_t bcsr_batch = 0;       // block product: blocks whose loads are issued together per thread (0 = default 4; 1, 2, 4)
     // sliced-ELL kernel (sell.cu)
     int64_t sell_chunk = 0;       // consecutive tiles a CTA takes per item; 0 = default (2 fused, 4 single product)
     int64_t sell_geom = 0;        // 0 auto, 1 = pattern geometry (4 entries per round trip, more CTAs per SM), 2 = explicit
@@ -72,6 +75,11 @@ struct nsk_options {
                                   // item-at-a-time kernel)
 };
 
+struct nsk_ipc_mapping {  // a peer allocation mapped into this process (dist.cu)
+    unsigned char handle[64];
+    void *base;
+};
+
 struct nsk_ctx_s {
     int device = 0;
     cudaStream_t own_stream = nullptr;
@@ -81,6 +89,7 @@ struct nsk_ctx_s {
     cudaDeviceProp prop{};
     uint64_t launches = 0;
     int last_spmv = 0;  // kernel family of the last product: 1 scalar, 2 stream (CSR), 3 packed, 4 sliced-ELL tiles
+    int last_sell[8] = {};  // plan of the last sliced-ELL launch (queries sell_uniform_width, sell_reach, sell_lead, ...)
     int last_mpk = 0;   // strategy of the last powers call: 1 levels, 4 packed level pipeline, 5 sliced-ELL level pipeline
     std::string last_error;
     nsk_options opt;
@@ -96,7 +105,9 @@ struct nsk_ctx_s {
     void *d_stage[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t stage_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     nsk_comm_s *comm = nullptr;
+    std::vector<nsk_ipc_mapping> ipc_maps;
 };
+void nsk_ipc_close_all(nsk_ctx_t ctx);  // dist.cu
 
 constexpr int NSK_MAX_PARTIALS = 4096;  // max blocks of a reducing kernel
 constexpr int NSK_RED_SLOTS = 96;       // max simultaneous sums per reducing kernel (Gram 9x9 = 81)

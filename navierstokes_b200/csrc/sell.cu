@@ -2058,6 +2058,14 @@ static int sl_run(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
         NSK_CUDA(ctx, cudaGetLastError());
     }
     ctx->launches++;
+    ctx->last_sell[0] = op->uniform_width;
+    ctx->last_sell[1] = plan->reach;
+    ctx->last_sell[2] = plan->lead;
+    ctx->last_sell[3] = plan->grid;
+    ctx->last_sell[4] = plan->d_ltile_buf ? 0 : 1;  // 1: every level walks the operator's own tile array
+    ctx->last_sell[5] = op->ntiles;
+    ctx->last_sell[6] = tma ? 1 : 0;
+    ctx->last_sell[7] = plan->ngroups;
     return NSK_OK;
 }
 

@@ -238,8 +238,61 @@ class DistOperator:
             pass
 
     # local vectors: n_cols_local doubles, owned part first
-    def new_vector(self) -> DeviceVector:
-        return self.ctx.zeros(self.n_cols_local)
+    def new_vector(self, shared: bool = False) -> DeviceVector:
+        """``shared=True`` (collective: every rank, same order): the vector is mapped into the neighbours' address
+        spaces and registered, so its halo travels by the push kernel over NVLink peer memory instead of NCCL."""
+        v = self.ctx.zeros(self.n_cols_local)
+        if shared:
+            self.enable_push()
+            self.ctx.sync()
+            mine = self._ipc_export(v.ptr)
+            gathered = [None] * self.world
+            self.dist.all_gather_object(gathered, mine)
+            if self._peers:
+                ptrs = (C.c_void_p * len(self._peers))()
+                for i, p in enumerate(self._peers):
+                    ptrs[i] = self._ipc_import(gathered[p])
+                self.ctx._ck(self.ctx.lib.nsk_dist_vector_register(self.h, v.ptr, ptrs))
+            self.dist.barrier()  # nobody pushes before every neighbour has registered
+        return v
+
+    def _ipc_export(self, devptr) -> bytes:
+        buf = (C.c_ubyte * 80)()
+        self.ctx._ck(self.ctx.lib.nsk_ipc_export(self.ctx.h, devptr, buf))
+        return bytes(buf)
+
+    def _ipc_import(self, handle: bytes) -> int:
+        buf = (C.c_ubyte * 80).from_buffer_copy(handle)
+        out = C.c_void_p()
+        self.ctx._ck(self.ctx.lib.nsk_ipc_import(self.ctx.h, buf, C.byref(out)))
+        return out.value
+
+    def enable_push(self) -> None:
+        """One-time setup of the halo push (collective): flag blocks and receive layouts are exchanged through
+        torch.distributed, every neighbour's flag block is mapped here (CUDA IPC; one node only)."""
+        if getattr(self, "_push_ready", False):
+            return
+        lib, ctx = self.ctx.lib, self.ctx
+        self._peers = [lib.nsk_dist_peer_rank(self.h, i) for i in range(lib.nsk_dist_peer_count(self.h))]
+        flags = C.c_void_p()
+        ctx._ck(lib.nsk_dist_push_flags(self.h, C.byref(flags)))
+        ctx.sync()
+        layouts = {}
+        for p in self._peers:
+            rs, rc = np.zeros(self.depth, np.int32), np.zeros(self.depth, np.int32)
+            ctx._ck(lib.nsk_dist_recv_layout(self.h, p, C.c_void_p(_ptr(rs)), C.c_void_p(_ptr(rc))))
+            layouts[p] = (rs, rc)
+        mine = {"flags": self._ipc_export(flags), "peers": self._peers, "layouts": layouts}
+        gathered = [None] * self.world
+        self.dist.all_gather_object(gathered, mine)
+        for p in self._peers:
+            theirs = gathered[p]
+            rs, rc = theirs["layouts"][self.rank]
+            rs, rc = np.ascontiguousarray(rs, np.int32), np.ascontiguousarray(rc, np.int32)
+            fp = self._ipc_import(theirs["flags"])
+            ctx._ck(lib.nsk_dist_push_peer(self.h, p, theirs["peers"].index(self.rank), C.c_void_p(_ptr(rs)),
+                                           C.c_void_p(_ptr(rc)), C.c_void_p(fp)))
+        self._push_ready = True
 
     def set_owned(self, v: DeviceVector, host: np.ndarray):
         host = np.ascontiguousarray(host, np.float64)

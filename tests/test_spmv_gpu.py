@@ -395,6 +395,17 @@ def test_bcsr4_fem_operator_matches_oracle_and_csr(ctx, oracle_lib):
     assert_bits_equal(dB.spmv(dx).to_host(), y)
     y_csr = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef).spmv(x)
     assert oracle_lib.rel_error(y_csr, y) <= 1e-13
+    # every load-batching instance of the block kernel (block rows of 27, 18, 12, 8 blocks: batches + remainders), both flavours
+    try:
+        ctx.set_option("bcsr_batch", 1)
+        want_ma = dB.spmv(dx, mode=nsk.EXACT_MULADD).to_host()  # the one-block-at-a-time instance (the round-1 kernel)
+        assert oracle_lib.rel_error(y, want_ma) <= 1e-14
+        for batch in (1, 2, 4):
+            ctx.set_option("bcsr_batch", batch)
+            assert_bits_equal(dB.spmv(dx).to_host(), y, f"batch {batch}")
+            assert_bits_equal(dB.spmv(dx, mode=nsk.EXACT_MULADD).to_host(), want_ma, f"batch {batch} muladd")
+    finally:
+        ctx.set_option("bcsr_batch", 0)
 
 
 # ---- BASELINE.json full sizes: size-independent properties (the CPU oracle would need minutes here; bench.py

@@ -75,6 +75,73 @@ def main():
     if not scg_ok:
         print(f"rank {rank}: s-step CG FAILED it={it4} rel={rel4} err={err4}", flush=True)
     bad += not scg_ok
+    # ---- halo push over NVLink peer memory: registered vectors, repeated calls (epochs / acknowledgements), mixed depths
+    sx = op.new_vector(shared=True)
+    op.set_owned(sx, x[lo:hi])
+    l0 = ctx.launch_count
+    for rep in range(3):
+        for k in (4, 1, 2, 4, 3):
+            lv = [op.new_vector() for _ in range(k)]
+            op.mpk(k, sx, lv)
+            for l in range(k):
+                ok = np.array_equal(op.get_owned(lv[l]).view(np.int64), ref[l][lo:hi].view(np.int64))
+                bad += not ok
+                if not ok:
+                    print(f"rank {rank}: MISMATCH (push) rep={rep} k={k} level={l}", flush=True)
+        op.spmv(sx, y)
+        bad += not np.array_equal(op.get_owned(y).view(np.int64), ref[0][lo:hi].view(np.int64))
+        # new contents in the same registered vector: the neighbours must see them
+        x2 = matgen.vec_uniform(A.n, seed=30 + rep)
+        op.set_owned(sx, x2[lo:hi])
+        ref2 = lib.mpk(A.ptrow, A.indcol, A.coef, 2, x2)
+        lv = [op.new_vector() for _ in range(2)]
+        op.mpk(2, sx, lv)
+        for l in range(2):
+            bad += not np.array_equal(op.get_owned(lv[l]).view(np.int64), ref2[l][lo:hi].view(np.int64))
+        op.set_owned(sx, x[lo:hi])
+    push_launches = ctx.launch_count - l0
+    # timing: depth-K exchange + ack, push vs NCCL (same vector, the option switches the path)
+    times = {}
+    lvK = [op.new_vector() for _ in range(K)]
+    for name, opt in (("push", 1), ("nccl", 0)):
+        ctx.set_option("halo_push", opt)
+        for _ in range(5):
+            op.mpk(K, sx, lvK)
+        ctx.sync(); dist.barrier()
+        e0, e1 = ctx.event(), ctx.event()
+        e0.record()
+        for _ in range(50):
+            op.mpk(K, sx, lvK)
+        e1.record()
+        times[name] = e0.elapsed_ms(e1) / 50 * 1e3
+    ctx.set_option("halo_push", 1)
+    if rank == 0:
+        print(f"push path: launches={push_launches}; small-grid k={K} call: push {times['push']:.1f} us, nccl {times['nccl']:.1f} us", flush=True)
+
+    # ---- an UNSTRUCTURED operator across the ranks: RCM'd P1 tet Laplacian, contiguous row blocks, depth-4 rings ----------
+    T = matgen.tet_p1_laplacian(14, rcm=True)
+    xt = matgen.vec_uniform(T.n, seed=5)
+    reft = lib.mpk(T.ptrow, T.indcol, T.coef, K, xt)
+    starts = (np.arange(world + 1, dtype=np.int64) * T.n // world).astype(np.int32)
+    top = nd.DistOperator(ctx, dist, starts, nd.GlobalCsrProvider(T), K)
+    tlo, thi = int(starts[rank]), int(starts[rank + 1])
+    for shared in (False, True):
+        tx = top.new_vector(shared=shared)
+        top.set_owned(tx, xt[tlo:thi])
+        for strat in (1, 5, 0):
+            ctx.set_option("mpk_kernel", strat)
+            for k in (1, 2, 4):
+                lv = [top.new_vector() for _ in range(k)]
+                top.mpk(k, tx, lv)
+                for l in range(k):
+                    ok = np.array_equal(top.get_owned(lv[l]).view(np.int64), reft[l][tlo:thi].view(np.int64))
+                    bad += not ok
+                    if not ok:
+                        print(f"rank {rank}: MISMATCH tet mesh shared={shared} strategy={strat} k={k} level={l}", flush=True)
+    ctx.set_option("mpk_kernel", 0)
+    if rank == 0:
+        print(f"unstructured operator (tet P1, n={T.n}) over {world} ranks: peers of rank 0 = {top.ctx.lib.nsk_dist_peer_count(top.h)}", flush=True)
+
     t = torch.tensor([bad], device=f"cuda:{local}")
     dist.all_reduce(t)
     if rank == 0:
