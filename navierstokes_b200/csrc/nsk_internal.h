@@ -64,7 +64,7 @@ struct nsk_options {
     int64_t bcsr_batch = 0;       // block product: blocks whose loads are issued together per thread (0 = default 4; 1, 2, 4)
     // sliced-ELL kernel (sell.cu)
     int64_t sell_chunk = 0;       // consecutive tiles a CTA takes per item; 0 = default (2 fused, 4 single product)
-    int64_t sell_geom = 0;        // 0 auto, 1 = pattern geometry (4 entries per round trip, more CTAs per SM), 2 = explicit
+    int64_t sell_geom = 0;        // 2 = operators stored with one global pattern still take the masked consumer path (A/B)
     int64_t sell_ctas_per_sm = 0; // 0 = what the occupancy calculator allows
     int64_t sell_flags = -1;      // < 0 default (3): bit 0 eviction / streaming hints, bit 1 L2 prefetch of level 0's tiles
     int64_t sell_pf_dist = 0;     // items ahead the L2 prefetch runs; 0 = default 2

@@ -101,6 +101,9 @@ struct SlParams {
     int flags;               // 1: evict-first / streaming hints for data nobody re-reads; 2: L2 prefetch of level 0's blobs;
                              // 4: inner levels load tiles with L1 allocation; 8: ... with an evict-last L2 policy
     int pf_dist;             // items ahead the L2 prefetch runs
+    int gpat;                // 1: every tile is stored with the ONE column pattern grel[] (slot e of row r: column r + grel[e])
+    int grel[8];
+    long long goff8[8];      // 8 * grel[e]: byte offsets, added to a row's x address straight from the constant bank
     int *error;              // host-mapped: set to 1 when a bounded wait expired (protocol bug or a lost CTA)
     // fused dot <dot_w, levels[0]> (k = 1 only; CG: p.Ap)
     const double *dot_w;
@@ -820,6 +823,164 @@ constexpr int SL_EXPLICIT_STAGE = 24576;         // stage of the explicit-column
 constexpr int SLT_NCW = SL_ROWS / 32;            // consumer warps: thread t owns row t of every tile
 constexpr int SLT_THREADS = SL_ROWS + 64;        // + dependency warp + service warp (producer and publisher)
 
+
+// ---- consumers of an operator stored with ONE global pattern (staged kernel) ----------------------------------------
+// Everything per-thread that does not change over the launch is folded into a few registers (shared-memory addresses as
+// 32-bit words, x / y pointers already offset by the thread's row), the pattern's byte offsets come from the constant
+// bank, and a warp whose 32 rows have every slot runs straight-line code: W gathers, W shared-memory loads, W links of
+// the chain, one store.  Warps with a row that lacks a slot (domain faces) take the masked variant of the same code.
+__device__ __forceinline__ bool sl_mbar_try_wait_a(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void sl_mbar_wait_a(uint32_t bar, uint32_t parity)
+{
+    if (sl_mbar_try_wait_a(bar, parity)) return;
+    uint32_t spins = 0;
+    while (!sl_mbar_try_wait_a(bar, parity))
+        if (++spins > (1u << 26)) __trap();  // bounded: a protocol bug must not hang the GPU
+}
+__device__ __forceinline__ void sl_mbar_arrive_a(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ double sl_lds_f64(uint32_t a)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(a), "n"(OFF));
+    return v;
+}
+__device__ __forceinline__ unsigned int sl_lds_u8(uint32_t a)
+{
+    unsigned int v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double sl_ld_x_b(const char *p)
+{
+    double v;
+    asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <int NV, int W, int E>
+struct SlChain {
+    template <bool MULADD>
+    static __device__ __forceinline__ void run(uint32_t a_val, const double (&xv)[NV][W], unsigned int m, bool masked, double &acc0, double &acc1)
+    {
+        if constexpr (E < W) {
+            if (!masked || (m & (1u << E))) {
+                const double a = sl_lds_f64<E * SL_ROWS * 8>(a_val);
+                acc0 = row_op<MULADD>(a, xv[0][E], acc0);
+                if (NV == 2) acc1 = row_op<MULADD>(a, xv[NV - 1][E], acc1);
+            }
+            SlChain<NV, W, E + 1>::template run<MULADD>(a_val, xv, m, masked, acc0, acc1);
+        }
+    }
+};
+
+// x entry at byte address base + off (one 64-bit add the compiler cannot fold into anything else, then the load)
+__device__ __forceinline__ double sl_ld_x_off(const char *base, long long off)
+{
+    double v;
+    asm volatile("{\n\t.reg .b64 a;\n\tadd.s64 a, %1, %2;\n\tld.global.f64 %0, [a];\n\t}" : "=d"(v) : "l"(base), "l"(off) : "memory");
+    return v;
+}
+__device__ __forceinline__ const char *sl_add_b(const char *base, long long off)
+{
+    const char *r;
+    asm volatile("add.s64 %0, %1, %2;" : "=l"(r) : "l"(base), "l"(off));
+    return r;
+}
+
+template <int NV, int W, int NS>
+__device__ __forceinline__ void sl_consume_gpat(const SlParams &P, const SlCta &C, int n_my, int tid, const unsigned char *stages,
+                                                const uint64_t *s_full, const uint64_t *s_empty, const uint64_t *s_ready,
+                                                unsigned int *s_fin, const int (*s_hdr)[2], const int (*s_desc)[SL_MAXCHUNK * 16])
+{
+    constexpr int STAGE = SL_ROWS + 8 * W * SL_ROWS;
+    constexpr unsigned int FULL = (1u << W) - 1u;
+    const uint32_t a_full = smem_u32(s_full), a_empty = smem_u32(s_empty), a_ready = smem_u32(s_ready);
+    const uint32_t a_mask = smem_u32(stages) + (uint32_t)tid;
+    const uint32_t a_val = smem_u32(stages) + SL_ROWS + 8u * (uint32_t)tid;
+    const char *const xsrc = reinterpret_cast<const char *>(C.src[0] + tid);
+    const char *const xsrc2 = NV == 2 ? reinterpret_cast<const char *>(C.src[1] + tid) : nullptr;
+    char *const ydst = reinterpret_cast<char *>(C.dst[0] + tid);
+    char *const ydst2 = NV == 2 ? reinterpret_cast<char *>(C.dst[1] + tid) : nullptr;
+    const bool last = C.last != 0;
+    const bool muladd = C.muladd != 0;
+    const bool lane0 = (tid & 31) == 0;
+    uint32_t so = 0, sb = 0, ph = 0;  // byte offset of the next tile's stage, of its barriers; parity of its completion
+    for (int it = 0; it < n_my; ++it) {
+        const int slot = it % SL_RING;
+        sl_mbar_wait_a(a_ready + 8u * slot, (uint32_t)(it / SL_RING) & 1u);
+        const int ntile = s_hdr[slot][0];
+        const int *d = s_desc[slot] + 2;
+        for (int j = 0; j < ntile; ++j, d += 16) {
+            const int2 q = *reinterpret_cast<const int2 *>(d);  // row0, live rows (clipped by the dependency warp)
+            const bool live = tid < q.y;
+            sl_mbar_wait_a(a_full + sb, ph);
+            const unsigned int m = sl_lds_u8(a_mask + so);
+            double xv[NV][W];
+            double acc0 = 0.0, acc1 = 0.0;
+            if (__all_sync(0xffffffffu, live && m == FULL)) {
+                const long long r8 = 8ll * q.x;
+                const char *xb = sl_add_b(xsrc, r8);
+                const char *xb2 = NV == 2 ? sl_add_b(xsrc2, r8) : nullptr;
+#pragma unroll
+                for (int e = 0; e < W; e++) {
+                    xv[0][e] = sl_ld_x_off(xb, P.goff8[e]);
+                    if (NV == 2) xv[NV - 1][e] = sl_ld_x_off(xb2, P.goff8[e]);
+                }
+                if (muladd) SlChain<NV, W, 0>::template run<true>(a_val + so, xv, m, false, acc0, acc1);
+                else SlChain<NV, W, 0>::template run<false>(a_val + so, xv, m, false, acc0, acc1);
+            } else {
+                // a dead row's own x entry must stay inside x: clamp its row
+                const long long r8 = 8ll * min(q.x, P.n_cols - 1 - tid);
+                const char *xb = sl_add_b(xsrc, r8);
+                const char *xb2 = NV == 2 ? sl_add_b(xsrc2, r8) : nullptr;
+#pragma unroll
+                for (int e = 0; e < W; e++) {
+                    const long long o = (m & (1u << e)) ? P.goff8[e] : 0ll;  // a slot the row lacks reads its own x entry
+                    xv[0][e] = sl_ld_x_off(xb, o);
+                    if (NV == 2) xv[NV - 1][e] = sl_ld_x_off(xb2, o);
+                }
+                if (muladd) SlChain<NV, W, 0>::template run<true>(a_val + so, xv, m, true, acc0, acc1);
+                else SlChain<NV, W, 0>::template run<false>(a_val + so, xv, m, true, acc0, acc1);
+            }
+            if (live) {
+                const long long w8 = 8ll * q.x;
+                if (last) __stcs(reinterpret_cast<double *>(ydst + w8), acc0);  // nobody in this launch re-reads the last level
+                else *reinterpret_cast<double *>(ydst + w8) = acc0;
+                if (NV == 2) {
+                    if (last) __stcs(reinterpret_cast<double *>(ydst2 + w8), acc1);
+                    else *reinterpret_cast<double *>(ydst2 + w8) = acc1;
+                }
+            }
+            __syncwarp();
+            if (lane0) sl_mbar_arrive_a(a_empty + sb);  // the stage may be refilled (the warp's reads of it are done)
+            so += STAGE;
+            sb += 8;
+            if (sb == 8u * NS) {
+                so = 0;
+                sb = 0;
+                ph ^= 1u;
+            }
+        }
+        __syncwarp();
+        if (lane0) red_release_cta_shared_add(&s_fin[slot], 1u);  // the slot may be reused and the item published
+    }
+}
+
 template <int NV, int W, int NS, int MINB>
 __global__ void __launch_bounds__(SLT_THREADS, MINB) sell_tma_kernel(const SlParams P)
 {
@@ -829,7 +990,7 @@ __global__ void __launch_bounds__(SLT_THREADS, MINB) sell_tma_kernel(const SlPar
     constexpr int STAGE = W > 0 ? SL_ROWS + 8 * W * SL_ROWS : SL_EXPLICIT_STAGE;
     extern __shared__ __align__(128) unsigned char stages[];  // NS stages
     __shared__ uint64_t s_full[NS];           // the stage's tile has landed (bulk copy complete_tx)
-    __shared__ unsigned int s_free[NS];       // consumer warps that finished the stage's tile, counted over the launch
+    __shared__ uint64_t s_empty[NS];          // every consumer warp has finished the stage's tile (one arrival per warp)
     __shared__ __align__(16) int s_desc[SL_RING][SL_MAXCHUNK * 16];
     __shared__ int s_hdr[SL_RING][2];
     __shared__ uint64_t s_ready[SL_RING];     // item's inputs complete + descriptors in place
@@ -855,7 +1016,7 @@ __global__ void __launch_bounds__(SLT_THREADS, MINB) sell_tma_kernel(const SlPar
         }
         for (int s = 0; s < NS; s++) {
             mbar_init(&s_full[s], 1);
-            s_free[s] = 0u;
+            mbar_init(&s_empty[s], SLT_NCW);
         }
         fence_mbar_init();
         s_cta.src[0] = level == 0 ? P.x : P.levels[level - 1];
@@ -895,7 +1056,7 @@ __global__ void __launch_bounds__(SLT_THREADS, MINB) sell_tma_kernel(const SlPar
             bool progress = false;
             if (n < total) {
                 const int st = n % NS;
-                const bool ok = n < NS || ld_acquire_cta_shared_u32(&s_free[st]) >= (unsigned int)SLT_NCW * (unsigned int)(n / NS);
+                const bool ok = n < NS || mbar_try_wait(&s_empty[st], (uint32_t)(n / NS - 1) & 1u);
                 if (ok) {
                     if ((n & ~31) != off_base) {
                         off_base = n & ~31;
@@ -1014,7 +1175,12 @@ __global__ void __launch_bounds__(SLT_THREADS, MINB) sell_tma_kernel(const SlPar
                 }
             }
             if (broken && lane == 0) *P.error = 1;
-            if (lane < 4 * SL_MAXCHUNK) reinterpret_cast<int4 *>(s_desc[s])[lane] = dq;
+            if (lane < 4 * SL_MAXCHUNK) {
+                int4 dw = dq;
+                // quarter 0 of a descriptor = {off lo, off hi, row0, nrows}: rows beyond the level's row prefix are dead
+                if ((lane & 3) == 0) dw.w = min(dw.w, s_cta.row_end - dw.z);
+                reinterpret_cast<int4 *>(s_desc[s])[lane] = dw;
+            }
             if (lane == 0) s_hdr[s][0] = ntile;
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_ready[s]);  // release.cta: descriptors + everything acquired above
@@ -1026,54 +1192,73 @@ __global__ void __launch_bounds__(SLT_THREADS, MINB) sell_tma_kernel(const SlPar
     const int t = tid;
     const int cmax = P.n_cols - 1;
     const double *val = reinterpret_cast<const double *>(stages + SL_ROWS) + t;
+    // per-CTA constants in registers (the asm loads below clobber memory: the compiler would re-read s_cta per tile)
+    const double *const src = s_cta.src[0];
+    const double *const src2 = NV == 2 ? s_cta.src[1] : nullptr;
+    double *const dst = s_cta.dst[0];
+    double *const dst2 = NV == 2 ? s_cta.dst[1] : nullptr;
+    const int row_end = s_cta.row_end;
+    const bool last = s_cta.last != 0;
+    const bool muladd = s_cta.muladd != 0;
+    const bool gpat = W > 0 && P.gpat != 0;
+    int n_done = 0;
     double dot_acc = 0.0;
     int st = 0;
     uint32_t ph = 0;  // stage of the next tile, parity of its completion
-    for (int it = 0; it < n_my; ++it) {
+    if constexpr (W > 0) {
+        if (gpat && !P.dot_w) {  // (the fused dot of CG's product stays with the loop below)
+            sl_consume_gpat<NV, W, NS>(P, s_cta, n_my, tid, stages, s_full, s_empty, s_ready, s_fin, s_hdr, s_desc);
+            n_done = n_my;
+        }
+    }
+    for (int it = n_done; it < n_my; ++it) {
         const int slot = it % SL_RING;
         mbar_wait(&s_ready[slot], (it / SL_RING) & 1);
         const int ntile = s_hdr[slot][0];
         for (int j = 0; j < ntile; ++j) {
             const int *d = s_desc[slot] + 16 * j;
             const int2 q = *reinterpret_cast<const int2 *>(d + 2);  // row0, nrows
-            const int4 r0 = *reinterpret_cast<const int4 *>(d + 8), r1 = *reinterpret_cast<const int4 *>(d + 12);
-            const int rel[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
             const int row = q.x + t;
-            const double *src = s_cta.src[0];
-            const double *src2 = NV == 2 ? s_cta.src[1] : nullptr;
+            const bool live = t < q.y && row < row_end;
             double acc0 = 0.0, acc1 = 0.0;
             if constexpr (W > 0) {
-                const int rowc = min(row, cmax);
                 mbar_wait(&s_full[st], ph);
                 const unsigned int m = stages[(size_t)st * STAGE + t];
-                double xv[NV][W];
-#pragma unroll
-                for (int e = 0; e < W; e++) {
-                    const int idx = rowc + ((m & (1u << e)) ? rel[e] : 0);  // a slot the row lacks reads its own x entry
-                    xv[0][e] = sl_ld_x(src + idx);
-                    if (NV == 2) xv[NV - 1][e] = sl_ld_x(src2 + idx);
-                }
                 const double *vs = val + (size_t)st * (STAGE / 8);
-                if (s_cta.muladd) {
+                double xv[NV][W];
+                {
+                    const int4 r0 = *reinterpret_cast<const int4 *>(d + 8), r1 = *reinterpret_cast<const int4 *>(d + 12);
+                    const int rel[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+                    const int rowc = min(row, cmax);
 #pragma unroll
-                    for (int e = 0; e < W; e++)
-                        if (m & (1u << e)) {
-                            const double a = vs[e * SL_ROWS];
-                            acc0 = row_op<true>(a, xv[0][e], acc0);
-                            if (NV == 2) acc1 = row_op<true>(a, xv[NV - 1][e], acc1);
-                        }
-                } else {
+                    for (int e = 0; e < W; e++) {
+                        const int idx = rowc + ((m & (1u << e)) ? rel[e] : 0);  // a slot the row lacks reads its own x entry
+                        xv[0][e] = sl_ld_x(src + idx);
+                        if (NV == 2) xv[NV - 1][e] = sl_ld_x(src2 + idx);
+                    }
+                    if (muladd) {
 #pragma unroll
-                    for (int e = 0; e < W; e++)
-                        if (m & (1u << e)) {
-                            const double a = vs[e * SL_ROWS];
-                            acc0 = row_op<false>(a, xv[0][e], acc0);
-                            if (NV == 2) acc1 = row_op<false>(a, xv[NV - 1][e], acc1);
-                        }
+                        for (int e = 0; e < W; e++)
+                            if (m & (1u << e)) {
+                                const double a = vs[e * SL_ROWS];
+                                acc0 = row_op<true>(a, xv[0][e], acc0);
+                                if (NV == 2) acc1 = row_op<true>(a, xv[NV - 1][e], acc1);
+                            }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < W; e++)
+                            if (m & (1u << e)) {
+                                const double a = vs[e * SL_ROWS];
+                                acc0 = row_op<false>(a, xv[0][e], acc0);
+                                if (NV == 2) acc1 = row_op<false>(a, xv[NV - 1][e], acc1);
+                            }
+                    }
                 }
             } else {
-                // explicit columns: rel[s] = slots of slice s (this warp's rows: slice `warp`), the slices stored one
+                // explicit columns: d[8 + s] = slots of slice s (this warp's rows: slice `warp`), the slices stored one
                 // after the other; lengths and columns from the stage, coefficients and x from global in batches of 8
+                const int4 r0 = *reinterpret_cast<const int4 *>(d + 8), r1 = *reinterpret_cast<const int4 *>(d + 12);
+                const int rel[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
                 const int rp = d[6], tot = d[4];
                 int soff = 0;
 #pragma unroll
@@ -1083,7 +1268,7 @@ __global__ void __launch_bounds__(SLT_THREADS, MINB) sell_tma_kernel(const SlPar
                 const long long off = ((long long)(unsigned int)d[0]) | ((long long)d[1] << 32);
                 const int pre = sl_round_up(2 * rp, 128) + 128 * tot;
                 const double *vg = reinterpret_cast<const double *>(P.blobs + off + pre) + (size_t)soff * 32 + lane;
-                const uint64_t pol = sl_policy(s_cta.last != 0);
+                const uint64_t pol = sl_policy(last);
                 mbar_wait(&s_full[st], ph);
                 const unsigned char *stg = stages + (size_t)st * STAGE;
                 const int len = warp * 32 < rp ? (int)reinterpret_cast<const unsigned short *>(stg)[t] : 0;
@@ -1103,7 +1288,7 @@ __global__ void __launch_bounds__(SLT_THREADS, MINB) sell_tma_kernel(const SlPar
 #pragma unroll
                     for (int u = 0; u < 8; u++)
                         if (e0 + u < len) {
-                            if (s_cta.muladd) {
+                            if (muladd) {
                                 acc0 = row_op<true>(a[u], xv[0][u], acc0);
                                 if (NV == 2) acc1 = row_op<true>(a[u], xv[NV - 1][u], acc1);
                             } else {
@@ -1113,9 +1298,17 @@ __global__ void __launch_bounds__(SLT_THREADS, MINB) sell_tma_kernel(const SlPar
                         }
                 }
             }
-            if (t < q.y && row < s_cta.row_end) sl_store_row<NV>(P, s_cta, row, acc0, acc1, dot_acc);
+            if (live) {
+                if (last) __stcs(dst + row, acc0);  // nobody in this launch re-reads the last level
+                else dst[row] = acc0;
+                if (NV == 2) {
+                    if (last) __stcs(dst2 + row, acc1);
+                    else dst2[row] = acc1;
+                }
+                if (NV == 1 && P.dot_w) dot_acc = __fma_rn(P.dot_w[row], acc0, dot_acc);
+            }
             __syncwarp();
-            if (lane == 0) red_release_cta_shared_add(&s_free[st], 1u);  // the stage may be refilled
+            if (lane == 0) mbar_arrive(&s_empty[st]);  // the stage may be refilled (the warp's reads of it are done)
             if (++st == NS) {
                 st = 0;
                 ph ^= 1u;
@@ -1203,6 +1396,8 @@ struct SellHost {
     int n_pattern = 0;
     int uniform_width = 0;  // > 0: every tile is a pattern tile stored with this many slots
     int explicit_prefix = 0;  // > 0: every tile has explicit columns; largest lengths + columns prefix of a blob (bytes)
+    int global_pattern = 0;   // 1: every tile is stored with ONE column pattern (grel, uniform_width slots)
+    int grel[SL_PSLOTS] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 static void sl_parallel(int n, const std::function<void(int)> &body)
@@ -1245,7 +1440,7 @@ static std::string sl_pack_host(int n, int n_cols, int64_t nnz, const int *ptrow
     std::vector<SlTile> &st = out.stiles;
     st.assign(ntiles, SlTile());
     // 1. per tile: format, geometry, size
-    std::atomic<int> too_long(0);
+    std::atomic<int> too_long(0), unordered(0);
     std::vector<std::array<int, 8>> sw_all((size_t)ntiles);  // the slices' widths (explicit layout)
     sl_parallel(ntiles, [&](int t) {
         const nsk_tile &tl = tiles[t];
@@ -1283,6 +1478,7 @@ static std::string sl_pack_host(int n, int n_cols, int64_t nnz, const int *ptrow
                 }
             }
             if (pattern && !ascending) {
+                unordered.store(1);
                 // any other entry order: the first row of full width is the pattern, every row must be a sub-pattern
                 // of it with slots ascending in entry order (the chain's order is the row's storage order)
                 int rref = 0;
@@ -1327,7 +1523,27 @@ static std::string sl_pack_host(int n, int n_cols, int64_t nnz, const int *ptrow
     // line) are padded with slots no row has, so the streaming kernel runs one straight-line instance over all of them.
     out.uniform_width = 0;
     out.explicit_prefix = 0;
+    out.global_pattern = 0;
     if (n_pattern == ntiles && wmax >= 1) {
+        // ONE pattern for the whole operator when the union of the tiles' patterns still has at most 8 slots (any
+        // stencil on a box: the tiles on a domain face only lack some of the interior tiles' offsets).  The kernel
+        // then takes the offsets from its parameters (constant bank) and a warp whose 32 rows have every slot runs
+        // straight-line code without masks.  Needs rows with ascending columns (slot order = entry order).
+        if (!unordered.load()) {
+            std::vector<int> uni;
+            for (int t = 0; t < ntiles && (int)uni.size() <= SL_PSLOTS; t++)
+                for (int e = 0; e < st[t].width; e++) {
+                    auto it = std::lower_bound(uni.begin(), uni.end(), st[t].rel[e]);
+                    if (it == uni.end() || *it != st[t].rel[e]) uni.insert(it, st[t].rel[e]);
+                }
+            if ((int)uni.size() <= SL_PSLOTS) {
+                out.global_pattern = 1;
+                wmax = (int)uni.size();
+                for (int e = 0; e < SL_PSLOTS; e++) out.grel[e] = e < wmax ? uni[e] : 0;
+                for (int t = 0; t < ntiles; t++)
+                    for (int e = 0; e < SL_PSLOTS; e++) st[t].rel[e] = out.grel[e];
+            }
+        }
         out.uniform_width = wmax;
         for (int t = 0; t < ntiles; t++) {
             st[t].width = wmax;  // rel[] beyond the tile's own slots is already zero
@@ -1754,7 +1970,8 @@ struct SlPlan {
 struct SellOp {
     bool ok = false;
     std::string why;
-    int ntiles = 0, n_pattern = 0, uniform_width = 0, explicit_prefix = 0;
+    int ntiles = 0, n_pattern = 0, uniform_width = 0, explicit_prefix = 0, global_pattern = 0;
+    int grel[SL_PSLOTS] = {0, 0, 0, 0, 0, 0, 0, 0};
     size_t blob_bytes = 0;
     unsigned char *d_blobs = nullptr;
     SlTile *d_tiles = nullptr;
@@ -1833,6 +2050,8 @@ static SellOp *sl_get(nsk_csr_t A)
     op->n_pattern = H.n_pattern;
     op->uniform_width = H.uniform_width;
     op->explicit_prefix = H.explicit_prefix;
+    op->global_pattern = H.global_pattern;
+    for (int e = 0; e < SL_PSLOTS; e++) op->grel[e] = H.grel[e];
     op->blob_bytes = H.blob_bytes;
     op->h_tiles.swap(H.stiles);
     op->csr_view.tile_rows = SL_ROWS;
@@ -2037,6 +2256,11 @@ static int sl_run(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
     P.muladd = mode == NSK_EXACT_MULADD ? 1 : 0;
     P.flags = ctx->opt.sell_flags >= 0 ? (int)ctx->opt.sell_flags : 3;
     P.pf_dist = ctx->opt.sell_pf_dist > 0 ? (int)ctx->opt.sell_pf_dist : 2;
+    P.gpat = (op->global_pattern && ctx->opt.sell_geom != 2) ? 1 : 0;  // option sell_geom = 2: masked path everywhere
+    for (int e = 0; e < SL_PSLOTS; e++) {
+        P.grel[e] = op->grel[e];
+        P.goff8[e] = 8ll * op->grel[e];
+    }
     P.error = op->d_error;
     P.dot_w = dot_w;
     P.partials = ctx->d_partials;

@@ -54,6 +54,7 @@ def main():
     ap.add_argument("--stream", default="0")
     ap.add_argument("--rows", default="0")
     ap.add_argument("--tma", default="0")
+    ap.add_argument("--geom", default="0", help="sell_geom: 0 default, 2 = masked consumer path everywhere (A/B of the straight-line path)")
     ap.add_argument("--no-packed", action="store_true")
     args = ap.parse_args()
     t0 = time.time()
@@ -94,8 +95,9 @@ def main():
     dA.spmv(x, y, 0)
     ctx.sync()
     print(f"# sliced-ELL setup + first product {time.time()-t1:.2f}s", flush=True)
-    for chunk, cps, stream, rows, tma in itertools.product(ints(args.spmv_chunks), ints(args.cps), ints(args.stream),
-                                                           ints(args.rows), ints(args.tma)):
+    for chunk, cps, stream, rows, tma, geom in itertools.product(ints(args.spmv_chunks), ints(args.cps), ints(args.stream),
+                                                                 ints(args.rows), ints(args.tma), ints(args.geom)):
+        ctx.set_option("sell_geom", geom)
         ctx.set_option("sell_tma", tma)
         ctx.set_option("sell_rows", rows)
         ctx.set_option("sell_chunk", chunk)
@@ -105,7 +107,7 @@ def main():
         dA.spmv(x, y, 0)
         ok = same_bits(y.to_host(), ref1) and ctx.query("last_spmv_kernel") == 4
         ms = timed(ctx, lambda: dA.spmv(x, y, 0), args.reps)
-        print(f"spmv sell chunk={chunk} cps={cps} stream={stream} rows={rows} tma={tma}: {ms:8.4f} ms {B/ms/1e6:8.1f} GB/s {B/ms/1e6/peak:6.3f}  "
+        print(f"spmv sell chunk={chunk} cps={cps} stream={stream} rows={rows} tma={tma} geom={geom}: {ms:8.4f} ms {B/ms/1e6:8.1f} GB/s {B/ms/1e6/peak:6.3f}  "
               f"{'OK' if ok else 'MISMATCH'}", flush=True)
     ctx.set_option("spmv_kernel", 0)
 
@@ -129,9 +131,10 @@ def main():
             print(f"mpk k={k} packed (strategy {ctx.query('last_mpk_strategy')}): {ms:8.4f} ms  B_mpk {Bk/ms/1e6:8.1f} GB/s "
                   f"({Bk/ms/1e6/peak:5.3f})  {'OK' if ok else 'MISMATCH'}", flush=True)
         ctx.set_option("mpk_kernel", 5)
-        for chunk, cps, flags, pf, l2, w0, stream, rows, tma in itertools.product(
+        for chunk, cps, flags, pf, l2, w0, stream, rows, tma, geom in itertools.product(
                 ints(args.chunks), ints(args.cps), ints(args.flags), ints(args.pf), ints(args.l2), ints(args.w0),
-                ints(args.stream), ints(args.rows), ints(args.tma)):
+                ints(args.stream), ints(args.rows), ints(args.tma), ints(args.geom)):
+            ctx.set_option("sell_geom", geom)
             ctx.set_option("sell_tma", tma)
             ctx.set_option("sell_rows", rows)
             ctx.set_option("sell_chunk", chunk)
@@ -148,7 +151,7 @@ def main():
             nl = ctx.launch_count - l0
             ok = all(same_bits(lv[i].to_host(), ref[i]) for i in range(k))
             ms = timed(ctx, lambda: dA.mpk(k, x, lv, 0), max(4, args.reps // 2))
-            print(f"mpk k={k} sell chunk={chunk} stream={stream} rows={rows} tma={tma} cps={cps} flags={flags} pf={pf} l2={l2} w0={w0} "
+            print(f"mpk k={k} sell chunk={chunk} stream={stream} rows={rows} tma={tma} geom={geom} cps={cps} flags={flags} pf={pf} l2={l2} w0={w0} "
                   f"launches={nl} strategy={ctx.query('last_mpk_strategy')}: {ms:8.4f} ms  B_mpk {Bk/ms/1e6:8.1f} GB/s "
                   f"({Bk/ms/1e6/peak:5.3f})  {'OK' if ok else 'MISMATCH'}", flush=True)
         ctx.set_option("mpk_kernel", 0)
