@@ -148,6 +148,7 @@ NSK_API int nsk_ctx_set_option(nsk_ctx_t c, const char *name, int64_t v)
     else if (!strcmp(name, "sell_chunk")) c->opt.sell_chunk = v;
     else if (!strcmp(name, "sell_geom")) c->opt.sell_geom = v;
     else if (!strcmp(name, "sell_ctas_per_sm")) c->opt.sell_ctas_per_sm = v;
+    else if (!strcmp(name, "sell_max_ctas")) c->opt.sell_max_ctas = v;
     else if (!strcmp(name, "sell_flags")) c->opt.sell_flags = v;
     else if (!strcmp(name, "sell_pf_dist")) c->opt.sell_pf_dist = v;
     else if (!strcmp(name, "sell_stream")) c->opt.sell_stream = v;

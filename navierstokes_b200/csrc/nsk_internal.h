@@ -66,6 +66,7 @@ struct nsk_options {
     int64_t sell_chunk = 0;       // consecutive tiles a CTA takes per item; 0 = default (2 fused, 4 single product)
     int64_t sell_geom = 0;        // 2 = operators stored with one global pattern still take the masked consumer path (A/B)
     int64_t sell_ctas_per_sm = 0; // 0 = what the occupancy calculator allows
+    int64_t sell_max_ctas = 0;    // > 0: cap of the persistent grid (tests: many items per CTA)
     int64_t sell_flags = -1;      // < 0 default (3): bit 0 eviction / streaming hints, bit 1 L2 prefetch of level 0's tiles
     int64_t sell_pf_dist = 0;     // items ahead the L2 prefetch runs; 0 = default 2
     int64_t sell_rows = 0;        // streaming kernel: rows of a tile per consumer thread (0 = default 1, 2)

@@ -10,7 +10,7 @@ from conftest import CSR_CASES, VECS, assert_bits_equal, golden
 
 pytestmark = pytest.mark.gpu
 
-SELL_OPTS = ("spmv_kernel", "mpk_kernel", "sell_chunk", "sell_ctas_per_sm", "sell_stream", "sell_rows", "sell_tma", "sell_pf_dist", "wave_l2_pct",
+SELL_OPTS = ("spmv_kernel", "mpk_kernel", "sell_chunk", "sell_ctas_per_sm", "sell_max_ctas", "sell_geom", "sell_stream", "sell_rows", "sell_tma", "sell_pf_dist", "wave_l2_pct",
              "pipe_w0_pct")
 
 
@@ -223,3 +223,31 @@ def test_sell_ragged_and_empty_rows(sell, oracle_lib):
         x = matgen.vec_uniform(n, seed=2)
         dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
         assert_bits_equal(dA.spmv(x), oracle_lib.spmv(A.ptrow, A.indcol, A.coef, x), f"n={n}")
+
+
+@pytest.mark.parametrize("gen,args", [("laplace3d_7pt", (64, 64, 24)), ("laplace2d_5pt", (512, 300)), ("laplace3d_7pt", (33, 31, 40))])
+@pytest.mark.parametrize("rows,tma", [(0, 0), (1, 0), (1, 4)])
+def test_sell_long_streams_per_cta(sell, oracle_lib, gen, args, rows, tma):
+    """A handful of CTAs walk the whole operator: every stage, ring slot and barrier phase is reused many times (two rows per
+    thread with its two teams sharing the stage ring, one row per thread with three and four stages)."""
+    ctx = sell
+    A = getattr(matgen, gen)(*args)
+    x = matgen.vec_uniform(A.n, seed=3)
+    dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
+    ctx.set_option("sell_rows", rows)
+    ctx.set_option("sell_tma", tma)
+    ctx.set_option("wave_l2_pct", 1000)
+    dx = ctx.to_device(x)
+    try:
+        for cap in (1, 3, 8, 29):
+            ctx.set_option("sell_max_ctas", cap)
+            assert_bits_equal(dA.spmv(x), oracle_lib.spmv(A.ptrow, A.indcol, A.coef, x), f"{gen}{args} spmv cap={cap}")
+            assert ctx.query("last_spmv_kernel") == 4
+            for k in (2, 4):
+                ref = oracle_lib.mpk(A.ptrow, A.indcol, A.coef, k, x)
+                for rep in range(2):
+                    lv = dA.mpk(k, dx)
+                    assert ctx.query("last_mpk_strategy") == 5
+                    assert_bits_equal(np.stack([l.to_host() for l in lv]), ref, f"{gen}{args} k={k} cap={cap} rep={rep}")
+    finally:
+        ctx.set_option("sell_max_ctas", 0)
