@@ -223,6 +223,9 @@ int64_t nsk_csr_mpk_bytes(nsk_csr_t A, int k);
  * form the default kernels stream from HBM), built on first call; 0 when the operator does not pack
  * (its tiles reference x in too many runs) and the CSR kernels are used instead. */
 int64_t nsk_csr_packed_bytes(nsk_csr_t A);
+/* Bytes of the sliced-ELL tile copy (csrc/sell.cu) the default product / fused-powers kernels stream; 0 when the operator
+ * is not stored that way.  Builds the tiles if no product has run yet. */
+int64_t nsk_csr_tile_bytes(nsk_csr_t A);
 
 /* y = A x.   x: n_cols doubles, y: n doubles. */
 int nsk_spmv(nsk_csr_t A, const double *x, double *y, nsk_mode mode, nsk_where where);
@@ -245,6 +248,19 @@ int nsk_bcsr4_create(nsk_ctx_t ctx, int nbrows, int64_t nblocks, const int *ptro
 int nsk_bcsr4_destroy(nsk_bcsr4_t B);
 /* y = B x, both 4*nbrows doubles.  Exact modes follow SpMV_BCSR_FMA's (block, j) order. */
 int nsk_spmv_bcsr4(nsk_bcsr4_t B, const double *x, double *y, nsk_mode mode, nsk_where where);
+/* levels[l] = B^(l+1) x, l < k: replaces SpM2V_BCSR / _OPT / _FMA / _AVX2 (reference mpk/SpM2V.cpp:376-801) for k = 2,
+ * any k <= 16.  Bit-identical to k block products in (block, j) order.  k device-resident launches of the block kernel
+ * by default; option mpk_kernel = 5 runs one fused launch of the level pipeline on the scalar expansion of the blocks. */
+int nsk_bcsr4_mpk(nsk_bcsr4_t B, int k, const double *x, double *const *levels, nsk_mode mode, nsk_where where);
+/* Y = B X for s dense columns (column-major; ldx, ldy >= 4 * nbrows; device pointers: columns 16-byte aligned).
+ * Replaces MatMatMult_SeqBAIJ_4_AVX2(A, X, Y, s_step) (reference src/kernels/spmm_avx2.c:7-109): columns in groups of
+ * four, per block a four-link fma chain that is then ADDED to the row's sum -- the same grouping, bit for bit.  The
+ * reference's horizontal reduction (:93-99) adds four equal lanes and so returns 4 * (B X); this entry returns B X
+ * (multiplying by 4 is exact, the tests compare 4 * Y with the literal restatement). */
+int nsk_spmm_bcsr4(nsk_bcsr4_t B, int s, const double *X, int64_t ldx, double *Y, int64_t ldy, nsk_where where);
+/* V(:,0) = v0, V(:,j+1) = B V(:,j) for j < s (V: s + 1 columns, leading dimension ldv): the monomial Krylov basis of
+ * BuildKrylovBasis_AVX2 (reference src/kernels/spmm_avx2.c:112-168), one single-column product per vector. */
+int nsk_krylov_basis_bcsr4(nsk_bcsr4_t B, int s, const double *v0, double *V, int64_t ldv, nsk_where where);
 
 /* ---- vectors (device-side dot / axpy family used by the Krylov solvers) ---------------------- */
 /* result pointers are HOST doubles; the call returns after the value has landed. */

@@ -8,7 +8,7 @@ load the library or touch a GPU; creating a ``Context`` does, and fails loudly w
 from . import matgen  # noqa: F401
 from .api import (  # noqa: F401
     DEVICE, EXACT_FMA, EXACT_MULADD, FAST, HOST, Bcsr4Matrix, Context, CsrMatrix, DeviceVector, NskError,
-    Generate1stlayer_BCSR4, SpM2V, SpM2V0, SpM2V_BCSR, SpM2V_BCSR_AVX2, SpM2V_BCSR_FMA, SpM2V_BCSR_OPT, SpMV_BCSR, SpMV_BCSR_AVX2, SpMV_BCSR_FMA, SpMV_BCSR_OPT, bcsr4x4_matrix,
+    BuildKrylovBasis_AVX2, Generate1stlayer_BCSR4, MatMatMult_SeqBAIJ_4_AVX2, SpM2V, SpM2V0, SpM2V_BCSR, SpM2V_BCSR_AVX2, SpM2V_BCSR_FMA, SpM2V_BCSR_OPT, SpMV_BCSR, SpMV_BCSR_AVX2, SpMV_BCSR_FMA, SpMV_BCSR_OPT, bcsr4x4_matrix,
     COO2CSR, Generate1stlayer, generate_BCSR4, read_mtx, SpM2V_CSR, SpM2V_CSR_AVX2, SpM2V_CSR_OPT, SpM3V, SpM4V, SpMV_CSR, SpMV_CSR_AVX2,
     SpMV_CSR_FMA, SpMV_CSR_OPT, csrmatrix, default_context, flush_cache, norm2, orthogonalize, orthonormalize_against_basis, rel_error,
 )

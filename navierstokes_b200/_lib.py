@@ -70,12 +70,16 @@ SIGNATURES = {
     "nsk_csr_spmv_bytes": (C.c_int64, [C.c_void_p]),
     "nsk_csr_mpk_bytes": (C.c_int64, [C.c_void_p, C.c_int]),
     "nsk_csr_packed_bytes": (C.c_int64, [C.c_void_p]),
+    "nsk_csr_tile_bytes": (C.c_int64, [C.c_void_p]),
     "nsk_spmv": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "nsk_mpk": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, c_void_pp, C.c_int, C.c_int]),
     "nsk_mpk_multi": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_void_pp, c_void_pp, C.c_int, C.c_int]),
     "nsk_bcsr4_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, c_void_pp]),
     "nsk_bcsr4_destroy": (C.c_int, [C.c_void_p]),
     "nsk_spmv_bcsr4": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "nsk_bcsr4_mpk": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "nsk_spmm_bcsr4": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int]),
+    "nsk_krylov_basis_bcsr4": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
     "nsk_dot": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, c_double_p, C.c_int]),
     "nsk_norm2": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, c_double_p, C.c_int]),
     "nsk_rel_error": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, c_double_p, C.c_int]),

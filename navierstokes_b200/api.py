@@ -303,6 +303,11 @@ class CsrMatrix:
         """Bytes of the tile-packed copy the default kernels stream (0: operator does not pack, CSR kernels run)."""
         return int(self.ctx.lib.nsk_csr_packed_bytes(self.h))
 
+    @property
+    def tile_bytes(self) -> int:
+        """Bytes of the sliced-ELL tile copy the default kernels stream (0: not stored that way)."""
+        return int(self.ctx.lib.nsk_csr_tile_bytes(self.h))
+
     def mpk_bytes(self, k: int) -> int:
         return int(self.ctx.lib.nsk_csr_mpk_bytes(self.h, k))
 
@@ -417,6 +422,38 @@ class Bcsr4Matrix:
         self.ctx._ck(self.ctx.lib.nsk_spmv_bcsr4(self.h, C.c_void_p(_ptr(x)), C.c_void_p(_ptr(y)), mode, HOST))
         return y
 
+    def mpk(self, k: int, x, levels=None, mode: int = EXACT_FMA):
+        """levels[l] = B^(l+1) x (SpM2V_BCSR* of the reference for k = 2, mpk/SpM2V.cpp:376-801).  numpy in -> list of numpy
+        out; DeviceVector in -> enqueue only."""
+        if isinstance(x, DeviceVector):
+            levels = [self.ctx.empty(self.n) for _ in range(k)] if levels is None else levels
+            arr = (C.c_void_p * k)(*[l.ptr for l in levels])
+            self.ctx._ck(self.ctx.lib.nsk_bcsr4_mpk(self.h, k, x.ptr, arr, mode, DEVICE))
+            return levels
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        assert x.size == self.n
+        levels = [np.empty(self.n) for _ in range(k)] if levels is None else levels
+        arr = (C.c_void_p * k)(*[C.c_void_p(_ptr(l)) for l in levels])
+        self.ctx._ck(self.ctx.lib.nsk_bcsr4_mpk(self.h, k, C.c_void_p(_ptr(x)), arr, mode, HOST))
+        return levels
+
+    def spmm(self, X: np.ndarray) -> np.ndarray:
+        """Y = B X for the s columns of X (n x s): MatMatMult_SeqBAIJ_4_AVX2 (src/kernels/spmm_avx2.c:7-109)."""
+        X = np.asfortranarray(X, dtype=np.float64)
+        assert X.ndim == 2 and X.shape[0] == self.n
+        s = X.shape[1]
+        Y = np.zeros((self.n, s), order="F")
+        self.ctx._ck(self.ctx.lib.nsk_spmm_bcsr4(self.h, s, C.c_void_p(_ptr(X)), self.n, C.c_void_p(_ptr(Y)), self.n, HOST))
+        return Y
+
+    def krylov_basis(self, v0: np.ndarray, s: int) -> np.ndarray:
+        """[v0, B v0, ..., B^s v0] (n x (s+1)): BuildKrylovBasis_AVX2 (src/kernels/spmm_avx2.c:112-168)."""
+        v0 = np.ascontiguousarray(v0, dtype=np.float64)
+        assert v0.size == self.n
+        V = np.zeros((self.n, s + 1), order="F")
+        self.ctx._ck(self.ctx.lib.nsk_krylov_basis_bcsr4(self.h, s, C.c_void_p(_ptr(v0)), C.c_void_p(_ptr(V)), self.n, HOST))
+        return V
+
 
 # =================================================================================================
 # reference-named layer
@@ -518,9 +555,7 @@ def SpMV_BCSR_AVX2(y, x, A: bcsr4x4_matrix):
 
 
 def _spm2v_bcsr(z, y, x, A: bcsr4x4_matrix, mode):
-    g = A.gpu()
-    g.spmv(x, _out(y, 4 * A.nrows), mode)
-    g.spmv(y, _out(z, 4 * A.nrows), mode)
+    A.gpu().mpk(2, x, [_out(y, 4 * A.nrows), _out(z, 4 * A.nrows)], mode)
 
 
 def SpM2V_BCSR(z, y, x, A: bcsr4x4_matrix, ptrowendB=None):
@@ -542,6 +577,16 @@ def SpM2V_BCSR_FMA(z, y, x, A: bcsr4x4_matrix, ptrowendB=None):
 def SpM2V_BCSR_AVX2(z, y, x, A: bcsr4x4_matrix, ptrowendB=None):
     """mpk/SpM2V.cpp:675: lane i of the AVX2 kernel runs row 4*bi+i's (block, j) fma chain."""
     _spm2v_bcsr(z, y, x, A, EXACT_FMA)
+
+
+def MatMatMult_SeqBAIJ_4_AVX2(A: bcsr4x4_matrix, X, Y, s_step: int):
+    """Y = A X on s_step dense columns (reference src/kernels/spmm_avx2.c:7-109; returns A X, not the reference's 4 A X)."""
+    Y[:, :s_step] = A.gpu().spmm(np.asarray(X)[:, :s_step])
+
+
+def BuildKrylovBasis_AVX2(A: bcsr4x4_matrix, v0, s_step: int):
+    """V = [v0, A v0, ..., A^s v0] (reference src/kernels/spmm_avx2.c:112-168)."""
+    return A.gpu().krylov_basis(v0, s_step)
 
 
 def Generate1stlayer_BCSR4(ptrowendB, A: bcsr4x4_matrix):

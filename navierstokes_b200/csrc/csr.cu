@@ -136,6 +136,13 @@ NSK_API int64_t nsk_csr_packed_bytes(nsk_csr_t A)
     return (int64_t)nsk_packed_bytes(A);
 }
 
+NSK_API int64_t nsk_csr_tile_bytes(nsk_csr_t A)
+{
+    if (!A) return 0;
+    cudaSetDevice(A->ctx->device);
+    return (int64_t)nsk_sell_bytes(A);
+}
+
 int nsk_halo_exchange_dev(nsk_csr_t A, double *xlocal, int depth, bool allow_push);
 int nsk_halo_release_dev(nsk_csr_t A, const double *xlocal, int depth);  // dist.cu
 

@@ -162,6 +162,8 @@ struct nsk_bcsr4_s {
     int *d_ptrow = nullptr;
     int *d_indcol = nullptr;
     double *d_coef = nullptr;
+    std::vector<int> h_ptrow;         // block row pointers (host copy: sizes of the scalar expansion)
+    nsk_csr_t expanded = nullptr;     // scalar CSR with the blocks' explicit zeros, built on the first FUSED powers call
 };
 
 // ---- kernel launchers (spmv_kernels.cu) -----------------------------------------------------

@@ -982,250 +982,9 @@ __device__ __forceinline__ void sl_consume_gpat(const SlParams &P, const SlCta &
     }
 }
 
-// The same with FOUR stages and items of four tiles (the three-CTAs-per-SM instances, 64 registers): tile j of every
-// item lives in stage j, so all stage addresses are immediates and every barrier's parity is the item's, and a thread
-// keeps the rows of TWO tiles in flight (2 W gathers before the first link of either chain).  Only the very last item of
-// a level can be short; it is taken tile by tile.
-template <int W>
-__device__ __forceinline__ void sl_consume_gpat_pairs(const SlParams &P, const SlCta &C, int n_my, int tid, const unsigned char *stages,
-                                                      const uint64_t *s_full, const uint64_t *s_empty, const uint64_t *s_ready,
-                                                      unsigned int *s_fin, const int (*s_hdr)[2], const int (*s_desc)[SL_MAXCHUNK * 16])
-{
-    constexpr int STAGE = SL_ROWS + 8 * W * SL_ROWS;
-    constexpr unsigned int FULL = (1u << W) - 1u;
-    const uint32_t a_full = smem_u32(s_full), a_empty = smem_u32(s_empty), a_ready = smem_u32(s_ready);
-    const uint32_t a_mask = smem_u32(stages) + (uint32_t)tid;
-    const uint32_t a_val = smem_u32(stages) + SL_ROWS + 8u * (uint32_t)tid;
-    const char *const xsrc = reinterpret_cast<const char *>(C.src[0] + tid);
-    char *const ydst = reinterpret_cast<char *>(C.dst[0] + tid);
-    const bool last = C.last != 0;
-    const bool muladd = C.muladd != 0;
-    const bool lane0 = (tid & 31) == 0;
-    for (int it = 0; it < n_my; ++it) {
-        const int slot = it % SL_RING;
-        const uint32_t ph = (uint32_t)it & 1u;
-        sl_mbar_wait_a(a_ready + 8u * slot, (uint32_t)(it / SL_RING) & 1u);
-        const int ntile = s_hdr[slot][0];
-        const int *d = s_desc[slot] + 2;
-        if (ntile == 4) {
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const int2 q0 = *reinterpret_cast<const int2 *>(d + 32 * h);       // row0, live rows
-                const int2 q1 = *reinterpret_cast<const int2 *>(d + 32 * h + 16);
-                const uint32_t o0 = (uint32_t)(2 * h) * STAGE, o1 = (uint32_t)(2 * h + 1) * STAGE;
-                sl_mbar_wait_a(a_full + 16u * h, ph);
-                const unsigned int m0 = sl_lds_u8(a_mask + o0);
-                sl_mbar_wait_a(a_full + 16u * h + 8u, ph);
-                const unsigned int m1 = sl_lds_u8(a_mask + o1);
-                const bool live0 = tid < q0.y, live1 = tid < q1.y;
-                double xv0[1][W], xv1[1][W];
-                double acc0 = 0.0, acc1 = 0.0, dummy = 0.0;
-                if (__all_sync(0xffffffffu, live0 && live1 && m0 == FULL && m1 == FULL)) {
-                    const char *xb0 = sl_add_b(xsrc, 8ll * q0.x);
-                    const char *xb1 = sl_add_b(xsrc, 8ll * q1.x);
-#pragma unroll
-                    for (int e = 0; e < W; e++) xv0[0][e] = sl_ld_x_off(xb0, P.goff8[e]);
-#pragma unroll
-                    for (int e = 0; e < W; e++) xv1[0][e] = sl_ld_x_off(xb1, P.goff8[e]);
-                    if (muladd) {
-                        SlChain<1, W, 0>::template run<true>(a_val + o0, xv0, m0, false, acc0, dummy);
-                        SlChain<1, W, 0>::template run<true>(a_val + o1, xv1, m1, false, acc1, dummy);
-                    } else {
-                        SlChain<1, W, 0>::template run<false>(a_val + o0, xv0, m0, false, acc0, dummy);
-                        SlChain<1, W, 0>::template run<false>(a_val + o1, xv1, m1, false, acc1, dummy);
-                    }
-                } else {
-                    const int cm = P.n_cols - 1 - tid;  // a dead row's own x entry must stay inside x
-                    const char *xb0 = sl_add_b(xsrc, 8ll * min(q0.x, cm));
-                    const char *xb1 = sl_add_b(xsrc, 8ll * min(q1.x, cm));
-#pragma unroll
-                    for (int e = 0; e < W; e++) xv0[0][e] = sl_ld_x_off(xb0, (m0 & (1u << e)) ? P.goff8[e] : 0ll);
-#pragma unroll
-                    for (int e = 0; e < W; e++) xv1[0][e] = sl_ld_x_off(xb1, (m1 & (1u << e)) ? P.goff8[e] : 0ll);
-                    if (muladd) {
-                        SlChain<1, W, 0>::template run<true>(a_val + o0, xv0, m0, true, acc0, dummy);
-                        SlChain<1, W, 0>::template run<true>(a_val + o1, xv1, m1, true, acc1, dummy);
-                    } else {
-                        SlChain<1, W, 0>::template run<false>(a_val + o0, xv0, m0, true, acc0, dummy);
-                        SlChain<1, W, 0>::template run<false>(a_val + o1, xv1, m1, true, acc1, dummy);
-                    }
-                }
-                if (live0) {
-                    double *y = reinterpret_cast<double *>(ydst + 8ll * q0.x);
-                    if (last) __stcs(y, acc0);
-                    else *y = acc0;
-                }
-                if (live1) {
-                    double *y = reinterpret_cast<double *>(ydst + 8ll * q1.x);
-                    if (last) __stcs(y, acc1);
-                    else *y = acc1;
-                }
-                __syncwarp();
-                if (lane0) {
-                    sl_mbar_arrive_a(a_empty + 16u * h);
-                    sl_mbar_arrive_a(a_empty + 16u * h + 8u);
-                }
-            }
-        } else {
-            for (int j = 0; j < ntile; ++j, d += 16) {
-                const int2 q = *reinterpret_cast<const int2 *>(d);
-                const bool live = tid < q.y;
-                const uint32_t so = (uint32_t)j * STAGE;
-                sl_mbar_wait_a(a_full + 8u * j, ph);
-                const unsigned int m = sl_lds_u8(a_mask + so);
-                const char *xb = sl_add_b(xsrc, 8ll * min(q.x, P.n_cols - 1 - tid));
-                double xv[1][W];
-                double acc0 = 0.0, dummy = 0.0;
-#pragma unroll
-                for (int e = 0; e < W; e++) xv[0][e] = sl_ld_x_off(xb, (m & (1u << e)) ? P.goff8[e] : 0ll);
-                if (muladd) SlChain<1, W, 0>::template run<true>(a_val + so, xv, m, true, acc0, dummy);
-                else SlChain<1, W, 0>::template run<false>(a_val + so, xv, m, true, acc0, dummy);
-                if (live) {
-                    double *y = reinterpret_cast<double *>(ydst + 8ll * q.x);
-                    if (last) __stcs(y, acc0);
-                    else *y = acc0;
-                }
-                __syncwarp();
-                if (lane0) sl_mbar_arrive_a(a_empty + 8u * j);
-            }
-        }
-        __syncwarp();
-        if (lane0) red_release_cta_shared_add(&s_fin[slot], 1u);  // the slot may be reused and the item published
-    }
-}
-
-// ---- two rows per thread (operators with one global pattern, one right-hand side, even tile boundaries, 16-byte
-// aligned vectors).  The eight consumer warps form two TEAMS of four; team g takes tiles g, g + 2, ... of the CTA's
-// stream, thread u of a team owns rows 2u and 2u + 1 of the tile: coefficients by LDS.128, x by LDG.128 for even pattern
-// offsets (two LDG.64 for odd ones), y by STG.128 -- half the instructions per row, and 2 W x entries in flight per
-// thread.  Tiles whose gathers cannot leave x whatever the masks say (all but the first / last few of the operator) issue
-// them BEFORE waiting for the coefficient stage; the masks then only predicate the links of the chains.
-__device__ __forceinline__ void sl_ld_x2_off(const char *base, long long off, double &a, double &b)
-{
-    asm volatile("{\n\t.reg .b64 p;\n\tadd.s64 p, %2, %3;\n\tld.global.v2.f64 {%0, %1}, [p];\n\t}" : "=d"(a), "=d"(b) : "l"(base), "l"(off) : "memory");
-}
-__device__ __forceinline__ void sl_ld_x11_off(const char *base, long long off, double &a, double &b)
-{
-    asm volatile("{\n\t.reg .b64 p;\n\tadd.s64 p, %2, %3;\n\tld.global.f64 %0, [p];\n\tld.global.f64 %1, [p+8];\n\t}" : "=d"(a), "=d"(b) : "l"(base), "l"(off) : "memory");
-}
-template <int OFF>
-__device__ __forceinline__ void sl_lds_v2f64(uint32_t a, double &x, double &y)
-{
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(x), "=d"(y) : "r"(a), "n"(OFF));
-}
-__device__ __forceinline__ unsigned int sl_lds_u16(uint32_t a)
-{
-    unsigned int v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-}
-
-template <int W, int E>
-struct SlChain2 {
-    template <bool MULADD>
-    static __device__ __forceinline__ void run(uint32_t a_val, const double (&xv)[W][2], unsigned int m, bool masked, double &acc0, double &acc1)
-    {
-        if constexpr (E < W) {
-            double a0, a1;
-            sl_lds_v2f64<E * SL_ROWS * 8>(a_val, a0, a1);
-            if (!masked || (m & (1u << E))) acc0 = row_op<MULADD>(a0, xv[E][0], acc0);
-            if (!masked || (m & (256u << E))) acc1 = row_op<MULADD>(a1, xv[E][1], acc1);
-            SlChain2<W, E + 1>::template run<MULADD>(a_val, xv, m, masked, acc0, acc1);
-        }
-    }
-};
-
-template <int W, int NS>
-__device__ __forceinline__ void sl_consume_gpat2(const SlParams &P, const SlCta &C, int n_my, int tid, const unsigned char *stages,
-                                                 const uint64_t *s_full, const uint64_t *s_empty, const uint64_t *s_ready,
-                                                 unsigned int *s_fin, const int (*s_hdr)[2], const int (*s_desc)[SL_MAXCHUNK * 16])
-{
-    constexpr int STAGE = SL_ROWS + 8 * W * SL_ROWS;
-    constexpr unsigned int FULL2 = ((1u << W) - 1u) * 257u;  // both rows have every slot
-    const int team = tid >> 7;
-    const int u = tid & 127;
-    const uint32_t a_full = smem_u32(s_full), a_empty = smem_u32(s_empty), a_ready = smem_u32(s_ready);
-    const uint32_t a_mask = smem_u32(stages) + 2u * (uint32_t)u;
-    const uint32_t a_val = smem_u32(stages) + SL_ROWS + 16u * (uint32_t)u;
-    const char *const xsrc = reinterpret_cast<const char *>(C.src[0] + 2 * u);
-    char *const ydst = reinterpret_cast<char *>(C.dst[0] + 2 * u);
-    const bool last = C.last != 0;
-    const bool muladd = C.muladd != 0;
-    const bool lane0 = (tid & 31) == 0;
-    // rows [lo, hi] of the operator may gather unconditionally: every pattern offset stays inside x
-    const int lo = -P.grel[0], hi = P.n_cols - SL_ROWS - P.grel[W - 1];
-    // Both teams walk ALL tiles of the stream (stage and parity advance per tile) and merely observe the landing of the
-    // other team's tiles: a barrier's parity tells one phase from the next only, so a team must not skip a phase of a
-    // stage it shares (every non-final item has an even number of tiles: tile j of an item belongs to team j & 1).
-    uint32_t st = 0, ph = 0;
-    for (int it = 0; it < n_my; ++it) {
-        const int slot = it % SL_RING;
-        sl_mbar_wait_a(a_ready + 8u * slot, (uint32_t)(it / SL_RING) & 1u);
-        const int ntile = s_hdr[slot][0];
-        const int *d = s_desc[slot] + 2;
-        for (int j = 0; j < ntile; ++j, d += 16) {
-            if ((j & 1) != team) {
-                sl_mbar_wait_a(a_full + 8u * st, ph);
-                if (++st == (uint32_t)NS) {
-                    st = 0;
-                    ph ^= 1u;
-                }
-                continue;
-            }
-            const int2 q = *reinterpret_cast<const int2 *>(d);  // row0, live rows (clipped by the dependency warp)
-            const uint32_t so = st * STAGE;
-            const bool inside = q.x >= lo && q.x <= hi;
-            double xv[W][2];
-            double acc0 = 0.0, acc1 = 0.0;
-            unsigned int m;
-            if (inside) {
-                const char *xb = sl_add_b(xsrc, 8ll * q.x);
-#pragma unroll
-                for (int e = 0; e < W; e++) {
-                    if (P.goff8[e] & 8) sl_ld_x11_off(xb, P.goff8[e], xv[e][0], xv[e][1]);
-                    else sl_ld_x2_off(xb, P.goff8[e], xv[e][0], xv[e][1]);
-                }
-                sl_mbar_wait_a(a_full + 8u * st, ph);
-                m = sl_lds_u16(a_mask + so);
-            } else {
-                // first / last tiles of the operator: the masks decide what may be read; a dead row's own entry is clamped
-                sl_mbar_wait_a(a_full + 8u * st, ph);
-                m = sl_lds_u16(a_mask + so);
-                const int cm = P.n_cols - 1 - 2 * u;
-                const char *xb0 = sl_add_b(xsrc, 8ll * min(q.x, cm));
-                const char *xb1 = sl_add_b(xsrc, 8ll * min(q.x, cm - 1));
-#pragma unroll
-                for (int e = 0; e < W; e++) {
-                    xv[e][0] = sl_ld_x_off(xb0, (m & (1u << e)) ? P.goff8[e] : 0ll);
-                    xv[e][1] = sl_ld_x_off(xb1, (m & (256u << e)) ? P.goff8[e] + 8 : 8ll);
-                }
-            }
-            const bool whole = __all_sync(0xffffffffu, m == FULL2);
-            if (muladd) SlChain2<W, 0>::template run<true>(a_val + so, xv, m, !whole, acc0, acc1);
-            else SlChain2<W, 0>::template run<false>(a_val + so, xv, m, !whole, acc0, acc1);
-            double *y = reinterpret_cast<double *>(ydst + 8ll * q.x);
-            if (2 * u + 1 < q.y) {
-                if (last) __stcs(reinterpret_cast<double2 *>(y), make_double2(acc0, acc1));  // nobody in this launch re-reads the last level
-                else *reinterpret_cast<double2 *>(y) = make_double2(acc0, acc1);
-            } else if (2 * u < q.y) {
-                y[0] = acc0;
-            }
-            __syncwarp();
-            if (lane0) sl_mbar_arrive_a(a_empty + 8u * st);  // the stage may be refilled (the warp's reads of it are done)
-            if (++st == (uint32_t)NS) {
-                st = 0;
-                ph ^= 1u;
-            }
-        }
-        __syncwarp();
-        if (lane0) red_release_cta_shared_add(&s_fin[slot], 1u);  // the slot may be reused and the item published
-    }
-}
-
-template <int NV, int W, int NS, int MINB, int R = 1>
+template <int NV, int W, int NS, int MINB>
 __global__ void __launch_bounds__(SLT_THREADS, MINB) sell_tma_kernel(const SlParams P)
 {
-    static_assert(R == 1 || (R == 2 && NV == 1 && W > 0), "two rows per thread: one right-hand side, pattern tiles");
     static_assert(W >= 0 && W <= SL_PSLOTS, "pattern width (0: tiles with explicit columns)");
     // pattern tiles: a stage holds the whole blob (mask + W x 256 coefficients); explicit tiles: the lengths + columns
     // prefix of the blob (the coefficients are loaded by the consumers together with the x gathers)
@@ -1258,7 +1017,7 @@ __global__ void __launch_bounds__(SLT_THREADS, MINB) sell_tma_kernel(const SlPar
         }
         for (int s = 0; s < NS; s++) {
             mbar_init(&s_full[s], 1);
-            mbar_init(&s_empty[s], SLT_NCW / R);  // R = 2: a tile is taken by one team of four warps
+            mbar_init(&s_empty[s], SLT_NCW);
         }
         fence_mbar_init();
         s_cta.src[0] = level == 0 ? P.x : P.levels[level - 1];
@@ -1466,16 +1225,9 @@ __global__ void __launch_bounds__(SLT_THREADS, MINB) sell_tma_kernel(const SlPar
     double dot_acc = 0.0;
     int st = 0;
     uint32_t ph = 0;  // stage of the next tile, parity of its completion
-    if constexpr (R == 2) {
-        sl_consume_gpat2<W, NS>(P, s_cta, n_my, tid, stages, s_full, s_empty, s_ready, s_fin, s_hdr, s_desc);
-        return;
-    }
     if constexpr (W > 0) {
         if (gpat && !P.dot_w) {  // (the fused dot of CG's product stays with the loop below)
-            if (NV == 1 && NS == 4 && P.chunk == 4 && (P.flags & 32))
-                sl_consume_gpat_pairs<W>(P, s_cta, n_my, tid, stages, s_full, s_empty, s_ready, s_fin, s_hdr, s_desc);
-            else
-                sl_consume_gpat<NV, W, NS>(P, s_cta, n_my, tid, stages, s_full, s_empty, s_ready, s_fin, s_hdr, s_desc);
+            sl_consume_gpat<NV, W, NS>(P, s_cta, n_my, tid, stages, s_full, s_empty, s_ready, s_fin, s_hdr, s_desc);
             n_done = n_my;
         }
     }
@@ -1633,22 +1385,6 @@ static sl_fn sl_lookup_tma_w(int w, int *stage_bytes)
     }
     return nullptr;
 }
-// two rows per thread: five stages, three CTAs of 64 registers per SM
-static sl_fn sl_lookup_tma2(int w, int *smem)
-{
-    *smem = (SL_ROWS + 8 * w * SL_ROWS) * 5;
-    switch (w) {
-    case 1: return sell_tma_kernel<1, 1, 5, 3, 2>;
-    case 2: return sell_tma_kernel<1, 2, 5, 3, 2>;
-    case 3: return sell_tma_kernel<1, 3, 5, 3, 2>;
-    case 4: return sell_tma_kernel<1, 4, 5, 3, 2>;
-    case 5: return sell_tma_kernel<1, 5, 5, 3, 2>;
-    case 6: return sell_tma_kernel<1, 6, 5, 3, 2>;
-    case 7: return sell_tma_kernel<1, 7, 5, 3, 2>;
-    case 8: return sell_tma_kernel<1, 8, 5, 3, 2>;
-    }
-    return nullptr;
-}
 // stages per CTA: 3 (four CTAs of 48 registers per SM) or 4 (three CTAs of 64 registers); two right-hand sides: 3 CTAs;
 // w = 0: explicit-column tiles (3 stages of 24 KB, three CTAs per SM)
 static SlLaunch sl_lookup_tma(int nv, int w, int ns, int *smem)
@@ -1682,7 +1418,6 @@ struct SellHost {
     int explicit_prefix = 0;  // > 0: every tile has explicit columns; largest lengths + columns prefix of a blob (bytes)
     int global_pattern = 0;   // 1: every tile is stored with ONE column pattern (grel, uniform_width slots)
     int grel[SL_PSLOTS] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int even_tiles = 0;       // 1: every tile starts at an even row (128-bit accesses of two rows per thread stay aligned)
 };
 
 static void sl_parallel(int n, const std::function<void(int)> &body)
@@ -1856,9 +1591,6 @@ static std::string sl_pack_host(int n, int n_cols, int64_t nnz, const int *ptrow
     if ((double)total > 1.5 * (12.0 * (double)nnz + 4.0 * n) + 65536.0) return "row lengths too ragged for sliced-ELL tiles";
     out.blob_bytes = total;
     out.n_pattern = n_pattern;
-    out.even_tiles = 1;
-    for (int t = 0; t < ntiles; t++)
-        if (st[t].row0 & 1) out.even_tiles = 0;
     out.blobs.assign(total + 128, 0);
     // 2. the blobs
     sl_parallel(ntiles, [&](int t) {
@@ -2258,7 +1990,7 @@ struct SlPlan {
 struct SellOp {
     bool ok = false;
     std::string why;
-    int ntiles = 0, n_pattern = 0, uniform_width = 0, explicit_prefix = 0, global_pattern = 0, even_tiles = 0;
+    int ntiles = 0, n_pattern = 0, uniform_width = 0, explicit_prefix = 0, global_pattern = 0;
     int grel[SL_PSLOTS] = {0, 0, 0, 0, 0, 0, 0, 0};
     size_t blob_bytes = 0;
     unsigned char *d_blobs = nullptr;
@@ -2339,7 +2071,6 @@ static SellOp *sl_get(nsk_csr_t A)
     op->uniform_width = H.uniform_width;
     op->explicit_prefix = H.explicit_prefix;
     op->global_pattern = H.global_pattern;
-    op->even_tiles = H.even_tiles;
     for (int e = 0; e < SL_PSLOTS; e++) op->grel[e] = H.grel[e];
     op->blob_bytes = H.blob_bytes;
     op->h_tiles.swap(H.stiles);
@@ -2486,16 +2217,9 @@ static int sl_run(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
     const bool tma_e = op->uniform_width == 0 && op->explicit_prefix > 0 && op->explicit_prefix <= SL_EXPLICIT_STAGE;
     const bool tma = (op->uniform_width > 0 || tma_e) && ctx->opt.sell_tma >= 0;
     int smem = 0;
-    SlLaunch L = tma ? sl_lookup_tma(nv, op->uniform_width, ctx->opt.sell_tma == 0 ? 3 : (int)ctx->opt.sell_tma, &smem)
+    const SlLaunch L = tma ? sl_lookup_tma(nv, op->uniform_width, ctx->opt.sell_tma == 0 ? 3 : (int)ctx->opt.sell_tma, &smem)
                      : stream ? sl_lookup_stream(nv, op->uniform_width, depth, rows)
                               : sl_lookup(nv, sl_plan_chunk(ctx, nv, false));
-    // two rows per thread (option sell_rows: 0 = when applicable, 1 = never): one global pattern, one right-hand side, no
-    // fused dot, even tile boundaries and items, every vector 16-byte aligned
-    bool two_rows = tma && nv == 1 && !dot_w && op->global_pattern && op->even_tiles && op->uniform_width > 0 &&
-                    ctx->opt.sell_rows != 1 && ctx->opt.sell_geom != 2 && sl_plan_chunk(ctx, nv, true) == 4 &&
-                    (reinterpret_cast<uintptr_t>(d_x) & 15) == 0;
-    for (int l = 0; l < k && two_rows; l++) two_rows = (reinterpret_cast<uintptr_t>(d_levels[l]) & 15) == 0;
-    if (two_rows) L.fn = sl_lookup_tma2(op->uniform_width, &smem);
     sl_fn fn = L.fn;
     if (tma) NSK_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     if (!tma) {
@@ -2613,7 +2337,7 @@ static int sl_run(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
     ctx->last_sell[3] = plan->grid;
     ctx->last_sell[4] = plan->d_ltile_buf ? 0 : 1;  // 1: every level walks the operator's own tile array
     ctx->last_sell[5] = op->ntiles;
-    ctx->last_sell[6] = tma ? (two_rows ? 2 : 1) : 0;
+    ctx->last_sell[6] = tma ? 1 : 0;
     ctx->last_sell[7] = plan->ngroups;
     return NSK_OK;
 }

@@ -170,9 +170,9 @@ void spm2v_b(double *z, double *y, const double *x, const bcsr4x4_matrix &B, nsk
 {
     std::lock_guard<std::mutex> lk(g_mu);
     nsk_bcsr4_t h = device_bcsr(B);
-    int s = nsk_spmv_bcsr4(h, x, y, mode, NSK_HOST);
-    if (s == NSK_OK) s = nsk_spmv_bcsr4(h, y, z, mode, NSK_HOST);
-    if (s != NSK_OK) die("nsk_spmv_bcsr4", s);
+    double *levels[2] = {y, z};
+    int s = nsk_bcsr4_mpk(h, 2, x, levels, mode, NSK_HOST);  // one call: x in once, both levels out
+    if (s != NSK_OK) die("nsk_bcsr4_mpk", s);
 }
 
 }  // namespace

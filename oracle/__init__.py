@@ -79,6 +79,8 @@ class _Oracle:
                                                 C.c_void_p, C.c_void_p, C.c_void_p]
             l.oracle_generate_bcsr4.restype = C.c_int64
             l.oracle_spmv_bcsr4_fma.argtypes = [C.c_int, _i32p, _i32p, _f64p, _f64p, _f64p]
+            l.oracle_spmm_baij4.argtypes = [C.c_int, _i32p, _i32p, _f64p, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p,
+                                            C.c_longlong, C.c_int]
             l.oracle_norm2.argtypes = [C.c_int64, _f64p]
             l.oracle_norm2.restype = C.c_double
             l.oracle_rel_error.argtypes = [C.c_int64, _f64p, _f64p]
@@ -179,6 +181,15 @@ class _Oracle:
         y = np.empty(4 * nb)
         self.l.oracle_spmv_bcsr4_fma(nb, _i32(ptrow), _i32(indcol), _f64(coef), _f64(x), y)
         return y
+
+    def spmm_baij4(self, ptrow, indcol, coef, X, literal=False):
+        """MatMatMult_SeqBAIJ_4_AVX2 restated (literal: with the reference's factor 4 from its lane reduction)."""
+        nb = len(ptrow) - 1
+        X = np.asfortranarray(X, dtype=np.float64)
+        Y = np.zeros((4 * nb, X.shape[1]), order="F")
+        self.l.oracle_spmm_baij4(nb, _i32(ptrow), _i32(indcol), _f64(coef), X.shape[1], X.ctypes.data, 4 * nb,
+                                 Y.ctypes.data, 4 * nb, 1 if literal else 0)
+        return Y
 
     # -- vectors ---------------------------------------------------------------------------
     def norm2(self, x):

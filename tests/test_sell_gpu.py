@@ -226,15 +226,15 @@ def test_sell_ragged_and_empty_rows(sell, oracle_lib):
 
 
 @pytest.mark.parametrize("gen,args", [("laplace3d_7pt", (64, 64, 24)), ("laplace2d_5pt", (512, 300)), ("laplace3d_7pt", (33, 31, 40))])
-@pytest.mark.parametrize("rows,tma", [(0, 0), (1, 0), (1, 4)])
-def test_sell_long_streams_per_cta(sell, oracle_lib, gen, args, rows, tma):
-    """A handful of CTAs walk the whole operator: every stage, ring slot and barrier phase is reused many times (two rows per
-    thread with its two teams sharing the stage ring, one row per thread with three and four stages)."""
+@pytest.mark.parametrize("geom,tma", [(0, 0), (2, 0), (0, 4)])
+def test_sell_long_streams_per_cta(sell, oracle_lib, gen, args, geom, tma):
+    """A handful of CTAs walk the whole operator: every stage, ring slot and barrier phase is reused many times (straight-line
+    and masked consumer paths, three and four stages)."""
     ctx = sell
     A = getattr(matgen, gen)(*args)
     x = matgen.vec_uniform(A.n, seed=3)
     dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
-    ctx.set_option("sell_rows", rows)
+    ctx.set_option("sell_geom", geom)
     ctx.set_option("sell_tma", tma)
     ctx.set_option("wave_l2_pct", 1000)
     dx = ctx.to_device(x)

@@ -603,3 +603,78 @@ def test_mpk_multi_pair_is_one_launch_and_muladd(ctx, oracle_lib, reset_options)
         for l in range(3):
             y = oracle_lib.spmv_muladd(A.ptrow, A.indcol, A.coef, y)
             assert_bits_equal(lm[v][l].to_host(), y, f"muladd vector {v} level {l}")
+
+
+@pytest.mark.parametrize("s", [1, 3, 4, 6, 9])
+def test_bcsr4_spmm_matches_the_restated_reference(ctx, oracle_lib, s):
+    """Y = A X on s dense columns (MatMatMult_SeqBAIJ_4_AVX2, src/kernels/spmm_avx2.c:7-109): the product bit for bit in the
+    reference's grouping (per block a four-link fma chain, then an add), and 4 * Y == the literal restatement including
+    the reference's lane reduction; also through the reference-named layer and against a dense product."""
+    A = matgen.fem_baij4(6)
+    Bh = matgen.csr_to_bcsr4(A)
+    rng = np.random.default_rng(5)
+    X = np.asfortranarray(rng.uniform(-1.0, 1.0, size=(A.n, s)))
+    B = nsk.Bcsr4Matrix(ctx, Bh.ptrow, Bh.indcol, Bh.coef)
+    Y = B.spmm(X)
+    ref = oracle_lib.spmm_baij4(Bh.ptrow, Bh.indcol, Bh.coef, X)
+    assert_bits_equal(Y, ref, f"spmm s={s}")
+    assert_bits_equal(4.0 * Y, oracle_lib.spmm_baij4(Bh.ptrow, Bh.indcol, Bh.coef, X, literal=True), "literal (factor 4)")
+    for k in range(s):  # same operator, different association than the single-chain product: close, not equal
+        assert nsk.rel_error(oracle_lib.spmv_bcsr4(Bh.ptrow, Bh.indcol, Bh.coef, X[:, k].copy()), Y[:, k].copy()) <= 1e-14
+    Bn = nsk.bcsr4x4_matrix(nrows=Bh.nbrows, nblocks=len(Bh.indcol), ptrow=Bh.ptrow, indcol=Bh.indcol, coef=Bh.coef)
+    Y2 = np.zeros_like(Y)
+    nsk.MatMatMult_SeqBAIJ_4_AVX2(Bn, X, Y2, s)
+    assert_bits_equal(Y2, ref, "reference-named layer")
+
+
+def test_bcsr4_krylov_basis(ctx, oracle_lib):
+    """[v0, A v0, ..., A^s v0] (BuildKrylovBasis_AVX2, src/kernels/spmm_avx2.c:112-168): column j + 1 is the one-column
+    product of column j, bit for bit; device-resident call equals the host call."""
+    A = matgen.fem_baij4(5)
+    Bh = matgen.csr_to_bcsr4(A)
+    v0 = matgen.vec_uniform(A.n, seed=9)
+    B = nsk.Bcsr4Matrix(ctx, Bh.ptrow, Bh.indcol, Bh.coef)
+    s = 5
+    V = B.krylov_basis(v0, s)
+    assert_bits_equal(V[:, 0].copy(), v0)
+    for j in range(s):
+        nxt = oracle_lib.spmm_baij4(Bh.ptrow, Bh.indcol, Bh.coef, V[:, j:j + 1])
+        assert_bits_equal(V[:, j + 1].copy(), nxt[:, 0].copy(), f"basis column {j + 1}")
+    Bn = nsk.bcsr4x4_matrix(nrows=Bh.nbrows, nblocks=len(Bh.indcol), ptrow=Bh.ptrow, indcol=Bh.indcol, coef=Bh.coef)
+    assert_bits_equal(nsk.BuildKrylovBasis_AVX2(Bn, v0, s), V)
+
+
+@pytest.mark.parametrize("k", [2, 3, 5])
+def test_bcsr4_powers_block_products_and_fused_expansion(ctx, oracle_lib, k):
+    """nsk_bcsr4_mpk (SpM2V_BCSR* for k = 2, mpk/SpM2V.cpp:376-801): k block products by default, ONE fused launch of the
+    level pipeline on the scalar expansion with mpk_kernel = 5 -- both bit-identical to k x SpMV_BCSR_FMA of the oracle,
+    host and device calls, both exact flavours agree level by level with repeated products."""
+    A = matgen.fem_baij4(7)
+    Bh = matgen.csr_to_bcsr4(A)
+    x = matgen.vec_uniform(A.n, seed=13)
+    ref, src = [], x
+    for _ in range(k):
+        src = oracle_lib.spmv_bcsr4(Bh.ptrow, Bh.indcol, Bh.coef, src)
+        ref.append(src)
+    B = nsk.Bcsr4Matrix(ctx, Bh.ptrow, Bh.indcol, Bh.coef)
+    try:
+        for strat in (0, 5):
+            ctx.set_option("mpk_kernel", strat)
+            before = ctx.launch_count
+            lv = B.mpk(k, ctx.to_device(x))
+            launches = ctx.launch_count - before
+            assert launches == (k if strat == 0 else 1), f"strategy {strat}: {launches} launches"
+            assert ctx.query("last_mpk_strategy") == (1 if strat == 0 else 5)
+            for l in range(k):
+                assert_bits_equal(lv[l].to_host(), ref[l], f"strategy {strat} level {l}")
+            host = B.mpk(k, x)
+            for l in range(k):
+                assert_bits_equal(host[l], ref[l], f"host call, strategy {strat} level {l}")
+        ctx.set_option("mpk_kernel", 0)
+        ma = B.mpk(k, x, mode=nsk.EXACT_MULADD)
+        src = x
+        for l in range(k):
+            src = B.spmv(src, mode=nsk.EXACT_MULADD)
+            assert_bits_equal(ma[l], src, f"muladd level {l}")
+    finally:
+        ctx.set_option("mpk_kernel", 0)
