@@ -198,6 +198,8 @@ int nsk_sell_host_create(int n, int n_cols, int64_t nnz, const int *ptrow, const
 const char *nsk_sell_host_why(void *handle);
 int nsk_sell_host_stats(void *handle, int64_t *bytes, int64_t *ntiles, int64_t *pattern_tiles);
 int nsk_sell_host_expand(void *handle, int *ptrow, int *indcol, double *coef);
+/* Number of slots of the operator's global column pattern (0: none), its offsets, and how many tiles are stored with it. */
+int nsk_sell_host_global_pattern(void *handle, int *rel, int64_t *global_tiles);
 /* CPU model of the fused sliced-ELL kernel's protocol on the schedule the GPU path would build: items of `chunk`
  * consecutive tiles, forward dependencies and window back-pressure through per-group completion counters, in-order
  * CTAs with up to `ring` open items that finish in any order but are published in order.  Same return convention as

@@ -58,6 +58,7 @@ SIGNATURES = {
     "nsk_pack_host_destroy": (None, [C.c_void_p]),
     "nsk_sell_host_create": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, c_void_pp]),
     "nsk_sell_host_why": (C.c_char_p, [C.c_void_p]),
+    "nsk_sell_host_global_pattern": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "nsk_sell_host_stats": (C.c_int, [C.c_void_p, c_int64_p, c_int64_p, c_int64_p]),
     "nsk_sell_host_expand": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nsk_sell_host_simulate": (C.c_longlong, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -199,6 +199,7 @@ struct SlCta {
     const double *src[2];
     double *dst[2];
     int row_end, last, muladd, pad;
+    int grel[8];  // the operator's global pattern (for code that cannot reach the kernel parameters)
 };
 
 template <int NV>
@@ -906,7 +907,8 @@ __device__ __forceinline__ const char *sl_add_b(const char *base, long long off)
 template <int NV, int W, int NS>
 __device__ __forceinline__ void sl_consume_gpat(const SlParams &P, const SlCta &C, int n_my, int tid, const unsigned char *stages,
                                                 const uint64_t *s_full, const uint64_t *s_empty, const uint64_t *s_ready,
-                                                unsigned int *s_fin, const int (*s_hdr)[2], const int (*s_desc)[SL_MAXCHUNK * 16])
+                                                unsigned int *s_fin, const int (*s_hdr)[2], const int (*s_desc)[SL_MAXCHUNK * 16],
+                                                int &it_io, int &st_io, uint32_t &ph_io)
 {
     constexpr int STAGE = SL_ROWS + 8 * W * SL_ROWS;
     constexpr unsigned int FULL = (1u << W) - 1u;
@@ -920,11 +922,14 @@ __device__ __forceinline__ void sl_consume_gpat(const SlParams &P, const SlCta &
     const bool last = C.last != 0;
     const bool muladd = C.muladd != 0;
     const bool lane0 = (tid & 31) == 0;
-    uint32_t so = 0, sb = 0, ph = 0;  // byte offset of the next tile's stage, of its barriers; parity of its completion
-    for (int it = 0; it < n_my; ++it) {
+    // byte offset of the next tile's stage, of its barriers; parity of its completion
+    uint32_t so = (uint32_t)st_io * STAGE, sb = 8u * (uint32_t)st_io, ph = ph_io;
+    int it = it_io;
+    for (; it < n_my; ++it) {
         const int slot = it % SL_RING;
         sl_mbar_wait_a(a_ready + 8u * slot, (uint32_t)(it / SL_RING) & 1u);
         const int ntile = s_hdr[slot][0];
+        if (s_hdr[slot][1] == 0) break;  // an item with an exception tile (a pattern of its own): the caller's general loop takes it
         const int *d = s_desc[slot] + 2;
         for (int j = 0; j < ntile; ++j, d += 16) {
             const int2 q = *reinterpret_cast<const int2 *>(d);  // row0, live rows (clipped by the dependency warp)
@@ -980,6 +985,9 @@ __device__ __forceinline__ void sl_consume_gpat(const SlParams &P, const SlCta &
         __syncwarp();
         if (lane0) red_release_cta_shared_add(&s_fin[slot], 1u);  // the slot may be reused and the item published
     }
+    it_io = it;
+    st_io = (int)(sb >> 3);
+    ph_io = ph;
 }
 
 template <int NV, int W, int NS, int MINB>
@@ -1027,6 +1035,7 @@ __global__ void __launch_bounds__(SLT_THREADS, MINB) sell_tma_kernel(const SlPar
         s_cta.row_end = P.level_rows[level];
         s_cta.last = ((P.flags & 1) && level == P.k - 1) ? 1 : 0;
         s_cta.muladd = P.muladd;
+        for (int e = 0; e < 8; e++) s_cta.grel[e] = P.grel[e];
     }
     __syncthreads();
 
@@ -1196,7 +1205,12 @@ __global__ void __launch_bounds__(SLT_THREADS, MINB) sell_tma_kernel(const SlPar
                 if ((lane & 3) == 0) dw.w = min(dw.w, s_cta.row_end - dw.z);
                 reinterpret_cast<int4 *>(s_desc[s])[lane] = dw;
             }
-            if (lane == 0) s_hdr[s][0] = ntile;
+            // word 6 of a pattern tile's descriptor: 1 = stored with the operator's global pattern (quarter 1 of the descriptor)
+            const bool pure = __all_sync(0xffffffffu, !((lane & 3) == 1 && lane < 4 * ntile) || dq.z != 0);
+            if (lane == 0) {
+                s_hdr[s][0] = ntile;
+                s_hdr[s][1] = pure ? 1 : 0;
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_ready[s]);  // release.cta: descriptors + everything acquired above
         }
@@ -1225,13 +1239,14 @@ __global__ void __launch_bounds__(SLT_THREADS, MINB) sell_tma_kernel(const SlPar
     double dot_acc = 0.0;
     int st = 0;
     uint32_t ph = 0;  // stage of the next tile, parity of its completion
-    if constexpr (W > 0) {
-        if (gpat && !P.dot_w) {  // (the fused dot of CG's product stays with the loop below)
-            sl_consume_gpat<NV, W, NS>(P, s_cta, n_my, tid, stages, s_full, s_empty, s_ready, s_fin, s_hdr, s_desc);
-            n_done = n_my;
-        }
-    }
     for (int it = n_done; it < n_my; ++it) {
+        if constexpr (W > 0) {
+            if (gpat && !P.dot_w) {  // (the fused dot of CG's product stays with the general code below)
+                // items of global-pattern tiles; comes back at an item that holds an exception tile (or at the end)
+                sl_consume_gpat<NV, W, NS>(P, s_cta, n_my, tid, stages, s_full, s_empty, s_ready, s_fin, s_hdr, s_desc, it, st, ph);
+                if (it >= n_my) break;
+            }
+        }
         const int slot = it % SL_RING;
         mbar_wait(&s_ready[slot], (it / SL_RING) & 1);
         const int ntile = s_hdr[slot][0];
@@ -1460,7 +1475,8 @@ static std::string sl_pack_host(int n, int n_cols, int64_t nnz, const int *ptrow
     std::vector<SlTile> &st = out.stiles;
     st.assign(ntiles, SlTile());
     // 1. per tile: format, geometry, size
-    std::atomic<int> too_long(0), unordered(0);
+    std::atomic<int> too_long(0);
+    std::vector<char> unordered((size_t)ntiles, 0);  // tile whose rows do not list their columns in ascending order
     std::vector<std::array<int, 8>> sw_all((size_t)ntiles);  // the slices' widths (explicit layout)
     sl_parallel(ntiles, [&](int t) {
         const nsk_tile &tl = tiles[t];
@@ -1498,7 +1514,7 @@ static std::string sl_pack_host(int n, int n_cols, int64_t nnz, const int *ptrow
                 }
             }
             if (pattern && !ascending) {
-                unordered.store(1);
+                unordered[t] = 1;
                 // any other entry order: the first row of full width is the pattern, every row must be a sub-pattern
                 // of it with slots ascending in entry order (the chain's order is the row's storage order)
                 int rref = 0;
@@ -1545,23 +1561,44 @@ static std::string sl_pack_host(int n, int n_cols, int64_t nnz, const int *ptrow
     out.explicit_prefix = 0;
     out.global_pattern = 0;
     if (n_pattern == ntiles && wmax >= 1) {
-        // ONE pattern for the whole operator when the union of the tiles' patterns still has at most 8 slots (any
-        // stencil on a box: the tiles on a domain face only lack some of the interior tiles' offsets).  The kernel
-        // then takes the offsets from its parameters (constant bank) and a warp whose 32 rows have every slot runs
-        // straight-line code without masks.  Needs rows with ascending columns (slot order = entry order).
-        if (!unordered.load()) {
+        // ONE pattern for (nearly) the whole operator: the union of the tiles' patterns when it still has at most 8 slots
+        // (any stencil on a box: the tiles on a domain face only lack some of the interior tiles' offsets); otherwise the
+        // union of the most frequent patterns that fits (a distributed slab: the tiles next to a ghost ring reference it
+        // at offsets of their own and stay EXCEPTIONS with their own pattern).  The kernel takes the global offsets from
+        // its parameters (constant bank); a warp of a global tile whose 32 rows have every slot runs straight-line code
+        // without masks.  Global tiles need rows with ascending columns (slot order = entry order); rp = 1 marks a global tile.
+        {
+            std::map<std::array<int, 9>, int> freq;  // {pw, rel[0..7]} -> tiles
+            for (int t = 0; t < ntiles; t++) {
+                if (unordered[t]) continue;  // (slots in entry order, not by offset: always an exception)
+                std::array<int, 9> key = {st[t].width, 0, 0, 0, 0, 0, 0, 0, 0};
+                for (int e = 0; e < st[t].width; e++) key[1 + e] = st[t].rel[e];
+                freq[key]++;
+            }
+            std::vector<std::pair<int, std::array<int, 9>>> order;
+            for (auto &kv : freq) order.push_back({kv.second, kv.first});
+            std::stable_sort(order.begin(), order.end(), [](const auto &a, const auto &b) { return a.first > b.first; });
             std::vector<int> uni;
-            for (int t = 0; t < ntiles && (int)uni.size() <= SL_PSLOTS; t++)
-                for (int e = 0; e < st[t].width; e++) {
-                    auto it = std::lower_bound(uni.begin(), uni.end(), st[t].rel[e]);
-                    if (it == uni.end() || *it != st[t].rel[e]) uni.insert(it, st[t].rel[e]);
+            for (auto &o : order) {
+                std::vector<int> u2 = uni;
+                for (int e = 0; e < o.second[0]; e++) {
+                    auto it = std::lower_bound(u2.begin(), u2.end(), o.second[1 + e]);
+                    if (it == u2.end() || *it != o.second[1 + e]) u2.insert(it, o.second[1 + e]);
                 }
-            if ((int)uni.size() <= SL_PSLOTS) {
+                if ((int)u2.size() <= wmax) uni.swap(u2);  // never wider than the widest tile: a slot costs every tile 2 KB
+            }
+            if ((int)uni.size() == wmax) {
+                // (the straight-line path runs all W slots of the kernel instance: the global pattern must fill them)
                 out.global_pattern = 1;
                 wmax = (int)uni.size();
                 for (int e = 0; e < SL_PSLOTS; e++) out.grel[e] = e < wmax ? uni[e] : 0;
-                for (int t = 0; t < ntiles; t++)
-                    for (int e = 0; e < SL_PSLOTS; e++) st[t].rel[e] = out.grel[e];
+                for (int t = 0; t < ntiles; t++) {
+                    bool sub = !unordered[t];
+                    for (int e = 0; e < st[t].width && sub; e++) sub = std::binary_search(uni.begin(), uni.end(), st[t].rel[e]);
+                    st[t].rp = sub ? 1 : 0;
+                    if (sub)
+                        for (int e = 0; e < SL_PSLOTS; e++) st[t].rel[e] = out.grel[e];
+                }
             }
         }
         out.uniform_width = wmax;
@@ -1895,6 +1932,19 @@ NSK_API int nsk_sell_host_stats(void *handle, int64_t *bytes, int64_t *ntiles, i
     if (ntiles) *ntiles = (int64_t)h->H.stiles.size();
     if (pattern_tiles) *pattern_tiles = h->H.n_pattern;
     return NSK_OK;
+}
+
+// Global pattern of the operator: returns its number of slots (0: none), the offsets in rel[8] and the number of tiles
+// stored with it (the others are exceptions with a pattern of their own).
+NSK_API int nsk_sell_host_global_pattern(void *handle, int *rel, int64_t *global_tiles)
+{
+    nsk_sell_host_s *h = static_cast<nsk_sell_host_s *>(handle);
+    if (!h->why.empty() || !h->H.global_pattern) return 0;
+    int64_t g = 0;
+    for (const SlTile &d : h->H.stiles) g += d.rp != 0;
+    if (global_tiles) *global_tiles = g;
+    for (int e = 0; e < SL_PSLOTS && rel; e++) rel[e] = h->H.grel[e];
+    return h->H.uniform_width;
 }
 
 // Expands the tiles back to CSR (row pointers, global columns, values).  Arrays sized n+1 / nnz by the caller.

@@ -208,3 +208,46 @@ def test_protocol_model_detects_missing_forward_dependencies():
     assert found >= 1
     res, _, _ = simulate(A, 3, 1, 40, 444, seed=0, pmax_bias=0)
     assert res == 0
+
+
+def _global_pattern(ptrow, indcol, coef, n_cols):
+    lib = _lib.load()
+    ptrow = np.ascontiguousarray(ptrow, np.int32)
+    indcol = np.ascontiguousarray(indcol, np.int32)
+    coef = np.ascontiguousarray(coef, np.float64)
+    h = C.c_void_p()
+    assert lib.nsk_sell_host_create(len(ptrow) - 1, n_cols, len(indcol), ptrow.ctypes.data, indcol.ctypes.data, coef.ctypes.data,
+                                    C.byref(h)) == 0
+    rel = np.zeros(8, np.int32)
+    g, nt = C.c_int64(0), C.c_int64(0)
+    w = lib.nsk_sell_host_global_pattern(h, rel.ctypes.data, C.byref(g))
+    lib.nsk_sell_host_stats(h, None, C.byref(nt), None)
+    lib.nsk_sell_host_destroy(h)
+    return w, rel, g.value, nt.value
+
+
+def test_sell_global_pattern_of_a_stencil():
+    """A 7-point operator on a box has ONE pattern for all tiles (faces only lack offsets): the kernel's straight-line path."""
+    A = matgen.laplace3d_7pt(256, 6, 5)
+    w, rel, g, nt = _global_pattern(A.ptrow, A.indcol, A.coef, A.n)
+    assert w == 7 and g == nt
+    assert list(rel[:7]) == [-256 * 6, -256, -1, 0, 1, 256, 256 * 6]
+
+
+@pytest.mark.parametrize("rank", [0, 1, 2])
+def test_sell_global_pattern_of_a_distributed_slab_has_exception_tiles(rank):
+    """The local operator of a z-slab with depth-4 ghost rings: the tiles next to a ring reference it at offsets of their own
+    and keep their own pattern (exceptions); everything else shares the global pattern; the blobs still expand to the input."""
+    from navierstokes_b200 import distributed as nd
+    nx, ny, nz = 256, 5, 12
+    plan = nd.Plan.build(3, rank, nd.slab_row_starts(nz, nx * ny, 3), 4, nd.StencilProvider(nx, ny, nz))
+    A = plan.local_csr()
+    why, out = sell(A.ptrow, A.indcol, A.coef, A.ncols)
+    assert not why
+    p2, c2, v2, _, ntiles, npat = out
+    assert np.array_equal(p2, A.ptrow) and np.array_equal(c2, A.indcol)
+    assert_bits_equal(v2, A.coef)
+    assert npat == ntiles
+    w, rel, g, nt = _global_pattern(A.ptrow, A.indcol, A.coef, A.ncols)
+    # rank 0 only has rings above its slab, stored right behind it at the stencil's own offsets: no exception needed
+    assert w == 7 and nt == ntiles and 10 <= g <= nt and (g < nt or rank == 0), (w, g, nt)

@@ -153,7 +153,8 @@ def main():
             ms = timed(ctx, lambda: dA.mpk(k, x, lv, 0), max(4, args.reps // 2))
             print(f"mpk k={k} sell chunk={chunk} stream={stream} rows={rows} tma={tma} geom={geom} cps={cps} flags={flags} pf={pf} l2={l2} w0={w0} "
                   f"launches={nl} strategy={ctx.query('last_mpk_strategy')}: {ms:8.4f} ms  B_mpk {Bk/ms/1e6:8.1f} GB/s "
-                  f"({Bk/ms/1e6/peak:5.3f})  {'OK' if ok else 'MISMATCH'}", flush=True)
+                  f"({Bk/ms/1e6/peak:5.3f})  {'OK' if ok else 'MISMATCH'}  reach={ctx.query('sell_reach')} lead={ctx.query('sell_lead')} "
+                  f"grid={ctx.query('sell_grid')} groups={ctx.query('sell_ngroups')}", flush=True)
         ctx.set_option("mpk_kernel", 0)
 
 
