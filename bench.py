@@ -366,6 +366,14 @@ def main():
         spmv_once()
     s1.record()
     spmv_ms = max_over_ranks(s0.elapsed_ms(s1) / max(args.steps, 10))
+    spmv_traffic = None
+    if tfile.exists() and world == 1:
+        try:
+            t = json.loads(tfile.read_text())
+            if t.get("spmv", {}).get("strategy") == ctx.query("last_spmv_kernel"):
+                spmv_traffic = t["spmv"]["dram_bytes_per_launch"]
+        except Exception:
+            spmv_traffic = None
 
     # ---- end to end through the public host-pointer API (pinned host buffers, copies inside) -------------
     for _ in range(2):
@@ -386,14 +394,22 @@ def main():
         "clocks": clocks,
         "e2e": {"value": equiv_total / e2e_ms / 1e6, "unit": "GB/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": 8 * n_local * world, "d2h_bytes_per_step": 8 * n_local * K_POWERS * world,
-                "note": "nsk_mpk with NSK_HOST pointers: pinned x in, k level vectors out, operator resident in HBM",
+                "note": "nsk_mpk with NSK_HOST pointers: pinned x in, k level vectors out, operator resident in HBM; PCIe-bound "
+                        "(the host-pointer call runs the k products one launch each and copies level l out on a second stream "
+                        "while level l+1 is computed, so the fused kernel is not on this path; device-resident callers such "
+                        "as nsk_cg get `value`)",
                 "checksum": checksum},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": kern_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(kern_bytes)},
         "spmv": {"ms": spmv_ms, "achieved_GBps": spmv_bytes * world / spmv_ms / 1e6,
-                 "frac_of_peak": spmv_bytes / spmv_ms / 1e6 / peak, "algorithmic_bytes": int(spmv_bytes)},
+                 "frac_of_peak": spmv_bytes / spmv_ms / 1e6 / peak, "algorithmic_bytes": int(spmv_bytes),
+                 "traffic": spmv_traffic,
+                 "traffic_GBps": (spmv_traffic / spmv_ms / 1e6) if spmv_traffic else None,
+                 "note": "frac_of_peak divides CSR bytes (12 B/nnz + vectors) by the time of a kernel that streams an "
+                         "index-free tile format (8 B/nnz + 1 B/row): above 1 by construction; traffic_GBps = ncu DRAM "
+                         "bytes of that kernel / its time is the physical rate"},
         "mpk_bytes_rate_GBps": mpk_bytes * world / ms_step / 1e6,
         "value_note": "value = k * B_spmv / t (what k separate products would have to move; above the HBM peak by construction "
                       "when the fused kernel reads the operator once). The compulsory-bytes rate of the fused kernel is "
@@ -413,115 +429,124 @@ def main():
                          f"extended by {K_POWERS} ghost planes, all {K_POWERS} level vectors, owned rows"}
     # ---- strong scaling beside the weak number: the SAME 256^3 problem split over the ranks ---------------------
     if world > 1 and args.scaling == "weak" and not args.no_strong:
-        import torch
-        from navierstokes_b200 import distributed as nd
-        sop = nd.DistStencil3D(ctx, dist, GRID, GRID, GRID, halo_depth=K_POWERS)
-        sx_host = np.sin(0.001 * (sop.row_begin + np.arange(sop.n_owned)))
-        sdx = sop.new_vector(shared=True)
-        sop.set_owned(sdx, sx_host)
-        sdlv = [sop.new_vector() for _ in range(K_POWERS)]
-        for _ in range(5):
-            sop.mpk(K_POWERS, sdx, sdlv)
-        barrier()
-        g0, g1 = ctx.event(), ctx.event()
-        g0.record()
-        for _ in range(args.steps):
-            sop.mpk(K_POWERS, sdx, sdlv)
-        g1.record()
-        s_ms = max_over_ranks(g0.elapsed_ms(g1) / args.steps)
-        # halo exchange alone (depth k), same operator
-        for _ in range(3):
-            sop.halo_exchange(sdx, K_POWERS)
-        barrier()
-        g0.record()
-        for _ in range(args.steps):
-            sop.halo_exchange(sdx, K_POWERS)
-        g1.record()
-        h_ms = max_over_ranks(g0.elapsed_ms(g1) / args.steps)
-        ctx.set_option("halo_push", 0)  # the same exchange through pack + ncclSend/ncclRecv + unpack, for comparison
-        for _ in range(3):
-            sop.halo_exchange(sdx, K_POWERS)
-        barrier()
-        g0.record()
-        for _ in range(args.steps):
-            sop.halo_exchange(sdx, K_POWERS)
-        g1.record()
-        hn_ms = max_over_ranks(g0.elapsed_ms(g1) / args.steps)
-        ctx.set_option("halo_push", 1)
-        sbad = 0
-        if not args.no_parity:
-            got = [sop.get_owned(v) for v in sdlv]
-            sbad, _ = slab_parity(matgen, GRID, GRID, GRID, sop.row_begin, sop.n_owned, K_POWERS, got,
-                                  max(1, cpu_threads() // world))
-        t = torch.tensor([1.0 if sbad == 0 else 0.0], dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        n_tot = GRID ** 3
-        nnz_tot = 7 * n_tot - 6 * GRID * GRID
-        spmv_tot = 12 * nnz_tot + 4 * (n_tot + 1) + 16 * n_tot
-        out["strong"] = {"workload": f"3D 7-point Laplacian {GRID}^3 split over {world} GPUs (z-slabs), k={K_POWERS}",
-                         "ms_per_step": s_ms, "value": K_POWERS * spmv_tot / s_ms / 1e6, "unit": "GB/s",
-                         "halo_exchange_us": h_ms * 1e3, "halo_exchange_nccl_us": hn_ms * 1e3,
-                         "efficiency_vs_n1_note": "t(1 GPU) / (N * t(N GPUs)) with t(1 GPU) = this build's N=1 ms_per_step "
-                                                  "(the driver's SCALE record); not computed here",
-                         "parity": {"ranks_ok": int(t[0].item()), "ranks": world, "bitwise": bool(int(t[0].item()) == world)}}
-        sop.close()
+        try:
+            import torch
+            from navierstokes_b200 import distributed as nd
+            sop = nd.DistStencil3D(ctx, dist, GRID, GRID, GRID, halo_depth=K_POWERS)
+            sx_host = np.sin(0.001 * (sop.row_begin + np.arange(sop.n_owned)))
+            sdx = sop.new_vector(shared=True)
+            sop.set_owned(sdx, sx_host)
+            sdlv = [sop.new_vector() for _ in range(K_POWERS)]
+            for _ in range(5):
+                sop.mpk(K_POWERS, sdx, sdlv)
+            barrier()
+            g0, g1 = ctx.event(), ctx.event()
+            g0.record()
+            for _ in range(args.steps):
+                sop.mpk(K_POWERS, sdx, sdlv)
+            g1.record()
+            s_ms = max_over_ranks(g0.elapsed_ms(g1) / args.steps)
+            # halo exchange alone (depth k), same operator
+            for _ in range(3):
+                sop.halo_exchange(sdx, K_POWERS)
+            barrier()
+            g0.record()
+            for _ in range(args.steps):
+                sop.halo_exchange(sdx, K_POWERS)
+            g1.record()
+            h_ms = max_over_ranks(g0.elapsed_ms(g1) / args.steps)
+            ctx.set_option("halo_push", 0)  # the same exchange through pack + ncclSend/ncclRecv + unpack, for comparison
+            for _ in range(3):
+                sop.halo_exchange(sdx, K_POWERS)
+            barrier()
+            g0.record()
+            for _ in range(args.steps):
+                sop.halo_exchange(sdx, K_POWERS)
+            g1.record()
+            hn_ms = max_over_ranks(g0.elapsed_ms(g1) / args.steps)
+            ctx.set_option("halo_push", 1)
+            sbad = 0
+            if not args.no_parity:
+                got = [sop.get_owned(v) for v in sdlv]
+                sbad, _ = slab_parity(matgen, GRID, GRID, GRID, sop.row_begin, sop.n_owned, K_POWERS, got,
+                                      max(1, cpu_threads() // world))
+            t = torch.tensor([1.0 if sbad == 0 else 0.0], dtype=torch.float64, device=f"cuda:{local_rank}")
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            n_tot = GRID ** 3
+            nnz_tot = 7 * n_tot - 6 * GRID * GRID
+            spmv_tot = 12 * nnz_tot + 4 * (n_tot + 1) + 16 * n_tot
+            out["strong"] = {"workload": f"3D 7-point Laplacian {GRID}^3 split over {world} GPUs (z-slabs), k={K_POWERS}",
+                             "ms_per_step": s_ms, "value": K_POWERS * spmv_tot / s_ms / 1e6, "unit": "GB/s",
+                             "halo_exchange_us": h_ms * 1e3, "halo_exchange_nccl_us": hn_ms * 1e3,
+                             "efficiency_vs_n1_note": "t(1 GPU) / (N * t(N GPUs)) with t(1 GPU) = this build's N=1 ms_per_step "
+                                                      "(the driver's SCALE record); not computed here",
+                             "parity": {"ranks_ok": int(t[0].item()), "ranks": world, "bitwise": bool(int(t[0].item()) == world)}}
+            sop.close()
+        except Exception as exc:  # a failing sub-record must not take the headline line with it
+            out["strong"] = {"error": f"{type(exc).__name__}: {exc}"[:400]}
     # ---- BASELINE config 5 on the full box: pressure-Poisson CG on 512^3 over 8 GPUs, classical and s-step (s = 4) ----
     if world > 1 and not args.no_cg and (world == 8 or args.c5):
-        import torch
-        from navierstokes_b200 import distributed as nd
-        del dlv, dx
-        nxy, planes = args.c5_grid, args.c5_grid // 8
-        t0 = time.perf_counter()
-        cop = nd.DistStencil3D(ctx, dist, nxy, nxy, planes * world, halo_depth=K_POWERS)
-        plan_s = time.perf_counter() - t0
-        gidx = cop.row_begin + np.arange(cop.n_owned)
-        x_true = np.sin(0.001 * gidx) + 0.5
-        cdx, cdb = cop.new_vector(), cop.new_vector()
-        cop.set_owned(cdx, x_true)
-        cop.spmv(cdx, cdb)
-        b_own = cop.get_owned(cdb)
-        rec = {"workload": f"7-point Laplacian {nxy}x{nxy}x{planes * world} over {world} GPUs (z-slabs), b = A x_true, x0 = 0, "
-                           f"to ||r||/||b|| <= 1e-8", "plan_s": plan_s}
-        for s_step, name in ((1, "classical"), (4, "sstep4")):
-            cop.cg(b_own, tol=1e-300, maxit=8, sstep=s_step)  # warm: plans, tile format, workspaces
-            barrier()
+        try:
+            import torch
+            from navierstokes_b200 import distributed as nd
+            del dlv, dx
+            nxy, planes = args.c5_grid, args.c5_grid // 8
             t0 = time.perf_counter()
-            xs, it, rel, ok = cop.cg(b_own, tol=1e-8, maxit=4000, sstep=s_step)
-            barrier()
-            dt = time.perf_counter() - t0
-            # true residual, recomputed from the returned solution with one more distributed product
-            cop.set_owned(cdx, xs)
+            cop = nd.DistStencil3D(ctx, dist, nxy, nxy, planes * world, halo_depth=K_POWERS)
+            plan_s = time.perf_counter() - t0
+            gidx = cop.row_begin + np.arange(cop.n_owned)
+            x_true = np.sin(0.001 * gidx) + 0.5
+            cdx, cdb = cop.new_vector(), cop.new_vector()
+            cop.set_owned(cdx, x_true)
             cop.spmv(cdx, cdb)
-            r = b_own - cop.get_owned(cdb)
-            t = torch.tensor([float(r @ r), float(b_own @ b_own), 0.0], dtype=torch.float64, device=f"cuda:{local_rank}")
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            e = torch.tensor([float(np.max(np.abs(xs - x_true)))], dtype=torch.float64, device=f"cuda:{local_rank}")
-            dist.all_reduce(e, op=dist.ReduceOp.MAX)
-            rec[name] = {"iters_to_1e-8": int(it), "converged": bool(ok), "iters_per_s": it / dt, "solve_ms": dt * 1e3,
-                         "relres_recurrence": float(rel), "true_relres": float((t[0] / t[1]).sqrt().item()),
-                         "max_abs_err_vs_x_true": float(e.item())}
-        rec["note"] = ("host wall clock around nsk_cg with the owned parts of b and x in host memory (copies included); parity of CG "
-                       "is unpinned (the reference has no CG): checked through the true residual")
-        out["cg"] = rec
-        cop.close()
+            b_own = cop.get_owned(cdb)
+            rec = {"workload": f"7-point Laplacian {nxy}x{nxy}x{planes * world} over {world} GPUs (z-slabs), b = A x_true, x0 = 0, "
+                               f"to ||r||/||b|| <= 1e-8", "plan_s": plan_s}
+            for s_step, name in ((1, "classical"), (4, "sstep4")):
+                cop.cg(b_own, tol=1e-300, maxit=8, sstep=s_step)  # warm: plans, tile format, workspaces
+                barrier()
+                t0 = time.perf_counter()
+                xs, it, rel, ok = cop.cg(b_own, tol=1e-8, maxit=4000, sstep=s_step)
+                barrier()
+                dt = time.perf_counter() - t0
+                # true residual, recomputed from the returned solution with one more distributed product
+                cop.set_owned(cdx, xs)
+                cop.spmv(cdx, cdb)
+                r = b_own - cop.get_owned(cdb)
+                t = torch.tensor([float(r @ r), float(b_own @ b_own), 0.0], dtype=torch.float64, device=f"cuda:{local_rank}")
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                e = torch.tensor([float(np.max(np.abs(xs - x_true)))], dtype=torch.float64, device=f"cuda:{local_rank}")
+                dist.all_reduce(e, op=dist.ReduceOp.MAX)
+                rec[name] = {"iters_to_1e-8": int(it), "converged": bool(ok), "iters_per_s": it / dt, "solve_ms": dt * 1e3,
+                             "relres_recurrence": float(rel), "true_relres": float((t[0] / t[1]).sqrt().item()),
+                             "max_abs_err_vs_x_true": float(e.item())}
+            rec["note"] = ("host wall clock around nsk_cg with the owned parts of b and x in host memory (copies included); parity of CG "
+                           "is unpinned (the reference has no CG): checked through the true residual")
+            out["cg"] = rec
+            cop.close()
+        except Exception as exc:  # a failing sub-record must not take the headline line with it
+            out["cg"] = {"error": f"{type(exc).__name__}: {exc}"[:400]}
     # ---- Poisson CG iterations per second on the same operator (BASELINE metric, second half) ------------------
     if world == 1 and not args.no_cg:
-        b = ctx.empty(A.n)
-        dA.spmv(dx, b)
-        xs = ctx.empty(A.n)
-        cg = {}
-        for s_step, name in ((1, "classical"), (4, "sstep4")):
-            nit = 48
-            dA.cg(b, xs, tol=1e-300, maxit=nit, sstep=s_step)  # warm: plans, workspace
-            ctx.sync()
-            t0 = time.perf_counter()
-            _, it, _, _ = dA.cg(b, xs, tol=1e-300, maxit=nit, sstep=s_step)
-            ctx.sync()
-            cg[name + "_iters_per_s"] = it / (time.perf_counter() - t0)
-        cg["note"] = ("48 iterations each on the 256^3 operator, device-resident b and x, host wall clock around the whole "
-                      "nsk_cg call (includes its workspace allocation)")
-        out["cg"] = cg
-        del b, xs
+        try:
+            b = ctx.empty(A.n)
+            dA.spmv(dx, b)
+            xs = ctx.empty(A.n)
+            cg = {}
+            for s_step, name in ((1, "classical"), (4, "sstep4")):
+                nit = 48
+                dA.cg(b, xs, tol=1e-300, maxit=nit, sstep=s_step)  # warm: plans, workspace
+                ctx.sync()
+                t0 = time.perf_counter()
+                _, it, _, _ = dA.cg(b, xs, tol=1e-300, maxit=nit, sstep=s_step)
+                ctx.sync()
+                cg[name + "_iters_per_s"] = it / (time.perf_counter() - t0)
+            cg["note"] = ("48 iterations each on the 256^3 operator, device-resident b and x, host wall clock around the whole "
+                          "nsk_cg call (includes its workspace allocation)")
+            out["cg"] = cg
+            del b, xs
+        except Exception as exc:  # a failing sub-record must not take the headline line with it
+            out["cg"] = {"error": f"{type(exc).__name__}: {exc}"[:400]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         T = cpu_threads()
         ref = CpuReference(A, T)

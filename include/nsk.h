@@ -265,7 +265,12 @@ int nsk_spmm_bcsr4(nsk_bcsr4_t B, int s, const double *X, int64_t ldx, double *Y
 int nsk_krylov_basis_bcsr4(nsk_bcsr4_t B, int s, const double *v0, double *V, int64_t ldv, nsk_where where);
 
 /* ---- vectors (device-side dot / axpy family used by the Krylov solvers) ---------------------- */
-/* result pointers are HOST doubles; the call returns after the value has landed. */
+/* result pointers are HOST doubles; the call returns after the value has landed.
+ * COLLECTIVE SEMANTICS: once a communicator is attached to the context (nsk_comm_init with nranks > 1) the vectors are
+ * taken as the owned parts of distributed vectors and nsk_dot, nsk_norm2, nsk_rel_error, nsk_orthogonalize,
+ * nsk_orthonormalize_against_basis and nsk_gram SUM THEIR REDUCTIONS OVER ALL RANKS (in-stream ncclAllReduce): every
+ * rank must make the same call, a call on one rank alone blocks.  For a rank-local result (a check on one rank, a
+ * local norm) set nsk_ctx_set_option(ctx, "local_reductions", 1) around the call; nsk_cg always reduces globally. */
 int nsk_dot(nsk_ctx_t ctx, int64_t n, const double *a, const double *b, double *result,
             nsk_where where);
 int nsk_norm2(nsk_ctx_t ctx, int64_t n, const double *x, double *result, nsk_where where);
@@ -314,9 +319,12 @@ int nsk_comm_allreduce_sum(nsk_ctx_t ctx, double *dbuf, int count); /* in place,
  * Planning is host-only (no GPU, no communicator) and driven by the host layer, which supplies the
  * matrix rows of each ring (from a generator, a file, or by fetching them from their owners):
  *
- *     nsk_plan_create(...)
- *     while (nsk_plan_frontier(plan, &cnt, &rows), cnt > 0)  nsk_plan_add_rows(plan, cnt, ptr, cols, vals);
- *     nsk_plan_finalize(plan)
+ *     nsk_plan_create(..., depth, &plan)
+ *     for (stage = 0; stage < depth; stage++) {              // exactly `depth` rounds: owned rows, ring 1 .. ring depth-1
+ *         nsk_plan_frontier(plan, &cnt, &rows);              // cnt may be 0 (a rank whose ring is empty): still call
+ *         nsk_plan_add_rows(plan, cnt, ptr, cols, vals);     // add_rows (NULL arrays are fine when cnt == 0)
+ *     }
+ *     nsk_plan_finalize(plan)                                // fails unless all `depth` rounds were supplied
  *     for every peer p: nsk_plan_requests(plan, p, ...)  -> ship the id list to p (any transport)
  *                       nsk_plan_add_send(plan, p, ...)  <- the list p shipped to us
  *     nsk_csr_create_dist(ctx, plan, &A)
@@ -325,8 +333,9 @@ typedef struct nsk_plan_s *nsk_plan_t;
 
 int nsk_plan_create(int nranks, int rank, const int *row_starts /* nranks+1 */, int depth, nsk_plan_t *plan);
 int nsk_plan_destroy(nsk_plan_t plan);
-/* Global ids (ascending) of the rows whose matrix rows must be supplied next; *count == 0 when done.
- * First call: the owned rows; then ring 1, ..., ring depth-1. */
+/* Global ids (ascending) of the rows whose matrix rows must be supplied next.  First call: the owned rows; then
+ * ring 1, ..., ring depth-1.  *count == 0 means "this ring is empty" before the last round (do not stop: supply the
+ * empty round) and "all rounds supplied" after it. */
 int nsk_plan_frontier(nsk_plan_t plan, int *count, const int **global_rows);
 /* Rows of the current frontier, in frontier order: ptr[count+1], global column ids, values. */
 int nsk_plan_add_rows(nsk_plan_t plan, int count, const int *ptr, const int *cols_global, const double *vals);

@@ -144,6 +144,7 @@ NSK_API int nsk_ctx_set_option(nsk_ctx_t c, const char *name, int64_t v)
     else if (!strcmp(name, "stream_exact_kind")) c->opt.stream_exact_kind = v;
     else if (!strcmp(name, "pipe_interleave")) c->opt.pipe_interleave = v;
     else if (!strcmp(name, "halo_push")) c->opt.halo_push = v;
+    else if (!strcmp(name, "local_reductions")) c->opt.local_reductions = v;
     else if (!strcmp(name, "bcsr_batch")) c->opt.bcsr_batch = v;
     else if (!strcmp(name, "sell_chunk")) c->opt.sell_chunk = v;
     else if (!strcmp(name, "sell_geom")) c->opt.sell_geom = v;

@@ -239,6 +239,13 @@ struct Staged {
     }
 };
 const int SLOT_PUBLIC = 0;  // scalar slots 0..7 belong to the public one-shot calls
+// The public reductions sum over the communicator's ranks (x, y are the owned parts of distributed vectors) unless the
+// caller asked for rank-local results (option local_reductions: a check on one rank only must not enter a collective).
+inline int vec_allreduce(nsk_ctx_t ctx, int slot0, int count)
+{
+    if (ctx->opt.local_reductions) return NSK_OK;
+    return nsk_comm_allreduce_slots(ctx, slot0, count);
+}
 }  // namespace
 
 NSK_API int nsk_dot(nsk_ctx_t ctx, int64_t n, const double *a, const double *b, double *result, nsk_where where)
@@ -249,7 +256,7 @@ NSK_API int nsk_dot(nsk_ctx_t ctx, int64_t n, const double *a, const double *b, 
     const double *da = S.in(0, a, n, where), *db = (b == a) ? da : S.in(1, b, n, where);
     NSK_TRY(S.status);
     NSK_TRY(nsk_launch_dot(ctx, n, da, db, SLOT_PUBLIC));
-    NSK_TRY(nsk_comm_allreduce_slots(ctx, SLOT_PUBLIC, 1));
+    NSK_TRY(vec_allreduce(ctx, SLOT_PUBLIC, 1));
     return nsk_read_scalars(ctx, SLOT_PUBLIC, 1, result);
 }
 
@@ -271,7 +278,7 @@ NSK_API int nsk_rel_error(nsk_ctx_t ctx, int64_t n, const double *ref, const dou
     NSK_TRY(S.status);
     NSK_TRY(nsk_launch_diff_norm2sq(ctx, n, da, db, SLOT_PUBLIC));
     NSK_TRY(nsk_launch_dot(ctx, n, da, da, SLOT_PUBLIC + 1));
-    NSK_TRY(nsk_comm_allreduce_slots(ctx, SLOT_PUBLIC, 2));
+    NSK_TRY(vec_allreduce(ctx, SLOT_PUBLIC, 2));
     double v[2];
     NSK_TRY(nsk_read_scalars(ctx, SLOT_PUBLIC, 2, v));
     *result = sqrt(v[0]) / sqrt(v[1]);
@@ -303,7 +310,7 @@ NSK_API int nsk_orthogonalize(nsk_ctx_t ctx, int64_t n, const double *x, double 
     double *dy = const_cast<double *>(S.in(1, y, n, where));
     NSK_TRY(S.status);
     NSK_TRY(nsk_launch_dot(ctx, n, dx, dy, SLOT_PUBLIC));
-    NSK_TRY(nsk_comm_allreduce_slots(ctx, SLOT_PUBLIC, 1));
+    NSK_TRY(vec_allreduce(ctx, SLOT_PUBLIC, 1));
     // y += (-alpha * beta) * x with beta read on the device: no host round trip between dot and axpy
     NSK_TRY(nsk_launch_axpy_dev(ctx, n, ctx->d_scalars + SLOT_PUBLIC, -alpha, dx, dy));
     if (where == NSK_HOST)
@@ -342,11 +349,11 @@ NSK_API int nsk_orthonormalize_against_basis(nsk_ctx_t ctx, int64_t n, int m, co
             dx = dbuf;
         }
         NSK_TRY(nsk_launch_dot(ctx, n, dy, dx, SLOT_PUBLIC));
-        NSK_TRY(nsk_comm_allreduce_slots(ctx, SLOT_PUBLIC, 1));
+        NSK_TRY(vec_allreduce(ctx, SLOT_PUBLIC, 1));
         NSK_TRY(nsk_launch_axpy_dev(ctx, n, ctx->d_scalars + SLOT_PUBLIC, -1.0, dx, dy));  // y -= <y,x> x
     }
     NSK_TRY(nsk_launch_dot(ctx, n, dy, dy, SLOT_PUBLIC));
-    NSK_TRY(nsk_comm_allreduce_slots(ctx, SLOT_PUBLIC, 1));
+    NSK_TRY(vec_allreduce(ctx, SLOT_PUBLIC, 1));
     if (where == NSK_HOST) NSK_CUDA(ctx, cudaMemcpyAsync(y, dy, nb, cudaMemcpyDeviceToHost, ctx->stream));
     double yy = 0.0;
     NSK_TRY(nsk_read_scalars(ctx, SLOT_PUBLIC, 1, &yy));  // also completes the copy above
@@ -373,7 +380,7 @@ NSK_API int nsk_gram(nsk_ctx_t ctx, int64_t n, int m, const double *const *V, do
     const int ns = m * (m + 1) / 2;
     const int slot0 = 64;
     NSK_TRY(nsk_launch_gram(ctx, n, m, dv, slot0));
-    NSK_TRY(nsk_comm_allreduce_slots(ctx, slot0, ns));
+    NSK_TRY(vec_allreduce(ctx, slot0, ns));
     double tri[45];
     NSK_TRY(nsk_read_scalars(ctx, slot0, ns, tri));
     int s = 0;

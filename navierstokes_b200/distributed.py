@@ -88,11 +88,9 @@ class Plan:
     @classmethod
     def build(cls, nranks, rank, row_starts, depth, provider) -> "Plan":
         p = cls(nranks, rank, row_starts, depth)
-        while True:
+        for _ in range(depth):  # exactly `depth` rounds (owned rows, ring 1 .. ring depth-1); a ring may be empty
             cnt, rows = C.c_int(), C.c_void_p()
             _lib.check(p.lib.nsk_plan_frontier(p.h, C.byref(cnt), C.byref(rows)))
-            if cnt.value == 0 and p._stage_done():
-                break
             gids = np.ctypeslib.as_array(C.cast(rows, C.POINTER(C.c_int)), shape=(cnt.value,)).copy() if cnt.value \
                 else np.zeros(0, np.int32)
             ptr, cols, vals = provider.rows(gids)
@@ -101,13 +99,9 @@ class Plan:
             vals = np.ascontiguousarray(vals, np.float64)
             _lib.check(p.lib.nsk_plan_add_rows(p.h, cnt.value, C.c_void_p(_ptr(ptr)), C.c_void_p(_ptr(cols)),
                                               C.c_void_p(_ptr(vals))))
-            p._stages = getattr(p, "_stages", 0) + 1
         _lib.check(p.lib.nsk_plan_finalize(p.h))
         p._read_sizes()
         return p
-
-    def _stage_done(self):
-        return getattr(self, "_stages", 0) >= self.depth
 
     def _read_sizes(self):
         no, nr, nc, nnz = C.c_int(), C.c_int(), C.c_int(), C.c_int64()

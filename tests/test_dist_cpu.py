@@ -106,3 +106,29 @@ def test_plan_argument_errors():
     assert lib.nsk_plan_create(2, 0, C.c_void_p(rs.ctypes.data), 2, C.byref(h)) == 0
     assert lib.nsk_plan_finalize(h) == -1  # rows not supplied yet
     lib.nsk_plan_destroy(h)
+
+
+def test_plan_loop_with_empty_rings():
+    """The loop nsk.h documents: exactly `depth` frontier / add_rows rounds, empty rings included (a rank of a
+    block-diagonal operator has no ghosts at all; stopping at the first empty frontier would leave the plan unfinalizable)."""
+    from navierstokes_b200 import build, matgen, distributed as nd
+    build.build()
+    n = 12
+    ptr = np.arange(n + 1, dtype=np.int32)
+    A = matgen.Csr(n=n, ptrow=ptr, indcol=np.arange(n, dtype=np.int32), coef=np.full(n, 2.0), ncols=n)  # diagonal
+    rs = np.array([0, 5, 12], np.int32)
+    for rank in range(2):
+        plan = nd.Plan.build(2, rank, rs, 3, nd.GlobalCsrProvider(A))
+        assert plan.n_owned == rs[rank + 1] - rs[rank] == plan.n_rows_local == plan.n_cols_local
+        assert len(plan.ghosts()) == 0 and list(plan.level_rows) == [plan.n_owned] * 3
+        plan.close()
+    # one coupling only: rank 0's last row reads rank 1's first -> ring 1 has one entry, ring 2 (depth 3) is empty on rank 0
+    lens = np.ones(n, np.int64)
+    lens[4] = 2
+    ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    col = np.concatenate([np.arange(4), [4, 5], np.arange(5, 12)]).astype(np.int32)
+    B = matgen.Csr(n=n, ptrow=ptr, indcol=col, coef=np.ones(len(col)), ncols=n)
+    assert B.ptrow[-1] == len(col)
+    plan = nd.Plan.build(2, 0, rs, 3, nd.GlobalCsrProvider(B))
+    assert list(plan.ghosts()) == [5] and plan.n_rows_local == 6 and plan.n_cols_local == 6
+    plan.close()
