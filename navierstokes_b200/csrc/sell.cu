@@ -990,7 +990,7 @@ __device__ __forceinline__ void sl_consume_gpat(const SlParams &P, const SlCta &
     ph_io = ph;
 }
 
-template <int NV, int W, int NS, int MINB>
+template <int NV, int W, int NS, int MINB, int EB = 8>
 __global__ void __launch_bounds__(SLT_THREADS, MINB) sell_tma_kernel(const SlParams P)
 {
     static_assert(W >= 0 && W <= SL_PSLOTS, "pattern width (0: tiles with explicit columns)");
@@ -1308,12 +1308,12 @@ __global__ void __launch_bounds__(SLT_THREADS, MINB) sell_tma_kernel(const SlPar
                 const unsigned char *stg = stages + (size_t)st * STAGE;
                 const int len = warp * 32 < rp ? (int)reinterpret_cast<const unsigned short *>(stg)[t] : 0;
                 const int *cs = reinterpret_cast<const int *>(stg + sl_round_up(2 * rp, 128)) + (size_t)soff * 32 + lane;
-                for (int e0 = 0; e0 < mine; e0 += 8) {
-                    double a[8], xv[NV][8];
+                for (int e0 = 0; e0 < mine; e0 += EB) {
+                    double a[EB], xv[NV][EB];
                     // every load unconditional (each destination register defined once): a batch that runs past the
                     // slice's last slot re-reads that slot; padding entries carry a valid column (0); neither is used
 #pragma unroll
-                    for (int u = 0; u < 8; u++) {
+                    for (int u = 0; u < EB; u++) {
                         const int e = min(e0 + u, mine - 1);
                         const int cc = cs[e * 32];
                         a[u] = sl_ld_coef(vg + (size_t)e * 32, pol);
@@ -1321,7 +1321,7 @@ __global__ void __launch_bounds__(SLT_THREADS, MINB) sell_tma_kernel(const SlPar
                         if (NV == 2) xv[NV - 1][u] = sl_ld_x(src2 + cc);
                     }
 #pragma unroll
-                    for (int u = 0; u < 8; u++)
+                    for (int u = 0; u < EB; u++)
                         if (e0 + u < len) {
                             if (muladd) {
                                 acc0 = row_op<true>(a[u], xv[0][u], acc0);
@@ -1408,7 +1408,12 @@ static SlLaunch sl_lookup_tma(int nv, int w, int ns, int *smem)
     L.threads = SLT_THREADS;
     L.launch_regs = 0;  // no register hand-over in this kernel
     if (w == 0) {
-        L.fn = nv == 2 ? sell_tma_kernel<2, 0, 3, 2> : sell_tma_kernel<1, 0, 3, 3>;
+        // entries of a row whose loads are issued together (EB): 8 (three CTAs per SM) or, option sell_tma = 16 / 17,
+        // 16 with two / three CTAs per SM (a 15-entry FEM row then costs one memory round trip per level instead of two)
+        if (nv == 2) L.fn = sell_tma_kernel<2, 0, 3, 2>;
+        else if (ns == 16) L.fn = sell_tma_kernel<1, 0, 3, 2, 16>;
+        else if (ns == 17) L.fn = sell_tma_kernel<1, 0, 3, 3, 16>;
+        else L.fn = sell_tma_kernel<1, 0, 3, 3>;
         *smem = SL_EXPLICIT_STAGE * 3;
         return L;
     }

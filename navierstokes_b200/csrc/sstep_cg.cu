@@ -54,9 +54,15 @@ __global__ void scg_inner_kernel(double *scal, int s, double tol2, int max_iters
     rc[s + 1] = 1.0;
     double rr = G[s + 1][s + 1];
     int iters = (int)scal[SG_ITERS];
-    double done = scal[SG_DONE], brk = 0.0;
+    // done and brk are sticky: an outer step launched after convergence (or a breakdown) -- the host reads the status only
+    // every other outer step -- leaves x' = 0, r' = e_r, p' = e_p, i.e. the update is the identity
+    double done = scal[SG_DONE], brk = scal[SG_BREAK];
     const double bb = scal[SG_BB];
-    for (int j = 0; j < s && done == 0.0 && iters < max_iters; j++) {
+    if (done != 0.0 || brk != 0.0) {  // latched: identity coordinates, status and <r, r> stay as they were
+        for (int i = 0; i < m; i++) { scal[SG_XC + i] = xc[i]; scal[SG_RC + i] = rc[i]; scal[SG_PC + i] = pc[i]; }
+        return;
+    }
+    for (int j = 0; j < s && done == 0.0 && brk == 0.0 && iters < max_iters; j++) {
         // w = B p': shift inside the P block (0..s) and inside the R block (s+1..2s)
         for (int i = 0; i < m; i++) w[i] = 0.0;
         for (int i = 0; i < s; i++) w[i + 1] = pc[i];
@@ -188,6 +194,10 @@ int nsk_scg_device(nsk_csr_t A, const double *d_b, double *d_x, double tol, int 
     int done_iters = 0;
     bool converged = false, broke = false;
     double rr = bb;
+    // The status (iterations, converged, breakdown) is latched on the device; the host reads it every SCG_POLL outer
+    // steps (and whenever the iteration cap could have been reached), so the stream is drained once per 2s iterations.
+    constexpr int SCG_POLL = 2;
+    int since = 0;
     while (done_iters < maxit && !converged && !broke) {
         SCG_TRY(nsk_mpk_device2(A, s, p, lvP.data(), r, lvR.data(), NSK_EXACT_FMA));
         SCG_TRY(nsk_launch_gram(ctx, n, m, gram_ptrs, SG_G));
@@ -200,7 +210,9 @@ int nsk_scg_device(nsk_csr_t A, const double *d_b, double *d_x, double tol, int 
         }
         ctx->launches += 2;
         SCG_CUDA(cudaGetLastError());
-        SCG_TRY(nsk_read_scalars(ctx, SG_RR, 5, h));  // one small D2H + sync per s iterations
+        if (++since < SCG_POLL && done_iters + (since + 1) * s <= maxit) continue;
+        since = 0;
+        SCG_TRY(nsk_read_scalars(ctx, SG_RR, 5, h));  // one small D2H + sync per SCG_POLL * s iterations
         rr = h[0];
         converged = h[SG_DONE - SG_RR] != 0.0;
         done_iters = (int)h[SG_ITERS - SG_RR];
