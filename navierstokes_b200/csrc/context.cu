@@ -145,6 +145,9 @@ NSK_API int nsk_ctx_set_option(nsk_ctx_t c, const char *name, int64_t v)
     else if (!strcmp(name, "pipe_interleave")) c->opt.pipe_interleave = v;
     else if (!strcmp(name, "halo_push")) c->opt.halo_push = v;
     else if (!strcmp(name, "local_reductions")) c->opt.local_reductions = v;
+    else if (!strcmp(name, "gram_wide")) c->opt.gram_wide = v;
+    else if (!strcmp(name, "mpk_auto_explicit")) c->opt.mpk_auto_explicit = v;
+    else if (!strcmp(name, "scg_update_wide")) c->opt.scg_update_wide = v;
     else if (!strcmp(name, "bcsr_batch")) c->opt.bcsr_batch = v;
     else if (!strcmp(name, "sell_chunk")) c->opt.sell_chunk = v;
     else if (!strcmp(name, "sell_geom")) c->opt.sell_geom = v;

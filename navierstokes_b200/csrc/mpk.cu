@@ -50,7 +50,7 @@ int nsk_mpk_local(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
     // coefficients, no per-entry index), else the packed one when the operator packs, else k products
     if (automatic) {
         sel = 4;
-        if (k > 1 && nsk_sell_uniform(A)) sel = 5;
+        if (k > 1 && (nsk_sell_uniform(A) || (ctx->opt.mpk_auto_explicit > 0 && nsk_sell_explicit_staged(A)))) sel = 5;
         // Unstructured operators (explicit columns, x gathered entry by entry) stay with k products: measured on the
         // RCM-ordered tetrahedral P1 Laplacian (8.1 M rows, 15 per row), the product already runs at the HBM copy rate
         // (0.237 ms, 6.8 TB/s) and both it and the fused sliced-ELL pipeline (mpk_kernel = 5: 2.43 ms for k = 8 against

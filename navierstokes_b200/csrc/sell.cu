@@ -1408,12 +1408,14 @@ static SlLaunch sl_lookup_tma(int nv, int w, int ns, int *smem)
     L.threads = SLT_THREADS;
     L.launch_regs = 0;  // no register hand-over in this kernel
     if (w == 0) {
-        // entries of a row whose loads are issued together (EB): 8 (three CTAs per SM) or, option sell_tma = 16 / 17,
-        // 16 with two / three CTAs per SM (a 15-entry FEM row then costs one memory round trip per level instead of two)
+        // entries of a row whose loads are issued together (EB): 16 with two CTAs per SM (a 15-entry FEM row costs one
+        // memory round trip per level instead of two); option sell_tma = 8: 8 with three CTAs, 17: 16 with three CTAs
+        // measured on the RCM-ordered tet-P1 operator (8.1 M rows, k = 4): 16 / two CTAs 0.80 ms, 8 / three CTAs 1.10 ms,
+        // 16 / three CTAs (spills) 2.09 ms, four products 0.95 ms (profiles/r02_c4_variants.txt) -> 16 / two is the default
         if (nv == 2) L.fn = sell_tma_kernel<2, 0, 3, 2>;
-        else if (ns == 16) L.fn = sell_tma_kernel<1, 0, 3, 2, 16>;
+        else if (ns == 8) L.fn = sell_tma_kernel<1, 0, 3, 3>;
         else if (ns == 17) L.fn = sell_tma_kernel<1, 0, 3, 3, 16>;
-        else L.fn = sell_tma_kernel<1, 0, 3, 3>;
+        else L.fn = sell_tma_kernel<1, 0, 3, 2, 16>;
         *smem = SL_EXPLICIT_STAGE * 3;
         return L;
     }

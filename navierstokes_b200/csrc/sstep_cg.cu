@@ -129,6 +129,63 @@ __global__ void __launch_bounds__(256) scg_update_kernel(int64_t n, ScgPtrs V, d
     }
 }
 
+// Step 4, wide form: the 3 M coordinates live in shared memory (read back as broadcast LDS operands) instead of 6 M
+// registers, and a thread updates two consecutive elements with 128-bit accesses -- 4 x the bytes in flight per SM of the
+// kernel above (98 registers, 80 bytes per thread: 0.61 of the HBM copy peak, profiles/r02_cg_launches.txt).  Per element
+// the three fma chains run in the same order, so the results are bit-identical to scg_update_kernel.
+template <int M>
+__global__ void __launch_bounds__(256) scg_update_wide_kernel(int64_t n, ScgPtrs V, double *__restrict__ x, double *r, double *p,
+                                                              const double *__restrict__ scal)
+{
+    __shared__ double c[3][M];
+    if (threadIdx.x < M) {
+        c[0][threadIdx.x] = scal[SG_XC + threadIdx.x];
+        c[1][threadIdx.x] = scal[SG_RC + threadIdx.x];
+        c[2][threadIdx.x] = scal[SG_PC + threadIdx.x];
+    }
+    __syncthreads();
+    const volatile double *cv = &c[0][0];
+    const int64_t n2 = n >> 1;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+        double2 v[M];
+#pragma unroll
+        for (int a = 0; a < M; a++) v[a] = reinterpret_cast<const double2 *>(V.v[a])[i];
+        double2 xs = reinterpret_cast<const double2 *>(x)[i], rs = make_double2(0.0, 0.0), ps = make_double2(0.0, 0.0);
+        asm volatile("" ::: "memory");  // all M + 1 loads are issued before the first coordinate is read
+#pragma unroll
+        for (int a = 0; a < M; a++) {
+            // volatile: re-read per trip (broadcast LDS) -- hoisted out of the loop the 27 coordinates cost 54 registers
+            const double xa = cv[a], ra = cv[M + a], pa = cv[2 * M + a];
+            xs.x = __fma_rn(xa, v[a].x, xs.x);
+            xs.y = __fma_rn(xa, v[a].y, xs.y);
+            rs.x = __fma_rn(ra, v[a].x, rs.x);
+            rs.y = __fma_rn(ra, v[a].y, rs.y);
+            ps.x = __fma_rn(pa, v[a].x, ps.x);
+            ps.y = __fma_rn(pa, v[a].y, ps.y);
+        }
+        reinterpret_cast<double2 *>(x)[i] = xs;
+        reinterpret_cast<double2 *>(r)[i] = rs;
+        reinterpret_cast<double2 *>(p)[i] = ps;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int64_t i = n - 1;
+        double v[M];
+#pragma unroll
+        for (int a = 0; a < M; a++) v[a] = V.v[a][i];
+        double xs = x[i], rs = 0.0, ps = 0.0;
+#pragma unroll
+        for (int a = 0; a < M; a++) {
+            xs = __fma_rn(c[0][a], v[a], xs);
+            rs = __fma_rn(c[1][a], v[a], rs);
+            ps = __fma_rn(c[2][a], v[a], ps);
+        }
+        x[i] = xs;
+        r[i] = rs;
+        p[i] = ps;
+    }
+}
+
 int nsk_scg_device(nsk_csr_t A, const double *d_b, double *d_x, double tol, int maxit, int s, int *iters,
                    double *relres)
 {
@@ -191,6 +248,9 @@ int nsk_scg_device(nsk_csr_t A, const double *d_b, double *d_x, double tol, int 
     int64_t want = ((int64_t)n + 511) / 512;
     const int64_t cap = (int64_t)ctx->prop.multiProcessorCount * 8;
     const int grid = (int)(want < 1 ? 1 : (want < cap ? want : cap));
+    // 128-bit form of the block update: every vector 16-byte aligned (the workspace is; x is the caller's)
+    bool wide = ctx->opt.scg_update_wide >= 0 && (reinterpret_cast<uintptr_t>(d_x) & 15) == 0;
+    for (int i = 0; i < m; i++) wide = wide && (reinterpret_cast<uintptr_t>(V.v[i]) & 15) == 0;
     int done_iters = 0;
     bool converged = false, broke = false;
     double rr = bb;
@@ -203,10 +263,18 @@ int nsk_scg_device(nsk_csr_t A, const double *d_b, double *d_x, double tol, int 
         SCG_TRY(nsk_launch_gram(ctx, n, m, gram_ptrs, SG_G));
         SCG_TRY(nsk_comm_allreduce_slots(ctx, SG_G, m * (m + 1) / 2));
         scg_inner_kernel<<<1, 1, 0, ctx->stream>>>(scal, s, tol2, maxit);
-        switch (m) {
-            case 5: scg_update_kernel<5><<<grid, 256, 0, ctx->stream>>>(n, V, d_x, r, p, scal); break;
-            case 7: scg_update_kernel<7><<<grid, 256, 0, ctx->stream>>>(n, V, d_x, r, p, scal); break;
-            default: scg_update_kernel<9><<<grid, 256, 0, ctx->stream>>>(n, V, d_x, r, p, scal); break;
+        if (wide) {
+            switch (m) {
+                case 5: scg_update_wide_kernel<5><<<grid, 256, 0, ctx->stream>>>(n, V, d_x, r, p, scal); break;
+                case 7: scg_update_wide_kernel<7><<<grid, 256, 0, ctx->stream>>>(n, V, d_x, r, p, scal); break;
+                default: scg_update_wide_kernel<9><<<grid, 256, 0, ctx->stream>>>(n, V, d_x, r, p, scal); break;
+            }
+        } else {
+            switch (m) {
+                case 5: scg_update_kernel<5><<<grid, 256, 0, ctx->stream>>>(n, V, d_x, r, p, scal); break;
+                case 7: scg_update_kernel<7><<<grid, 256, 0, ctx->stream>>>(n, V, d_x, r, p, scal); break;
+                default: scg_update_kernel<9><<<grid, 256, 0, ctx->stream>>>(n, V, d_x, r, p, scal); break;
+            }
         }
         ctx->launches += 2;
         SCG_CUDA(cudaGetLastError());

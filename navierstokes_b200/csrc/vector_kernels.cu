@@ -155,6 +155,75 @@ __global__ void __launch_bounds__(VEC_THREADS) gram_kernel(int64_t n, GramPtrs P
     grid_finish<NS>(acc, partials, ticket, out);
 }
 
+// Wide Gram pass for the s-step block (M = 7 or 9 vectors, 28 / 45 sums): the accumulators alone take 2 NS registers per
+// thread, so the register file -- not the grid -- decides how many bytes an SM has in flight.  gram_kernel<9> (one element
+// per thread and trip, 128 registers, 512 threads per SM -> 36 KB in flight per SM) reaches 0.59 of the HBM copy peak
+// (profiles/r02_cg_launches.txt); here a thread keeps 2 x E2 elements of every vector in flight (E2 128-bit loads per
+// vector, all issued before the first fma) and one CTA of GW_THREADS threads owns the SM's registers.
+// Needs 16-byte aligned vectors; the tail (n odd) is one scalar element.  Summation order differs from gram_kernel (as it
+// does between any two grids): the Gram block is compared with tolerances, like every tree-summed reduction here.
+constexpr int GW_THREADS = 384;
+template <int M, int E2>
+__global__ void __launch_bounds__(GW_THREADS, 1) gram_wide_kernel(int64_t n, GramPtrs P, double *partials, unsigned int *ticket,
+                                                                  double *out)
+{
+    constexpr int NS = M * (M + 1) / 2;
+    constexpr int NW = GW_THREADS / 32;
+    __shared__ double sh[NS * NW];
+    double acc[NS];
+#pragma unroll
+    for (int s = 0; s < NS; s++) acc[s] = 0.0;
+    const int64_t n2 = n >> 1;  // double2 elements
+    const int64_t chunk = (int64_t)GW_THREADS * E2;
+    const int64_t stride = (int64_t)gridDim.x * chunk;
+    for (int64_t base = (int64_t)blockIdx.x * chunk + threadIdx.x; base < n2; base += stride) {
+        double2 v[E2][M];
+#pragma unroll
+        for (int e = 0; e < E2; e++) {
+            const int64_t i = base + (int64_t)e * GW_THREADS;
+#pragma unroll
+            for (int a = 0; a < M; a++)
+                v[e][a] = i < n2 ? reinterpret_cast<const double2 *>(P.v[a])[i] : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int e = 0; e < E2; e++) {
+            int s = 0;
+#pragma unroll
+            for (int a = 0; a < M; a++)
+#pragma unroll
+                for (int b = a; b < M; b++) {
+                    acc[s] = __fma_rn(v[e][a].x, v[e][b].x, acc[s]);
+                    acc[s] = __fma_rn(v[e][a].y, v[e][b].y, acc[s]);
+                    s++;
+                }
+        }
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        int s = 0;
+#pragma unroll
+        for (int a = 0; a < M; a++)
+#pragma unroll
+            for (int b = a; b < M; b++) { acc[s] = __fma_rn(P.v[a][n - 1], P.v[b][n - 1], acc[s]); s++; }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[s] += __shfl_xor_sync(0xffffffffu, acc[s], o);
+        if (lane == 0) sh[s * NW + warp] = acc[s];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            double t = 0.0;
+            for (int w = 0; w < NW; w++) t += sh[s * NW + w];
+            acc[s] = t;
+        }
+    }
+    grid_finish<NS>(acc, partials, ticket, out);
+}
+
 // ---- launchers --------------------------------------------------------------------------------
 int nsk_launch_dot(nsk_ctx_t ctx, int64_t n, const double *a, const double *b, int slot)
 {
@@ -199,6 +268,17 @@ int nsk_launch_gram(nsk_ctx_t ctx, int64_t n, int m, const double *const *vptrs,
     for (int i = 0; i < 12; i++) P.v[i] = i < m ? vptrs[i] : nullptr;
     int grid = vec_grid(ctx, n * 4);
     double *out = ctx->d_scalars + slot0;
+    // s-step blocks on a long vector: the wide kernel (one CTA per SM, 4 elements of every vector in flight per thread)
+    bool aligned = true;
+    for (int i = 0; i < m; i++) aligned = aligned && (reinterpret_cast<uintptr_t>(vptrs[i]) & 15) == 0;
+    if ((m == 9 || m == 7) && aligned && n >= (int64_t)1 << 16 && ctx->opt.gram_wide >= 0) {
+        const int g = ctx->prop.multiProcessorCount;
+        if (m == 9) gram_wide_kernel<9, 2><<<g, GW_THREADS, 0, ctx->stream>>>(n, P, ctx->d_partials, ctx->d_ticket, out);
+        else gram_wide_kernel<7, 2><<<g, GW_THREADS, 0, ctx->stream>>>(n, P, ctx->d_partials, ctx->d_ticket, out);
+        ctx->launches++;
+        NSK_CUDA(ctx, cudaGetLastError());
+        return NSK_OK;
+    }
 #define GRAM_CASE(M) case M: gram_kernel<M><<<grid, VEC_THREADS, 0, ctx->stream>>>(n, P, ctx->d_partials, ctx->d_ticket, out); break;
     switch (m) {
         GRAM_CASE(1) GRAM_CASE(2) GRAM_CASE(3) GRAM_CASE(4) GRAM_CASE(5)

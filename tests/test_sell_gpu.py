@@ -74,7 +74,7 @@ SELL_OPS = [("laplace3d_7pt", (40,)), ("laplace2d_5pt", (300,)), ("laplace3d_7pt
 
 @pytest.mark.parametrize("chunk,stream,rows,tma", [(0, 0, 0, 0), (1, 0, 0, 3), (4, 0, 0, 6), (2, -1, 0, -1), (4, 2, 2, -1),
                                                    (3, 3, 2, -1), (1, 2, 1, -1),
-                                                   (0, 0, 0, 16), (2, 0, 0, 17)])  # explicit tiles: 16 entries per round trip
+                                                   (0, 0, 0, 8), (2, 0, 0, 17)])  # explicit tiles: 8 entries per round trip / 16 with 3 CTAs
 @pytest.mark.parametrize("gen,args", SELL_OPS)
 def test_sell_spmv_and_mpk_bitwise(sell, oracle_lib, gen, args, chunk, stream, rows, tma):
     """Stencils (pattern tiles, no per-entry index), an RCM-ordered tetrahedral P1 Laplacian, a 4-dof-per-node FEM operator

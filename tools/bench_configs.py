@@ -76,6 +76,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--only", default="")
+    ap.add_argument("--c1", type=int, default=0, help="cells per edge of the C1 FEM-like operator (default 50 -> 530 k rows)")
     args = ap.parse_args()
     only = set(args.only.split(",")) if args.only else None
     ctx = nsk.Context(0)
@@ -89,7 +90,7 @@ def main():
 
     if not only or "c1" in only:
         t0 = time.time()
-        A = matgen.fem_baij4(24 if args.quick else 50)  # 51^3 nodes x 4 dof = 530 k rows, ~55 nnz/row (350 MB of CSR)
+        A = matgen.fem_baij4(args.c1 if args.c1 > 0 else (24 if args.quick else 50))  # 51^3 nodes x 4 dof = 530 k rows, ~55 nnz/row (350 MB of CSR)
         print(f"# C1 assembled in {time.time()-t0:.1f}s", flush=True)
         dA = spmv_and_mpk(ctx, "C1 FEM BAIJ-4", A, (2,), reps)
         try:
@@ -98,10 +99,10 @@ def main():
             xb = ctx.to_device(matgen.vec_uniform(A.n, 1))
             yb = ctx.empty(A.n)
             nblk = len(B.indcol)
-            for batch in (1, 2, 4):
+            for batch in (1, 2, 4, 8):
                 ctx.set_option("bcsr_batch", batch)
                 ms = timed(ctx, lambda: dB.spmv(xb, yb), reps)
-                report(f"C1 FEM BAIJ-4 SpMV 4x4 block CSR, {batch} block(s) of loads in flight", ms,
+                report(f"C1 FEM BAIJ-4 SpMV 4x4 block CSR, {batch if batch < 8 else '4 (256-bit loads)'} block(s) of loads in flight", ms,
                        128 * nblk + 4 * nblk + 4 * (A.n // 4 + 1) + 16 * A.n)
             ctx.set_option("bcsr_batch", 0)
         except Exception as e:  # generator helper may be absent

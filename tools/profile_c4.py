@@ -23,9 +23,11 @@ from bench_c4 import tetgen, timed  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--m", type=int, default=200)
 ap.add_argument("--k", type=int, default=4)
-ap.add_argument("--variants", default="0,16,17")
+ap.add_argument("--variants", default="0,8,17", help="sell_tma values: 0 = default (16 entries per trip, 2 CTAs/SM), 8, 17")
 ap.add_argument("--ctas", default="0", help="comma list of sell_ctas_per_sm values (0 = occupancy)")
 ap.add_argument("--chunks", default="0", help="comma list of sell_chunk values (0 = default)")
+ap.add_argument("--l2", default="0", help="comma list of wave_l2_pct values (0 = default 88)")
+ap.add_argument("--flags", default="-1", help="comma list of sell_flags values (-1 = default 3)")
 ap.add_argument("--timing", action="store_true")
 ap.add_argument("--ncu", action="store_true")
 ap.add_argument("--reps", type=int, default=4)
@@ -48,10 +50,14 @@ if not args.ncu:
 ctx.set_option("mpk_kernel", 5)
 for v in [int(x) for x in args.variants.split(",")]:
     for c in [int(x) for x in args.ctas.split(",")]:
-        for ch in [int(x) for x in args.chunks.split(",")]:
+      for ch in [int(x) for x in args.chunks.split(",")]:
+       for l2 in [int(x) for x in args.l2.split(",")]:
+        for fl in [int(x) for x in args.flags.split(",")]:
             ctx.set_option("sell_tma", v)
             ctx.set_option("sell_ctas_per_sm", c)
             ctx.set_option("sell_chunk", ch)
+            ctx.set_option("wave_l2_pct", l2)
+            ctx.set_option("sell_flags", fl)
             for l in lv:
                 ctx.lib.nsk_memset0(ctx.h, l.ptr, 8 * n)
             l0 = ctx.launch_count
@@ -63,7 +69,7 @@ for v in [int(x) for x in args.variants.split(",")]:
                 print(f"variant sell_tma={v} ctas={c} chunk={ch}: launches={launches} bitwise={same}", flush=True)
                 continue
             ms = timed(ctx, lambda: dA.mpk(k, dx, lv), args.reps)
-            print(json.dumps({"sell_tma": v, "ctas_per_sm": c, "chunk": ch, "k": k, "ms": round(ms, 4), "rows_per_us": round(n * k / ms / 1e3, 1),
+            print(json.dumps({"sell_tma": v, "ctas_per_sm": c, "chunk": ch, "l2_pct": l2, "flags": fl, "k": k, "ms": round(ms, 4), "rows_per_us": round(n * k / ms / 1e3, 1),
                               "vs_products": round(ms1 / ms, 3), "launches": launches, "strategy": ctx.query("last_mpk_strategy"),
                               "grid": ctx.query("sell_grid"), "reach": ctx.query("sell_reach"), "lead": ctx.query("sell_lead"),
                               "bitwise": bool(same)}), flush=True)
