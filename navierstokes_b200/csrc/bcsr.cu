@@ -21,18 +21,10 @@ __device__ __forceinline__ double2 ld_stream(const double2 *p)
     return v;
 }
 
-// One 256-bit load (sm_100: LDG.E.256) of the thread's whole block row: the four threads of a block row then read one
-// 128-byte line with four fully used 32-byte sectors, instead of touching every sector twice with 16-byte halves.
-__device__ __forceinline__ void ld_stream32(const double *p, double2 &lo, double2 &hi)
-{
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0, %1, %2, %3}, [%4];"
-                 : "=d"(lo.x), "=d"(lo.y), "=d"(hi.x), "=d"(hi.y) : "l"(p));
-}
-
 // Loads of BATCH consecutive blocks (block column, two 16-byte halves of the thread's block row, the 32-byte x sector)
 // are all issued before the first dependent fma, so one thread keeps 4 x BATCH 16-byte loads in flight instead of 4: the
 // chain itself stays strictly in (block, j) order.
-template <bool MULADD, int BATCH, bool WIDE = false>
+template <bool MULADD, int BATCH>
 __global__ void __launch_bounds__(256) spmv_bcsr4_kernel(int nbrows, const int *__restrict__ ptrow,
                                                          const int *__restrict__ indcol,
                                                          const double *__restrict__ coef,
@@ -52,12 +44,8 @@ __global__ void __launch_bounds__(256) spmv_bcsr4_kernel(int nbrows, const int *
 #pragma unroll
         for (int u = 0; u < BATCH; u++) {
             const double2 *blk = reinterpret_cast<const double2 *>(coef + 16 * (size_t)(ia + u) + 4 * i);
-            if (WIDE) {
-                ld_stream32(reinterpret_cast<const double *>(blk), a01[u], a23[u]);
-            } else {
-                a01[u] = ld_stream(blk);
-                a23[u] = ld_stream(blk + 1);
-            }
+            a01[u] = ld_stream(blk);
+            a23[u] = ld_stream(blk + 1);
         }
 #pragma unroll
         for (int u = 0; u < BATCH; u++) {
@@ -154,15 +142,14 @@ NSK_API int nsk_spmv_bcsr4(nsk_bcsr4_t B, const double *x, double *y, nsk_mode m
     const int rows = 4 * B->nbrows;
     if (rows > 0) {
         const int blocks = (rows + 255) / 256;
-        const int batch = ctx->opt.bcsr_batch > 0 ? (int)ctx->opt.bcsr_batch : 4;
+        // blocks whose loads are issued together: 2 by default (530 k rows: 0.0472 ms with 2 or 4, 0.0503 with 1; 1.56 M rows:
+        // 0.1209 / 0.1225 / 0.1270 ms = 0.986 / 0.973 / 0.939 of the copy peak; one 256-bit load per block row instead of
+        // two 128-bit halves was slower: 0.0513 / 0.1312 ms -- profiles/r02_final_configs_c1.txt)
+        const int batch = ctx->opt.bcsr_batch > 0 ? (int)ctx->opt.bcsr_batch : 2;
 #define NSK_BCSR_LAUNCH(MA, BT) \
     spmv_bcsr4_kernel<MA, BT><<<blocks, 256, 0, ctx->stream>>>(B->nbrows, B->d_ptrow, B->d_indcol, B->d_coef, dx, dy)
         const bool ma = mode == NSK_EXACT_MULADD;
-        if (batch >= 8) {  // 256-bit block-row loads, four blocks in flight
-            if (ma) spmv_bcsr4_kernel<true, 4, true><<<blocks, 256, 0, ctx->stream>>>(B->nbrows, B->d_ptrow, B->d_indcol, B->d_coef, dx, dy);
-            else spmv_bcsr4_kernel<false, 4, true><<<blocks, 256, 0, ctx->stream>>>(B->nbrows, B->d_ptrow, B->d_indcol, B->d_coef, dx, dy);
-        }
-        else if (batch >= 4) { if (ma) NSK_BCSR_LAUNCH(true, 4); else NSK_BCSR_LAUNCH(false, 4); }
+        if (batch >= 4) { if (ma) NSK_BCSR_LAUNCH(true, 4); else NSK_BCSR_LAUNCH(false, 4); }
         else if (batch >= 2) { if (ma) NSK_BCSR_LAUNCH(true, 2); else NSK_BCSR_LAUNCH(false, 2); }
         else { if (ma) NSK_BCSR_LAUNCH(true, 1); else NSK_BCSR_LAUNCH(false, 1); }
 #undef NSK_BCSR_LAUNCH

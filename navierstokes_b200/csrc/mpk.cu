@@ -15,6 +15,8 @@
 //   with whole tiles (coefficients, local columns, x runs) staged in shared memory.
 // (Strategies 2 and 3 of round 1 -- the skewed wavefront and the level pipeline over plain CSR with global gathers --
 // lost to k launches wherever they were measured and are gone.)
+#include <algorithm>
+
 #include "nsk_internal.h"
 
 int nsk_dist_mpk(nsk_csr_t A, int k, const double *d_x, double *const *d_levels, nsk_mode mode);  // dist.cu
@@ -48,14 +50,17 @@ int nsk_mpk_local(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
     const bool automatic = sel == 0;
     // default: the sliced-ELL level pipeline for operators made of pattern tiles (stencils, regular bands: staged
     // coefficients, no per-entry index), else the packed one when the operator packs, else k products
+    bool explicit_auto = false;
     if (automatic) {
         sel = 4;
-        if (k > 1 && (nsk_sell_uniform(A) || (ctx->opt.mpk_auto_explicit > 0 && nsk_sell_explicit_staged(A)))) sel = 5;
-        // Unstructured operators (explicit columns, x gathered entry by entry) stay with k products: measured on the
-        // RCM-ordered tetrahedral P1 Laplacian (8.1 M rows, 15 per row), the product already runs at the HBM copy rate
-        // (0.237 ms, 6.8 TB/s) and both it and the fused sliced-ELL pipeline (mpk_kernel = 5: 2.43 ms for k = 8 against
-        // 1.90 ms for 8 products) sit on the same bound -- the L1 wavefronts of the uncoalesced x gathers, ~12 per
-        // warp-load -- which re-reading the operator from L2 instead of HBM does not move (profiles/r02_configs.txt).
+        if (k > 1 && nsk_sell_uniform(A)) sel = 5;
+        // Unstructured operators (explicit-column tiles whose columns fit a stage: ~15-23 entries per row): fused when at
+        // least min(k, 4) levels fit one launch's L2 window.  Measured on the RCM-ordered tetrahedral P1 Laplacian, k = 8
+        // (profiles/r02_c4_variants.txt, r02_configs.txt): 1.03 M rows 0.260 ms fused vs 0.296 ms as 8 products (1.14x),
+        // 8.1 M rows 1.70 vs 1.89 ms (1.12x, two launches of four levels), 49.8 M rows 11.6 vs 11.8 ms (three levels per
+        // launch at most: no gain, so k products).  The product itself runs at the HBM copy rate there; the fused kernel
+        // is bound by the latency of the uncoalesced x gathers, not by HBM.
+        else if (k > 1 && ctx->opt.mpk_auto_explicit >= 0 && nsk_sell_explicit_staged(A)) { sel = 5; explicit_auto = true; }
     }
     const bool sell = sel == 5 && k > 1 && nsk_sell_applicable(A);
     if (sel == 5 && !sell) sel = 4;
@@ -68,11 +73,16 @@ int nsk_mpk_local(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
         while (done < k) {
             const int left = k - done;
             int took = 0;
-            for (int kk = left; kk >= 2 && !took; kk--) {
+            const int lo = (explicit_auto && done == 0) ? std::min(k, 4) : 2;
+            for (int kk = left; kk >= lo && !took; kk--) {
                 int s = sell ? nsk_sell_run(A, kk, src, d_levels + done, mode, level_rows ? level_rows + done : nullptr, nullptr, -1)
                              : nsk_packed_run(A, kk, src, d_levels + done, mode, level_rows ? level_rows + done : nullptr, nullptr, -1);
                 if (s == NSK_OK) took = kk;
                 else if (s != NSK_ERR_UNSUPPORTED) return s;
+            }
+            if (!took && explicit_auto && done == 0) {  // too few levels per launch to pay: k products
+                ctx->last_mpk = 1;
+                return nsk_mpk_levels(A, k, d_x, d_levels, mode, level_rows);
             }
             if (!took) {  // a single level (or nothing fits): one product
                 nsk_spmv_args a;

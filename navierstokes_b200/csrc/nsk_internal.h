@@ -60,12 +60,12 @@ struct nsk_options {
     int64_t wave_slack_pct = -1;  // extra level skew, % of (resident CTAs x stages / k) tiles; <0 = default 150
     int64_t wave_l2_pct = 0;      // share of L2 the wavefront window may occupy, %; 0 = default 80
     int64_t scg_update_wide = 0;  // < 0: s-step block update through the scalar kernel (comparison)
-    int64_t mpk_auto_explicit = 0; // 1: automatic strategy also fuses operators stored as explicit-column tiles (unstructured FEM)
+    int64_t mpk_auto_explicit = 0; // < 0: the automatic strategy never fuses operators stored as explicit-column tiles (unstructured FEM)
     int64_t gram_wide = 0;        // < 0: s-step Gram blocks always through the one-element-per-thread kernel (comparison)
     int64_t local_reductions = 0; // 1: nsk_dot / norm2 / rel_error / orthogonalize / gram do not all-reduce over the communicator
     int64_t halo_push = 1;        // distributed operators: registered vectors exchange their halo by pushing over NVLink
                                   // peer memory (0: always NCCL)
-    int64_t bcsr_batch = 0;       // block product: blocks whose loads are issued together per thread (0 = default 4; 1, 2, 4)
+    int64_t bcsr_batch = 0;       // block product: blocks whose loads are issued together per thread (0 = default 2; 1, 2, 4)
     // sliced-ELL kernel (sell.cu)
     int64_t sell_chunk = 0;       // consecutive tiles a CTA takes per item; 0 = default (2 fused, 4 single product)
     int64_t sell_geom = 0;        // 2 = operators stored with one global pattern still take the masked consumer path (A/B)

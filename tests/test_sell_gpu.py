@@ -252,3 +252,37 @@ def test_sell_long_streams_per_cta(sell, oracle_lib, gen, args, geom, tma):
                     assert_bits_equal(np.stack([l.to_host() for l in lv]), ref, f"{gen}{args} k={k} cap={cap} rep={rep}")
     finally:
         ctx.set_option("sell_max_ctas", 0)
+
+
+def test_auto_strategy_fuses_unstructured_when_the_window_fits(ctx, oracle_lib):
+    """Default options: an operator stored as explicit-column tiles (RCM-ordered tet P1 Laplacian) runs k >= 2 powers as ONE
+    fused launch when min(k, 4) levels fit the L2 window, as k products otherwise (tiny L2 budget) or when the option
+    mpk_auto_explicit is negative -- the same bits every way."""
+    A = matgen.tet_p1_laplacian(24, 2, True)
+    x = matgen.vec_uniform(A.n, seed=5)
+    dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
+    dx = ctx.to_device(x)
+    try:
+        for k in (2, 4, 6):
+            ref = oracle_lib.mpk(A.ptrow, A.indcol, A.coef, k, x)
+            lv = [ctx.zeros(A.n) for _ in range(k)]
+            before = ctx.launch_count
+            dA.mpk(k, dx, lv)
+            assert ctx.query("last_mpk_strategy") == 5 and ctx.launch_count - before == 1, f"k={k}: one fused launch expected"
+            assert_bits_equal(np.stack([l.to_host() for l in lv]), ref, f"auto fused k={k}")
+            ctx.set_option("mpk_auto_explicit", -1)
+            before = ctx.launch_count
+            dA.mpk(k, dx, lv)
+            assert ctx.query("last_mpk_strategy") == 1 and ctx.launch_count - before == k
+            assert_bits_equal(np.stack([l.to_host() for l in lv]), ref, f"auto off k={k}")
+            ctx.set_option("mpk_auto_explicit", 0)
+        ctx.set_option("wave_l2_pct", 1)  # no window fits 1 % of L2: products
+        k = 4
+        ref = oracle_lib.mpk(A.ptrow, A.indcol, A.coef, k, x)
+        lv = [ctx.zeros(A.n) for _ in range(k)]
+        dA.mpk(k, dx, lv)
+        assert ctx.query("last_mpk_strategy") == 1
+        assert_bits_equal(np.stack([l.to_host() for l in lv]), ref, "window rejected")
+    finally:
+        ctx.set_option("mpk_auto_explicit", 0)
+        ctx.set_option("wave_l2_pct", 0)
