@@ -142,6 +142,16 @@ def main():
     if rank == 0:
         print(f"unstructured operator (tet P1, n={T.n}) over {world} ranks: peers of rank 0 = {top.ctx.lib.nsk_dist_peer_count(top.h)}", flush=True)
 
+    # ---- reductions: collective by default once a communicator is attached, rank-local on request -------------------
+    xo = np.ascontiguousarray(x[lo:hi])
+    glob = ctx.dot(xo, xo)                      # every rank calls: the sum over all ranks
+    bad += not (abs(glob - float(x @ x)) <= 1e-9 * float(x @ x))
+    ctx.set_option("local_reductions", 1)
+    if rank == world - 1:                       # ONE rank alone: must not enter a collective
+        loc = ctx.dot(xo, xo)
+        bad += not (abs(loc - float(xo @ xo)) <= 1e-9 * float(xo @ xo))
+    ctx.set_option("local_reductions", 0)
+
     t = torch.tensor([bad], device=f"cuda:{local}")
     dist.all_reduce(t)
     if rank == 0:
