@@ -60,7 +60,14 @@ int nsk_mpk_local(nsk_csr_t A, int k, const double *d_x, double *const *d_levels
         // 8.1 M rows 1.70 vs 1.89 ms (1.12x, two launches of four levels), 49.8 M rows 11.6 vs 11.8 ms (three levels per
         // launch at most: no gain, so k products).  The product itself runs at the HBM copy rate there; the fused kernel
         // is bound by the latency of the uncoalesced x gathers, not by HBM.
-        else if (k > 1 && ctx->opt.mpk_auto_explicit >= 0 && nsk_sell_explicit_staged(A)) { sel = 5; explicit_auto = true; }
+        // Small operators stay with products too (fill and drain of the level pipeline: a 0.59 M-row slab of a 2-GPU split
+        // runs k = 8 in 0.204 ms fused against 0.187 ms as products, profiles/r02_dist_c4_2gpu.txt): threshold 1 M rows,
+        // option mpk_auto_explicit = rows (> 0) moves it, < 0 switches the rule off.
+        else if (k > 1 && ctx->opt.mpk_auto_explicit >= 0 &&
+                 A->n >= (ctx->opt.mpk_auto_explicit > 0 ? ctx->opt.mpk_auto_explicit : 1000000) && nsk_sell_explicit_staged(A)) {
+            sel = 5;
+            explicit_auto = true;
+        }
     }
     const bool sell = sel == 5 && k > 1 && nsk_sell_applicable(A);
     if (sel == 5 && !sell) sel = 4;

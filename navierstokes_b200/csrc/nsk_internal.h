@@ -60,7 +60,8 @@ struct nsk_options {
     int64_t wave_slack_pct = -1;  // extra level skew, % of (resident CTAs x stages / k) tiles; <0 = default 150
     int64_t wave_l2_pct = 0;      // share of L2 the wavefront window may occupy, %; 0 = default 80
     int64_t scg_update_wide = 0;  // < 0: s-step block update through the scalar kernel (comparison)
-    int64_t mpk_auto_explicit = 0; // < 0: the automatic strategy never fuses operators stored as explicit-column tiles (unstructured FEM)
+    int64_t mpk_auto_explicit = 0; // automatic strategy on operators stored as explicit-column tiles (unstructured FEM): fused from
+                                   // 1 M rows (0), from this many rows (> 0), never (< 0)
     int64_t gram_wide = 0;        // < 0: s-step Gram blocks always through the one-element-per-thread kernel (comparison)
     int64_t local_reductions = 0; // 1: nsk_dot / norm2 / rel_error / orthogonalize / gram do not all-reduce over the communicator
     int64_t halo_push = 1;        // distributed operators: registered vectors exchange their halo by pushing over NVLink

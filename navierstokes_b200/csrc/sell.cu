@@ -36,6 +36,7 @@
 #include <cstring>
 #include <functional>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <thread>
 
@@ -1430,10 +1431,20 @@ static SlLaunch sl_lookup_tma(int nv, int w, int ns, int *smem)
 // -----------------------------------------------------------------------------------------------
 // host side: tiling + pattern detection + blobs
 // -----------------------------------------------------------------------------------------------
+// Uninitialised byte buffer (std::vector would zero a gigabyte on one thread before the threaded packer overwrites it).
+struct SlRawBuf {
+    std::unique_ptr<unsigned char[]> p;
+    size_t n = 0;
+    void alloc(size_t bytes) { p.reset(new unsigned char[bytes]); n = bytes; }
+    unsigned char *data() { return p.get(); }
+    const unsigned char *data() const { return p.get(); }
+    size_t size() const { return n; }
+};
+
 struct SellHost {
     std::vector<nsk_tile> tiles;   // {row0, nrows, nz0, nz1}: input of nsk_wave_deps
     std::vector<SlTile> stiles;
-    std::vector<unsigned char> blobs;
+    SlRawBuf blobs;                // every tile's bytes are zeroed by the thread that fills the tile
     size_t blob_bytes = 0;
     int n_pattern = 0;
     int uniform_width = 0;  // > 0: every tile is a pattern tile stored with this many slots
@@ -1635,12 +1646,14 @@ static std::string sl_pack_host(int n, int n_cols, int64_t nnz, const int *ptrow
     if ((double)total > 1.5 * (12.0 * (double)nnz + 4.0 * n) + 65536.0) return "row lengths too ragged for sliced-ELL tiles";
     out.blob_bytes = total;
     out.n_pattern = n_pattern;
-    out.blobs.assign(total + 128, 0);
+    out.blobs.alloc(total + 128);
+    memset(out.blobs.data() + total, 0, 128);
     // 2. the blobs
     sl_parallel(ntiles, [&](int t) {
         const nsk_tile &tl = tiles[t];
         const SlTile &d = st[t];
         unsigned char *b = out.blobs.data() + d.off;
+        memset(b, 0, (size_t)d.bytes);  // padding slots / rows read as zeros
         if (d.fmt == SL_FMT_PATTERN) {
             unsigned char *mask = b;
             double *val = reinterpret_cast<double *>(b + SL_ROWS);
@@ -2101,15 +2114,18 @@ static SellOp *sl_get(nsk_csr_t A)
     if (n == 0 || A->nnz == 0) { op->why = "empty operator"; return op; }
     if ((int)ptrow.size() != n + 1) { op->why = "host row pointers missing"; return op; }
     // the caller's host arrays are gone: read the entries back once and pack on the host
-    std::vector<int> indcol((size_t)A->nnz);
-    std::vector<double> coef((size_t)A->nnz);
-    if (cudaMemcpy(indcol.data(), A->d_indcol, sizeof(int) * (size_t)A->nnz, cudaMemcpyDeviceToHost) != cudaSuccess ||
-        cudaMemcpy(coef.data(), A->d_coef, sizeof(double) * (size_t)A->nnz, cudaMemcpyDeviceToHost) != cudaSuccess) {
+    // (uninitialised buffers: a std::vector would zero 1.4 GB for a 256^3 operator before the copy overwrites it)
+    std::unique_ptr<int[]> indcol(new int[(size_t)A->nnz]);
+    std::unique_ptr<double[]> coef(new double[(size_t)A->nnz]);
+    if (cudaMemcpy(indcol.get(), A->d_indcol, sizeof(int) * (size_t)A->nnz, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(coef.get(), A->d_coef, sizeof(double) * (size_t)A->nnz, cudaMemcpyDeviceToHost) != cudaSuccess) {
         op->why = "reading the operator back failed";
         return op;
     }
     SellHost H;
-    op->why = sl_pack_host(n, A->n_cols, A->nnz, ptrow.data(), indcol.data(), coef.data(), A->breaks, H);
+    op->why = sl_pack_host(n, A->n_cols, A->nnz, ptrow.data(), indcol.get(), coef.get(), A->breaks, H);
+    indcol.reset();
+    coef.reset();
     if (!op->why.empty()) return op;
     const int ntiles = (int)H.tiles.size();
     if (cudaMalloc(&op->d_blobs, H.blobs.size()) != cudaSuccess ||

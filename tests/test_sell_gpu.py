@@ -263,7 +263,11 @@ def test_auto_strategy_fuses_unstructured_when_the_window_fits(ctx, oracle_lib):
     dA = nsk.CsrMatrix(ctx, A.ptrow, A.indcol, A.coef)
     dx = ctx.to_device(x)
     try:
+        lv = [ctx.zeros(A.n) for _ in range(2)]
+        dA.mpk(2, dx, lv)
+        assert ctx.query("last_mpk_strategy") == 1, "below the default size threshold (1 M rows): products"
         for k in (2, 4, 6):
+            ctx.set_option("mpk_auto_explicit", 1)  # threshold: 1 row
             ref = oracle_lib.mpk(A.ptrow, A.indcol, A.coef, k, x)
             lv = [ctx.zeros(A.n) for _ in range(k)]
             before = ctx.launch_count
@@ -275,7 +279,7 @@ def test_auto_strategy_fuses_unstructured_when_the_window_fits(ctx, oracle_lib):
             dA.mpk(k, dx, lv)
             assert ctx.query("last_mpk_strategy") == 1 and ctx.launch_count - before == k
             assert_bits_equal(np.stack([l.to_host() for l in lv]), ref, f"auto off k={k}")
-            ctx.set_option("mpk_auto_explicit", 0)
+        ctx.set_option("mpk_auto_explicit", 1)
         ctx.set_option("wave_l2_pct", 1)  # no window fits 1 % of L2: products
         k = 4
         ref = oracle_lib.mpk(A.ptrow, A.indcol, A.coef, k, x)

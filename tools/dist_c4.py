@@ -2,7 +2,7 @@
 (GlobalCsrProvider), ONE halo exchange per matrix-powers call, ghost levels recomputed on shrinking prefixes.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 \
-        tools/dist_c4.py [--m 200] [--k 8]
+        tools/dist_c4.py [--mesh 200] [--k 8]
 
 Every rank generates the same global operator on the host (fast generator + nsk_rcm), builds its slab, runs k products and the
 automatic strategy, and compares its owned rows of ALL k levels bit for bit with the CPU oracle (k x SpMV_CSR_FMA restated) on
@@ -24,7 +24,7 @@ sys.path.insert(0, str(ROOT / "tools"))
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--m", type=int, default=200)
+    ap.add_argument("--mesh", type=int, default=200, dest="m")
     ap.add_argument("--k", type=int, default=8)
     ap.add_argument("--reps", type=int, default=5)
     args = ap.parse_args()
