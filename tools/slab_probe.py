@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--strong", action="store_true", help="split grid^3 over the ranks instead of grid^3 per rank")
     ap.add_argument("--sweep", action="store_true")
     ap.add_argument("--once", action="store_true", help="3 warm-up calls + ONE call (for ncu)")
+    ap.add_argument("--timing", action="store_true", help="one call with the dependency-warp wait instrumentation (pk_timing)")
     ap.add_argument("--set", action="append", default=[], help="option=value, applied before the first call")
     args = ap.parse_args()
     import navierstokes_b200 as nsk
@@ -79,6 +80,11 @@ def main():
         return
     print(f"k={K} default: {timed():.1f} us  strategy {ctx.query('last_mpk_strategy')}  plan "
           + str({q: ctx.query(q) for q in ('sell_reach', 'sell_lead', 'sell_grid', 'sell_ntiles', 'sell_ngroups')}), flush=True)
+    if args.timing:
+        ctx.set_option("pk_timing", 1)
+        call()
+        ctx.sync()
+        ctx.set_option("pk_timing", 0)
     if args.sweep:
         for name, vals in (("wave_l2_pct", (80, 88, 92, 96, 100, 105)), ("sell_chunk", (2, 3, 4)), ("pipe_w0_pct", (90, 110, 125)),
                            ("sell_pf_dist", (1, 3, 4)), ("pipe_interleave", (0,))):
