@@ -105,7 +105,9 @@ int nsk_ctx_device_info(nsk_ctx_t ctx, int *sm_count, int64_t *l2_bytes, int *sm
  *                    format for other operators that pack, else k launches) | 1 k launches | 4 level pipeline
  *                    (packed) | 5 level pipeline (sliced-ELL tiles: any operator whose rows are not too ragged)
  *   sell_tma         all-pattern operators: coefficient stages per CTA of the staged kernel (0 = default 3: four CTAs per
- *                    SM; 4: three CTAs; < 0 = the register kernels) | sell_chunk tiles per item (0 = default) |
+ *                    SM; 4: three CTAs; < 0 = the register kernels); explicit-column operators: entries of a row loaded
+ *                    per round trip (0 = default 16 with two CTAs per SM; 8: 8 with three CTAs; 17: 16 with three CTAs)
+ *                    | sell_chunk tiles per item (0 = default) |
  *                    sell_stream, sell_rows (register kernels) | sell_ctas_per_sm | sell_flags | sell_pf_dist
  *   packed_variant, stream_variant   0 default, n = table entry n-1 of that kernel
  *   wave_l2_pct      share of L2 the fused kernels' window may occupy (0 = default: 88 sliced-ELL, 70 packed)
@@ -114,7 +116,14 @@ int nsk_ctx_device_info(nsk_ctx_t ctx, int *sm_count, int64_t *l2_bytes, int *sm
  *                    experiment switches documented next to nsk_options in csrc/nsk_internal.h
  *   pk_flags         bit 0 (default on) cache hints for data nobody re-reads | bit 1 poll without sleeping | bit 2
  *                    publish with red.release
- *   pk_timing        1: the packed kernel prints its stage-cycle breakdown to stderr (debugging aid) */
+ *   pk_timing        1: the fused kernels print their stage-cycle / dependency-wait breakdown to stderr (debugging aid)
+ *   mpk_auto_explicit  automatic strategy on unstructured operators (explicit-column tiles): fused from 1 M rows when
+ *                    min(k, 4) levels fit one launch (0 = default), from `value` rows (> 0), never (< 0)
+ *   local_reductions 1: nsk_dot / nsk_norm2 / nsk_rel_error / nsk_orthogonalize / nsk_gram return rank-local results although
+ *                    a communicator is attached (no collective)
+ *   bcsr_batch       block product: blocks whose loads are issued together (0 = default 2; 1, 2, 4)
+ *   gram_wide, scg_update_wide   < 0: the one-element-per-thread forms of the s-step Gram pass / block update (comparison)
+ *   halo_push        0: distributed operators always exchange halos through NCCL (default 1: registered vectors push) */
 int nsk_ctx_set_option(nsk_ctx_t ctx, const char *name, int64_t value);
 
 /* CUDA-event timing on the context's stream (what bench.py brackets its timed regions with). */
