@@ -23,7 +23,13 @@ from navierstokes_b200 import _lib, matgen  # noqa: E402
 
 
 def tetgen(m, perm_seed, threads):
-    lib = C.CDLL(str(ROOT / "tools" / "bin" / "libtetgen.so"))
+    so = ROOT / "tools" / "bin" / "libtetgen.so"
+    src = ROOT / "tools" / "gen" / "tetgen.cpp"
+    if not so.exists() or so.stat().st_mtime < src.stat().st_mtime:  # built artefact (git-ignored): compile on first use
+        import subprocess
+        so.parent.mkdir(exist_ok=True)
+        subprocess.run(["g++", "-O3", "-std=c++17", "-shared", "-fPIC", "-pthread", "-o", str(so), str(src)], check=True)
+    lib = C.CDLL(str(so))
     lib.tetgen_rows.restype = C.c_int64
     lib.tetgen_rows.argtypes = [C.c_int, C.c_double, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     n = (m + 1) ** 3
