@@ -6,6 +6,8 @@
 #include <map>
 #include <mutex>
 
+#include <thread>
+
 #include "nsk_internal.h"
 #include "wave_common.h"
 
@@ -32,25 +34,39 @@ void nsk_wave_set_block_extents(nsk_csr_t A, const int *ptrow, const int *indcol
     S.blk_row0.clear(); S.blk_min.clear(); S.blk_max.clear();
     const int n = A->n;
     const bool ranked = !A->row_rank.empty();
+    // blocks of 32 rows (cut at the breaks of a distributed slab), then their column extents -- the second pass threaded
     size_t bi = 0;
     int r = 0;
     while (r < n) {
         while (bi < A->breaks.size() && A->breaks[bi] <= r) bi++;
         const int seg_end = bi < A->breaks.size() ? std::min(n, A->breaks[bi]) : n;
-        const int r1 = std::min(seg_end, r + 32);
-        int mn = INT32_MAX, mx = -1;
-        for (int j = ptrow[r]; j < ptrow[r1]; j++) {
-            int c = indcol[j];
-            if (c >= n) continue;
-            if (ranked) c = A->row_rank[c];
-            mn = c < mn ? c : mn;
-            mx = c > mx ? c : mx;
-        }
         S.blk_row0.push_back(r);
-        S.blk_min.push_back(mn);
-        S.blk_max.push_back(mx);
-        r = r1;
+        r = std::min(seg_end, r + 32);
     }
+    const int nblk = (int)S.blk_row0.size();
+    S.blk_min.assign((size_t)nblk, INT32_MAX);
+    S.blk_max.assign((size_t)nblk, -1);
+    const int nth = nblk > (1 << 15) ? (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency())) : 1;
+    auto work = [&](int t) {
+        const int b0 = (int)((int64_t)nblk * t / nth), b1 = (int)((int64_t)nblk * (t + 1) / nth);
+        for (int b = b0; b < b1; b++) {
+            const int ra = S.blk_row0[(size_t)b], rb = b + 1 < nblk ? S.blk_row0[(size_t)b + 1] : n;
+            int mn = INT32_MAX, mx = -1;
+            for (int j = ptrow[ra]; j < ptrow[rb]; j++) {
+                int c = indcol[j];
+                if (c >= n) continue;
+                if (ranked) c = A->row_rank[c];
+                mn = c < mn ? c : mn;
+                mx = c > mx ? c : mx;
+            }
+            S.blk_min[(size_t)b] = mn;
+            S.blk_max[(size_t)b] = mx;
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nth; t++) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
 }
 
 void nsk_wave_free(nsk_csr_t A)
