@@ -110,7 +110,7 @@ int nsk_ctx_device_info(nsk_ctx_t ctx, int *sm_count, int64_t *l2_bytes, int *sm
  *                    | sell_chunk tiles per item (0 = default) |
  *                    sell_stream, sell_rows (register kernels) | sell_ctas_per_sm | sell_flags | sell_pf_dist
  *   packed_variant, stream_variant   0 default, n = table entry n-1 of that kernel
- *   wave_l2_pct      share of L2 the fused kernels' window may occupy (0 = default: 88 sliced-ELL, 70 packed)
+ *   wave_l2_pct      share of L2 the fused kernels' window may occupy (0 = default: 92 sliced-ELL pattern operators, 88 otherwise, 70 packed)
  *   wave_slack_pct   explicit window slack (< 0 = size it from the L2 budget)
  *   pipe_bp_global, pipe_interleave, pipe_w0_pct, pk_flags, stream_exact_kind, spmv_ctas_per_sm
  *                    experiment switches documented next to nsk_options in csrc/nsk_internal.h

@@ -2198,8 +2198,12 @@ static SlPlan *sl_plan(nsk_csr_t A, SellOp *op, int k, const int *level_rows, in
         // stay L2-resident is (k-1) * lead tiles of blobs plus the level vectors over it; by default the slack is
         // whatever the L2 budget allows.
         const double tile_bytes = (double)op->blob_bytes / ntiles + 8.0 * SL_ROWS * (k + 1) * nv;
-        // budget: 88 % of L2 by default (256^3, k = 4: 0.583 ms at 80 %, 0.553 at 90 %, 0.560 at 100 %, 0.581 at 110 %)
-        const double budget = (l2_pct > 0 ? (double)l2_pct : 88.0) / 100.0 * (double)ctx->prop.l2CacheSize;
+        // budget: share of L2 the window may take.  Pattern operators, one right-hand side: 92 % (256^3, k = 4, final kernel:
+        // 0.5130 ms at 86 %, 0.5087 at 88, 0.5050 at 90, 0.5035 at 92, 0.5028 at 94 -- profiles/r02_sweep_final.txt; a slab
+        // with ghost rows: 535.8 us at 88, 535.6 at 92, 541.4 at 96, 549.7 at 100); two right-hand sides and explicit-column
+        // operators (whose gathers compete for L2): 88 %
+        const double l2_default = (op->uniform_width > 0 && nv == 1) ? 92.0 : 88.0;
+        const double budget = (l2_pct > 0 ? (double)l2_pct : l2_default) / 100.0 * (double)ctx->prop.l2CacheSize;
         const int lead_min = D.reach + 1 + WF_GROUP + chunk;
         if (lead_pct >= 0)
             p.lead = lead_min + (int)((double)lead_pct / 100.0 * 2.0 * (resident / k) * chunk + 0.999);
